@@ -1,0 +1,113 @@
+"""fp32 restatement of BLIP2_MR.forward_mr / prompt_concatenation / generate
+(lavis/models/blip2_mr_models/blip2_mr.py:433-570, 572-824, 826-988) composed around the pinned
+sub-module oracles.  blip2_mr.py itself cannot be imported here (peft / tokenizer files absent), so
+this file follows it line by line; default branch only: input_time_format='seconds_integers',
+interleave_data=True, task='qformer_freeze_lora' (every lavis/projects/mr_BLIP yaml).
+Test infrastructure only (see oracle/__init__.py)."""
+import torch
+
+from . import vit as _vit, qformer as _qf, t5 as _t5
+from .beam_search import beam_search
+
+
+def seconds_integers(timestamps, durations, table):
+    """utils.py:388-434."""
+    ts, ds = [], []
+    for t, dur in zip(timestamps, durations):
+        ts.append([int(table.get(round(x.item()), round(x.item()))) for x in t])
+        ds.append(table.get(round(dur.item()), round(dur.item())))
+    return ts, ds
+
+
+def frame_tokens(sd, d, video, frame_token_aggregation=None):
+    """blip2_mr.py:443-510: ViT -> ln_vision -> Q-Former -> t5_proj (-> mean) -> [b, t*n, c]."""
+    b, t = video.shape[:2]
+    image = video.reshape(-1, *video.shape[2:])
+    image_embeds = _vit.ln_vision(sd, d, _vit.vit_forward(sd, d, image))
+    q = _qf.qformer_forward(sd, d, image_embeds)
+    f = torch.nn.functional.linear(q, sd["t5_proj.weight"], sd["t5_proj.bias"])
+    if frame_token_aggregation:
+        f = f.mean(dim=1, keepdim=True)
+    return f.reshape(b, -1, f.shape[-1]), {"image_embeds": image_embeds, "qformer": q}
+
+
+def clean_timestamp_ids(tok, values):
+    """get_clean_timestamp_tokens_and_embs, blip2_mr.py:1561-1608: tokenize str(v) without specials,
+    drop a leading id 3."""
+    ids = tok([str(v) for v in values], add_special_tokens=False)["input_ids"]
+    return [i[1:] if i[0] == 3 else i for i in ids]
+
+
+def prompt_concatenation(sd, d, tok, timestamps, durations, frames_for_t5, video_prompt_end, query_prompt,
+                         task_prompt, n_per_frame, table=None, max_txt_len=200, prefix=_t5.PREFIX):
+    """blip2_mr.py:572-824, interleave branch:
+       [f_0 (n) | ts_0 | f_1 | ts_1 | ... | '>' | duration] (left-padded) ++ video_prompt_end ++ query+task."""
+    emb = sd[prefix + "shared.weight"]
+    ts, ds = seconds_integers(timestamps, durations, table or {})
+    end = tok(video_prompt_end, padding="longest", add_special_tokens=False, truncation=True,
+              max_length=max_txt_len, return_tensors="pt")
+    text = tok([q + t for q, t in zip(query_prompt, task_prompt)], padding="longest", truncation=True,
+               max_length=max_txt_len, return_tensors="pt")
+    sep = tok.convert_tokens_to_ids(">")
+    B, TN, C = frames_for_t5.shape
+    T = TN // n_per_frame
+    rows = []
+    for j in range(B):
+        ts_ids = clean_timestamp_ids(tok, ts[j])
+        dur_ids = clean_timestamp_ids(tok, [ds[j]])[0]
+        parts = []
+        for i in range(T):
+            parts.append(frames_for_t5[j, i * n_per_frame:(i + 1) * n_per_frame])
+            parts.append(emb[torch.tensor(ts_ids[i])])
+        parts.append(emb[torch.tensor([sep])])
+        parts.append(emb[torch.tensor(dur_ids)])
+        rows.append(torch.cat(parts))
+    L = max(len(r) for r in rows)
+    # reference pads with pad_token_id * ones (= zeros) on the LEFT and still marks them attended (:744-779)
+    rows = [torch.cat([torch.zeros(L - len(r), C), r]) if len(r) < L else r for r in rows]
+    inter = torch.stack(rows)
+    inputs = torch.cat([inter, emb[end.input_ids], emb[text.input_ids]], dim=1)
+    atts = torch.cat([torch.ones(B, L, dtype=torch.long), end.attention_mask, text.attention_mask], dim=1)
+    return inputs, atts
+
+
+def forward_mr(sd, d, tok, samples, frame_token_aggregation=None, table=None, max_txt_len=200):
+    """blip2_mr.py:433-570 -> dict(loss, logits, inputs_embeds, attention_mask, labels, ...)."""
+    f, aux = frame_tokens(sd, d, samples["video"], frame_token_aggregation)
+    n = 1 if frame_token_aggregation else d.num_query
+    inputs, atts = prompt_concatenation(sd, d, tok, samples["timestamps"], samples["duration"], f,
+                                        samples["video_prompt_end"], samples["query_prompt"],
+                                        samples["task_prompt"], n, table, max_txt_len)
+    ans = tok(samples["relevant_windows"], padding="longest", truncation=True, max_length=max_txt_len,
+              return_tensors="pt")
+    labels = ans.input_ids.masked_fill(ans.input_ids == tok.pad_token_id, -100)
+    out = _t5.t5_forward(sd, d, inputs, atts, labels, ans.attention_mask)
+    out.update(inputs_embeds=inputs, attention_mask=atts, labels=labels, frames_for_t5=f, **aux)
+    return out
+
+
+@torch.no_grad()
+def generate(sd, d, tok, samples, post_process, num_beams=5, max_length=50, min_length=1, length_penalty=1.0,
+             frame_token_aggregation=None, table=None):
+    """blip2_mr.py:826-946 (no-cache decoder re-run each step, as the reference effectively does)."""
+    f, _ = frame_tokens(sd, d, samples["video"], frame_token_aggregation)
+    n = 1 if frame_token_aggregation else d.num_query
+    inputs, atts = prompt_concatenation(sd, d, tok, samples["timestamps"], samples["duration"], f,
+                                        samples["video_prompt_end"], samples["query_prompt"],
+                                        samples["task_prompt"], n, table)
+    enc = _t5.t5_encoder(sd, d, inputs, atts)
+    B = inputs.shape[0]
+    enc_b = enc.repeat_interleave(num_beams, dim=0)
+    atts_b = atts.repeat_interleave(num_beams, dim=0)
+
+    def step(ids):
+        dec = _t5.t5_decoder(sd, d, ids, enc_b, atts_b)
+        return _t5.t5_logits(sd, d, dec[:, -1])
+
+    seqs = beam_search(step, B, num_beams, max_length, min_length, length_penalty,
+                       eos_id=tok.eos_token_id, pad_id=tok.pad_token_id)
+    raw = tok.batch_decode(seqs, skip_special_tokens=True)
+    dur = samples["duration"]
+    return {"prediction": [post_process(p) for p in raw], "raw_prediction": raw, "sequences": seqs,
+            "answer": samples["relevant_windows"], "qid": samples["query_id"],
+            "duration": dur.tolist() if torch.is_tensor(dur) else dur}

@@ -1,0 +1,126 @@
+"""The oracle (oracle/*.py, fp32 CPU restatement) against the golden vectors produced by the
+reference's own modules (tests/golden/make_golden.py).  CPU only."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from mr_blip_b200.dims import TINY, T5_PREFIX
+from mr_blip_b200.tokenizer import SyntheticT5Tokenizer
+from mr_blip_b200 import mr_utils
+from oracle import vit as ovit, qformer as oqf, t5 as ot5, blip2_mr as ob, synth
+from oracle.beam_search import beam_search
+
+TOL = dict(rtol=2e-4, atol=2e-4)   # fp32 vs fp32, different op order only
+
+
+def _np(x):
+    return x.detach().numpy()
+
+
+def test_vision_stack_matches_reference(tiny_sd, golden_dir):
+    gold = np.load(os.path.join(golden_dir, "vision_tiny.npz"))
+    d = TINY
+    frames = torch.randn(2, 3, d.img_size, d.img_size, generator=torch.Generator().manual_seed(7))
+    assert abs(frames.double().sum().item() - float(gold["frames_checksum"])) < 1e-6, "input RNG drifted"
+    with torch.no_grad():
+        v = ovit.vit_forward(tiny_sd, d, frames)
+        ie = ovit.ln_vision(tiny_sd, d, v)
+        q = oqf.qformer_forward(tiny_sd, d, ie)
+        p = torch.nn.functional.linear(q, tiny_sd["t5_proj.weight"], tiny_sd["t5_proj.bias"])
+    tk = gold["vit_tokens"].tolist()
+    np.testing.assert_allclose(_np(v[:, tk]), gold["vit_out"], **TOL)
+    np.testing.assert_allclose(_np(ie[:, tk]), gold["image_embeds"], **TOL)
+    np.testing.assert_allclose(_np(q), gold["qformer_out"], **TOL)
+    np.testing.assert_allclose(_np(p[:, :, ::8]), gold["t5_proj_out"], **TOL)
+
+
+def _t5_inputs(d):
+    g = torch.Generator().manual_seed(11)
+    emb = torch.randn(2, 72, d.d_model, generator=g) * 2.0
+    mask = torch.ones(2, 72, dtype=torch.long)
+    mask[1, 60:] = 0
+    labels = torch.randint(2, 1000, (2, 9), generator=g)
+    labels[:, -1] = 1
+    labels[1, 6:] = -100
+    labels[1, 5] = 1
+    return emb, mask, labels
+
+
+def test_t5_loss_logits_and_lora_grads_match_reference(tiny_sd, golden_dir):
+    gold = np.load(os.path.join(golden_dir, "t5_tiny.npz"))
+    d = TINY
+    emb, mask, labels = _t5_inputs(d)
+    assert abs(emb.double().sum().item() - float(gold["emb_checksum"])) < 1e-6
+    assert (labels.numpy() == gold["labels"]).all()
+    probes = [k[3:] for k in gold.files if k.startswith("gA.")]
+    sd = dict(tiny_sd)
+    leaves = {}
+    for name in probes:
+        for ab in ("lora_A", "lora_B"):
+            k = f"{T5_PREFIX}{name}.{ab}.default.weight"
+            leaves[k] = sd[k].clone().requires_grad_(True)
+            sd[k] = leaves[k]
+    emb.requires_grad_(True)
+    out = ot5.t5_forward(sd, d, emb, mask, labels, (labels != -100).long())
+    out["loss"].backward()
+    assert abs(out["loss"].item() - float(gold["loss"])) < 1e-4
+    np.testing.assert_allclose(_np(out["logits"][:, :, :256]), gold["logits_head"], **TOL)
+    np.testing.assert_allclose(_np(torch.logsumexp(out["logits"], -1)), gold["logits_lse"], **TOL)
+    np.testing.assert_allclose(_np(out["encoder_last_hidden_state"][:, ::8, ::4]), gold["enc_out"], rtol=1e-3, atol=1e-3)
+    np.testing.assert_allclose(_np(emb.grad[:, ::4, ::4]), gold["d_emb"], rtol=1e-3, atol=1e-6)
+    for name in probes:
+        gA = leaves[f"{T5_PREFIX}{name}.lora_A.default.weight"].grad
+        gB = leaves[f"{T5_PREFIX}{name}.lora_B.default.weight"].grad
+        if name == "lm_head":
+            gB = gB[::16]
+        np.testing.assert_allclose(_np(gA), gold["gA." + name], rtol=2e-3, atol=2e-6, err_msg=name)
+        np.testing.assert_allclose(_np(gB), gold["gB." + name], rtol=2e-3, atol=2e-6, err_msg=name)
+
+
+def test_forward_mr_matches_reference_composition(tiny_sd, golden_dir):
+    gold = np.load(os.path.join(golden_dir, "forward_mr_tiny.npz"))
+    samples = synth.make_samples(batch=2, frames=3, seed=3)
+    assert abs(samples["video"].double().sum().item() - float(gold["video_checksum"])) < 1e-6
+    with torch.no_grad():
+        out = ob.forward_mr(tiny_sd, TINY, SyntheticT5Tokenizer(), samples)
+    assert out["inputs_embeds"].shape[1] == int(gold["L_enc"])
+    assert (out["labels"].numpy() == gold["labels"]).all()
+    assert abs(out["loss"].item() - float(gold["loss"])) < 2e-4
+    np.testing.assert_allclose(_np(out["inputs_embeds"][:, ::16, ::8]), gold["inputs_embeds"], **TOL)
+    np.testing.assert_allclose(_np(out["logits"][:, :, :256]), gold["logits_head"], rtol=1e-3, atol=1e-3)
+
+
+def test_string_helpers_match_reference(golden_dir):
+    gold = json.load(open(os.path.join(golden_dir, "mr_utils_golden.json")))
+    for s, want in gold["post_process"]:
+        assert mr_utils.post_process(s) == want, s
+    for s, want in gold["moment_str_to_list"]:
+        assert mr_utils.moment_str_to_list(mr_utils.post_process(s)) == want, s
+    si = gold["seconds_integers"]
+    ts = [torch.tensor(t) for t in si["timestamps"]]
+    table = {int(k): v for k, v in si["table"].items()}
+    out = mr_utils.get_timestamps_as_seconds_integers(ts, torch.tensor(si["durations"]), table)
+    assert [t.tolist() for t in out[0]] == si["out_ts"] and out[1] == si["out_dur"] and out[2] == si["out_prompt"]
+    o_ts, o_d = ob.seconds_integers(ts, torch.tensor(si["durations"]), table)
+    assert o_ts == si["out_ts"] and o_d == si["out_dur"]
+
+
+def test_beam_search_degenerates_to_greedy_and_respects_eos():
+    V = 12
+    table = torch.full((V, V), -5.0)
+    for i in range(V):
+        table[i, (i + 3) % V] = 2.0       # deterministic chain 0->3->6->9->0...
+    table[9, 1] = 4.0                     # 9 -> eos
+
+    def step(ids):
+        return table[ids[:, -1]]
+
+    out = beam_search(step, batch=2, num_beams=1, max_new_tokens=10)
+    assert out.tolist() == [[0, 3, 6, 9, 1]] * 2
+    out5 = beam_search(step, batch=1, num_beams=5, max_new_tokens=10)
+    assert out5[0, 0].item() == 0 and 1 in out5[0].tolist()
+    capped = beam_search(lambda ids: table[ids[:, -1]].index_fill(1, torch.tensor([1]), -50.0), 1, 3, max_new_tokens=4)
+    assert capped.shape[1] <= 5
