@@ -1,0 +1,91 @@
+/* mrblip_b200.h -- C ABI of libmrblip_b200.so: the sm_100a kernels behind the BLIP2_MR hot path.
+ *
+ * The reference (sudo-Boris/mr-Blip) is pure Python/PyTorch and has NO FFI of its own: its
+ * "operator API" for this path is the LAVIS nn.Module surface.  Each entry point
+ * below therefore cites the reference PyTorch call site whose device work it replaces; the Python
+ * host side (mr_blip_b200/*.py) mirrors the LAVIS classes and binds these symbols through ctypes
+ * (mr_blip_b200/_lib.py).  INTEGRATION.md shows the reference-side patch.
+ *
+ * Conventions: every pointer is a DEVICE pointer borrowed from the caller (no allocation, no
+ * ownership transfer); sizes are element counts; `ld*`/`*_rs`/`*_bs` are element strides;
+ * dtype codes: 0 = fp16, 1 = bf16, 2 = fp32; `stream` is a cudaStream_t; calls are asynchronous and
+ * stream-ordered, re-entrant per device.  Return 0 on success, <0 on error
+ * (-1 bad argument, -2 CUDA error -- text from mrb_last_error(), -3 unsupported shape).
+ */
+#ifndef MRBLIP_B200_H
+#define MRBLIP_B200_H
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+int mrb_abi_version(void);
+const char* mrb_last_error(void);
+
+/* D[M,N] = epi(A[M,K] . B[N,K]^T): tcgen05/TMEM/TMA GEMM.  epi: +bias[N] (fp32), exact-erf GELU, + fp32 residual
+ * (may alias out), output fp16/bf16/fp32; row_group = 256 selects the ViT patch-embed row remap (+cls slot, +pos_embed).
+ * Replaces F.linear / nn.Linear / Conv2d(k=s=14) at: eva_vit.py:122-125,146,54-61,196-203; Qformer.py:185-196,
+ * 278-289,349-375; blip2_mr.py:491; modeling_t5.py:323-329,542-558,611,1870 and their autograd dgrads. */
+int mrb_gemm(const void* A, long long lda, const void* B, long long ldb, int M, int N, int K, int dtype,
+             const float* bias, int gelu, const float* resid, long long ldr, void* out, int out_dtype, long long ldc,
+             int row_group, int force_bn, void* stream);
+
+/* softmax(scale * Q K^T + bias[h, j - i] + mask) V, scores never written to HBM; optional log-sum-exp for backward.
+ * Replaces eva_vit.py:128-145, Qformer.py:198-268, modeling_t5.py:561-610. */
+int mrb_attention_fwd(const void* q, long long q_bs, long long q_rs, const void* k, long long k_bs, long long k_rs,
+                      const void* v, long long v_bs, long long v_rs, void* o, long long o_bs, long long o_rs,
+                      int B, int H, int Lq, int Lk, int hd, int dtype, float scale, const float* bias, int bias_len,
+                      int bias_zero, const int* kmask, int causal, int q_pos0, float* lse, void* stream);
+/* dQ, dK, dV of the above (autograd of modeling_t5.py:561-610); hd <= 64. delta_ws: fp32 [B*H*Lq] workspace. */
+int mrb_attention_bwd(const void* q, long long q_bs, long long q_rs, const void* k, long long k_bs, long long k_rs,
+                      const void* v, long long v_bs, long long v_rs, const void* o, long long o_bs, long long o_rs,
+                      const void* dout, long long do_bs, long long do_rs, void* dq, void* dk, void* dv,
+                      int B, int H, int Lq, int Lk, int hd, int dtype, float scale, const float* bias, int bias_len,
+                      int bias_zero, const int* kmask, int causal, int q_pos0, const float* lse, float* delta_ws,
+                      void* stream);
+
+/* mode 0: LayerNorm(x [+ add]) (eva_vit.py:175-176, blip2.py:113-119, Qformer.py:104-108,288);
+ * mode 1: T5 RMSNorm (modeling_t5.py:263-277).  fp32 in; optional fp32 out, 16-bit out (ld_h), and x+add out. */
+int mrb_norm(const float* x, const float* add, const float* w, const float* bias, float eps, int rows, int C, int mode,
+             float* out_f32, void* out_h, int h_dtype, long long ld_h, float* sum_out, void* stream);
+/* dres += d/dx RMSNorm(x; w) . dy   (autograd of modeling_t5.py:263-277, weights frozen) */
+int mrb_rmsnorm_bwd(const float* x, const float* w, const float* dy, float eps, int rows, int C, float* dres, void* stream);
+
+/* frames fp32 [F,3,S,S] -> patch matrix [F*(S/P)^2, ldA] (16-bit), zero padded: A operand of the patch-embed GEMM
+ * (eva_vit.py:196-203). */
+int mrb_patchify(const float* img, void* out, int dtype, int frames, int img_size, int patch, int ldA, void* stream);
+/* x[f, 0, :] = cls_token + pos_embed[0]  (eva_vit.py:328-331) */
+int mrb_cls_pos(const float* cls, const float* pos, float* x, int frames, int tokens, int C, void* stream);
+
+/* h = gelu(ab[:, :F]) * ab[:, F:]  and its backward  (modeling_t5.py:323-329) */
+int mrb_gated_gelu_fwd(const void* ab, void* h, int M, int F, long long ldh, int dtype, void* stream);
+int mrb_gated_gelu_bwd(const void* ab, const void* dh, long long lddh, void* dab, int M, int F, int dtype, void* stream);
+
+/* inputs_embeds assembly (blip2_mr.py:691-783 interleave + embed_tokens lookups) from an int32 row table:
+ * idx >= 0 embedding row, idx < 0 frame-token row -(idx+1), INT_MIN zero row; and its backward to the frame tokens. */
+int mrb_gather_rows(const int* idx, const float* emb, const float* frames, float* out, int rows, int C, void* stream);
+int mrb_scatter_frames(const int* idx, const float* dout, float* dframes, int rows, int C, void* stream);
+/* frame_token_aggregation == "mean" (blip2_mr.py:493-498) and backward */
+int mrb_group_mean(const float* x, float* out, int groups, int n, int C, void* stream);
+int mrb_group_mean_bwd(const float* dout, float* dx, int groups, int n, int C, void* stream);
+
+/* CrossEntropyLoss(ignore_index=-100) rows + d(logits) (modeling_t5.py:1872-1875) */
+int mrb_cross_entropy(const float* logits, const long long* labels, int rows, int V, float* row_loss, void* dlogits,
+                      int d_dtype, long long ldd, float gscale, void* stream);
+
+/* LoRA (peft lora.Linear, configured at blip2_mr.py:193-200): x_ext[:, K:K+32] = x_ext[:, :K] . A^T (R = 8/16/24 rows) */
+int mrb_lora_down(void* x_ext, long long ldx, const float* A, int M, int K, int R, int dtype, void* stream);
+/* out[C,8] (or [8,C] when transposed_out) += P[M,C]^T . Q[M,8]: LoRA A/B weight gradients */
+int mrb_skinny_wgrad(const void* P, long long ldp, const void* Q, long long ldq, int M, int C, float* out,
+                     int transposed_out, int dtype, void* stream);
+
+/* plumbing: casts, 16-bit transpose, fp32 column sums (t5_proj bias grad), y = a*x + b*y */
+int mrb_cast_f32_to_h(const float* in, void* out, long long n, int dtype, void* stream);
+int mrb_cast2d_f32_to_h(const float* in, long long ld_in, void* out, long long ld_out, int rows, int cols, int dtype, void* stream);
+int mrb_transpose16(const void* in, long long ld_in, void* out, long long ld_out, int rows, int cols, void* stream);
+int mrb_colsum(const float* in, int rows, int C, float* out, void* stream);
+int mrb_axpby(const float* x, float* y, long long n, float a, float b, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,595 @@
+// Fused flash-style attention (softmax(scale*Q K^T + bias + mask) V) for the four attention shapes of
+// the path: EVA ViT (eva_vit.py:118-148, 257 tokens, hd 88), Q-Former self/cross (Qformer.py:169-275,
+// 32x32 / 32x257, hd 64), T5 encoder/decoder self + cross (modeling_t5.py:474-620, no 1/sqrt(d),
+// bucketed relative bias, padding / causal mask), plus the T5 backward (dQ and dK/dV kernels).
+// Scores never touch HBM.  This first version drives the tensor cores through mma.sync m16n8k16
+// (HMMA); the tcgen05 port of the long-sequence T5 case is tracked in DESIGN.md.
+#include "common.cuh"
+
+namespace mrb {
+
+struct AttnParams {
+  const void* q; const void* k; const void* v; void* o;
+  long long q_bs, q_rs, k_bs, k_rs, v_bs, v_rs, o_bs, o_rs;   // batch / row strides (elements); head h at column h*hd
+  int B, H, Lq, Lk, hd;
+  float scale;
+  const float* bias;        // [H, bias_len] indexed by (j - i_abs) + bias_zero, or null
+  int bias_len, bias_zero;
+  const int* kmask;         // [B, Lk] 1 = attend, or null
+  int causal;               // key j allowed iff j <= i + q_pos0
+  int q_pos0;               // absolute position of query row 0
+  float* lse;               // [B, H, Lq] or null
+  // backward
+  const void* dout; long long do_bs, do_rs;
+  const float* delta;       // [B, H, Lq] rowsum(dO * O)
+  void* dq; void* dk; void* dv;   // same layout/strides as q/k/v
+};
+
+constexpr int BQ = 64, BKV = 64, NTHREADS = 128;
+
+template <typename T> struct MmaType;
+template <> struct MmaType<__half> {
+  static __device__ __forceinline__ void mma(float* c, const uint32_t* a, uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3]) : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+  }
+  static __device__ __forceinline__ uint32_t pack(float x, float y) { __half2 h = __floats2half2_rn(x, y); return *reinterpret_cast<uint32_t*>(&h); }
+};
+template <> struct MmaType<__nv_bfloat16> {
+  static __device__ __forceinline__ void mma(float* c, const uint32_t* a, uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3]) : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+  }
+  static __device__ __forceinline__ uint32_t pack(float x, float y) { __nv_bfloat162 h = __floats2bfloat162_rn(x, y); return *reinterpret_cast<uint32_t*>(&h); }
+};
+
+__device__ __forceinline__ void ldsm_x4(uint32_t* r, uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void ldsm_x4_t(uint32_t* r, uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, bool valid) {
+  const int sz = valid ? 16 : 0;
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// Load a [ROWS x HD] tile (row stride HD+8 elements in smem) of a [L, *] matrix; rows >= L and columns >= hd zero-filled.
+template <typename T, int HD, int ROWS>
+__device__ __forceinline__ void load_tile(uint32_t smem, const T* g, long long rs, int row0, int L, int hd) {
+  constexpr int CH = HD / 8;  // 16-byte chunks per row
+  for (int i = threadIdx.x; i < ROWS * CH; i += NTHREADS) {
+    const int r = i / CH, c = i - r * CH;
+    const bool ok = (row0 + r < L) && (c * 8 < hd);
+    const T* src = ok ? g + static_cast<long long>(row0 + r) * rs + c * 8 : g;
+    cp_async16(smem + (r * (HD + 8) + c * 8) * 2, src, ok);
+  }
+}
+
+// score post-processing shared by forward and backward: scale, relative bias, masks
+struct ScoreCtx {
+  float scale; const float* bias; int bias_zero; const int* kmask; int causal, q_pos0, Lk;
+  __device__ __forceinline__ float apply(float s, int i, int j) const {
+    if (j >= Lk) return -INFINITY;
+    s *= scale;
+    if (bias) s += __ldg(bias + (j - (i + q_pos0)) + bias_zero);
+    if (kmask && __ldg(kmask + j) == 0) return -INFINITY;
+    if (causal && j > i + q_pos0) return -INFINITY;
+    return s;
+  }
+};
+
+template <typename T, int HD>
+__global__ void __launch_bounds__(NTHREADS) attn_fwd_kernel(const AttnParams p) {
+  constexpr int LDS = HD + 8;
+  extern __shared__ __align__(16) uint8_t smem_attn[];
+  T* sQ = reinterpret_cast<T*>(smem_attn);
+  T* sK = sQ + BQ * LDS;
+  T* sV = sK + 2 * BKV * LDS;
+  const int b = blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * BQ;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t4 = lane & 3;
+  const T* gq = static_cast<const T*>(p.q) + b * p.q_bs + static_cast<long long>(h) * p.hd;
+  const T* gk = static_cast<const T*>(p.k) + b * p.k_bs + static_cast<long long>(h) * p.hd;
+  const T* gv = static_cast<const T*>(p.v) + b * p.v_bs + static_cast<long long>(h) * p.hd;
+  ScoreCtx sc{p.scale, p.bias ? p.bias + static_cast<long long>(h) * p.bias_len : nullptr, p.bias_zero,
+              p.kmask ? p.kmask + static_cast<long long>(b) * p.Lk : nullptr, p.causal, p.q_pos0, p.Lk};
+
+  int n_kv = (p.Lk + BKV - 1) / BKV;
+  if (p.causal) n_kv = min(n_kv, (q0 + BQ - 1 + p.q_pos0) / BKV + 1);
+
+  load_tile<T, HD, BQ>(smem_u32(sQ), gq, p.q_rs, q0, p.Lq, p.hd);
+  load_tile<T, HD, BKV>(smem_u32(sK), gk, p.k_rs, 0, p.Lk, p.hd);
+  load_tile<T, HD, BKV>(smem_u32(sV), gv, p.v_rs, 0, p.Lk, p.hd);
+  cp_async_commit();
+
+  float o_acc[HD / 8][4];
+#pragma unroll
+  for (int i = 0; i < HD / 8; ++i) o_acc[i][0] = o_acc[i][1] = o_acc[i][2] = o_acc[i][3] = 0.f;
+  float m_run[2] = {-INFINITY, -INFINITY}, l_run[2] = {0.f, 0.f};
+  uint32_t qf[HD / 16][4];
+  const float LOG2E = 1.4426950408889634f;
+
+  for (int kv = 0; kv < n_kv; ++kv) {
+    const int buf = kv & 1;
+    if (kv + 1 < n_kv) {
+      load_tile<T, HD, BKV>(smem_u32(sK + (buf ^ 1) * BKV * LDS), gk, p.k_rs, (kv + 1) * BKV, p.Lk, p.hd);
+      load_tile<T, HD, BKV>(smem_u32(sV + (buf ^ 1) * BKV * LDS), gv, p.v_rs, (kv + 1) * BKV, p.Lk, p.hd);
+      cp_async_commit();
+      cp_async_wait<1>();
+    } else {
+      cp_async_wait<0>();
+    }
+    __syncthreads();
+    if (kv == 0) {
+#pragma unroll
+      for (int kk = 0; kk < HD / 16; ++kk)
+        ldsm_x4(qf[kk], smem_u32(sQ + (warp * 16 + (lane & 15)) * LDS + kk * 16 + (lane >> 4) * 8));
+    }
+    const T* cK = sK + buf * BKV * LDS;
+    const T* cV = sV + buf * BKV * LDS;
+    // S = Q K^T  (16 x 64 per warp)
+    float s[BKV / 8][4];
+#pragma unroll
+    for (int i = 0; i < BKV / 8; ++i) s[i][0] = s[i][1] = s[i][2] = s[i][3] = 0.f;
+#pragma unroll
+    for (int kk = 0; kk < HD / 16; ++kk) {
+#pragma unroll
+      for (int nb = 0; nb < BKV / 16; ++nb) {
+        uint32_t kf[4];
+        ldsm_x4(kf, smem_u32(cK + (nb * 16 + (lane >> 4) * 8 + (lane & 7)) * LDS + kk * 16 + ((lane >> 3) & 1) * 8));
+        MmaType<T>::mma(s[2 * nb], qf[kk], kf[0], kf[1]);
+        MmaType<T>::mma(s[2 * nb + 1], qf[kk], kf[2], kf[3]);
+      }
+    }
+    // scale / bias / mask, online softmax
+    const int i0 = q0 + warp * 16 + g;
+    float m_new[2] = {m_run[0], m_run[1]};
+#pragma unroll
+    for (int nb = 0; nb < BKV / 8; ++nb) {
+      const int j = kv * BKV + nb * 8 + 2 * t4;
+      s[nb][0] = sc.apply(s[nb][0], i0, j);
+      s[nb][1] = sc.apply(s[nb][1], i0, j + 1);
+      s[nb][2] = sc.apply(s[nb][2], i0 + 8, j);
+      s[nb][3] = sc.apply(s[nb][3], i0 + 8, j + 1);
+      m_new[0] = fmaxf(m_new[0], fmaxf(s[nb][0], s[nb][1]));
+      m_new[1] = fmaxf(m_new[1], fmaxf(s[nb][2], s[nb][3]));
+    }
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      m_new[r] = fmaxf(m_new[r], __shfl_xor_sync(0xffffffffu, m_new[r], 1));
+      m_new[r] = fmaxf(m_new[r], __shfl_xor_sync(0xffffffffu, m_new[r], 2));
+    }
+    float corr[2], msc[2];
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      msc[r] = (m_new[r] == -INFINITY) ? 0.f : m_new[r] * LOG2E;
+      corr[r] = (m_run[r] == -INFINITY) ? 0.f : exp2f(m_run[r] * LOG2E - msc[r]);
+      m_run[r] = m_new[r];
+      l_run[r] *= corr[r];
+    }
+    uint32_t pf[BKV / 16][4];
+#pragma unroll
+    for (int nb = 0; nb < BKV / 8; ++nb) {
+      const float p0 = exp2f(s[nb][0] * LOG2E - msc[0]), p1 = exp2f(s[nb][1] * LOG2E - msc[0]);
+      const float p2 = exp2f(s[nb][2] * LOG2E - msc[1]), p3 = exp2f(s[nb][3] * LOG2E - msc[1]);
+      l_run[0] += p0 + p1;
+      l_run[1] += p2 + p3;
+      pf[nb >> 1][(nb & 1) * 2] = MmaType<T>::pack(p0, p1);
+      pf[nb >> 1][(nb & 1) * 2 + 1] = MmaType<T>::pack(p2, p3);
+    }
+#pragma unroll
+    for (int i = 0; i < HD / 8; ++i) {
+      o_acc[i][0] *= corr[0]; o_acc[i][1] *= corr[0];
+      o_acc[i][2] *= corr[1]; o_acc[i][3] *= corr[1];
+    }
+    // O += P V
+#pragma unroll
+    for (int kk = 0; kk < BKV / 16; ++kk) {
+#pragma unroll
+      for (int db = 0; db < HD / 16; ++db) {
+        uint32_t vf[4];
+        ldsm_x4_t(vf, smem_u32(cV + (kk * 16 + ((lane >> 3) & 1) * 8 + (lane & 7)) * LDS + db * 16 + (lane >> 4) * 8));
+        MmaType<T>::mma(o_acc[2 * db], pf[kk], vf[0], vf[1]);
+        MmaType<T>::mma(o_acc[2 * db + 1], pf[kk], vf[2], vf[3]);
+      }
+    }
+    __syncthreads();
+  }
+  // finalize
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    l_run[r] += __shfl_xor_sync(0xffffffffu, l_run[r], 1);
+    l_run[r] += __shfl_xor_sync(0xffffffffu, l_run[r], 2);
+  }
+  T* go = static_cast<T*>(p.o) + b * p.o_bs + static_cast<long long>(h) * p.hd;
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    const int i = q0 + warp * 16 + g + r * 8;
+    if (i >= p.Lq) continue;
+    const float inv = l_run[r] > 0.f ? 1.f / l_run[r] : 0.f;
+#pragma unroll
+    for (int nb = 0; nb < HD / 8; ++nb) {
+      const int c = nb * 8 + 2 * t4;
+      if (c < p.hd) {
+        const uint32_t w = MmaType<T>::pack(o_acc[nb][2 * r] * inv, o_acc[nb][2 * r + 1] * inv);
+        *reinterpret_cast<uint32_t*>(go + static_cast<long long>(i) * p.o_rs + c) = w;
+      }
+    }
+    if (p.lse && t4 == 0)
+      p.lse[(static_cast<long long>(b) * p.H + h) * p.Lq + i] = m_run[r] + logf(l_run[r]);
+  }
+}
+
+// delta[b,h,i] = sum_d dO[b,i,h,d] * O[b,i,h,d]
+template <typename T>
+__global__ void attn_delta_kernel(const AttnParams p) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  const int total = p.B * p.H * p.Lq;
+  if (row >= total) return;
+  const int i = row % p.Lq, h = (row / p.Lq) % p.H, b = row / (p.Lq * p.H);
+  const T* o = static_cast<const T*>(p.o) + b * p.o_bs + static_cast<long long>(i) * p.o_rs + h * p.hd;
+  const T* d = static_cast<const T*>(p.dout) + b * p.do_bs + static_cast<long long>(i) * p.do_rs + h * p.hd;
+  float acc = 0.f;
+  for (int c = lane; c < p.hd; c += 32) acc += to_f32(o[c]) * to_f32(d[c]);
+  acc = warp_sum(acc);
+  if (lane == 0) const_cast<float*>(p.delta)[row] = acc;
+}
+
+// dQ = scale * sum_j dS_ij K_j   with dS = P * (dO V^T - delta).  One CTA per 64 query rows.
+template <typename T, int HD>
+__global__ void __launch_bounds__(NTHREADS) attn_bwd_dq_kernel(const AttnParams p) {
+  constexpr int LDS = HD + 8;
+  extern __shared__ __align__(16) uint8_t smem_attn[];
+  T* sQ = reinterpret_cast<T*>(smem_attn);
+  T* sdO = sQ + BQ * LDS;
+  T* sK = sdO + BQ * LDS;
+  T* sV = sK + 2 * BKV * LDS;
+  const int b = blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * BQ;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t4 = lane & 3;
+  const T* gq = static_cast<const T*>(p.q) + b * p.q_bs + static_cast<long long>(h) * p.hd;
+  const T* gk = static_cast<const T*>(p.k) + b * p.k_bs + static_cast<long long>(h) * p.hd;
+  const T* gv = static_cast<const T*>(p.v) + b * p.v_bs + static_cast<long long>(h) * p.hd;
+  const T* gdo = static_cast<const T*>(p.dout) + b * p.do_bs + static_cast<long long>(h) * p.hd;
+  ScoreCtx sc{p.scale, p.bias ? p.bias + static_cast<long long>(h) * p.bias_len : nullptr, p.bias_zero,
+              p.kmask ? p.kmask + static_cast<long long>(b) * p.Lk : nullptr, p.causal, p.q_pos0, p.Lk};
+  int n_kv = (p.Lk + BKV - 1) / BKV;
+  if (p.causal) n_kv = min(n_kv, (q0 + BQ - 1 + p.q_pos0) / BKV + 1);
+
+  load_tile<T, HD, BQ>(smem_u32(sQ), gq, p.q_rs, q0, p.Lq, p.hd);
+  load_tile<T, HD, BQ>(smem_u32(sdO), gdo, p.do_rs, q0, p.Lq, p.hd);
+  load_tile<T, HD, BKV>(smem_u32(sK), gk, p.k_rs, 0, p.Lk, p.hd);
+  load_tile<T, HD, BKV>(smem_u32(sV), gv, p.v_rs, 0, p.Lk, p.hd);
+  cp_async_commit();
+
+  const long long stat = (static_cast<long long>(b) * p.H + h) * p.Lq;
+  float lse[2], dl[2];
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    const int i = q0 + warp * 16 + g + r * 8;
+    lse[r] = i < p.Lq ? p.lse[stat + i] : 0.f;
+    dl[r] = i < p.Lq ? p.delta[stat + i] : 0.f;
+  }
+  float dq_acc[HD / 8][4];
+#pragma unroll
+  for (int i = 0; i < HD / 8; ++i) dq_acc[i][0] = dq_acc[i][1] = dq_acc[i][2] = dq_acc[i][3] = 0.f;
+  uint32_t qf[HD / 16][4], dof[HD / 16][4];
+
+  for (int kv = 0; kv < n_kv; ++kv) {
+    const int buf = kv & 1;
+    if (kv + 1 < n_kv) {
+      load_tile<T, HD, BKV>(smem_u32(sK + (buf ^ 1) * BKV * LDS), gk, p.k_rs, (kv + 1) * BKV, p.Lk, p.hd);
+      load_tile<T, HD, BKV>(smem_u32(sV + (buf ^ 1) * BKV * LDS), gv, p.v_rs, (kv + 1) * BKV, p.Lk, p.hd);
+      cp_async_commit();
+      cp_async_wait<1>();
+    } else {
+      cp_async_wait<0>();
+    }
+    __syncthreads();
+    if (kv == 0) {
+#pragma unroll
+      for (int kk = 0; kk < HD / 16; ++kk) {
+        ldsm_x4(qf[kk], smem_u32(sQ + (warp * 16 + (lane & 15)) * LDS + kk * 16 + (lane >> 4) * 8));
+        ldsm_x4(dof[kk], smem_u32(sdO + (warp * 16 + (lane & 15)) * LDS + kk * 16 + (lane >> 4) * 8));
+      }
+    }
+    const T* cK = sK + buf * BKV * LDS;
+    const T* cV = sV + buf * BKV * LDS;
+    float s[BKV / 8][4], dp[BKV / 8][4];
+#pragma unroll
+    for (int i = 0; i < BKV / 8; ++i) {
+      s[i][0] = s[i][1] = s[i][2] = s[i][3] = 0.f;
+      dp[i][0] = dp[i][1] = dp[i][2] = dp[i][3] = 0.f;
+    }
+#pragma unroll
+    for (int kk = 0; kk < HD / 16; ++kk) {
+#pragma unroll
+      for (int nb = 0; nb < BKV / 16; ++nb) {
+        uint32_t kf[4], vf[4];
+        const int off = (nb * 16 + (lane >> 4) * 8 + (lane & 7)) * LDS + kk * 16 + ((lane >> 3) & 1) * 8;
+        ldsm_x4(kf, smem_u32(cK + off));
+        ldsm_x4(vf, smem_u32(cV + off));
+        MmaType<T>::mma(s[2 * nb], qf[kk], kf[0], kf[1]);
+        MmaType<T>::mma(s[2 * nb + 1], qf[kk], kf[2], kf[3]);
+        MmaType<T>::mma(dp[2 * nb], dof[kk], vf[0], vf[1]);
+        MmaType<T>::mma(dp[2 * nb + 1], dof[kk], vf[2], vf[3]);
+      }
+    }
+    const int i0 = q0 + warp * 16 + g;
+    uint32_t dsf[BKV / 16][4];
+#pragma unroll
+    for (int nb = 0; nb < BKV / 8; ++nb) {
+      const int j = kv * BKV + nb * 8 + 2 * t4;
+      float ds[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int r = e >> 1;
+        const float sv = sc.apply(s[nb][e], i0 + r * 8, j + (e & 1));
+        const float pr = (sv == -INFINITY) ? 0.f : __expf(sv - lse[r]);
+        ds[e] = pr * (dp[nb][e] - dl[r]) * p.scale;
+      }
+      dsf[nb >> 1][(nb & 1) * 2] = MmaType<T>::pack(ds[0], ds[1]);
+      dsf[nb >> 1][(nb & 1) * 2 + 1] = MmaType<T>::pack(ds[2], ds[3]);
+    }
+    // dQ += dS K   (B operand = K [key x d] -> transposed ldmatrix)
+#pragma unroll
+    for (int kk = 0; kk < BKV / 16; ++kk) {
+#pragma unroll
+      for (int db = 0; db < HD / 16; ++db) {
+        uint32_t kf[4];
+        ldsm_x4_t(kf, smem_u32(cK + (kk * 16 + ((lane >> 3) & 1) * 8 + (lane & 7)) * LDS + db * 16 + (lane >> 4) * 8));
+        MmaType<T>::mma(dq_acc[2 * db], dsf[kk], kf[0], kf[1]);
+        MmaType<T>::mma(dq_acc[2 * db + 1], dsf[kk], kf[2], kf[3]);
+      }
+    }
+    __syncthreads();
+  }
+  T* gdq = static_cast<T*>(p.dq) + b * p.q_bs + static_cast<long long>(h) * p.hd;
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    const int i = q0 + warp * 16 + g + r * 8;
+    if (i >= p.Lq) continue;
+#pragma unroll
+    for (int nb = 0; nb < HD / 8; ++nb) {
+      const int c = nb * 8 + 2 * t4;
+      if (c < p.hd)
+        *reinterpret_cast<uint32_t*>(gdq + static_cast<long long>(i) * p.q_rs + c) =
+            MmaType<T>::pack(dq_acc[nb][2 * r], dq_acc[nb][2 * r + 1]);
+    }
+  }
+}
+
+// dK_j = scale * sum_i dS_ij Q_i,  dV_j = sum_i P_ij dO_i.  One CTA per 64 keys; works on the transposed
+// problem (keys are the MMA M dimension) so P^T / dS^T fragments feed the second MMAs directly.
+template <typename T, int HD>
+__global__ void __launch_bounds__(NTHREADS) attn_bwd_dkv_kernel(const AttnParams p) {
+  constexpr int LDS = HD + 8;
+  extern __shared__ __align__(16) uint8_t smem_attn[];
+  T* sK = reinterpret_cast<T*>(smem_attn);
+  T* sV = sK + BKV * LDS;
+  T* sQ = sV + BKV * LDS;
+  T* sdO = sQ + 2 * BQ * LDS;
+  float* sLse = reinterpret_cast<float*>(sdO + 2 * BQ * LDS);
+  float* sDl = sLse + 2 * BQ;
+  const int b = blockIdx.z, h = blockIdx.y, k0 = blockIdx.x * BKV;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t4 = lane & 3;
+  const T* gq = static_cast<const T*>(p.q) + b * p.q_bs + static_cast<long long>(h) * p.hd;
+  const T* gk = static_cast<const T*>(p.k) + b * p.k_bs + static_cast<long long>(h) * p.hd;
+  const T* gv = static_cast<const T*>(p.v) + b * p.v_bs + static_cast<long long>(h) * p.hd;
+  const T* gdo = static_cast<const T*>(p.dout) + b * p.do_bs + static_cast<long long>(h) * p.hd;
+  ScoreCtx sc{p.scale, p.bias ? p.bias + static_cast<long long>(h) * p.bias_len : nullptr, p.bias_zero,
+              p.kmask ? p.kmask + static_cast<long long>(b) * p.Lk : nullptr, p.causal, p.q_pos0, p.Lk};
+  const long long stat = (static_cast<long long>(b) * p.H + h) * p.Lq;
+  const int n_q = (p.Lq + BQ - 1) / BQ;
+  int q_begin = 0;
+  if (p.causal) q_begin = max(0, (k0 - p.q_pos0) / BQ);   // rows i with i + q_pos0 >= k0
+
+  auto load_q = [&](int qt, int buf) {
+    load_tile<T, HD, BQ>(smem_u32(sQ + buf * BQ * LDS), gq, p.q_rs, qt * BQ, p.Lq, p.hd);
+    load_tile<T, HD, BQ>(smem_u32(sdO + buf * BQ * LDS), gdo, p.do_rs, qt * BQ, p.Lq, p.hd);
+    if (threadIdx.x < BQ) {
+      const int i = qt * BQ + threadIdx.x;
+      sLse[buf * BQ + threadIdx.x] = i < p.Lq ? p.lse[stat + i] : 0.f;
+      sDl[buf * BQ + threadIdx.x] = i < p.Lq ? p.delta[stat + i] : 0.f;
+    }
+  };
+  load_tile<T, HD, BKV>(smem_u32(sK), gk, p.k_rs, k0, p.Lk, p.hd);
+  load_tile<T, HD, BKV>(smem_u32(sV), gv, p.v_rs, k0, p.Lk, p.hd);
+  if (q_begin < n_q) load_q(q_begin, 0);
+  cp_async_commit();
+
+  float dk_acc[HD / 8][4], dv_acc[HD / 8][4];
+#pragma unroll
+  for (int i = 0; i < HD / 8; ++i) {
+    dk_acc[i][0] = dk_acc[i][1] = dk_acc[i][2] = dk_acc[i][3] = 0.f;
+    dv_acc[i][0] = dv_acc[i][1] = dv_acc[i][2] = dv_acc[i][3] = 0.f;
+  }
+  uint32_t kf_a[HD / 16][4], vf_a[HD / 16][4];
+
+  for (int qt = q_begin; qt < n_q; ++qt) {
+    const int buf = (qt - q_begin) & 1;
+    if (qt + 1 < n_q) {
+      load_q(qt + 1, buf ^ 1);
+      cp_async_commit();
+      cp_async_wait<1>();
+    } else {
+      cp_async_wait<0>();
+    }
+    __syncthreads();
+    if (qt == q_begin) {
+#pragma unroll
+      for (int kk = 0; kk < HD / 16; ++kk) {
+        ldsm_x4(kf_a[kk], smem_u32(sK + (warp * 16 + (lane & 15)) * LDS + kk * 16 + (lane >> 4) * 8));
+        ldsm_x4(vf_a[kk], smem_u32(sV + (warp * 16 + (lane & 15)) * LDS + kk * 16 + (lane >> 4) * 8));
+      }
+    }
+    const T* cQ = sQ + buf * BQ * LDS;
+    const T* cdO = sdO + buf * BQ * LDS;
+    // S^T = K Q^T, dP^T = V dO^T   (16 keys x 64 queries per warp)
+    float st[BQ / 8][4], dpt[BQ / 8][4];
+#pragma unroll
+    for (int i = 0; i < BQ / 8; ++i) {
+      st[i][0] = st[i][1] = st[i][2] = st[i][3] = 0.f;
+      dpt[i][0] = dpt[i][1] = dpt[i][2] = dpt[i][3] = 0.f;
+    }
+#pragma unroll
+    for (int kk = 0; kk < HD / 16; ++kk) {
+#pragma unroll
+      for (int nb = 0; nb < BQ / 16; ++nb) {
+        uint32_t qf[4], dof[4];
+        const int off = (nb * 16 + (lane >> 4) * 8 + (lane & 7)) * LDS + kk * 16 + ((lane >> 3) & 1) * 8;
+        ldsm_x4(qf, smem_u32(cQ + off));
+        ldsm_x4(dof, smem_u32(cdO + off));
+        MmaType<T>::mma(st[2 * nb], kf_a[kk], qf[0], qf[1]);
+        MmaType<T>::mma(st[2 * nb + 1], kf_a[kk], qf[2], qf[3]);
+        MmaType<T>::mma(dpt[2 * nb], vf_a[kk], dof[0], dof[1]);
+        MmaType<T>::mma(dpt[2 * nb + 1], vf_a[kk], dof[2], dof[3]);
+      }
+    }
+    const int j0 = k0 + warp * 16 + g;
+    uint32_t ptf[BQ / 16][4], dstf[BQ / 16][4];
+#pragma unroll
+    for (int nb = 0; nb < BQ / 8; ++nb) {
+      float pr[4], ds[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int il = nb * 8 + 2 * t4 + (e & 1);       // query within tile (column of S^T)
+        const int i = qt * BQ + il;
+        const int j = j0 + (e >> 1) * 8;
+        const float sv = (i < p.Lq) ? sc.apply(st[nb][e], i, j) : -INFINITY;
+        pr[e] = (sv == -INFINITY) ? 0.f : __expf(sv - sLse[buf * BQ + il]);
+        ds[e] = pr[e] * (dpt[nb][e] - sDl[buf * BQ + il]) * p.scale;
+      }
+      ptf[nb >> 1][(nb & 1) * 2] = MmaType<T>::pack(pr[0], pr[1]);
+      ptf[nb >> 1][(nb & 1) * 2 + 1] = MmaType<T>::pack(pr[2], pr[3]);
+      dstf[nb >> 1][(nb & 1) * 2] = MmaType<T>::pack(ds[0], ds[1]);
+      dstf[nb >> 1][(nb & 1) * 2 + 1] = MmaType<T>::pack(ds[2], ds[3]);
+    }
+    // dV += P^T dO ; dK += dS^T Q    (B operands [query x d] -> transposed ldmatrix)
+#pragma unroll
+    for (int kk = 0; kk < BQ / 16; ++kk) {
+#pragma unroll
+      for (int db = 0; db < HD / 16; ++db) {
+        uint32_t f1[4], f2[4];
+        const int off = (kk * 16 + ((lane >> 3) & 1) * 8 + (lane & 7)) * LDS + db * 16 + (lane >> 4) * 8;
+        ldsm_x4_t(f1, smem_u32(cdO + off));
+        ldsm_x4_t(f2, smem_u32(cQ + off));
+        MmaType<T>::mma(dv_acc[2 * db], ptf[kk], f1[0], f1[1]);
+        MmaType<T>::mma(dv_acc[2 * db + 1], ptf[kk], f1[2], f1[3]);
+        MmaType<T>::mma(dk_acc[2 * db], dstf[kk], f2[0], f2[1]);
+        MmaType<T>::mma(dk_acc[2 * db + 1], dstf[kk], f2[2], f2[3]);
+      }
+    }
+    __syncthreads();
+  }
+  T* gdk = static_cast<T*>(p.dk) + b * p.k_bs + static_cast<long long>(h) * p.hd;
+  T* gdv = static_cast<T*>(p.dv) + b * p.v_bs + static_cast<long long>(h) * p.hd;
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    const int j = k0 + warp * 16 + g + r * 8;
+    if (j >= p.Lk) continue;
+#pragma unroll
+    for (int nb = 0; nb < HD / 8; ++nb) {
+      const int c = nb * 8 + 2 * t4;
+      if (c < p.hd) {
+        *reinterpret_cast<uint32_t*>(gdk + static_cast<long long>(j) * p.k_rs + c) = MmaType<T>::pack(dk_acc[nb][2 * r], dk_acc[nb][2 * r + 1]);
+        *reinterpret_cast<uint32_t*>(gdv + static_cast<long long>(j) * p.v_rs + c) = MmaType<T>::pack(dv_acc[nb][2 * r], dv_acc[nb][2 * r + 1]);
+      }
+    }
+  }
+}
+
+template <typename K>
+static int set_smem(K kernel, int bytes) {
+  cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  return e == cudaSuccess ? MRB_OK : mrb_set_error(e);
+}
+
+template <typename T, int HD>
+static int launch_fwd(const AttnParams& p, cudaStream_t s) {
+  const int smem = (BQ + 4 * BKV) * (HD + 8) * 2;
+  static bool cfg = false;
+  if (!cfg) { if (int rc = set_smem(attn_fwd_kernel<T, HD>, smem)) return rc; cfg = true; }
+  dim3 grid((p.Lq + BQ - 1) / BQ, p.H, p.B);
+  attn_fwd_kernel<T, HD><<<grid, NTHREADS, smem, s>>>(p);
+  MRB_CHECK_LAUNCH();
+  return MRB_OK;
+}
+
+template <typename T, int HD>
+static int launch_bwd(const AttnParams& p, cudaStream_t s) {
+  {
+    const int rows = p.B * p.H * p.Lq;
+    attn_delta_kernel<T><<<(rows + 7) / 8, 256, 0, s>>>(p);
+    MRB_CHECK_LAUNCH();
+  }
+  {
+    const int smem = (2 * BQ + 4 * BKV) * (HD + 8) * 2;
+    static bool cfg = false;
+    if (!cfg) { if (int rc = set_smem(attn_bwd_dq_kernel<T, HD>, smem)) return rc; cfg = true; }
+    dim3 grid((p.Lq + BQ - 1) / BQ, p.H, p.B);
+    attn_bwd_dq_kernel<T, HD><<<grid, NTHREADS, smem, s>>>(p);
+    MRB_CHECK_LAUNCH();
+  }
+  {
+    const int smem = (2 * BKV + 4 * BQ) * (HD + 8) * 2 + 4 * BQ * 4;
+    static bool cfg = false;
+    if (!cfg) { if (int rc = set_smem(attn_bwd_dkv_kernel<T, HD>, smem)) return rc; cfg = true; }
+    dim3 grid((p.Lk + BKV - 1) / BKV, p.H, p.B);
+    attn_bwd_dkv_kernel<T, HD><<<grid, NTHREADS, smem, s>>>(p);
+    MRB_CHECK_LAUNCH();
+  }
+  return MRB_OK;
+}
+
+}  // namespace mrb
+
+using namespace mrb;
+
+static int check_attn(const AttnParams& p, int dtype) {
+  if (dtype != MRB_DT_F16 && dtype != MRB_DT_BF16) return MRB_ERR_ARG;
+  if (p.hd <= 0 || p.hd > 96 || (p.hd & 7)) return MRB_ERR_UNSUPPORTED;
+  if ((p.q_rs | p.k_rs | p.v_rs | p.o_rs | p.q_bs | p.k_bs | p.v_bs | p.o_bs) & 7) return MRB_ERR_ARG;
+  return MRB_OK;
+}
+
+extern "C" int mrb_attention_fwd(const void* q, long long q_bs, long long q_rs, const void* k, long long k_bs, long long k_rs,
+                                 const void* v, long long v_bs, long long v_rs, void* o, long long o_bs, long long o_rs,
+                                 int B, int H, int Lq, int Lk, int hd, int dtype, float scale, const float* bias,
+                                 int bias_len, int bias_zero, const int* kmask, int causal, int q_pos0, float* lse,
+                                 void* stream) {
+  if (B <= 0 || H <= 0 || Lq <= 0 || Lk <= 0) return MRB_OK;
+  AttnParams p{};
+  p.q = q; p.k = k; p.v = v; p.o = o;
+  p.q_bs = q_bs; p.q_rs = q_rs; p.k_bs = k_bs; p.k_rs = k_rs; p.v_bs = v_bs; p.v_rs = v_rs; p.o_bs = o_bs; p.o_rs = o_rs;
+  p.B = B; p.H = H; p.Lq = Lq; p.Lk = Lk; p.hd = hd; p.scale = scale;
+  p.bias = bias; p.bias_len = bias_len; p.bias_zero = bias_zero; p.kmask = kmask; p.causal = causal; p.q_pos0 = q_pos0;
+  p.lse = lse;
+  if (int rc = check_attn(p, dtype)) return rc;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (dtype == MRB_DT_F16) return hd <= 64 ? launch_fwd<__half, 64>(p, s) : launch_fwd<__half, 96>(p, s);
+  return hd <= 64 ? launch_fwd<__nv_bfloat16, 64>(p, s) : launch_fwd<__nv_bfloat16, 96>(p, s);
+}
+
+extern "C" int mrb_attention_bwd(const void* q, long long q_bs, long long q_rs, const void* k, long long k_bs, long long k_rs,
+                                 const void* v, long long v_bs, long long v_rs, const void* o, long long o_bs, long long o_rs,
+                                 const void* dout, long long do_bs, long long do_rs, void* dq, void* dk, void* dv,
+                                 int B, int H, int Lq, int Lk, int hd, int dtype, float scale, const float* bias,
+                                 int bias_len, int bias_zero, const int* kmask, int causal, int q_pos0, const float* lse,
+                                 float* delta_ws, void* stream) {
+  if (B <= 0 || H <= 0 || Lq <= 0 || Lk <= 0) return MRB_OK;
+  AttnParams p{};
+  p.q = q; p.k = k; p.v = v; p.o = const_cast<void*>(o);
+  p.q_bs = q_bs; p.q_rs = q_rs; p.k_bs = k_bs; p.k_rs = k_rs; p.v_bs = v_bs; p.v_rs = v_rs; p.o_bs = o_bs; p.o_rs = o_rs;
+  p.B = B; p.H = H; p.Lq = Lq; p.Lk = Lk; p.hd = hd; p.scale = scale;
+  p.bias = bias; p.bias_len = bias_len; p.bias_zero = bias_zero; p.kmask = kmask; p.causal = causal; p.q_pos0 = q_pos0;
+  p.lse = const_cast<float*>(lse); p.dout = dout; p.do_bs = do_bs; p.do_rs = do_rs; p.delta = delta_ws;
+  p.dq = dq; p.dk = dk; p.dv = dv;
+  if (int rc = check_attn(p, dtype)) return rc;
+  if (hd > 64 || ((do_bs | do_rs) & 7)) return MRB_ERR_UNSUPPORTED;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (dtype == MRB_DT_F16) return launch_bwd<__half, 64>(p, s);
+  return launch_bwd<__nv_bfloat16, 64>(p, s);
+}

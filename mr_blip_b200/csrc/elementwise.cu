@@ -1,0 +1,568 @@
+// HBM-bound kernels of the path: LayerNorm / T5 RMSNorm (+backward), patch extraction for the ViT
+// patch-embed GEMM, cls/pos rows, gated-GELU, the interleave gather that assembles inputs_embeds
+// (blip2_mr.py:691-783), embedding lookup, cross-entropy, LoRA down-projection and LoRA weight
+// gradients, casts/transposes.  All are one pass over their operands with 16-byte accesses.
+#include "common.cuh"
+
+namespace mrb {
+
+// ---------------------------------------------------------------- LayerNorm / RMSNorm (fp32 in)
+// One warp per row, row cached in registers (C <= 2048, C % 4 == 0).
+// mode 0: LayerNorm(x [+ add]) * w + b (eva_vit.py:175-176, blip2.py:113-119, Qformer.py:278-289)
+// mode 1: T5 RMSNorm (modeling_t5.py:263-277)
+template <int MAXV>
+__global__ void __launch_bounds__(256) norm_kernel(const float* __restrict__ x, const float* __restrict__ add,
+                                                   const float* __restrict__ w, const float* __restrict__ bias,
+                                                   float eps, int rows, int C, int mode, float* __restrict__ out_f32,
+                                                   void* __restrict__ out_h, int h_dtype, long long ld_h,
+                                                   float* __restrict__ sum_out) {
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const int nv = C >> 2;
+  const float4* xr = reinterpret_cast<const float4*>(x + static_cast<long long>(row) * C);
+  const float4* ar = add ? reinterpret_cast<const float4*>(add + static_cast<long long>(row) * C) : nullptr;
+  float4 v[MAXV];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    const int c = lane + i * 32;
+    if (c < nv) {
+      v[i] = xr[c];
+      if (ar) { const float4 a = ar[c]; v[i].x += a.x; v[i].y += a.y; v[i].z += a.z; v[i].w += a.w; }
+      s += v[i].x + v[i].y + v[i].z + v[i].w;
+    }
+  }
+  if (sum_out) {   // x + add is also the next residual stream
+    float4* so = reinterpret_cast<float4*>(sum_out + static_cast<long long>(row) * C);
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i) { const int c = lane + i * 32; if (c < nv) so[c] = v[i]; }
+  }
+  float mean = 0.f;
+  if (mode == 0) mean = warp_sum(s) / C;
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    const int c = lane + i * 32;
+    if (c < nv) {
+      const float a = v[i].x - mean, b = v[i].y - mean, cc = v[i].z - mean, d = v[i].w - mean;
+      q += a * a + b * b + cc * cc + d * d;
+    }
+  }
+  const float rstd = rsqrtf(warp_sum(q) / C + eps);
+  const float4* wr = reinterpret_cast<const float4*>(w);
+  const float4* br = bias ? reinterpret_cast<const float4*>(bias) : nullptr;
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    const int c = lane + i * 32;
+    if (c < nv) {
+      const float4 ww = wr[c];
+      float4 y;
+      y.x = (v[i].x - mean) * rstd * ww.x; y.y = (v[i].y - mean) * rstd * ww.y;
+      y.z = (v[i].z - mean) * rstd * ww.z; y.w = (v[i].w - mean) * rstd * ww.w;
+      if (br) { const float4 bb = br[c]; y.x += bb.x; y.y += bb.y; y.z += bb.z; y.w += bb.w; }
+      if (out_f32) reinterpret_cast<float4*>(out_f32 + static_cast<long long>(row) * C)[c] = y;
+      if (out_h) {
+        uint2 pk;
+        pk.x = pack2(y.x, y.y, h_dtype);
+        pk.y = pack2(y.z, y.w, h_dtype);
+        reinterpret_cast<uint2*>(static_cast<uint16_t*>(out_h) + static_cast<long long>(row) * ld_h)[c] = pk;
+      }
+    }
+  }
+}
+
+// RMSNorm backward: dres[row] += rstd * (w*dy) - x * rstd^3 * mean(w*dy*x)       (weights frozen: no dw)
+template <int MAXV>
+__global__ void __launch_bounds__(256) rmsnorm_bwd_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                          const float* __restrict__ dy, float eps, int rows, int C,
+                                                          float* __restrict__ dres) {
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const int nv = C >> 2;
+  const float4* xr = reinterpret_cast<const float4*>(x + static_cast<long long>(row) * C);
+  const float4* dr = reinterpret_cast<const float4*>(dy + static_cast<long long>(row) * C);
+  const float4* wr = reinterpret_cast<const float4*>(w);
+  float4 xv[MAXV], gv[MAXV];
+  float ss = 0.f, dot = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    const int c = lane + i * 32;
+    if (c < nv) {
+      xv[i] = xr[c];
+      const float4 d = dr[c], ww = wr[c];
+      gv[i] = make_float4(d.x * ww.x, d.y * ww.y, d.z * ww.z, d.w * ww.w);
+      ss += xv[i].x * xv[i].x + xv[i].y * xv[i].y + xv[i].z * xv[i].z + xv[i].w * xv[i].w;
+      dot += gv[i].x * xv[i].x + gv[i].y * xv[i].y + gv[i].z * xv[i].z + gv[i].w * xv[i].w;
+    }
+  }
+  const float rstd = rsqrtf(warp_sum(ss) / C + eps);
+  const float coef = warp_sum(dot) / C * rstd * rstd * rstd;
+  float4* out = reinterpret_cast<float4*>(dres + static_cast<long long>(row) * C);
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    const int c = lane + i * 32;
+    if (c < nv) {
+      float4 o = out[c];
+      o.x += gv[i].x * rstd - xv[i].x * coef; o.y += gv[i].y * rstd - xv[i].y * coef;
+      o.z += gv[i].z * rstd - xv[i].z * coef; o.w += gv[i].w * rstd - xv[i].w * coef;
+      out[c] = o;
+    }
+  }
+}
+
+// ---------------------------------------------------------------- ViT patch extraction (eva_vit.py:196-203)
+// frames fp32 [F,3,S,S] -> A [F*G*G, ldA] half with column k = c*P*P + i*P + j (the Conv2d weight's flattened
+// order); columns [3*P*P, ldA) are zero.  One thread per (patch, c, i): P contiguous pixels.
+__global__ void patchify_kernel(const float* __restrict__ img, void* __restrict__ out, int dtype, int F, int S, int P,
+                                int ldA) {
+  const int G = S / P;
+  const long long total = static_cast<long long>(F) * G * G * 3 * P;
+  const long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  if (idx >= total) return;
+  // fastest: patch column px (coalesced reads along an image row), then i, c, patch row, frame
+  const int px = idx % G;
+  long long r = idx / G;
+  const int i = r % P; r /= P;
+  const int c = r % 3; r /= 3;
+  const int py = r % G;
+  const int f = r / G;
+  const float* src = img + ((static_cast<long long>(f) * 3 + c) * S + (py * P + i)) * S + px * P;
+  uint16_t* dst = static_cast<uint16_t*>(out) + (static_cast<long long>(f) * G * G + py * G + px) * ldA + (c * P + i) * P;
+  for (int j = 0; j + 1 < P; j += 2) {
+    const float2 v = *reinterpret_cast<const float2*>(src + j);
+    *reinterpret_cast<uint32_t*>(dst + j) = pack2(v.x, v.y, dtype);
+  }
+  if (P & 1) dst[P - 1] = static_cast<uint16_t>(pack2(src[P - 1], 0.f, dtype) & 0xffff);
+  if (c == 2 && i == P - 1) {
+    for (int k = 3 * P * P; k < ldA; ++k) dst[k - (c * P + i) * P] = 0;
+  }
+}
+
+// x[f, 0, :] = cls + pos[0]   (eva_vit.py:328-331)
+__global__ void cls_pos_kernel(const float* __restrict__ cls, const float* __restrict__ pos, float* __restrict__ x,
+                               int F, int tokens, int C) {
+  const long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  if (idx >= static_cast<long long>(F) * C) return;
+  const int c = idx % C;
+  const int f = idx / C;
+  x[(static_cast<long long>(f) * tokens) * C + c] = cls[c] + pos[c];
+}
+
+// ---------------------------------------------------------------- gated GELU (modeling_t5.py:323-329)
+// ab [M, 2F] half (columns [0,F) = wi_0 x, [F,2F) = wi_1 x) -> h [M, ldh] half = gelu(a) * b
+__global__ void gated_gelu_fwd_kernel(const uint4* __restrict__ ab, uint4* __restrict__ h, int M, int F, long long ldh,
+                                      int dtype) {
+  const int fv = F >> 3;
+  const long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  if (idx >= static_cast<long long>(M) * fv) return;
+  const int c = idx % fv;
+  const long long m = idx / fv;
+  const uint4 a = ab[m * (2 * fv) + c], b = ab[m * (2 * fv) + fv + c];
+  const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, bw[4] = {b.x, b.y, b.z, b.w};
+  uint32_t o[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+    o[i] = pack2(gelu_erf(unpack_lo(aw[i], dtype)) * unpack_lo(bw[i], dtype),
+                 gelu_erf(unpack_hi(aw[i], dtype)) * unpack_hi(bw[i], dtype), dtype);
+  h[m * (ldh >> 3) + c] = make_uint4(o[0], o[1], o[2], o[3]);
+}
+// dab[:, :F] = dh * b * gelu'(a) ; dab[:, F:] = dh * gelu(a)
+__global__ void gated_gelu_bwd_kernel(const uint4* __restrict__ ab, const uint4* __restrict__ dh, long long lddh,
+                                      uint4* __restrict__ dab, int M, int F, int dtype) {
+  const int fv = F >> 3;
+  const long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  if (idx >= static_cast<long long>(M) * fv) return;
+  const int c = idx % fv;
+  const long long m = idx / fv;
+  const uint4 a = ab[m * (2 * fv) + c], b = ab[m * (2 * fv) + fv + c], d = dh[m * (lddh >> 3) + c];
+  const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, bw[4] = {b.x, b.y, b.z, b.w}, dw[4] = {d.x, d.y, d.z, d.w};
+  uint32_t oa[4], ob[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float a0 = unpack_lo(aw[i], dtype), a1 = unpack_hi(aw[i], dtype);
+    const float b0 = unpack_lo(bw[i], dtype), b1 = unpack_hi(bw[i], dtype);
+    const float d0 = unpack_lo(dw[i], dtype), d1 = unpack_hi(dw[i], dtype);
+    oa[i] = pack2(d0 * b0 * gelu_erf_grad(a0), d1 * b1 * gelu_erf_grad(a1), dtype);
+    ob[i] = pack2(d0 * gelu_erf(a0), d1 * gelu_erf(a1), dtype);
+  }
+  dab[m * (2 * fv) + c] = make_uint4(oa[0], oa[1], oa[2], oa[3]);
+  dab[m * (2 * fv) + fv + c] = make_uint4(ob[0], ob[1], ob[2], ob[3]);
+}
+
+// ---------------------------------------------------------------- interleave gather (blip2_mr.py:691-783)
+// out[r, :] (fp32) = table row:  idx >= 0 -> emb[idx] (fp32 embedding table)
+//                               idx <  0 and != INT_MIN -> frames[-(idx+1)] (fp32 frame tokens)
+//                               idx == INT_MIN -> zeros (left padding)
+__global__ void gather_rows_kernel(const int* __restrict__ idx, const float* __restrict__ emb,
+                                   const float* __restrict__ frames, float* __restrict__ out, int rows, int C) {
+  const int r = blockIdx.x;
+  if (r >= rows) return;
+  const int id = idx[r];
+  const float4* src = nullptr;
+  if (id >= 0) src = reinterpret_cast<const float4*>(emb + static_cast<long long>(id) * C);
+  else if (id != INT_MIN) src = reinterpret_cast<const float4*>(frames + static_cast<long long>(-(id + 1)) * C);
+  float4* dst = reinterpret_cast<float4*>(out + static_cast<long long>(r) * C);
+  for (int c = threadIdx.x; c < (C >> 2); c += blockDim.x) dst[c] = src ? src[c] : make_float4(0.f, 0.f, 0.f, 0.f);
+}
+// backward of the gather w.r.t. the frame tokens: dframes[-(idx+1)] = dout[r]  (each frame row appears once)
+__global__ void scatter_frames_kernel(const int* __restrict__ idx, const float* __restrict__ dout,
+                                      float* __restrict__ dframes, int rows, int C) {
+  const int r = blockIdx.x;
+  if (r >= rows) return;
+  const int id = idx[r];
+  if (id >= 0 || id == INT_MIN) return;
+  const float4* src = reinterpret_cast<const float4*>(dout + static_cast<long long>(r) * C);
+  float4* dst = reinterpret_cast<float4*>(dframes + static_cast<long long>(-(id + 1)) * C);
+  for (int c = threadIdx.x; c < (C >> 2); c += blockDim.x) dst[c] = src[c];
+}
+
+// mean over groups of n consecutive rows (frame_token_aggregation == "mean", blip2_mr.py:493-498)
+__global__ void group_mean_kernel(const float* __restrict__ x, float* __restrict__ out, int groups, int n, int C) {
+  const long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  if (idx >= static_cast<long long>(groups) * C) return;
+  const int c = idx % C;
+  const long long gidx = idx / C;
+  float s = 0.f;
+  for (int i = 0; i < n; ++i) s += x[(gidx * n + i) * C + c];
+  out[idx] = s / n;
+}
+__global__ void group_mean_bwd_kernel(const float* __restrict__ dout, float* __restrict__ dx, int groups, int n, int C) {
+  const long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  if (idx >= static_cast<long long>(groups) * n * C) return;
+  const int c = idx % C;
+  const long long row = idx / C;
+  dx[idx] = dout[(row / n) * C + c] / n;
+}
+
+// ---------------------------------------------------------------- cross entropy (modeling_t5.py:1872-1875)
+// logits fp32 [rows, V]; labels int64 (-100 = ignore).  loss_sum += -log p[label]; dlogits = (p - onehot) * gscale
+__global__ void __launch_bounds__(1024) ce_kernel(const float* __restrict__ logits, const long long* __restrict__ labels,
+                                                  int V, float* __restrict__ row_loss, void* __restrict__ dlogits,
+                                                  int d_dtype, long long ldd, float gscale) {
+  __shared__ float red[32];
+  __shared__ float bval;
+  const int row = blockIdx.x;
+  const float* lr = logits + static_cast<long long>(row) * V;
+  const long long lab = labels[row];
+  float mx = -INFINITY;
+  for (int c = threadIdx.x; c < V; c += blockDim.x) mx = fmaxf(mx, lr[c]);
+  mx = warp_max(mx);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = mx;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float v = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : -INFINITY;
+    v = warp_max(v);
+    if (threadIdx.x == 0) bval = v;
+  }
+  __syncthreads();
+  mx = bval;
+  float sm = 0.f;
+  for (int c = threadIdx.x; c < V; c += blockDim.x) sm += __expf(lr[c] - mx);
+  sm = warp_sum(sm);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = sm;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float v = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.f;
+    v = warp_sum(v);
+    if (threadIdx.x == 0) bval = v;
+  }
+  __syncthreads();
+  const float lse = mx + logf(bval);
+  if (threadIdx.x == 0) row_loss[row] = (lab >= 0) ? (lse - lr[lab]) : 0.f;
+  if (dlogits) {
+    uint16_t* dr = static_cast<uint16_t*>(dlogits) + static_cast<long long>(row) * ldd;
+    const float gs = (lab >= 0) ? gscale : 0.f;
+    for (int c = threadIdx.x * 2; c < V; c += blockDim.x * 2) {
+      float p0 = __expf(lr[c] - lse), p1 = (c + 1 < V) ? __expf(lr[c + 1] - lse) : 0.f;
+      if (c == lab) p0 -= 1.f;
+      if (c + 1 == lab) p1 -= 1.f;
+      *reinterpret_cast<uint32_t*>(dr + c) = pack2(p0 * gs, p1 * gs, d_dtype);
+    }
+  }
+}
+
+// ---------------------------------------------------------------- LoRA down-projection
+// xa[m, j] = sum_k x[m, k] * A[j, k], j < R (R <= 32), written (zero-padded to 32) at x[m, K .. K+32).
+// x is the [M, K+32] "extended" activation buffer consumed by the tcgen05 GEMM with [W | B | 0] weights.
+template <int R>
+__global__ void __launch_bounds__(256) lora_down_kernel(uint16_t* __restrict__ x, long long ldx, const float* __restrict__ A,
+                                                         int M, int K, int dtype) {
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= M) return;
+  uint16_t* xr = x + static_cast<long long>(row) * ldx;
+  float acc[R];
+#pragma unroll
+  for (int j = 0; j < R; ++j) acc[j] = 0.f;
+  for (int k = lane * 8; k < K; k += 256) {
+    const uint4 v = *reinterpret_cast<const uint4*>(xr + k);
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+    float xv[8];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { xv[2 * i] = unpack_lo(w[i], dtype); xv[2 * i + 1] = unpack_hi(w[i], dtype); }
+#pragma unroll
+    for (int j = 0; j < R; ++j) {
+      const float4 a0 = *reinterpret_cast<const float4*>(A + static_cast<long long>(j) * K + k);
+      const float4 a1 = *reinterpret_cast<const float4*>(A + static_cast<long long>(j) * K + k + 4);
+      acc[j] += xv[0] * a0.x + xv[1] * a0.y + xv[2] * a0.z + xv[3] * a0.w + xv[4] * a1.x + xv[5] * a1.y + xv[6] * a1.z + xv[7] * a1.w;
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < R; ++j) acc[j] = warp_sum(acc[j]);
+  float mine = 0.f;
+#pragma unroll
+  for (int j = 0; j < R; ++j) if (lane == j) mine = acc[j];
+  xr[K + lane] = static_cast<uint16_t>(pack2(mine, 0.f, dtype) & 0xffff);
+}
+
+// ---------------------------------------------------------------- skinny wgrad: out[c, r] (+)= sum_m P[m, c] * Q[m, r]
+// P half [M, C] (ldp), Q half [M, 8] (ldq): LoRA dB = dY^T xa, dA = dxa^T x (transposed store), fp32 atomics.
+__global__ void __launch_bounds__(256) skinny_wgrad_kernel(const uint16_t* __restrict__ P, long long ldp,
+                                                           const uint16_t* __restrict__ Q, long long ldq, int M, int C,
+                                                           float* __restrict__ out, int transposed_out, int dtype,
+                                                           int rows_per_block) {
+  __shared__ float red[4][64][9];
+  const int cx = threadIdx.x & 63, my = threadIdx.x >> 6;
+  const int c = blockIdx.x * 64 + cx;
+  const int m0 = blockIdx.y * rows_per_block, m1 = min(M, m0 + rows_per_block);
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  if (c < C) {
+    for (int m = m0 + my; m < m1; m += 4) {
+      const uint16_t pw = P[static_cast<long long>(m) * ldp + c];
+      const float pv = (dtype == MRB_DT_F16) ? __half2float(__ushort_as_half(pw)) : __uint_as_float(static_cast<uint32_t>(pw) << 16);
+      const uint4 qv = *reinterpret_cast<const uint4*>(Q + static_cast<long long>(m) * ldq);
+      const uint32_t w[4] = {qv.x, qv.y, qv.z, qv.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { acc[2 * i] += pv * unpack_lo(w[i], dtype); acc[2 * i + 1] += pv * unpack_hi(w[i], dtype); }
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < 8; ++r) red[my][cx][r] = acc[r];
+  __syncthreads();
+  if (my == 0 && c < C) {
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+      const float s = red[0][cx][r] + red[1][cx][r] + red[2][cx][r] + red[3][cx][r];
+      if (transposed_out) atomicAdd(out + static_cast<long long>(r) * C + c, s);
+      else atomicAdd(out + static_cast<long long>(c) * 8 + r, s);
+    }
+  }
+}
+
+// ---------------------------------------------------------------- casts / transpose / column sums
+__global__ void cast_f32_to_h_kernel(const float4* __restrict__ in, uint2* __restrict__ out, long long n4, int dtype) {
+  const long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  if (i >= n4) return;
+  const float4 v = in[i];
+  out[i] = make_uint2(pack2(v.x, v.y, dtype), pack2(v.z, v.w, dtype));
+}
+// 2D strided cast: out[r, c] = in[r, c] for c < cols (ld_in / ld_out element strides)
+__global__ void cast2d_f32_to_h_kernel(const float* __restrict__ in, long long ld_in, uint16_t* __restrict__ out,
+                                       long long ld_out, int rows, int cols, int dtype) {
+  const long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  const int cv = cols >> 1;
+  if (idx >= static_cast<long long>(rows) * cv) return;
+  const int c = (idx % cv) * 2;
+  const long long r = idx / cv;
+  const float2 v = *reinterpret_cast<const float2*>(in + r * ld_in + c);
+  *reinterpret_cast<uint32_t*>(out + r * ld_out + c) = pack2(v.x, v.y, dtype);
+}
+// out[c, r] = in[r, c]  (16-bit elements), 32x32 tiles through shared memory
+__global__ void transpose16_kernel(const uint16_t* __restrict__ in, long long ld_in, uint16_t* __restrict__ out,
+                                   long long ld_out, int rows, int cols) {
+  __shared__ uint16_t tile[32][34];
+  const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int r = r0 + i, c = c0 + threadIdx.x;
+    tile[i][threadIdx.x] = (r < rows && c < cols) ? in[static_cast<long long>(r) * ld_in + c] : 0;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int c = c0 + i, r = r0 + threadIdx.x;
+    if (c < cols && r < rows) out[static_cast<long long>(c) * ld_out + r] = tile[threadIdx.x][i];
+  }
+}
+// out[c] (+)= sum_r in[r, c]   (fp32), used for the t5_proj bias gradient
+__global__ void colsum_kernel(const float* __restrict__ in, int rows, int C, float* __restrict__ out, int rows_per_block) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const int r0 = blockIdx.y * rows_per_block, r1 = min(rows, r0 + rows_per_block);
+  float s = 0.f;
+  for (int r = r0; r < r1; ++r) s += in[static_cast<long long>(r) * C + c];
+  atomicAdd(out + c, s);
+}
+// y = a*x + b*y over fp32 vectors (grad accumulation / residual sums on the flat streams)
+__global__ void axpby_kernel(const float4* __restrict__ x, float4* __restrict__ y, long long n4, float a, float b) {
+  const long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  if (i >= n4) return;
+  const float4 xv = x[i];
+  float4 yv = y[i];
+  yv.x = a * xv.x + b * yv.x; yv.y = a * xv.y + b * yv.y; yv.z = a * xv.z + b * yv.z; yv.w = a * xv.w + b * yv.w;
+  y[i] = yv;
+}
+
+}  // namespace mrb
+
+using namespace mrb;
+#define STREAM static_cast<cudaStream_t>(stream)
+static inline unsigned blocks_for(long long n, int per) { return static_cast<unsigned>((n + per - 1) / per); }
+
+extern "C" int mrb_norm(const float* x, const float* add, const float* w, const float* bias, float eps, int rows, int C,
+                        int mode, float* out_f32, void* out_h, int h_dtype, long long ld_h, float* sum_out, void* stream) {
+  if (rows <= 0) return MRB_OK;
+  if ((C & 3) || C > 2048 || (out_h && (ld_h & 3))) return MRB_ERR_ARG;
+  const unsigned grid = blocks_for(rows, 8);
+  if (C <= 1024) norm_kernel<8><<<grid, 256, 0, STREAM>>>(x, add, w, bias, eps, rows, C, mode, out_f32, out_h, h_dtype, ld_h, sum_out);
+  else if (C <= 1536) norm_kernel<12><<<grid, 256, 0, STREAM>>>(x, add, w, bias, eps, rows, C, mode, out_f32, out_h, h_dtype, ld_h, sum_out);
+  else norm_kernel<16><<<grid, 256, 0, STREAM>>>(x, add, w, bias, eps, rows, C, mode, out_f32, out_h, h_dtype, ld_h, sum_out);
+  MRB_CHECK_LAUNCH();
+  return MRB_OK;
+}
+
+extern "C" int mrb_rmsnorm_bwd(const float* x, const float* w, const float* dy, float eps, int rows, int C, float* dres,
+                               void* stream) {
+  if (rows <= 0) return MRB_OK;
+  if ((C & 3) || C > 2048) return MRB_ERR_ARG;
+  rmsnorm_bwd_kernel<16><<<blocks_for(rows, 8), 256, 0, STREAM>>>(x, w, dy, eps, rows, C, dres);
+  MRB_CHECK_LAUNCH();
+  return MRB_OK;
+}
+
+extern "C" int mrb_patchify(const float* img, void* out, int dtype, int frames, int img_size, int patch, int ldA, void* stream) {
+  if (frames <= 0) return MRB_OK;
+  if (img_size % patch || (patch & 1) || ldA < 3 * patch * patch || (ldA & 7)) return MRB_ERR_ARG;
+  const int G = img_size / patch;
+  const long long total = static_cast<long long>(frames) * G * G * 3 * patch;
+  patchify_kernel<<<blocks_for(total, 256), 256, 0, STREAM>>>(img, out, dtype, frames, img_size, patch, ldA);
+  MRB_CHECK_LAUNCH();
+  return MRB_OK;
+}
+
+extern "C" int mrb_cls_pos(const float* cls, const float* pos, float* x, int frames, int tokens, int C, void* stream) {
+  if (frames <= 0) return MRB_OK;
+  cls_pos_kernel<<<blocks_for(static_cast<long long>(frames) * C, 256), 256, 0, STREAM>>>(cls, pos, x, frames, tokens, C);
+  MRB_CHECK_LAUNCH();
+  return MRB_OK;
+}
+
+extern "C" int mrb_gated_gelu_fwd(const void* ab, void* h, int M, int F, long long ldh, int dtype, void* stream) {
+  if (M <= 0) return MRB_OK;
+  if ((F & 7) || (ldh & 7)) return MRB_ERR_ARG;
+  gated_gelu_fwd_kernel<<<blocks_for(static_cast<long long>(M) * (F >> 3), 256), 256, 0, STREAM>>>(
+      static_cast<const uint4*>(ab), static_cast<uint4*>(h), M, F, ldh, dtype);
+  MRB_CHECK_LAUNCH();
+  return MRB_OK;
+}
+extern "C" int mrb_gated_gelu_bwd(const void* ab, const void* dh, long long lddh, void* dab, int M, int F, int dtype, void* stream) {
+  if (M <= 0) return MRB_OK;
+  if ((F & 7) || (lddh & 7)) return MRB_ERR_ARG;
+  gated_gelu_bwd_kernel<<<blocks_for(static_cast<long long>(M) * (F >> 3), 256), 256, 0, STREAM>>>(
+      static_cast<const uint4*>(ab), static_cast<const uint4*>(dh), lddh, static_cast<uint4*>(dab), M, F, dtype);
+  MRB_CHECK_LAUNCH();
+  return MRB_OK;
+}
+
+extern "C" int mrb_gather_rows(const int* idx, const float* emb, const float* frames, float* out, int rows, int C, void* stream) {
+  if (rows <= 0) return MRB_OK;
+  if (C & 3) return MRB_ERR_ARG;
+  gather_rows_kernel<<<rows, 256, 0, STREAM>>>(idx, emb, frames, out, rows, C);
+  MRB_CHECK_LAUNCH();
+  return MRB_OK;
+}
+extern "C" int mrb_scatter_frames(const int* idx, const float* dout, float* dframes, int rows, int C, void* stream) {
+  if (rows <= 0) return MRB_OK;
+  if (C & 3) return MRB_ERR_ARG;
+  scatter_frames_kernel<<<rows, 256, 0, STREAM>>>(idx, dout, dframes, rows, C);
+  MRB_CHECK_LAUNCH();
+  return MRB_OK;
+}
+extern "C" int mrb_group_mean(const float* x, float* out, int groups, int n, int C, void* stream) {
+  if (groups <= 0) return MRB_OK;
+  group_mean_kernel<<<blocks_for(static_cast<long long>(groups) * C, 256), 256, 0, STREAM>>>(x, out, groups, n, C);
+  MRB_CHECK_LAUNCH();
+  return MRB_OK;
+}
+extern "C" int mrb_group_mean_bwd(const float* dout, float* dx, int groups, int n, int C, void* stream) {
+  if (groups <= 0) return MRB_OK;
+  group_mean_bwd_kernel<<<blocks_for(static_cast<long long>(groups) * n * C, 256), 256, 0, STREAM>>>(dout, dx, groups, n, C);
+  MRB_CHECK_LAUNCH();
+  return MRB_OK;
+}
+
+extern "C" int mrb_cross_entropy(const float* logits, const long long* labels, int rows, int V, float* row_loss,
+                                 void* dlogits, int d_dtype, long long ldd, float gscale, void* stream) {
+  if (rows <= 0) return MRB_OK;
+  if (dlogits && (ldd & 1)) return MRB_ERR_ARG;
+  ce_kernel<<<rows, 1024, 0, STREAM>>>(logits, labels, V, row_loss, dlogits, d_dtype, ldd, gscale);
+  MRB_CHECK_LAUNCH();
+  return MRB_OK;
+}
+
+extern "C" int mrb_lora_down(void* x_ext, long long ldx, const float* A, int M, int K, int R, int dtype, void* stream) {
+  if (M <= 0) return MRB_OK;
+  if ((K & 255) || (ldx & 7) || ldx < K + 32) return MRB_ERR_ARG;
+  const unsigned grid = blocks_for(M, 8);
+  uint16_t* x = static_cast<uint16_t*>(x_ext);
+  switch (R) {
+    case 8: lora_down_kernel<8><<<grid, 256, 0, STREAM>>>(x, ldx, A, M, K, dtype); break;
+    case 16: lora_down_kernel<16><<<grid, 256, 0, STREAM>>>(x, ldx, A, M, K, dtype); break;
+    case 24: lora_down_kernel<24><<<grid, 256, 0, STREAM>>>(x, ldx, A, M, K, dtype); break;
+    default: return MRB_ERR_UNSUPPORTED;
+  }
+  MRB_CHECK_LAUNCH();
+  return MRB_OK;
+}
+
+extern "C" int mrb_skinny_wgrad(const void* P, long long ldp, const void* Q, long long ldq, int M, int C, float* out,
+                                int transposed_out, int dtype, void* stream) {
+  if (M <= 0 || C <= 0) return MRB_OK;
+  if (ldq & 7) return MRB_ERR_ARG;
+  const int rows_per_block = 512;
+  dim3 grid(blocks_for(C, 64), blocks_for(M, rows_per_block));
+  skinny_wgrad_kernel<<<grid, 256, 0, STREAM>>>(static_cast<const uint16_t*>(P), ldp, static_cast<const uint16_t*>(Q), ldq,
+                                                M, C, out, transposed_out, dtype, rows_per_block);
+  MRB_CHECK_LAUNCH();
+  return MRB_OK;
+}
+
+extern "C" int mrb_cast_f32_to_h(const float* in, void* out, long long n, int dtype, void* stream) {
+  if (n <= 0) return MRB_OK;
+  if (n & 3) return MRB_ERR_ARG;
+  cast_f32_to_h_kernel<<<blocks_for(n >> 2, 256), 256, 0, STREAM>>>(reinterpret_cast<const float4*>(in),
+                                                                    static_cast<uint2*>(out), n >> 2, dtype);
+  MRB_CHECK_LAUNCH();
+  return MRB_OK;
+}
+extern "C" int mrb_cast2d_f32_to_h(const float* in, long long ld_in, void* out, long long ld_out, int rows, int cols,
+                                   int dtype, void* stream) {
+  if (rows <= 0 || cols <= 0) return MRB_OK;
+  if ((cols & 1) || (ld_in & 1) || (ld_out & 1)) return MRB_ERR_ARG;
+  cast2d_f32_to_h_kernel<<<blocks_for(static_cast<long long>(rows) * (cols >> 1), 256), 256, 0, STREAM>>>(
+      in, ld_in, static_cast<uint16_t*>(out), ld_out, rows, cols, dtype);
+  MRB_CHECK_LAUNCH();
+  return MRB_OK;
+}
+extern "C" int mrb_transpose16(const void* in, long long ld_in, void* out, long long ld_out, int rows, int cols, void* stream) {
+  if (rows <= 0 || cols <= 0) return MRB_OK;
+  dim3 grid(blocks_for(cols, 32), blocks_for(rows, 32)), block(32, 8);
+  transpose16_kernel<<<grid, block, 0, STREAM>>>(static_cast<const uint16_t*>(in), ld_in, static_cast<uint16_t*>(out), ld_out, rows, cols);
+  MRB_CHECK_LAUNCH();
+  return MRB_OK;
+}
+extern "C" int mrb_colsum(const float* in, int rows, int C, float* out, void* stream) {
+  if (rows <= 0) return MRB_OK;
+  dim3 grid(blocks_for(C, 256), blocks_for(rows, 256));
+  colsum_kernel<<<grid, 256, 0, STREAM>>>(in, rows, C, out, 256);
+  MRB_CHECK_LAUNCH();
+  return MRB_OK;
+}
+extern "C" int mrb_axpby(const float* x, float* y, long long n, float a, float b, void* stream) {
+  if (n <= 0) return MRB_OK;
+  if (n & 3) return MRB_ERR_ARG;
+  axpby_kernel<<<blocks_for(n >> 2, 256), 256, 0, STREAM>>>(reinterpret_cast<const float4*>(x), reinterpret_cast<float4*>(y), n >> 2, a, b);
+  MRB_CHECK_LAUNCH();
+  return MRB_OK;
+}

@@ -1,0 +1,328 @@
+// tcgen05 GEMM for every dense contraction on the BLIP2_MR hot path (SURVEY.md §2c K1,K3,K5,K6,K8,
+// K10,K11,K14,K16,K17,K18 and the dgrad GEMMs of K19):
+//
+//     D[M,N] = epilogue( A[M,K] . B[N,K]^T )        A, B: fp16 or bf16, K-major (nn.Linear layout)
+//
+// Blackwell-native structure: persistent CTAs (one per SM), warp-specialised
+//   warp 0     TMA producer   (cp.async.bulk.tensor 2D, SWIZZLE_128B, 64-element K slabs)
+//   warp 1     MMA issuer     (single elected thread, tcgen05.mma cta_group::1 kind::f16, 128 x BN x 16)
+//   warps 2-5  epilogue       (tcgen05.ld 32x32b from TMEM -> bias / GELU / fp32 residual -> global)
+// with a STAGES-deep smem ring (full/empty mbarriers) and a double-buffered fp32 accumulator in TMEM
+// (tmem_full/tmem_empty mbarriers) so the epilogue of tile i overlaps the MMAs of tile i+1.
+#include "common.cuh"
+
+namespace mrb {
+
+struct GemmParams {
+  int M, N, K;
+  int m_tiles, n_tiles;
+  int dtype;            // A/B: MRB_DT_F16 / MRB_DT_BF16
+  // epilogue
+  const float* bias;    // [N] or null
+  int gelu;             // exact erf GELU after bias
+  const float* resid;   // fp32 [*, ldr] added after activation, or null (may alias out when out is fp32)
+  long long ldr;
+  void* out;
+  int out_dtype;        // MRB_DT_*
+  long long ldc;
+  int row_group;        // G > 0: patch-embed row remap  out_row = (m/G)*(G+1)+1+m%G, resid_row = 1+m%G
+};
+
+constexpr int BM = 128;
+constexpr int BK = 64;
+constexpr int GROUP_M = 16;   // m-tiles per L2 super-group
+
+template <int BN, int STAGES>
+struct GemmSmem {
+  static constexpr int A_BYTES = BM * BK * 2;
+  static constexpr int B_BYTES = BN * BK * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int BAR_OFFSET = STAGES * STAGE_BYTES;
+  static constexpr int TOTAL = BAR_OFFSET + (2 * STAGES + 4) * 8 + 16 + 1024;  // + alignment slack
+};
+
+__device__ __forceinline__ void tile_coords(int t, int m_tiles, int n_tiles, int& tm, int& tn) {
+  const int per_group = GROUP_M * n_tiles;
+  const int g = t / per_group;
+  const int r = t - g * per_group;
+  const int gm = min(GROUP_M, m_tiles - g * GROUP_M);
+  tm = g * GROUP_M + r % gm;
+  tn = r / gm;
+}
+
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(192, 1)
+gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
+  using S = GemmSmem<BN, STAGES>;
+  constexpr uint32_t TMEM_COLS = (2 * BN <= 256) ? 256 : 512;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + S::BAR_OFFSET);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full = empty_bar + STAGES;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int num_tiles = p.m_tiles * p.n_tiles;
+  const int k_blocks = (p.K + BK - 1) / BK;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tmem_full[s], 1);
+      mbar_init(&tmem_empty[s], 4);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_holder, TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_holder;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+        int tm, tn;
+        tile_coords(t, p.m_tiles, p.n_tiles, tm, tn);
+        for (int kb = 0; kb < k_blocks; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * S::STAGE_BYTES;
+          mbar_expect_tx(&full_bar[stage], S::STAGE_BYTES);
+          tma_load_2d(sa, &tmA, &full_bar[stage], kb * BK, tm * BM);
+          tma_load_2d(sa + S::A_BYTES, &tmB, &full_bar[stage], kb * BK, tn * BN);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    const uint32_t idesc = umma_idesc_f16(p.dtype == MRB_DT_BF16 ? 1 : 0, BM, BN);
+    int stage = 0;
+    uint32_t phase = 0;
+    int it = 0;
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
+      const int as = it & 1;
+      const uint32_t aphase = (it >> 1) & 1;
+      mbar_wait(&tmem_empty[as], aphase ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + as * BN;
+      for (int kb = 0; kb < k_blocks; ++kb) {
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after();
+        if (lane == 0) {
+          const uint32_t a_addr = smem_u32(smem + stage * S::STAGE_BYTES);
+          const uint32_t b_addr = a_addr + S::A_BYTES;
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) {
+            umma_f16(d_tmem, umma_desc_sw128(a_addr + k * 32), umma_desc_sw128(b_addr + k * 32), idesc,
+                     (kb > 0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);                    // frees the smem slot when the MMAs retire
+          if (kb == k_blocks - 1) umma_commit(&tmem_full[as]);  // accumulator complete -> epilogue
+        }
+        __syncwarp();
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else {
+    // ===================== epilogue warps =====================
+    const int quad = warp & 3;                 // TMEM lane quadrant this warp may read
+    const int row_in_tile = quad * 32 + lane;
+    int it = 0;
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
+      int tm, tn;
+      tile_coords(t, p.m_tiles, p.n_tiles, tm, tn);
+      const int as = it & 1;
+      const uint32_t aphase = (it >> 1) & 1;
+      mbar_wait(&tmem_full[as], aphase);
+      tc_fence_after();
+      const int m = tm * BM + row_in_tile;
+      const bool row_ok = m < p.M;
+      long long out_row = m, res_row = m;
+      if (p.row_group > 0) {
+        const int f = m / p.row_group, r = m - f * p.row_group;
+        out_row = static_cast<long long>(f) * (p.row_group + 1) + 1 + r;
+        res_row = 1 + r;
+      }
+      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + as * BN;
+#pragma unroll 1
+      for (int c = 0; c < BN; c += 32) {
+        const int n0 = tn * BN + c;
+        if (n0 >= p.N) break;                  // warp-uniform
+        uint32_t r[32];
+        tmem_ld_32x32b_x32(t_row + c, r);
+        tmem_ld_wait();
+        if (row_ok) {
+          float v[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+          const int ncols = min(32, p.N - n0);   // multiple of 8
+          if (p.bias) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (j < ncols) v[j] += __ldg(p.bias + n0 + j);
+          }
+          if (p.gelu) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
+          }
+          if (p.resid) {
+            const float4* rp = reinterpret_cast<const float4*>(p.resid + res_row * p.ldr + n0);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              if (j * 4 < ncols) {
+                const float4 x = rp[j];
+                v[4 * j] += x.x; v[4 * j + 1] += x.y; v[4 * j + 2] += x.z; v[4 * j + 3] += x.w;
+              }
+            }
+          }
+          if (p.out_dtype == MRB_DT_F32) {
+            float4* op = reinterpret_cast<float4*>(static_cast<float*>(p.out) + out_row * p.ldc + n0);
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              if (j * 4 < ncols) op[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+          } else {
+            uint4* op = reinterpret_cast<uint4*>(static_cast<uint16_t*>(p.out) + out_row * p.ldc + n0);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              if (j * 8 < ncols) {
+                uint4 w;
+                w.x = pack2(v[8 * j], v[8 * j + 1], p.out_dtype);
+                w.y = pack2(v[8 * j + 2], v[8 * j + 3], p.out_dtype);
+                w.z = pack2(v[8 * j + 4], v[8 * j + 5], p.out_dtype);
+                w.w = pack2(v[8 * j + 6], v[8 * j + 7], p.out_dtype);
+                op[j] = w;
+              }
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty[as]);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+// ---------------------------------------------------------------- host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(ptr);
+  }
+  return fn;
+}
+
+// 2D row-major [rows, cols] 16-bit tensor, box = 64 cols x box_rows, 128B swizzle
+static int make_tmap(CUtensorMap* map, const void* base, int dtype, long long rows, long long cols, long long ld,
+                     int box_rows) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) return MRB_ERR_CUDA;
+  cuuint64_t gdim[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
+  cuuint64_t gstr[1] = {static_cast<cuuint64_t>(ld) * 2};
+  cuuint32_t box[2] = {static_cast<cuuint32_t>(BK), static_cast<cuuint32_t>(box_rows)};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(map, dtype == MRB_DT_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2,
+                  const_cast<void*>(base), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? MRB_OK : MRB_ERR_CUDA;
+}
+
+static int g_num_sms = 0;
+
+template <int BN, int STAGES>
+static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, GemmParams& p, cudaStream_t stream) {
+  using S = GemmSmem<BN, STAGES>;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_tcgen05_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL);
+    if (e != cudaSuccess) return mrb_set_error(e);
+    configured = true;
+  }
+  p.n_tiles = (p.N + BN - 1) / BN;
+  const int tiles = p.m_tiles * p.n_tiles;
+  const int grid = tiles < g_num_sms ? tiles : g_num_sms;
+  gemm_tcgen05_kernel<BN, STAGES><<<grid, 192, S::TOTAL, stream>>>(tmA, tmB, p);
+  MRB_CHECK_LAUNCH();
+  return MRB_OK;
+}
+
+}  // namespace mrb
+
+using namespace mrb;
+
+// Pick the N tile: minimise padded columns, prefer the widest tile on ties (fewer A re-reads).
+static int pick_bn(int N) {
+  const int cand[3] = {256, 192, 128};
+  int best = 256;
+  long long best_cost = -1;
+  for (int i = 0; i < 3; ++i) {
+    const int bn = cand[i];
+    const long long padded = static_cast<long long>((N + bn - 1) / bn) * bn;
+    // 128-wide tiles run the MMA at the smem-bandwidth limit: charge them 10 %
+    const long long cost = padded * (bn == 128 ? 110 : 100);
+    if (best_cost < 0 || cost < best_cost) { best_cost = cost; best = bn; }
+  }
+  return best;
+}
+
+extern "C" int mrb_gemm(const void* A, long long lda, const void* B, long long ldb, int M, int N, int K, int dtype,
+                        const float* bias, int gelu, const float* resid, long long ldr, void* out, int out_dtype,
+                        long long ldc, int row_group, int force_bn, void* stream) {
+  if (M <= 0 || N <= 0 || K <= 0) return MRB_OK;
+  if ((dtype != MRB_DT_F16 && dtype != MRB_DT_BF16) || (N & 7) || (lda & 7) || (ldb & 7) || (K & 7)) return MRB_ERR_ARG;
+  if ((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(B) | reinterpret_cast<uintptr_t>(out)) & 15) return MRB_ERR_ARG;
+  if (out_dtype == MRB_DT_F32 ? (ldc & 3) : (ldc & 7)) return MRB_ERR_ARG;
+  if (resid && ((ldr & 3) || (reinterpret_cast<uintptr_t>(resid) & 15))) return MRB_ERR_ARG;
+  if (g_num_sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+  }
+  const int bn = force_bn ? force_bn : pick_bn(N);
+  CUtensorMap tmA, tmB;
+  int rc = make_tmap(&tmA, A, dtype, M, K, lda, BM);
+  if (rc) return rc;
+  rc = make_tmap(&tmB, B, dtype, N, K, ldb, bn);
+  if (rc) return rc;
+  GemmParams p;
+  p.M = M; p.N = N; p.K = K;
+  p.m_tiles = (M + BM - 1) / BM;
+  p.n_tiles = 0;
+  p.dtype = dtype;
+  p.bias = bias; p.gelu = gelu; p.resid = resid; p.ldr = ldr;
+  p.out = out; p.out_dtype = out_dtype; p.ldc = ldc; p.row_group = row_group;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  switch (bn) {
+    case 256: return launch_gemm<256, 4>(tmA, tmB, p, s);
+    case 192: return launch_gemm<192, 5>(tmA, tmB, p, s);
+    case 128: return launch_gemm<128, 6>(tmA, tmB, p, s);
+    default: return MRB_ERR_ARG;
+  }
+}

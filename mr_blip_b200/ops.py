@@ -1,0 +1,168 @@
+"""Torch-tensor front end of the C ABI: checks devices/dtypes/contiguity, passes raw device pointers
+and the current CUDA stream.  PyTorch here is plumbing only (allocation, streams); all arithmetic on
+the hot path happens inside libmrblip_b200.so."""
+import torch
+
+from . import _lib
+
+F16, BF16, F32 = 0, 1, 2
+_DT = {torch.float16: F16, torch.bfloat16: BF16, torch.float32: F32}
+INT_MIN = -2 ** 31
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t):
+    return 0 if t is None else t.data_ptr()
+
+
+def _check(t, *dtypes):
+    assert t.is_cuda, "hot-path tensors must live on the GPU (no CPU fallback)"
+    if dtypes:
+        assert t.dtype in dtypes, (t.dtype, dtypes)
+    return t
+
+
+def gemm(a, b, out=None, bias=None, gelu=False, resid=None, out_dtype=None, row_group=0, out_rows=None, force_bn=0,
+         M=None, K=None):
+    """out = epi(a[M,K] @ b[N,K]^T).  a/b fp16 or bf16 2-D (row stride >= K, unit column stride)."""
+    _check(a, torch.float16, torch.bfloat16)
+    _check(b, a.dtype)
+    assert a.stride(1) == 1 and b.stride(1) == 1
+    M = a.shape[0] if M is None else M
+    K = a.shape[1] if K is None else K
+    N = b.shape[0]
+    assert b.shape[1] >= K or b.shape[1] == K, (a.shape, b.shape)
+    if out is None:
+        out_dtype = out_dtype or a.dtype
+        out = torch.empty((out_rows or M, N), dtype=out_dtype, device=a.device)
+    assert out.stride(1) == 1
+    if bias is not None:
+        _check(bias, torch.float32)
+    if resid is not None:
+        _check(resid, torch.float32)
+        assert resid.stride(1) == 1
+    _lib.call("mrb_gemm", a.data_ptr(), a.stride(0), b.data_ptr(), b.stride(0), M, N, K, _DT[a.dtype], _ptr(bias),
+              int(gelu), _ptr(resid), resid.stride(0) if resid is not None else 0, out.data_ptr(), _DT[out.dtype],
+              out.stride(0), row_group, force_bn, _stream())
+    return out
+
+
+def attention_fwd(q, k, v, out, B, H, Lq, Lk, hd, scale, q_strides, k_strides, v_strides, o_strides, bias=None,
+                  bias_zero=0, kmask=None, causal=False, q_pos0=0, lse=None):
+    """q/k/v/out: tensors whose data_ptr is row 0 / head 0; *_strides = (batch stride, row stride) in elements."""
+    _check(q, torch.float16, torch.bfloat16)
+    if kmask is not None:
+        _check(kmask, torch.int32)
+    _lib.call("mrb_attention_fwd", q.data_ptr(), q_strides[0], q_strides[1], k.data_ptr(), k_strides[0], k_strides[1],
+              v.data_ptr(), v_strides[0], v_strides[1], out.data_ptr(), o_strides[0], o_strides[1], B, H, Lq, Lk, hd,
+              _DT[q.dtype], float(scale), _ptr(bias), bias.shape[1] if bias is not None else 0, bias_zero, _ptr(kmask),
+              int(causal), q_pos0, _ptr(lse), _stream())
+    return out
+
+
+def attention_bwd(q, k, v, o, dout, dq, dk, dv, B, H, Lq, Lk, hd, scale, q_strides, k_strides, v_strides, o_strides,
+                  do_strides, lse, delta_ws, bias=None, bias_zero=0, kmask=None, causal=False, q_pos0=0):
+    _lib.call("mrb_attention_bwd", q.data_ptr(), q_strides[0], q_strides[1], k.data_ptr(), k_strides[0], k_strides[1],
+              v.data_ptr(), v_strides[0], v_strides[1], o.data_ptr(), o_strides[0], o_strides[1], dout.data_ptr(),
+              do_strides[0], do_strides[1], dq.data_ptr(), dk.data_ptr(), dv.data_ptr(), B, H, Lq, Lk, hd, _DT[q.dtype],
+              float(scale), _ptr(bias), bias.shape[1] if bias is not None else 0, bias_zero, _ptr(kmask), int(causal),
+              q_pos0, lse.data_ptr(), delta_ws.data_ptr(), _stream())
+
+
+def norm(x, w, bias, eps, mode, add=None, out_f32=None, out_h=None, sum_out=None, ld_h=None):
+    """mode 0 LayerNorm / 1 RMSNorm over the last dim of fp32 x [rows, C] (+ add)."""
+    _check(x, torch.float32)
+    rows, C = x.shape
+    assert x.is_contiguous()
+    _lib.call("mrb_norm", x.data_ptr(), _ptr(add), w.data_ptr(), _ptr(bias), float(eps), rows, C, mode, _ptr(out_f32),
+              _ptr(out_h), _DT[out_h.dtype] if out_h is not None else 0,
+              (ld_h if ld_h is not None else (out_h.stride(0) if out_h is not None else 0)), _ptr(sum_out), _stream())
+
+
+def rmsnorm_bwd(x, w, dy, eps, dres):
+    rows, C = x.shape
+    assert dy.is_contiguous() and dres.is_contiguous() and dy.dtype == torch.float32
+    _lib.call("mrb_rmsnorm_bwd", x.data_ptr(), w.data_ptr(), dy.data_ptr(), float(eps), rows, C, dres.data_ptr(), _stream())
+
+
+def patchify(img, out, img_size, patch):
+    _check(img, torch.float32)
+    assert img.is_contiguous()
+    _lib.call("mrb_patchify", img.data_ptr(), out.data_ptr(), _DT[out.dtype], img.shape[0], img_size, patch,
+              out.stride(0), _stream())
+
+
+def cls_pos(cls, pos, x, frames, tokens, C):
+    _lib.call("mrb_cls_pos", cls.data_ptr(), pos.data_ptr(), x.data_ptr(), frames, tokens, C, _stream())
+
+
+def gated_gelu_fwd(ab, h, M, F):
+    _lib.call("mrb_gated_gelu_fwd", ab.data_ptr(), h.data_ptr(), M, F, h.stride(0), _DT[ab.dtype], _stream())
+
+
+def gated_gelu_bwd(ab, dh, dab, M, F):
+    _lib.call("mrb_gated_gelu_bwd", ab.data_ptr(), dh.data_ptr(), dh.stride(0), dab.data_ptr(), M, F, _DT[ab.dtype], _stream())
+
+
+def gather_rows(idx, emb, frames, out):
+    _check(idx, torch.int32)
+    rows, C = out.shape
+    _lib.call("mrb_gather_rows", idx.data_ptr(), emb.data_ptr(), _ptr(frames), out.data_ptr(), rows, C, _stream())
+
+
+def scatter_frames(idx, dout, dframes):
+    rows, C = dout.shape
+    _lib.call("mrb_scatter_frames", idx.data_ptr(), dout.data_ptr(), dframes.data_ptr(), rows, C, _stream())
+
+
+def group_mean(x, out, groups, n, C):
+    _lib.call("mrb_group_mean", x.data_ptr(), out.data_ptr(), groups, n, C, _stream())
+
+
+def group_mean_bwd(dout, dx, groups, n, C):
+    _lib.call("mrb_group_mean_bwd", dout.data_ptr(), dx.data_ptr(), groups, n, C, _stream())
+
+
+def cross_entropy(logits, labels, row_loss, dlogits=None, gscale=1.0):
+    _check(logits, torch.float32)
+    _check(labels, torch.int64)
+    rows, V = logits.shape
+    assert logits.is_contiguous()
+    _lib.call("mrb_cross_entropy", logits.data_ptr(), labels.data_ptr(), rows, V, row_loss.data_ptr(), _ptr(dlogits),
+              _DT[dlogits.dtype] if dlogits is not None else 0, dlogits.stride(0) if dlogits is not None else 0,
+              float(gscale), _stream())
+
+
+def lora_down(x_ext, A, M, K, R):
+    _check(A, torch.float32)
+    _lib.call("mrb_lora_down", x_ext.data_ptr(), x_ext.stride(0), A.data_ptr(), M, K, R, _DT[x_ext.dtype], _stream())
+
+
+def skinny_wgrad(P, ldp, Q, ldq, M, C, out, transposed_out, dtype):
+    _lib.call("mrb_skinny_wgrad", P, ldp, Q, ldq, M, C, out.data_ptr(), int(transposed_out), dtype, _stream())
+
+
+def cast_to(x, out):
+    assert x.is_contiguous() and out.is_contiguous()
+    _lib.call("mrb_cast_f32_to_h", x.data_ptr(), out.data_ptr(), x.numel(), _DT[out.dtype], _stream())
+    return out
+
+
+def cast2d(x, out, rows, cols):
+    _lib.call("mrb_cast2d_f32_to_h", x.data_ptr(), x.stride(0), out.data_ptr(), out.stride(0), rows, cols, _DT[out.dtype], _stream())
+
+
+def transpose16(x, out, rows, cols):
+    _lib.call("mrb_transpose16", x.data_ptr(), x.stride(0), out.data_ptr(), out.stride(0), rows, cols, _stream())
+
+
+def colsum(x, out):
+    rows, C = x.shape
+    _lib.call("mrb_colsum", x.data_ptr(), rows, C, out.data_ptr(), _stream())
+
+
+def axpby(x, y, a, b):
+    _lib.call("mrb_axpby", x.data_ptr(), y.data_ptr(), x.numel(), float(a), float(b), _stream())
