@@ -30,11 +30,12 @@ int mrb_gemm(const void* A, long long lda, const void* B, long long ldb, int M, 
              int row_group, int force_bn, void* stream);
 
 /* softmax(scale * Q K^T + bias[h, j - i] + mask) V, scores never written to HBM; optional log-sum-exp for backward.
+ * kv_div > 1: query batch b reads K/V/mask batch b / kv_div (beams sharing one encoder output).
  * Replaces eva_vit.py:128-145, Qformer.py:198-268, modeling_t5.py:561-610. */
 int mrb_attention_fwd(const void* q, long long q_bs, long long q_rs, const void* k, long long k_bs, long long k_rs,
                       const void* v, long long v_bs, long long v_rs, void* o, long long o_bs, long long o_rs,
                       int B, int H, int Lq, int Lk, int hd, int dtype, float scale, const float* bias, int bias_len,
-                      int bias_zero, const int* kmask, int causal, int q_pos0, float* lse, void* stream);
+                      int bias_zero, const int* kmask, int kv_div, int causal, int q_pos0, float* lse, void* stream);
 /* dQ, dK, dV of the above (autograd of modeling_t5.py:561-610); hd <= 64. delta_ws: fp32 [B*H*Lq] workspace. */
 int mrb_attention_bwd(const void* q, long long q_bs, long long q_rs, const void* k, long long k_bs, long long k_rs,
                       const void* v, long long v_bs, long long v_rs, const void* o, long long o_bs, long long o_rs,
@@ -47,8 +48,10 @@ int mrb_attention_bwd(const void* q, long long q_bs, long long q_rs, const void*
  * mode 1: T5 RMSNorm (modeling_t5.py:263-277).  fp32 in; optional fp32 out, 16-bit out (ld_h), and x+add out. */
 int mrb_norm(const float* x, const float* add, const float* w, const float* bias, float eps, int rows, int C, int mode,
              float* out_f32, void* out_h, int h_dtype, long long ld_h, float* sum_out, void* stream);
-/* dres += d/dx RMSNorm(x; w) . dy   (autograd of modeling_t5.py:263-277, weights frozen) */
-int mrb_rmsnorm_bwd(const float* x, const float* w, const float* dy, float eps, int rows, int C, float* dres, void* stream);
+/* dres += d/dx RMSNorm(x; w) . dy   (autograd of modeling_t5.py:263-277, weights frozen).  dy fp32 or 16-bit with row
+ * stride ld_dy; with lora_A != NULL, dy is an extended dgrad buffer [rows, C+32] and dy += dy[:, C:C+R] . A first. */
+int mrb_rmsnorm_bwd(const float* x, const float* w, const void* dy, int dy_dtype, long long ld_dy, const float* lora_A,
+                    int R, float eps, int rows, int C, float* dres, void* stream);
 
 /* frames fp32 [F,3,S,S] -> patch matrix [F*(S/P)^2, ldA] (16-bit), zero padded: A operand of the patch-embed GEMM
  * (eva_vit.py:196-203). */
@@ -70,10 +73,12 @@ int mrb_group_mean_bwd(const float* dout, float* dx, int groups, int n, int C, v
 
 /* CrossEntropyLoss(ignore_index=-100) rows + d(logits) (modeling_t5.py:1872-1875) */
 int mrb_cross_entropy(const float* logits, const long long* labels, int rows, int V, float* row_loss, void* dlogits,
-                      int d_dtype, long long ldd, float gscale, void* stream);
+                      int d_dtype, long long ldd, float gscale, float* loss_sum, void* stream);
 
 /* LoRA (peft lora.Linear, configured at blip2_mr.py:193-200): x_ext[:, K:K+32] = x_ext[:, :K] . A^T (R = 8/16/24 rows) */
 int mrb_lora_down(void* x_ext, long long ldx, const float* A, int M, int K, int R, int dtype, void* stream);
+/* LoRA input gradient: x_ext[:, :K] += x_ext[:, K:K+R] . A (in place), or acc[M,K] (fp32) += that sum when acc != NULL */
+int mrb_lora_up_add(void* x_ext, long long ldx, const float* A, int R, int M, int K, int dtype, float* acc, void* stream);
 /* out[C,8] (or [8,C] when transposed_out) += P[M,C]^T . Q[M,8]: LoRA A/B weight gradients */
 int mrb_skinny_wgrad(const void* P, long long ldp, const void* Q, long long ldq, int M, int C, float* out,
                      int transposed_out, int dtype, void* stream);

@@ -12,11 +12,12 @@ _p, _ll, _i, _f = ctypes.c_void_p, ctypes.c_longlong, ctypes.c_int, ctypes.c_flo
 SIGNATURES = {
     "mrb_gemm": [_p, _ll, _p, _ll, _i, _i, _i, _i, _p, _i, _p, _ll, _p, _i, _ll, _i, _i, _p],
     "mrb_attention_fwd": [_p, _ll, _ll, _p, _ll, _ll, _p, _ll, _ll, _p, _ll, _ll, _i, _i, _i, _i, _i, _i, _f, _p, _i, _i,
-                          _p, _i, _i, _p, _p],
+                          _p, _i, _i, _i, _p, _p],
     "mrb_attention_bwd": [_p, _ll, _ll, _p, _ll, _ll, _p, _ll, _ll, _p, _ll, _ll, _p, _ll, _ll, _p, _p, _p,
                           _i, _i, _i, _i, _i, _i, _f, _p, _i, _i, _p, _i, _i, _p, _p, _p],
     "mrb_norm": [_p, _p, _p, _p, _f, _i, _i, _i, _p, _p, _i, _ll, _p, _p],
-    "mrb_rmsnorm_bwd": [_p, _p, _p, _f, _i, _i, _p, _p],
+    "mrb_rmsnorm_bwd": [_p, _p, _p, _i, _ll, _p, _i, _f, _i, _i, _p, _p],
+    "mrb_lora_up_add": [_p, _ll, _p, _i, _i, _i, _i, _p, _p],
     "mrb_patchify": [_p, _p, _i, _i, _i, _i, _i, _p],
     "mrb_cls_pos": [_p, _p, _p, _i, _i, _i, _p],
     "mrb_gated_gelu_fwd": [_p, _p, _i, _i, _ll, _i, _p],
@@ -25,7 +26,7 @@ SIGNATURES = {
     "mrb_scatter_frames": [_p, _p, _p, _i, _i, _p],
     "mrb_group_mean": [_p, _p, _i, _i, _i, _p],
     "mrb_group_mean_bwd": [_p, _p, _i, _i, _i, _p],
-    "mrb_cross_entropy": [_p, _p, _i, _i, _p, _p, _i, _ll, _f, _p],
+    "mrb_cross_entropy": [_p, _p, _i, _i, _p, _p, _i, _ll, _f, _p, _p],
     "mrb_lora_down": [_p, _ll, _p, _i, _i, _i, _i, _p],
     "mrb_skinny_wgrad": [_p, _ll, _p, _ll, _i, _i, _p, _i, _i, _p],
     "mrb_cast_f32_to_h": [_p, _p, _ll, _i, _p],

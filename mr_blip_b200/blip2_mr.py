@@ -1,0 +1,350 @@
+"""BLIP2_MR (Mr. BLIP / Chrono) behind the LAVIS model surface, computed by the sm_100a kernels.
+
+Drop-in for lavis/models/blip2_mr_models/blip2_mr.py: registry name "blip2_mr", from_config keys
+(:1420-1464), forward(samples) -> {"loss"} (:300-307, :433-570), generate(samples, ...) -> dict
+(:826-946), attribute / state-dict names (visual_encoder.*, ln_vision.*, Qformer.bert.*,
+query_tokens, t5_proj.*, t5_model.base_model.model.* with peft-style lora_A/lora_B.default keys).
+
+forward() in training mode runs forward AND backward kernels in one sweep and returns a loss whose
+autograd node hands the finished gradients to .backward() (so GradScaler, DDP reducer hooks and
+gradient accumulation in lavis/tasks/base_task.py:66-68,157-248 work unchanged).
+There is no CPU or eager-PyTorch fallback: without a CUDA device / built extension, forward raises.
+"""
+import logging
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from . import ops, mr_utils
+from .base_model import BaseModel, attach, disabled_train
+from .dims import Dims, FULL, T5_PREFIX, init_state_dict
+from .registry import registry
+from .t5 import T5Engine
+from .tokenizer import load_t5_tokenizer
+from .vision import VitEngine, QFormerEngine
+
+INT_MIN = -2 ** 31
+
+
+class _HandOverGrads(torch.autograd.Function):
+    """loss = f(params) where df/dparams was already computed by the backward kernels."""
+
+    @staticmethod
+    def forward(ctx, loss, n, *params_and_grads):
+        ctx.grads = params_and_grads[n:]
+        return loss.clone()
+
+    @staticmethod
+    def backward(ctx, g):
+        return (None, None) + tuple(None if gr is None else gr * g for gr in ctx.grads) + (None,) * len(ctx.grads)
+
+
+class Blip2Base(BaseModel):
+    """blip2.py:27-119 surface (builders are replaced by the seeded / checkpoint-loaded parameter tree)."""
+
+
+@registry.register_model("blip2_mr")
+class BLIP2_MR(Blip2Base):
+    PRETRAINED_MODEL_CONFIG_DICT = {
+        "pretrain_flant5xl": "configs/models/blip2/blip2_pretrain_flant5xl.yaml",
+    }
+
+    def __init__(self, img_size=224, drop_path_rate=0, use_grad_checkpoint=False, vit_precision="fp16",
+                 freeze_vit=True, num_query_token=32, t5_model="google/flan-t5-xl", num_beams=5, prompt="",
+                 max_txt_len=200, apply_lemmatizer=False, input_time_format="seconds_integers",
+                 interleave_data=True, frame_token_aggregation=None, task="qformer_freeze_lora",
+                 num_frames_for_answer=4, resample_frames=False, dims: Dims = None, init_seed=1234,
+                 lora_b_std=0.0, state_dict=None, tokenizer=None):
+        super().__init__()
+        self.dims = d = dims or FULL
+        assert img_size == d.img_size and num_query_token == d.num_query
+        if "QA" in task:
+            raise NotImplementedError("the NExT-QA/GQA branch (blip2_mr.py:309-431) is outside the hot path (SURVEY.md §2 row 21)")
+        if "lora" not in task:
+            raise NotImplementedError("only LoRA tasks are implemented (every mr_BLIP yaml uses qformer_freeze_lora)")
+        if not interleave_data:
+            raise NotImplementedError("non-interleaved prompt design is not used by any mr_BLIP recipe")
+        self.task = task
+        self.use_lora = True
+        self.post_process = mr_utils.post_process
+        self.input_time_format = input_time_format
+        self.interleave_data = interleave_data
+        self.frame_token_aggregation = frame_token_aggregation
+        self.num_query_token = num_query_token
+        self.max_txt_len = max_txt_len
+        self.num_beams = num_beams
+        self.vit_precision = vit_precision
+
+        # ---- parameters under the reference's names ------------------------------------------------
+        sd = state_dict if state_dict is not None else init_state_dict(d, seed=init_seed, lora_b_std=lora_b_std)
+        shared = None
+        for name, t in sd.items():
+            if name == "query_tokens":
+                attach(self, name, t.clone(), requires_grad="qformer_freeze" not in task)
+                continue
+            if name.startswith(T5_PREFIX) and name.endswith("embed_tokens.weight"):
+                continue                                     # tied to shared.weight below
+            train = ("lora_A" in name or "lora_B" in name or name.startswith("t5_proj.")
+                     or (name.startswith("Qformer.") and "qformer_freeze" not in task))
+            t = t.clone()
+            if name.startswith("visual_encoder.") and vit_precision == "fp16" and t.ndim >= 2 and "pos_embed" not in name \
+                    and "cls_token" not in name:
+                t = t.half()                                 # convert_weights_to_fp16, eva_vit.py:397-412
+            if name.startswith("visual_encoder.") and name.endswith((".fc1.bias", ".fc2.bias", ".proj.bias")) \
+                    and vit_precision == "fp16":
+                t = t.half()
+            p = attach(self, name, t, requires_grad=train and t.is_floating_point())
+            if name == T5_PREFIX + "shared.weight":
+                shared = p
+        for side in ("encoder", "decoder"):                  # HF ties embed_tokens to shared
+            attach(self, T5_PREFIX + side + ".embed_tokens.weight", shared)
+        if freeze_vit:
+            self.visual_encoder.eval()
+            self.visual_encoder.train = disabled_train.__get__(self.visual_encoder)
+            logging.info("freeze vision encoder")
+
+        # ---- tokenizer + number-token hygiene (blip2_mr.py:143,165-168) ----------------------------
+        self.t5_tokenizer = tokenizer or load_t5_tokenizer(t5_model)
+        self.annoying_numbers, _ = mr_utils.find_annoying_numbers(self.t5_tokenizer, 200)
+        self.annoying_numbers_replacement_dict = mr_utils.find_annoying_numbers_replacement_dict(self.annoying_numbers)
+        self.seperator_token = self.t5_tokenizer.convert_tokens_to_ids(">")
+        self.pad_token_id = self.t5_tokenizer.pad_token_id
+        self._engines = None
+        self._lora_versions = None
+
+    # ---------------------------------------------------------------------------------------------
+    @classmethod
+    def from_config(cls, cfg):
+        """Same keys as blip2_mr.py:1420-1464.  `pretrained` / `finetuned` are loaded when they are local files;
+        otherwise the seeded synthetic weights stay (no network in this environment)."""
+        get = cfg.get
+        model = cls(img_size=get("image_size", 224), drop_path_rate=get("drop_path_rate", 0),
+                    use_grad_checkpoint=get("use_grad_checkpoint", False), vit_precision=get("vit_precision", "fp16"),
+                    freeze_vit=get("freeze_vit", True), num_query_token=get("num_query_token", 32),
+                    t5_model=get("t5_model", "google/flan-t5-xl"), num_beams=get("num_beams", 5), prompt=get("prompt", ""),
+                    max_txt_len=get("max_len", 200), apply_lemmatizer=get("apply_lemmatizer", False),
+                    input_time_format=get("input_time_format", "seconds_integers"),
+                    interleave_data=get("interleave_data", True), frame_token_aggregation=get("frame_token_aggregation", None),
+                    task=get("task", "qformer_freeze_lora"), num_frames_for_answer=get("num_frames_for_answer", 4),
+                    resample_frames=get("resample_frames", False), dims=get("dims", None),
+                    init_seed=get("init_seed", 1234), lora_b_std=get("lora_b_std", 0.0))
+        model.load_checkpoint_from_config(cfg)
+        return model
+
+    def load_checkpoint_from_config(self, cfg, **kwargs):
+        """blip2_mr.py:1466-1495: pretrained BLIP-2 weights, then the finetuned LoRA adapter (local files only)."""
+        import os
+        for key in ("pretrained", "finetuned") if cfg.get("load_finetuned", True) else ("pretrained",):
+            path = cfg.get(key, None)
+            if path and os.path.isfile(path):
+                self.load_checkpoint(path)
+            elif path:
+                logging.warning("%s checkpoint %s is not a local file; keeping seeded weights", key, path)
+
+    def _weights_changed(self):
+        self._engines = None
+
+    # ---------------------------------------------------------------------------------------------
+    def _get(self, name):
+        obj = self
+        for p in name.split("."):
+            obj = obj._modules[p] if p in obj._modules else obj._parameters[p]
+        return obj
+
+    def engines(self):
+        if self._engines is None:
+            if not torch.cuda.is_available() or self.device.type != "cuda":
+                raise RuntimeError("BLIP2_MR runs only on a CUDA device through libmrblip_b200.so "
+                                   "(no CPU / eager fallback); move the model with .cuda()")
+            d = self.dims
+            self._engines = (VitEngine(d, self._get), QFormerEngine(d, self._get), T5Engine(d, self._get))
+            self._lora_versions = None
+        vit, qf, t5 = self._engines
+        vers = tuple(p._version for g in t5.groups for p in g.A_params + g.B_params)
+        vers += (self.t5_proj.weight._version, self.t5_proj.bias._version)
+        if vers != self._lora_versions:                      # optimizer.step() happened: re-pack the trainable bits
+            t5.refresh()
+            qf.set_t5_proj(self.t5_proj.weight, self.t5_proj.bias)
+            self._lora_versions = vers
+        return vit, qf, t5
+
+    # ---------------------------------------------------------------------------------------------
+    def get_frame_embeddings_and_attentions(self, image, want_aux=False):
+        """blip2_mr.py:948-988: ViT -> ln_vision -> Q-Former -> t5_proj (-> mean).  image [b,t,3,H,W].
+        -> frames_for_t5 fp32 [b, t*n, 2048], ones [b, t*n]."""
+        vit, qf, _ = self.engines()
+        if isinstance(image, list):
+            image = torch.stack(image)
+        b, t = image.shape[:2]
+        img = image.reshape(b * t, *image.shape[2:]).to(device="cuda", dtype=torch.float32, non_blocking=True)
+        x = vit.forward(img)
+        h, h16 = qf.forward(x, b * t)
+        f = qf.project(h16)
+        n = self.dims.num_query
+        if self.frame_token_aggregation:
+            assert self.frame_token_aggregation in ["mean"], "Invalid aggregation method, please choose from ['mean']"
+            agg = torch.empty((b * t, self.dims.d_model), dtype=torch.float32, device="cuda")
+            ops.group_mean(f, agg, b * t, n, self.dims.d_model)
+            f, n = agg, 1
+        atts = torch.ones((b, t * n), dtype=torch.long, device="cuda")
+        if want_aux:
+            return f.view(b, t * n, -1), atts, (h, h16)
+        return f.view(b, t * n, -1), atts
+
+    def _timestamps(self, timestamps, durations):
+        fmt, table = self.input_time_format, self.annoying_numbers_replacement_dict
+        fns = {"seconds_integers": mr_utils.get_timestamps_as_seconds_integers,
+               "relative_integers": mr_utils.get_timestamps_as_relative_integers,
+               "framenumbers": mr_utils.get_timestamps_as_framenumbers}
+        if fmt not in fns:
+            raise ValueError("Invalid input_time_format, please choose from ['framenumbers', 'relative_integers', "
+                             "'seconds_integers'] (float formats are not implemented)")
+        return fns[fmt](timestamps, durations, table)
+
+    def _clean_ids(self, values):
+        """get_clean_timestamp_tokens_and_embs (blip2_mr.py:1561-1608): ids without specials, leading '▁' (3) dropped."""
+        ids = self.t5_tokenizer([str(v) for v in values], add_special_tokens=False)["input_ids"]
+        return [i[1:] if (len(i) > 1 and i[0] == 3) else i for i in ids]
+
+    def prompt_concatenation(self, timestamps, durations, frames_for_t5, frames_atts_for_t5, video_prompt_end,
+                             query_prompt, task_prompt):
+        """blip2_mr.py:572-824 (interleave branch).  Host side builds only an int32 row table; one gather
+        kernel writes inputs_embeds.  -> (inputs_embeds fp32 [B, L, D] cuda, attention_mask long [B, L] cuda,
+        video_prompt list[str]); the row table is kept for the backward scatter."""
+        tok = self.t5_tokenizer
+        B, TN, C = frames_for_t5.shape
+        n = 1 if self.frame_token_aggregation else self.num_query_token
+        T = TN // n
+        if "add_duration" in self.task:
+            video_prompt_end = ["{}<extra_id_0>\n".format(">" + str(round(float(x), 2))) for x in durations]
+        ts = torch.as_tensor(timestamps).detach().cpu()
+        du = torch.as_tensor(durations).detach().cpu()
+        ts_list, dur_list, video_prompt = self._timestamps(ts, du)
+        end = tok(video_prompt_end, padding="longest", add_special_tokens=False, truncation=True,
+                  max_length=self.max_txt_len, return_tensors="pt")
+        if "no_task_prompt" in self.task:
+            text_prompt = [q for q in query_prompt]
+        else:
+            text_prompt = [q + t for q, t in zip(query_prompt, task_prompt)]
+        text = tok(text_prompt, padding="longest", truncation=True, max_length=self.max_txt_len, return_tensors="pt")
+        rows = []
+        for j in range(B):
+            ts_ids = self._clean_ids(ts_list[j].tolist())
+            dur_ids = self._clean_ids([dur_list[j] if not torch.is_tensor(dur_list[j]) else dur_list[j].item()])[0]
+            seq = []
+            base = j * T * n
+            for i in range(T):
+                seq.extend(range(-(base + i * n) - 1, -(base + (i + 1) * n) - 1, -1))
+                seq.extend(ts_ids[i])
+            seq.append(self.seperator_token)
+            seq.extend(dur_ids)
+            rows.append(seq)
+        Lv = max(len(r) for r in rows)
+        Le = Lv + end.input_ids.shape[1] + text.input_ids.shape[1]
+        table = np.empty((B, Le), dtype=np.int64)
+        for j, r in enumerate(rows):
+            table[j, :Lv - len(r)] = INT_MIN                  # left padding = pad_token_id * ones = zero rows (:744-754)
+            table[j, Lv - len(r):Lv] = r
+        table[:, Lv:Lv + end.input_ids.shape[1]] = end.input_ids.numpy()
+        table[:, Lv + end.input_ids.shape[1]:] = text.input_ids.numpy()
+        atts = torch.cat([torch.ones((B, Lv), dtype=torch.long), end.attention_mask, text.attention_mask], dim=1)
+        idx = torch.from_numpy(table.astype(np.int32)).to("cuda", non_blocking=True)
+        _, _, t5 = self.engines()
+        inputs = torch.empty((B * Le, C), dtype=torch.float32, device="cuda")
+        ops.gather_rows(idx.reshape(-1), t5.emb, frames_for_t5.reshape(B * TN, C), inputs)
+        self._last_row_table = idx
+        return inputs.view(B, Le, C), atts.to("cuda", non_blocking=True), video_prompt
+
+    # ---------------------------------------------------------------------------------------------
+    def forward(self, samples):
+        return self.forward_mr(samples)
+
+    def forward_mr(self, samples, want_logits=False):
+        """blip2_mr.py:433-570."""
+        vit, qf, t5 = self.engines()
+        d = self.dims
+        image = samples["video"]
+        b, t = image.shape[:2]
+        need_grad = self.training and torch.is_grad_enabled()
+        frames, frames_atts, (qh, qh16) = self.get_frame_embeddings_and_attentions(image, want_aux=True)
+        inputs, atts, _ = self.prompt_concatenation(samples["timestamps"], samples["duration"], frames, frames_atts,
+                                                     samples["video_prompt_end"], samples["query_prompt"],
+                                                     samples["task_prompt"])
+        ans = self.t5_tokenizer(samples["relevant_windows"], padding="longest", truncation=True,
+                                max_length=self.max_txt_len, return_tensors="pt")
+        labels = ans.input_ids.masked_fill(ans.input_ids == self.t5_tokenizer.pad_token_id, -100)
+        if need_grad:
+            t5.zero_grads()
+        out = t5.loss(inputs, atts, labels, ans.attention_mask, backward=need_grad, want_logits=want_logits)
+        loss = out["loss"].reshape(())
+        if need_grad:
+            n = d.num_query
+            M = b * t * n
+            d_frames = torch.zeros((b * t * (1 if self.frame_token_aggregation else n), d.d_model),
+                                   dtype=torch.float32, device="cuda")
+            din = out["d_inputs_embeds"].reshape(-1, d.d_model)
+            ops.scatter_frames(self._last_row_table.reshape(-1), din, d_frames)
+            if self.frame_token_aggregation:
+                full = torch.empty((M, d.d_model), dtype=torch.float32, device="cuda")
+                ops.group_mean_bwd(d_frames, full, b * t, n, d.d_model)
+                d_frames = full
+            pairs = t5.param_grads() + self._t5_proj_grads(d_frames, qh, M)
+            params = [p for p, _ in pairs]
+            grads = [g for _, g in pairs]
+            loss = _HandOverGrads.apply(loss, len(params), *params, *grads)
+        res = {"loss": loss}
+        if want_logits:
+            res.update(logits=out["logits"], inputs_embeds=inputs, attention_mask=atts, labels=labels,
+                       qformer=qh.view(b * t, d.num_query, -1), frames_for_t5=frames)
+        return res
+
+    def _t5_proj_grads(self, d_frames, qh, M):
+        """dW = dF^T . h, db = colsum(dF) for t5_proj (trainable, blip2_mr.py:291 note in SURVEY.md §3.1)."""
+        d = self.dims
+        BF = torch.bfloat16
+        Mp = (M + 7) // 8 * 8
+        df16 = torch.empty((M, d.d_model), dtype=BF, device="cuda")
+        ops.cast_to(d_frames, df16)
+        h16 = torch.empty((M, d.qf_hidden), dtype=BF, device="cuda")
+        ops.cast_to(qh.contiguous(), h16)
+        dft = torch.zeros((d.d_model, Mp), dtype=BF, device="cuda")
+        ht = torch.zeros((d.qf_hidden, Mp), dtype=BF, device="cuda")
+        ops.transpose16(df16, dft, M, d.d_model)
+        ops.transpose16(h16, ht, M, d.qf_hidden)
+        dW = ops.gemm(dft, ht, out_dtype=torch.float32)       # [2048, 768]
+        db = torch.zeros((d.d_model,), dtype=torch.float32, device="cuda")
+        ops.colsum(d_frames, db)
+        return [(self.t5_proj.weight, dW), (self.t5_proj.bias, db)]
+
+    # ---------------------------------------------------------------------------------------------
+    @torch.no_grad()
+    def generate(self, samples, use_nucleus_sampling=False, num_beams=5, max_length=50, min_length=1, top_p=0.9,
+                 repetition_penalty=1.0, length_penalty=1.0, num_captions=1, temperature=1, output_attentions=False):
+        """blip2_mr.py:826-946.  Beam search restates transformers 4.46.1 semantics (see generation.py) with
+        cross K/V projected once and an incremental decoder."""
+        from .generation import beam_search
+        if use_nucleus_sampling:
+            raise NotImplementedError("nucleus sampling is not used by the moment-retrieval task (moment_retrieval.py:33-36)")
+        _, _, t5 = self.engines()
+        frames, frames_atts = self.get_frame_embeddings_and_attentions(samples["video"])
+        inputs, atts, video_prompt = self.prompt_concatenation(samples["timestamps"], samples["duration"], frames,
+                                                               frames_atts, samples["video_prompt_end"],
+                                                               samples["query_prompt"], samples["task_prompt"])
+        seqs = beam_search(t5, inputs, atts, num_beams=num_beams, max_new_tokens=max_length, min_length=min_length,
+                           length_penalty=length_penalty, eos_id=self.t5_tokenizer.eos_token_id,
+                           pad_id=self.t5_tokenizer.pad_token_id)
+        pred_ans = self.t5_tokenizer.batch_decode(seqs, skip_special_tokens=True)
+        out = {}
+        dur = samples["duration"]
+        out["duration"] = dur.tolist() if isinstance(dur, torch.Tensor) else dur
+        if self.input_time_format in ("relative_integers", "relative_floats"):
+            prediction = [self.post_process(p) for p in pred_ans]
+            out["prediction"] = mr_utils.convert_to_absolute_time(prediction, out["duration"])
+        else:
+            out["prediction"] = [self.post_process(p) for p in pred_ans]
+        out["raw_prediction"] = pred_ans
+        out["answer"] = samples["relevant_windows"]
+        out["qid"] = samples["query_id"]
+        out["sequences"] = seqs
+        return out

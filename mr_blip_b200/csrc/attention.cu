@@ -16,6 +16,7 @@ struct AttnParams {
   const float* bias;        // [H, bias_len] indexed by (j - i_abs) + bias_zero, or null
   int bias_len, bias_zero;
   const int* kmask;         // [B, Lk] 1 = attend, or null
+  int kv_div;               // K/V (and kmask) batch index = b / kv_div  (beams sharing one encoder output)
   int causal;               // key j allowed iff j <= i + q_pos0
   int q_pos0;               // absolute position of query row 0
   float* lse;               // [B, H, Lq] or null
@@ -91,10 +92,10 @@ __global__ void __launch_bounds__(NTHREADS) attn_fwd_kernel(const AttnParams p) 
   const int b = blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * BQ;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t4 = lane & 3;
   const T* gq = static_cast<const T*>(p.q) + b * p.q_bs + static_cast<long long>(h) * p.hd;
-  const T* gk = static_cast<const T*>(p.k) + b * p.k_bs + static_cast<long long>(h) * p.hd;
-  const T* gv = static_cast<const T*>(p.v) + b * p.v_bs + static_cast<long long>(h) * p.hd;
+  const T* gk = static_cast<const T*>(p.k) + (b / p.kv_div) * p.k_bs + static_cast<long long>(h) * p.hd;
+  const T* gv = static_cast<const T*>(p.v) + (b / p.kv_div) * p.v_bs + static_cast<long long>(h) * p.hd;
   ScoreCtx sc{p.scale, p.bias ? p.bias + static_cast<long long>(h) * p.bias_len : nullptr, p.bias_zero,
-              p.kmask ? p.kmask + static_cast<long long>(b) * p.Lk : nullptr, p.causal, p.q_pos0, p.Lk};
+              p.kmask ? p.kmask + static_cast<long long>(b / p.kv_div) * p.Lk : nullptr, p.causal, p.q_pos0, p.Lk};
 
   int n_kv = (p.Lk + BKV - 1) / BKV;
   if (p.causal) n_kv = min(n_kv, (q0 + BQ - 1 + p.q_pos0) / BKV + 1);
@@ -250,11 +251,11 @@ __global__ void __launch_bounds__(NTHREADS) attn_bwd_dq_kernel(const AttnParams 
   const int b = blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * BQ;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t4 = lane & 3;
   const T* gq = static_cast<const T*>(p.q) + b * p.q_bs + static_cast<long long>(h) * p.hd;
-  const T* gk = static_cast<const T*>(p.k) + b * p.k_bs + static_cast<long long>(h) * p.hd;
-  const T* gv = static_cast<const T*>(p.v) + b * p.v_bs + static_cast<long long>(h) * p.hd;
+  const T* gk = static_cast<const T*>(p.k) + (b / p.kv_div) * p.k_bs + static_cast<long long>(h) * p.hd;
+  const T* gv = static_cast<const T*>(p.v) + (b / p.kv_div) * p.v_bs + static_cast<long long>(h) * p.hd;
   const T* gdo = static_cast<const T*>(p.dout) + b * p.do_bs + static_cast<long long>(h) * p.hd;
   ScoreCtx sc{p.scale, p.bias ? p.bias + static_cast<long long>(h) * p.bias_len : nullptr, p.bias_zero,
-              p.kmask ? p.kmask + static_cast<long long>(b) * p.Lk : nullptr, p.causal, p.q_pos0, p.Lk};
+              p.kmask ? p.kmask + static_cast<long long>(b / p.kv_div) * p.Lk : nullptr, p.causal, p.q_pos0, p.Lk};
   int n_kv = (p.Lk + BKV - 1) / BKV;
   if (p.causal) n_kv = min(n_kv, (q0 + BQ - 1 + p.q_pos0) / BKV + 1);
 
@@ -376,11 +377,11 @@ __global__ void __launch_bounds__(NTHREADS) attn_bwd_dkv_kernel(const AttnParams
   const int b = blockIdx.z, h = blockIdx.y, k0 = blockIdx.x * BKV;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t4 = lane & 3;
   const T* gq = static_cast<const T*>(p.q) + b * p.q_bs + static_cast<long long>(h) * p.hd;
-  const T* gk = static_cast<const T*>(p.k) + b * p.k_bs + static_cast<long long>(h) * p.hd;
-  const T* gv = static_cast<const T*>(p.v) + b * p.v_bs + static_cast<long long>(h) * p.hd;
+  const T* gk = static_cast<const T*>(p.k) + (b / p.kv_div) * p.k_bs + static_cast<long long>(h) * p.hd;
+  const T* gv = static_cast<const T*>(p.v) + (b / p.kv_div) * p.v_bs + static_cast<long long>(h) * p.hd;
   const T* gdo = static_cast<const T*>(p.dout) + b * p.do_bs + static_cast<long long>(h) * p.hd;
   ScoreCtx sc{p.scale, p.bias ? p.bias + static_cast<long long>(h) * p.bias_len : nullptr, p.bias_zero,
-              p.kmask ? p.kmask + static_cast<long long>(b) * p.Lk : nullptr, p.causal, p.q_pos0, p.Lk};
+              p.kmask ? p.kmask + static_cast<long long>(b / p.kv_div) * p.Lk : nullptr, p.causal, p.q_pos0, p.Lk};
   const long long stat = (static_cast<long long>(b) * p.H + h) * p.Lq;
   const int n_q = (p.Lq + BQ - 1) / BQ;
   int q_begin = 0;
@@ -558,14 +559,14 @@ static int check_attn(const AttnParams& p, int dtype) {
 extern "C" int mrb_attention_fwd(const void* q, long long q_bs, long long q_rs, const void* k, long long k_bs, long long k_rs,
                                  const void* v, long long v_bs, long long v_rs, void* o, long long o_bs, long long o_rs,
                                  int B, int H, int Lq, int Lk, int hd, int dtype, float scale, const float* bias,
-                                 int bias_len, int bias_zero, const int* kmask, int causal, int q_pos0, float* lse,
+                                 int bias_len, int bias_zero, const int* kmask, int kv_div, int causal, int q_pos0, float* lse,
                                  void* stream) {
   if (B <= 0 || H <= 0 || Lq <= 0 || Lk <= 0) return MRB_OK;
   AttnParams p{};
   p.q = q; p.k = k; p.v = v; p.o = o;
   p.q_bs = q_bs; p.q_rs = q_rs; p.k_bs = k_bs; p.k_rs = k_rs; p.v_bs = v_bs; p.v_rs = v_rs; p.o_bs = o_bs; p.o_rs = o_rs;
   p.B = B; p.H = H; p.Lq = Lq; p.Lk = Lk; p.hd = hd; p.scale = scale;
-  p.bias = bias; p.bias_len = bias_len; p.bias_zero = bias_zero; p.kmask = kmask; p.causal = causal; p.q_pos0 = q_pos0;
+  p.bias = bias; p.bias_len = bias_len; p.bias_zero = bias_zero; p.kmask = kmask; p.causal = causal; p.q_pos0 = q_pos0; p.kv_div = kv_div > 0 ? kv_div : 1;
   p.lse = lse;
   if (int rc = check_attn(p, dtype)) return rc;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
@@ -584,7 +585,7 @@ extern "C" int mrb_attention_bwd(const void* q, long long q_bs, long long q_rs, 
   p.q = q; p.k = k; p.v = v; p.o = const_cast<void*>(o);
   p.q_bs = q_bs; p.q_rs = q_rs; p.k_bs = k_bs; p.k_rs = k_rs; p.v_bs = v_bs; p.v_rs = v_rs; p.o_bs = o_bs; p.o_rs = o_rs;
   p.B = B; p.H = H; p.Lq = Lq; p.Lk = Lk; p.hd = hd; p.scale = scale;
-  p.bias = bias; p.bias_len = bias_len; p.bias_zero = bias_zero; p.kmask = kmask; p.causal = causal; p.q_pos0 = q_pos0;
+  p.bias = bias; p.bias_len = bias_len; p.bias_zero = bias_zero; p.kmask = kmask; p.causal = causal; p.q_pos0 = q_pos0; p.kv_div = 1;
   p.lse = const_cast<float*>(lse); p.dout = dout; p.do_bs = do_bs; p.do_rs = do_rs; p.delta = delta_ws;
   p.dq = dq; p.dk = dk; p.dv = dv;
   if (int rc = check_attn(p, dtype)) return rc;

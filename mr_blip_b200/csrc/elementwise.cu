@@ -73,17 +73,24 @@ __global__ void __launch_bounds__(256) norm_kernel(const float* __restrict__ x, 
 }
 
 // RMSNorm backward: dres[row] += rstd * (w*dy) - x * rstd^3 * mean(w*dy*x)       (weights frozen: no dw)
+// dy: fp32 or 16-bit [rows, ld]; when A != null the LoRA input gradient is folded in first:
+//     dy_eff[k] = dy[k] + sum_r dy[C + r] * A[r, k]      (dy is then an "extended" dgrad buffer [rows, C+32])
 template <int MAXV>
 __global__ void __launch_bounds__(256) rmsnorm_bwd_kernel(const float* __restrict__ x, const float* __restrict__ w,
-                                                          const float* __restrict__ dy, float eps, int rows, int C,
+                                                          const void* __restrict__ dy, int dy_dtype, long long ld,
+                                                          const float* __restrict__ A, int R, float eps, int rows, int C,
                                                           float* __restrict__ dres) {
   const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= rows) return;
   const int nv = C >> 2;
   const float4* xr = reinterpret_cast<const float4*>(x + static_cast<long long>(row) * C);
-  const float4* dr = reinterpret_cast<const float4*>(dy + static_cast<long long>(row) * C);
   const float4* wr = reinterpret_cast<const float4*>(w);
+  float dxa = 0.f;   // lane r holds dy[C + r]
+  if (A && lane < R) {
+    const uint16_t v = static_cast<const uint16_t*>(dy)[static_cast<long long>(row) * ld + C + lane];
+    dxa = (dy_dtype == MRB_DT_F16) ? __half2float(__ushort_as_half(v)) : __uint_as_float(static_cast<uint32_t>(v) << 16);
+  }
   float4 xv[MAXV], gv[MAXV];
   float ss = 0.f, dot = 0.f;
 #pragma unroll
@@ -91,7 +98,21 @@ __global__ void __launch_bounds__(256) rmsnorm_bwd_kernel(const float* __restric
     const int c = lane + i * 32;
     if (c < nv) {
       xv[i] = xr[c];
-      const float4 d = dr[c], ww = wr[c];
+      float4 d;
+      if (dy_dtype == MRB_DT_F32) {
+        d = reinterpret_cast<const float4*>(static_cast<const float*>(dy) + static_cast<long long>(row) * ld)[c];
+      } else {
+        const uint2 pk = reinterpret_cast<const uint2*>(static_cast<const uint16_t*>(dy) + static_cast<long long>(row) * ld)[c];
+        d = make_float4(unpack_lo(pk.x, dy_dtype), unpack_hi(pk.x, dy_dtype), unpack_lo(pk.y, dy_dtype), unpack_hi(pk.y, dy_dtype));
+      }
+      if (A) {
+        for (int r = 0; r < R; ++r) {
+          const float g = __shfl_sync(0xffffffffu, dxa, r);
+          const float4 a = reinterpret_cast<const float4*>(A + static_cast<long long>(r) * C)[c];
+          d.x += g * a.x; d.y += g * a.y; d.z += g * a.z; d.w += g * a.w;
+        }
+      }
+      const float4 ww = wr[c];
       gv[i] = make_float4(d.x * ww.x, d.y * ww.y, d.z * ww.z, d.w * ww.w);
       ss += xv[i].x * xv[i].x + xv[i].y * xv[i].y + xv[i].z * xv[i].z + xv[i].w * xv[i].w;
       dot += gv[i].x * xv[i].x + gv[i].y * xv[i].y + gv[i].z * xv[i].z + gv[i].w * xv[i].w;
@@ -109,6 +130,43 @@ __global__ void __launch_bounds__(256) rmsnorm_bwd_kernel(const float* __restric
       o.z += gv[i].z * rstd - xv[i].z * coef; o.w += gv[i].w * rstd - xv[i].w * coef;
       out[c] = o;
     }
+  }
+}
+
+// LoRA input-gradient fix-up on an extended dgrad buffer x [M, K+32] (16-bit):
+//   y[m, k] = x[m, k] + sum_r x[m, K + r] * A[r, k];   in place, or accumulated into fp32 acc [M, K] when acc != null
+__global__ void __launch_bounds__(256) lora_up_add_kernel(uint16_t* __restrict__ x, long long ldx, const float* __restrict__ A,
+                                                           int R, int M, int K, int dtype, float* __restrict__ acc) {
+  const int kv = K >> 3;
+  const long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  if (idx >= static_cast<long long>(M) * kv) return;
+  const int c = (idx % kv) * 8;
+  const long long m = idx / kv;
+  uint16_t* xr = x + m * ldx;
+  const uint4 v = *reinterpret_cast<const uint4*>(xr + c);
+  const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+  float y[8];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { y[2 * i] = unpack_lo(w[i], dtype); y[2 * i + 1] = unpack_hi(w[i], dtype); }
+  for (int r = 0; r < R; r += 2) {
+    const uint32_t gw = *reinterpret_cast<const uint32_t*>(xr + K + r);
+    const float g0 = unpack_lo(gw, dtype), g1 = unpack_hi(gw, dtype);
+    const float4 a0 = *reinterpret_cast<const float4*>(A + static_cast<long long>(r) * K + c);
+    const float4 a1 = *reinterpret_cast<const float4*>(A + static_cast<long long>(r) * K + c + 4);
+    const float4 b0 = *reinterpret_cast<const float4*>(A + static_cast<long long>(r + 1) * K + c);
+    const float4 b1 = *reinterpret_cast<const float4*>(A + static_cast<long long>(r + 1) * K + c + 4);
+    y[0] += g0 * a0.x + g1 * b0.x; y[1] += g0 * a0.y + g1 * b0.y; y[2] += g0 * a0.z + g1 * b0.z; y[3] += g0 * a0.w + g1 * b0.w;
+    y[4] += g0 * a1.x + g1 * b1.x; y[5] += g0 * a1.y + g1 * b1.y; y[6] += g0 * a1.z + g1 * b1.z; y[7] += g0 * a1.w + g1 * b1.w;
+  }
+  if (acc) {
+    float4* ap = reinterpret_cast<float4*>(acc + m * K + c);
+    float4 p0 = ap[0], p1 = ap[1];
+    p0.x += y[0]; p0.y += y[1]; p0.z += y[2]; p0.w += y[3];
+    p1.x += y[4]; p1.y += y[5]; p1.z += y[6]; p1.w += y[7];
+    ap[0] = p0; ap[1] = p1;
+  } else {
+    *reinterpret_cast<uint4*>(xr + c) = make_uint4(pack2(y[0], y[1], dtype), pack2(y[2], y[3], dtype),
+                                                   pack2(y[4], y[5], dtype), pack2(y[6], y[7], dtype));
   }
 }
 
@@ -240,7 +298,8 @@ __global__ void group_mean_bwd_kernel(const float* __restrict__ dout, float* __r
 // logits fp32 [rows, V]; labels int64 (-100 = ignore).  loss_sum += -log p[label]; dlogits = (p - onehot) * gscale
 __global__ void __launch_bounds__(1024) ce_kernel(const float* __restrict__ logits, const long long* __restrict__ labels,
                                                   int V, float* __restrict__ row_loss, void* __restrict__ dlogits,
-                                                  int d_dtype, long long ldd, float gscale) {
+                                                  int d_dtype, long long ldd, float gscale,
+                                                  float* __restrict__ loss_sum) {
   __shared__ float red[32];
   __shared__ float bval;
   const int row = blockIdx.x;
@@ -271,7 +330,11 @@ __global__ void __launch_bounds__(1024) ce_kernel(const float* __restrict__ logi
   }
   __syncthreads();
   const float lse = mx + logf(bval);
-  if (threadIdx.x == 0) row_loss[row] = (lab >= 0) ? (lse - lr[lab]) : 0.f;
+  if (threadIdx.x == 0) {
+    const float l = (lab >= 0) ? (lse - lr[lab]) : 0.f;
+    if (row_loss) row_loss[row] = l;
+    if (loss_sum && lab >= 0) atomicAdd(loss_sum, l * gscale);   // gscale = 1 / #valid targets -> mean loss
+  }
   if (dlogits) {
     uint16_t* dr = static_cast<uint16_t*>(dlogits) + static_cast<long long>(row) * ldd;
     const float gs = (lab >= 0) ? gscale : 0.f;
@@ -422,11 +485,21 @@ extern "C" int mrb_norm(const float* x, const float* add, const float* w, const 
   return MRB_OK;
 }
 
-extern "C" int mrb_rmsnorm_bwd(const float* x, const float* w, const float* dy, float eps, int rows, int C, float* dres,
-                               void* stream) {
+extern "C" int mrb_rmsnorm_bwd(const float* x, const float* w, const void* dy, int dy_dtype, long long ld_dy,
+                               const float* lora_A, int R, float eps, int rows, int C, float* dres, void* stream) {
   if (rows <= 0) return MRB_OK;
-  if ((C & 3) || C > 2048) return MRB_ERR_ARG;
-  rmsnorm_bwd_kernel<16><<<blocks_for(rows, 8), 256, 0, STREAM>>>(x, w, dy, eps, rows, C, dres);
+  if ((C & 3) || C > 2048 || (ld_dy & 3) || R > 32 || (lora_A && dy_dtype == MRB_DT_F32)) return MRB_ERR_ARG;
+  rmsnorm_bwd_kernel<16><<<blocks_for(rows, 8), 256, 0, STREAM>>>(x, w, dy, dy_dtype, ld_dy, lora_A, R, eps, rows, C, dres);
+  MRB_CHECK_LAUNCH();
+  return MRB_OK;
+}
+
+extern "C" int mrb_lora_up_add(void* x_ext, long long ldx, const float* A, int R, int M, int K, int dtype, float* acc,
+                               void* stream) {
+  if (M <= 0) return MRB_OK;
+  if ((K & 7) || (ldx & 7) || (R & 1) || R > 32) return MRB_ERR_ARG;
+  lora_up_add_kernel<<<blocks_for(static_cast<long long>(M) * (K >> 3), 256), 256, 0, STREAM>>>(
+      static_cast<uint16_t*>(x_ext), ldx, A, R, M, K, dtype, acc);
   MRB_CHECK_LAUNCH();
   return MRB_OK;
 }
@@ -493,10 +566,10 @@ extern "C" int mrb_group_mean_bwd(const float* dout, float* dx, int groups, int 
 }
 
 extern "C" int mrb_cross_entropy(const float* logits, const long long* labels, int rows, int V, float* row_loss,
-                                 void* dlogits, int d_dtype, long long ldd, float gscale, void* stream) {
+                                 void* dlogits, int d_dtype, long long ldd, float gscale, float* loss_sum, void* stream) {
   if (rows <= 0) return MRB_OK;
   if (dlogits && (ldd & 1)) return MRB_ERR_ARG;
-  ce_kernel<<<rows, 1024, 0, STREAM>>>(logits, labels, V, row_loss, dlogits, d_dtype, ldd, gscale);
+  ce_kernel<<<rows, 1024, 0, STREAM>>>(logits, labels, V, row_loss, dlogits, d_dtype, ldd, gscale, loss_sum);
   MRB_CHECK_LAUNCH();
   return MRB_OK;
 }

@@ -51,7 +51,7 @@ def gemm(a, b, out=None, bias=None, gelu=False, resid=None, out_dtype=None, row_
 
 
 def attention_fwd(q, k, v, out, B, H, Lq, Lk, hd, scale, q_strides, k_strides, v_strides, o_strides, bias=None,
-                  bias_zero=0, kmask=None, causal=False, q_pos0=0, lse=None):
+                  bias_zero=0, kmask=None, causal=False, q_pos0=0, lse=None, kv_div=1):
     """q/k/v/out: tensors whose data_ptr is row 0 / head 0; *_strides = (batch stride, row stride) in elements."""
     _check(q, torch.float16, torch.bfloat16)
     if kmask is not None:
@@ -59,7 +59,7 @@ def attention_fwd(q, k, v, out, B, H, Lq, Lk, hd, scale, q_strides, k_strides, v
     _lib.call("mrb_attention_fwd", q.data_ptr(), q_strides[0], q_strides[1], k.data_ptr(), k_strides[0], k_strides[1],
               v.data_ptr(), v_strides[0], v_strides[1], out.data_ptr(), o_strides[0], o_strides[1], B, H, Lq, Lk, hd,
               _DT[q.dtype], float(scale), _ptr(bias), bias.shape[1] if bias is not None else 0, bias_zero, _ptr(kmask),
-              int(causal), q_pos0, _ptr(lse), _stream())
+              kv_div, int(causal), q_pos0, _ptr(lse), _stream())
     return out
 
 
@@ -82,10 +82,16 @@ def norm(x, w, bias, eps, mode, add=None, out_f32=None, out_h=None, sum_out=None
               (ld_h if ld_h is not None else (out_h.stride(0) if out_h is not None else 0)), _ptr(sum_out), _stream())
 
 
-def rmsnorm_bwd(x, w, dy, eps, dres):
+def rmsnorm_bwd(x, w, dy, eps, dres, lora_A=None, R=0):
+    """dres += RMSNorm'(x; w) . dy; dy fp32 or 16-bit (row stride dy.stride(0)); lora_A folds dy[:, C:C+R] . A in."""
     rows, C = x.shape
-    assert dy.is_contiguous() and dres.is_contiguous() and dy.dtype == torch.float32
-    _lib.call("mrb_rmsnorm_bwd", x.data_ptr(), w.data_ptr(), dy.data_ptr(), float(eps), rows, C, dres.data_ptr(), _stream())
+    assert dres.is_contiguous() and x.is_contiguous()
+    _lib.call("mrb_rmsnorm_bwd", x.data_ptr(), w.data_ptr(), dy.data_ptr(), _DT[dy.dtype], dy.stride(0), _ptr(lora_A), R,
+              float(eps), rows, C, dres.data_ptr(), _stream())
+
+
+def lora_up_add(x_ext, A, R, M, K, acc=None):
+    _lib.call("mrb_lora_up_add", x_ext.data_ptr(), x_ext.stride(0), A.data_ptr(), R, M, K, _DT[x_ext.dtype], _ptr(acc), _stream())
 
 
 def patchify(img, out, img_size, patch):
@@ -126,14 +132,14 @@ def group_mean_bwd(dout, dx, groups, n, C):
     _lib.call("mrb_group_mean_bwd", dout.data_ptr(), dx.data_ptr(), groups, n, C, _stream())
 
 
-def cross_entropy(logits, labels, row_loss, dlogits=None, gscale=1.0):
+def cross_entropy(logits, labels, row_loss=None, dlogits=None, gscale=1.0, loss_sum=None):
     _check(logits, torch.float32)
     _check(labels, torch.int64)
     rows, V = logits.shape
     assert logits.is_contiguous()
-    _lib.call("mrb_cross_entropy", logits.data_ptr(), labels.data_ptr(), rows, V, row_loss.data_ptr(), _ptr(dlogits),
+    _lib.call("mrb_cross_entropy", logits.data_ptr(), labels.data_ptr(), rows, V, _ptr(row_loss), _ptr(dlogits),
               _DT[dlogits.dtype] if dlogits is not None else 0, dlogits.stride(0) if dlogits is not None else 0,
-              float(gscale), _stream())
+              float(gscale), _ptr(loss_sum), _stream())
 
 
 def lora_down(x_ext, A, M, K, R):

@@ -1,0 +1,462 @@
+"""FlanT5-XL with LoRA on the GPU: teacher-forced forward + hand-written backward (LoRA A/B
+gradients and the gradient w.r.t. inputs_embeds), encoder-only forward, and incremental decoding
+with cached K/V.  Restates lavis/models/blip2_models/modeling_t5.py (T5Stack.forward :1021-1282,
+T5Attention :474-620, T5LayerFF :331-347, T5ForConditionalGeneration.forward :1734-1893) and peft's
+lora.Linear as configured at blip2_mr.py:193-200, kernel by kernel through the C ABI.
+
+Data layout (HBM):
+  * residual stream h: fp32 [M, d_model] (reference keeps fp32 residuals under bf16 autocast).
+  * every Linear input lives in an "extended" bf16 buffer [M, K+32]: columns [0,K) hold x, columns
+    [K, K+8j+8) hold the LoRA down-projections x.A_j^T of the (up to 3) Linears sharing that input.
+    The frozen weight is stored once as W_ext = [W | B_0 B_1 B_2 | 0] (bf16 [N, K+32]), so
+    base(x) + B(A x) is ONE tcgen05 GEMM; W_ext^T is kept for the dgrad GEMM, whose extra 32 output
+    columns are exactly dL/d(xA^T) -- the operand of the LoRA weight gradients.
+  * LoRA B changes every optimiser step: refresh() re-copies B into the 8-column slots.
+Dropout (T5 0.1, LoRA 0.05) is not applied: see DESIGN.md "Out of scope / gaps".
+"""
+import math
+
+import torch
+
+from . import ops
+from .dims import Dims, T5_PREFIX
+
+BF = torch.bfloat16
+EXT = 32
+
+
+def _f(t):
+    return t.detach().to(device="cuda", dtype=torch.float32).contiguous()
+
+
+class LoraGroup:
+    """Linears that share one input (q|k|v, wi_0|wi_1, or a single Linear) packed as one ext GEMM."""
+
+    def __init__(self, get, names, scale):
+        self.names = names
+        Ws = [get(n + ".base_layer.weight") for n in names]
+        self.K = Ws[0].shape[1]
+        self.Ns = [w.shape[0] for w in Ws]
+        self.N = sum(self.Ns)
+        self.n = len(names)
+        self.R = 8 * self.n
+        self.scale = scale
+        self.A_params = [get(n + ".lora_A.default.weight") for n in names]
+        self.B_params = [get(n + ".lora_B.default.weight") for n in names]
+        assert all(a.shape[0] == 8 for a in self.A_params), "kernels are specialised for LoRA r = 8"
+        K = self.K
+        self.ext = torch.zeros((self.N, K + EXT), dtype=BF, device="cuda")
+        off = 0
+        for w in Ws:
+            self.ext[off:off + w.shape[0], :K] = w.detach().to("cuda")
+            off += w.shape[0]
+        self.ext_t = torch.zeros((K + EXT, self.N), dtype=BF, device="cuda")
+        self.A_cat = torch.zeros((self.R, K), dtype=torch.float32, device="cuda")
+        self.offs = [sum(self.Ns[:j]) for j in range(self.n)]
+        self.dA = [torch.zeros((8, K), dtype=torch.float32, device="cuda") for _ in names]
+        self.dB = [torch.zeros((n_, 8), dtype=torch.float32, device="cuda") for n_ in self.Ns]
+        self._dst, self._src = [], []
+        for j in range(self.n):
+            o, n_ = self.offs[j], self.Ns[j]
+            self._dst += [self.ext[o:o + n_, K + 8 * j:K + 8 * j + 8], self.ext_t[K + 8 * j:K + 8 * j + 8, o:o + n_],
+                          self.A_cat[8 * j:8 * j + 8]]
+        ops.transpose16(self.ext, self.ext_t, self.N, K + EXT)
+        self.refresh()
+
+    def refresh(self):
+        src = []
+        for j in range(self.n):
+            b = self.B_params[j].detach()
+            if self.scale != 1.0:
+                b = b * self.scale
+            src += [b, b.t(), self.A_params[j].detach()]
+        torch._foreach_copy_(self._dst, src)
+
+    def forward(self, x_ext, M, out=None, resid=None, out_dtype=BF):
+        ops.lora_down(x_ext, self.A_cat, M, self.K, self.R)
+        return ops.gemm(x_ext, self.ext, out=out, resid=resid, out_dtype=out_dtype, M=M)
+
+    def backward(self, dy16, x_ext, M, dx_ext=None):
+        """-> dx_ext [M, K+32] (bf16): columns [0,K) = dy.W (LoRA term NOT yet added), [K, K+R) = dy.B_j.
+        Accumulates dA_j, dB_j."""
+        dx_ext = ops.gemm(dy16, self.ext_t, out=dx_ext, M=M)
+        K = self.K
+        es = dy16.element_size()
+        for j in range(self.n):
+            o, n_ = self.offs[j], self.Ns[j]
+            ops.skinny_wgrad(dy16.data_ptr() + o * es, dy16.stride(0), x_ext.data_ptr() + (K + 8 * j) * es,
+                             x_ext.stride(0), M, n_, self.dB[j], False, ops.BF16)
+            ops.skinny_wgrad(x_ext.data_ptr(), x_ext.stride(0), dx_ext.data_ptr() + (K + 8 * j) * es,
+                             dx_ext.stride(0), M, K, self.dA[j], True, ops.BF16)
+        return dx_ext
+
+    def zero_grads(self):
+        for g in self.dA + self.dB:
+            g.zero_()
+
+    def grads(self):
+        out = []
+        for j in range(self.n):
+            gb = self.dB[j] if self.scale == 1.0 else self.dB[j] * self.scale
+            out += [(self.A_params[j], self.dA[j]), (self.B_params[j], gb)]
+        return out
+
+
+_BUCKET_CACHE = {}
+
+
+def _bucket_index(Lq, Lk, bidirectional, num_buckets, max_distance):
+    """Bucket id for every delta = j - i in [-(Lq-1), Lk-1], computed on the HOST with the reference's own
+    float formula (modeling_t5.py:393-445) so bucket boundaries agree bit-for-bit with the CPU oracle."""
+    key = (Lq, Lk, bidirectional, num_buckets, max_distance)
+    if key not in _BUCKET_CACHE:
+        rel = torch.arange(-(Lq - 1), Lk, dtype=torch.long)
+        nb = num_buckets
+        buckets = torch.zeros_like(rel)
+        if bidirectional:
+            nb //= 2
+            buckets = buckets + (rel > 0).to(torch.long) * nb
+            rel = torch.abs(rel)
+        else:
+            rel = -torch.min(rel, torch.zeros_like(rel))
+        max_exact = nb // 2
+        is_small = rel < max_exact
+        large = max_exact + (torch.log(rel.float() / max_exact) / math.log(max_distance / max_exact)
+                             * (nb - max_exact)).to(torch.long)
+        large = torch.min(large, torch.full_like(large, nb - 1))
+        buckets = buckets + torch.where(is_small, rel, large)
+        _BUCKET_CACHE[key] = buckets.to("cuda")
+    return _BUCKET_CACHE[key]
+
+
+class T5Engine:
+    def __init__(self, d: Dims, get, prefix=T5_PREFIX):
+        self.d = d
+        D = d.d_model
+        scale = d.lora_alpha / d.lora_r
+        self.emb = get(prefix + "shared.weight")          # fp32 [V, D] (embed_tokens is tied to it)
+        assert self.emb.is_cuda
+        self.groups = []
+
+        def grp(names):
+            g = LoraGroup(get, names, scale)
+            self.groups.append(g)
+            return g
+
+        def attn(p):
+            return dict(qkv=grp([p + ".q", p + ".k", p + ".v"]), o=grp([p + ".o"]))
+
+        self.enc, self.dec = [], []
+        for i in range(d.t5_layers):
+            b = f"{prefix}encoder.block.{i}."
+            L = attn(b + "layer.0.SelfAttention")
+            L.update(ln0=_f(get(b + "layer.0.layer_norm.weight")), ln1=_f(get(b + "layer.1.layer_norm.weight")),
+                     wi=grp([b + "layer.1.DenseReluDense.wi_0", b + "layer.1.DenseReluDense.wi_1"]),
+                     wo=grp([b + "layer.1.DenseReluDense.wo"]))
+            self.enc.append(L)
+        self.enc_bias = _f(get(prefix + "encoder.block.0.layer.0.SelfAttention.relative_attention_bias.weight"))
+        self.enc_final_ln = _f(get(prefix + "encoder.final_layer_norm.weight"))
+        for i in range(d.t5_dec_layers):
+            b = f"{prefix}decoder.block.{i}."
+            L = attn(b + "layer.0.SelfAttention")
+            c = b + "layer.1.EncDecAttention"
+            L.update(ln0=_f(get(b + "layer.0.layer_norm.weight")), ln1=_f(get(b + "layer.1.layer_norm.weight")),
+                     ln2=_f(get(b + "layer.2.layer_norm.weight")),
+                     cq=grp([c + ".q"]), ckv=grp([c + ".k", c + ".v"]), co=grp([c + ".o"]),
+                     wi=grp([b + "layer.2.DenseReluDense.wi_0", b + "layer.2.DenseReluDense.wi_1"]),
+                     wo=grp([b + "layer.2.DenseReluDense.wo"]))
+            self.dec.append(L)
+        self.dec_bias = _f(get(prefix + "decoder.block.0.layer.0.SelfAttention.relative_attention_bias.weight"))
+        self.dec_final_ln = _f(get(prefix + "decoder.final_layer_norm.weight"))
+        self.lm_head = grp([prefix + "lm_head"])
+
+    # ------------------------------------------------------------------ helpers
+    def refresh(self):
+        for g in self.groups:
+            g.refresh()
+
+    def zero_grads(self):
+        for g in self.groups:
+            g.zero_grads()
+
+    def param_grads(self):
+        out = []
+        for g in self.groups:
+            out += g.grads()
+        return out
+
+    def _bias(self, table, Lq, Lk, bidirectional):
+        d = self.d
+        idx = _bucket_index(Lq, Lk, bidirectional, d.rel_buckets, d.rel_max_dist)
+        return table[idx].t().contiguous()                 # [H, Lq+Lk-1], zero delta at column Lq-1
+
+    def _ext(self, M, K):
+        return torch.empty((M, K + EXT), dtype=BF, device="cuda")
+
+    def _self_attn(self, qkv, out_ext, B, L, bias, kmask, causal, lse):
+        d = self.d
+        inner = d.t5_heads * d.d_kv
+        rs = 3 * inner
+        ops.attention_fwd(qkv, qkv[:, inner:], qkv[:, 2 * inner:], out_ext, B, d.t5_heads, L, L, d.d_kv, 1.0,
+                          (L * rs, rs), (L * rs, rs), (L * rs, rs), (L * out_ext.stride(0), out_ext.stride(0)),
+                          bias=bias, bias_zero=L - 1, kmask=kmask, causal=causal, lse=lse)
+
+    def _ff(self, L, h, M, save):
+        d = self.d
+        xn = self._ext(M, d.d_model)
+        ops.norm(h, L["ln_ff"], None, d.t5_ln_eps, 1, out_h=xn)
+        ab = L["wi"].forward(xn, M)
+        hm = self._ext(M, d.d_ff)
+        ops.gated_gelu_fwd(ab, hm, M, d.d_ff)
+        h2 = torch.empty_like(h)
+        L["wo"].forward(hm, M, out=h2, resid=h)
+        if save is not None:
+            save.update(ff_x=h, ff_xn=xn, ff_ab=ab, ff_hm=hm)
+        return h2
+
+    def _ff_bwd(self, L, s, dh, M):
+        """dh (fp32 residual-stream gradient) is updated in place."""
+        d = self.d
+        dy = torch.empty((M, d.d_model), dtype=BF, device="cuda")
+        ops.cast_to(dh, dy)
+        dhm = L["wo"].backward(dy, s["ff_hm"], M)
+        ops.lora_up_add(dhm, L["wo"].A_cat, 8, M, d.d_ff)
+        dab = torch.empty_like(s["ff_ab"])
+        ops.gated_gelu_bwd(s["ff_ab"], dhm, dab, M, d.d_ff)
+        dxn = L["wi"].backward(dab, s["ff_xn"], M)
+        ops.rmsnorm_bwd(s["ff_x"], L["ln_ff"], dxn, d.t5_ln_eps, dh, lora_A=L["wi"].A_cat, R=16)
+
+    # ------------------------------------------------------------------ encoder
+    def encoder_forward(self, x, kmask, B, L, save=None):
+        """x fp32 [B*L, D] inputs_embeds; -> normalised encoder output in an ext bf16 buffer [B*L, D+32]."""
+        d = self.d
+        M = B * L
+        bias = self._bias(self.enc_bias, L, L, True)
+        h = x
+        for li, layer in enumerate(self.enc):
+            layer["ln_ff"] = layer["ln1"]
+            s = {} if save is not None else None
+            xn = self._ext(M, d.d_model)
+            ops.norm(h, layer["ln0"], None, d.t5_ln_eps, 1, out_h=xn)
+            qkv = layer["qkv"].forward(xn, M)
+            ao = self._ext(M, d.d_model)
+            lse = torch.empty((B, d.t5_heads, L), dtype=torch.float32, device="cuda") if save is not None else None
+            self._self_attn(qkv, ao, B, L, bias, kmask, False, lse)
+            h1 = torch.empty_like(h)
+            layer["o"].forward(ao, M, out=h1, resid=h)
+            if s is not None:
+                s.update(x=h, xn=xn, qkv=qkv, ao=ao, lse=lse)
+            h = self._ff(layer, h1, M, s)
+            if save is not None:
+                save.append(s)
+        out = self._ext(M, d.d_model)
+        ops.norm(h, self.enc_final_ln, None, d.t5_ln_eps, 1, out_h=out)
+        return out, h, bias
+
+    def encoder_backward(self, saves, h_last, d_enc_out, kmask, B, L, bias):
+        """d_enc_out fp32 [M, D]: gradient w.r.t. the normalised encoder output -> gradient w.r.t. inputs_embeds."""
+        d = self.d
+        M = B * L
+        dh = torch.zeros((M, d.d_model), dtype=torch.float32, device="cuda")
+        ops.rmsnorm_bwd(h_last, self.enc_final_ln, d_enc_out, d.t5_ln_eps, dh)
+        inner = d.t5_heads * d.d_kv
+        ws = torch.empty((B * d.t5_heads * L,), dtype=torch.float32, device="cuda")
+        for layer, s in zip(reversed(self.enc), reversed(saves)):
+            self._ff_bwd(layer, s, dh, M)
+            dy = torch.empty((M, d.d_model), dtype=BF, device="cuda")
+            ops.cast_to(dh, dy)
+            dao = layer["o"].backward(dy, s["ao"], M)
+            ops.lora_up_add(dao, layer["o"].A_cat, 8, M, d.d_model)
+            qkv, rs = s["qkv"], 3 * inner
+            dqkv = torch.empty_like(qkv)
+            st = (L * rs, rs)
+            so = (L * dao.stride(0), dao.stride(0))
+            ops.attention_bwd(qkv, qkv[:, inner:], qkv[:, 2 * inner:], s["ao"], dao, dqkv, dqkv[:, inner:],
+                              dqkv[:, 2 * inner:], B, d.t5_heads, L, L, d.d_kv, 1.0, st, st, st, so, so, s["lse"], ws,
+                              bias=bias, bias_zero=L - 1, kmask=kmask, causal=False)
+            dxn = layer["qkv"].backward(dqkv, s["xn"], M)
+            ops.rmsnorm_bwd(s["x"], layer["ln0"], dxn, d.t5_ln_eps, dh, lora_A=layer["qkv"].A_cat, R=24)
+            s.clear()
+        return dh
+
+    # ------------------------------------------------------------------ decoder (teacher forced)
+    def decoder_forward(self, dec_ids, dmask, enc_ext, enc_kmask, B, Ld, Le, save=None):
+        d = self.d
+        M, Me = B * Ld, B * Le
+        inner = d.t5_heads * d.d_kv
+        h = torch.empty((M, d.d_model), dtype=torch.float32, device="cuda")
+        ops.gather_rows(dec_ids.reshape(-1).to(torch.int32), self.emb, None, h)
+        bias = self._bias(self.dec_bias, Ld, Ld, False)
+        for layer in self.dec:
+            layer["ln_ff"] = layer["ln2"]
+            s = {} if save is not None else None
+            xn = self._ext(M, d.d_model)
+            ops.norm(h, layer["ln0"], None, d.t5_ln_eps, 1, out_h=xn)
+            qkv = layer["qkv"].forward(xn, M)
+            ao = self._ext(M, d.d_model)
+            lse = torch.empty((B, d.t5_heads, Ld), dtype=torch.float32, device="cuda") if save is not None else None
+            self._self_attn(qkv, ao, B, Ld, bias, dmask, True, lse)
+            h1 = torch.empty_like(h)
+            layer["o"].forward(ao, M, out=h1, resid=h)
+            # cross attention
+            xn2 = self._ext(M, d.d_model)
+            ops.norm(h1, layer["ln1"], None, d.t5_ln_eps, 1, out_h=xn2)
+            cq = layer["cq"].forward(xn2, M)
+            ckv = layer["ckv"].forward(enc_ext, Me)
+            co = self._ext(M, d.d_model)
+            lse2 = torch.empty((B, d.t5_heads, Ld), dtype=torch.float32, device="cuda") if save is not None else None
+            ops.attention_fwd(cq, ckv, ckv[:, inner:], co, B, d.t5_heads, Ld, Le, d.d_kv, 1.0, (Ld * inner, inner),
+                              (Le * 2 * inner, 2 * inner), (Le * 2 * inner, 2 * inner), (Ld * co.stride(0), co.stride(0)),
+                              kmask=enc_kmask, lse=lse2)
+            h2 = torch.empty_like(h)
+            layer["co"].forward(co, M, out=h2, resid=h1)
+            if s is not None:
+                s.update(x=h, xn=xn, qkv=qkv, ao=ao, lse=lse, x1=h1, xn2=xn2, cq=cq, ckv=ckv, co=co, lse2=lse2)
+            h = self._ff(layer, h2, M, s)
+            if save is not None:
+                save.append(s)
+        out = self._ext(M, d.d_model)
+        ops.norm(h, self.dec_final_ln, None, d.t5_ln_eps, 1, out_h=out)
+        return out, h, bias
+
+    def decoder_backward(self, saves, h_last, d_out_ext, dmask, enc_ext, enc_kmask, B, Ld, Le, bias):
+        """d_out_ext: ext bf16 dgrad buffer from lm_head.backward.  -> d(enc normalised output) fp32 [Me, D]."""
+        d = self.d
+        M, Me = B * Ld, B * Le
+        inner = d.t5_heads * d.d_kv
+        dh = torch.zeros((M, d.d_model), dtype=torch.float32, device="cuda")
+        ops.rmsnorm_bwd(h_last, self.dec_final_ln, d_out_ext, d.t5_ln_eps, dh, lora_A=self.lm_head.A_cat, R=8)
+        d_enc = torch.zeros((Me, d.d_model), dtype=torch.float32, device="cuda")
+        ws = torch.empty((B * d.t5_heads * Ld,), dtype=torch.float32, device="cuda")
+        for layer, s in zip(reversed(self.dec), reversed(saves)):
+            self._ff_bwd(layer, s, dh, M)
+            # cross attention
+            dy = torch.empty((M, d.d_model), dtype=BF, device="cuda")
+            ops.cast_to(dh, dy)
+            dco = layer["co"].backward(dy, s["co"], M)
+            ops.lora_up_add(dco, layer["co"].A_cat, 8, M, d.d_model)
+            cq, ckv = s["cq"], s["ckv"]
+            dcq, dckv = torch.empty_like(cq), torch.empty_like(ckv)
+            sq, sk = (Ld * inner, inner), (Le * 2 * inner, 2 * inner)
+            so = (Ld * dco.stride(0), dco.stride(0))
+            ops.attention_bwd(cq, ckv, ckv[:, inner:], s["co"], dco, dcq, dckv, dckv[:, inner:], B, d.t5_heads, Ld, Le,
+                              d.d_kv, 1.0, sq, sk, sk, so, so, s["lse2"], ws, kmask=enc_kmask)
+            ops.lora_down(enc_ext, layer["ckv"].A_cat, Me, d.d_model, 16)     # recompute this layer's x.A^T columns
+            denc_ext = layer["ckv"].backward(dckv, enc_ext, Me)
+            ops.lora_up_add(denc_ext, layer["ckv"].A_cat, 16, Me, d.d_model, acc=d_enc)
+            dxn2 = layer["cq"].backward(dcq, s["xn2"], M)
+            ops.rmsnorm_bwd(s["x1"], layer["ln1"], dxn2, d.t5_ln_eps, dh, lora_A=layer["cq"].A_cat, R=8)
+            # self attention
+            ops.cast_to(dh, dy)
+            dao = layer["o"].backward(dy, s["ao"], M)
+            ops.lora_up_add(dao, layer["o"].A_cat, 8, M, d.d_model)
+            qkv, rs = s["qkv"], 3 * inner
+            dqkv = torch.empty_like(qkv)
+            st, so = (Ld * rs, rs), (Ld * dao.stride(0), dao.stride(0))
+            ops.attention_bwd(qkv, qkv[:, inner:], qkv[:, 2 * inner:], s["ao"], dao, dqkv, dqkv[:, inner:],
+                              dqkv[:, 2 * inner:], B, d.t5_heads, Ld, Ld, d.d_kv, 1.0, st, st, st, so, so, s["lse"], ws,
+                              bias=bias, bias_zero=Ld - 1, kmask=dmask, causal=True)
+            dxn = layer["qkv"].backward(dqkv, s["xn"], M)
+            ops.rmsnorm_bwd(s["x"], layer["ln0"], dxn, d.t5_ln_eps, dh, lora_A=layer["qkv"].A_cat, R=24)
+            s.clear()
+        return d_enc                                         # (dh = grad of the frozen embedding rows: dropped)
+
+    # ------------------------------------------------------------------ loss (+ grads)
+    def loss(self, inputs_embeds, attention_mask, labels, decoder_attention_mask, backward=True, want_logits=False):
+        """T5ForConditionalGeneration.forward with labels (modeling_t5.py:1734-1893).
+        inputs_embeds fp32 [B, Le, D] (cuda), attention_mask [B, Le], labels int64 [B, Ld] (-100 = ignore).
+        -> dict(loss [1] fp32, logits?, d_inputs_embeds?)   and LoRA grads accumulated in the groups."""
+        d = self.d
+        B, Le, D = inputs_embeds.shape
+        Ld = labels.shape[1]
+        x = inputs_embeds.reshape(B * Le, D).contiguous()
+        kmask = attention_mask.to(device="cuda", dtype=torch.int32).contiguous()
+        labels = labels.to("cuda")
+        dmask = (decoder_attention_mask.to(device="cuda", dtype=torch.int32).contiguous()
+                 if decoder_attention_mask is not None else None)
+        dec_ids = torch.zeros_like(labels)                   # _shift_right, modeling_t5.py:919-948
+        dec_ids[:, 1:] = labels[:, :-1]
+        dec_ids.masked_fill_(dec_ids == -100, 0)
+        enc_saves = [] if backward else None
+        dec_saves = [] if backward else None
+        enc_ext, enc_h, enc_bias = self.encoder_forward(x, kmask, B, Le, enc_saves)
+        dec_ext, dec_h, dec_bias = self.decoder_forward(dec_ids, dmask, enc_ext, kmask, B, Ld, Le, dec_saves)
+        M = B * Ld
+        logits = self.lm_head.forward(dec_ext, M, out_dtype=torch.float32)       # [M, V] fp32
+        flat = labels.reshape(-1).contiguous()
+        n_valid = int((flat != -100).sum().item())
+        loss = torch.zeros((1,), dtype=torch.float32, device="cuda")
+        dlogits = torch.empty((M, d.vocab), dtype=BF, device="cuda") if backward else None
+        ops.cross_entropy(logits, flat, None, dlogits, 1.0 / max(n_valid, 1), loss_sum=loss)
+        out = {"loss": loss}
+        if want_logits:
+            out["logits"] = logits.view(B, Ld, d.vocab)
+            out["encoder_last_hidden_state"] = enc_ext[:, :D].float().view(B, Le, D)
+        if backward:
+            ddec_ext = self.lm_head.backward(dlogits, dec_ext, M)
+            d_enc = self.decoder_backward(dec_saves, dec_h, ddec_ext, dmask, enc_ext, kmask, B, Ld, Le, dec_bias)
+            d_in = self.encoder_backward(enc_saves, enc_h, d_enc, kmask, B, Le, enc_bias)
+            out["d_inputs_embeds"] = d_in.view(B, Le, D)
+        return out
+
+    # ------------------------------------------------------------------ generation
+    def encode(self, inputs_embeds, attention_mask):
+        B, Le, D = inputs_embeds.shape
+        kmask = attention_mask.to(device="cuda", dtype=torch.int32).contiguous()
+        enc_ext, _, _ = self.encoder_forward(inputs_embeds.reshape(B * Le, D).contiguous(), kmask, B, Le, None)
+        return enc_ext, kmask
+
+    def init_decode(self, enc_ext, B, Le, beams, max_len):
+        """Project the encoder output to every decoder layer's cross K/V ONCE (the reference re-projects it at
+        every step) and allocate the self-attention K/V cache."""
+        d = self.d
+        inner = d.t5_heads * d.d_kv
+        st = {"cross": [], "k": [], "v": [], "B": B, "Le": Le, "beams": beams, "max_len": max_len}
+        for layer in self.dec:
+            st["cross"].append(layer["ckv"].forward(enc_ext, B * Le))
+            st["k"].append(torch.zeros((B * beams, max_len, inner), dtype=BF, device="cuda"))
+            st["v"].append(torch.zeros((B * beams, max_len, inner), dtype=BF, device="cuda"))
+        st["bias"] = self._bias(self.dec_bias, max_len, max_len, False)
+        return st
+
+    def reorder_cache(self, st, beam_idx):
+        for i in range(len(self.dec)):
+            st["k"][i] = st["k"][i].index_select(0, beam_idx)
+            st["v"][i] = st["v"][i].index_select(0, beam_idx)
+
+    def decode_step(self, st, token_ids, t, enc_kmask):
+        """One incremental decoder step for token position t: token_ids int64 [B*beams] -> logits fp32 [B*beams, V]."""
+        d = self.d
+        NB = token_ids.shape[0]
+        inner = d.t5_heads * d.d_kv
+        Lm = st["max_len"]
+        h = torch.empty((NB, d.d_model), dtype=torch.float32, device="cuda")
+        ops.gather_rows(token_ids.to(torch.int32), self.emb, None, h)
+        for li, layer in enumerate(self.dec):
+            layer["ln_ff"] = layer["ln2"]
+            xn = self._ext(NB, d.d_model)
+            ops.norm(h, layer["ln0"], None, d.t5_ln_eps, 1, out_h=xn)
+            qkv = layer["qkv"].forward(xn, NB)
+            st["k"][li][:, t] = qkv[:, inner:2 * inner]
+            st["v"][li][:, t] = qkv[:, 2 * inner:]
+            ao = self._ext(NB, d.d_model)
+            ops.attention_fwd(qkv, st["k"][li], st["v"][li], ao, NB, d.t5_heads, 1, t + 1, d.d_kv, 1.0,
+                              (3 * inner, 3 * inner), (Lm * inner, inner), (Lm * inner, inner), (ao.stride(0), ao.stride(0)),
+                              bias=st["bias"], bias_zero=Lm - 1, q_pos0=t)
+            h1 = torch.empty_like(h)
+            layer["o"].forward(ao, NB, out=h1, resid=h)
+            xn2 = self._ext(NB, d.d_model)
+            ops.norm(h1, layer["ln1"], None, d.t5_ln_eps, 1, out_h=xn2)
+            cq = layer["cq"].forward(xn2, NB)
+            ckv = st["cross"][li]
+            co = self._ext(NB, d.d_model)
+            Le = st["Le"]
+            ops.attention_fwd(cq, ckv, ckv[:, inner:], co, NB, d.t5_heads, 1, Le, d.d_kv, 1.0, (inner, inner),
+                              (Le * 2 * inner, 2 * inner), (Le * 2 * inner, 2 * inner), (co.stride(0), co.stride(0)),
+                              kmask=enc_kmask, kv_div=st["beams"])
+            h2 = torch.empty_like(h)
+            layer["co"].forward(co, NB, out=h2, resid=h1)
+            h = self._ff(layer, h2, NB, None)
+        out = self._ext(NB, d.d_model)
+        ops.norm(h, self.dec_final_ln, None, d.t5_ln_eps, 1, out_h=out)
+        return self.lm_head.forward(out, NB, out_dtype=torch.float32)

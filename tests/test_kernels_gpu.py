@@ -194,6 +194,24 @@ def test_rmsnorm_bwd(ops):
     want = dres + x.grad
     ops.rmsnorm_bwd(x.detach(), w, dy, 1e-6, dres)
     _close(dres, want, 1e-4, 1e-5, "rmsnorm bwd")
+    # 16-bit extended dgrad buffer with the LoRA term folded in: dy_eff = dy + dy[:, C:C+R] . A
+    R = 24
+    ext = _rand((rows, C + 32), torch.bfloat16, 1.0, 40)
+    A = _rand((R, C), torch.float32, 0.05, 41)
+    dy_eff = ext[:, :C].float() + ext[:, C:C + R].float() @ A
+    x2 = x.detach().clone().requires_grad_(True)
+    y2 = w * (x2 * torch.rsqrt(x2.pow(2).mean(-1, keepdim=True) + 1e-6))
+    y2.backward(dy_eff)
+    dres2 = torch.zeros((rows, C), device="cuda")
+    ops.rmsnorm_bwd(x.detach(), w, ext, 1e-6, dres2, lora_A=A, R=R)
+    _close(dres2, x2.grad, 1e-4, 1e-5, "rmsnorm bwd + lora")
+    # standalone fix-up kernel, in place and accumulating
+    e2 = ext.clone()
+    ops.lora_up_add(e2, A, R, rows, C)
+    _close(e2[:, :C], dy_eff, 8e-3, 8e-3, "lora_up_add in place")
+    acc = torch.ones((rows, C), device="cuda")
+    ops.lora_up_add(ext.clone(), A, R, rows, C, acc=acc)
+    _close(acc, dy_eff + 1.0, 1e-5, 1e-5, "lora_up_add acc")
 
 
 # ------------------------------------------------------------------------------------------- small kernels
@@ -246,11 +264,13 @@ def test_cross_entropy(ops):
     n_valid = (labels >= 0).sum().item()
     row_loss = torch.zeros(rows, device="cuda")
     dl = torch.zeros((rows, V), dtype=torch.bfloat16, device="cuda")
-    ops.cross_entropy(logits, labels, row_loss, dl, 1.0 / n_valid)
+    loss = torch.zeros(1, device="cuda")
+    ops.cross_entropy(logits, labels, row_loss, dl, 1.0 / n_valid, loss_sum=loss)
     lg = logits.clone().requires_grad_(True)
     want = torch.nn.functional.cross_entropy(lg, labels, ignore_index=-100)
     want.backward()
     assert abs(row_loss.sum().item() / n_valid - want.item()) < 1e-4
+    assert abs(loss.item() - want.item()) < 1e-4
     _close(dl, lg.grad, 1e-2, 1e-7, "dlogits")
 
 
