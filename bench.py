@@ -1,0 +1,266 @@
+#!/usr/bin/env python
+"""bench.py -- BASELINE.json's metric: video-clips/sec, fwd+bwd (+AdamW step), 60-frame QVH config
+(batch 4 per GPU, 60 frames, 32 Q-Former queries, ViT-g + FlanT5-XL + LoRA r=8), synthetic data and
+seeded random-init weights (no network).
+
+  python bench.py --gpus N --steps K --warmup W            (N > 1: launched by torch.distributed.run)
+  python bench.py --impl reference ...                     the reference's CPU path (oracle port) on host cores
+
+One JSON line on stdout (rank 0).  value = clips/s with the frame tensor resident in HBM; e2e = the
+same step through the public API (BLIP2_MR.forward on a samples dict holding the video in PINNED
+HOST memory: H2D copy of [B,60,3,224,224] fp32 and the D2H loss read are inside the timed region).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+METRIC = "video_clips_per_sec_fwd_bwd_qvh60"
+UNIT = "clips/s"
+BATCH, FRAMES, QUERY_WORDS = 4, 60, 32
+FLOPS_PER_CLIP = 44.83e12          # GEMM + attention FLOPs, fwd+bwd, one 60-frame QVH clip
+
+
+def peaks():
+    try:
+        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))), "measured"
+    except Exception:
+        return {"bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "hbm_gbs": 6650.0}, "fallback"
+
+
+class ClockSampler(threading.Thread):
+    """Samples nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self.stop_flag = index, [], False
+
+    def run(self):
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                self.rows.append([x.strip() for x in out.strip().split(",")])
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def summary(self):
+        self.stop_flag = True
+        sm = sorted(float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit())
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) >= 7 and r[3 + i] == "Active" for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(self.rows[0][1]), "reasons": reasons,
+                "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------ CPU reference arm
+def cpu_reference_step(frames_sample, threads, full=True):
+    """One fwd+bwd of the oracle (CPU fp32 restatement of the reference path) on 1 clip x frames_sample frames,
+    FULL widths and depths.  Layer weights are one set of tensors aliased across layers (timing only)."""
+    from mr_blip_b200.dims import FULL, T5_PREFIX, init_state_dict
+    from mr_blip_b200.tokenizer import SyntheticT5Tokenizer
+    from oracle import blip2_mr as ob, synth
+    torch.set_num_threads(threads)
+    d = FULL
+    import dataclasses
+    one = init_state_dict(dataclasses.replace(d, vit_depth=1, qf_layers=2, t5_layers=1, t5_dec_layers=1), seed=1,
+                          lora_b_std=0.02)
+    sd = dict(one)
+
+    def alias(prefix_fmt, n, src_idx_fn):
+        for i in range(n):
+            src = prefix_fmt % src_idx_fn(i)
+            dst = prefix_fmt % i
+            for k in list(one):
+                if k.startswith(src):
+                    sd[dst + k[len(src):]] = one[k]
+
+    alias("visual_encoder.blocks.%d.", d.vit_depth, lambda i: 0)
+    alias("Qformer.bert.encoder.layer.%d.", d.qf_layers, lambda i: i % 2)
+    alias(T5_PREFIX + "encoder.block.%d.", d.t5_layers, lambda i: 0)
+    alias(T5_PREFIX + "decoder.block.%d.", d.t5_dec_layers, lambda i: 0)
+    leaves = {k: v.clone().requires_grad_(True) for k, v in sd.items() if "lora_" in k or k.startswith("t5_proj.")}
+    sd.update(leaves)
+    tok = SyntheticT5Tokenizer()
+    samples = synth.make_samples(batch=1, frames=frames_sample, query_words=QUERY_WORDS, seed=0)
+
+    def step():
+        t0 = time.perf_counter()
+        out = ob.forward_mr(sd, d, tok, samples)
+        out["loss"].backward()
+        for v in leaves.values():
+            v.grad = None
+        return time.perf_counter() - t0
+
+    return step
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    fs = args.cpu_frames
+    step = cpu_reference_step(fs, threads)
+    for _ in range(max(args.warmup, 0)):
+        step()
+    ts = [step() for _ in range(args.steps)]
+    per = sum(ts) / len(ts)
+    val = (fs / FRAMES) / per
+    sample = ("oracle port (fp32 PyTorch restatement of the reference path) fwd+bwd on 1 clip x %d of %d frames, full "
+              "ViT-g/Q-Former/FlanT5-XL widths and depths, layer weights aliased; clips/s extrapolated linearly in frames"
+              % (fs, FRAMES))
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": per * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "QVH: batch 4, 60 frames, 32 Q-Former queries, ViT-g + FlanT5-XL LoRA, fwd+bwd",
+                       "sample": sample},
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------ B200 arm
+def run_b200(args):
+    from mr_blip_b200 import _lib, ops, dist as mdist
+    from mr_blip_b200.blip2_mr import BLIP2_MR
+    from mr_blip_b200.dims import FULL, init_state_dict
+    from oracle import synth        # synthetic samples generator only (input construction, not compute)
+    import torch.distributed as tdist
+
+    rank, world, local = mdist.init_distributed_mode()
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    d = FULL
+    t_build = time.time()
+    sd = init_state_dict(d, seed=1234, lora_b_std=0.02, device="cuda")
+    model = BLIP2_MR(dims=d, state_dict=sd).to(dev).train()
+    del sd
+    trainable = [p for p in model.parameters() if p.requires_grad]
+    opt = torch.optim.AdamW(trainable, lr=1e-5, weight_decay=0.05, fused=True)
+    reducer = mdist.GradAllReducer(trainable)
+    samples = synth.make_samples(batch=BATCH, frames=FRAMES, query_words=QUERY_WORDS, seed=100 + rank)
+    video_host = samples["video"].pin_memory()
+    video_dev = video_host.to(dev)
+    build_s = time.time() - t_build
+
+    def step(video, read_loss):
+        samples["video"] = video
+        loss = model(samples)["loss"]
+        loss.backward()
+        reducer()
+        opt.step()
+        opt.zero_grad(set_to_none=True)
+        return loss.item() if read_loss else loss
+
+    def barrier():
+        if world > 1:
+            tdist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(video, read_loss, steps):
+        barrier()
+        l0 = _lib.launch_count
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            last = step(video, read_loss)
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            tdist.all_reduce(t, op=tdist.ReduceOp.MAX)
+            ms = t.item()
+        return ms, _lib.launch_count - l0, last
+
+    for _ in range(max(args.warmup, 3)):
+        step(video_dev, False)
+    sampler = ClockSampler(local)
+    sampler.start()
+    ms, launches, last_loss = timed(video_dev, False, args.steps)
+    clocks = sampler.summary()
+    for _ in range(2):
+        step(video_host, True)
+    ms_e2e, _, _ = timed(video_host, True, args.steps)
+    clips = BATCH * world * args.steps
+    value = clips / (ms / 1e3)
+    e2e = clips / (ms_e2e / 1e3)
+
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": "QVH: batch 4 per GPU, 60 frames, 32 Q-Former queries, ViT-g (fp16) + FlanT5-XL (bf16) "
+                                   "LoRA r=8, fwd+bwd + fused AdamW step, eval-mode dropout",
+                       "l2": "working set per step (GBs of activations, 144.5 MB frame tensor) exceeds the 126 MB L2",
+                       "parallelism": "dp%d" % world, "weights": "seeded random init (device RNG)",
+                       "model_build_s": round(build_s, 1)},
+            "clocks": clocks,
+            "e2e": {"value": e2e, "unit": UNIT, "ms_per_step": ms_e2e / args.steps,
+                    "h2d_bytes_per_step": int(video_host.numel() * 4 + BATCH * 2100 * 4), "d2h_bytes_per_step": 4},
+            "gpu_launches": int(launches),
+            "tensor_frac_of_step": round(value / world * FLOPS_PER_CLIP / 1e12 / peaks()[0]["bf16_tflops_sustained"], 4),
+            "loss": float(last_loss)}
+
+    if rank == 0:
+        # ---- roofline of the dominant kernel (gemm_tcgen05_kernel): CUDA events around every launch of one more step
+        ops.GEMM_PROFILE = []
+        step(video_dev, False)
+        torch.cuda.synchronize()
+        prof, ops.GEMM_PROFILE = ops.GEMM_PROFILE, None
+        flops = sum(2.0 * m * n * k for m, n, k, _, _ in prof)
+        gms = sum(a.elapsed_time(b) for _, _, _, a, b in prof)
+        pk, how = peaks()
+        ach = flops / (gms / 1e3) / 1e12
+        line["roofline"] = {"kernel": "gemm_tcgen05_kernel", "bound": "tensor", "achieved": ach,
+                            "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s", "frac": ach / pk["bf16_tflops_sustained"],
+                            "peak_source": how + " bf16_tflops_sustained (kernel timed inside a long step)",
+                            "launches_per_step": len(prof), "flops_per_launch": flops / max(len(prof), 1),
+                            "avg_launch_ms": gms / max(len(prof), 1), "share_of_step": gms / (ms / args.steps),
+                            "traffic": None}
+        if world == 1 and not args.no_cpu_baseline:
+            threads = os.cpu_count() or 1
+            cstep = cpu_reference_step(args.cpu_frames, threads)
+            cstep()
+            t = cstep()
+            line["cpu_baseline"] = {"value": (args.cpu_frames / FRAMES) / t, "unit": UNIT, "cores": threads, "kind": "port",
+                                    "sample": "oracle port fwd+bwd, 1 clip x %d of %d frames (full-depth model, aliased "
+                                              "layer weights), extrapolated linearly in frames; 1 warm-up + 1 timed"
+                                              % (args.cpu_frames, FRAMES)}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        tdist.barrier()
+        tdist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--cpu-frames", type=int, default=4, help="frames of one clip the CPU baseline sample runs")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -37,7 +37,8 @@ SIGNATURES = {
 }
 
 _lib = None
-launch_count = 0     # kernels-launching C-ABI calls made so far (bench.py reports the delta as gpu_launches)
+launch_count = 0     # kernels launched through the C ABI so far (bench.py reports the delta as gpu_launches)
+_KERNELS_PER_CALL = {"mrb_attention_bwd": 3}
 
 
 class MrbError(RuntimeError):
@@ -68,7 +69,7 @@ def call(name, *args):
     global launch_count
     lib = _lib or load()
     rc = getattr(lib, name)(*args)
-    launch_count += 1
+    launch_count += _KERNELS_PER_CALL.get(name, 1)
     if rc != 0:
         kind = {-1: "bad argument", -2: "CUDA error", -3: "unsupported shape"}.get(rc, "error")
         raise MrbError("%s failed: %s (%d) %s" % (name, kind, rc, lib.mrb_last_error().decode()))

@@ -207,15 +207,10 @@ class BLIP2_MR(Blip2Base):
         ids = self.t5_tokenizer([str(v) for v in values], add_special_tokens=False)["input_ids"]
         return [i[1:] if (len(i) > 1 and i[0] == 3) else i for i in ids]
 
-    def prompt_concatenation(self, timestamps, durations, frames_for_t5, frames_atts_for_t5, video_prompt_end,
-                             query_prompt, task_prompt):
-        """blip2_mr.py:572-824 (interleave branch).  Host side builds only an int32 row table; one gather
-        kernel writes inputs_embeds.  -> (inputs_embeds fp32 [B, L, D] cuda, attention_mask long [B, L] cuda,
-        video_prompt list[str]); the row table is kept for the backward scatter."""
+    def build_prompt_table(self, timestamps, durations, B, T, n, video_prompt_end, query_prompt, task_prompt):
+        """Host half of prompt_concatenation (blip2_mr.py:572-824, interleave branch): an int32 row table
+        [B, Le] (>= 0: embedding id, < 0: frame-token row -(idx+1), INT_MIN: zero row) + attention mask."""
         tok = self.t5_tokenizer
-        B, TN, C = frames_for_t5.shape
-        n = 1 if self.frame_token_aggregation else self.num_query_token
-        T = TN // n
         if "add_duration" in self.task:
             video_prompt_end = ["{}<extra_id_0>\n".format(">" + str(round(float(x), 2))) for x in durations]
         ts = torch.as_tensor(timestamps).detach().cpu()
@@ -231,7 +226,8 @@ class BLIP2_MR(Blip2Base):
         rows = []
         for j in range(B):
             ts_ids = self._clean_ids(ts_list[j].tolist())
-            dur_ids = self._clean_ids([dur_list[j] if not torch.is_tensor(dur_list[j]) else dur_list[j].item()])[0]
+            dur = dur_list[j]
+            dur_ids = self._clean_ids([dur.item() if torch.is_tensor(dur) else dur])[0]
             seq = []
             base = j * T * n
             for i in range(T):
@@ -241,15 +237,26 @@ class BLIP2_MR(Blip2Base):
             seq.extend(dur_ids)
             rows.append(seq)
         Lv = max(len(r) for r in rows)
-        Le = Lv + end.input_ids.shape[1] + text.input_ids.shape[1]
-        table = np.empty((B, Le), dtype=np.int64)
+        n_end, n_text = end.input_ids.shape[1], text.input_ids.shape[1]
+        table = np.empty((B, Lv + n_end + n_text), dtype=np.int64)
         for j, r in enumerate(rows):
             table[j, :Lv - len(r)] = INT_MIN                  # left padding = pad_token_id * ones = zero rows (:744-754)
             table[j, Lv - len(r):Lv] = r
-        table[:, Lv:Lv + end.input_ids.shape[1]] = end.input_ids.numpy()
-        table[:, Lv + end.input_ids.shape[1]:] = text.input_ids.numpy()
+        table[:, Lv:Lv + n_end] = end.input_ids.numpy()
+        table[:, Lv + n_end:] = text.input_ids.numpy()
         atts = torch.cat([torch.ones((B, Lv), dtype=torch.long), end.attention_mask, text.attention_mask], dim=1)
-        idx = torch.from_numpy(table.astype(np.int32)).to("cuda", non_blocking=True)
+        return table.astype(np.int32), atts, video_prompt
+
+    def prompt_concatenation(self, timestamps, durations, frames_for_t5, frames_atts_for_t5, video_prompt_end,
+                             query_prompt, task_prompt):
+        """blip2_mr.py:572-824.  The host builds only the row table; one gather kernel writes inputs_embeds.
+        -> (inputs_embeds fp32 [B, L, D] cuda, attention_mask long [B, L] cuda, video_prompt list[str])."""
+        B, TN, C = frames_for_t5.shape
+        n = 1 if self.frame_token_aggregation else self.num_query_token
+        table, atts, video_prompt = self.build_prompt_table(timestamps, durations, B, TN // n, n, video_prompt_end,
+                                                            query_prompt, task_prompt)
+        Le = table.shape[1]
+        idx = torch.from_numpy(table).to("cuda", non_blocking=True)
         _, _, t5 = self.engines()
         inputs = torch.empty((B * Le, C), dtype=torch.float32, device="cuda")
         ops.gather_rows(idx.reshape(-1), t5.emb, frames_for_t5.reshape(B * TN, C), inputs)

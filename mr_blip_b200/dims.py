@@ -75,13 +75,25 @@ LORA_TARGETS = ("q", "k", "v", "o", "wi_0", "wi_1", "wo", "lm_head")
 
 
 def _trunc_normal(shape, std, gen):
-    t = torch.empty(shape, dtype=torch.float32)
+    t = torch.empty(shape, dtype=torch.float32, device=gen.device)
     torch.nn.init.trunc_normal_(t, mean=0.0, std=std, a=-2.0, b=2.0, generator=gen)
     return t
 
 
 def _normal(shape, std, gen):
-    return torch.empty(shape, dtype=torch.float32).normal_(0.0, std, generator=gen)
+    return torch.empty(shape, dtype=torch.float32, device=gen.device).normal_(0.0, std, generator=gen)
+
+
+def _rand(shape, gen):
+    return torch.rand(shape, generator=gen, device=gen.device)
+
+
+def _ones(n, gen):
+    return torch.ones(n, device=gen.device)
+
+
+def _zeros(*shape, gen):
+    return torch.zeros(*shape, device=gen.device)
 
 
 def init_vit(d: Dims, gen, sd, prefix="visual_encoder."):
@@ -91,19 +103,19 @@ def init_vit(d: Dims, gen, sd, prefix="visual_encoder."):
     sd[prefix + "pos_embed"] = _trunc_normal((1, d.vit_tokens, W), 0.02, gen)
     fan_in = 3 * P * P
     bound = 1.0 / math.sqrt(fan_in)  # nn.Conv2d default init (kaiming_uniform a=sqrt5)
-    sd[prefix + "patch_embed.proj.weight"] = (torch.rand((W, 3, P, P), generator=gen) * 2 - 1) * bound
-    sd[prefix + "patch_embed.proj.bias"] = (torch.rand((W,), generator=gen) * 2 - 1) * bound
+    sd[prefix + "patch_embed.proj.weight"] = (_rand((W, 3, P, P), gen) * 2 - 1) * bound
+    sd[prefix + "patch_embed.proj.bias"] = (_rand((W,), gen) * 2 - 1) * bound
     for i in range(d.vit_depth):
         b = f"{prefix}blocks.{i}."
-        sd[b + "norm1.weight"] = torch.ones(W)
-        sd[b + "norm1.bias"] = torch.zeros(W)
+        sd[b + "norm1.weight"] = _ones(W, gen)
+        sd[b + "norm1.bias"] = _zeros(W, gen=gen)
         sd[b + "attn.q_bias"] = _normal((W,), 0.02, gen)   # zeros in the reference init; random here so
         sd[b + "attn.v_bias"] = _normal((W,), 0.02, gen)   # the bias path is exercised
         sd[b + "attn.qkv.weight"] = _trunc_normal((3 * W, W), 0.02, gen)
         sd[b + "attn.proj.weight"] = _trunc_normal((W, W), 0.02, gen) / math.sqrt(2.0 * (i + 1))
         sd[b + "attn.proj.bias"] = _normal((W,), 0.02, gen)
-        sd[b + "norm2.weight"] = torch.ones(W)
-        sd[b + "norm2.bias"] = torch.zeros(W)
+        sd[b + "norm2.weight"] = _ones(W, gen)
+        sd[b + "norm2.bias"] = _zeros(W, gen=gen)
         sd[b + "mlp.fc1.weight"] = _trunc_normal((d.vit_mlp, W), 0.02, gen)
         sd[b + "mlp.fc1.bias"] = _normal((d.vit_mlp,), 0.02, gen)
         sd[b + "mlp.fc2.weight"] = _trunc_normal((W, d.vit_mlp), 0.02, gen) / math.sqrt(2.0 * (i + 1))
@@ -118,19 +130,19 @@ def init_qformer(d: Dims, gen, sd, prefix="Qformer.bert."):
     """Qformer.py:664-674: Linear/Embedding normal(0, .02), LN 1/0; query_tokens normal(0, .02)
     (blip2.py:57-60); ln_vision is blip2.py:113-119's LayerNorm(1408)."""
     H, E = d.qf_hidden, d.vit_width
-    sd["ln_vision.weight"] = torch.ones(E) + _normal((E,), 0.02, gen)
+    sd["ln_vision.weight"] = _ones(E, gen) + _normal((E,), 0.02, gen)
     sd["ln_vision.bias"] = _normal((E,), 0.02, gen)
     sd["query_tokens"] = _normal((1, d.num_query, H), 0.02, gen)
-    sd[prefix + "embeddings.LayerNorm.weight"] = torch.ones(H)
-    sd[prefix + "embeddings.LayerNorm.bias"] = torch.zeros(H)
+    sd[prefix + "embeddings.LayerNorm.weight"] = _ones(H, gen)
+    sd[prefix + "embeddings.LayerNorm.bias"] = _zeros(H, gen=gen)
 
     def lin(name, out_f, in_f):
         sd[name + ".weight"] = _normal((out_f, in_f), 0.02, gen)
         sd[name + ".bias"] = _normal((out_f,), 0.02, gen)
 
     def ln(name):
-        sd[name + ".weight"] = torch.ones(H)
-        sd[name + ".bias"] = torch.zeros(H)
+        sd[name + ".weight"] = _ones(H, gen)
+        sd[name + ".bias"] = _zeros(H, gen=gen)
 
     for i in range(d.qf_layers):
         b = f"{prefix}encoder.layer.{i}."
@@ -162,11 +174,11 @@ def init_t5(d: Dims, gen, sd, prefix=T5_PREFIX, lora_b_std=0.0, lm_head_std=None
     def lora_linear(name, out_f, in_f, std):
         sd[name + ".base_layer.weight"] = _normal((out_f, in_f), std, gen)
         bound = 1.0 / math.sqrt(in_f)  # kaiming_uniform(a=sqrt 5) on [r, in_f]
-        sd[name + ".lora_A.default.weight"] = (torch.rand((r, in_f), generator=gen) * 2 - 1) * bound
+        sd[name + ".lora_A.default.weight"] = (_rand((r, in_f), gen) * 2 - 1) * bound
         if lora_b_std > 0:
             sd[name + ".lora_B.default.weight"] = _normal((out_f, r), lora_b_std, gen)
         else:
-            sd[name + ".lora_B.default.weight"] = torch.zeros(out_f, r)
+            sd[name + ".lora_B.default.weight"] = _zeros(out_f, r, gen=gen)
 
     def attn(name, has_bias):
         lora_linear(name + ".q", inner, D, (D * KV) ** -0.5)
@@ -188,38 +200,45 @@ def init_t5(d: Dims, gen, sd, prefix=T5_PREFIX, lora_b_std=0.0, lm_head_std=None
     for i in range(d.t5_layers):
         b = f"{prefix}encoder.block.{i}."
         attn(b + "layer.0.SelfAttention", i == 0)
-        sd[b + "layer.0.layer_norm.weight"] = torch.ones(D) + _normal((D,), 0.02, gen)
+        sd[b + "layer.0.layer_norm.weight"] = _ones(D, gen) + _normal((D,), 0.02, gen)
         ff(b + "layer.1.DenseReluDense")
-        sd[b + "layer.1.layer_norm.weight"] = torch.ones(D) + _normal((D,), 0.02, gen)
-    sd[prefix + "encoder.final_layer_norm.weight"] = torch.ones(D)
+        sd[b + "layer.1.layer_norm.weight"] = _ones(D, gen) + _normal((D,), 0.02, gen)
+    sd[prefix + "encoder.final_layer_norm.weight"] = _ones(D, gen)
     for i in range(d.t5_dec_layers):
         b = f"{prefix}decoder.block.{i}."
         attn(b + "layer.0.SelfAttention", i == 0)
-        sd[b + "layer.0.layer_norm.weight"] = torch.ones(D) + _normal((D,), 0.02, gen)
+        sd[b + "layer.0.layer_norm.weight"] = _ones(D, gen) + _normal((D,), 0.02, gen)
         attn(b + "layer.1.EncDecAttention", False)
-        sd[b + "layer.1.layer_norm.weight"] = torch.ones(D) + _normal((D,), 0.02, gen)
+        sd[b + "layer.1.layer_norm.weight"] = _ones(D, gen) + _normal((D,), 0.02, gen)
         ff(b + "layer.2.DenseReluDense")
-        sd[b + "layer.2.layer_norm.weight"] = torch.ones(D) + _normal((D,), 0.02, gen)
-    sd[prefix + "decoder.final_layer_norm.weight"] = torch.ones(D)
+        sd[b + "layer.2.layer_norm.weight"] = _ones(D, gen) + _normal((D,), 0.02, gen)
+    sd[prefix + "decoder.final_layer_norm.weight"] = _ones(D, gen)
     lora_linear(prefix + "lm_head", d.vocab, D, lm_head_std)
 
 
 def init_t5_proj(d: Dims, gen, sd):
     """nn.Linear(768, 2048) default init (blip2_mr.py:267-269)."""
     bound = 1.0 / math.sqrt(d.qf_hidden)
-    sd["t5_proj.weight"] = (torch.rand((d.d_model, d.qf_hidden), generator=gen) * 2 - 1) * bound
-    sd["t5_proj.bias"] = (torch.rand((d.d_model,), generator=gen) * 2 - 1) * bound
+    sd["t5_proj.weight"] = (_rand((d.d_model, d.qf_hidden), gen) * 2 - 1) * bound
+    sd["t5_proj.bias"] = (_rand((d.d_model,), gen) * 2 - 1) * bound
 
 
-def init_state_dict(d: Dims = FULL, seed: int = 1234, lora_b_std: float = 0.0, parts=("vit", "qformer", "t5")):
-    """Seeded fp32 CPU state dict with the reference's key names (SURVEY.md §5 checkpoint row)."""
+def init_state_dict(d: Dims = FULL, seed: int = 1234, lora_b_std: float = 0.0, parts=("vit", "qformer", "t5"),
+                    device="cpu"):
+    """Seeded fp32 state dict with the reference's key names (SURVEY.md §5 checkpoint row).  device="cpu" is
+    what parity tests and golden vectors use (bit-reproducible); device="cuda" draws the full-size 4 B
+    parameters on the GPU in seconds for throughput runs (different random stream, same distributions)."""
     sd = {}
+
+    def gen(k):
+        return torch.Generator(device=device).manual_seed(seed + k)
+
     # one generator per part so that a part's weights do not depend on which other parts are built
     if "vit" in parts:
-        init_vit(d, torch.Generator().manual_seed(seed), sd)
+        init_vit(d, gen(0), sd)
     if "qformer" in parts:
-        init_qformer(d, torch.Generator().manual_seed(seed + 1), sd)
-        init_t5_proj(d, torch.Generator().manual_seed(seed + 2), sd)
+        init_qformer(d, gen(1), sd)
+        init_t5_proj(d, gen(2), sd)
     if "t5" in parts:
-        init_t5(d, torch.Generator().manual_seed(seed + 3), sd, lora_b_std=lora_b_std)
+        init_t5(d, gen(3), sd, lora_b_std=lora_b_std)
     return sd

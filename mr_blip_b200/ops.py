@@ -8,6 +8,7 @@ from . import _lib
 F16, BF16, F32 = 0, 1, 2
 _DT = {torch.float16: F16, torch.bfloat16: BF16, torch.float32: F32}
 INT_MIN = -2 ** 31
+GEMM_PROFILE = None      # set to a list to record (M, N, K, cuda start event, cuda end event) per GEMM launch
 
 
 def _stream():
@@ -44,9 +45,16 @@ def gemm(a, b, out=None, bias=None, gelu=False, resid=None, out_dtype=None, row_
     if resid is not None:
         _check(resid, torch.float32)
         assert resid.stride(1) == 1
+    if GEMM_PROFILE is not None:
+        ev0 = torch.cuda.Event(enable_timing=True)
+        ev0.record()
     _lib.call("mrb_gemm", a.data_ptr(), a.stride(0), b.data_ptr(), b.stride(0), M, N, K, _DT[a.dtype], _ptr(bias),
               int(gelu), _ptr(resid), resid.stride(0) if resid is not None else 0, out.data_ptr(), _DT[out.dtype],
               out.stride(0), row_group, force_bn, _stream())
+    if GEMM_PROFILE is not None:
+        ev1 = torch.cuda.Event(enable_timing=True)
+        ev1.record()
+        GEMM_PROFILE.append((M, N, K, ev0, ev1))
     return out
 
 

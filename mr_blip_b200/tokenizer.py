@@ -139,9 +139,15 @@ class SyntheticT5Tokenizer:
 
 
 def load_t5_tokenizer(name="google/flan-t5-xl"):
-    """Real tokenizer when cached locally, else the synthetic stand-in (never touches the network)."""
+    """Real tokenizer when its files are cached locally, else the synthetic stand-in (never touches the
+    network).  transformers 5.x returns an EMPTY tokenizer instead of raising when files are missing, so the
+    result is validated before it is trusted."""
     try:
         from transformers import T5TokenizerFast
-        return T5TokenizerFast.from_pretrained(name, local_files_only=True)
+        tok = T5TokenizerFast.from_pretrained(name, local_files_only=True)
+        ids = tok("the video shows 25 seconds")["input_ids"]
+        if len(tok) >= 32000 and tok.unk_token_id not in ids[:-1] and len(ids) >= 5:
+            return tok
     except Exception:
-        return SyntheticT5Tokenizer()
+        pass
+    return SyntheticT5Tokenizer()

