@@ -165,7 +165,7 @@ def run_b200(args):
         reducer()
         opt.step()
         opt.zero_grad(set_to_none=True)
-        return loss.item() if read_loss else loss
+        return loss.item() if read_loss else loss.detach()
 
     def barrier():
         if world > 1:

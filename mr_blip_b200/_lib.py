@@ -65,10 +65,21 @@ def load():
     return lib
 
 
+PROFILE = None       # set to a list: every call appends (name, start_event, end_event) (tools/step_breakdown.py)
+
+
 def call(name, *args):
     global launch_count
     lib = _lib or load()
-    rc = getattr(lib, name)(*args)
+    if PROFILE is not None:
+        import torch
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        rc = getattr(lib, name)(*args)
+        e1.record()
+        PROFILE.append((name, e0, e1))
+    else:
+        rc = getattr(lib, name)(*args)
     launch_count += _KERNELS_PER_CALL.get(name, 1)
     if rc != 0:
         kind = {-1: "bad argument", -2: "CUDA error", -3: "unsupported shape"}.get(rc, "error")
