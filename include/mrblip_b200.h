@@ -36,6 +36,12 @@ int mrb_attention_fwd(const void* q, long long q_bs, long long q_rs, const void*
                       const void* v, long long v_bs, long long v_rs, void* o, long long o_bs, long long o_rs,
                       int B, int H, int Lq, int Lk, int hd, int dtype, float scale, const float* bias, int bias_len,
                       int bias_zero, const int* kmask, int kv_div, int causal, int q_pos0, float* lse, void* stream);
+/* Same contract, tcgen05/TMEM/TMA implementation (S and O tiles in tensor memory, K/V by TMA, P through swizzled smem)
+ * for the large shapes: hd == 64 (T5) or 64 < hd <= 96 (ViT hd 88, zero-filled to 96 by the tensor map). */
+int mrb_attention_fwd_tc(const void* q, long long q_bs, long long q_rs, const void* k, long long k_bs, long long k_rs,
+                         const void* v, long long v_bs, long long v_rs, void* o, long long o_bs, long long o_rs,
+                         int B, int H, int Lq, int Lk, int hd, int dtype, float scale, const float* bias, int bias_len,
+                         int bias_zero, const int* kmask, int kv_div, int causal, int q_pos0, float* lse, void* stream);
 /* dQ, dK, dV of the above (autograd of modeling_t5.py:561-610); hd <= 64. delta_ws: fp32 [B*H*Lq] workspace. */
 int mrb_attention_bwd(const void* q, long long q_bs, long long q_rs, const void* k, long long k_bs, long long k_rs,
                       const void* v, long long v_bs, long long v_rs, const void* o, long long o_bs, long long o_rs,

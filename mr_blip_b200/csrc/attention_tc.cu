@@ -1,0 +1,418 @@
+// tcgen05 flash-attention forward for the two big attention shapes of the path:
+//   * T5 encoder self-attention (modeling_t5.py:561-610): hd 64, L ~ 2037, additive bucketed bias + padding mask
+//   * EVA ViT attention (eva_vit.py:128-145): hd 88 (handled as 64 + 32 with TMA zero fill of d >= 88), 257 tokens
+// One CTA per (128-query tile, head, batch):
+//   warp 0      TMA producer: Q once, then a ring of K/V tiles (4-D tensor maps: d, head, token, batch)
+//   warp 1      single-thread tcgen05.mma issuer:  S_j = Q K_j^T  (128 x BKV x hd, fp32 in TMEM, double buffered)
+//                                                  O_j = P_j V_j   (128 x hd, V read MN-major straight from its [key][d] tile)
+//   warps 2-5   softmax: one thread per query row (TMEM lane): tcgen05.ld S, scale/bias/mask, online max/sum, exp2,
+//               P_j -> bf16/fp16 -> SWIZZLE_128B smem (A operand of the PV MMA), O accumulated in registers from the
+//               per-tile TMEM result so no TMEM read-modify-write hazard exists.
+// The last KV tile is issued with N = round_up(remaining keys, 16), so 257 keys cost 2 x 128 + 16, not 3 x 128.
+#include "common.cuh"
+
+namespace mrb {
+
+struct AttnTcParams {
+  int B, H, Lq, Lk, hd;
+  int dtype;
+  float scale;
+  const float* bias; int bias_len, bias_zero;   // [H, bias_len], index (j - i) + bias_zero
+  const int* kmask;                              // [B, Lk] or null
+  int kv_div, causal, q_pos0;
+  void* o; long long o_bs, o_rs;
+  float* lse;                                    // [B, H, Lq] or null
+};
+
+constexpr int TQ = 128, TKV = 128;
+
+__device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+
+// generic UMMA smem descriptor: swizzle_bytes 128 / 64, sbo / lbo in bytes
+__device__ __forceinline__ uint64_t umma_desc(uint32_t addr, uint32_t lbo, uint32_t sbo, uint32_t layout) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((addr & 0x3FFFF) >> 4);
+  d |= static_cast<uint64_t>((lbo >> 4) & 0x3FFF) << 16;
+  d |= static_cast<uint64_t>((sbo >> 4) & 0x3FFF) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(layout) << 61;
+  return d;
+}
+constexpr uint32_t LAYOUT_SW128 = 2, LAYOUT_SW64 = 4;
+
+__host__ __device__ constexpr uint32_t idesc_f16(int fmt, int M, int N, int b_mn_major) {
+  return (1u << 4) | (static_cast<uint32_t>(fmt) << 7) | (static_cast<uint32_t>(fmt) << 10) |
+         (static_cast<uint32_t>(b_mn_major) << 16) | (static_cast<uint32_t>(N >> 3) << 17) |
+         (static_cast<uint32_t>(M >> 4) << 24);
+}
+
+template <int HD>   // 64, or 96 (= 64-wide SW128 atom + 32-wide SW64 atom)
+struct TcSmem {
+  static constexpr bool SPLIT = (HD == 96);
+  static constexpr int Q_BYTES = TQ * 64 * 2 + (SPLIT ? TQ * 32 * 2 : 0);
+  static constexpr int KV_ONE = TKV * 64 * 2 + (SPLIT ? TKV * 32 * 2 : 0);   // one of K or V
+  static constexpr int STAGE_BYTES = 2 * KV_ONE;
+  static constexpr int STAGES = 2;
+  static constexpr int P_BYTES = TQ * TKV * 2;                                 // two 64-key atoms
+  static constexpr int OFF_Q = 0;
+  static constexpr int OFF_KV = Q_BYTES;
+  static constexpr int OFF_P = OFF_KV + STAGES * STAGE_BYTES;
+  static constexpr int OFF_BAR = OFF_P + 2 * P_BYTES;
+  static constexpr int NBAR = 1 + 2 * STAGES + 12;
+  static constexpr int TOTAL = OFF_BAR + NBAR * 8 + 16 + 1024;
+};
+
+template <int HD>
+__global__ void __launch_bounds__(192, 1)
+attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                   const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmQ2,
+                   const __grid_constant__ CUtensorMap tmK2, const __grid_constant__ CUtensorMap tmV2,
+                   const AttnTcParams p) {
+  using S = TcSmem<HD>;
+  constexpr bool SPLIT = S::SPLIT;
+  constexpr int STAGES = S::STAGES;
+  constexpr uint32_t TMEM_COLS = 512;
+  constexpr int S_COL = 0, O_COL = 256;          // S0 [0,128) S1 [128,256) ; O0 [256,256+HD) O1 [256+HD, 256+2HD)
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S::OFF_BAR);
+  uint64_t* q_full = bars;
+  uint64_t* kv_full = bars + 1;
+  uint64_t* kv_empty = kv_full + STAGES;
+  uint64_t* s_full = kv_empty + STAGES;
+  uint64_t* s_empty = s_full + 2;
+  uint64_t* p_full = s_empty + 2;
+  uint64_t* p_empty = p_full + 2;
+  uint64_t* o_full = p_empty + 2;
+  uint64_t* o_empty = o_full + 2;
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + S::NBAR);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int b = blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * TQ;
+  const int bkv = b / p.kv_div;
+  int n_kv = (p.Lk + TKV - 1) / TKV;
+  if (p.causal) n_kv = min(n_kv, (q0 + TQ - 1 + p.q_pos0) / TKV + 1);
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV);
+    mbar_init(q_full, 1);
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 1); }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&s_full[s], 1); mbar_init(&s_empty[s], 4);
+      mbar_init(&p_full[s], 4); mbar_init(&p_empty[s], 1);
+      mbar_init(&o_full[s], 1); mbar_init(&o_empty[s], 4);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_holder, TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_holder;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      mbar_expect_tx(q_full, S::Q_BYTES);
+      tma_load_4d(smem + S::OFF_Q, &tmQ, q_full, 0, h, q0, b);
+      if (SPLIT) tma_load_4d(smem + S::OFF_Q + TQ * 128, &tmQ2, q_full, 64, h, q0, b);
+      for (int j = 0; j < n_kv; ++j) {
+        const int st = j % STAGES;
+        mbar_wait(&kv_empty[st], ((j / STAGES) & 1) ^ 1);
+        uint8_t* sk = smem + S::OFF_KV + st * S::STAGE_BYTES;
+        uint8_t* sv = sk + S::KV_ONE;
+        mbar_expect_tx(&kv_full[st], S::STAGE_BYTES);
+        tma_load_4d(sk, &tmK, &kv_full[st], 0, h, j * TKV, bkv);
+        tma_load_4d(sv, &tmV, &kv_full[st], 0, h, j * TKV, bkv);
+        if (SPLIT) {
+          tma_load_4d(sk + TKV * 128, &tmK2, &kv_full[st], 64, h, j * TKV, bkv);
+          tma_load_4d(sv + TKV * 128, &tmV2, &kv_full[st], 64, h, j * TKV, bkv);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    const int fmt = p.dtype == MRB_DT_BF16 ? 1 : 0;
+    const uint32_t q_addr = smem_u32(smem + S::OFF_Q);
+    auto tail_n = [&](int j) {   // keys in KV tile j, rounded up to the UMMA N granularity (16)
+      const int rem = p.Lk - j * TKV;
+      return rem >= TKV ? TKV : ((rem + 15) & ~15);
+    };
+    auto issue_pv = [&](int i) {
+      const int st = i % STAGES, pb = i & 1;
+      mbar_wait(&p_full[pb], (i >> 1) & 1);
+      mbar_wait(&o_empty[pb], ((i >> 1) & 1) ^ 1);
+      tc_fence_after();
+      if (lane == 0) {
+        const uint32_t p_addr = smem_u32(smem + S::OFF_P + pb * S::P_BYTES);
+        const uint32_t v_addr = smem_u32(smem + S::OFF_KV + st * S::STAGE_BYTES + S::KV_ONE);
+        const uint32_t d_o = tmem_base + O_COL + pb * HD;
+        const int ksteps = tail_n(i) / 16;
+        const uint32_t id64 = idesc_f16(fmt, TQ, 64, 1);
+        const uint32_t id32 = idesc_f16(fmt, TQ, 32, 1);
+        for (int k = 0; k < ksteps; ++k) {
+          // A = P (K-major, SW128): 64-key atom (k/4), 32-byte step inside the atom
+          const uint64_t a = umma_desc(p_addr + (k >> 2) * (TQ * 128) + (k & 3) * 32, 16, 1024, LAYOUT_SW128);
+          // B = V [key][d] read MN-major: 16 keys = two 8-key groups of 1024 B (SW128) / 512 B (SW64)
+          const uint64_t bv = umma_desc(v_addr + k * 2048, TKV * 128, 1024, LAYOUT_SW128);
+          umma_f16(d_o, a, bv, id64, k > 0 ? 1u : 0u);
+          if (SPLIT) {
+            const uint64_t bv2 = umma_desc(v_addr + TKV * 128 + k * 1024, TKV * 64, 512, LAYOUT_SW64);
+            umma_f16(d_o + 64, a, bv2, id32, k > 0 ? 1u : 0u);
+          }
+        }
+        umma_commit(&o_full[pb]);
+        umma_commit(&kv_empty[st]);
+        umma_commit(&p_empty[pb]);
+      }
+      __syncwarp();
+    };
+    mbar_wait(q_full, 0);
+    for (int j = 0; j < n_kv; ++j) {
+      const int st = j % STAGES, sb = j & 1;
+      mbar_wait(&kv_full[st], (j / STAGES) & 1);
+      mbar_wait(&s_empty[sb], ((j >> 1) & 1) ^ 1);
+      tc_fence_after();
+      if (lane == 0) {
+        const uint32_t k_addr = smem_u32(smem + S::OFF_KV + st * S::STAGE_BYTES);
+        const uint32_t d_s = tmem_base + S_COL + sb * TKV;
+        const uint32_t ids = idesc_f16(fmt, TQ, tail_n(j), 0);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          umma_f16(d_s, umma_desc(q_addr + k * 32, 16, 1024, LAYOUT_SW128), umma_desc(k_addr + k * 32, 16, 1024, LAYOUT_SW128),
+                   ids, k > 0 ? 1u : 0u);
+        if (SPLIT) {
+#pragma unroll
+          for (int k = 0; k < 2; ++k)
+            umma_f16(d_s, umma_desc(q_addr + TQ * 128 + k * 32, 16, 512, LAYOUT_SW64),
+                     umma_desc(k_addr + TKV * 128 + k * 32, 16, 512, LAYOUT_SW64), ids, 1u);
+        }
+        umma_commit(&s_full[sb]);
+      }
+      __syncwarp();
+      if (j > 0) issue_pv(j - 1);
+    }
+    issue_pv(n_kv - 1);
+  } else {
+    // ===================== softmax / epilogue warps: one thread per query row =====================
+    const int quad = warp & 3;
+    const int r = quad * 32 + lane;
+    const int i_abs = min(q0 + r, p.Lq - 1) + p.q_pos0;     // rows past Lq are computed but never stored
+    const uint32_t lane_base = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
+    const float LOG2E = 1.4426950408889634f;
+    const float sl2 = p.scale * LOG2E;
+    const float* brow = p.bias ? p.bias + static_cast<long long>(h) * p.bias_len + p.bias_zero - i_abs : nullptr;
+    const int* mrow = p.kmask ? p.kmask + static_cast<long long>(bkv) * p.Lk : nullptr;
+    float o_reg[HD];
+#pragma unroll
+    for (int c = 0; c < HD; ++c) o_reg[c] = 0.f;
+    float m_run = -INFINITY, l_run = 0.f, corr_prev = 1.f;
+
+    auto accumulate_o = [&](int i, float corr) {
+      const int pb = i & 1;
+      mbar_wait(&o_full[pb], (i >> 1) & 1);
+      tc_fence_after();
+#pragma unroll
+      for (int c = 0; c < HD; c += 32) {
+        uint32_t v[32];
+        tmem_ld_32x32b_x32(lane_base + O_COL + pb * HD + c, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int e = 0; e < 32; ++e) o_reg[c + e] = o_reg[c + e] * corr + __uint_as_float(v[e]);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&o_empty[pb]);
+    };
+
+    for (int j = 0; j < n_kv; ++j) {
+      const int sb = j & 1;
+      const int kv0 = j * TKV;
+      const int ncols = min(TKV, p.Lk - kv0);            // valid keys in this tile
+      const int nc32 = (ncols + 31) & ~31;
+      mbar_wait(&s_full[sb], (j >> 1) & 1);
+      tc_fence_after();
+      // tile-level mask summary (warp-uniform): 128-bit mask of attendable keys
+      uint32_t mbits[4] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu};
+      bool need_elem_mask = (ncols < TKV) || (p.causal && kv0 + TKV - 1 > q0 + quad * 32 + p.q_pos0);
+      if (mrow) {
+#pragma unroll
+        for (int w = 0; w < 4; ++w) {
+          const int jj = kv0 + w * 32 + lane;
+          const int ok = (jj < p.Lk) ? __ldg(mrow + jj) : 0;
+          mbits[w] = __ballot_sync(0xffffffffu, ok != 0);
+        }
+        need_elem_mask = need_elem_mask || ((mbits[0] & mbits[1] & mbits[2] & mbits[3]) != 0xffffffffu);
+      }
+      auto score = [&](float raw, int c) {              // c = column within tile
+        float s = raw * sl2;
+        if (brow && c < ncols) s += __ldg(brow + kv0 + c) * LOG2E;
+        if (need_elem_mask) {
+          const bool ok = (c < ncols) && ((mbits[c >> 5] >> (c & 31)) & 1u) && !(p.causal && kv0 + c > i_abs);
+          if (!ok) s = -INFINITY;
+        }
+        return s;                                        // log2 domain
+      };
+      // pass 1: row max
+      float m_new = m_run;
+      for (int c = 0; c < nc32; c += 32) {
+        uint32_t v[32];
+        tmem_ld_32x32b_x32(lane_base + S_COL + sb * TKV + c, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int e = 0; e < 32; ++e) m_new = fmaxf(m_new, score(__uint_as_float(v[e]), c + e));
+      }
+      const float m_use = (m_new == -INFINITY) ? 0.f : m_new;
+      const float corr = (m_run == -INFINITY) ? 0.f : exp2f(m_run - m_use);
+      m_run = m_new;
+      // pass 2: P = exp2(s - m) -> 16-bit -> swizzled smem
+      const int pb = j & 1;
+      mbar_wait(&p_empty[pb], ((j >> 1) & 1) ^ 1);
+      uint8_t* prow = smem + S::OFF_P + pb * S::P_BYTES + r * 128;
+      float rsum = 0.f;
+      const int npad = (ncols + 15) & ~15;               // the PV MMA reads keys [0, npad)
+      for (int c = 0; c < nc32; c += 32) {
+        uint32_t v[32];
+        tmem_ld_32x32b_x32(lane_base + S_COL + sb * TKV + c, v);
+        tmem_ld_wait();
+        uint32_t pk[16];
+#pragma unroll
+        for (int e = 0; e < 32; e += 2) {
+          const float p0 = exp2f(score(__uint_as_float(v[e]), c + e) - m_use);
+          const float p1 = exp2f(score(__uint_as_float(v[e + 1]), c + e + 1) - m_use);
+          rsum += p0 + p1;
+          pk[e >> 1] = pack2(p0, p1, p.dtype);
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {                    // 4 x 16-byte chunks of 8 keys
+          const int key0 = c + q * 8;
+          if (key0 < npad) {
+            const int atom = key0 >> 6, chunk = (key0 & 63) >> 3;
+            *reinterpret_cast<uint4*>(prow + atom * (TQ * 128) + ((chunk ^ (r & 7)) << 4)) =
+                make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
+          }
+        }
+      }
+      l_run = l_run * corr + rsum;
+      fence_proxy_async();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) { mbar_arrive(&p_full[pb]); mbar_arrive(&s_empty[sb]); }
+      // fold the previous tile's PV result while this tile's PV runs
+      if (j > 0) accumulate_o(j - 1, corr_prev);
+      corr_prev = corr;
+    }
+    accumulate_o(n_kv - 1, corr_prev);
+    // epilogue
+    const int i = q0 + r;
+    if (i < p.Lq) {
+      const float inv = l_run > 0.f ? 1.f / l_run : 0.f;
+      uint16_t* orow = static_cast<uint16_t*>(p.o) + b * p.o_bs + static_cast<long long>(i) * p.o_rs + static_cast<long long>(h) * p.hd;
+#pragma unroll
+      for (int c = 0; c < HD; c += 8) {
+        if (c < p.hd) {
+          *reinterpret_cast<uint4*>(orow + c) =
+              make_uint4(pack2(o_reg[c] * inv, o_reg[c + 1] * inv, p.dtype), pack2(o_reg[c + 2] * inv, o_reg[c + 3] * inv, p.dtype),
+                         pack2(o_reg[c + 4] * inv, o_reg[c + 5] * inv, p.dtype), pack2(o_reg[c + 6] * inv, o_reg[c + 7] * inv, p.dtype));
+        }
+      }
+      if (p.lse) p.lse[(static_cast<long long>(b) * p.H + h) * p.Lq + i] = (m_run + log2f(l_run)) * 0.6931471805599453f;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+// ---------------------------------------------------------------- host
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(ptr);
+  }
+  return fn;
+}
+
+// 4-D view (d, head, token, batch) of a [B, L, heads*hd] 16-bit tensor; box = box_d x 1 x 128 x 1
+static int make_tmap4(CUtensorMap* map, const void* base, int dtype, int hd, int heads, int L, int B, long long rs,
+                      long long bs, int box_d, bool sw64) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) return MRB_ERR_CUDA;
+  cuuint64_t gdim[4] = {static_cast<cuuint64_t>(hd), static_cast<cuuint64_t>(heads), static_cast<cuuint64_t>(L),
+                        static_cast<cuuint64_t>(B)};
+  cuuint64_t gstr[3] = {static_cast<cuuint64_t>(hd) * 2, static_cast<cuuint64_t>(rs) * 2, static_cast<cuuint64_t>(bs) * 2};
+  cuuint32_t box[4] = {static_cast<cuuint32_t>(box_d), 1, 128, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = fn(map, dtype == MRB_DT_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4,
+                  const_cast<void*>(base), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  sw64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? MRB_OK : MRB_ERR_CUDA;
+}
+
+template <int HD>
+static int launch_tc(const CUtensorMap* maps, const AttnTcParams& p, cudaStream_t s) {
+  using S = TcSmem<HD>;
+  static bool cfg = false;
+  if (!cfg) {
+    cudaError_t e = cudaFuncSetAttribute(attn_fwd_tc_kernel<HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL);
+    if (e != cudaSuccess) return mrb_set_error(e);
+    cfg = true;
+  }
+  dim3 grid((p.Lq + TQ - 1) / TQ, p.H, p.B);
+  attn_fwd_tc_kernel<HD><<<grid, 192, S::TOTAL, s>>>(maps[0], maps[1], maps[2], maps[3], maps[4], maps[5], p);
+  MRB_CHECK_LAUNCH();
+  return MRB_OK;
+}
+
+}  // namespace mrb
+
+using namespace mrb;
+
+// Same contract as mrb_attention_fwd (include/mrblip_b200.h); requires hd == 64 or 64 < hd <= 96 with hd % 8 == 0.
+extern "C" int mrb_attention_fwd_tc(const void* q, long long q_bs, long long q_rs, const void* k, long long k_bs, long long k_rs,
+                                    const void* v, long long v_bs, long long v_rs, void* o, long long o_bs, long long o_rs,
+                                    int B, int H, int Lq, int Lk, int hd, int dtype, float scale, const float* bias,
+                                    int bias_len, int bias_zero, const int* kmask, int kv_div, int causal, int q_pos0,
+                                    float* lse, void* stream) {
+  if (B <= 0 || H <= 0 || Lq <= 0 || Lk <= 0) return MRB_OK;
+  if (dtype != MRB_DT_F16 && dtype != MRB_DT_BF16) return MRB_ERR_ARG;
+  if (!(hd == 64 || (hd > 64 && hd <= 96 && (hd & 7) == 0))) return MRB_ERR_UNSUPPORTED;
+  if ((q_rs | k_rs | v_rs | o_rs | q_bs | k_bs | v_bs | o_bs) & 7) return MRB_ERR_ARG;
+  if (kv_div <= 0) kv_div = 1;
+  const int Bkv = (B + kv_div - 1) / kv_div;
+  CUtensorMap maps[6];
+  const bool split = hd > 64;
+  int rc = make_tmap4(&maps[0], q, dtype, hd, H, Lq, B, q_rs, q_bs, 64, false);
+  if (!rc) rc = make_tmap4(&maps[1], k, dtype, hd, H, Lk, Bkv, k_rs, k_bs, 64, false);
+  if (!rc) rc = make_tmap4(&maps[2], v, dtype, hd, H, Lk, Bkv, v_rs, v_bs, 64, false);
+  if (!rc && split) {
+    rc = make_tmap4(&maps[3], q, dtype, hd, H, Lq, B, q_rs, q_bs, 32, true);
+    if (!rc) rc = make_tmap4(&maps[4], k, dtype, hd, H, Lk, Bkv, k_rs, k_bs, 32, true);
+    if (!rc) rc = make_tmap4(&maps[5], v, dtype, hd, H, Lk, Bkv, v_rs, v_bs, 32, true);
+  } else if (!rc) {
+    maps[3] = maps[0]; maps[4] = maps[1]; maps[5] = maps[2];
+  }
+  if (rc) return rc;
+  AttnTcParams p{};
+  p.B = B; p.H = H; p.Lq = Lq; p.Lk = Lk; p.hd = hd; p.dtype = dtype; p.scale = scale;
+  p.bias = bias; p.bias_len = bias_len; p.bias_zero = bias_zero; p.kmask = kmask; p.kv_div = kv_div;
+  p.causal = causal; p.q_pos0 = q_pos0; p.o = o; p.o_bs = o_bs; p.o_rs = o_rs; p.lse = lse;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  return split ? launch_tc<96>(maps, p, s) : launch_tc<64>(maps, p, s);
+}

@@ -8,6 +8,7 @@ from . import _lib
 F16, BF16, F32 = 0, 1, 2
 _DT = {torch.float16: F16, torch.bfloat16: BF16, torch.float32: F32}
 INT_MIN = -2 ** 31
+USE_TC_ATTENTION = True
 GEMM_PROFILE = None      # set to a list to record (M, N, K, cuda start event, cuda end event) per GEMM launch
 
 
@@ -59,12 +60,15 @@ def gemm(a, b, out=None, bias=None, gelu=False, resid=None, out_dtype=None, row_
 
 
 def attention_fwd(q, k, v, out, B, H, Lq, Lk, hd, scale, q_strides, k_strides, v_strides, o_strides, bias=None,
-                  bias_zero=0, kmask=None, causal=False, q_pos0=0, lse=None, kv_div=1):
-    """q/k/v/out: tensors whose data_ptr is row 0 / head 0; *_strides = (batch stride, row stride) in elements."""
+                  bias_zero=0, kmask=None, causal=False, q_pos0=0, lse=None, kv_div=1, impl="auto"):
+    """q/k/v/out: tensors whose data_ptr is row 0 / head 0; *_strides = (batch stride, row stride) in elements.
+    impl: "tc" = tcgen05 kernel, "mma" = mma.sync kernel, "auto" = tcgen05 for >= 128 query rows and hd 64 / 72..96."""
     _check(q, torch.float16, torch.bfloat16)
     if kmask is not None:
         _check(kmask, torch.int32)
-    _lib.call("mrb_attention_fwd", q.data_ptr(), q_strides[0], q_strides[1], k.data_ptr(), k_strides[0], k_strides[1],
+    tc_ok = (hd == 64 or (64 < hd <= 96 and hd % 8 == 0))
+    use_tc = impl == "tc" or (impl == "auto" and USE_TC_ATTENTION and tc_ok and Lq >= 128)
+    _lib.call("mrb_attention_fwd_tc" if use_tc else "mrb_attention_fwd", q.data_ptr(), q_strides[0], q_strides[1], k.data_ptr(), k_strides[0], k_strides[1],
               v.data_ptr(), v_strides[0], v_strides[1], out.data_ptr(), o_strides[0], o_strides[1], B, H, Lq, Lk, hd,
               _DT[q.dtype], float(scale), _ptr(bias), bias.shape[1] if bias is not None else 0, bias_zero, _ptr(kmask),
               kv_div, int(causal), q_pos0, _ptr(lse), _stream())

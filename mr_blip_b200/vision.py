@@ -67,8 +67,14 @@ class VitEngine:
             ops.norm(x, blk["ln1_w"], blk["ln1_b"], d.vit_ln_eps, 0, out_h=xn)
             ops.gemm(xn, blk["qkv_w"], out=qkv, bias=blk["qkv_b"])
             rs = 3 * W
-            ops.attention_fwd(qkv, qkv[:, W:], qkv[:, 2 * W:], ao, F_, Hh, T, T, hd, hd ** -0.5,
-                              (T * rs, rs), (T * rs, rs), (T * rs, rs), (T * W, W))
+            # 257 = 2 x 128 + 1: the first 256 query rows run as two full tcgen05 tiles, the last row in the small kernel
+            Tq = (T // 128) * 128 if ops.USE_TC_ATTENTION else 0
+            if Tq:
+                ops.attention_fwd(qkv, qkv[:, W:], qkv[:, 2 * W:], ao, F_, Hh, Tq, T, hd, hd ** -0.5,
+                                  (T * rs, rs), (T * rs, rs), (T * rs, rs), (T * W, W), impl="tc")
+            if Tq < T:
+                ops.attention_fwd(qkv[Tq:], qkv[:, W:], qkv[:, 2 * W:], ao[Tq:], F_, Hh, T - Tq, T, hd, hd ** -0.5,
+                                  (T * rs, rs), (T * rs, rs), (T * rs, rs), (T * W, W), impl="mma")
             ops.gemm(ao, blk["proj_w"], out=x, bias=blk["proj_b"], resid=x)
             ops.norm(x, blk["ln2_w"], blk["ln2_b"], d.vit_ln_eps, 0, out_h=xn)
             ops.gemm(xn, blk["fc1_w"], out=hid, bias=blk["fc1_b"], gelu=True)

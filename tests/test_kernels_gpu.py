@@ -106,14 +106,16 @@ def _attn_ref(q, k, v, scale, bias=None, kmask=None, causal=False, q_pos0=0):
     return torch.matmul(p, vf).permute(0, 2, 1, 3), torch.logsumexp(s, dim=-1)
 
 
+@pytest.mark.parametrize("impl", ["mma", "tc"])
 @pytest.mark.parametrize("B,H,L,hd,dtype", [(3, 16, 257, 88, torch.float16), (2, 12, 32, 64, torch.float16),
-                                            (2, 32, 200, 64, torch.bfloat16)])
-def test_attention_fwd_fused_qkv_layout(ops, B, H, L, hd, dtype):
+                                            (2, 32, 200, 64, torch.bfloat16), (2, 4, 640, 64, torch.bfloat16),
+                                            (1, 2, 129, 80, torch.float16)])
+def test_attention_fwd_fused_qkv_layout(ops, B, H, L, hd, dtype, impl):
     qkv = _rand((B, L, 3, H, hd), dtype, 1.0, 12)
     out = torch.zeros((B, L, H, hd), dtype=dtype, device="cuda")
     rs = 3 * H * hd
     ops.attention_fwd(qkv[:, :, 0], qkv[:, :, 1], qkv[:, :, 2], out, B, H, L, L, hd, hd ** -0.5,
-                      (L * rs, rs), (L * rs, rs), (L * rs, rs), (L * H * hd, H * hd))
+                      (L * rs, rs), (L * rs, rs), (L * rs, rs), (L * H * hd, H * hd), impl=impl)
     want, _ = _attn_ref(qkv[:, :, 0], qkv[:, :, 1], qkv[:, :, 2], hd ** -0.5)
     tol = 2e-2 if dtype == torch.bfloat16 else 4e-3       # P is rounded to 16 bit before P.V
     _close(out, want, tol, tol, "attention fwd")
@@ -130,8 +132,9 @@ def test_attention_cross_small_q(ops):
     _close(out, want, 4e-3, 4e-3, "cross attention")
 
 
-@pytest.mark.parametrize("Lq,Lk,causal", [(150, 150, False), (21, 21, True), (21, 333, False)])
-def test_attention_t5_bias_mask_fwd_bwd(ops, Lq, Lk, causal):
+@pytest.mark.parametrize("impl", ["mma", "tc"])
+@pytest.mark.parametrize("Lq,Lk,causal", [(150, 150, False), (21, 21, True), (21, 333, False), (300, 300, True)])
+def test_attention_t5_bias_mask_fwd_bwd(ops, Lq, Lk, causal, impl):
     B, H, hd = 2, 32, 64
     dt = torch.bfloat16
     q, k, v = (_rand((B, L, H, hd), dt, 0.5, s) for L, s in ((Lq, 15), (Lk, 16), (Lk, 17)))
@@ -146,7 +149,7 @@ def test_attention_t5_bias_mask_fwd_bwd(ops, Lq, Lk, causal):
     lse = torch.zeros((B, H, Lq), dtype=torch.float32, device="cuda")
     st = lambda L: (L * H * hd, H * hd)
     ops.attention_fwd(q, k, v, out, B, H, Lq, Lk, hd, 1.0, st(Lq), st(Lk), st(Lk), st(Lq), bias=table, bias_zero=Lq - 1,
-                      kmask=kmask, causal=causal, lse=lse)
+                      kmask=kmask, causal=causal, lse=lse, impl=impl)
     qr, kr, vr = (t.float().requires_grad_(True) for t in (q, k, v))
     want, want_lse = _attn_ref(qr, kr, vr, 1.0, bias_full, kmask, causal)
     _close(out, want, 2e-2, 2e-2, "t5 attention fwd")
