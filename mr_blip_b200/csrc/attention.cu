@@ -71,9 +71,10 @@ __device__ __forceinline__ void load_tile(uint32_t smem, const T* g, long long r
 
 // score post-processing shared by forward and backward: scale, relative bias, masks
 struct ScoreCtx {
-  float scale; const float* bias; int bias_zero; const int* kmask; int causal, q_pos0, Lk;
+  float scale; const float* bias; int bias_zero; const int* kmask; int causal, q_pos0, Lk, Lq;
   __device__ __forceinline__ float apply(float s, int i, int j) const {
     if (j >= Lk) return -INFINITY;
+    i = min(i, Lq - 1);                      // rows past Lq are never stored; keep their bias index in range
     s *= scale;
     if (bias) s += __ldg(bias + (j - (i + q_pos0)) + bias_zero);
     if (kmask && __ldg(kmask + j) == 0) return -INFINITY;
@@ -95,7 +96,7 @@ __global__ void __launch_bounds__(NTHREADS) attn_fwd_kernel(const AttnParams p) 
   const T* gk = static_cast<const T*>(p.k) + (b / p.kv_div) * p.k_bs + static_cast<long long>(h) * p.hd;
   const T* gv = static_cast<const T*>(p.v) + (b / p.kv_div) * p.v_bs + static_cast<long long>(h) * p.hd;
   ScoreCtx sc{p.scale, p.bias ? p.bias + static_cast<long long>(h) * p.bias_len : nullptr, p.bias_zero,
-              p.kmask ? p.kmask + static_cast<long long>(b / p.kv_div) * p.Lk : nullptr, p.causal, p.q_pos0, p.Lk};
+              p.kmask ? p.kmask + static_cast<long long>(b / p.kv_div) * p.Lk : nullptr, p.causal, p.q_pos0, p.Lk, p.Lq};
 
   int n_kv = (p.Lk + BKV - 1) / BKV;
   if (p.causal) n_kv = min(n_kv, (q0 + BQ - 1 + p.q_pos0) / BKV + 1);
@@ -255,7 +256,7 @@ __global__ void __launch_bounds__(NTHREADS) attn_bwd_dq_kernel(const AttnParams 
   const T* gv = static_cast<const T*>(p.v) + (b / p.kv_div) * p.v_bs + static_cast<long long>(h) * p.hd;
   const T* gdo = static_cast<const T*>(p.dout) + b * p.do_bs + static_cast<long long>(h) * p.hd;
   ScoreCtx sc{p.scale, p.bias ? p.bias + static_cast<long long>(h) * p.bias_len : nullptr, p.bias_zero,
-              p.kmask ? p.kmask + static_cast<long long>(b / p.kv_div) * p.Lk : nullptr, p.causal, p.q_pos0, p.Lk};
+              p.kmask ? p.kmask + static_cast<long long>(b / p.kv_div) * p.Lk : nullptr, p.causal, p.q_pos0, p.Lk, p.Lq};
   int n_kv = (p.Lk + BKV - 1) / BKV;
   if (p.causal) n_kv = min(n_kv, (q0 + BQ - 1 + p.q_pos0) / BKV + 1);
 
@@ -381,7 +382,7 @@ __global__ void __launch_bounds__(NTHREADS) attn_bwd_dkv_kernel(const AttnParams
   const T* gv = static_cast<const T*>(p.v) + (b / p.kv_div) * p.v_bs + static_cast<long long>(h) * p.hd;
   const T* gdo = static_cast<const T*>(p.dout) + b * p.do_bs + static_cast<long long>(h) * p.hd;
   ScoreCtx sc{p.scale, p.bias ? p.bias + static_cast<long long>(h) * p.bias_len : nullptr, p.bias_zero,
-              p.kmask ? p.kmask + static_cast<long long>(b / p.kv_div) * p.Lk : nullptr, p.causal, p.q_pos0, p.Lk};
+              p.kmask ? p.kmask + static_cast<long long>(b / p.kv_div) * p.Lk : nullptr, p.causal, p.q_pos0, p.Lk, p.Lq};
   const long long stat = (static_cast<long long>(b) * p.H + h) * p.Lq;
   const int n_q = (p.Lq + BQ - 1) / BQ;
   int q_begin = 0;

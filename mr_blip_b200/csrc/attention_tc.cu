@@ -24,7 +24,8 @@ struct AttnTcParams {
   float* lse;                                    // [B, H, Lq] or null
 };
 
-constexpr int TQ = 128, TKV = 128;
+constexpr int TQ = 128, TKV = 128;     // per softmax group: 128 query rows; a CTA runs two groups (256 rows)
+constexpr float TAU = 8.0f;            // stale-max slack (log2 domain): P entries stay below 2^8
 
 __device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2, int c3) {
   asm volatile(
@@ -32,8 +33,13 @@ __device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* m
       ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
       : "memory");
 }
+__device__ __forceinline__ float ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 
-// generic UMMA smem descriptor: swizzle_bytes 128 / 64, sbo / lbo in bytes
+// generic UMMA smem descriptor: lbo / sbo in bytes
 __device__ __forceinline__ uint64_t umma_desc(uint32_t addr, uint32_t lbo, uint32_t sbo, uint32_t layout) {
   uint64_t d = 0;
   d |= static_cast<uint64_t>((addr & 0x3FFFF) >> 4);
@@ -45,30 +51,31 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t addr, uint32_t lbo, uint3
 }
 constexpr uint32_t LAYOUT_SW128 = 2, LAYOUT_SW64 = 4;
 
-__host__ __device__ constexpr uint32_t idesc_f16(int fmt, int M, int N, int b_mn_major) {
+__host__ __device__ constexpr uint32_t idesc_f16(int fmt, int M, int N, int a_mn_major, int b_mn_major) {
   return (1u << 4) | (static_cast<uint32_t>(fmt) << 7) | (static_cast<uint32_t>(fmt) << 10) |
-         (static_cast<uint32_t>(b_mn_major) << 16) | (static_cast<uint32_t>(N >> 3) << 17) |
-         (static_cast<uint32_t>(M >> 4) << 24);
+         (static_cast<uint32_t>(a_mn_major) << 15) | (static_cast<uint32_t>(b_mn_major) << 16) |
+         (static_cast<uint32_t>(N >> 3) << 17) | (static_cast<uint32_t>(M >> 4) << 24);
 }
 
 template <int HD>   // 64, or 96 (= 64-wide SW128 atom + 32-wide SW64 atom)
 struct TcSmem {
   static constexpr bool SPLIT = (HD == 96);
-  static constexpr int Q_BYTES = TQ * 64 * 2 + (SPLIT ? TQ * 32 * 2 : 0);
+  static constexpr int Q_ONE = TQ * 64 * 2 + (SPLIT ? TQ * 32 * 2 : 0);       // one group's Q tile
   static constexpr int KV_ONE = TKV * 64 * 2 + (SPLIT ? TKV * 32 * 2 : 0);   // one of K or V
   static constexpr int STAGE_BYTES = 2 * KV_ONE;
   static constexpr int STAGES = 2;
-  static constexpr int P_BYTES = TQ * TKV * 2;                                 // two 64-key atoms
+  static constexpr int P_BYTES = TQ * TKV * 2;                                 // two 64-key atoms, per group
   static constexpr int OFF_Q = 0;
-  static constexpr int OFF_KV = Q_BYTES;
+  static constexpr int OFF_KV = 2 * Q_ONE;
   static constexpr int OFF_P = OFF_KV + STAGES * STAGE_BYTES;
-  static constexpr int OFF_BAR = OFF_P + 2 * P_BYTES;
-  static constexpr int NBAR = 1 + 2 * STAGES + 12;
+  static constexpr int OFF_BIAS = OFF_P + 2 * P_BYTES;                         // 8 warps x 160 floats
+  static constexpr int OFF_BAR = OFF_BIAS + 8 * 160 * 4;
+  static constexpr int NBAR = 1 + 2 * STAGES + 6;
   static constexpr int TOTAL = OFF_BAR + NBAR * 8 + 16 + 1024;
 };
 
 template <int HD>
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(320, 1)
 attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                    const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmQ2,
                    const __grid_constant__ CUtensorMap tmK2, const __grid_constant__ CUtensorMap tmV2,
@@ -77,36 +84,30 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   constexpr bool SPLIT = S::SPLIT;
   constexpr int STAGES = S::STAGES;
   constexpr uint32_t TMEM_COLS = 512;
-  constexpr int S_COL = 0, O_COL = 256;          // S0 [0,128) S1 [128,256) ; O0 [256,256+HD) O1 [256+HD, 256+2HD)
+  constexpr int S_COL = 0, O_COL = 256;          // S_A [0,128) S_B [128,256) ; O_A [256,256+HD) O_B [256+HD, 256+2HD)
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S::OFF_BAR);
   uint64_t* q_full = bars;
   uint64_t* kv_full = bars + 1;
   uint64_t* kv_empty = kv_full + STAGES;
-  uint64_t* s_full = kv_empty + STAGES;
-  uint64_t* s_empty = s_full + 2;
-  uint64_t* p_full = s_empty + 2;
-  uint64_t* p_empty = p_full + 2;
-  uint64_t* o_full = p_empty + 2;
-  uint64_t* o_empty = o_full + 2;
+  uint64_t* s_full = kv_empty + STAGES;    // [2] per group
+  uint64_t* p_full = s_full + 2;
+  uint64_t* o_full = p_full + 2;
   uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + S::NBAR);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int b = blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * TQ;
+  const int b = blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * (2 * TQ);
   const int bkv = b / p.kv_div;
+  const int n_groups = (q0 + TQ < p.Lq) ? 2 : 1;           // the second 128-row group may be empty
   int n_kv = (p.Lk + TKV - 1) / TKV;
-  if (p.causal) n_kv = min(n_kv, (q0 + TQ - 1 + p.q_pos0) / TKV + 1);
+  if (p.causal) n_kv = min(n_kv, (min(q0 + n_groups * TQ, p.Lq) - 1 + p.q_pos0) / TKV + 1);
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV);
     mbar_init(q_full, 1);
     for (int s = 0; s < STAGES; ++s) { mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 1); }
-    for (int s = 0; s < 2; ++s) {
-      mbar_init(&s_full[s], 1); mbar_init(&s_empty[s], 4);
-      mbar_init(&p_full[s], 4); mbar_init(&p_empty[s], 1);
-      mbar_init(&o_full[s], 1); mbar_init(&o_empty[s], 4);
-    }
+    for (int g = 0; g < 2; ++g) { mbar_init(&s_full[g], 1); mbar_init(&p_full[g], 4); mbar_init(&o_full[g], 1); }
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_holder, TMEM_COLS);
@@ -118,9 +119,11 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
-      mbar_expect_tx(q_full, S::Q_BYTES);
-      tma_load_4d(smem + S::OFF_Q, &tmQ, q_full, 0, h, q0, b);
-      if (SPLIT) tma_load_4d(smem + S::OFF_Q + TQ * 128, &tmQ2, q_full, 64, h, q0, b);
+      mbar_expect_tx(q_full, n_groups * S::Q_ONE);
+      for (int g = 0; g < n_groups; ++g) {
+        tma_load_4d(smem + S::OFF_Q + g * S::Q_ONE, &tmQ, q_full, 0, h, q0 + g * TQ, b);
+        if (SPLIT) tma_load_4d(smem + S::OFF_Q + g * S::Q_ONE + TQ * 128, &tmQ2, q_full, 64, h, q0 + g * TQ, b);
+      }
       for (int j = 0; j < n_kv; ++j) {
         const int st = j % STAGES;
         mbar_wait(&kv_empty[st], ((j / STAGES) & 1) ^ 1);
@@ -138,190 +141,232 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     const int fmt = p.dtype == MRB_DT_BF16 ? 1 : 0;
-    const uint32_t q_addr = smem_u32(smem + S::OFF_Q);
     auto tail_n = [&](int j) {   // keys in KV tile j, rounded up to the UMMA N granularity (16)
       const int rem = p.Lk - j * TKV;
       return rem >= TKV ? TKV : ((rem + 15) & ~15);
     };
-    auto issue_pv = [&](int i) {
-      const int st = i % STAGES, pb = i & 1;
-      mbar_wait(&p_full[pb], (i >> 1) & 1);
-      mbar_wait(&o_empty[pb], ((i >> 1) & 1) ^ 1);
-      tc_fence_after();
-      if (lane == 0) {
-        const uint32_t p_addr = smem_u32(smem + S::OFF_P + pb * S::P_BYTES);
-        const uint32_t v_addr = smem_u32(smem + S::OFF_KV + st * S::STAGE_BYTES + S::KV_ONE);
-        const uint32_t d_o = tmem_base + O_COL + pb * HD;
-        const int ksteps = tail_n(i) / 16;
-        const uint32_t id64 = idesc_f16(fmt, TQ, 64, 1);
-        const uint32_t id32 = idesc_f16(fmt, TQ, 32, 1);
-        for (int k = 0; k < ksteps; ++k) {
-          // A = P (K-major, SW128): 64-key atom (k/4), 32-byte step inside the atom
-          const uint64_t a = umma_desc(p_addr + (k >> 2) * (TQ * 128) + (k & 3) * 32, 16, 1024, LAYOUT_SW128);
-          // B = V [key][d] read MN-major: 16 keys = two 8-key groups of 1024 B (SW128) / 512 B (SW64)
-          const uint64_t bv = umma_desc(v_addr + k * 2048, TKV * 128, 1024, LAYOUT_SW128);
-          umma_f16(d_o, a, bv, id64, k > 0 ? 1u : 0u);
-          if (SPLIT) {
-            const uint64_t bv2 = umma_desc(v_addr + TKV * 128 + k * 1024, TKV * 64, 512, LAYOUT_SW64);
-            umma_f16(d_o + 64, a, bv2, id32, k > 0 ? 1u : 0u);
-          }
-        }
-        umma_commit(&o_full[pb]);
-        umma_commit(&kv_empty[st]);
-        umma_commit(&p_empty[pb]);
+    auto issue_qk = [&](int g, int j) {
+      const int st = j % STAGES;
+      const uint32_t q_addr = smem_u32(smem + S::OFF_Q + g * S::Q_ONE);
+      const uint32_t k_addr = smem_u32(smem + S::OFF_KV + st * S::STAGE_BYTES);
+      const uint32_t d_s = tmem_base + S_COL + g * TKV;
+      const uint32_t ids = idesc_f16(fmt, TQ, tail_n(j), 0, 0);
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        umma_f16(d_s, umma_desc(q_addr + k * 32, 16, 1024, LAYOUT_SW128), umma_desc(k_addr + k * 32, 16, 1024, LAYOUT_SW128),
+                 ids, k > 0 ? 1u : 0u);
+      if (SPLIT) {
+#pragma unroll
+        for (int k = 0; k < 2; ++k)
+          umma_f16(d_s, umma_desc(q_addr + TQ * 128 + k * 32, 16, 512, LAYOUT_SW64),
+                   umma_desc(k_addr + TKV * 128 + k * 32, 16, 512, LAYOUT_SW64), ids, 1u);
       }
-      __syncwarp();
+      umma_commit(&s_full[g]);
+    };
+    auto issue_pv = [&](int g, int j) {
+      const int st = j % STAGES;
+      const uint32_t p_addr = smem_u32(smem + S::OFF_P + g * S::P_BYTES);
+      const uint32_t v_addr = smem_u32(smem + S::OFF_KV + st * S::STAGE_BYTES + S::KV_ONE);
+      const uint32_t d_o = tmem_base + O_COL + g * HD;
+      const int ksteps = tail_n(j) / 16;
+      const uint32_t id64 = idesc_f16(fmt, TQ, 64, 0, 1);
+      const uint32_t id32 = idesc_f16(fmt, TQ, 32, 0, 1);
+      for (int k = 0; k < ksteps; ++k) {
+        // A = P (K-major, SW128): 64-key atom (k/4), 32-byte step inside the atom
+        const uint64_t a = umma_desc(p_addr + (k >> 2) * (TQ * 128) + (k & 3) * 32, 16, 1024, LAYOUT_SW128);
+        // B = V [key][d] read MN-major: 16 keys = two 8-key groups of 1024 B (SW128) / 512 B (SW64)
+        umma_f16(d_o, a, umma_desc(v_addr + k * 2048, TKV * 128, 1024, LAYOUT_SW128), id64, k > 0 ? 1u : 0u);
+        if (SPLIT)
+          umma_f16(d_o + 64, a, umma_desc(v_addr + TKV * 128 + k * 1024, TKV * 64, 512, LAYOUT_SW64), id32, k > 0 ? 1u : 0u);
+      }
+      umma_commit(&o_full[g]);
     };
     mbar_wait(q_full, 0);
+    mbar_wait(&kv_full[0], 0);
+    tc_fence_after();
+    if (lane == 0)
+      for (int g = 0; g < n_groups; ++g) issue_qk(g, 0);
+    __syncwarp();
     for (int j = 0; j < n_kv; ++j) {
-      const int st = j % STAGES, sb = j & 1;
-      mbar_wait(&kv_full[st], (j / STAGES) & 1);
-      mbar_wait(&s_empty[sb], ((j >> 1) & 1) ^ 1);
-      tc_fence_after();
-      if (lane == 0) {
-        const uint32_t k_addr = smem_u32(smem + S::OFF_KV + st * S::STAGE_BYTES);
-        const uint32_t d_s = tmem_base + S_COL + sb * TKV;
-        const uint32_t ids = idesc_f16(fmt, TQ, tail_n(j), 0);
-#pragma unroll
-        for (int k = 0; k < 4; ++k)
-          umma_f16(d_s, umma_desc(q_addr + k * 32, 16, 1024, LAYOUT_SW128), umma_desc(k_addr + k * 32, 16, 1024, LAYOUT_SW128),
-                   ids, k > 0 ? 1u : 0u);
-        if (SPLIT) {
-#pragma unroll
-          for (int k = 0; k < 2; ++k)
-            umma_f16(d_s, umma_desc(q_addr + TQ * 128 + k * 32, 16, 512, LAYOUT_SW64),
-                     umma_desc(k_addr + TKV * 128 + k * 32, 16, 512, LAYOUT_SW64), ids, 1u);
+      for (int g = 0; g < n_groups; ++g) {
+        mbar_wait(&p_full[g], j & 1);
+        if (g == 0 && j + 1 < n_kv) mbar_wait(&kv_full[(j + 1) % STAGES], ((j + 1) / STAGES) & 1);
+        tc_fence_after();
+        if (lane == 0) {
+          issue_pv(g, j);
+          if (g == n_groups - 1) umma_commit(&kv_empty[j % STAGES]);   // K_j / V_j fully consumed
+          if (j + 1 < n_kv) issue_qk(g, j + 1);
         }
-        umma_commit(&s_full[sb]);
+        __syncwarp();
       }
-      __syncwarp();
-      if (j > 0) issue_pv(j - 1);
     }
-    issue_pv(n_kv - 1);
   } else {
-    // ===================== softmax / epilogue warps: one thread per query row =====================
-    const int quad = warp & 3;
-    const int r = quad * 32 + lane;
-    const int i_abs = min(q0 + r, p.Lq - 1) + p.q_pos0;     // rows past Lq are computed but never stored
-    const uint32_t lane_base = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
-    const float LOG2E = 1.4426950408889634f;
-    const float sl2 = p.scale * LOG2E;
-    const float* brow = p.bias ? p.bias + static_cast<long long>(h) * p.bias_len + p.bias_zero - i_abs : nullptr;
-    const int* mrow = p.kmask ? p.kmask + static_cast<long long>(bkv) * p.Lk : nullptr;
-    float o_reg[HD];
+    // ===================== softmax groups: one thread per query row =====================
+    const int g = (warp - 2) >> 2;                         // group 0: warps 2-5, group 1: warps 6-9
+    if (g < n_groups) {
+      const int quad = warp & 3;
+      const int r = quad * 32 + lane;
+      const int qg0 = q0 + g * TQ;
+      const int i_abs = min(qg0 + r, p.Lq - 1) + p.q_pos0;     // rows past Lq are computed but never stored
+      const uint32_t lane_base = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
+      const uint32_t s_addr = lane_base + S_COL + g * TKV;
+      const uint32_t o_addr = lane_base + O_COL + g * HD;
+      const float LOG2E = 1.4426950408889634f;
+      const float sl2 = p.scale * LOG2E;
+      const float* bhead = p.bias ? p.bias + static_cast<long long>(h) * p.bias_len : nullptr;
+      const int* mrow = p.kmask ? p.kmask + static_cast<long long>(bkv) * p.Lk : nullptr;
+      float* wbias = reinterpret_cast<float*>(smem + S::OFF_BIAS) + (warp - 2) * 160;   // this warp's bias window
+      uint8_t* prow = smem + S::OFF_P + g * S::P_BYTES + r * 128;
+      float o_reg[HD];
 #pragma unroll
-    for (int c = 0; c < HD; ++c) o_reg[c] = 0.f;
-    float m_run = -INFINITY, l_run = 0.f, corr_prev = 1.f;
+      for (int c = 0; c < HD; ++c) o_reg[c] = 0.f;
+      float m_ref = -INFINITY, l_run = 0.f;
+      // window index for (row r, column c): (kv0 + c) - i_abs + zero = w0 + (31 - lane) + c, w0 = bias index of
+      // (column 0, last row of this warp)
+      const int i_warp_last = min(qg0 + quad * 32 + 31, p.Lq - 1) + p.q_pos0;
 
-    auto accumulate_o = [&](int i, float corr) {
-      const int pb = i & 1;
-      mbar_wait(&o_full[pb], (i >> 1) & 1);
-      tc_fence_after();
+      auto fold_o = [&](int j) {
+        mbar_wait(&o_full[g], j & 1);
+        tc_fence_after();
 #pragma unroll
-      for (int c = 0; c < HD; c += 32) {
-        uint32_t v[32];
-        tmem_ld_32x32b_x32(lane_base + O_COL + pb * HD + c, v);
-        tmem_ld_wait();
+        for (int c = 0; c < HD; c += 32) {
+          uint32_t v[32];
+          tmem_ld_32x32b_x32(o_addr + c, v);
+          tmem_ld_wait();
 #pragma unroll
-        for (int e = 0; e < 32; ++e) o_reg[c + e] = o_reg[c + e] * corr + __uint_as_float(v[e]);
-      }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&o_empty[pb]);
-    };
-
-    for (int j = 0; j < n_kv; ++j) {
-      const int sb = j & 1;
-      const int kv0 = j * TKV;
-      const int ncols = min(TKV, p.Lk - kv0);            // valid keys in this tile
-      const int nc32 = (ncols + 31) & ~31;
-      mbar_wait(&s_full[sb], (j >> 1) & 1);
-      tc_fence_after();
-      // tile-level mask summary (warp-uniform): 128-bit mask of attendable keys
-      uint32_t mbits[4] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu};
-      bool need_elem_mask = (ncols < TKV) || (p.causal && kv0 + TKV - 1 > q0 + quad * 32 + p.q_pos0);
-      if (mrow) {
-#pragma unroll
-        for (int w = 0; w < 4; ++w) {
-          const int jj = kv0 + w * 32 + lane;
-          const int ok = (jj < p.Lk) ? __ldg(mrow + jj) : 0;
-          mbits[w] = __ballot_sync(0xffffffffu, ok != 0);
+          for (int e = 0; e < 32; ++e) o_reg[c + e] += __uint_as_float(v[e]);
         }
-        need_elem_mask = need_elem_mask || ((mbits[0] & mbits[1] & mbits[2] & mbits[3]) != 0xffffffffu);
-      }
-      auto score = [&](float raw, int c) {              // c = column within tile
-        float s = raw * sl2;
-        if (brow && c < ncols) s += __ldg(brow + kv0 + c) * LOG2E;
-        if (need_elem_mask) {
-          const bool ok = (c < ncols) && ((mbits[c >> 5] >> (c & 31)) & 1u) && !(p.causal && kv0 + c > i_abs);
-          if (!ok) s = -INFINITY;
-        }
-        return s;                                        // log2 domain
       };
-      // pass 1: row max
-      float m_new = m_run;
-      for (int c = 0; c < nc32; c += 32) {
-        uint32_t v[32];
-        tmem_ld_32x32b_x32(lane_base + S_COL + sb * TKV + c, v);
-        tmem_ld_wait();
-#pragma unroll
-        for (int e = 0; e < 32; ++e) m_new = fmaxf(m_new, score(__uint_as_float(v[e]), c + e));
-      }
-      const float m_use = (m_new == -INFINITY) ? 0.f : m_new;
-      const float corr = (m_run == -INFINITY) ? 0.f : exp2f(m_run - m_use);
-      m_run = m_new;
-      // pass 2: P = exp2(s - m) -> 16-bit -> swizzled smem
-      const int pb = j & 1;
-      mbar_wait(&p_empty[pb], ((j >> 1) & 1) ^ 1);
-      uint8_t* prow = smem + S::OFF_P + pb * S::P_BYTES + r * 128;
-      float rsum = 0.f;
-      const int npad = (ncols + 15) & ~15;               // the PV MMA reads keys [0, npad)
-      for (int c = 0; c < nc32; c += 32) {
-        uint32_t v[32];
-        tmem_ld_32x32b_x32(lane_base + S_COL + sb * TKV + c, v);
-        tmem_ld_wait();
-        uint32_t pk[16];
-#pragma unroll
-        for (int e = 0; e < 32; e += 2) {
-          const float p0 = exp2f(score(__uint_as_float(v[e]), c + e) - m_use);
-          const float p1 = exp2f(score(__uint_as_float(v[e + 1]), c + e + 1) - m_use);
-          rsum += p0 + p1;
-          pk[e >> 1] = pack2(p0, p1, p.dtype);
+
+      for (int j = 0; j < n_kv; ++j) {
+        const int kv0 = j * TKV;
+        const int ncols = min(TKV, p.Lk - kv0);
+        const int nc32 = (ncols + 31) & ~31;
+        const int npad = (ncols + 15) & ~15;               // the PV MMA reads keys [0, npad)
+        // stage this warp's bias window (pre-multiplied by log2 e) while the QK MMA runs
+        if (bhead) {
+          __syncwarp();
+          const int w0 = kv0 - i_warp_last + p.bias_zero;
+          for (int k = lane; k < 160; k += 32) {
+            const int idx = w0 + k;
+            wbias[k] = (idx >= 0 && idx < p.bias_len) ? __ldg(bhead + idx) * LOG2E : 0.f;
+          }
+          __syncwarp();
         }
+        uint32_t mb0 = 0xffffffffu, mb1 = 0xffffffffu, mb2 = 0xffffffffu, mb3 = 0xffffffffu;
+        bool masked = (ncols < TKV) || (p.causal && kv0 + TKV - 1 > qg0 + quad * 32 + p.q_pos0);
+        if (mrow) {
+          const int jj = kv0 + lane;
+          mb0 = __ballot_sync(0xffffffffu, (jj < p.Lk) && __ldg(mrow + min(jj, p.Lk - 1)) != 0);
+          mb1 = __ballot_sync(0xffffffffu, (jj + 32 < p.Lk) && __ldg(mrow + min(jj + 32, p.Lk - 1)) != 0);
+          mb2 = __ballot_sync(0xffffffffu, (jj + 64 < p.Lk) && __ldg(mrow + min(jj + 64, p.Lk - 1)) != 0);
+          mb3 = __ballot_sync(0xffffffffu, (jj + 96 < p.Lk) && __ldg(mrow + min(jj + 96, p.Lk - 1)) != 0);
+          masked = masked || ((mb0 & mb1 & mb2 & mb3) != 0xffffffffu);
+        }
+        // the bias window of THIS thread's row starts at wbias[31 - lane + (i_warp_last - i_abs) ...]: rows are consecutive
+        const float* wrow = wbias + (i_warp_last - i_abs);
+
+        mbar_wait(&s_full[g], j & 1);
+        tc_fence_after();
+        if (j > 0) fold_o(j - 1);
+
+        // score of column c (log2 domain), chunk-level helpers
+        auto load_scores = [&](int c, float* sv) {
+          uint32_t v[32];
+          tmem_ld_32x32b_x32(s_addr + c, v);
+          tmem_ld_wait();
+          const uint32_t mw = (c == 0) ? mb0 : (c == 32) ? mb1 : (c == 64) ? mb2 : mb3;
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {                    // 4 x 16-byte chunks of 8 keys
-          const int key0 = c + q * 8;
-          if (key0 < npad) {
-            const int atom = key0 >> 6, chunk = (key0 & 63) >> 3;
-            *reinterpret_cast<uint4*>(prow + atom * (TQ * 128) + ((chunk ^ (r & 7)) << 4)) =
-                make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
+          for (int e = 0; e < 32; ++e) {
+            float s = __uint_as_float(v[e]) * sl2;
+            if (bhead) s += wrow[c + e];
+            if (masked) {
+              const bool ok = (c + e < ncols) && ((mw >> e) & 1u) && !(p.causal && kv0 + c + e > i_abs);
+              if (!ok) s = -INFINITY;
+            }
+            sv[e] = s;
+          }
+        };
+        auto tile_max = [&]() {
+          float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
+          for (int c = 0; c < nc32; c += 32) {
+            float sv[32];
+            load_scores(c, sv);
+#pragma unroll
+            for (int e = 0; e < 32; e += 4) {
+              mx0 = fmaxf(mx0, sv[e]); mx1 = fmaxf(mx1, sv[e + 1]); mx2 = fmaxf(mx2, sv[e + 2]); mx3 = fmaxf(mx3, sv[e + 3]);
+            }
+          }
+          return fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
+        };
+        // exp + pack + store with reference max mref; returns row sum, tracks the true tile max
+        auto exp_store = [&](float mref, float& tmax) {
+          float rs0 = 0.f, rs1 = 0.f, mx0 = -INFINITY, mx1 = -INFINITY;
+          for (int c = 0; c < nc32; c += 32) {
+            float sv[32];
+            load_scores(c, sv);
+            uint32_t pk[16];
+#pragma unroll
+            for (int e = 0; e < 32; e += 2) {
+              mx0 = fmaxf(mx0, sv[e]); mx1 = fmaxf(mx1, sv[e + 1]);
+              const float p0 = ex2(sv[e] - mref), p1 = ex2(sv[e + 1] - mref);
+              rs0 += p0; rs1 += p1;
+              pk[e >> 1] = pack2(p0, p1, p.dtype);
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {                  // 4 x 16-byte chunks of 8 keys
+              const int key0 = c + q * 8;
+              if (key0 < npad) {
+                const int atom = key0 >> 6, chunk = (key0 & 63) >> 3;
+                *reinterpret_cast<uint4*>(prow + atom * (TQ * 128) + ((chunk ^ (r & 7)) << 4)) =
+                    make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
+              }
+            }
+          }
+          tmax = fmaxf(mx0, mx1);
+          return rs0 + rs1;
+        };
+
+        // NOTE: tcgen05.ld is warp-collective (.sync.aligned): every branch around it must be warp-uniform.
+        float tmax, rsum;
+        if (j == 0) {                                      // no reference yet: exact two-pass tile
+          const float mx = tile_max();
+          if (mx != -INFINITY) m_ref = mx;
+          rsum = exp_store(mx == -INFINITY ? 0.f : mx, tmax);
+        } else {
+          rsum = exp_store(m_ref == -INFINITY ? 0.f : m_ref, tmax);   // single pass against the stale max
+          if (__any_sync(0xffffffffu, tmax > m_ref + TAU)) {          // rare: some row's max jumped; redo the tile exactly
+            const float m_new = fmaxf(m_ref, tmax);
+            const float corr = (m_ref == -INFINITY) ? 0.f : ex2(m_ref - m_new);
+            l_run *= corr;
+#pragma unroll
+            for (int c = 0; c < HD; ++c) o_reg[c] *= corr;
+            m_ref = m_new;
+            rsum = exp_store(m_ref == -INFINITY ? 0.f : m_ref, tmax);
           }
         }
+        l_run += rsum;
+        fence_proxy_async();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&p_full[g]);
       }
-      l_run = l_run * corr + rsum;
-      fence_proxy_async();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) { mbar_arrive(&p_full[pb]); mbar_arrive(&s_empty[sb]); }
-      // fold the previous tile's PV result while this tile's PV runs
-      if (j > 0) accumulate_o(j - 1, corr_prev);
-      corr_prev = corr;
-    }
-    accumulate_o(n_kv - 1, corr_prev);
-    // epilogue
-    const int i = q0 + r;
-    if (i < p.Lq) {
-      const float inv = l_run > 0.f ? 1.f / l_run : 0.f;
-      uint16_t* orow = static_cast<uint16_t*>(p.o) + b * p.o_bs + static_cast<long long>(i) * p.o_rs + static_cast<long long>(h) * p.hd;
+      fold_o(n_kv - 1);
+      // epilogue
+      const int i = qg0 + r;
+      if (i < p.Lq) {
+        const float inv = l_run > 0.f ? 1.f / l_run : 0.f;
+        uint16_t* orow = static_cast<uint16_t*>(p.o) + b * p.o_bs + static_cast<long long>(i) * p.o_rs + static_cast<long long>(h) * p.hd;
 #pragma unroll
-      for (int c = 0; c < HD; c += 8) {
-        if (c < p.hd) {
-          *reinterpret_cast<uint4*>(orow + c) =
-              make_uint4(pack2(o_reg[c] * inv, o_reg[c + 1] * inv, p.dtype), pack2(o_reg[c + 2] * inv, o_reg[c + 3] * inv, p.dtype),
-                         pack2(o_reg[c + 4] * inv, o_reg[c + 5] * inv, p.dtype), pack2(o_reg[c + 6] * inv, o_reg[c + 7] * inv, p.dtype));
+        for (int c = 0; c < HD; c += 8) {
+          if (c < p.hd) {
+            *reinterpret_cast<uint4*>(orow + c) =
+                make_uint4(pack2(o_reg[c] * inv, o_reg[c + 1] * inv, p.dtype), pack2(o_reg[c + 2] * inv, o_reg[c + 3] * inv, p.dtype),
+                           pack2(o_reg[c + 4] * inv, o_reg[c + 5] * inv, p.dtype), pack2(o_reg[c + 6] * inv, o_reg[c + 7] * inv, p.dtype));
+          }
         }
+        if (p.lse) p.lse[(static_cast<long long>(b) * p.H + h) * p.Lq + i] = (m_ref + log2f(l_run)) * 0.6931471805599453f;
       }
-      if (p.lse) p.lse[(static_cast<long long>(b) * p.H + h) * p.Lq + i] = (m_run + log2f(l_run)) * 0.6931471805599453f;
     }
   }
   tc_fence_before();
@@ -374,8 +419,8 @@ static int launch_tc(const CUtensorMap* maps, const AttnTcParams& p, cudaStream_
     if (e != cudaSuccess) return mrb_set_error(e);
     cfg = true;
   }
-  dim3 grid((p.Lq + TQ - 1) / TQ, p.H, p.B);
-  attn_fwd_tc_kernel<HD><<<grid, 192, S::TOTAL, s>>>(maps[0], maps[1], maps[2], maps[3], maps[4], maps[5], p);
+  dim3 grid((p.Lq + 2 * TQ - 1) / (2 * TQ), p.H, p.B);
+  attn_fwd_tc_kernel<HD><<<grid, 320, S::TOTAL, s>>>(maps[0], maps[1], maps[2], maps[3], maps[4], maps[5], p);
   MRB_CHECK_LAUNCH();
   return MRB_OK;
 }

@@ -88,7 +88,7 @@ def test_t5_loss_logits_grads_vs_reference_golden(model, golden_dir):
 @pytest.mark.parametrize("batch,frames,agg,seed", [(2, 3, None, 3), (3, 2, None, 5), (2, 4, "mean", 9), (1, 1, None, 1)])
 def test_forward_backward_vs_oracle(model, tiny_sd, golden_dir, batch, frames, agg, seed):
     from oracle import blip2_mr as ob, synth
-    samples = synth.make_samples(batch=batch, frames=frames, seed=seed, query_words=4 + 3 * seed % 7)
+    samples = synth.make_samples(batch=batch, frames=frames, seed=seed, query_words=8 if seed == 3 else 4 + seed)
     if batch > 1 and seed != 3:
         samples["duration"][1] = 37.0                      # second clip shorter -> different prompt ids
         samples["timestamps"][1] = samples["timestamps"][1] * (37.0 / 143.0)

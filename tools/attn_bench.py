@@ -1,0 +1,48 @@
+"""Time the attention kernels (tcgen05 vs mma.sync) on the path's two big shapes. python tools/attn_bench.py"""
+import sys
+
+import torch
+
+sys.path.insert(0, ".")
+from mr_blip_b200 import ops  # noqa: E402
+
+
+def timeit(fn, iters=5):
+    fn()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(iters):
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        fn()
+        e.record()
+        torch.cuda.synchronize()
+        ts.append(s.elapsed_time(e))
+    return sorted(ts)[len(ts) // 2]
+
+
+def main():
+    only = sys.argv[1] if len(sys.argv) > 1 else None
+    impls = (sys.argv[2],) if len(sys.argv) > 2 else ("mma", "tc")
+    for name, B, H, L, hd, dt, with_bias in [("vit", 240, 16, 257, 88, torch.float16, False),
+                                             ("t5enc", 4, 32, 2037, 64, torch.bfloat16, True),
+                                             ("t5enc_nobias", 4, 32, 2037, 64, torch.bfloat16, False),
+                                             ("t5enc_4017", 2, 32, 4017, 64, torch.bfloat16, True)]:
+        if only and name != only:
+            continue
+        qkv = (torch.randn(B, L, 3, H, hd, device="cuda") * 0.5).to(dt)
+        out = torch.empty(B, L, H, hd, device="cuda", dtype=dt)
+        rs = 3 * H * hd
+        bias = torch.randn(H, 2 * L - 1, device="cuda") if with_bias else None
+        kmask = torch.ones(B, L, dtype=torch.int32, device="cuda") if with_bias else None
+        flops = 4.0 * B * H * L * L * hd
+        for impl in impls:
+            Lq = L if impl == "mma" else (L // 128) * 128 if name == "vit" else L
+            ms = timeit(lambda: ops.attention_fwd(qkv[:, :, 0], qkv[:, :, 1], qkv[:, :, 2], out, B, H, Lq, L, hd, hd ** -0.5,
+                                                  (L * rs, rs), (L * rs, rs), (L * rs, rs), (L * H * hd, H * hd), bias=bias,
+                                                  bias_zero=L - 1, kmask=kmask, impl=impl))
+            print("%-14s %-4s %8.3f ms  %7.1f TFLOP/s" % (name, impl, ms, flops / ms / 1e9), flush=True)
+
+
+if __name__ == "__main__":
+    main()
