@@ -74,6 +74,109 @@ struct TcSmem {
   static constexpr int TOTAL = OFF_BAR + NBAR * 8 + 16 + 1024;
 };
 
+// ---- softmax building blocks (one thread = one query row; all tcgen05.ld calls are warp-uniform) ----
+struct RowCtx {
+  uint32_t s_addr;          // TMEM address of this row's S tile (lane + column base)
+  float sl2;                // scale * log2(e)
+  const float* wrow;        // this row's bias window in shared memory (already * log2 e), column c -> wrow[c]
+  uint32_t mb[4];           // attendable-key bits of the tile
+  int ncols, kv0, i_abs, causal;
+};
+
+template <bool HAS_BIAS, bool MASKED>
+__device__ __forceinline__ void load_scores(const RowCtx& x, int c, float* sv) {
+  uint32_t v[32];
+  tmem_ld_32x32b_x32(x.s_addr + c, v);
+  tmem_ld_wait();
+  const uint32_t mw = (c == 0) ? x.mb[0] : (c == 32) ? x.mb[1] : (c == 64) ? x.mb[2] : x.mb[3];
+#pragma unroll
+  for (int e = 0; e < 32; ++e) {
+    float s = HAS_BIAS ? fmaf(__uint_as_float(v[e]), x.sl2, x.wrow[c + e]) : __uint_as_float(v[e]) * x.sl2;
+    if (MASKED) {
+      const bool ok = (c + e < x.ncols) && ((mw >> e) & 1u) && !(x.causal && x.kv0 + c + e > x.i_abs);
+      s = ok ? s : -INFINITY;
+    }
+    sv[e] = s;
+  }
+}
+
+template <bool HAS_BIAS, bool MASKED>
+__device__ __forceinline__ float tile_max(const RowCtx& x, int nc32) {
+  float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
+  for (int c = 0; c < nc32; c += 32) {
+    float sv[32];
+    load_scores<HAS_BIAS, MASKED>(x, c, sv);
+#pragma unroll
+    for (int e = 0; e < 32; e += 4) {
+      mx0 = fmaxf(mx0, sv[e]); mx1 = fmaxf(mx1, sv[e + 1]); mx2 = fmaxf(mx2, sv[e + 2]); mx3 = fmaxf(mx3, sv[e + 3]);
+    }
+  }
+  return fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
+}
+
+// P = exp2(s - mref) -> 16 bit -> SWIZZLE_128B rows of the P tile; returns the row sum, tracks the true tile max
+template <bool HAS_BIAS, bool MASKED>
+__device__ __forceinline__ float exp_store(const RowCtx& x, int nc32, int npad, float mref, uint8_t* prow, int r, int dtype,
+                                           float& tmax) {
+  float rs0 = 0.f, rs1 = 0.f, mx0 = -INFINITY, mx1 = -INFINITY;
+  for (int c = 0; c < nc32; c += 32) {
+    float sv[32];
+    load_scores<HAS_BIAS, MASKED>(x, c, sv);
+    uint32_t pk[16];
+#pragma unroll
+    for (int e = 0; e < 32; e += 2) {
+      mx0 = fmaxf(mx0, sv[e]); mx1 = fmaxf(mx1, sv[e + 1]);
+      const float p0 = ex2(sv[e] - mref), p1 = ex2(sv[e + 1] - mref);
+      rs0 += p0; rs1 += p1;
+      pk[e >> 1] = pack2(p0, p1, dtype);
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {                  // 4 x 16-byte chunks of 8 keys
+      const int key0 = c + q * 8;
+      if (!MASKED || key0 < npad) {
+        const int atom = key0 >> 6, chunk = (key0 & 63) >> 3;
+        *reinterpret_cast<uint4*>(prow + atom * (TQ * 128) + ((chunk ^ (r & 7)) << 4)) =
+            make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
+      }
+    }
+  }
+  tmax = fmaxf(mx0, mx1);
+  return rs0 + rs1;
+}
+
+template <bool HAS_BIAS, bool MASKED>
+__device__ __forceinline__ float softmax_tile(const RowCtx& x, int j, int nc32, int npad, uint8_t* prow, int r, int dtype,
+                                              float& m_ref, float& l_run, uint32_t o_addr, int hd_cols) {
+  // NOTE: tcgen05.ld is warp-collective (.sync.aligned): every branch around it must be warp-uniform.
+  float tmax, rsum;
+  if (j == 0) {                                      // no reference yet: exact two-pass tile
+    const float mx = tile_max<HAS_BIAS, MASKED>(x, nc32);
+    if (mx != -INFINITY) m_ref = mx;
+    rsum = exp_store<HAS_BIAS, MASKED>(x, nc32, npad, mx == -INFINITY ? 0.f : mx, prow, r, dtype, tmax);
+  } else {
+    rsum = exp_store<HAS_BIAS, MASKED>(x, nc32, npad, m_ref == -INFINITY ? 0.f : m_ref, prow, r, dtype, tmax);
+    if (__any_sync(0xffffffffu, tmax > m_ref + TAU)) {   // rare: some row's max jumped; redo the tile exactly
+      const float m_new = fmaxf(m_ref, tmax);
+      const float corr = (m_ref == -INFINITY) ? 0.f : ex2(m_ref - m_new);
+      l_run *= corr;
+      // s_full(j) completed => PV(j-1) completed (in-order tensor pipe); PV(j) is not issued before p_full(j):
+      // this thread owns its TMEM lane of O right now.
+      for (int c = 0; c < hd_cols; c += 32) {
+        uint32_t v[32];
+        tmem_ld_32x32b_x32(o_addr + c, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int e = 0; e < 32; ++e) v[e] = __float_as_uint(__uint_as_float(v[e]) * corr);
+        tmem_st_32x32b_x32(o_addr + c, v);
+      }
+      tmem_st_wait();
+      m_ref = m_new;
+      rsum = exp_store<HAS_BIAS, MASKED>(x, nc32, npad, m_ref == -INFINITY ? 0.f : m_ref, prow, r, dtype, tmax);
+    }
+  }
+  return rsum;
+}
+
 template <int HD>
 __global__ void __launch_bounds__(320, 1)
 attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
@@ -86,7 +189,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   constexpr uint32_t TMEM_COLS = 512;
   constexpr int S_COL = 0, O_COL = 256;          // S_A [0,128) S_B [128,256) ; O_A [256,256+HD) O_B [256+HD, 256+2HD)
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S::OFF_BAR);
   uint64_t* q_full = bars;
   uint64_t* kv_full = bars + 1;
@@ -175,9 +278,9 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         // A = P (K-major, SW128): 64-key atom (k/4), 32-byte step inside the atom
         const uint64_t a = umma_desc(p_addr + (k >> 2) * (TQ * 128) + (k & 3) * 32, 16, 1024, LAYOUT_SW128);
         // B = V [key][d] read MN-major: 16 keys = two 8-key groups of 1024 B (SW128) / 512 B (SW64)
-        umma_f16(d_o, a, umma_desc(v_addr + k * 2048, TKV * 128, 1024, LAYOUT_SW128), id64, k > 0 ? 1u : 0u);
+        umma_f16(d_o, a, umma_desc(v_addr + k * 2048, TKV * 128, 1024, LAYOUT_SW128), id64, (k > 0 || j > 0) ? 1u : 0u);
         if (SPLIT)
-          umma_f16(d_o + 64, a, umma_desc(v_addr + TKV * 128 + k * 1024, TKV * 64, 512, LAYOUT_SW64), id32, k > 0 ? 1u : 0u);
+          umma_f16(d_o + 64, a, umma_desc(v_addr + TKV * 128 + k * 1024, TKV * 64, 512, LAYOUT_SW64), id32, (k > 0 || j > 0) ? 1u : 0u);
       }
       umma_commit(&o_full[g]);
     };
@@ -217,26 +320,10 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       const int* mrow = p.kmask ? p.kmask + static_cast<long long>(bkv) * p.Lk : nullptr;
       float* wbias = reinterpret_cast<float*>(smem + S::OFF_BIAS) + (warp - 2) * 160;   // this warp's bias window
       uint8_t* prow = smem + S::OFF_P + g * S::P_BYTES + r * 128;
-      float o_reg[HD];
-#pragma unroll
-      for (int c = 0; c < HD; ++c) o_reg[c] = 0.f;
       float m_ref = -INFINITY, l_run = 0.f;
       // window index for (row r, column c): (kv0 + c) - i_abs + zero = w0 + (31 - lane) + c, w0 = bias index of
       // (column 0, last row of this warp)
       const int i_warp_last = min(qg0 + quad * 32 + 31, p.Lq - 1) + p.q_pos0;
-
-      auto fold_o = [&](int j) {
-        mbar_wait(&o_full[g], j & 1);
-        tc_fence_after();
-#pragma unroll
-        for (int c = 0; c < HD; c += 32) {
-          uint32_t v[32];
-          tmem_ld_32x32b_x32(o_addr + c, v);
-          tmem_ld_wait();
-#pragma unroll
-          for (int e = 0; e < 32; ++e) o_reg[c + e] += __uint_as_float(v[e]);
-        }
-      };
 
       for (int j = 0; j < n_kv; ++j) {
         const int kv0 = j * TKV;
@@ -253,97 +340,30 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
           }
           __syncwarp();
         }
-        uint32_t mb0 = 0xffffffffu, mb1 = 0xffffffffu, mb2 = 0xffffffffu, mb3 = 0xffffffffu;
+        RowCtx x;
+        x.s_addr = s_addr; x.sl2 = sl2; x.ncols = ncols; x.kv0 = kv0; x.i_abs = i_abs; x.causal = p.causal;
+        x.mb[0] = x.mb[1] = x.mb[2] = x.mb[3] = 0xffffffffu;
         bool masked = (ncols < TKV) || (p.causal && kv0 + TKV - 1 > qg0 + quad * 32 + p.q_pos0);
         if (mrow) {
           const int jj = kv0 + lane;
-          mb0 = __ballot_sync(0xffffffffu, (jj < p.Lk) && __ldg(mrow + min(jj, p.Lk - 1)) != 0);
-          mb1 = __ballot_sync(0xffffffffu, (jj + 32 < p.Lk) && __ldg(mrow + min(jj + 32, p.Lk - 1)) != 0);
-          mb2 = __ballot_sync(0xffffffffu, (jj + 64 < p.Lk) && __ldg(mrow + min(jj + 64, p.Lk - 1)) != 0);
-          mb3 = __ballot_sync(0xffffffffu, (jj + 96 < p.Lk) && __ldg(mrow + min(jj + 96, p.Lk - 1)) != 0);
-          masked = masked || ((mb0 & mb1 & mb2 & mb3) != 0xffffffffu);
+#pragma unroll
+          for (int w = 0; w < 4; ++w)
+            x.mb[w] = __ballot_sync(0xffffffffu, (jj + 32 * w < p.Lk) && __ldg(mrow + min(jj + 32 * w, p.Lk - 1)) != 0);
+          masked = masked || ((x.mb[0] & x.mb[1] & x.mb[2] & x.mb[3]) != 0xffffffffu);
         }
-        // the bias window of THIS thread's row starts at wbias[31 - lane + (i_warp_last - i_abs) ...]: rows are consecutive
-        const float* wrow = wbias + (i_warp_last - i_abs);
+        // rows of a warp are consecutive: this row's window starts (i_warp_last - i_abs) floats into the warp window
+        x.wrow = wbias + (i_warp_last - i_abs);
 
         mbar_wait(&s_full[g], j & 1);
         tc_fence_after();
-        if (j > 0) fold_o(j - 1);
 
-        // score of column c (log2 domain), chunk-level helpers
-        auto load_scores = [&](int c, float* sv) {
-          uint32_t v[32];
-          tmem_ld_32x32b_x32(s_addr + c, v);
-          tmem_ld_wait();
-          const uint32_t mw = (c == 0) ? mb0 : (c == 32) ? mb1 : (c == 64) ? mb2 : mb3;
-#pragma unroll
-          for (int e = 0; e < 32; ++e) {
-            float s = __uint_as_float(v[e]) * sl2;
-            if (bhead) s += wrow[c + e];
-            if (masked) {
-              const bool ok = (c + e < ncols) && ((mw >> e) & 1u) && !(p.causal && kv0 + c + e > i_abs);
-              if (!ok) s = -INFINITY;
-            }
-            sv[e] = s;
-          }
-        };
-        auto tile_max = [&]() {
-          float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
-          for (int c = 0; c < nc32; c += 32) {
-            float sv[32];
-            load_scores(c, sv);
-#pragma unroll
-            for (int e = 0; e < 32; e += 4) {
-              mx0 = fmaxf(mx0, sv[e]); mx1 = fmaxf(mx1, sv[e + 1]); mx2 = fmaxf(mx2, sv[e + 2]); mx3 = fmaxf(mx3, sv[e + 3]);
-            }
-          }
-          return fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
-        };
-        // exp + pack + store with reference max mref; returns row sum, tracks the true tile max
-        auto exp_store = [&](float mref, float& tmax) {
-          float rs0 = 0.f, rs1 = 0.f, mx0 = -INFINITY, mx1 = -INFINITY;
-          for (int c = 0; c < nc32; c += 32) {
-            float sv[32];
-            load_scores(c, sv);
-            uint32_t pk[16];
-#pragma unroll
-            for (int e = 0; e < 32; e += 2) {
-              mx0 = fmaxf(mx0, sv[e]); mx1 = fmaxf(mx1, sv[e + 1]);
-              const float p0 = ex2(sv[e] - mref), p1 = ex2(sv[e + 1] - mref);
-              rs0 += p0; rs1 += p1;
-              pk[e >> 1] = pack2(p0, p1, p.dtype);
-            }
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {                  // 4 x 16-byte chunks of 8 keys
-              const int key0 = c + q * 8;
-              if (key0 < npad) {
-                const int atom = key0 >> 6, chunk = (key0 & 63) >> 3;
-                *reinterpret_cast<uint4*>(prow + atom * (TQ * 128) + ((chunk ^ (r & 7)) << 4)) =
-                    make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
-              }
-            }
-          }
-          tmax = fmaxf(mx0, mx1);
-          return rs0 + rs1;
-        };
-
-        // NOTE: tcgen05.ld is warp-collective (.sync.aligned): every branch around it must be warp-uniform.
-        float tmax, rsum;
-        if (j == 0) {                                      // no reference yet: exact two-pass tile
-          const float mx = tile_max();
-          if (mx != -INFINITY) m_ref = mx;
-          rsum = exp_store(mx == -INFINITY ? 0.f : mx, tmax);
+        float rsum;
+        if (bhead) {
+          rsum = masked ? softmax_tile<true, true>(x, j, nc32, npad, prow, r, p.dtype, m_ref, l_run, o_addr, HD)
+                        : softmax_tile<true, false>(x, j, nc32, npad, prow, r, p.dtype, m_ref, l_run, o_addr, HD);
         } else {
-          rsum = exp_store(m_ref == -INFINITY ? 0.f : m_ref, tmax);   // single pass against the stale max
-          if (__any_sync(0xffffffffu, tmax > m_ref + TAU)) {          // rare: some row's max jumped; redo the tile exactly
-            const float m_new = fmaxf(m_ref, tmax);
-            const float corr = (m_ref == -INFINITY) ? 0.f : ex2(m_ref - m_new);
-            l_run *= corr;
-#pragma unroll
-            for (int c = 0; c < HD; ++c) o_reg[c] *= corr;
-            m_ref = m_new;
-            rsum = exp_store(m_ref == -INFINITY ? 0.f : m_ref, tmax);
-          }
+          rsum = masked ? softmax_tile<false, true>(x, j, nc32, npad, prow, r, p.dtype, m_ref, l_run, o_addr, HD)
+                        : softmax_tile<false, false>(x, j, nc32, npad, prow, r, p.dtype, m_ref, l_run, o_addr, HD);
         }
         l_run += rsum;
         fence_proxy_async();
@@ -351,20 +371,32 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         __syncwarp();
         if (lane == 0) mbar_arrive(&p_full[g]);
       }
-      fold_o(n_kv - 1);
-      // epilogue
+      // epilogue: O (accumulated in TMEM over all KV tiles) / l
+      mbar_wait(&o_full[g], (n_kv - 1) & 1);
+      tc_fence_after();
       const int i = qg0 + r;
-      if (i < p.Lq) {
-        const float inv = l_run > 0.f ? 1.f / l_run : 0.f;
-        uint16_t* orow = static_cast<uint16_t*>(p.o) + b * p.o_bs + static_cast<long long>(i) * p.o_rs + static_cast<long long>(h) * p.hd;
+      const float inv = l_run > 0.f ? 1.f / l_run : 0.f;
+      uint16_t* orow = static_cast<uint16_t*>(p.o) + b * p.o_bs + static_cast<long long>(min(i, p.Lq - 1)) * p.o_rs +
+                       static_cast<long long>(h) * p.hd;
 #pragma unroll
-        for (int c = 0; c < HD; c += 8) {
-          if (c < p.hd) {
-            *reinterpret_cast<uint4*>(orow + c) =
-                make_uint4(pack2(o_reg[c] * inv, o_reg[c + 1] * inv, p.dtype), pack2(o_reg[c + 2] * inv, o_reg[c + 3] * inv, p.dtype),
-                           pack2(o_reg[c + 4] * inv, o_reg[c + 5] * inv, p.dtype), pack2(o_reg[c + 6] * inv, o_reg[c + 7] * inv, p.dtype));
+      for (int c0 = 0; c0 < HD; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld_32x32b_x32(o_addr + c0, v);
+        tmem_ld_wait();
+        if (i < p.Lq) {
+#pragma unroll
+          for (int c = 0; c < 32; c += 8) {
+            if (c0 + c < p.hd) {
+              *reinterpret_cast<uint4*>(orow + c0 + c) =
+                  make_uint4(pack2(__uint_as_float(v[c]) * inv, __uint_as_float(v[c + 1]) * inv, p.dtype),
+                             pack2(__uint_as_float(v[c + 2]) * inv, __uint_as_float(v[c + 3]) * inv, p.dtype),
+                             pack2(__uint_as_float(v[c + 4]) * inv, __uint_as_float(v[c + 5]) * inv, p.dtype),
+                             pack2(__uint_as_float(v[c + 6]) * inv, __uint_as_float(v[c + 7]) * inv, p.dtype));
+            }
           }
         }
+      }
+      if (i < p.Lq) {
         if (p.lse) p.lse[(static_cast<long long>(b) * p.H + h) * p.Lq + i] = (m_ref + log2f(l_run)) * 0.6931471805599453f;
       }
     }
