@@ -50,6 +50,15 @@ int mrb_attention_bwd(const void* q, long long q_bs, long long q_rs, const void*
                       int bias_zero, const int* kmask, int causal, int q_pos0, const float* lse, float* delta_ws,
                       void* stream);
 
+/* tcgen05 implementation of mrb_attention_bwd (hd == 64): a dK/dV kernel (keys stationary, 64-query tiles streamed)
+ * and a dQ kernel (queries stationary, 64-key tiles streamed); S^T/dP^T tiles and the dK/dV/dQ accumulators live in TMEM. */
+int mrb_attention_bwd_tc(const void* q, long long q_bs, long long q_rs, const void* k, long long k_bs, long long k_rs,
+                         const void* v, long long v_bs, long long v_rs, const void* o, long long o_bs, long long o_rs,
+                         const void* dout, long long do_bs, long long do_rs, void* dq, void* dk, void* dv,
+                         int B, int H, int Lq, int Lk, int hd, int dtype, float scale, const float* bias, int bias_len,
+                         int bias_zero, const int* kmask, int causal, int q_pos0, const float* lse, float* delta_ws,
+                         void* stream);
+
 /* mode 0: LayerNorm(x [+ add]) (eva_vit.py:175-176, blip2.py:113-119, Qformer.py:104-108,288);
  * mode 1: T5 RMSNorm (modeling_t5.py:263-277).  fp32 in; optional fp32 out, 16-bit out (ld_h), and x+add out. */
 int mrb_norm(const float* x, const float* add, const float* w, const float* bias, float eps, int rows, int C, int mode,

@@ -17,6 +17,8 @@ SIGNATURES = {
                              _p, _i, _i, _i, _p, _p],
     "mrb_attention_bwd": [_p, _ll, _ll, _p, _ll, _ll, _p, _ll, _ll, _p, _ll, _ll, _p, _ll, _ll, _p, _p, _p,
                           _i, _i, _i, _i, _i, _i, _f, _p, _i, _i, _p, _i, _i, _p, _p, _p],
+    "mrb_attention_bwd_tc": [_p, _ll, _ll, _p, _ll, _ll, _p, _ll, _ll, _p, _ll, _ll, _p, _ll, _ll, _p, _p, _p,
+                             _i, _i, _i, _i, _i, _i, _f, _p, _i, _i, _p, _i, _i, _p, _p, _p],
     "mrb_norm": [_p, _p, _p, _p, _f, _i, _i, _i, _p, _p, _i, _ll, _p, _p],
     "mrb_rmsnorm_bwd": [_p, _p, _p, _i, _ll, _p, _i, _f, _i, _i, _p, _p],
     "mrb_lora_up_add": [_p, _ll, _p, _i, _i, _i, _i, _p, _p],
@@ -40,7 +42,7 @@ SIGNATURES = {
 
 _lib = None
 launch_count = 0     # kernels launched through the C ABI so far (bench.py reports the delta as gpu_launches)
-_KERNELS_PER_CALL = {"mrb_attention_bwd": 3}
+_KERNELS_PER_CALL = {"mrb_attention_bwd": 3, "mrb_attention_bwd_tc": 3}
 
 
 class MrbError(RuntimeError):

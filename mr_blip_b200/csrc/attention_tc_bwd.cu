@@ -1,0 +1,434 @@
+// tcgen05 flash-attention backward for T5 (hd 64; modeling_t5.py:561-610 under autograd): two kernels built from one
+// template.  Forward recap: S = scale*Q K^T + bias + mask, P = softmax(S), O = P V, lse = logsumexp(S).
+//   MODE_DKV  CTA owns 2 x 128 keys (two softmax groups); streams 64-query tiles (Q_t, dO_t):
+//               S^T  = K_g Q_t^T        dP^T = V_g dO_t^T           (128 x 64 fp32 tiles in TMEM)
+//               P^T  = exp(S^T - lse),  dS^T = P^T * (dP^T - delta) * scale   -> 16-bit, SWIZZLE_128B smem tiles
+//               dV_g += P^T dO_t        dK_g += dS^T Q_t             (accumulated in TMEM over all query tiles)
+//   MODE_DQ   CTA owns 2 x 128 queries; streams 64-key tiles (K_t, V_t):
+//               S = Q_g K_t^T, dP = dO_g V_t^T, dS = P * (dP - delta) * scale,  dQ_g += dS K_t
+// Same warp roles and mbarrier protocol as attention_tc.cu (TMA producer / single-thread MMA issuer / 2 x 4 warps with
+// one thread per TMEM lane).  The B operands of the accumulating MMAs (dO_t, Q_t, K_t) are read MN-major straight from
+// their [row][d] tiles, so nothing is transposed in memory.
+#include "common.cuh"
+
+namespace mrb {
+
+struct AttnBwdParams {
+  int B, H, Lq, Lk, dtype;
+  float scale;
+  const float* bias; int bias_len, bias_zero;
+  const int* kmask;
+  int causal, q_pos0;
+  const float* lse; const float* delta;          // [B, H, Lq]
+  void* out1; long long o1_bs, o1_rs;            // DKV: dK ; DQ: dQ
+  void* out2; long long o2_bs, o2_rs;            // DKV: dV
+};
+
+constexpr int MODE_DKV = 0, MODE_DQ = 1;
+constexpr int TS = 128;      // stationary rows per group
+constexpr int TT = 64;       // streamed rows per tile
+constexpr int BHD = 64;
+
+__device__ __forceinline__ void tma_load_4d_b(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ float ex2b(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ uint64_t udesc(uint32_t addr, uint32_t lbo, uint32_t sbo) {   // SWIZZLE_128B
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((addr & 0x3FFFF) >> 4);
+  d |= static_cast<uint64_t>((lbo >> 4) & 0x3FFF) << 16;
+  d |= static_cast<uint64_t>((sbo >> 4) & 0x3FFF) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(2) << 61;
+  return d;
+}
+__host__ __device__ constexpr uint32_t idesc_b(int fmt, int M, int N, int b_mn_major) {
+  return (1u << 4) | (static_cast<uint32_t>(fmt) << 7) | (static_cast<uint32_t>(fmt) << 10) |
+         (static_cast<uint32_t>(b_mn_major) << 16) | (static_cast<uint32_t>(N >> 3) << 17) | (static_cast<uint32_t>(M >> 4) << 24);
+}
+
+struct BwdSmem {
+  static constexpr int X_BYTES = TS * 128;                 // one stationary tile (128 rows x 64 d)
+  static constexpr int U_BYTES = TT * 128;                 // one streamed tile (64 rows x 64 d)
+  static constexpr int STAGES = 3;
+  static constexpr int OFF_X = 0;                          // [group][X, Y]
+  static constexpr int OFF_U = 4 * X_BYTES;                // [stage][U, W]
+  static constexpr int OFF_E = OFF_U + STAGES * 2 * U_BYTES;   // [group][P, dS] 128 x 64 16-bit operand tiles
+  static constexpr int OFF_WIN = OFF_E + 4 * X_BYTES;      // 8 warps x (96 bias + 64 lse + 64 delta) floats
+  static constexpr int WIN_FLOATS = 96 + 64 + 64;
+  static constexpr int OFF_BAR = OFF_WIN + 8 * WIN_FLOATS * 4;
+  static constexpr int NBAR = 1 + 2 * STAGES + 6;
+  static constexpr int TOTAL = OFF_BAR + NBAR * 8 + 16 + 1024;
+};
+
+template <int MODE>
+__global__ void __launch_bounds__(320, 1)
+attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmY,
+                   const __grid_constant__ CUtensorMap tmU, const __grid_constant__ CUtensorMap tmW, const AttnBwdParams p) {
+  using S = BwdSmem;
+  constexpr int STAGES = S::STAGES;
+  constexpr uint32_t TMEM_COLS = 512;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S::OFF_BAR);
+  uint64_t* x_full = bars;
+  uint64_t* st_full = bars + 1;
+  uint64_t* st_empty = st_full + STAGES;
+  uint64_t* t_full = st_empty + STAGES;
+  uint64_t* e_full = t_full + 2;
+  uint64_t* acc_full = e_full + 2;
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + S::NBAR);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int b = blockIdx.z, h = blockIdx.y, x0 = blockIdx.x * (2 * TS);
+  const int Lstat = (MODE == MODE_DKV) ? p.Lk : p.Lq;      // stationary / streamed sequence lengths
+  const int Lstrm = (MODE == MODE_DKV) ? p.Lq : p.Lk;
+  const int n_groups = (x0 + TS < Lstat) ? 2 : 1;
+  int t_begin = 0, t_end = (Lstrm + TT - 1) / TT;
+  if (p.causal) {
+    if (MODE == MODE_DQ) t_end = min(t_end, (min(x0 + n_groups * TS, p.Lq) - 1 + p.q_pos0) / TT + 1);   // keys j <= i_max
+    else t_begin = min(t_end - 1, max(0, (x0 - p.q_pos0) / TT));                                       // queries i >= j_min - q_pos0
+  }
+  const int n_t = t_end - t_begin;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmX); tma_prefetch_desc(&tmY); tma_prefetch_desc(&tmU); tma_prefetch_desc(&tmW);
+    mbar_init(x_full, 1);
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&st_full[s], 1); mbar_init(&st_empty[s], 1); }
+    for (int g = 0; g < 2; ++g) { mbar_init(&t_full[g], 1); mbar_init(&e_full[g], 4); mbar_init(&acc_full[g], 1); }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_holder, TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_holder;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      mbar_expect_tx(x_full, n_groups * 2 * S::X_BYTES);
+      for (int g = 0; g < n_groups; ++g) {
+        tma_load_4d_b(smem + S::OFF_X + (2 * g) * S::X_BYTES, &tmX, x_full, 0, h, x0 + g * TS, b);
+        tma_load_4d_b(smem + S::OFF_X + (2 * g + 1) * S::X_BYTES, &tmY, x_full, 0, h, x0 + g * TS, b);
+      }
+      for (int t = 0; t < n_t; ++t) {
+        const int st = t % STAGES;
+        mbar_wait(&st_empty[st], ((t / STAGES) & 1) ^ 1);
+        uint8_t* su = smem + S::OFF_U + st * 2 * S::U_BYTES;
+        mbar_expect_tx(&st_full[st], 2 * S::U_BYTES);
+        tma_load_4d_b(su, &tmU, &st_full[st], 0, h, (t_begin + t) * TT, b);
+        tma_load_4d_b(su + S::U_BYTES, &tmW, &st_full[st], 0, h, (t_begin + t) * TT, b);
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    const int fmt = p.dtype == MRB_DT_BF16 ? 1 : 0;
+    const uint32_t id_t = idesc_b(fmt, TS, TT, 0);          // 128 x 64, both operands K-major (contraction over d)
+    const uint32_t id_a = idesc_b(fmt, TS, BHD, 1);         // 128 x 64(d), B MN-major (contraction over streamed rows)
+    auto issue_T = [&](int g, int t) {
+      const int st = t % STAGES;
+      const uint32_t x_addr = smem_u32(smem + S::OFF_X + (2 * g) * S::X_BYTES);
+      const uint32_t y_addr = x_addr + S::X_BYTES;
+      const uint32_t u_addr = smem_u32(smem + S::OFF_U + st * 2 * S::U_BYTES);
+      const uint32_t w_addr = u_addr + S::U_BYTES;
+      const uint32_t d1 = tmem_base + g * 256, d2 = d1 + 64;
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        umma_f16(d1, udesc(x_addr + k * 32, 16, 1024), udesc(u_addr + k * 32, 16, 1024), id_t, k > 0 ? 1u : 0u);
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        umma_f16(d2, udesc(y_addr + k * 32, 16, 1024), udesc(w_addr + k * 32, 16, 1024), id_t, k > 0 ? 1u : 0u);
+      umma_commit(&t_full[g]);
+    };
+    auto issue_acc = [&](int g, int t) {
+      const int st = t % STAGES;
+      const uint32_t e_addr = smem_u32(smem + S::OFF_E + (2 * g) * S::X_BYTES);      // P tile, then dS tile
+      const uint32_t u_addr = smem_u32(smem + S::OFF_U + st * 2 * S::U_BYTES);
+      const uint32_t w_addr = u_addr + S::U_BYTES;
+      const uint32_t a1 = tmem_base + g * 256 + 128, a2 = a1 + 64;
+      const uint32_t acc = t > 0 ? 1u : 0u;
+      if (MODE == MODE_DKV) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k)      // dV += P^T dO_t
+          umma_f16(a1, udesc(e_addr + k * 32, 16, 1024), udesc(w_addr + k * 2048, TT * 128, 1024), id_a, (k > 0) ? 1u : acc);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)      // dK += dS^T Q_t
+          umma_f16(a2, udesc(e_addr + S::X_BYTES + k * 32, 16, 1024), udesc(u_addr + k * 2048, TT * 128, 1024), id_a,
+                   (k > 0) ? 1u : acc);
+      } else {
+#pragma unroll
+        for (int k = 0; k < 4; ++k)      // dQ += dS K_t
+          umma_f16(a1, udesc(e_addr + S::X_BYTES + k * 32, 16, 1024), udesc(u_addr + k * 2048, TT * 128, 1024), id_a,
+                   (k > 0) ? 1u : acc);
+      }
+    };
+    mbar_wait(x_full, 0);
+    mbar_wait(&st_full[0], 0);
+    tc_fence_after();
+    if (lane == 0)
+      for (int g = 0; g < n_groups; ++g) issue_T(g, 0);
+    __syncwarp();
+    for (int t = 0; t < n_t; ++t) {
+      for (int g = 0; g < n_groups; ++g) {
+        mbar_wait(&e_full[g], t & 1);
+        if (g == 0 && t + 1 < n_t) mbar_wait(&st_full[(t + 1) % STAGES], ((t + 1) / STAGES) & 1);
+        tc_fence_after();
+        if (lane == 0) {
+          issue_acc(g, t);
+          if (g == n_groups - 1) umma_commit(&st_empty[t % STAGES]);
+          if (t + 1 < n_t) issue_T(g, t + 1);
+          else umma_commit(&acc_full[g]);
+        }
+        __syncwarp();
+      }
+    }
+  } else {
+    // ===================== elementwise groups: one thread per stationary row =====================
+    const int g = (warp - 2) >> 2;
+    if (g < n_groups) {
+      const int quad = warp & 3;
+      const int r = quad * 32 + lane;
+      const int xg0 = x0 + g * TS;
+      const int row = xg0 + r;                               // key index (DKV) or query index (DQ)
+      const int row_c = min(row, Lstat - 1);
+      const uint32_t lane_base = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + g * 256;
+      const float LOG2E = 1.4426950408889634f;
+      const float sl2 = p.scale * LOG2E;
+      const float* bhead = p.bias ? p.bias + static_cast<long long>(h) * p.bias_len : nullptr;
+      const long long stat_off = (static_cast<long long>(b) * p.H + h) * p.Lq;
+      float* win = reinterpret_cast<float*>(smem + S::OFF_WIN) + (warp - 2) * S::WIN_FLOATS;
+      float* wlse = win + 96;
+      float* wdl = win + 160;
+      uint8_t* prow = smem + S::OFF_E + (2 * g) * S::X_BYTES + r * 128;     // P row; dS row at + X_BYTES
+      // per-row constants
+      float lse_row = 0.f, dl_row = 0.f;
+      bool row_key_ok = true;
+      if (MODE == MODE_DQ) {
+        lse_row = p.lse[stat_off + row_c] * LOG2E;
+        dl_row = p.delta[stat_off + row_c];
+      } else if (p.kmask) {
+        row_key_ok = __ldg(p.kmask + static_cast<long long>(b) * p.Lk + row_c) != 0;
+      }
+      const int warp_row_first = min(xg0 + quad * 32, Lstat - 1), warp_row_last = min(xg0 + quad * 32 + 31, Lstat - 1);
+
+      for (int t = 0; t < n_t; ++t) {
+        const int u0 = (t_begin + t) * TT;                   // first streamed row (query for DKV, key for DQ)
+        __syncwarp();
+        // ---- stage the per-warp windows: bias (pre-multiplied by log2 e) and, for DKV, lse / delta of the 64 queries
+        if (bhead) {
+          // DQ : idx(row i, col j=u0+c) = (u0 + c) - (i + q_pos0) + zero   -> W[k] = bias[w0 + k], w0 from the warp's last row
+          // DKV: idx(row j, col i=u0+c) = j - (u0 + c + q_pos0) + zero     -> w0 from the warp's first row and c = 63
+          const int w0 = (MODE == MODE_DQ) ? (u0 - (warp_row_last + p.q_pos0) + p.bias_zero)
+                                           : (warp_row_first - (u0 + 63 + p.q_pos0) + p.bias_zero);
+          for (int k = lane; k < 96; k += 32) {
+            const int idx = w0 + k;
+            win[k] = (idx >= 0 && idx < p.bias_len) ? __ldg(bhead + idx) * LOG2E : 0.f;
+          }
+        }
+        uint32_t cm0 = 0xffffffffu, cm1 = 0xffffffffu;       // per-column validity bits (keys for DQ)
+        if (MODE == MODE_DKV) {
+          for (int k = lane; k < 64; k += 32) {
+            const int i = u0 + k;
+            wlse[k] = (i < p.Lq) ? p.lse[stat_off + i] * LOG2E : 0.f;
+            wdl[k] = (i < p.Lq) ? p.delta[stat_off + i] : 0.f;
+          }
+        } else {
+          const int* mrow = p.kmask ? p.kmask + static_cast<long long>(b) * p.Lk : nullptr;
+          const int j0 = u0 + lane, j1 = u0 + 32 + lane;
+          cm0 = __ballot_sync(0xffffffffu, j0 < p.Lk && (!mrow || __ldg(mrow + min(j0, p.Lk - 1)) != 0));
+          cm1 = __ballot_sync(0xffffffffu, j1 < p.Lk && (!mrow || __ldg(mrow + min(j1, p.Lk - 1)) != 0));
+        }
+        __syncwarp();
+        const float* wrow = (MODE == MODE_DQ) ? (win + (warp_row_last - row_c)) : (win + (row_c - warp_row_first) + 63);
+
+        mbar_wait(&t_full[g], t & 1);
+        tc_fence_after();
+#pragma unroll
+        for (int c0 = 0; c0 < TT; c0 += 32) {
+          uint32_t sv[32], dv[32];
+          tmem_ld_32x32b_x32(lane_base + c0, sv);
+          tmem_ld_32x32b_x32(lane_base + 64 + c0, dv);
+          tmem_ld_wait();
+          const uint32_t cm = c0 == 0 ? cm0 : cm1;
+          uint32_t pp[16], pd[16];
+#pragma unroll
+          for (int e = 0; e < 32; e += 2) {
+            float pr[2], ds[2];
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+              const int c = c0 + e + q;
+              float s = __uint_as_float(sv[e + q]) * sl2;
+              if (bhead) s += (MODE == MODE_DQ) ? wrow[c] : wrow[-c];
+              const float lse_c = (MODE == MODE_DQ) ? lse_row : wlse[c];
+              const float dl_c = (MODE == MODE_DQ) ? dl_row : wdl[c];
+              float pv = ex2b(s - lse_c);
+              bool ok;
+              if (MODE == MODE_DQ) ok = ((cm >> (e + q)) & 1u) && !(p.causal && u0 + c > row_c + p.q_pos0);
+              else ok = row_key_ok && !(p.causal && row_c > u0 + c + p.q_pos0);
+              pv = ok ? pv : 0.f;
+              pr[q] = pv;
+              ds[q] = pv * (__uint_as_float(dv[e + q]) - dl_c) * p.scale;
+            }
+            pp[e >> 1] = pack2(pr[0], pr[1], p.dtype);
+            pd[e >> 1] = pack2(ds[0], ds[1], p.dtype);
+          }
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const int chunk = (c0 >> 3) + q;
+            const int off = (chunk ^ (r & 7)) << 4;
+            if (MODE == MODE_DKV)
+              *reinterpret_cast<uint4*>(prow + off) = make_uint4(pp[4 * q], pp[4 * q + 1], pp[4 * q + 2], pp[4 * q + 3]);
+            *reinterpret_cast<uint4*>(prow + S::X_BYTES + off) = make_uint4(pd[4 * q], pd[4 * q + 1], pd[4 * q + 2], pd[4 * q + 3]);
+          }
+        }
+        fence_proxy_async();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&e_full[g]);
+      }
+      // ---- write the accumulators
+      mbar_wait(&acc_full[g], 0);
+      tc_fence_after();
+      const int n_out = (MODE == MODE_DKV) ? 2 : 1;
+      for (int a = 0; a < n_out; ++a) {
+        // DKV: TMEM acc1 = dV -> out2, acc2 = dK -> out1 ; DQ: acc1 = dQ -> out1
+        void* outp = (MODE == MODE_DKV) ? (a == 0 ? p.out2 : p.out1) : p.out1;
+        const long long bs = (MODE == MODE_DKV && a == 0) ? p.o2_bs : p.o1_bs;
+        const long long rs = (MODE == MODE_DKV && a == 0) ? p.o2_rs : p.o1_rs;
+        uint16_t* orow = static_cast<uint16_t*>(outp) + b * bs + static_cast<long long>(row_c) * rs + static_cast<long long>(h) * BHD;
+#pragma unroll
+        for (int c0 = 0; c0 < BHD; c0 += 32) {
+          uint32_t v[32];
+          tmem_ld_32x32b_x32(lane_base + 128 + a * 64 + c0, v);
+          tmem_ld_wait();
+          if (row < Lstat) {
+#pragma unroll
+            for (int c = 0; c < 32; c += 8)
+              *reinterpret_cast<uint4*>(orow + c0 + c) =
+                  make_uint4(pack2(__uint_as_float(v[c]), __uint_as_float(v[c + 1]), p.dtype),
+                             pack2(__uint_as_float(v[c + 2]), __uint_as_float(v[c + 3]), p.dtype),
+                             pack2(__uint_as_float(v[c + 4]), __uint_as_float(v[c + 5]), p.dtype),
+                             pack2(__uint_as_float(v[c + 6]), __uint_as_float(v[c + 7]), p.dtype));
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+// delta[b,h,i] = sum_d dO[b,i,h,d] * O[b,i,h,d]  (16-bit inputs, hd = 64: one warp per row, 2 elements per lane)
+__global__ void attn_delta64_kernel(const uint16_t* __restrict__ o, long long o_bs, long long o_rs, const uint16_t* __restrict__ d_o,
+                                    long long do_bs, long long do_rs, float* __restrict__ delta, int B, int H, int Lq, int dtype) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= B * H * Lq) return;
+  const int i = row % Lq, h = (row / Lq) % H, b = row / (Lq * H);
+  const uint32_t ow = *reinterpret_cast<const uint32_t*>(o + b * o_bs + static_cast<long long>(i) * o_rs + h * 64 + lane * 2);
+  const uint32_t dw = *reinterpret_cast<const uint32_t*>(d_o + b * do_bs + static_cast<long long>(i) * do_rs + h * 64 + lane * 2);
+  float acc = unpack_lo(ow, dtype) * unpack_lo(dw, dtype) + unpack_hi(ow, dtype) * unpack_hi(dw, dtype);
+  acc = warp_sum(acc);
+  if (lane == 0) delta[row] = acc;
+}
+
+// ---------------------------------------------------------------- host
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_fn_b() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(ptr);
+  }
+  return fn;
+}
+static int make_tmap4b(CUtensorMap* map, const void* base, int dtype, int heads, int L, int B, long long rs, long long bs,
+                       int box_rows) {
+  EncodeTiledFn fn = encode_fn_b();
+  if (!fn) return MRB_ERR_CUDA;
+  cuuint64_t gdim[4] = {64, static_cast<cuuint64_t>(heads), static_cast<cuuint64_t>(L), static_cast<cuuint64_t>(B)};
+  cuuint64_t gstr[3] = {128, static_cast<cuuint64_t>(rs) * 2, static_cast<cuuint64_t>(bs) * 2};
+  cuuint32_t box[4] = {64, 1, static_cast<cuuint32_t>(box_rows), 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = fn(map, dtype == MRB_DT_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4,
+                  const_cast<void*>(base), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? MRB_OK : MRB_ERR_CUDA;
+}
+
+template <int MODE>
+static int launch_bwd_tc(const CUtensorMap& x, const CUtensorMap& y, const CUtensorMap& u, const CUtensorMap& w,
+                         const AttnBwdParams& p, int Lstat, cudaStream_t s) {
+  static bool cfg = false;
+  if (!cfg) {
+    cudaError_t e = cudaFuncSetAttribute(attn_bwd_tc_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, BwdSmem::TOTAL);
+    if (e != cudaSuccess) return mrb_set_error(e);
+    cfg = true;
+  }
+  dim3 grid((Lstat + 2 * TS - 1) / (2 * TS), p.H, p.B);
+  attn_bwd_tc_kernel<MODE><<<grid, 320, BwdSmem::TOTAL, s>>>(x, y, u, w, p);
+  MRB_CHECK_LAUNCH();
+  return MRB_OK;
+}
+
+}  // namespace mrb
+
+using namespace mrb;
+
+// Same contract as mrb_attention_bwd; hd must be 64.
+extern "C" int mrb_attention_bwd_tc(const void* q, long long q_bs, long long q_rs, const void* k, long long k_bs, long long k_rs,
+                                    const void* v, long long v_bs, long long v_rs, const void* o, long long o_bs, long long o_rs,
+                                    const void* dout, long long do_bs, long long do_rs, void* dq, void* dk, void* dv,
+                                    int B, int H, int Lq, int Lk, int hd, int dtype, float scale, const float* bias,
+                                    int bias_len, int bias_zero, const int* kmask, int causal, int q_pos0, const float* lse,
+                                    float* delta_ws, void* stream) {
+  if (B <= 0 || H <= 0 || Lq <= 0 || Lk <= 0) return MRB_OK;
+  if (hd != 64) return MRB_ERR_UNSUPPORTED;
+  if (dtype != MRB_DT_F16 && dtype != MRB_DT_BF16) return MRB_ERR_ARG;
+  if ((q_rs | k_rs | v_rs | o_rs | do_rs | q_bs | k_bs | v_bs | o_bs | do_bs) & 7) return MRB_ERR_ARG;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  {
+    const int rows = B * H * Lq;
+    attn_delta64_kernel<<<(rows + 7) / 8, 256, 0, s>>>(static_cast<const uint16_t*>(o), o_bs, o_rs,
+                                                         static_cast<const uint16_t*>(dout), do_bs, do_rs, delta_ws, B, H, Lq, dtype);
+    MRB_CHECK_LAUNCH();
+  }
+  AttnBwdParams p{};
+  p.B = B; p.H = H; p.Lq = Lq; p.Lk = Lk; p.dtype = dtype; p.scale = scale;
+  p.bias = bias; p.bias_len = bias_len; p.bias_zero = bias_zero; p.kmask = kmask; p.causal = causal; p.q_pos0 = q_pos0;
+  p.lse = lse; p.delta = delta_ws;
+  CUtensorMap mq128, mk128, mv128, mdo128, mq64, mk64, mv64, mdo64;
+  int rc = make_tmap4b(&mq128, q, dtype, H, Lq, B, q_rs, q_bs, TS);
+  if (!rc) rc = make_tmap4b(&mk128, k, dtype, H, Lk, B, k_rs, k_bs, TS);
+  if (!rc) rc = make_tmap4b(&mv128, v, dtype, H, Lk, B, v_rs, v_bs, TS);
+  if (!rc) rc = make_tmap4b(&mdo128, dout, dtype, H, Lq, B, do_rs, do_bs, TS);
+  if (!rc) rc = make_tmap4b(&mq64, q, dtype, H, Lq, B, q_rs, q_bs, TT);
+  if (!rc) rc = make_tmap4b(&mk64, k, dtype, H, Lk, B, k_rs, k_bs, TT);
+  if (!rc) rc = make_tmap4b(&mv64, v, dtype, H, Lk, B, v_rs, v_bs, TT);
+  if (!rc) rc = make_tmap4b(&mdo64, dout, dtype, H, Lq, B, do_rs, do_bs, TT);
+  if (rc) return rc;
+  // dK, dV: stationary K, V; streamed Q, dO
+  p.out1 = dk; p.o1_bs = k_bs; p.o1_rs = k_rs; p.out2 = dv; p.o2_bs = v_bs; p.o2_rs = v_rs;
+  rc = launch_bwd_tc<MODE_DKV>(mk128, mv128, mq64, mdo64, p, Lk, s);
+  if (rc) return rc;
+  // dQ: stationary Q, dO; streamed K, V
+  p.out1 = dq; p.o1_bs = q_bs; p.o1_rs = q_rs; p.out2 = nullptr;
+  return launch_bwd_tc<MODE_DQ>(mq128, mdo128, mk64, mv64, p, Lq, s);
+}

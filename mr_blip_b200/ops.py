@@ -76,8 +76,9 @@ def attention_fwd(q, k, v, out, B, H, Lq, Lk, hd, scale, q_strides, k_strides, v
 
 
 def attention_bwd(q, k, v, o, dout, dq, dk, dv, B, H, Lq, Lk, hd, scale, q_strides, k_strides, v_strides, o_strides,
-                  do_strides, lse, delta_ws, bias=None, bias_zero=0, kmask=None, causal=False, q_pos0=0):
-    _lib.call("mrb_attention_bwd", q.data_ptr(), q_strides[0], q_strides[1], k.data_ptr(), k_strides[0], k_strides[1],
+                  do_strides, lse, delta_ws, bias=None, bias_zero=0, kmask=None, causal=False, q_pos0=0, impl="auto"):
+    use_tc = impl == "tc" or (impl == "auto" and USE_TC_ATTENTION and hd == 64 and Lq >= 128 and Lk >= 128)
+    _lib.call("mrb_attention_bwd_tc" if use_tc else "mrb_attention_bwd", q.data_ptr(), q_strides[0], q_strides[1], k.data_ptr(), k_strides[0], k_strides[1],
               v.data_ptr(), v_strides[0], v_strides[1], o.data_ptr(), o_strides[0], o_strides[1], dout.data_ptr(),
               do_strides[0], do_strides[1], dq.data_ptr(), dk.data_ptr(), dv.data_ptr(), B, H, Lq, Lk, hd, _DT[q.dtype],
               float(scale), _ptr(bias), bias.shape[1] if bias is not None else 0, bias_zero, _ptr(kmask), int(causal),

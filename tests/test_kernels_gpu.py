@@ -133,7 +133,8 @@ def test_attention_cross_small_q(ops):
 
 
 @pytest.mark.parametrize("impl", ["mma", "tc"])
-@pytest.mark.parametrize("Lq,Lk,causal", [(150, 150, False), (21, 21, True), (21, 333, False), (300, 300, True)])
+@pytest.mark.parametrize("Lq,Lk,causal", [(150, 150, False), (21, 21, True), (21, 333, False), (300, 300, True),
+                                          (257, 400, False), (513, 513, False)])
 def test_attention_t5_bias_mask_fwd_bwd(ops, Lq, Lk, causal, impl):
     B, H, hd = 2, 32, 64
     dt = torch.bfloat16
@@ -158,7 +159,7 @@ def test_attention_t5_bias_mask_fwd_bwd(ops, Lq, Lk, causal, impl):
     dq, dk, dv = torch.zeros_like(q), torch.zeros_like(k), torch.zeros_like(v)
     ws = torch.zeros((B * H * Lq,), dtype=torch.float32, device="cuda")
     ops.attention_bwd(q, k, v, out, dout, dq, dk, dv, B, H, Lq, Lk, hd, 1.0, st(Lq), st(Lk), st(Lk), st(Lq), st(Lq),
-                      lse, ws, bias=table, bias_zero=Lq - 1, kmask=kmask, causal=causal)
+                      lse, ws, bias=table, bias_zero=Lq - 1, kmask=kmask, causal=causal, impl=impl)
     # 16-bit P/dS operands: errors scale with the gradient magnitude
     for got, ref, nm in ((dq, qr.grad, "dq"), (dk, kr.grad, "dk"), (dv, vr.grad, "dv")):
         _close(got, ref, 3e-2, 3e-2 * ref.abs().max().item(), nm)
