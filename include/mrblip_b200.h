@@ -76,7 +76,8 @@ int mrb_cls_pos(const float* cls, const float* pos, float* x, int frames, int to
 
 /* h = gelu(ab[:, :F]) * ab[:, F:]  and its backward  (modeling_t5.py:323-329) */
 int mrb_gated_gelu_fwd(const void* ab, void* h, int M, int F, long long ldh, int dtype, void* stream);
-int mrb_gated_gelu_bwd(const void* ab, const void* dh, long long lddh, void* dab, int M, int F, int dtype, void* stream);
+int mrb_gated_gelu_bwd(const void* ab, const void* dh, long long lddh, void* dab, long long lddab, int M, int F, int dtype,
+                       void* stream);
 
 /* inputs_embeds assembly (blip2_mr.py:691-783 interleave + embed_tokens lookups) from an int32 row table:
  * idx >= 0 embedding row, idx < 0 frame-token row -(idx+1), INT_MIN zero row; and its backward to the frame tokens. */
@@ -97,6 +98,10 @@ int mrb_lora_up_add(void* x_ext, long long ldx, const float* A, int R, int M, in
 /* out[C,8] (or [8,C] when transposed_out) += P[M,C]^T . Q[M,8]: LoRA A/B weight gradients */
 int mrb_skinny_wgrad(const void* P, long long ldp, const void* Q, long long ldq, int M, int C, float* out,
                      int transposed_out, int dtype, void* stream);
+
+/* out[m, r] = sum_k x[m,k] W[r,k], r < 32, 16-bit: LoRA down-projection when M is tiny (decoder); larger M use mrb_gemm */
+int mrb_small_down(const void* x, long long ldx, const void* W, long long ldw, int M, int K, void* out, long long ldo,
+                   int dtype, void* stream);
 
 /* plumbing: casts, 16-bit transpose, fp32 column sums (t5_proj bias grad), y = a*x + b*y */
 int mrb_cast_f32_to_h(const float* in, void* out, long long n, int dtype, void* stream);

@@ -25,7 +25,7 @@ SIGNATURES = {
     "mrb_patchify": [_p, _p, _i, _i, _i, _i, _i, _p],
     "mrb_cls_pos": [_p, _p, _p, _i, _i, _i, _p],
     "mrb_gated_gelu_fwd": [_p, _p, _i, _i, _ll, _i, _p],
-    "mrb_gated_gelu_bwd": [_p, _p, _ll, _p, _i, _i, _i, _p],
+    "mrb_gated_gelu_bwd": [_p, _p, _ll, _p, _ll, _i, _i, _i, _p],
     "mrb_gather_rows": [_p, _p, _p, _p, _i, _i, _p],
     "mrb_scatter_frames": [_p, _p, _p, _i, _i, _p],
     "mrb_group_mean": [_p, _p, _i, _i, _i, _p],
@@ -33,6 +33,7 @@ SIGNATURES = {
     "mrb_cross_entropy": [_p, _p, _i, _i, _p, _p, _i, _ll, _f, _p, _p],
     "mrb_lora_down": [_p, _ll, _p, _i, _i, _i, _i, _p],
     "mrb_skinny_wgrad": [_p, _ll, _p, _ll, _i, _i, _p, _i, _i, _p],
+    "mrb_small_down": [_p, _ll, _p, _ll, _i, _i, _p, _ll, _i, _p],
     "mrb_cast_f32_to_h": [_p, _p, _ll, _i, _p],
     "mrb_cast2d_f32_to_h": [_p, _ll, _p, _ll, _i, _i, _i, _p],
     "mrb_transpose16": [_p, _ll, _p, _ll, _i, _i, _p],

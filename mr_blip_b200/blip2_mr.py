@@ -37,7 +37,8 @@ class _HandOverGrads(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, g):
-        return (None, None) + tuple(None if gr is None else gr * g for gr in ctx.grads) + (None,) * len(ctx.grads)
+        scaled = torch._foreach_mul(list(ctx.grads), g)          # one multi-tensor kernel (GradScaler / accumulation factor)
+        return (None, None) + tuple(scaled) + (None,) * len(ctx.grads)
 
 
 class Blip2Base(BaseModel):

@@ -228,7 +228,7 @@ __global__ void gated_gelu_fwd_kernel(const uint4* __restrict__ ab, uint4* __res
 }
 // dab[:, :F] = dh * b * gelu'(a) ; dab[:, F:] = dh * gelu(a)
 __global__ void gated_gelu_bwd_kernel(const uint4* __restrict__ ab, const uint4* __restrict__ dh, long long lddh,
-                                      uint4* __restrict__ dab, int M, int F, int dtype) {
+                                      uint4* __restrict__ dab, long long lddab, int M, int F, int dtype) {
   const int fv = F >> 3;
   const long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
   if (idx >= static_cast<long long>(M) * fv) return;
@@ -245,8 +245,8 @@ __global__ void gated_gelu_bwd_kernel(const uint4* __restrict__ ab, const uint4*
     oa[i] = pack2(d0 * b0 * gelu_erf_grad(a0), d1 * b1 * gelu_erf_grad(a1), dtype);
     ob[i] = pack2(d0 * gelu_erf(a0), d1 * gelu_erf(a1), dtype);
   }
-  dab[m * (2 * fv) + c] = make_uint4(oa[0], oa[1], oa[2], oa[3]);
-  dab[m * (2 * fv) + fv + c] = make_uint4(ob[0], ob[1], ob[2], ob[3]);
+  dab[m * (lddab >> 3) + c] = make_uint4(oa[0], oa[1], oa[2], oa[3]);
+  dab[m * (lddab >> 3) + fv + c] = make_uint4(ob[0], ob[1], ob[2], ob[3]);
 }
 
 // ---------------------------------------------------------------- interleave gather (blip2_mr.py:691-783)
@@ -387,31 +387,90 @@ __global__ void __launch_bounds__(256) skinny_wgrad_kernel(const uint16_t* __res
                                                            const uint16_t* __restrict__ Q, long long ldq, int M, int C,
                                                            float* __restrict__ out, int transposed_out, int dtype,
                                                            int rows_per_block) {
-  __shared__ float red[4][64][9];
-  const int cx = threadIdx.x & 63, my = threadIdx.x >> 6;
-  const int c = blockIdx.x * 64 + cx;
+  // thread = (column group of 8 columns, row slice); block = 256 columns x rows_per_block rows.
+  // Row slices are combined with shared-memory atomics (layout [i][r][cg]: conflict-free), then one global atomic
+  // per output element and block.
+  __shared__ float red[64 * 32];
+  const int cg = threadIdx.x & 31, rs = threadIdx.x >> 5;
+  const int c0 = blockIdx.x * 256 + cg * 8;
   const int m0 = blockIdx.y * rows_per_block, m1 = min(M, m0 + rows_per_block);
-  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-  if (c < C) {
-    for (int m = m0 + my; m < m1; m += 4) {
-      const uint16_t pw = P[static_cast<long long>(m) * ldp + c];
-      const float pv = (dtype == MRB_DT_F16) ? __half2float(__ushort_as_half(pw)) : __uint_as_float(static_cast<uint32_t>(pw) << 16);
-      const uint4 qv = *reinterpret_cast<const uint4*>(Q + static_cast<long long>(m) * ldq);
-      const uint32_t w[4] = {qv.x, qv.y, qv.z, qv.w};
+  float acc[8][8];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) { acc[2 * i] += pv * unpack_lo(w[i], dtype); acc[2 * i + 1] += pv * unpack_hi(w[i], dtype); }
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int r = 0; r < 8; ++r) acc[i][r] = 0.f;
+  for (int i = threadIdx.x; i < 64 * 32; i += 256) red[i] = 0.f;
+  if (c0 < C) {
+#pragma unroll 4
+    for (int m = m0 + rs; m < m1; m += 8) {
+      const uint4 pv = *reinterpret_cast<const uint4*>(P + static_cast<long long>(m) * ldp + c0);
+      const uint4 qv = *reinterpret_cast<const uint4*>(Q + static_cast<long long>(m) * ldq);
+      const uint32_t pw[4] = {pv.x, pv.y, pv.z, pv.w}, qw[4] = {qv.x, qv.y, qv.z, qv.w};
+      float pf[8], qf[8];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        pf[2 * i] = unpack_lo(pw[i], dtype); pf[2 * i + 1] = unpack_hi(pw[i], dtype);
+        qf[2 * i] = unpack_lo(qw[i], dtype); qf[2 * i + 1] = unpack_hi(qw[i], dtype);
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int r = 0; r < 8; ++r) acc[i][r] = fmaf(pf[i], qf[r], acc[i][r]);
+    }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int r = 0; r < 8; ++r) atomicAdd(&red[(i * 8 + r) * 32 + cg], acc[i][r]);
+  __syncthreads();
+  for (int idx = threadIdx.x; idx < 64 * 32; idx += 256) {
+    const int g = idx & 31, ir = idx >> 5, i = ir >> 3, r = ir & 7;
+    const int c = blockIdx.x * 256 + g * 8 + i;
+    if (c < C) {
+      if (transposed_out) atomicAdd(out + static_cast<long long>(r) * C + c, red[idx]);
+      else atomicAdd(out + static_cast<long long>(c) * 8 + r, red[idx]);
+    }
+  }
+}
+
+// ---------------------------------------------------------------- LoRA down-projection for small M
+// out[m, r] = sum_k x[m, k] * W[r, k], r < 32 (16-bit x / W / out): one block per row.  Used when M is too small for the
+// tensor-core path to spread over the SMs (decoder steps).
+__global__ void __launch_bounds__(256) small_down_kernel(const uint16_t* __restrict__ x, long long ldx,
+                                                         const uint16_t* __restrict__ W, long long ldw, int K,
+                                                         uint16_t* __restrict__ out, long long ldo, int dtype) {
+  __shared__ float red[8][32];
+  const int m = blockIdx.x;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float acc[32];
+#pragma unroll
+  for (int r = 0; r < 32; ++r) acc[r] = 0.f;
+  for (int k = threadIdx.x * 8; k < K; k += 256 * 8) {
+    const uint4 xv = *reinterpret_cast<const uint4*>(x + static_cast<long long>(m) * ldx + k);
+    const uint32_t xw[4] = {xv.x, xv.y, xv.z, xv.w};
+    float xf[8];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { xf[2 * i] = unpack_lo(xw[i], dtype); xf[2 * i + 1] = unpack_hi(xw[i], dtype); }
+#pragma unroll
+    for (int r = 0; r < 32; ++r) {
+      const uint4 wv = *reinterpret_cast<const uint4*>(W + static_cast<long long>(r) * ldw + k);
+      const uint32_t ww[4] = {wv.x, wv.y, wv.z, wv.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i) acc[r] += xf[2 * i] * unpack_lo(ww[i], dtype) + xf[2 * i + 1] * unpack_hi(ww[i], dtype);
     }
   }
 #pragma unroll
-  for (int r = 0; r < 8; ++r) red[my][cx][r] = acc[r];
+  for (int r = 0; r < 32; ++r) {
+    const float v = warp_sum(acc[r]);
+    if (lane == 0) red[warp][r] = v;
+  }
   __syncthreads();
-  if (my == 0 && c < C) {
+  if (threadIdx.x < 32) {
+    float v = 0.f;
 #pragma unroll
-    for (int r = 0; r < 8; ++r) {
-      const float s = red[0][cx][r] + red[1][cx][r] + red[2][cx][r] + red[3][cx][r];
-      if (transposed_out) atomicAdd(out + static_cast<long long>(r) * C + c, s);
-      else atomicAdd(out + static_cast<long long>(c) * 8 + r, s);
-    }
+    for (int w = 0; w < 8; ++w) v += red[w][threadIdx.x];
+    out[static_cast<long long>(m) * ldo + threadIdx.x] = static_cast<uint16_t>(pack2(v, 0.f, dtype) & 0xffff);
   }
 }
 
@@ -529,11 +588,12 @@ extern "C" int mrb_gated_gelu_fwd(const void* ab, void* h, int M, int F, long lo
   MRB_CHECK_LAUNCH();
   return MRB_OK;
 }
-extern "C" int mrb_gated_gelu_bwd(const void* ab, const void* dh, long long lddh, void* dab, int M, int F, int dtype, void* stream) {
+extern "C" int mrb_gated_gelu_bwd(const void* ab, const void* dh, long long lddh, void* dab, long long lddab, int M, int F,
+                                  int dtype, void* stream) {
   if (M <= 0) return MRB_OK;
-  if ((F & 7) || (lddh & 7)) return MRB_ERR_ARG;
+  if ((F & 7) || (lddh & 7) || (lddab & 7) || lddab < 2 * F) return MRB_ERR_ARG;
   gated_gelu_bwd_kernel<<<blocks_for(static_cast<long long>(M) * (F >> 3), 256), 256, 0, STREAM>>>(
-      static_cast<const uint4*>(ab), static_cast<const uint4*>(dh), lddh, static_cast<uint4*>(dab), M, F, dtype);
+      static_cast<const uint4*>(ab), static_cast<const uint4*>(dh), lddh, static_cast<uint4*>(dab), lddab, M, F, dtype);
   MRB_CHECK_LAUNCH();
   return MRB_OK;
 }
@@ -592,11 +652,21 @@ extern "C" int mrb_lora_down(void* x_ext, long long ldx, const float* A, int M, 
 extern "C" int mrb_skinny_wgrad(const void* P, long long ldp, const void* Q, long long ldq, int M, int C, float* out,
                                 int transposed_out, int dtype, void* stream) {
   if (M <= 0 || C <= 0) return MRB_OK;
-  if (ldq & 7) return MRB_ERR_ARG;
-  const int rows_per_block = 512;
-  dim3 grid(blocks_for(C, 64), blocks_for(M, rows_per_block));
+  if ((ldq & 7) || (ldp & 7) || (C & 7) || (reinterpret_cast<uintptr_t>(P) & 15) || (reinterpret_cast<uintptr_t>(Q) & 15)) return MRB_ERR_ARG;
+  const int rows_per_block = 128;
+  dim3 grid(blocks_for(C, 256), blocks_for(M, rows_per_block));
   skinny_wgrad_kernel<<<grid, 256, 0, STREAM>>>(static_cast<const uint16_t*>(P), ldp, static_cast<const uint16_t*>(Q), ldq,
                                                 M, C, out, transposed_out, dtype, rows_per_block);
+  MRB_CHECK_LAUNCH();
+  return MRB_OK;
+}
+
+extern "C" int mrb_small_down(const void* x, long long ldx, const void* W, long long ldw, int M, int K, void* out,
+                              long long ldo, int dtype, void* stream) {
+  if (M <= 0) return MRB_OK;
+  if ((K & 7) || (ldx & 7) || (ldw & 7)) return MRB_ERR_ARG;
+  small_down_kernel<<<M, 256, 0, STREAM>>>(static_cast<const uint16_t*>(x), ldx, static_cast<const uint16_t*>(W), ldw, K,
+                                           static_cast<uint16_t*>(out), ldo, dtype);
   MRB_CHECK_LAUNCH();
   return MRB_OK;
 }

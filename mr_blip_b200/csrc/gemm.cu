@@ -6,7 +6,8 @@
 // Blackwell-native structure: persistent CTAs (one per SM), warp-specialised
 //   warp 0     TMA producer   (cp.async.bulk.tensor 2D, SWIZZLE_128B, 64-element K slabs)
 //   warp 1     MMA issuer     (single elected thread, tcgen05.mma cta_group::1 kind::f16, 128 x BN x 16)
-//   warps 2-5  epilogue       (tcgen05.ld 32x32b from TMEM -> bias / GELU / fp32 residual -> global)
+//   warps 2-9  epilogue       (tcgen05.ld 32x32b from TMEM -> bias / GELU / fp32 residual -> global; two warps per
+//                              TMEM lane quadrant, each taking half of the tile's columns)
 // with a STAGES-deep smem ring (full/empty mbarriers) and a double-buffered fp32 accumulator in TMEM
 // (tmem_full/tmem_empty mbarriers) so the epilogue of tile i overlaps the MMAs of tile i+1.
 #include "common.cuh"
@@ -51,7 +52,7 @@ __device__ __forceinline__ void tile_coords(int t, int m_tiles, int n_tiles, int
 }
 
 template <int BN, int STAGES>
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(320, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
   using S = GemmSmem<BN, STAGES>;
   constexpr uint32_t TMEM_COLS = (2 * BN <= 256) ? 256 : 512;
@@ -77,7 +78,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tmem_full[s], 1);
-      mbar_init(&tmem_empty[s], 4);
+      mbar_init(&tmem_empty[s], 8);
     }
     fence_barrier_init();
   }
@@ -136,17 +137,18 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       }
     }
   } else {
-    // ===================== epilogue warps =====================
+    // ===================== epilogue warps (8): warps 2-5 take the low half of the tile's columns, 6-9 the high half
     const int quad = warp & 3;                 // TMEM lane quadrant this warp may read
+    const int eg = (warp - 2) >> 2;            // column half
     const int row_in_tile = quad * 32 + lane;
+    constexpr int HALF = (BN >= 64) ? BN / 2 : BN;          // BN = 32: only the first group has columns
+    const int c_begin = eg * HALF, c_end = (BN >= 64) ? c_begin + HALF : (eg == 0 ? BN : 0);
     int it = 0;
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
       int tm, tn;
       tile_coords(t, p.m_tiles, p.n_tiles, tm, tn);
       const int as = it & 1;
       const uint32_t aphase = (it >> 1) & 1;
-      mbar_wait(&tmem_full[as], aphase);
-      tc_fence_after();
       const int m = tm * BM + row_in_tile;
       const bool row_ok = m < p.M;
       long long out_row = m, res_row = m;
@@ -155,37 +157,49 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         out_row = static_cast<long long>(f) * (p.row_group + 1) + 1 + r;
         res_row = 1 + r;
       }
+      const float* rbase = p.resid ? p.resid + res_row * p.ldr : nullptr;
+      // the residual does not depend on the MMA: fetch the first chunk before waiting for the accumulator
+      float4 rr[8];
+      auto load_resid = [&](int c) {
+        const int n0 = tn * BN + c;
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          rr[j] = (rbase && row_ok && c < c_end && n0 + 4 * j < p.N) ? reinterpret_cast<const float4*>(rbase + n0)[j]
+                                                                      : make_float4(0.f, 0.f, 0.f, 0.f);
+      };
+      load_resid(c_begin);
+      mbar_wait(&tmem_full[as], aphase);
+      tc_fence_after();
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + as * BN;
 #pragma unroll 1
-      for (int c = 0; c < BN; c += 32) {
+      for (int c = c_begin; c < c_end; c += 32) {
         const int n0 = tn * BN + c;
         if (n0 >= p.N) break;                  // warp-uniform
         uint32_t r[32];
         tmem_ld_32x32b_x32(t_row + c, r);
         tmem_ld_wait();
-        if (row_ok) {
-          float v[32];
+        float v[32];
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-          const int ncols = min(32, p.N - n0);   // multiple of 8
+        for (int j = 0; j < 8; ++j) {
+          v[4 * j] = __uint_as_float(r[4 * j]) + rr[j].x; v[4 * j + 1] = __uint_as_float(r[4 * j + 1]) + rr[j].y;
+          v[4 * j + 2] = __uint_as_float(r[4 * j + 2]) + rr[j].z; v[4 * j + 3] = __uint_as_float(r[4 * j + 3]) + rr[j].w;
+        }
+        if (p.resid && !p.gelu) load_resid(c + 32);          // next chunk's residual in flight during this chunk's stores
+        const int ncols = min(32, p.N - n0);   // multiple of 8
+        if (row_ok) {
           if (p.bias) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (j < ncols) v[j] += __ldg(p.bias + n0 + j);
-          }
-          if (p.gelu) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
-          }
-          if (p.resid) {
-            const float4* rp = reinterpret_cast<const float4*>(p.resid + res_row * p.ldr + n0);
-#pragma unroll
             for (int j = 0; j < 8; ++j) {
-              if (j * 4 < ncols) {
-                const float4 x = rp[j];
-                v[4 * j] += x.x; v[4 * j + 1] += x.y; v[4 * j + 2] += x.z; v[4 * j + 3] += x.w;
+              if (4 * j < ncols) {
+                const float4 bb = __ldg(reinterpret_cast<const float4*>(p.bias + n0) + j);
+                v[4 * j] += bb.x; v[4 * j + 1] += bb.y; v[4 * j + 2] += bb.z; v[4 * j + 3] += bb.w;
               }
             }
+          }
+          if (p.gelu) {
+            // (gelu and residual are never combined on this path; with gelu the residual registers are zero)
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
           }
           if (p.out_dtype == MRB_DT_F32) {
             float4* op = reinterpret_cast<float4*>(static_cast<float*>(p.out) + out_row * p.ldc + n0);
@@ -268,7 +282,7 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, GemmParam
   p.n_tiles = (p.N + BN - 1) / BN;
   const int tiles = p.m_tiles * p.n_tiles;
   const int grid = tiles < g_num_sms ? tiles : g_num_sms;
-  gemm_tcgen05_kernel<BN, STAGES><<<grid, 192, S::TOTAL, stream>>>(tmA, tmB, p);
+  gemm_tcgen05_kernel<BN, STAGES><<<grid, 320, S::TOTAL, stream>>>(tmA, tmB, p);
   MRB_CHECK_LAUNCH();
   return MRB_OK;
 }
@@ -277,16 +291,20 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, GemmParam
 
 using namespace mrb;
 
-// Pick the N tile: minimise padded columns, prefer the widest tile on ties (fewer A re-reads).
-static int pick_bn(int N) {
-  const int cand[3] = {256, 192, 128};
+// Pick the N tile: minimise (waves over the SMs) x (tile width) x (relative MMA inefficiency of narrow tiles).
+// Narrow tiles win only when the grid would otherwise leave most SMs idle (decoder steps, M <= 128).
+static int pick_bn(int M, int N, int sms) {
+  if (N <= 32) return 32;     // skinny LoRA down-projections: [M,K] x [32,K]^T
+  const int cand[4] = {256, 192, 128, 64};
+  const double eff[4] = {1.0, 1.05, 1.35, 1.8};
+  const long long m_tiles = (M + 127) / 128;
   int best = 256;
-  long long best_cost = -1;
-  for (int i = 0; i < 3; ++i) {
+  double best_cost = -1.0;
+  for (int i = 0; i < 4; ++i) {
     const int bn = cand[i];
-    const long long padded = static_cast<long long>((N + bn - 1) / bn) * bn;
-    // 128-wide tiles run the MMA at the smem-bandwidth limit: charge them 10 %
-    const long long cost = padded * (bn == 128 ? 110 : 100);
+    const long long tiles = m_tiles * ((N + bn - 1) / bn);
+    const double waves = tiles <= sms ? 1.0 : static_cast<double>(tiles) / sms;
+    const double cost = waves * bn * eff[i];
     if (best_cost < 0 || cost < best_cost) { best_cost = cost; best = bn; }
   }
   return best;
@@ -300,12 +318,13 @@ extern "C" int mrb_gemm(const void* A, long long lda, const void* B, long long l
   if ((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(B) | reinterpret_cast<uintptr_t>(out)) & 15) return MRB_ERR_ARG;
   if (out_dtype == MRB_DT_F32 ? (ldc & 3) : (ldc & 7)) return MRB_ERR_ARG;
   if (resid && ((ldr & 3) || (reinterpret_cast<uintptr_t>(resid) & 15))) return MRB_ERR_ARG;
+  if (resid && gelu) return MRB_ERR_UNSUPPORTED;      // no call site combines them (residual is added after a linear)
   if (g_num_sms == 0) {
     int dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
   }
-  const int bn = force_bn ? force_bn : pick_bn(N);
+  const int bn = force_bn ? force_bn : pick_bn(M, N, g_num_sms);
   CUtensorMap tmA, tmB;
   int rc = make_tmap(&tmA, A, dtype, M, K, lda, BM);
   if (rc) return rc;
@@ -323,6 +342,8 @@ extern "C" int mrb_gemm(const void* A, long long lda, const void* B, long long l
     case 256: return launch_gemm<256, 4>(tmA, tmB, p, s);
     case 192: return launch_gemm<192, 5>(tmA, tmB, p, s);
     case 128: return launch_gemm<128, 6>(tmA, tmB, p, s);
+    case 64: return launch_gemm<64, 8>(tmA, tmB, p, s);
+    case 32: return launch_gemm<32, 8>(tmA, tmB, p, s);
     default: return MRB_ERR_ARG;
   }
 }

@@ -67,7 +67,7 @@ def attention_fwd(q, k, v, out, B, H, Lq, Lk, hd, scale, q_strides, k_strides, v
     if kmask is not None:
         _check(kmask, torch.int32)
     tc_ok = (hd == 64 or (64 < hd <= 96 and hd % 8 == 0))
-    use_tc = impl == "tc" or (impl == "auto" and USE_TC_ATTENTION and tc_ok and Lq >= 128)
+    use_tc = impl == "tc" or (impl == "auto" and USE_TC_ATTENTION and tc_ok and (Lq >= 128 or Lk >= 512))
     _lib.call("mrb_attention_fwd_tc" if use_tc else "mrb_attention_fwd", q.data_ptr(), q_strides[0], q_strides[1], k.data_ptr(), k_strides[0], k_strides[1],
               v.data_ptr(), v_strides[0], v_strides[1], out.data_ptr(), o_strides[0], o_strides[1], B, H, Lq, Lk, hd,
               _DT[q.dtype], float(scale), _ptr(bias), bias.shape[1] if bias is not None else 0, bias_zero, _ptr(kmask),
@@ -77,7 +77,7 @@ def attention_fwd(q, k, v, out, B, H, Lq, Lk, hd, scale, q_strides, k_strides, v
 
 def attention_bwd(q, k, v, o, dout, dq, dk, dv, B, H, Lq, Lk, hd, scale, q_strides, k_strides, v_strides, o_strides,
                   do_strides, lse, delta_ws, bias=None, bias_zero=0, kmask=None, causal=False, q_pos0=0, impl="auto"):
-    use_tc = impl == "tc" or (impl == "auto" and USE_TC_ATTENTION and hd == 64 and Lq >= 128 and Lk >= 128)
+    use_tc = impl == "tc" or (impl == "auto" and USE_TC_ATTENTION and hd == 64 and (Lq >= 128 or Lk >= 512))
     _lib.call("mrb_attention_bwd_tc" if use_tc else "mrb_attention_bwd", q.data_ptr(), q_strides[0], q_strides[1], k.data_ptr(), k_strides[0], k_strides[1],
               v.data_ptr(), v_strides[0], v_strides[1], o.data_ptr(), o_strides[0], o_strides[1], dout.data_ptr(),
               do_strides[0], do_strides[1], dq.data_ptr(), dk.data_ptr(), dv.data_ptr(), B, H, Lq, Lk, hd, _DT[q.dtype],
@@ -123,7 +123,8 @@ def gated_gelu_fwd(ab, h, M, F):
 
 
 def gated_gelu_bwd(ab, dh, dab, M, F):
-    _lib.call("mrb_gated_gelu_bwd", ab.data_ptr(), dh.data_ptr(), dh.stride(0), dab.data_ptr(), M, F, _DT[ab.dtype], _stream())
+    _lib.call("mrb_gated_gelu_bwd", ab.data_ptr(), dh.data_ptr(), dh.stride(0), dab.data_ptr(), dab.stride(0), M, F,
+              _DT[ab.dtype], _stream())
 
 
 def gather_rows(idx, emb, frames, out):
@@ -162,6 +163,15 @@ def lora_down(x_ext, A, M, K, R):
 
 def skinny_wgrad(P, ldp, Q, ldq, M, C, out, transposed_out, dtype):
     _lib.call("mrb_skinny_wgrad", P, ldp, Q, ldq, M, C, out.data_ptr(), int(transposed_out), dtype, _stream())
+
+
+def down32(x, W, out, M):
+    """out[:, :32] = x[:M] . W^T for a 32-row 16-bit W: tensor-core GEMM, or the one-block-per-row kernel for tiny M."""
+    if M >= 256:
+        return gemm(x, W, out=out, M=M)
+    _lib.call("mrb_small_down", x.data_ptr(), x.stride(0), W.data_ptr(), W.stride(0), M, x.shape[1], out.data_ptr(),
+              out.stride(0), _DT[x.dtype], _stream())
+    return out
 
 
 def cast_to(x, out):

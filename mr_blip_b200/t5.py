@@ -30,37 +30,40 @@ def _f(t):
 
 
 class LoraGroup:
-    """Linears that share one input (q|k|v, wi_0|wi_1, or a single Linear) packed as one ext GEMM."""
+    """Linears that share one input (q|k|v, wi_0|wi_1, or a single Linear) packed so that forward AND backward are each
+    one skinny "down" GEMM (N = 32) plus one full tcgen05 GEMM:
+        forward : x_ext[:, K:]  = x . A_down^T            ;  y  = x_ext  . [W | sB]^T
+        backward: dy_ext[:, N:] = dy . B_down^T (= dy.sB) ;  dx = dy_ext . [W^T | A^T]^T   (= dy.W + (dy.sB).A)
+    LoRA weight gradients: dB_j = dy_j^T (x A_j^T)  and  dA_j = (dy_j sB_j)^T x  -- both skinny reductions over M."""
 
     def __init__(self, get, names, scale):
         self.names = names
         Ws = [get(n + ".base_layer.weight") for n in names]
-        self.K = Ws[0].shape[1]
+        self.K = K = Ws[0].shape[1]
         self.Ns = [w.shape[0] for w in Ws]
-        self.N = sum(self.Ns)
+        self.N = N = sum(self.Ns)
         self.n = len(names)
-        self.R = 8 * self.n
         self.scale = scale
         self.A_params = [get(n + ".lora_A.default.weight") for n in names]
         self.B_params = [get(n + ".lora_B.default.weight") for n in names]
         assert all(a.shape[0] == 8 for a in self.A_params), "kernels are specialised for LoRA r = 8"
-        K = self.K
-        self.ext = torch.zeros((self.N, K + EXT), dtype=BF, device="cuda")
+        self.offs = [sum(self.Ns[:j]) for j in range(self.n)]
+        self.ext = torch.zeros((N, K + EXT), dtype=BF, device="cuda")          # [W | sB | 0]
         off = 0
         for w in Ws:
             self.ext[off:off + w.shape[0], :K] = w.detach().to("cuda")
             off += w.shape[0]
-        self.ext_t = torch.zeros((K + EXT, self.N), dtype=BF, device="cuda")
-        self.A_cat = torch.zeros((self.R, K), dtype=torch.float32, device="cuda")
-        self.offs = [sum(self.Ns[:j]) for j in range(self.n)]
+        self.ext_b = torch.zeros((K, N + EXT), dtype=BF, device="cuda")        # [W^T | A^T | 0]
+        ops.transpose16(self.ext, self.ext_b, N, K)
+        self.A_down = torch.zeros((EXT, K), dtype=BF, device="cuda")
+        self.B_down = torch.zeros((EXT, N), dtype=BF, device="cuda")
         self.dA = [torch.zeros((8, K), dtype=torch.float32, device="cuda") for _ in names]
         self.dB = [torch.zeros((n_, 8), dtype=torch.float32, device="cuda") for n_ in self.Ns]
-        self._dst, self._src = [], []
+        self._dst = []
         for j in range(self.n):
             o, n_ = self.offs[j], self.Ns[j]
-            self._dst += [self.ext[o:o + n_, K + 8 * j:K + 8 * j + 8], self.ext_t[K + 8 * j:K + 8 * j + 8, o:o + n_],
-                          self.A_cat[8 * j:8 * j + 8]]
-        ops.transpose16(self.ext, self.ext_t, self.N, K + EXT)
+            self._dst += [self.ext[o:o + n_, K + 8 * j:K + 8 * j + 8], self.B_down[8 * j:8 * j + 8, o:o + n_],
+                          self.A_down[8 * j:8 * j + 8], self.ext_b[:, N + 8 * j:N + 8 * j + 8]]
         self.refresh()
 
     def refresh(self):
@@ -69,26 +72,32 @@ class LoraGroup:
             b = self.B_params[j].detach()
             if self.scale != 1.0:
                 b = b * self.scale
-            src += [b, b.t(), self.A_params[j].detach()]
+            a = self.A_params[j].detach()
+            src += [b, b.t(), a, a.t()]
         torch._foreach_copy_(self._dst, src)
 
+    def down(self, x_ext, M):
+        """x_ext[:, K:K+32] = x_ext[:, :K] . A_down^T  (the LoRA down-projections of the Linears in this group)."""
+        ops.down32(x_ext[:, :self.K], self.A_down, x_ext[:, self.K:], M)
+
     def forward(self, x_ext, M, out=None, resid=None, out_dtype=BF):
-        ops.lora_down(x_ext, self.A_cat, M, self.K, self.R)
+        self.down(x_ext, M)
         return ops.gemm(x_ext, self.ext, out=out, resid=resid, out_dtype=out_dtype, M=M)
 
-    def backward(self, dy16, x_ext, M, dx_ext=None):
-        """-> dx_ext [M, K+32] (bf16): columns [0,K) = dy.W (LoRA term NOT yet added), [K, K+R) = dy.B_j.
-        Accumulates dA_j, dB_j."""
-        dx_ext = ops.gemm(dy16, self.ext_t, out=dx_ext, M=M)
-        K = self.K
-        es = dy16.element_size()
+    def backward(self, dy_ext, x_ext, M, out=None, resid=None, out_dtype=BF):
+        """dy_ext [M, N+32] (columns [0,N) filled by the caller), x_ext = the saved forward input [M, K+32].
+        -> dx [M, K] (complete, LoRA term included); accumulates dA_j, dB_j."""
+        K, N = self.K, self.N
+        ops.down32(dy_ext[:, :N], self.B_down, dy_ext[:, N:], M)
+        dx = ops.gemm(dy_ext, self.ext_b, out=out, resid=resid, out_dtype=out_dtype, M=M)
+        es = 2
         for j in range(self.n):
             o, n_ = self.offs[j], self.Ns[j]
-            ops.skinny_wgrad(dy16.data_ptr() + o * es, dy16.stride(0), x_ext.data_ptr() + (K + 8 * j) * es,
+            ops.skinny_wgrad(dy_ext.data_ptr() + o * es, dy_ext.stride(0), x_ext.data_ptr() + (K + 8 * j) * es,
                              x_ext.stride(0), M, n_, self.dB[j], False, ops.BF16)
-            ops.skinny_wgrad(x_ext.data_ptr(), x_ext.stride(0), dx_ext.data_ptr() + (K + 8 * j) * es,
-                             dx_ext.stride(0), M, K, self.dA[j], True, ops.BF16)
-        return dx_ext
+            ops.skinny_wgrad(x_ext.data_ptr(), x_ext.stride(0), dy_ext.data_ptr() + (N + 8 * j) * es,
+                             dy_ext.stride(0), M, K, self.dA[j], True, ops.BF16)
+        return dx
 
     def zero_grads(self):
         for g in self.dA + self.dB:
@@ -196,10 +205,16 @@ class T5Engine:
     def _self_attn(self, qkv, out_ext, B, L, bias, kmask, causal, lse):
         d = self.d
         inner = d.t5_heads * d.d_kv
-        rs = 3 * inner
+        rs = qkv.stride(0)
         ops.attention_fwd(qkv, qkv[:, inner:], qkv[:, 2 * inner:], out_ext, B, d.t5_heads, L, L, d.d_kv, 1.0,
                           (L * rs, rs), (L * rs, rs), (L * rs, rs), (L * out_ext.stride(0), out_ext.stride(0)),
                           bias=bias, bias_zero=L - 1, kmask=kmask, causal=causal, lse=lse)
+
+    def _grad_ext(self, dh, M):
+        """fp32 residual-stream gradient -> 16-bit extended dgrad operand [M, d_model + 32]."""
+        dy = self._ext(M, self.d.d_model)
+        ops.cast2d(dh, dy, M, self.d.d_model)
+        return dy
 
     def _ff(self, L, h, M, save):
         d = self.d
@@ -217,20 +232,18 @@ class T5Engine:
     def _ff_bwd(self, L, s, dh, M):
         """dh (fp32 residual-stream gradient) is updated in place."""
         d = self.d
-        dy = torch.empty((M, d.d_model), dtype=BF, device="cuda")
-        ops.cast_to(dh, dy)
-        dhm = L["wo"].backward(dy, s["ff_hm"], M)
-        ops.lora_up_add(dhm, L["wo"].A_cat, 8, M, d.d_ff)
-        dab = torch.empty_like(s["ff_ab"])
+        dhm = L["wo"].backward(self._grad_ext(dh, M), s["ff_hm"], M)          # [M, d_ff]
+        dab = self._ext(M, 2 * d.d_ff)
         ops.gated_gelu_bwd(s["ff_ab"], dhm, dab, M, d.d_ff)
         dxn = L["wi"].backward(dab, s["ff_xn"], M)
-        ops.rmsnorm_bwd(s["ff_x"], L["ln_ff"], dxn, d.t5_ln_eps, dh, lora_A=L["wi"].A_cat, R=16)
+        ops.rmsnorm_bwd(s["ff_x"], L["ln_ff"], dxn, d.t5_ln_eps, dh)
 
     # ------------------------------------------------------------------ encoder
     def encoder_forward(self, x, kmask, B, L, save=None):
         """x fp32 [B*L, D] inputs_embeds; -> normalised encoder output in an ext bf16 buffer [B*L, D+32]."""
         d = self.d
         M = B * L
+        inner = d.t5_heads * d.d_kv
         bias = self._bias(self.enc_bias, L, L, True)
         h = x
         for li, layer in enumerate(self.enc):
@@ -238,7 +251,8 @@ class T5Engine:
             s = {} if save is not None else None
             xn = self._ext(M, d.d_model)
             ops.norm(h, layer["ln0"], None, d.t5_ln_eps, 1, out_h=xn)
-            qkv = layer["qkv"].forward(xn, M)
+            qkv = self._ext(M, 3 * inner)                    # ext width so that dqkv can share the layout
+            layer["qkv"].forward(xn, M, out=qkv[:, :3 * inner])
             ao = self._ext(M, d.d_model)
             lse = torch.empty((B, d.t5_heads, L), dtype=torch.float32, device="cuda") if save is not None else None
             self._self_attn(qkv, ao, B, L, bias, kmask, False, lse)
@@ -263,19 +277,17 @@ class T5Engine:
         ws = torch.empty((B * d.t5_heads * L,), dtype=torch.float32, device="cuda")
         for layer, s in zip(reversed(self.enc), reversed(saves)):
             self._ff_bwd(layer, s, dh, M)
-            dy = torch.empty((M, d.d_model), dtype=BF, device="cuda")
-            ops.cast_to(dh, dy)
-            dao = layer["o"].backward(dy, s["ao"], M)
-            ops.lora_up_add(dao, layer["o"].A_cat, 8, M, d.d_model)
-            qkv, rs = s["qkv"], 3 * inner
+            dao = layer["o"].backward(self._grad_ext(dh, M), s["ao"], M)       # [M, D] = dO of the attention
+            qkv = s["qkv"]
+            rs = qkv.stride(0)
             dqkv = torch.empty_like(qkv)
             st = (L * rs, rs)
-            so = (L * dao.stride(0), dao.stride(0))
             ops.attention_bwd(qkv, qkv[:, inner:], qkv[:, 2 * inner:], s["ao"], dao, dqkv, dqkv[:, inner:],
-                              dqkv[:, 2 * inner:], B, d.t5_heads, L, L, d.d_kv, 1.0, st, st, st, so, so, s["lse"], ws,
+                              dqkv[:, 2 * inner:], B, d.t5_heads, L, L, d.d_kv, 1.0, st, st, st,
+                              (L * s["ao"].stride(0), s["ao"].stride(0)), (L * dao.stride(0), dao.stride(0)), s["lse"], ws,
                               bias=bias, bias_zero=L - 1, kmask=kmask, causal=False)
             dxn = layer["qkv"].backward(dqkv, s["xn"], M)
-            ops.rmsnorm_bwd(s["x"], layer["ln0"], dxn, d.t5_ln_eps, dh, lora_A=layer["qkv"].A_cat, R=24)
+            ops.rmsnorm_bwd(s["x"], layer["ln0"], dxn, d.t5_ln_eps, dh)
             s.clear()
         return dh
 
@@ -292,7 +304,8 @@ class T5Engine:
             s = {} if save is not None else None
             xn = self._ext(M, d.d_model)
             ops.norm(h, layer["ln0"], None, d.t5_ln_eps, 1, out_h=xn)
-            qkv = layer["qkv"].forward(xn, M)
+            qkv = self._ext(M, 3 * inner)
+            layer["qkv"].forward(xn, M, out=qkv[:, :3 * inner])
             ao = self._ext(M, d.d_model)
             lse = torch.empty((B, d.t5_heads, Ld), dtype=torch.float32, device="cuda") if save is not None else None
             self._self_attn(qkv, ao, B, Ld, bias, dmask, True, lse)
@@ -301,13 +314,15 @@ class T5Engine:
             # cross attention
             xn2 = self._ext(M, d.d_model)
             ops.norm(h1, layer["ln1"], None, d.t5_ln_eps, 1, out_h=xn2)
-            cq = layer["cq"].forward(xn2, M)
-            ckv = layer["ckv"].forward(enc_ext, Me)
+            cq = self._ext(M, inner)
+            layer["cq"].forward(xn2, M, out=cq[:, :inner])
+            ckv = self._ext(Me, 2 * inner)
+            layer["ckv"].forward(enc_ext, Me, out=ckv[:, :2 * inner])
             co = self._ext(M, d.d_model)
             lse2 = torch.empty((B, d.t5_heads, Ld), dtype=torch.float32, device="cuda") if save is not None else None
-            ops.attention_fwd(cq, ckv, ckv[:, inner:], co, B, d.t5_heads, Ld, Le, d.d_kv, 1.0, (Ld * inner, inner),
-                              (Le * 2 * inner, 2 * inner), (Le * 2 * inner, 2 * inner), (Ld * co.stride(0), co.stride(0)),
-                              kmask=enc_kmask, lse=lse2)
+            qs, ks = cq.stride(0), ckv.stride(0)
+            ops.attention_fwd(cq, ckv, ckv[:, inner:], co, B, d.t5_heads, Ld, Le, d.d_kv, 1.0, (Ld * qs, qs),
+                              (Le * ks, ks), (Le * ks, ks), (Ld * co.stride(0), co.stride(0)), kmask=enc_kmask, lse=lse2)
             h2 = torch.empty_like(h)
             layer["co"].forward(co, M, out=h2, resid=h1)
             if s is not None:
@@ -319,45 +334,43 @@ class T5Engine:
         ops.norm(h, self.dec_final_ln, None, d.t5_ln_eps, 1, out_h=out)
         return out, h, bias
 
-    def decoder_backward(self, saves, h_last, d_out_ext, dmask, enc_ext, enc_kmask, B, Ld, Le, bias):
-        """d_out_ext: ext bf16 dgrad buffer from lm_head.backward.  -> d(enc normalised output) fp32 [Me, D]."""
+    def decoder_backward(self, saves, h_last, d_out, dmask, enc_ext, enc_kmask, B, Ld, Le, bias):
+        """d_out: gradient w.r.t. the normalised decoder output [M, D] (from lm_head.backward).
+        -> gradient w.r.t. the normalised encoder output, fp32 [Me, D]."""
         d = self.d
         M, Me = B * Ld, B * Le
         inner = d.t5_heads * d.d_kv
         dh = torch.zeros((M, d.d_model), dtype=torch.float32, device="cuda")
-        ops.rmsnorm_bwd(h_last, self.dec_final_ln, d_out_ext, d.t5_ln_eps, dh, lora_A=self.lm_head.A_cat, R=8)
+        ops.rmsnorm_bwd(h_last, self.dec_final_ln, d_out, d.t5_ln_eps, dh)
         d_enc = torch.zeros((Me, d.d_model), dtype=torch.float32, device="cuda")
         ws = torch.empty((B * d.t5_heads * Ld,), dtype=torch.float32, device="cuda")
         for layer, s in zip(reversed(self.dec), reversed(saves)):
             self._ff_bwd(layer, s, dh, M)
             # cross attention
-            dy = torch.empty((M, d.d_model), dtype=BF, device="cuda")
-            ops.cast_to(dh, dy)
-            dco = layer["co"].backward(dy, s["co"], M)
-            ops.lora_up_add(dco, layer["co"].A_cat, 8, M, d.d_model)
+            dco = layer["co"].backward(self._grad_ext(dh, M), s["co"], M)
             cq, ckv = s["cq"], s["ckv"]
             dcq, dckv = torch.empty_like(cq), torch.empty_like(ckv)
-            sq, sk = (Ld * inner, inner), (Le * 2 * inner, 2 * inner)
-            so = (Ld * dco.stride(0), dco.stride(0))
+            qs, ks = cq.stride(0), ckv.stride(0)
             ops.attention_bwd(cq, ckv, ckv[:, inner:], s["co"], dco, dcq, dckv, dckv[:, inner:], B, d.t5_heads, Ld, Le,
-                              d.d_kv, 1.0, sq, sk, sk, so, so, s["lse2"], ws, kmask=enc_kmask)
-            ops.lora_down(enc_ext, layer["ckv"].A_cat, Me, d.d_model, 16)     # recompute this layer's x.A^T columns
-            denc_ext = layer["ckv"].backward(dckv, enc_ext, Me)
-            ops.lora_up_add(denc_ext, layer["ckv"].A_cat, 16, Me, d.d_model, acc=d_enc)
+                              d.d_kv, 1.0, (Ld * qs, qs), (Le * ks, ks), (Le * ks, ks),
+                              (Ld * s["co"].stride(0), s["co"].stride(0)), (Ld * dco.stride(0), dco.stride(0)), s["lse2"], ws,
+                              kmask=enc_kmask)
+            layer["ckv"].down(enc_ext, Me)                   # recompute this layer's x.A^T columns of the shared input
+            layer["ckv"].backward(dckv, enc_ext, Me, out=d_enc, resid=d_enc)     # accumulates over the 24 layers
             dxn2 = layer["cq"].backward(dcq, s["xn2"], M)
-            ops.rmsnorm_bwd(s["x1"], layer["ln1"], dxn2, d.t5_ln_eps, dh, lora_A=layer["cq"].A_cat, R=8)
+            ops.rmsnorm_bwd(s["x1"], layer["ln1"], dxn2, d.t5_ln_eps, dh)
             # self attention
-            ops.cast_to(dh, dy)
-            dao = layer["o"].backward(dy, s["ao"], M)
-            ops.lora_up_add(dao, layer["o"].A_cat, 8, M, d.d_model)
-            qkv, rs = s["qkv"], 3 * inner
+            dao = layer["o"].backward(self._grad_ext(dh, M), s["ao"], M)
+            qkv = s["qkv"]
+            rs = qkv.stride(0)
             dqkv = torch.empty_like(qkv)
-            st, so = (Ld * rs, rs), (Ld * dao.stride(0), dao.stride(0))
+            st = (Ld * rs, rs)
             ops.attention_bwd(qkv, qkv[:, inner:], qkv[:, 2 * inner:], s["ao"], dao, dqkv, dqkv[:, inner:],
-                              dqkv[:, 2 * inner:], B, d.t5_heads, Ld, Ld, d.d_kv, 1.0, st, st, st, so, so, s["lse"], ws,
+                              dqkv[:, 2 * inner:], B, d.t5_heads, Ld, Ld, d.d_kv, 1.0, st, st, st,
+                              (Ld * s["ao"].stride(0), s["ao"].stride(0)), (Ld * dao.stride(0), dao.stride(0)), s["lse"], ws,
                               bias=bias, bias_zero=Ld - 1, kmask=dmask, causal=True)
             dxn = layer["qkv"].backward(dqkv, s["xn"], M)
-            ops.rmsnorm_bwd(s["x"], layer["ln0"], dxn, d.t5_ln_eps, dh, lora_A=layer["qkv"].A_cat, R=24)
+            ops.rmsnorm_bwd(s["x"], layer["ln0"], dxn, d.t5_ln_eps, dh)
             s.clear()
         return d_enc                                         # (dh = grad of the frozen embedding rows: dropped)
 
@@ -386,15 +399,15 @@ class T5Engine:
         flat = labels.reshape(-1).contiguous()
         n_valid = int((flat != -100).sum().item())
         loss = torch.zeros((1,), dtype=torch.float32, device="cuda")
-        dlogits = torch.empty((M, d.vocab), dtype=BF, device="cuda") if backward else None
+        dlogits = self._ext(M, d.vocab) if backward else None
         ops.cross_entropy(logits, flat, None, dlogits, 1.0 / max(n_valid, 1), loss_sum=loss)
         out = {"loss": loss}
         if want_logits:
             out["logits"] = logits.view(B, Ld, d.vocab)
             out["encoder_last_hidden_state"] = enc_ext[:, :D].float().view(B, Le, D)
         if backward:
-            ddec_ext = self.lm_head.backward(dlogits, dec_ext, M)
-            d_enc = self.decoder_backward(dec_saves, dec_h, ddec_ext, dmask, enc_ext, kmask, B, Ld, Le, dec_bias)
+            ddec = self.lm_head.backward(dlogits, dec_ext, M)
+            d_enc = self.decoder_backward(dec_saves, dec_h, ddec, dmask, enc_ext, kmask, B, Ld, Le, dec_bias)
             d_in = self.encoder_backward(enc_saves, enc_h, d_enc, kmask, B, Le, enc_bias)
             out["d_inputs_embeds"] = d_in.view(B, Le, D)
         return out
@@ -413,7 +426,9 @@ class T5Engine:
         inner = d.t5_heads * d.d_kv
         st = {"cross": [], "k": [], "v": [], "B": B, "Le": Le, "beams": beams, "max_len": max_len}
         for layer in self.dec:
-            st["cross"].append(layer["ckv"].forward(enc_ext, B * Le))
+            ckv = self._ext(B * Le, 2 * inner)
+            layer["ckv"].forward(enc_ext, B * Le, out=ckv[:, :2 * inner])
+            st["cross"].append(ckv)
             st["k"].append(torch.zeros((B * beams, max_len, inner), dtype=BF, device="cuda"))
             st["v"].append(torch.zeros((B * beams, max_len, inner), dtype=BF, device="cuda"))
         st["bias"] = self._bias(self.dec_bias, max_len, max_len, False)
@@ -451,8 +466,9 @@ class T5Engine:
             ckv = st["cross"][li]
             co = self._ext(NB, d.d_model)
             Le = st["Le"]
+            ks = ckv.stride(0)
             ops.attention_fwd(cq, ckv, ckv[:, inner:], co, NB, d.t5_heads, 1, Le, d.d_kv, 1.0, (inner, inner),
-                              (Le * 2 * inner, 2 * inner), (Le * 2 * inner, 2 * inner), (co.stride(0), co.stride(0)),
+                              (Le * ks, ks), (Le * ks, ks), (co.stride(0), co.stride(0)),
                               kmask=enc_kmask, kv_div=st["beams"])
             h2 = torch.empty_like(h)
             layer["co"].forward(co, NB, out=h2, resid=h1)

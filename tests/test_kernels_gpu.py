@@ -43,6 +43,9 @@ def _close(got, want, rtol, atol, what=""):
     (514, 1408, 6144, 0),       # ViT fc2, long K
     (64, 32128, 2048, 0),       # lm_head
     (4100, 2048, 2080, 0),      # T5 linear with LoRA-extended K
+    (56, 2048, 2080, 0),        # decoder step: narrow tiles spread over the SMs
+    (56, 2048, 2080, 64),
+    (8132, 32, 2048, 0),        # LoRA down-projection
 ])
 def test_gemm_plain(ops, dtype, M, N, K, bn):
     a = _rand((M, K), dtype, 1.0, 1)
@@ -295,6 +298,12 @@ def test_lora_down_and_wgrad(ops):
     xa = x[:, K + 8:K + 16]
     ops.skinny_wgrad(dy.data_ptr(), dy.stride(0), xa.data_ptr(), x.stride(0), M, N, dB, False, ops.BF16)
     _close(dB, dy.float().t() @ xa.float(), 1e-3, 1e-3, "dB")
+    # small-M down-projection kernel
+    Wd = _rand((32, K), torch.bfloat16, 0.05, 39)
+    xs = x[:56]
+    outd = torch.zeros((56, 32), dtype=torch.bfloat16, device="cuda")
+    ops.down32(xs[:, :K], Wd, outd, 56)
+    _close(outd, xs[:, :K].float() @ Wd.float().t(), 1e-2, 1e-2, "small down")
     dA = torch.zeros((8, K), dtype=torch.float32, device="cuda")
     ops.skinny_wgrad(x.data_ptr(), x.stride(0), dy[:, 8:16].contiguous().data_ptr(), 8, M, K, dA, True, ops.BF16)
     _close(dA, dy[:, 8:16].float().t() @ x[:, :K].float(), 1e-3, 1e-3, "dA")

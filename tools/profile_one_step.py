@@ -1,0 +1,23 @@
+"""One full-size QVH training step between cudaProfilerStart/Stop (for `ncu --profile-from-start off`)."""
+import sys
+
+import torch
+
+sys.path.insert(0, ".")
+from mr_blip_b200.blip2_mr import BLIP2_MR  # noqa: E402
+from mr_blip_b200.dims import FULL, init_state_dict  # noqa: E402
+from oracle import synth  # noqa: E402
+
+sd = init_state_dict(FULL, seed=1234, lora_b_std=0.02, device="cuda")
+model = BLIP2_MR(dims=FULL, state_dict=sd).cuda().train()
+del sd
+samples = synth.make_samples(batch=4, frames=60, query_words=32, seed=100)
+samples["video"] = samples["video"].cuda()
+for _ in range(2):
+    model(samples)["loss"].backward()
+torch.cuda.synchronize()
+torch.cuda.profiler.start()
+model(samples)["loss"].backward()
+torch.cuda.synchronize()
+torch.cuda.profiler.stop()
+print("done")

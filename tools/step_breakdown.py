@@ -29,6 +29,8 @@ def main():
     torch.cuda.synchronize()
     t_wall = time.perf_counter() - t0
     _lib.PROFILE = []
+    from mr_blip_b200 import ops
+    ops.GEMM_PROFILE = []
     # phase markers
     marks = {}
     vit, qf, t5 = model.engines()
@@ -54,6 +56,11 @@ def main():
     e1.record()
     torch.cuda.synchronize()
     prof, _lib.PROFILE = _lib.PROFILE, None
+    gprof, ops.GEMM_PROFILE = ops.GEMM_PROFILE, None
+    shapes = collections.defaultdict(lambda: [0, 0.0])
+    for m, n, k, a, b in gprof:
+        shapes[(m, n, k)][0] += 1
+        shapes[(m, n, k)][1] += a.elapsed_time(b)
     tot = collections.defaultdict(float)
     cnt = collections.Counter()
     for name, a, b in prof:
@@ -62,6 +69,8 @@ def main():
     step_ms = e0.elapsed_time(e1)
     res = {"step_ms_with_events": step_ms, "host_enqueue_ms": t_host * 1e3, "wall_ms_no_events": t_wall * 1e3,
            "phases_ms": {k: a.elapsed_time(b) for k, (a, b) in marks.items()},
+           "gemm_shapes": [{"M": m, "N": n, "K": k, "calls": c, "ms": round(t, 3), "tflops": round(2.0 * m * n * k * c / t / 1e9, 1)}
+                           for (m, n, k), (c, t) in sorted(shapes.items(), key=lambda x: -x[1][1])],
            "ops": {k: {"ms": round(v, 3), "calls": cnt[k]} for k, v in sorted(tot.items(), key=lambda x: -x[1])}}
     print(json.dumps(res, indent=1))
     if len(sys.argv) > 1:
