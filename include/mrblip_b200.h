@@ -36,6 +36,11 @@ int mrb_attention_fwd(const void* q, long long q_bs, long long q_rs, const void*
                       const void* v, long long v_bs, long long v_rs, void* o, long long o_bs, long long o_rs,
                       int B, int H, int Lq, int Lk, int hd, int dtype, float scale, const float* bias, int bias_len,
                       int bias_zero, const int* kmask, int kv_div, int causal, int q_pos0, float* lse, void* stream);
+/* One query row per (batch, head), no bias / mask: the 257th ViT token (257 = 2 x 128 + 1; the two full tiles use the
+ * tcgen05 kernel).  q / o point at that row of batch 0. */
+int mrb_attention_row(const void* q, long long q_bs, const void* k, long long k_bs, long long k_rs, const void* v,
+                      long long v_bs, long long v_rs, void* o, long long o_bs, int B, int H, int Lk, int hd, int dtype,
+                      float scale, void* stream);
 /* Same contract, tcgen05/TMEM/TMA implementation (S and O tiles in tensor memory, K/V by TMA, P through swizzled smem)
  * for the large shapes: hd == 64 (T5) or 64 < hd <= 96 (ViT hd 88, zero-filled to 96 by the tensor map). */
 int mrb_attention_fwd_tc(const void* q, long long q_bs, long long q_rs, const void* k, long long k_bs, long long k_rs,
@@ -99,6 +104,10 @@ int mrb_lora_up_add(void* x_ext, long long ldx, const float* A, int R, int M, in
 int mrb_skinny_wgrad(const void* P, long long ldp, const void* Q, long long ldq, int M, int C, float* out,
                      int transposed_out, int dtype, void* stream);
 
+/* tcgen05 implementation of mrb_skinny_wgrad for large M (both operands read MN-major, split-K over M, fp32 atomics);
+ * Q needs >= 16 readable columns per row. */
+int mrb_skinny_wgrad_tc(const void* P, long long ldp, const void* Q, long long ldq, int M, int C, float* out,
+                        int transposed_out, int dtype, void* stream);
 /* out[m, r] = sum_k x[m,k] W[r,k], r < 32, 16-bit: LoRA down-projection when M is tiny (decoder); larger M use mrb_gemm */
 int mrb_small_down(const void* x, long long ldx, const void* W, long long ldw, int M, int K, void* out, long long ldo,
                    int dtype, void* stream);

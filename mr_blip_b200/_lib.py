@@ -13,6 +13,7 @@ SIGNATURES = {
     "mrb_gemm": [_p, _ll, _p, _ll, _i, _i, _i, _i, _p, _i, _p, _ll, _p, _i, _ll, _i, _i, _p],
     "mrb_attention_fwd": [_p, _ll, _ll, _p, _ll, _ll, _p, _ll, _ll, _p, _ll, _ll, _i, _i, _i, _i, _i, _i, _f, _p, _i, _i,
                           _p, _i, _i, _i, _p, _p],
+    "mrb_attention_row": [_p, _ll, _p, _ll, _ll, _p, _ll, _ll, _p, _ll, _i, _i, _i, _i, _i, _f, _p],
     "mrb_attention_fwd_tc": [_p, _ll, _ll, _p, _ll, _ll, _p, _ll, _ll, _p, _ll, _ll, _i, _i, _i, _i, _i, _i, _f, _p, _i, _i,
                              _p, _i, _i, _i, _p, _p],
     "mrb_attention_bwd": [_p, _ll, _ll, _p, _ll, _ll, _p, _ll, _ll, _p, _ll, _ll, _p, _ll, _ll, _p, _p, _p,
@@ -33,6 +34,7 @@ SIGNATURES = {
     "mrb_cross_entropy": [_p, _p, _i, _i, _p, _p, _i, _ll, _f, _p, _p],
     "mrb_lora_down": [_p, _ll, _p, _i, _i, _i, _i, _p],
     "mrb_skinny_wgrad": [_p, _ll, _p, _ll, _i, _i, _p, _i, _i, _p],
+    "mrb_skinny_wgrad_tc": [_p, _ll, _p, _ll, _i, _i, _p, _i, _i, _p],
     "mrb_small_down": [_p, _ll, _p, _ll, _i, _i, _p, _ll, _i, _p],
     "mrb_cast_f32_to_h": [_p, _p, _ll, _i, _p],
     "mrb_cast2d_f32_to_h": [_p, _ll, _p, _ll, _i, _i, _i, _p],

@@ -503,6 +503,68 @@ __global__ void __launch_bounds__(NTHREADS) attn_bwd_dkv_kernel(const AttnParams
   }
 }
 
+// Single-query-row attention (the 257th ViT token: 257 = 2 x 128 + 1, the two full tiles go through the tcgen05 kernel).
+// One warp per (batch, head); lane l owns head-dim elements [4l, 4l+4).  No bias / mask.
+template <typename T>
+__global__ void __launch_bounds__(128) attn_row_kernel(const T* __restrict__ q, long long q_bs, const T* __restrict__ k,
+                                                       long long k_bs, long long k_rs, const T* __restrict__ v, long long v_bs,
+                                                       long long v_rs, T* __restrict__ o, long long o_bs, int B, int H, int Lk,
+                                                       int hd, float scale) {
+  extern __shared__ float sp[];                       // [4 warps][Lk] scores / probabilities
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int bh = blockIdx.x * 4 + warp;
+  if (bh >= B * H) return;
+  const int b = bh / H, h = bh % H;
+  float* p = sp + warp * Lk;
+  const bool act = lane * 4 < hd;
+  const int d0 = lane * 4;
+  float qv[4] = {0.f, 0.f, 0.f, 0.f};
+  if (act) {
+    const uint2 w = *reinterpret_cast<const uint2*>(q + b * q_bs + h * hd + d0);
+    const T* e = reinterpret_cast<const T*>(&w);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) qv[i] = to_f32(e[i]) * scale;
+  }
+  const T* kb = k + b * k_bs + h * hd + d0;
+  float mx = -INFINITY;
+  for (int j = 0; j < Lk; ++j) {
+    float s = 0.f;
+    if (act) {
+      const uint2 w = *reinterpret_cast<const uint2*>(kb + static_cast<long long>(j) * k_rs);
+      const T* e = reinterpret_cast<const T*>(&w);
+      s = qv[0] * to_f32(e[0]) + qv[1] * to_f32(e[1]) + qv[2] * to_f32(e[2]) + qv[3] * to_f32(e[3]);
+    }
+    s = warp_sum(s);
+    if (lane == 0) p[j] = s;
+    mx = fmaxf(mx, s);
+  }
+  __syncwarp();
+  float sum = 0.f;
+  for (int j = lane; j < Lk; j += 32) {
+    const float e = __expf(p[j] - mx);
+    p[j] = e;
+    sum += e;
+  }
+  sum = warp_sum(sum);
+  __syncwarp();
+  const T* vb = v + b * v_bs + h * hd + d0;
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  if (act) {
+    for (int j = 0; j < Lk; ++j) {
+      const uint2 w = *reinterpret_cast<const uint2*>(vb + static_cast<long long>(j) * v_rs);
+      const T* e = reinterpret_cast<const T*>(&w);
+      const float pj = p[j];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) acc[i] = fmaf(pj, to_f32(e[i]), acc[i]);
+    }
+    const float inv = 1.f / sum;
+    T r[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) r[i] = from_f32<T>(acc[i] * inv);
+    *reinterpret_cast<uint2*>(o + b * o_bs + h * hd + d0) = *reinterpret_cast<const uint2*>(r);
+  }
+}
+
 template <typename K>
 static int set_smem(K kernel, int bytes) {
   cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
@@ -594,4 +656,23 @@ extern "C" int mrb_attention_bwd(const void* q, long long q_bs, long long q_rs, 
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (dtype == MRB_DT_F16) return launch_bwd<__half, 64>(p, s);
   return launch_bwd<__nv_bfloat16, 64>(p, s);
+}
+
+// One query row per (batch, head): q/o point at that row of batch 0 (batch strides apply).  No bias / mask.
+extern "C" int mrb_attention_row(const void* q, long long q_bs, const void* k, long long k_bs, long long k_rs, const void* v,
+                                 long long v_bs, long long v_rs, void* o, long long o_bs, int B, int H, int Lk, int hd,
+                                 int dtype, float scale, void* stream) {
+  if (B <= 0 || H <= 0 || Lk <= 0) return MRB_OK;
+  if ((hd & 3) || hd > 128 || Lk > 4096 || ((q_bs | k_bs | k_rs | v_bs | v_rs | o_bs) & 3)) return MRB_ERR_ARG;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int blocks = (B * H + 3) / 4, smem = 4 * Lk * 4;
+  if (dtype == MRB_DT_F16)
+    attn_row_kernel<__half><<<blocks, 128, smem, s>>>(static_cast<const __half*>(q), q_bs, static_cast<const __half*>(k), k_bs, k_rs,
+                                                     static_cast<const __half*>(v), v_bs, v_rs, static_cast<__half*>(o), o_bs, B, H, Lk, hd, scale);
+  else if (dtype == MRB_DT_BF16)
+    attn_row_kernel<__nv_bfloat16><<<blocks, 128, smem, s>>>(static_cast<const __nv_bfloat16*>(q), q_bs, static_cast<const __nv_bfloat16*>(k), k_bs, k_rs,
+                                                            static_cast<const __nv_bfloat16*>(v), v_bs, v_rs, static_cast<__nv_bfloat16*>(o), o_bs, B, H, Lk, hd, scale);
+  else return MRB_ERR_ARG;
+  MRB_CHECK_LAUNCH();
+  return MRB_OK;
 }

@@ -434,6 +434,24 @@ __global__ void __launch_bounds__(256) skinny_wgrad_kernel(const uint16_t* __res
   }
 }
 
+// small-M variant (decoder steps): every output element is owned by one thread, no atomics.  out += P^T Q.
+__global__ void __launch_bounds__(256) skinny_wgrad_small_kernel(const uint16_t* __restrict__ P, long long ldp,
+                                                                 const uint16_t* __restrict__ Q, long long ldq, int M, int C,
+                                                                 float* __restrict__ out, int transposed_out, int dtype) {
+  const int r = threadIdx.x & 7;
+  const int c = blockIdx.x * 32 + (threadIdx.x >> 3);
+  if (c >= C) return;
+  float acc = 0.f;
+  for (int m = 0; m < M; ++m) {
+    const uint16_t pw = P[static_cast<long long>(m) * ldp + c], qw = Q[static_cast<long long>(m) * ldq + r];
+    const float pv = (dtype == MRB_DT_F16) ? __half2float(__ushort_as_half(pw)) : __uint_as_float(static_cast<uint32_t>(pw) << 16);
+    const float qv = (dtype == MRB_DT_F16) ? __half2float(__ushort_as_half(qw)) : __uint_as_float(static_cast<uint32_t>(qw) << 16);
+    acc = fmaf(pv, qv, acc);
+  }
+  if (transposed_out) out[static_cast<long long>(r) * C + c] += acc;
+  else out[static_cast<long long>(c) * 8 + r] += acc;
+}
+
 // ---------------------------------------------------------------- LoRA down-projection for small M
 // out[m, r] = sum_k x[m, k] * W[r, k], r < 32 (16-bit x / W / out): one block per row.  Used when M is too small for the
 // tensor-core path to spread over the SMs (decoder steps).
@@ -653,7 +671,14 @@ extern "C" int mrb_skinny_wgrad(const void* P, long long ldp, const void* Q, lon
                                 int transposed_out, int dtype, void* stream) {
   if (M <= 0 || C <= 0) return MRB_OK;
   if ((ldq & 7) || (ldp & 7) || (C & 7) || (reinterpret_cast<uintptr_t>(P) & 15) || (reinterpret_cast<uintptr_t>(Q) & 15)) return MRB_ERR_ARG;
-  const int rows_per_block = 128;
+  if (M <= 256) {
+    skinny_wgrad_small_kernel<<<blocks_for(C, 32), 256, 0, STREAM>>>(static_cast<const uint16_t*>(P), ldp,
+                                                                    static_cast<const uint16_t*>(Q), ldq, M, C, out,
+                                                                    transposed_out, dtype);
+    MRB_CHECK_LAUNCH();
+    return MRB_OK;
+  }
+  const int rows_per_block = 256;
   dim3 grid(blocks_for(C, 256), blocks_for(M, rows_per_block));
   skinny_wgrad_kernel<<<grid, 256, 0, STREAM>>>(static_cast<const uint16_t*>(P), ldp, static_cast<const uint16_t*>(Q), ldq,
                                                 M, C, out, transposed_out, dtype, rows_per_block);

@@ -75,6 +75,12 @@ def attention_fwd(q, k, v, out, B, H, Lq, Lk, hd, scale, q_strides, k_strides, v
     return out
 
 
+def attention_row(q, k, v, out, B, H, Lk, hd, scale, q_bs, k_strides, v_strides, o_bs):
+    """One query row per (batch, head): q/out data_ptr = that row of batch 0."""
+    _lib.call("mrb_attention_row", q.data_ptr(), q_bs, k.data_ptr(), k_strides[0], k_strides[1], v.data_ptr(), v_strides[0],
+              v_strides[1], out.data_ptr(), o_bs, B, H, Lk, hd, _DT[q.dtype], float(scale), _stream())
+
+
 def attention_bwd(q, k, v, o, dout, dq, dk, dv, B, H, Lq, Lk, hd, scale, q_strides, k_strides, v_strides, o_strides,
                   do_strides, lse, delta_ws, bias=None, bias_zero=0, kmask=None, causal=False, q_pos0=0, impl="auto"):
     use_tc = impl == "tc" or (impl == "auto" and USE_TC_ATTENTION and hd == 64 and (Lq >= 128 or Lk >= 512))
@@ -161,8 +167,10 @@ def lora_down(x_ext, A, M, K, R):
     _lib.call("mrb_lora_down", x_ext.data_ptr(), x_ext.stride(0), A.data_ptr(), M, K, R, _DT[x_ext.dtype], _stream())
 
 
-def skinny_wgrad(P, ldp, Q, ldq, M, C, out, transposed_out, dtype):
-    _lib.call("mrb_skinny_wgrad", P, ldp, Q, ldq, M, C, out.data_ptr(), int(transposed_out), dtype, _stream())
+def skinny_wgrad(P, ldp, Q, ldq, M, C, out, transposed_out, dtype, impl="auto"):
+    """out (+)= P[M,C]^T . Q[M,8]; tensor-core kernel for large M (Q then needs 16 readable columns), CUDA-core otherwise."""
+    tc = impl == "tc" or (impl == "auto" and M >= 1024)
+    _lib.call("mrb_skinny_wgrad_tc" if tc else "mrb_skinny_wgrad", P, ldp, Q, ldq, M, C, out.data_ptr(), int(transposed_out), dtype, _stream())
 
 
 def down32(x, W, out, M):

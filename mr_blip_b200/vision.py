@@ -72,7 +72,10 @@ class VitEngine:
             if Tq:
                 ops.attention_fwd(qkv, qkv[:, W:], qkv[:, 2 * W:], ao, F_, Hh, Tq, T, hd, hd ** -0.5,
                                   (T * rs, rs), (T * rs, rs), (T * rs, rs), (T * W, W), impl="tc")
-            if Tq < T:
+            if Tq == T - 1:
+                ops.attention_row(qkv[Tq:], qkv[:, W:], qkv[:, 2 * W:], ao[Tq:], F_, Hh, T, hd, hd ** -0.5,
+                                  T * rs, (T * rs, rs), (T * rs, rs), T * W)
+            elif Tq < T:
                 ops.attention_fwd(qkv[Tq:], qkv[:, W:], qkv[:, 2 * W:], ao[Tq:], F_, Hh, T - Tq, T, hd, hd ** -0.5,
                                   (T * rs, rs), (T * rs, rs), (T * rs, rs), (T * W, W), impl="mma")
             ops.gemm(ao, blk["proj_w"], out=x, bias=blk["proj_b"], resid=x)

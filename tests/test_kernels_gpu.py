@@ -124,6 +124,18 @@ def test_attention_fwd_fused_qkv_layout(ops, B, H, L, hd, dtype, impl):
     _close(out, want, tol, tol, "attention fwd")
 
 
+def test_attention_single_row(ops):
+    B, H, L, hd = 5, 16, 257, 88
+    qkv = _rand((B, L, 3, H, hd), torch.float16, 1.0, 42)
+    out = torch.zeros((B, L, H, hd), dtype=torch.float16, device="cuda")
+    rs = 3 * H * hd
+    ops.attention_row(qkv[:, L - 1, 0], qkv[:, :, 1], qkv[:, :, 2], out[:, L - 1], B, H, L, hd, hd ** -0.5,
+                      L * rs, (L * rs, rs), (L * rs, rs), L * H * hd)
+    want, _ = _attn_ref(qkv[:, :, 0], qkv[:, :, 1], qkv[:, :, 2], hd ** -0.5)
+    _close(out[:, L - 1], want[:, L - 1], 4e-3, 4e-3, "single row")
+    assert out[:, :L - 1].abs().max().item() == 0
+
+
 def test_attention_cross_small_q(ops):
     B, H, Lq, Lk, hd = 5, 12, 32, 257, 64
     q = _rand((B, Lq, H, hd), torch.float16, 1.0, 13)
@@ -296,8 +308,13 @@ def test_lora_down_and_wgrad(ops):
     dy = _rand((M, N), torch.bfloat16, 1.0, 36)
     dB = torch.zeros((N, 8), dtype=torch.float32, device="cuda")
     xa = x[:, K + 8:K + 16]
-    ops.skinny_wgrad(dy.data_ptr(), dy.stride(0), xa.data_ptr(), x.stride(0), M, N, dB, False, ops.BF16)
+    ops.skinny_wgrad(dy.data_ptr(), dy.stride(0), xa.data_ptr(), x.stride(0), M, N, dB, False, ops.BF16, impl="cc")
     _close(dB, dy.float().t() @ xa.float(), 1e-3, 1e-3, "dB")
+    for tr in (False, True):                                  # tensor-core variant, ragged M and C, both output layouts
+        o = torch.zeros((8, N) if tr else (N, 8), dtype=torch.float32, device="cuda")
+        ops.skinny_wgrad(dy.data_ptr(), dy.stride(0), xa.data_ptr(), x.stride(0), M, N, o, tr, ops.BF16, impl="tc")
+        want = dy.float().t() @ xa.float()
+        _close(o.t() if tr else o, want, 2e-3, 2e-3, "dB tc")
     # small-M down-projection kernel
     Wd = _rand((32, K), torch.bfloat16, 0.05, 39)
     xs = x[:56]
@@ -305,7 +322,7 @@ def test_lora_down_and_wgrad(ops):
     ops.down32(xs[:, :K], Wd, outd, 56)
     _close(outd, xs[:, :K].float() @ Wd.float().t(), 1e-2, 1e-2, "small down")
     dA = torch.zeros((8, K), dtype=torch.float32, device="cuda")
-    ops.skinny_wgrad(x.data_ptr(), x.stride(0), dy[:, 8:16].contiguous().data_ptr(), 8, M, K, dA, True, ops.BF16)
+    ops.skinny_wgrad(x.data_ptr(), x.stride(0), dy[:, 8:16].contiguous().data_ptr(), 8, M, K, dA, True, ops.BF16, impl="cc")
     _close(dA, dy[:, 8:16].float().t() @ x[:, :K].float(), 1e-3, 1e-3, "dA")
 
 
