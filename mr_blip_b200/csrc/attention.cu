@@ -525,19 +525,24 @@ __global__ void __launch_bounds__(128) attn_row_kernel(const T* __restrict__ q, 
 #pragma unroll
     for (int i = 0; i < 4; ++i) qv[i] = to_f32(e[i]) * scale;
   }
-  const T* kb = k + b * k_bs + h * hd + d0;
+  // scores: lane = key; the query row is broadcast from shared memory
+  float* sq = sp + 4 * Lk + warp * 128;
+  if (act) { sq[d0] = qv[0]; sq[d0 + 1] = qv[1]; sq[d0 + 2] = qv[2]; sq[d0 + 3] = qv[3]; }
+  __syncwarp();
   float mx = -INFINITY;
-  for (int j = 0; j < Lk; ++j) {
+  for (int j = lane; j < Lk; j += 32) {
+    const T* kr = k + b * k_bs + static_cast<long long>(j) * k_rs + h * hd;
     float s = 0.f;
-    if (act) {
-      const uint2 w = *reinterpret_cast<const uint2*>(kb + static_cast<long long>(j) * k_rs);
+    for (int d = 0; d < hd; d += 8) {
+      const uint4 w = *reinterpret_cast<const uint4*>(kr + d);
       const T* e = reinterpret_cast<const T*>(&w);
-      s = qv[0] * to_f32(e[0]) + qv[1] * to_f32(e[1]) + qv[2] * to_f32(e[2]) + qv[3] * to_f32(e[3]);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) s = fmaf(sq[d + i], to_f32(e[i]), s);
     }
-    s = warp_sum(s);
-    if (lane == 0) p[j] = s;
+    p[j] = s;
     mx = fmaxf(mx, s);
   }
+  mx = warp_max(mx);
   __syncwarp();
   float sum = 0.f;
   for (int j = lane; j < Lk; j += 32) {
@@ -550,6 +555,7 @@ __global__ void __launch_bounds__(128) attn_row_kernel(const T* __restrict__ q, 
   const T* vb = v + b * v_bs + h * hd + d0;
   float acc[4] = {0.f, 0.f, 0.f, 0.f};
   if (act) {
+#pragma unroll 8
     for (int j = 0; j < Lk; ++j) {
       const uint2 w = *reinterpret_cast<const uint2*>(vb + static_cast<long long>(j) * v_rs);
       const T* e = reinterpret_cast<const T*>(&w);
@@ -663,9 +669,9 @@ extern "C" int mrb_attention_row(const void* q, long long q_bs, const void* k, l
                                  long long v_bs, long long v_rs, void* o, long long o_bs, int B, int H, int Lk, int hd,
                                  int dtype, float scale, void* stream) {
   if (B <= 0 || H <= 0 || Lk <= 0) return MRB_OK;
-  if ((hd & 3) || hd > 128 || Lk > 4096 || ((q_bs | k_bs | k_rs | v_bs | v_rs | o_bs) & 3)) return MRB_ERR_ARG;
+  if ((hd & 7) || hd > 128 || Lk > 4096 || ((q_bs | k_bs | k_rs | v_bs | v_rs | o_bs) & 3)) return MRB_ERR_ARG;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  const int blocks = (B * H + 3) / 4, smem = 4 * Lk * 4;
+  const int blocks = (B * H + 3) / 4, smem = 4 * Lk * 4 + 4 * 128 * 4;
   if (dtype == MRB_DT_F16)
     attn_row_kernel<__half><<<blocks, 128, smem, s>>>(static_cast<const __half*>(q), q_bs, static_cast<const __half*>(k), k_bs, k_rs,
                                                      static_cast<const __half*>(v), v_bs, v_rs, static_cast<__half*>(o), o_bs, B, H, Lk, hd, scale);
