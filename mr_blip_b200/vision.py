@@ -124,6 +124,7 @@ class QFormerEngine:
         self.n_cross = len(kv_w)
         self.proj_w16 = None
         self.proj_b = None
+        self.xattn_events = None     # set to a list to time the cross-attention path (K/V projection GEMM + attention cores)
 
     def set_t5_proj(self, weight, bias):
         """t5_proj is trainable (blip2_mr.py:291 only sets an attribute on the Module): refresh per step."""
@@ -147,7 +148,12 @@ class QFormerEngine:
         ie16 = torch.empty((frames * T, d.vit_width), dtype=H16, device="cuda")
         ie32 = torch.empty((frames * T, d.vit_width), dtype=torch.float32, device="cuda") if return_all else None
         ops.norm(vit_out, self.lnv_w, self.lnv_b, 1e-5, 0, out_h=ie16, out_f32=ie32)
+        ev = self.xattn_events
+        if ev is not None:
+            e0 = torch.cuda.Event(enable_timing=True); e0.record()
         kv = ops.gemm(ie16, self.kv_w, bias=self.kv_b)                     # [F*257, n_cross*1536] fp16
+        if ev is not None:
+            e1 = torch.cuda.Event(enable_timing=True); e1.record(); ev.append((e0, e1))
         kv_rs = self.n_cross * 2 * Hq
         # BertEmbeddings on the query tokens is frame independent (Qformer.py:104-108): LN once, broadcast
         q0 = torch.empty((nq, Hq), dtype=torch.float32, device="cuda")
@@ -170,8 +176,12 @@ class QFormerEngine:
             if c is not None:
                 ops.gemm(h16, c["q"][0], out=qc, bias=c["q"][1])
                 kbase = kv[:, c["idx"] * 2 * Hq:]
+                if ev is not None:
+                    e0 = torch.cuda.Event(enable_timing=True); e0.record()
                 ops.attention_fwd(qc, kbase, kbase[:, Hq:], ctx, frames, heads, nq, T, hd, hd ** -0.5,
                                   (nq * Hq, Hq), (T * kv_rs, kv_rs), (T * kv_rs, kv_rs), (nq * Hq, Hq))
+                if ev is not None:
+                    e1 = torch.cuda.Event(enable_timing=True); e1.record(); ev.append((e0, e1))
                 self._attn_block(ctx, c["o"], c["ln"], h, h16, M)
             ops.gemm(h16, L["ffn_i"][0], out=inter, bias=L["ffn_i"][1], gelu=True)
             self._attn_block(inter, L["ffn_o"], L["ffn_ln"], h, h16, M)
