@@ -11,6 +11,7 @@
 // with a STAGES-deep smem ring (full/empty mbarriers) and a double-buffered fp32 accumulator in TMEM
 // (tmem_full/tmem_empty mbarriers) so the epilogue of tile i overlaps the MMAs of tile i+1.
 #include "common.cuh"
+#include <stdlib.h>
 
 namespace mrb {
 
@@ -26,6 +27,7 @@ struct GemmParams {
   void* out;
   int out_dtype;        // MRB_DT_*
   long long ldc;
+  int epi_direct;       // 16-bit outputs: row-per-thread stores instead of the staged (coalesced) epilogue
   int row_group;        // G > 0: patch-embed row remap  out_row = (m/G)*(G+1)+1+m%G, resid_row = 1+m%G
 };
 
@@ -38,7 +40,8 @@ struct GemmSmem {
   static constexpr int A_BYTES = BM * BK * 2;
   static constexpr int B_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int BAR_OFFSET = STAGES * STAGE_BYTES;
+  static constexpr int EPI_OFFSET = STAGES * STAGE_BYTES;                   // 8 warps x [32 rows][32 fp32], XOR-swizzled
+  static constexpr int BAR_OFFSET = EPI_OFFSET + 8 * 4096;
   static constexpr int TOTAL = BAR_OFFSET + (2 * STAGES + 4) * 8 + 16 + 1024;  // + alignment slack
 };
 
@@ -57,7 +60,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   using S = GemmSmem<BN, STAGES>;
   constexpr uint32_t TMEM_COLS = (2 * BN <= 256) ? 256 : 512;
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + S::BAR_OFFSET);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tmem_full = empty_bar + STAGES;
@@ -137,37 +140,23 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       }
     }
   } else {
-    // ===================== epilogue warps (8): warps 2-5 take the low half of the tile's columns, 6-9 the high half
+    // ===================== epilogue warps (8): warps 2-5 take the low half of the tile's columns, 6-9 the high half.
+    // Each 32 x 32 fp32 chunk goes TMEM -> registers (row per thread: bias, GELU) -> XOR-swizzled shared staging ->
+    // registers (4 rows x 128 B per warp instruction) so that the residual reads and the output writes are coalesced.
     const int quad = warp & 3;                 // TMEM lane quadrant this warp may read
     const int eg = (warp - 2) >> 2;            // column half
-    const int row_in_tile = quad * 32 + lane;
     constexpr int HALF = (BN >= 64) ? BN / 2 : BN;          // BN = 32: only the first group has columns
     const int c_begin = eg * HALF, c_end = (BN >= 64) ? c_begin + HALF : (eg == 0 ? BN : 0);
+    float4* stage4 = reinterpret_cast<float4*>(smem + S::EPI_OFFSET + (warp - 2) * 4096);
+    const int sub_row = lane >> 3, chunk = lane & 7;        // transposed phase: lane -> (row within group of 4, 16-byte chunk)
+    const bool direct16 = p.epi_direct && (p.out_dtype != MRB_DT_F32) && (p.resid == nullptr) && (p.row_group == 0);
     int it = 0;
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
       int tm, tn;
       tile_coords(t, p.m_tiles, p.n_tiles, tm, tn);
       const int as = it & 1;
       const uint32_t aphase = (it >> 1) & 1;
-      const int m = tm * BM + row_in_tile;
-      const bool row_ok = m < p.M;
-      long long out_row = m, res_row = m;
-      if (p.row_group > 0) {
-        const int f = m / p.row_group, r = m - f * p.row_group;
-        out_row = static_cast<long long>(f) * (p.row_group + 1) + 1 + r;
-        res_row = 1 + r;
-      }
-      const float* rbase = p.resid ? p.resid + res_row * p.ldr : nullptr;
-      // the residual does not depend on the MMA: fetch the first chunk before waiting for the accumulator
-      float4 rr[8];
-      auto load_resid = [&](int c) {
-        const int n0 = tn * BN + c;
-#pragma unroll
-        for (int j = 0; j < 8; ++j)
-          rr[j] = (rbase && row_ok && c < c_end && n0 + 4 * j < p.N) ? reinterpret_cast<const float4*>(rbase + n0)[j]
-                                                                      : make_float4(0.f, 0.f, 0.f, 0.f);
-      };
-      load_resid(c_begin);
+      const int m_base = tm * BM + quad * 32;
       mbar_wait(&tmem_full[as], aphase);
       tc_fence_after();
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + as * BN;
@@ -175,39 +164,32 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       for (int c = c_begin; c < c_end; c += 32) {
         const int n0 = tn * BN + c;
         if (n0 >= p.N) break;                  // warp-uniform
-        uint32_t r[32];
-        tmem_ld_32x32b_x32(t_row + c, r);
-        tmem_ld_wait();
-        float v[32];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          v[4 * j] = __uint_as_float(r[4 * j]) + rr[j].x; v[4 * j + 1] = __uint_as_float(r[4 * j + 1]) + rr[j].y;
-          v[4 * j + 2] = __uint_as_float(r[4 * j + 2]) + rr[j].z; v[4 * j + 3] = __uint_as_float(r[4 * j + 3]) + rr[j].w;
-        }
-        if (p.resid && !p.gelu) load_resid(c + 32);          // next chunk's residual in flight during this chunk's stores
         const int ncols = min(32, p.N - n0);   // multiple of 8
-        if (row_ok) {
-          if (p.bias) {
+        if (direct16) {
+          // ---- 16-bit output without residual: row-per-thread stores (64 B per thread and chunk); cheapest in instructions,
+          //      which is what bounds the bias / GELU epilogues of the short-K ViT GEMMs
+          uint32_t r[32];
+          tmem_ld_32x32b_x32(t_row + c, r);
+          tmem_ld_wait();
+          const int m = m_base + lane;
+          if (m < p.M) {
+            float v[32];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              if (4 * j < ncols) {
-                const float4 bb = __ldg(reinterpret_cast<const float4*>(p.bias + n0) + j);
-                v[4 * j] += bb.x; v[4 * j + 1] += bb.y; v[4 * j + 2] += bb.z; v[4 * j + 3] += bb.w;
+            for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+            if (p.bias) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                if (4 * j < ncols) {
+                  const float4 bb = __ldg(reinterpret_cast<const float4*>(p.bias + n0) + j);
+                  v[4 * j] += bb.x; v[4 * j + 1] += bb.y; v[4 * j + 2] += bb.z; v[4 * j + 3] += bb.w;
+                }
               }
             }
-          }
-          if (p.gelu) {
-            // (gelu and residual are never combined on this path; with gelu the residual registers are zero)
+            if (p.gelu) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
-          }
-          if (p.out_dtype == MRB_DT_F32) {
-            float4* op = reinterpret_cast<float4*>(static_cast<float*>(p.out) + out_row * p.ldc + n0);
-#pragma unroll
-            for (int j = 0; j < 8; ++j)
-              if (j * 4 < ncols) op[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-          } else {
-            uint4* op = reinterpret_cast<uint4*>(static_cast<uint16_t*>(p.out) + out_row * p.ldc + n0);
+              for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
+            }
+            uint4* op = reinterpret_cast<uint4*>(static_cast<uint16_t*>(p.out) + static_cast<long long>(m) * p.ldc + n0);
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
               if (j * 8 < ncols) {
@@ -218,6 +200,49 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 w.w = pack2(v[8 * j + 6], v[8 * j + 7], p.out_dtype);
                 op[j] = w;
               }
+            }
+          }
+          continue;
+        }
+        // ---- staged path: residual / bias for the transposed phase first (coalesced loads in flight during the TMEM read)
+        float4 rr[8];
+        const int col = n0 + chunk * 4;
+        const bool col_ok = chunk * 4 < ncols;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int m = m_base + i * 4 + sub_row;
+          rr[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (p.resid && m < p.M && col_ok) {
+            const long long rrow = p.row_group > 0 ? 1 + (m % p.row_group) : m;
+            rr[i] = *reinterpret_cast<const float4*>(p.resid + rrow * p.ldr + col);
+          }
+        }
+        float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (p.bias && col_ok) b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col));
+        uint32_t r[32];
+        tmem_ld_32x32b_x32(t_row + c, r);
+        tmem_ld_wait();
+        __syncwarp();                          // previous chunk's readers are done with the staging buffer
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          stage4[lane * 8 + (j ^ (lane & 7))] = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]),
+                                                           __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]));
+        __syncwarp();
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int rl = i * 4 + sub_row;
+          const int m = m_base + rl;
+          float4 x = stage4[rl * 8 + (chunk ^ (rl & 7))];
+          x.x += b4.x; x.y += b4.y; x.z += b4.z; x.w += b4.w;
+          if (p.gelu) { x.x = gelu_erf(x.x); x.y = gelu_erf(x.y); x.z = gelu_erf(x.z); x.w = gelu_erf(x.w); }
+          x.x += rr[i].x; x.y += rr[i].y; x.z += rr[i].z; x.w += rr[i].w;
+          if (m < p.M && col_ok) {
+            const long long orow = p.row_group > 0 ? static_cast<long long>(m / p.row_group) * (p.row_group + 1) + 1 + (m % p.row_group) : m;
+            if (p.out_dtype == MRB_DT_F32) {
+              *reinterpret_cast<float4*>(static_cast<float*>(p.out) + orow * p.ldc + col) = x;
+            } else {
+              *reinterpret_cast<uint2*>(static_cast<uint16_t*>(p.out) + orow * p.ldc + col) =
+                  make_uint2(pack2(x.x, x.y, p.out_dtype), pack2(x.z, x.w, p.out_dtype));
             }
           }
         }
@@ -337,10 +362,15 @@ extern "C" int mrb_gemm(const void* A, long long lda, const void* B, long long l
   p.dtype = dtype;
   p.bias = bias; p.gelu = gelu; p.resid = resid; p.ldr = ldr;
   p.out = out; p.out_dtype = out_dtype; p.ldc = ldc; p.row_group = row_group;
+  {
+    static int mode = -1;                 // MRB_GEMM_EPI=direct selects the row-per-thread 16-bit epilogue (A/B measurements)
+    if (mode < 0) { const char* e = getenv("MRB_GEMM_EPI"); mode = e ? (e[0] == 'd' ? 1 : 2) : 0; }
+    p.epi_direct = mode == 1 ? 1 : 0;
+  }
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   switch (bn) {
     case 256: return launch_gemm<256, 4>(tmA, tmB, p, s);
-    case 192: return launch_gemm<192, 5>(tmA, tmB, p, s);
+    case 192: return launch_gemm<192, 4>(tmA, tmB, p, s);
     case 128: return launch_gemm<128, 6>(tmA, tmB, p, s);
     case 64: return launch_gemm<64, 8>(tmA, tmB, p, s);
     case 32: return launch_gemm<32, 8>(tmA, tmB, p, s);
