@@ -160,21 +160,23 @@ __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // ---------------------------------------------------------------- misc math
-// erf by Abramowitz & Stegun 7.1.26 (|error| <= 1.5e-7, below fp16/bf16 output resolution): 2 MUFU + ~12 FMA-class ops
-// instead of erff's ~30; the GELU epilogue of the ViT fc1 GEMM is otherwise epilogue-bound.
-__device__ __forceinline__ float erf_as(float x) {
-  const float ax = fabsf(x);
-  const float t = __fdividef(1.0f, fmaf(0.3275911f, ax, 1.0f));
-  float poly = fmaf(1.061405429f, t, -1.453152027f);
-  poly = fmaf(poly, t, 1.421413741f);
-  poly = fmaf(poly, t, -0.284496736f);
-  poly = fmaf(poly, t, 0.254829592f);
-  poly *= t;
+// Exact-erf GELU through Abramowitz & Stegun 7.1.26 (|erf error| <= 1.5e-7, far below fp16/bf16 output resolution):
+//   erfc(z) = P(t) exp(-z^2), t = 1 / (1 + p z), z = |x| / sqrt(2)
+//   gelu(x) = x * (1 - h)  for x >= 0,   x * h  for x < 0,   h = 0.5 * erfc(z)
+// 2 MUFU + ~13 FMA-class ops (erff alone is ~30): the GELU epilogue of the short-K ViT fc1 GEMM is epilogue-bound.
+__device__ __forceinline__ float gelu_erf(float x) {
+  const float u = fabsf(x);
+  float t;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f * 0.70710678118654752f, u, 1.0f)));
+  float poly = fmaf(0.5f * 1.061405429f, t, 0.5f * -1.453152027f);
+  poly = fmaf(poly, t, 0.5f * 1.421413741f);
+  poly = fmaf(poly, t, 0.5f * -0.284496736f);
+  poly = fmaf(poly, t, 0.5f * 0.254829592f);
   float e;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-ax * ax * 1.4426950408889634f));
-  return copysignf(fmaf(-poly, e, 1.0f), x);
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(u * u * (-0.5f * 1.4426950408889634f)));
+  const float h = poly * t * e;                    // 0.5 * erfc(|x| / sqrt 2)
+  return x >= 0.f ? fmaf(-x, h, x) : x * h;
 }
-__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erf_as(x * 0.70710678118654752f)); }
 __device__ __forceinline__ float gelu_erf_grad(float x) {
   const float cdf = 0.5f * (1.0f + erff(x * 0.70710678118654752f));
   const float pdf = 0.3989422804014327f * __expf(-0.5f * x * x);
