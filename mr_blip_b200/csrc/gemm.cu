@@ -335,6 +335,10 @@ static int pick_bn(int M, int N, int sms) {
   return best;
 }
 
+extern "C" int mrb_gemm2_launch(const CUtensorMap* tmA, const CUtensorMap* tmB, int M, int N, int K, int dtype,
+                                const float* bias, int gelu, const float* resid, long long ldr, void* out, int out_dtype,
+                                long long ldc, int row_group, int num_sms, void* stream);
+
 extern "C" int mrb_gemm(const void* A, long long lda, const void* B, long long ldb, int M, int N, int K, int dtype,
                         const float* bias, int gelu, const float* resid, long long ldr, void* out, int out_dtype,
                         long long ldc, int row_group, int force_bn, void* stream) {
@@ -348,6 +352,17 @@ extern "C" int mrb_gemm(const void* A, long long lda, const void* B, long long l
     int dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+  }
+  static int use_2cta = -1;               // MRB_GEMM_2CTA=0 disables the CTA-pair kernel (A/B measurements)
+  if (use_2cta < 0) { const char* e = getenv("MRB_GEMM_2CTA"); use_2cta = (e && e[0] == '0') ? 0 : 1; }
+  if (use_2cta && force_bn == 0 && M >= 512 && N >= 256 && pick_bn(M, N, g_num_sms) == 256) {
+    CUtensorMap tmA2, tmB2;
+    int rc2 = make_tmap(&tmA2, A, dtype, M, K, lda, 128);
+    if (rc2) return rc2;
+    rc2 = make_tmap(&tmB2, B, dtype, N, K, ldb, 128);
+    if (rc2) return rc2;
+    return mrb_gemm2_launch(&tmA2, &tmB2, M, N, K, dtype, bias, gelu, resid, ldr, out, out_dtype, ldc, row_group,
+                            g_num_sms, stream);
   }
   const int bn = force_bn ? force_bn : pick_bn(M, N, g_num_sms);
   CUtensorMap tmA, tmB;

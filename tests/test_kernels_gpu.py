@@ -57,8 +57,9 @@ def test_gemm_plain(ops, dtype, M, N, K, bn):
     _close(out_h, want, 1e-2 if dtype == torch.bfloat16 else 2e-3, 1e-2 if dtype == torch.bfloat16 else 2e-3, "gemm 16-bit out")
 
 
-def test_gemm_epilogues(ops):
-    M, N, K = 771, 1408, 1408
+@pytest.mark.parametrize("M", [771, 4100])          # 4100 rows route through the 2-CTA (cta_group::2) kernel
+def test_gemm_epilogues(ops, M):
+    N, K = 1408, 1408
     a = _rand((M, K), torch.float16, 1.0, 3)
     b = _rand((N, K), torch.float16, 1.0 / math.sqrt(K), 4)
     bias = _rand((N,), torch.float32, 1.0, 5)
@@ -77,8 +78,9 @@ def test_gemm_epilogues(ops):
     assert outbuf[:, N:].abs().max().item() == 0
 
 
-def test_gemm_patch_embed_remap(ops):
-    F, G, C, K = 3, 256, 1408, 592
+@pytest.mark.parametrize("F", [3, 20])
+def test_gemm_patch_embed_remap(ops, F):
+    G, C, K = 256, 1408, 592
     a = _rand((F * G, K), torch.float16, 1.0, 8)
     w = _rand((C, K), torch.float16, 0.05, 9)
     bias = _rand((C,), torch.float32, 1.0, 10)
