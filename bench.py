@@ -244,7 +244,10 @@ def run_b200(args):
                             "peak_source": how + " bf16_tflops_sustained (kernel timed inside a long step)",
                             "launches_per_step": len(prof), "flops_per_launch": flops / max(len(prof), 1),
                             "avg_launch_ms": gms / max(len(prof), 1), "share_of_step": gms / (ms / args.steps),
-                            "traffic": None}
+                            # dram__bytes_read+write of ONE launch of the dominant shape (ViT fc1, M61680 N6144 K1408, bias+GELU)
+                            # from profiles/ncu_gemm2_fc1_r01.csv; its algorithmic bytes (A + B + C once) are 948.9e6
+                            "traffic": 927.3e6, "traffic_algorithmic": 948.9e6,
+                            "traffic_source": "profiles/ncu_gemm2_fc1_r01.csv (ncu --set full, one fc1 launch)"}
         line["qformer_xattn"] = {"what": "Q-Former cross-attention path: batched K/V projection GEMM (6 layers, tcgen05) + 6 attention cores",
                                  "flops_per_step": x_flops, "ms_per_step": x_ms, "achieved": x_flops / (x_ms / 1e3) / 1e12,
                                  "unit": "TFLOP/s", "frac": x_flops / (x_ms / 1e3) / 1e12 / pk["bf16_tflops_sustained"]}
