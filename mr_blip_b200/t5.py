@@ -7,11 +7,11 @@ lora.Linear as configured at blip2_mr.py:193-200, kernel by kernel through the C
 Data layout (HBM):
   * residual stream h: fp32 [M, d_model] (reference keeps fp32 residuals under bf16 autocast).
   * every Linear input lives in an "extended" bf16 buffer [M, K+32]: columns [0,K) hold x, columns
-    [K, K+8j+8) hold the LoRA down-projections x.A_j^T of the (up to 3) Linears sharing that input.
-    The frozen weight is stored once as W_ext = [W | B_0 B_1 B_2 | 0] (bf16 [N, K+32]), so
-    base(x) + B(A x) is ONE tcgen05 GEMM; W_ext^T is kept for the dgrad GEMM, whose extra 32 output
-    columns are exactly dL/d(xA^T) -- the operand of the LoRA weight gradients.
-  * LoRA B changes every optimiser step: refresh() re-copies B into the 8-column slots.
+    [K, K+8j+8) hold the LoRA down-projections x.A_j^T of the (up to 3) Linears sharing that input
+    (one N = 32 GEMM).  The frozen weight is stored once as W_ext = [W | sB_0 sB_1 sB_2 | 0]
+    (bf16 [N, K+32]), so base(x) + B(A x) is ONE tcgen05 GEMM.  Backward mirrors this with
+    [M, N+32] gradient buffers and [W^T | A^T | 0] weights (see LoraGroup).
+  * LoRA A/B change every optimiser step: refresh() re-copies them into their 8-column slots.
 Dropout (T5 0.1, LoRA 0.05) is not applied: see DESIGN.md "Out of scope / gaps".
 """
 import math
