@@ -92,7 +92,8 @@ int mrb_scatter_frames(const int* idx, const float* dout, float* dframes, int ro
 int mrb_group_mean(const float* x, float* out, int groups, int n, int C, void* stream);
 int mrb_group_mean_bwd(const float* dout, float* dx, int groups, int n, int C, void* stream);
 
-/* CrossEntropyLoss(ignore_index=-100) rows + d(logits) (modeling_t5.py:1872-1875) */
+/* CrossEntropyLoss(ignore_index=-100) rows + d(logits) (modeling_t5.py:1872-1875).  gscale scales loss_sum and dlogits;
+ * gscale < 0 selects the mean over valid targets with the count taken on the device (no host sync: graph-capturable). */
 int mrb_cross_entropy(const float* logits, const long long* labels, int rows, int V, float* row_loss, void* dlogits,
                       int d_dtype, long long ldd, float gscale, float* loss_sum, void* stream);
 
@@ -111,6 +112,12 @@ int mrb_skinny_wgrad_tc(const void* P, long long ldp, const void* Q, long long l
 /* out[m, r] = sum_k x[m,k] W[r,k], r < 32, 16-bit: LoRA down-projection when M is tiny (decoder); larger M use mrb_gemm */
 int mrb_small_down(const void* x, long long ldx, const void* W, long long ldw, int M, int K, void* out, long long ldo,
                    int dtype, void* stream);
+
+/* Re-pack of the trainable LoRA A [8,K] / B [N,8] (fp32) of n Linears into their 16-bit operand slots after an
+ * optimiser step: descs = device array of n records {A, B, ext_slot, ld, bdown_slot, ld, adown_slot, ld, extb_slot, ld,
+ * K, N (int64), scale (double)} (13 x 8 bytes each; see LoraPackDesc in csrc/elementwise.cu).  peft's lora.Linear keeps
+ * A/B as separate Parameters (blip2_mr.py:193-237); this is the layout change that lets base(x)+B(A x) be one GEMM. */
+int mrb_lora_pack(const void* descs, int n, int blocks_per_linear, int dtype, void* stream);
 
 /* plumbing: casts, 16-bit transpose, fp32 column sums (t5_proj bias grad), y = a*x + b*y */
 int mrb_cast_f32_to_h(const float* in, void* out, long long n, int dtype, void* stream);

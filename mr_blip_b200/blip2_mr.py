@@ -11,12 +11,13 @@ gradient accumulation in lavis/tasks/base_task.py:66-68,157-248 work unchanged).
 There is no CPU or eager-PyTorch fallback: without a CUDA device / built extension, forward raises.
 """
 import logging
+import os
 
 import numpy as np
 import torch
 import torch.nn as nn
 
-from . import ops, mr_utils
+from . import _lib, ops, mr_utils
 from .base_model import BaseModel, attach, disabled_train
 from .dims import Dims, FULL, T5_PREFIX, init_state_dict
 from .registry import registry
@@ -28,17 +29,46 @@ INT_MIN = -2 ** 31
 
 
 class _HandOverGrads(torch.autograd.Function):
-    """loss = f(params) where df/dparams was already computed by the backward kernels."""
+    """loss = f(params) where df/dparams was already computed by the backward kernels into ONE flat fp32 buffer
+    (BLIP2_MR._gflat).  backward() scales it by the incoming gradient (GradScaler / accumulation factor) with one kernel
+    and returns per-parameter views, so autograd / DDP hooks / the optimiser see ordinary .grad tensors."""
 
     @staticmethod
-    def forward(ctx, loss, n, *params_and_grads):
-        ctx.grads = params_and_grads[n:]
+    def forward(ctx, loss, model, *params):
+        ctx.model = model
         return loss.clone()
 
     @staticmethod
     def backward(ctx, g):
-        scaled = torch._foreach_mul(list(ctx.grads), g)          # one multi-tensor kernel (GradScaler / accumulation factor)
-        return (None, None) + tuple(scaled) + (None,) * len(ctx.grads)
+        return (None, None) + tuple(ctx.model._hand_over(g))
+
+
+class _GraphedStep:
+    """Static input buffers + the captured CUDA graph of the device half of one training step, for one shape signature
+    (clips, frames, encoder length, decoder length).  All small integer inputs travel in ONE pinned int32 buffer."""
+
+    def __init__(self, b, t, Le, Ld, img_size):
+        n = 2 * b * Le + 3 * b * Ld
+        self.host = torch.empty(n, dtype=torch.int32).pin_memory()
+        self.dev = torch.empty(n, dtype=torch.int32, device="cuda")
+        self.video = torch.empty((b, t, 3, img_size, img_size), dtype=torch.float32, device="cuda")
+        self.loss = torch.zeros((1,), dtype=torch.float32, device="cuda")
+        self.h, self.d = {}, {}
+        off = 0
+        for name, cnt, shape in (("idx", b * Le, (b * Le,)), ("kmask", b * Le, (b, Le)), ("labels", b * Ld, (b, Ld)),
+                                 ("dec_ids", b * Ld, (b, Ld)), ("dmask", b * Ld, (b, Ld))):
+            self.h[name] = self.host[off:off + cnt].view(shape)
+            self.d[name] = self.dev[off:off + cnt].view(shape)
+            off += cnt
+        self.graph = None
+        self.calls = 0
+        self.n_launch = 0
+
+    def stage(self, host, video):
+        for name in self.h:
+            self.h[name].copy_(torch.from_numpy(host[name]).view(self.h[name].shape))
+        self.dev.copy_(self.host, non_blocking=True)
+        self.video.copy_(video.reshape(self.video.shape), non_blocking=True)
 
 
 class Blip2Base(BaseModel):
@@ -56,7 +86,7 @@ class BLIP2_MR(Blip2Base):
                  max_txt_len=200, apply_lemmatizer=False, input_time_format="seconds_integers",
                  interleave_data=True, frame_token_aggregation=None, task="qformer_freeze_lora",
                  num_frames_for_answer=4, resample_frames=False, dims: Dims = None, init_seed=1234,
-                 lora_b_std=0.0, state_dict=None, tokenizer=None):
+                 lora_b_std=0.0, state_dict=None, tokenizer=None, cuda_graphs=True, graph_bucket=(16, 4)):
         super().__init__()
         self.dims = d = dims or FULL
         assert img_size == d.img_size and num_query_token == d.num_query
@@ -113,6 +143,14 @@ class BLIP2_MR(Blip2Base):
         self.pad_token_id = self.t5_tokenizer.pad_token_id
         self._engines = None
         self._lora_versions = None
+        # Training steps replay a captured CUDA graph per shape signature (first sight of a shape runs eagerly, the second
+        # captures).  Encoder / decoder lengths are padded (masked, exact) up to graph_bucket so few graphs cover a dataset.
+        self.cuda_graphs = cuda_graphs and os.environ.get("MRB_CUDA_GRAPHS", "1") != "0"
+        self.graph_bucket = graph_bucket
+        self.max_graphs = 8
+        self._steps = {}
+        self._graph_pool = None
+        self._in_device_step = False
 
     # ---------------------------------------------------------------------------------------------
     @classmethod
@@ -145,6 +183,7 @@ class BLIP2_MR(Blip2Base):
 
     def _weights_changed(self):
         self._engines = None
+        self._steps = {}
 
     # ---------------------------------------------------------------------------------------------
     def _get(self, name):
@@ -159,9 +198,23 @@ class BLIP2_MR(Blip2Base):
                 raise RuntimeError("BLIP2_MR runs only on a CUDA device through libmrblip_b200.so "
                                    "(no CPU / eager fallback); move the model with .cuda()")
             d = self.dims
-            self._engines = (VitEngine(d, self._get), QFormerEngine(d, self._get), T5Engine(d, self._get))
+            vit, qf, t5 = VitEngine(d, self._get), QFormerEngine(d, self._get), T5Engine(d, self._get)
+            self._engines = (vit, qf, t5)
             self._lora_versions = None
+            self._steps = {}
+            # every trainable gradient lives in one flat fp32 buffer: zeroed / scaled / all-reduced with single launches
+            pw, pb = self.t5_proj.weight, self.t5_proj.bias
+            n = t5.n_grad_elems()
+            self._gflat = torch.zeros(n + pw.numel() + pb.numel(), dtype=torch.float32, device="cuda")
+            self._hflat = torch.empty_like(self._gflat)
+            off = t5.bind_grads(self._gflat, 0)
+            assert off == n
+            self._g_projW = self._gflat[n:n + pw.numel()].view(pw.shape)
+            self._g_projb = self._gflat[n + pw.numel():].view(pb.shape)
+            self._grad_params = [p for p, _ in t5.param_grads()] + [pw, pb]
         vit, qf, t5 = self._engines
+        if self._in_device_step:                             # (captured) device step: LoRA re-pack is part of the step itself
+            return vit, qf, t5
         vers = tuple(p._version for g in t5.groups for p in g.A_params + g.B_params)
         vers += (self.t5_proj.weight._version, self.t5_proj.bias._version)
         if vers != self._lora_versions:                      # optimizer.step() happened: re-pack the trainable bits
@@ -261,54 +314,179 @@ class BLIP2_MR(Blip2Base):
         _, _, t5 = self.engines()
         inputs = torch.empty((B * Le, C), dtype=torch.float32, device="cuda")
         ops.gather_rows(idx.reshape(-1), t5.emb, frames_for_t5.reshape(B * TN, C), inputs)
-        self._last_row_table = idx
         return inputs.view(B, Le, C), atts.to("cuda", non_blocking=True), video_prompt
 
     # ---------------------------------------------------------------------------------------------
     def forward(self, samples):
         return self.forward_mr(samples)
 
-    def forward_mr(self, samples, want_logits=False):
-        """blip2_mr.py:433-570."""
-        vit, qf, t5 = self.engines()
-        d = self.dims
+    # ---- gradient hand-over ---------------------------------------------------------------------
+    def _grad_views(self, flat):
+        out, off = [], 0
+        for p in self._grad_params:
+            out.append(flat[off:off + p.numel()].view(p.shape))
+            off += p.numel()
+        return out
+
+    def _hand_over(self, g):
+        """g * (flat gradients of this step) -> per-parameter views.  The views alias self._hflat when no gradient is
+        pending (optimizer.zero_grad(set_to_none=True), the torch default); under gradient accumulation a fresh buffer is
+        used so that earlier .grad tensors (which may alias _hflat) are not overwritten."""
+        ps = self._grad_params
+        pending = any(p.grad is not None for p in (ps[0], ps[len(ps) // 2], ps[-1]))
+        dst = torch.empty_like(self._gflat) if pending else self._hflat
+        torch.mul(self._gflat, g.to(self._gflat.dtype), out=dst)
+        return self._grad_views(dst)
+
+    def flat_grads(self):
+        """The flat buffer that currently backs every trainable .grad (for a single all-reduce), or None."""
+        ps = getattr(self, "_grad_params", None)
+        if not ps or any(p.grad is None for p in ps):
+            return None
+        base, off = self._hflat.data_ptr(), 0
+        for p in ps:
+            if p.grad.data_ptr() != base + 4 * off or not p.grad.is_contiguous():
+                return None
+            off += p.numel()
+        return self._hflat
+
+    # ---- host half of a step --------------------------------------------------------------------
+    @staticmethod
+    def _video_of(samples):
         image = samples["video"]
-        b, t = image.shape[:2]
-        need_grad = self.training and torch.is_grad_enabled()
-        frames, frames_atts, (qh, qh16) = self.get_frame_embeddings_and_attentions(image, want_aux=True)
-        inputs, atts, _ = self.prompt_concatenation(samples["timestamps"], samples["duration"], frames, frames_atts,
-                                                     samples["video_prompt_end"], samples["query_prompt"],
-                                                     samples["task_prompt"])
+        return torch.stack(image) if isinstance(image, list) else image
+
+    def _host_phase(self, samples, bucket=None):
+        """Everything forward_mr does on the host (blip2_mr.py:513-534): timestamps -> strings -> ids, the interleave row
+        table, the tokenised answer.  -> numpy int32 arrays (idx [B*Le], kmask [B,Le], labels/dec_ids/dmask [B,Ld]).
+        bucket = (e, d): pad Le / Ld up to multiples with masked pad tokens / ignored targets (exact: masked keys and
+        -100 targets contribute nothing to the loss or to any gradient)."""
+        b, t = self._video_of(samples).shape[:2]
+        n = 1 if self.frame_token_aggregation else self.num_query_token
+        table, atts, _ = self.build_prompt_table(samples["timestamps"], samples["duration"], b, t, n,
+                                                 samples["video_prompt_end"], samples["query_prompt"], samples["task_prompt"])
         ans = self.t5_tokenizer(samples["relevant_windows"], padding="longest", truncation=True,
                                 max_length=self.max_txt_len, return_tensors="pt")
-        labels = ans.input_ids.masked_fill(ans.input_ids == self.t5_tokenizer.pad_token_id, -100)
+        labels = ans.input_ids.masked_fill(ans.input_ids == self.t5_tokenizer.pad_token_id, -100).numpy().astype(np.int32)
+        dmask = ans.attention_mask.numpy().astype(np.int32)
+        kmask = atts.numpy().astype(np.int32)
+        if bucket:
+            Le, Ld = table.shape[1], labels.shape[1]
+            pe, pd = -Le % bucket[0], -Ld % bucket[1]
+            if pe:
+                table = np.concatenate([table, np.full((b, pe), self.pad_token_id, np.int32)], axis=1)
+                kmask = np.concatenate([kmask, np.zeros((b, pe), np.int32)], axis=1)
+            if pd:
+                labels = np.concatenate([labels, np.full((b, pd), -100, np.int32)], axis=1)
+                dmask = np.concatenate([dmask, np.zeros((b, pd), np.int32)], axis=1)
+        dec_ids = np.zeros_like(labels)                      # _shift_right, modeling_t5.py:919-948
+        dec_ids[:, 1:] = labels[:, :-1]
+        dec_ids[dec_ids == -100] = 0
+        return dict(idx=np.ascontiguousarray(table.reshape(-1)), kmask=np.ascontiguousarray(kmask),
+                    labels=np.ascontiguousarray(labels), dec_ids=dec_ids, dmask=np.ascontiguousarray(dmask),
+                    b=b, t=t, Le=table.shape[1], Ld=labels.shape[1])
+
+    # ---- device half of a step (no host synchronisation: capturable) ------------------------------
+    def _device_phase(self, video, idx, kmask, labels, dec_ids, dmask, need_grad, want_logits=False, loss_out=None):
+        """ViT -> ln_vision -> Q-Former -> t5_proj -> interleave gather -> T5 loss (-> backward into the flat gradient
+        buffer).  idx int32 [B*Le], kmask/dmask int32, labels/dec_ids int64 -- all on the GPU."""
+        vit, qf, t5 = self.engines()
+        d = self.dims
+        b, t = video.shape[:2]
+        frames, _, (qh, qh16) = self.get_frame_embeddings_and_attentions(video, want_aux=True)
+        B, TN, C = frames.shape
+        Le = idx.numel() // B
+        inputs = torch.empty((B * Le, C), dtype=torch.float32, device="cuda")
+        ops.gather_rows(idx, t5.emb, frames.reshape(B * TN, C), inputs)
         if need_grad:
-            t5.zero_grads()
-        out = t5.loss(inputs, atts, labels, ans.attention_mask, backward=need_grad, want_logits=want_logits)
-        loss = out["loss"].reshape(())
+            self._gflat.zero_()
+        out = t5.loss_device(inputs.view(B, Le, C), kmask, labels, dec_ids, dmask, backward=need_grad,
+                             want_logits=want_logits, loss_out=loss_out)
         if need_grad:
             n = d.num_query
             M = b * t * n
             d_frames = torch.zeros((b * t * (1 if self.frame_token_aggregation else n), d.d_model),
                                    dtype=torch.float32, device="cuda")
             din = out["d_inputs_embeds"].reshape(-1, d.d_model)
-            ops.scatter_frames(self._last_row_table.reshape(-1), din, d_frames)
+            ops.scatter_frames(idx, din, d_frames)
             if self.frame_token_aggregation:
                 full = torch.empty((M, d.d_model), dtype=torch.float32, device="cuda")
                 ops.group_mean_bwd(d_frames, full, b * t, n, d.d_model)
                 d_frames = full
-            pairs = t5.param_grads() + self._t5_proj_grads(d_frames, qh, M)
-            params = [p for p, _ in pairs]
-            grads = [g for _, g in pairs]
-            loss = _HandOverGrads.apply(loss, len(params), *params, *grads)
+            self._t5_proj_grads(d_frames, qh, M)
+        if want_logits:
+            out.update(inputs_embeds=inputs.view(B, Le, C), qformer=qh.view(b * t, d.num_query, -1), frames_for_t5=frames)
+        return out
+
+    def _device_step(self, st):
+        """What a CUDA graph holds: LoRA / t5_proj re-pack (the optimiser changed them) + forward + backward."""
+        self.engines()
+        self._in_device_step = True
+        try:
+            _, qf, t5 = self._engines
+            t5.refresh()
+            qf.set_t5_proj(self.t5_proj.weight, self.t5_proj.bias)
+            x = st.d
+            self._device_phase(st.video, x["idx"], x["kmask"], x["labels"].to(torch.int64), x["dec_ids"].to(torch.int64),
+                               x["dmask"], need_grad=True, loss_out=st.loss)
+        finally:
+            self._in_device_step = False
+
+    def _graphed_step(self, samples):
+        host = self._host_phase(samples, bucket=self.graph_bucket)
+        key = (host["b"], host["t"], host["Le"], host["Ld"], bool(self.frame_token_aggregation))
+        st = self._steps.pop(key, None)
+        if st is None:
+            while len(self._steps) >= self.max_graphs:       # least recently used shape goes first
+                self._steps.pop(next(iter(self._steps)))
+            st = _GraphedStep(host["b"], host["t"], host["Le"], host["Ld"], self.dims.img_size)
+        self._steps[key] = st
+        self.engines()
+        st.stage(host, self._video_of(samples))
+        if st.graph is not None:
+            st.graph.replay()
+            _lib.launch_count += st.n_launch                 # the kernels the replay just ran (bench.py: gpu_launches)
+        elif st.calls == 0:
+            self._device_step(st)                            # first sight of this shape: eager (also the warm-up)
+        else:
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            l0 = _lib.launch_count
+            with torch.cuda.graph(g, pool=self._graph_pool, capture_error_mode="thread_local"):
+                self._device_step(st)
+            st.n_launch = _lib.launch_count - l0             # C-ABI kernels recorded into the graph
+            if self._graph_pool is None:
+                self._graph_pool = g.pool()
+            st.graph = g
+            g.replay()
+        st.calls += 1
+        self._lora_versions = None                           # the step re-packed LoRA itself; eager callers re-check
+        return st.loss
+
+    def forward_mr(self, samples, want_logits=False):
+        """blip2_mr.py:433-570."""
+        self.engines()
+        need_grad = self.training and torch.is_grad_enabled()
+        if need_grad and self.cuda_graphs and not want_logits:
+            loss = self._graphed_step(samples).reshape(())
+            return {"loss": _HandOverGrads.apply(loss, self, *self._grad_params)}
+        host = self._host_phase(samples)
+        dev = {k: torch.from_numpy(host[k]).to("cuda", non_blocking=True) for k in ("idx", "kmask", "labels", "dec_ids", "dmask")}
+        video = self._video_of(samples).to(device="cuda", dtype=torch.float32, non_blocking=True)
+        out = self._device_phase(video, dev["idx"], dev["kmask"], dev["labels"].to(torch.int64), dev["dec_ids"].to(torch.int64),
+                                 dev["dmask"], need_grad, want_logits)
+        loss = out["loss"].reshape(())
+        if need_grad:
+            loss = _HandOverGrads.apply(loss, self, *self._grad_params)
         res = {"loss": loss}
         if want_logits:
-            res.update(logits=out["logits"], inputs_embeds=inputs, attention_mask=atts, labels=labels,
-                       qformer=qh.view(b * t, d.num_query, -1), frames_for_t5=frames)
+            res.update(logits=out["logits"], inputs_embeds=out["inputs_embeds"], attention_mask=dev["kmask"].long(),
+                       labels=dev["labels"].long(), qformer=out["qformer"], frames_for_t5=out["frames_for_t5"])
         return res
 
     def _t5_proj_grads(self, d_frames, qh, M):
-        """dW = dF^T . h, db = colsum(dF) for t5_proj (trainable, blip2_mr.py:291 note in SURVEY.md §3.1)."""
+        """dW = dF^T . h, db = colsum(dF) for t5_proj (trainable, blip2_mr.py:291 note in SURVEY.md §3.1), written into
+        their slots of the flat gradient buffer (zeroed at the start of the step)."""
         d = self.dims
         BF = torch.bfloat16
         Mp = (M + 7) // 8 * 8
@@ -320,10 +498,8 @@ class BLIP2_MR(Blip2Base):
         ht = torch.zeros((d.qf_hidden, Mp), dtype=BF, device="cuda")
         ops.transpose16(df16, dft, M, d.d_model)
         ops.transpose16(h16, ht, M, d.qf_hidden)
-        dW = ops.gemm(dft, ht, out_dtype=torch.float32)       # [2048, 768]
-        db = torch.zeros((d.d_model,), dtype=torch.float32, device="cuda")
-        ops.colsum(d_frames, db)
-        return [(self.t5_proj.weight, dW), (self.t5_proj.bias, db)]
+        ops.gemm(dft, ht, out=self._g_projW)                  # [2048, 768]
+        ops.colsum(d_frames, self._g_projb)
 
     # ---------------------------------------------------------------------------------------------
     @torch.no_grad()

@@ -295,14 +295,23 @@ __global__ void group_mean_bwd_kernel(const float* __restrict__ dout, float* __r
 }
 
 // ---------------------------------------------------------------- cross entropy (modeling_t5.py:1872-1875)
-// logits fp32 [rows, V]; labels int64 (-100 = ignore).  loss_sum += -log p[label]; dlogits = (p - onehot) * gscale
+// logits fp32 [rows, V]; labels int64 (-100 = ignore).  loss_sum += -log p[label]; dlogits = (p - onehot) * gscale.
+// gscale < 0: mean reduction, 1 / #valid targets counted on the device (keeps the step free of host syncs / graph-capturable)
 __global__ void __launch_bounds__(1024) ce_kernel(const float* __restrict__ logits, const long long* __restrict__ labels,
-                                                  int V, float* __restrict__ row_loss, void* __restrict__ dlogits,
+                                                  int rows, int V, float* __restrict__ row_loss, void* __restrict__ dlogits,
                                                   int d_dtype, long long ldd, float gscale,
                                                   float* __restrict__ loss_sum) {
   __shared__ float red[32];
   __shared__ float bval;
   const int row = blockIdx.x;
+  if (gscale < 0.f) {
+    int cnt = 0;
+    for (int r0 = 0; r0 < rows; r0 += blockDim.x) {
+      const int r = r0 + threadIdx.x;
+      cnt += __syncthreads_count(r < rows && labels[r] >= 0);
+    }
+    gscale = 1.f / static_cast<float>(max(cnt, 1));
+  }
   const float* lr = logits + static_cast<long long>(row) * V;
   const long long lab = labels[row];
   float mx = -INFINITY;
@@ -434,22 +443,86 @@ __global__ void __launch_bounds__(256) skinny_wgrad_kernel(const uint16_t* __res
   }
 }
 
-// small-M variant (decoder steps): every output element is owned by one thread, no atomics.  out += P^T Q.
+// small-M variant (decoder steps): out += P^T Q without atomics.  A block owns 64 columns of P (lane -> 2 columns); its
+// 8 warps split the M rows (all loads independent: the kernel is pure latency), then reduce through shared memory.
 __global__ void __launch_bounds__(256) skinny_wgrad_small_kernel(const uint16_t* __restrict__ P, long long ldp,
                                                                  const uint16_t* __restrict__ Q, long long ldq, int M, int C,
                                                                  float* __restrict__ out, int transposed_out, int dtype) {
-  const int r = threadIdx.x & 7;
-  const int c = blockIdx.x * 32 + (threadIdx.x >> 3);
-  if (c >= C) return;
-  float acc = 0.f;
-  for (int m = 0; m < M; ++m) {
-    const uint16_t pw = P[static_cast<long long>(m) * ldp + c], qw = Q[static_cast<long long>(m) * ldq + r];
-    const float pv = (dtype == MRB_DT_F16) ? __half2float(__ushort_as_half(pw)) : __uint_as_float(static_cast<uint32_t>(pw) << 16);
-    const float qv = (dtype == MRB_DT_F16) ? __half2float(__ushort_as_half(qw)) : __uint_as_float(static_cast<uint32_t>(qw) << 16);
-    acc = fmaf(pv, qv, acc);
+  __shared__ float red[8][64 * 8 + 8];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int c = blockIdx.x * 64 + lane * 2;
+  float acc[2][8];
+#pragma unroll
+  for (int i = 0; i < 2; ++i)
+#pragma unroll
+    for (int r = 0; r < 8; ++r) acc[i][r] = 0.f;
+  if (c < C) {
+#pragma unroll 8
+    for (int m = warp; m < M; m += 8) {
+      const uint32_t pw = *reinterpret_cast<const uint32_t*>(P + static_cast<long long>(m) * ldp + c);
+      const uint4 qv = *reinterpret_cast<const uint4*>(Q + static_cast<long long>(m) * ldq);
+      const float p0 = unpack_lo(pw, dtype), p1 = unpack_hi(pw, dtype);
+      const uint32_t qw[4] = {qv.x, qv.y, qv.z, qv.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float q0 = unpack_lo(qw[i], dtype), q1 = unpack_hi(qw[i], dtype);
+        acc[0][2 * i] = fmaf(p0, q0, acc[0][2 * i]);     acc[0][2 * i + 1] = fmaf(p0, q1, acc[0][2 * i + 1]);
+        acc[1][2 * i] = fmaf(p1, q0, acc[1][2 * i]);     acc[1][2 * i + 1] = fmaf(p1, q1, acc[1][2 * i + 1]);
+      }
+    }
   }
-  if (transposed_out) out[static_cast<long long>(r) * C + c] += acc;
-  else out[static_cast<long long>(c) * 8 + r] += acc;
+#pragma unroll
+  for (int i = 0; i < 2; ++i)
+#pragma unroll
+    for (int r = 0; r < 8; ++r) red[warp][(lane * 2 + i) * 8 + r] = acc[i][r];
+  __syncthreads();
+  for (int idx = threadIdx.x; idx < 64 * 8; idx += 256) {
+    float v = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) v += red[w][idx];
+    const int cc = blockIdx.x * 64 + (idx >> 3), r = idx & 7;
+    if (cc < C) {
+      if (transposed_out) out[static_cast<long long>(r) * C + cc] += v;
+      else out[static_cast<long long>(cc) * 8 + r] += v;
+    }
+  }
+}
+
+// ---------------------------------------------------------------- LoRA re-pack after an optimiser step
+// For every LoRA-wrapped Linear j of a LoraGroup (mr_blip_b200/t5.py) the trainable fp32 A [8,K] / B [N,8] are copied as
+// 16-bit values into their four slots: [W | sB] columns, B_down rows, A_down rows and [W^T | A^T] columns.  One launch
+// for all Linears (descriptor table in device memory) instead of ~1700 strided copies per step.
+struct LoraPackDesc {
+  const float* A; const float* B;
+  uint16_t* ext_slot; long long ld_ext;        // [N, 8]: ext_slot[n * ld + r]   = s * B[n, r]
+  uint16_t* bdown_slot; long long ld_bdown;    // [8, N]: bdown_slot[r * ld + n] = s * B[n, r]
+  uint16_t* adown_slot; long long ld_adown;    // [8, K]: adown_slot[r * ld + k] = A[r, k]
+  uint16_t* extb_slot; long long ld_extb;      // [K, 8]: extb_slot[k * ld + r]  = A[r, k]
+  long long K, N;
+  double scale;
+};
+__global__ void __launch_bounds__(256) lora_pack_kernel(const LoraPackDesc* __restrict__ descs, int dtype) {
+  const LoraPackDesc d = descs[blockIdx.x];
+  const float s = static_cast<float>(d.scale);
+  for (long long i = blockIdx.y * 256 + threadIdx.x; i < max(d.K, d.N); i += static_cast<long long>(gridDim.y) * 256) {
+    if (i < d.N) {
+      const float4 b0 = *reinterpret_cast<const float4*>(d.B + i * 8), b1 = *reinterpret_cast<const float4*>(d.B + i * 8 + 4);
+      const float v[8] = {b0.x * s, b0.y * s, b0.z * s, b0.w * s, b1.x * s, b1.y * s, b1.z * s, b1.w * s};
+      *reinterpret_cast<uint4*>(d.ext_slot + i * d.ld_ext) =
+          make_uint4(pack2(v[0], v[1], dtype), pack2(v[2], v[3], dtype), pack2(v[4], v[5], dtype), pack2(v[6], v[7], dtype));
+#pragma unroll
+      for (int r = 0; r < 8; ++r) d.bdown_slot[r * d.ld_bdown + i] = static_cast<uint16_t>(pack2(v[r], 0.f, dtype) & 0xffff);
+    }
+    if (i < d.K) {
+      float v[8];
+#pragma unroll
+      for (int r = 0; r < 8; ++r) v[r] = d.A[r * d.K + i];
+#pragma unroll
+      for (int r = 0; r < 8; ++r) d.adown_slot[r * d.ld_adown + i] = static_cast<uint16_t>(pack2(v[r], 0.f, dtype) & 0xffff);
+      *reinterpret_cast<uint4*>(d.extb_slot + i * d.ld_extb) =
+          make_uint4(pack2(v[0], v[1], dtype), pack2(v[2], v[3], dtype), pack2(v[4], v[5], dtype), pack2(v[6], v[7], dtype));
+    }
+  }
 }
 
 // ---------------------------------------------------------------- LoRA down-projection for small M
@@ -647,7 +720,7 @@ extern "C" int mrb_cross_entropy(const float* logits, const long long* labels, i
                                  void* dlogits, int d_dtype, long long ldd, float gscale, float* loss_sum, void* stream) {
   if (rows <= 0) return MRB_OK;
   if (dlogits && (ldd & 1)) return MRB_ERR_ARG;
-  ce_kernel<<<rows, 1024, 0, STREAM>>>(logits, labels, V, row_loss, dlogits, d_dtype, ldd, gscale, loss_sum);
+  ce_kernel<<<rows, 1024, 0, STREAM>>>(logits, labels, rows, V, row_loss, dlogits, d_dtype, ldd, gscale, loss_sum);
   MRB_CHECK_LAUNCH();
   return MRB_OK;
 }
@@ -672,7 +745,7 @@ extern "C" int mrb_skinny_wgrad(const void* P, long long ldp, const void* Q, lon
   if (M <= 0 || C <= 0) return MRB_OK;
   if ((ldq & 7) || (ldp & 7) || (C & 7) || (reinterpret_cast<uintptr_t>(P) & 15) || (reinterpret_cast<uintptr_t>(Q) & 15)) return MRB_ERR_ARG;
   if (M <= 256) {
-    skinny_wgrad_small_kernel<<<blocks_for(C, 32), 256, 0, STREAM>>>(static_cast<const uint16_t*>(P), ldp,
+    skinny_wgrad_small_kernel<<<blocks_for(C, 64), 256, 0, STREAM>>>(static_cast<const uint16_t*>(P), ldp,
                                                                     static_cast<const uint16_t*>(Q), ldq, M, C, out,
                                                                     transposed_out, dtype);
     MRB_CHECK_LAUNCH();
@@ -682,6 +755,14 @@ extern "C" int mrb_skinny_wgrad(const void* P, long long ldp, const void* Q, lon
   dim3 grid(blocks_for(C, 256), blocks_for(M, rows_per_block));
   skinny_wgrad_kernel<<<grid, 256, 0, STREAM>>>(static_cast<const uint16_t*>(P), ldp, static_cast<const uint16_t*>(Q), ldq,
                                                 M, C, out, transposed_out, dtype, rows_per_block);
+  MRB_CHECK_LAUNCH();
+  return MRB_OK;
+}
+
+extern "C" int mrb_lora_pack(const void* descs, int n, int blocks_per_linear, int dtype, void* stream) {
+  if (n <= 0) return MRB_OK;
+  if (blocks_per_linear <= 0 || (dtype != MRB_DT_F16 && dtype != MRB_DT_BF16)) return MRB_ERR_ARG;
+  lora_pack_kernel<<<dim3(n, blocks_per_linear), 256, 0, STREAM>>>(static_cast<const LoraPackDesc*>(descs), dtype);
   MRB_CHECK_LAUNCH();
   return MRB_OK;
 }

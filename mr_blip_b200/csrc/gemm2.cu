@@ -18,6 +18,7 @@ struct Gemm2Params {
   const float* resid; long long ldr;
   void* out; int out_dtype; long long ldc;
   int row_group;
+  int tail;                 // 1: the last column tile runs a narrower MMA (MRB_GEMM2_TAIL=0 disables, for A/B runs)
 };
 
 constexpr int G2_BM = 128, G2_BN = 256, G2_BK = 64, G2_STAGES = 6, G2_GROUP_M = 8;
@@ -100,6 +101,14 @@ __device__ __forceinline__ void tile_coords2(int t, int m_tiles, int n_tiles, in
   tn = r / gm;
 }
 
+// Width of the MMA for column tile tn: 256, or the remaining columns rounded up to 64 for the last tile (N = 1408 = 5 x 256
+// + 128 in the ViT proj / fc2 GEMMs: the tail tile then costs half the tensor time).  Each CTA supplies n_mma / 2 rows of B.
+__device__ __forceinline__ int tile_n_mma(const Gemm2Params& p, int tn) {
+  const int rem = p.N - tn * G2_BN;
+  return (rem >= G2_BN || !p.tail) ? G2_BN : ((rem + 63) & ~63);
+}
+
+template <bool PIPE>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(320, 1)
 gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const Gemm2Params p) {
   constexpr uint32_t TMEM_COLS = 512;
@@ -145,13 +154,14 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
       for (int t = pair; t < num_tiles; t += n_pairs) {
         int tm, tn;
         tile_coords2(t, p.m_tiles, p.n_tiles, tm, tn);
+        const int b_row = tn * G2_BN + static_cast<int>(rank) * (tile_n_mma(p, tn) / 2);   // this CTA's half of the (tail) tile
         for (int kb = 0; kb < k_blocks; ++kb) {
           mbar_wait_cluster(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * G2_STAGE;
           const uint32_t lbar = map_to_cta(smem_u32(&full_bar[stage]), 0);
           if (leader) mbar_expect_tx(&full_bar[stage], 2 * G2_STAGE);
           tma2_load_2d(sa, &tmA, lbar, kb * G2_BK, tm * 256 + static_cast<int>(rank) * G2_BM);
-          tma2_load_2d(sa + G2_A_BYTES, &tmB, lbar, kb * G2_BK, tn * G2_BN + static_cast<int>(rank) * (G2_BN / 2));
+          tma2_load_2d(sa + G2_A_BYTES, &tmB, lbar, kb * G2_BK, b_row);
           if (++stage == G2_STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -159,11 +169,15 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
   } else if (warp == 1) {
     // ===================== MMA issuer (leader CTA only) =====================
     if (leader) {
-      const uint32_t idesc = umma_idesc_f16(p.dtype == MRB_DT_BF16 ? 1 : 0, 256, G2_BN);
+      const uint32_t idesc_full = umma_idesc_f16(p.dtype == MRB_DT_BF16 ? 1 : 0, 256, G2_BN);
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
       for (int t = pair; t < num_tiles; t += n_pairs, ++it) {
+        int tm, tn;
+        tile_coords2(t, p.m_tiles, p.n_tiles, tm, tn);
+        const int n_mma = tile_n_mma(p, tn);
+        const uint32_t idesc = n_mma == G2_BN ? idesc_full : umma_idesc_f16(p.dtype == MRB_DT_BF16 ? 1 : 0, 256, n_mma);
         const int as = it & 1;
         const uint32_t aphase = (it >> 1) & 1;
         mbar_wait_cluster(&tmem_empty[as], aphase ^ 1);
@@ -191,8 +205,6 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     // ===================== epilogue warps (8 per CTA): same staged epilogue as gemm.cu =====================
     const int quad = warp & 3;
     const int eg = (warp - 2) >> 2;
-    constexpr int HALF = G2_BN / 2;
-    const int c_begin = eg * HALF, c_end = c_begin + HALF;
     float4* stage4 = reinterpret_cast<float4*>(smem + G2_EPI_OFFSET + (warp - 2) * 4096);
     const int sub_row = lane >> 3, chunk = lane & 7;
     const uint32_t empty_remote0 = map_to_cta(smem_u32(&tmem_empty[0]), 0);
@@ -203,33 +215,20 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
       tile_coords2(t, p.m_tiles, p.n_tiles, tm, tn);
       const int as = it & 1;
       const uint32_t aphase = (it >> 1) & 1;
+      const int half = tile_n_mma(p, tn) / 2;             // multiple of 32: each warp group takes half of the tile's columns
+      const int c_begin = eg * half, c_end = c_begin + half;
       const int m_base = tm * 256 + static_cast<int>(rank) * G2_BM + quad * 32;
       mbar_wait_cluster(&tmem_full[as], aphase);
       tc_fence_after();
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + as * G2_BN;
-#pragma unroll 1
-      for (int c = c_begin; c < c_end; c += 32) {
+      // One 32 x 32 fp32 chunk: TMEM registers (row per thread) -> XOR-swizzled staging -> 4 rows x 128 B per warp instruction
+      // (coalesced residual reads / output writes), bias + GELU + residual in between.
+      auto epi_chunk = [&](const uint32_t (&r)[32], const int c, const float4 (&rr)[8], const float4 b4) {
         const int n0 = tn * G2_BN + c;
-        if (n0 >= p.N) break;
         const int ncols = min(32, p.N - n0);
-        float4 rr[8];
         const int col = n0 + chunk * 4;
         const bool col_ok = chunk * 4 < ncols;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int m = m_base + i * 4 + sub_row;
-          rr[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (p.resid && m < p.M && col_ok) {
-            const long long rrow = p.row_group > 0 ? 1 + (m % p.row_group) : m;
-            rr[i] = *reinterpret_cast<const float4*>(p.resid + rrow * p.ldr + col);
-          }
-        }
-        float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (p.bias && col_ok) b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col));
-        uint32_t r[32];
-        tmem_ld_32x32b_x32(t_row + c, r);
-        tmem_ld_wait();
-        __syncwarp();
+        __syncwarp();                          // previous chunk's readers are done with the staging buffer
 #pragma unroll
         for (int j = 0; j < 8; ++j)
           stage4[lane * 8 + (j ^ (lane & 7))] = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]),
@@ -253,6 +252,60 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
             }
           }
         }
+      };
+      // residual / bias of a chunk (issued before the TMEM wait so that the loads are in flight during it)
+      auto epi_prefetch = [&](const int c, float4 (&rr)[8], float4& b4) {
+        const int n0 = tn * G2_BN + c;
+        const int col = n0 + chunk * 4;
+        const bool col_ok = n0 + chunk * 4 < p.N;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int m = m_base + i * 4 + sub_row;
+          rr[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (p.resid && m < p.M && col_ok) {
+            const long long rrow = p.row_group > 0 ? 1 + (m % p.row_group) : m;
+            rr[i] = *reinterpret_cast<const float4*>(p.resid + rrow * p.ldr + col);
+          }
+        }
+        b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (p.bias && col_ok) b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col));
+      };
+      if (PIPE) {
+        // software pipeline over the (up to 4) chunks of this warp: the tcgen05.ld of chunk i+1 is in flight while chunk i
+        // runs its math and stores; the accumulator buffer is handed back to the MMA warp as soon as the last load landed.
+        const int nch = min(half, max(0, p.N - (tn * G2_BN + c_begin)) + 31) / 32;
+        uint32_t ra[32], rb[32];
+        float4 rr[8], b4;
+        if (nch > 0) tmem_ld_32x32b_x32(t_row + c_begin, ra);
+#pragma unroll
+        for (int ci = 0; ci < 4; ci += 2) {
+          if (ci < nch) {
+            epi_prefetch(c_begin + ci * 32, rr, b4);
+            tmem_ld_wait();
+            if (ci + 1 < nch) tmem_ld_32x32b_x32(t_row + c_begin + (ci + 1) * 32, rb);
+            else { tc_fence_before(); __syncwarp(); if (lane == 0) mbar_arrive_remote(as ? empty_remote1 : empty_remote0); }
+            epi_chunk(ra, c_begin + ci * 32, rr, b4);
+          }
+          if (ci + 1 < nch) {
+            epi_prefetch(c_begin + (ci + 1) * 32, rr, b4);
+            tmem_ld_wait();
+            if (ci + 2 < nch) tmem_ld_32x32b_x32(t_row + c_begin + (ci + 2) * 32, ra);
+            else { tc_fence_before(); __syncwarp(); if (lane == 0) mbar_arrive_remote(as ? empty_remote1 : empty_remote0); }
+            epi_chunk(rb, c_begin + (ci + 1) * 32, rr, b4);
+          }
+        }
+        if (nch == 0) { tc_fence_before(); __syncwarp(); if (lane == 0) mbar_arrive_remote(as ? empty_remote1 : empty_remote0); }
+        continue;
+      }
+#pragma unroll 1
+      for (int c = c_begin; c < c_end; c += 32) {
+        if (tn * G2_BN + c >= p.N) break;
+        float4 rr[8], b4;
+        epi_prefetch(c, rr, b4);
+        uint32_t r[32];
+        tmem_ld_32x32b_x32(t_row + c, r);
+        tmem_ld_wait();
+        epi_chunk(r, c, rr, b4);
       }
       tc_fence_before();
       __syncwarp();
@@ -278,20 +331,28 @@ extern "C" int mrb_gemm2_launch(const CUtensorMap* tmA, const CUtensorMap* tmB, 
                                 long long ldc, int row_group, int num_sms, void* stream) {
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(gemm2_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, G2_SMEM);
+    cudaError_t e = cudaFuncSetAttribute(gemm2_tcgen05_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, G2_SMEM);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(gemm2_tcgen05_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, G2_SMEM);
     if (e != cudaSuccess) return mrb_set_error(e);
     configured = true;
   }
+  static int pipe = -1;                   // MRB_GEMM2_EPI=plain selects the unpipelined epilogue (A/B measurements)
+  if (pipe < 0) { const char* e = getenv("MRB_GEMM2_EPI"); pipe = (e && e[0] == 'p' && e[1] == 'l') ? 0 : 1; }
   Gemm2Params p;
   p.M = M; p.N = N; p.K = K;
   p.m_tiles = (M + 255) / 256;
   p.n_tiles = (N + G2_BN - 1) / G2_BN;
   p.dtype = dtype; p.bias = bias; p.gelu = gelu; p.resid = resid; p.ldr = ldr;
   p.out = out; p.out_dtype = out_dtype; p.ldc = ldc; p.row_group = row_group;
+  static int tail = -1;
+  if (tail < 0) { const char* e = getenv("MRB_GEMM2_TAIL"); tail = (e && e[0] == '0') ? 0 : 1; }
+  p.tail = tail;
   const int tiles = p.m_tiles * p.n_tiles;
   int pairs = num_sms / 2;
   if (tiles < pairs) pairs = tiles;
-  gemm2_tcgen05_kernel<<<2 * pairs, 320, G2_SMEM, static_cast<cudaStream_t>(stream)>>>(*tmA, *tmB, p);
+  if (pipe) gemm2_tcgen05_kernel<true><<<2 * pairs, 320, G2_SMEM, static_cast<cudaStream_t>(stream)>>>(*tmA, *tmB, p);
+  else gemm2_tcgen05_kernel<false><<<2 * pairs, 320, G2_SMEM, static_cast<cudaStream_t>(stream)>>>(*tmA, *tmB, p);
   MRB_CHECK_LAUNCH();
   return MRB_OK;
 }

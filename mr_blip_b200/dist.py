@@ -2,8 +2,8 @@
 init_distributed_mode and the DDP wrap at lavis/runners/runner_base.py:89-96).
 
 The path shards by clip with no data-path collective; the only exchange is the all-reduce of the 19.5 M
-trainable gradients (LoRA A/B + t5_proj, 78 MB fp32) once per optimiser step.  GradAllReducer packs them
-into one flat buffer -> one NCCL all-reduce (AVG) -> unpack, instead of DDP's 25 MB buckets.  The model is
+trainable gradients (LoRA A/B + t5_proj, 78 MB fp32) once per optimiser step.  The backward kernels write them into
+one flat buffer, so GradAllReducer issues one in-place NCCL all-reduce (AVG) instead of DDP's 25 MB buckets.  The model is
 also compatible with torch DDP itself (gradients are handed to autograd, see blip2_mr._HandOverGrads)."""
 import datetime
 import os
@@ -34,24 +34,42 @@ def is_dist():
 
 
 class GradAllReducer:
-    """Flat-buffer gradient averaging over the trainable parameters."""
+    """Gradient averaging over the trainable parameters with ONE all-reduce.  When the model keeps its gradients in one
+    flat buffer (BLIP2_MR.flat_grads(): every .grad is a view of it) that buffer is reduced in place; otherwise the
+    gradients are packed into a flat staging buffer, reduced and copied back."""
 
-    def __init__(self, params):
+    def __init__(self, params, flat_fn=None):
         self.params = [p for p in params if p.requires_grad]
-        n = sum(p.numel() for p in self.params)
-        self.flat = torch.zeros(n, dtype=torch.float32, device=self.params[0].device) if self.params else None
-        self.views, off = [], 0
-        for p in self.params:
-            self.views.append(self.flat[off:off + p.numel()].view_as(p))
-            off += p.numel()
+        self.flat_fn = flat_fn
+        self.flat, self.views = None, []
+
+    def _staging(self):
+        if self.flat is None:
+            n = sum(p.numel() for p in self.params)
+            self.flat = torch.zeros(n, dtype=torch.float32, device=self.params[0].device)
+            off = 0
+            for p in self.params:
+                self.views.append(self.flat[off:off + p.numel()].view_as(p))
+                off += p.numel()
+        return self.flat
 
     def __call__(self):
         if not is_dist() or not self.params:
             return
+        world = dist.get_world_size()
+        flat = self.flat_fn() if self.flat_fn is not None else None
+        if flat is not None:                                 # zero-copy: the .grad tensors alias `flat`
+            if dist.get_backend() == "nccl":
+                dist.all_reduce(flat, op=dist.ReduceOp.AVG)
+            else:
+                dist.all_reduce(flat, op=dist.ReduceOp.SUM)
+                flat.div_(world)
+            return
+        flat = self._staging()
         grads = [p.grad if p.grad is not None else torch.zeros_like(p) for p in self.params]
         torch._foreach_copy_(self.views, grads)
-        dist.all_reduce(self.flat, op=dist.ReduceOp.SUM)
-        self.flat.div_(dist.get_world_size())
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM)
+        flat.div_(world)
         for p, v in zip(self.params, self.views):
             if p.grad is None:
                 p.grad = v.clone()

@@ -167,6 +167,12 @@ def lora_down(x_ext, A, M, K, R):
     _lib.call("mrb_lora_down", x_ext.data_ptr(), x_ext.stride(0), A.data_ptr(), M, K, R, _DT[x_ext.dtype], _stream())
 
 
+def lora_pack(table, n, blocks_per_linear):
+    """table: int64 [n, 13] device array of LoraPackDesc records (T5Engine.refresh)."""
+    _check(table, torch.int64)
+    _lib.call("mrb_lora_pack", table.data_ptr(), n, blocks_per_linear, BF16, _stream())
+
+
 def skinny_wgrad(P, ldp, Q, ldq, M, C, out, transposed_out, dtype, impl="auto"):
     """out (+)= P[M,C]^T . Q[M,8]; tensor-core kernel for large M (Q then needs 16 readable columns), CUDA-core otherwise."""
     tc = impl == "tc" or (impl == "auto" and M >= 1024)

@@ -67,6 +67,7 @@ class LoraGroup:
         self.refresh()
 
     def refresh(self):
+        """Copy the (updated) LoRA A/B of this group into their 16-bit slots; T5Engine.refresh does all groups in one launch."""
         src = []
         for j in range(self.n):
             b = self.B_params[j].detach()
@@ -75,6 +76,29 @@ class LoraGroup:
             a = self.A_params[j].detach()
             src += [b, b.t(), a, a.t()]
         torch._foreach_copy_(self._dst, src)
+
+    def pack_records(self):
+        """One LoraPackDesc (csrc/elementwise.cu) per Linear of the group: 13 x int64."""
+        import numpy as np
+        recs = []
+        for j in range(self.n):
+            ext_slot, bdown_slot, adown_slot, extb_slot = self._dst[4 * j:4 * j + 4]
+            a, b = self.A_params[j], self.B_params[j]
+            assert a.is_contiguous() and b.is_contiguous() and a.dtype == torch.float32 and b.dtype == torch.float32
+            recs.append([a.data_ptr(), b.data_ptr(), ext_slot.data_ptr(), self.ext.stride(0), bdown_slot.data_ptr(),
+                         self.B_down.stride(0), adown_slot.data_ptr(), self.A_down.stride(0), extb_slot.data_ptr(),
+                         self.ext_b.stride(0), self.K, self.Ns[j], int(np.float64(self.scale).view(np.int64))])
+        return recs
+
+    def bind_grads(self, flat, off):
+        """Re-point dA/dB at consecutive views of one flat fp32 buffer (order = grads()). -> new offset."""
+        for j in range(self.n):
+            nA, nB = 8 * self.K, self.Ns[j] * 8
+            self.dA[j] = flat[off:off + nA].view(8, self.K)
+            off += nA
+            self.dB[j] = flat[off:off + nB].view(self.Ns[j], 8)
+            off += nB
+        return off
 
     def down(self, x_ext, M):
         """x_ext[:, K:K+32] = x_ext[:, :K] . A_down^T  (the LoRA down-projections of the Linears in this group)."""
@@ -106,12 +130,19 @@ class LoraGroup:
     def grads(self):
         out = []
         for j in range(self.n):
-            gb = self.dB[j] if self.scale == 1.0 else self.dB[j] * self.scale
-            out += [(self.A_params[j], self.dA[j]), (self.B_params[j], gb)]
+            out += [(self.A_params[j], self.dA[j]), (self.B_params[j], self.dB[j])]
         return out
 
 
 _BUCKET_CACHE = {}
+
+
+def shift_right(labels):
+    """_shift_right (modeling_t5.py:919-948): decoder_start_token_id = pad = 0, -100 -> pad."""
+    dec_ids = torch.zeros_like(labels)
+    dec_ids[:, 1:] = labels[:, :-1]
+    dec_ids.masked_fill_(dec_ids == -100, 0)
+    return dec_ids
 
 
 def _bucket_index(Lq, Lk, bidirectional, num_buckets, max_distance):
@@ -178,11 +209,31 @@ class T5Engine:
         self.dec_bias = _f(get(prefix + "decoder.block.0.layer.0.SelfAttention.relative_attention_bias.weight"))
         self.dec_final_ln = _f(get(prefix + "decoder.final_layer_norm.weight"))
         self.lm_head = grp([prefix + "lm_head"])
+        self._pack_table = None
 
     # ------------------------------------------------------------------ helpers
     def refresh(self):
+        """Re-pack every LoRA A/B after an optimiser step: one kernel over a device-resident descriptor table."""
+        if self._pack_table is None:
+            import numpy as np
+            recs = [r for g in self.groups for r in g.pack_records()]
+            self._pack_table = torch.from_numpy(np.asarray(recs, dtype=np.int64)).to("cuda")
+            self._pack_blocks = max(1, (max(max(g.K, max(g.Ns)) for g in self.groups) + 2047) // 2048)
+        ops.lora_pack(self._pack_table, self._pack_table.shape[0], self._pack_blocks)
+
+    def n_grad_elems(self):
+        return sum(8 * g.K + 8 * n for g in self.groups for n in g.Ns)
+
+    def bind_grads(self, flat, off=0):
         for g in self.groups:
-            g.refresh()
+            off = g.bind_grads(flat, off)
+        return off
+
+    def scale_grads(self):
+        """dB of a LoRA with alpha != r carries the alpha / r factor (no-op for the reference's alpha = r = 8)."""
+        for g in self.groups:
+            if g.scale != 1.0:
+                torch._foreach_mul_(list(g.dB), g.scale)
 
     def zero_grads(self):
         for g in self.groups:
@@ -379,17 +430,20 @@ class T5Engine:
         """T5ForConditionalGeneration.forward with labels (modeling_t5.py:1734-1893).
         inputs_embeds fp32 [B, Le, D] (cuda), attention_mask [B, Le], labels int64 [B, Ld] (-100 = ignore).
         -> dict(loss [1] fp32, logits?, d_inputs_embeds?)   and LoRA grads accumulated in the groups."""
-        d = self.d
-        B, Le, D = inputs_embeds.shape
-        Ld = labels.shape[1]
-        x = inputs_embeds.reshape(B * Le, D).contiguous()
         kmask = attention_mask.to(device="cuda", dtype=torch.int32).contiguous()
         labels = labels.to("cuda")
         dmask = (decoder_attention_mask.to(device="cuda", dtype=torch.int32).contiguous()
                  if decoder_attention_mask is not None else None)
-        dec_ids = torch.zeros_like(labels)                   # _shift_right, modeling_t5.py:919-948
-        dec_ids[:, 1:] = labels[:, :-1]
-        dec_ids.masked_fill_(dec_ids == -100, 0)
+        return self.loss_device(inputs_embeds, kmask, labels, shift_right(labels), dmask, backward, want_logits)
+
+    def loss_device(self, inputs_embeds, kmask, labels, dec_ids, dmask, backward=True, want_logits=False, loss_out=None):
+        """Device half of loss(): every argument already lives on the GPU (kmask / dmask int32, labels / dec_ids int64) and
+        nothing below synchronises with the host, so the whole call can be captured into a CUDA graph.  The mean over the
+        valid targets is taken on the device (mrb_cross_entropy, gscale < 0).  loss_out: optional fp32 [1] to write into."""
+        d = self.d
+        B, Le, D = inputs_embeds.shape
+        Ld = labels.shape[1]
+        x = inputs_embeds.reshape(B * Le, D).contiguous()
         enc_saves = [] if backward else None
         dec_saves = [] if backward else None
         enc_ext, enc_h, enc_bias = self.encoder_forward(x, kmask, B, Le, enc_saves)
@@ -397,10 +451,10 @@ class T5Engine:
         M = B * Ld
         logits = self.lm_head.forward(dec_ext, M, out_dtype=torch.float32)       # [M, V] fp32
         flat = labels.reshape(-1).contiguous()
-        n_valid = int((flat != -100).sum().item())
-        loss = torch.zeros((1,), dtype=torch.float32, device="cuda")
+        loss = loss_out if loss_out is not None else torch.empty((1,), dtype=torch.float32, device="cuda")
+        loss.zero_()
         dlogits = self._ext(M, d.vocab) if backward else None
-        ops.cross_entropy(logits, flat, None, dlogits, 1.0 / max(n_valid, 1), loss_sum=loss)
+        ops.cross_entropy(logits, flat, None, dlogits, -1.0, loss_sum=loss)
         out = {"loss": loss}
         if want_logits:
             out["logits"] = logits.view(B, Ld, d.vocab)
@@ -409,6 +463,7 @@ class T5Engine:
             ddec = self.lm_head.backward(dlogits, dec_ext, M)
             d_enc = self.decoder_backward(dec_saves, dec_h, ddec, dmask, enc_ext, kmask, B, Ld, Le, dec_bias)
             d_in = self.encoder_backward(enc_saves, enc_h, d_enc, kmask, B, Le, enc_bias)
+            self.scale_grads()
             out["d_inputs_embeds"] = d_in.view(B, Le, D)
         return out
 

@@ -33,6 +33,12 @@ def _worker(rank, world, port, out):
     red()
     ok = torch.allclose(params[0].grad, torch.full((8, 16), 1.5)) and torch.allclose(params[1].grad, torch.arange(5.0) / 2)
     ok = ok and params[2].grad is None
+    # zero-copy path: every .grad is a view of one flat buffer (what BLIP2_MR.flat_grads() hands to the reducer)
+    flat = torch.arange(8 * 16 + 5, dtype=torch.float32) * (rank + 1)
+    params[0].grad, params[1].grad = flat[:128].view(8, 16), flat[128:]
+    mdist.GradAllReducer(params, flat_fn=lambda: flat)()
+    want = torch.arange(8 * 16 + 5, dtype=torch.float32) * 1.5
+    ok = ok and torch.allclose(flat, want) and torch.allclose(params[0].grad.reshape(-1), want[:128])
     out[rank] = bool(ok)
     dist.barrier()
     dist.destroy_process_group()

@@ -90,6 +90,29 @@ def test_prompt_table_matches_oracle_layout(tiny_sd):
     assert prompts[0].startswith(">") and prompts[0].count(">") == 5
 
 
+def test_host_phase_bucket_padding_is_masked(tiny_sd):
+    """Host half of a training step: padding Le / Ld up to the CUDA-graph bucket only appends masked pad tokens and
+    ignored (-100) targets; the decoder input is the reference's _shift_right of the labels."""
+    from mr_blip_b200.blip2_mr import BLIP2_MR
+    from oracle import synth
+    m = BLIP2_MR(dims=TINY, state_dict={k: v for k, v in tiny_sd.items()})
+    s = synth.make_samples(batch=2, frames=3, seed=8)
+    h0, h1 = m._host_phase(s), m._host_phase(s, bucket=(16, 4))
+    B, Le, Ld = 2, h0["Le"], h0["Ld"]
+    assert h1["Le"] % 16 == 0 and h1["Ld"] % 4 == 0 and 0 <= h1["Le"] - Le < 16 and 0 <= h1["Ld"] - Ld < 4
+    t0, t1 = h0["idx"].reshape(B, Le), h1["idx"].reshape(B, h1["Le"])
+    assert (t1[:, :Le] == t0).all() and (t1[:, Le:] == m.pad_token_id).all()
+    assert (h1["kmask"][:, :Le] == h0["kmask"]).all() and (h1["kmask"][:, Le:] == 0).all()
+    assert (h1["labels"][:, :Ld] == h0["labels"]).all() and (h1["labels"][:, Ld:] == -100).all()
+    assert (h1["dmask"][:, Ld:] == 0).all()
+    lab = torch.from_numpy(h0["labels"]).long()
+    want = torch.zeros_like(lab)
+    want[:, 1:] = lab[:, :-1]
+    want[want == -100] = 0
+    assert torch.equal(torch.from_numpy(h0["dec_ids"]).long(), want) and (h1["dec_ids"][:, :Ld] == h0["dec_ids"]).all()
+    assert all(h1[k].dtype == np.int32 and h1[k].flags["C_CONTIGUOUS"] for k in ("idx", "kmask", "labels", "dec_ids", "dmask"))
+
+
 def test_synthetic_tokenizer_roundtrip_and_number_tokens():
     from mr_blip_b200.tokenizer import SyntheticT5Tokenizer, load_t5_tokenizer
     from mr_blip_b200 import mr_utils

@@ -293,6 +293,10 @@ def test_cross_entropy(ops):
     assert abs(row_loss.sum().item() / n_valid - want.item()) < 1e-4
     assert abs(loss.item() - want.item()) < 1e-4
     _close(dl, lg.grad, 1e-2, 1e-7, "dlogits")
+    # gscale < 0: the mean over valid targets is taken on the device (graph-capturable step)
+    dl2, loss2 = torch.zeros_like(dl), torch.zeros(1, device="cuda")
+    ops.cross_entropy(logits, labels, None, dl2, -1.0, loss_sum=loss2)
+    assert abs(loss2.item() - want.item()) < 1e-4 and torch.equal(dl2, dl)
 
 
 def test_lora_down_and_wgrad(ops):
@@ -326,6 +330,14 @@ def test_lora_down_and_wgrad(ops):
     dA = torch.zeros((8, K), dtype=torch.float32, device="cuda")
     ops.skinny_wgrad(x.data_ptr(), x.stride(0), dy[:, 8:16].contiguous().data_ptr(), 8, M, K, dA, True, ops.BF16, impl="cc")
     _close(dA, dy[:, 8:16].float().t() @ x[:, :K].float(), 1e-3, 1e-3, "dA")
+    # decoder-sized M (the no-atomics kernel): accumulates into a non-zero output, ragged C, both layouts
+    for Ms, C in ((56, 1000), (13, 2048), (256, 72)):
+        P, Q = _rand((Ms, C), torch.bfloat16, 1.0, 40), _rand((Ms, 8), torch.bfloat16, 1.0, 41)
+        for tr in (False, True):
+            o = torch.ones((8, C) if tr else (C, 8), dtype=torch.float32, device="cuda")
+            ops.skinny_wgrad(P.data_ptr(), P.stride(0), Q.data_ptr(), Q.stride(0), Ms, C, o, tr, ops.BF16, impl="cc")
+            want = 1.0 + P.float().t() @ Q.float()
+            _close(o.t() if tr else o, want, 1e-4, 1e-4, "small-M wgrad")
 
 
 def test_casts_transpose_colsum(ops):

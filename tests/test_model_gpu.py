@@ -136,6 +136,80 @@ def test_grad_scaling_and_accumulation(model):
     assert _relfro(p.grad, g1 * 9.0) < 1e-5
 
 
+def _train_grads(model, samples):
+    for q in model.parameters():
+        q.grad = None
+    loss = model(samples)["loss"]
+    loss.backward()
+    return loss.item(), {n: p.grad.clone() for n, p in model.named_parameters() if p.requires_grad}
+
+
+@pytest.mark.parametrize("agg", [None, "mean"])
+def test_graphed_step_matches_eager_step(model, agg):
+    """The captured CUDA graph of a training step (default path of model(samples) in train mode) reproduces the eager
+    kernel sequence: loss and every gradient, on replays with NEW inputs of the same shape, with the encoder / decoder
+    lengths padded to the graph bucket (masked pads are exact) and after an optimiser-style in-place parameter update."""
+    from oracle import synth
+    model.train()
+    model.frame_token_aggregation = agg
+    a = synth.make_samples(batch=2, frames=3, seed=21)
+    b = synth.make_samples(batch=2, frames=3, seed=22)
+    try:
+        model.cuda_graphs = False
+        want_a, want_b = _train_grads(model, a), _train_grads(model, b)
+        model.cuda_graphs, model.graph_bucket = True, (16, 4)
+        model._steps.clear()
+        for rnd, (s, want) in enumerate([(a, want_a), (b, want_b), (a, want_a), (b, want_b)]):
+            loss, grads = _train_grads(model, s)
+            assert abs(loss - want[0]) < 1e-4, (rnd, loss, want[0])
+            for n, g in grads.items():
+                assert _relfro(g, want[1][n]) < 2e-3, (rnd, n)        # fp32 atomics in the LoRA weight-gradient kernels
+        st = list(model._steps.values())
+        assert len(st) == 1 and st[0].graph is not None and st[0].calls == 4
+        flat = model.flat_grads()                             # every .grad is a view of one buffer -> single all-reduce
+        assert flat is not None and flat.numel() == sum(p.numel() for p in model.parameters() if p.requires_grad)
+        # parameters change in place (optimizer.step): the graph re-packs LoRA / t5_proj itself
+        p = model._get(T5_PREFIX + "encoder.block.0.layer.0.SelfAttention.q.lora_B.default.weight")
+        keep = p.detach().clone()
+        with torch.no_grad():
+            p.add_(0.05)
+        got = _train_grads(model, a)
+        model.cuda_graphs = False
+        want = _train_grads(model, a)
+        with torch.no_grad():
+            p.copy_(keep)
+        assert abs(got[0] - want[0]) < 1e-4 and abs(got[0] - want_a[0]) > 1e-6
+        for n, g in got[1].items():
+            assert _relfro(g, want[1][n]) < 2e-3, n
+    finally:
+        model.cuda_graphs, model.frame_token_aggregation = True, None
+        for q in model.parameters():
+            q.grad = None
+
+
+def test_lora_pack_kernel_matches_copies(model):
+    """mrb_lora_pack (one launch, descriptor table) writes exactly what the per-tensor strided copies write."""
+    _, _, t5 = model.engines()
+    touched = [q for g in t5.groups[:3] + t5.groups[-2:] for q in g.A_params + g.B_params]
+    keep = [q.detach().clone() for q in touched]
+    with torch.no_grad():
+        for q in touched:
+            q.add_(torch.randn_like(q) * 0.01)
+    t5.refresh()
+    got = [(g.ext.clone(), g.ext_b.clone(), g.A_down.clone(), g.B_down.clone()) for g in t5.groups]
+    for g in t5.groups:
+        for buf in (g.ext[:, g.K:], g.ext_b[:, g.N:], g.A_down, g.B_down):
+            buf.zero_()
+        g.refresh()
+    for g, bufs in zip(t5.groups, got):
+        for x, y in zip(bufs, (g.ext, g.ext_b, g.A_down, g.B_down)):
+            assert torch.equal(x, y)
+    with torch.no_grad():
+        for q, k in zip(touched, keep):
+            q.copy_(k)
+    model._weights_changed()
+
+
 def test_generate_vs_oracle_beam_search(model, tiny_sd):
     from oracle import blip2_mr as ob, synth
     from mr_blip_b200.mr_utils import post_process

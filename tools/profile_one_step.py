@@ -13,7 +13,7 @@ model = BLIP2_MR(dims=FULL, state_dict=sd).cuda().train()
 del sd
 samples = synth.make_samples(batch=4, frames=60, query_words=32, seed=100)
 samples["video"] = samples["video"].cuda()
-for _ in range(2):
+for _ in range(3):                      # eager, capture, replay: the profiled step replays the CUDA graph (ncu profiles its kernel nodes)
     model(samples)["loss"].backward()
 torch.cuda.synchronize()
 torch.cuda.profiler.start()
