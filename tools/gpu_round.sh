@@ -5,7 +5,7 @@ set -u
 O=gpurun_out
 mkdir -p $O
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.limit --format=csv > $O/smi.txt 2>&1
-( timeout 1200 python -m pytest tests -m gpu -q --maxfail=10 -x --deselect tests/test_model_gpu.py::test_generate_vs_oracle_beam_search 2>&1 | tail -40 ) > $O/pytest.log 2>&1
+( timeout 1200 python -m pytest tests -m gpu -q --maxfail=10 2>&1 | tail -40 ) > $O/pytest.log 2>&1
 tail -5 $O/pytest.log
 ( timeout 600 python tools/step_breakdown.py $O/step_breakdown.json 2>&1 | tail -5 ) > $O/breakdown.log 2>&1
 python tools/print_breakdown.py 2>&1 | head -20
