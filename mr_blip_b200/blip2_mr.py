@@ -481,7 +481,7 @@ class BLIP2_MR(Blip2Base):
         res = {"loss": loss}
         if want_logits:
             res.update(logits=out["logits"], inputs_embeds=out["inputs_embeds"], attention_mask=dev["kmask"].long(),
-                       labels=dev["labels"].long(), qformer=out["qformer"], frames_for_t5=out["frames_for_t5"])
+                       labels=torch.from_numpy(host["labels"]).long(), qformer=out["qformer"], frames_for_t5=out["frames_for_t5"])
         return res
 
     def _t5_proj_grads(self, d_frames, qh, M):

@@ -224,6 +224,186 @@ __global__ void __launch_bounds__(NTHREADS) attn_fwd_kernel(const AttnParams p) 
   }
 }
 
+// ---------------------------------------------------------------- few queries x a few hundred keys (Q-Former cross-attention)
+// Qformer.py:198-268 with encoder_hidden_states: 32 query tokens attend to the 257 ViT tokens of their frame, hd 64, no bias,
+// all-ones mask.  One CTA per (frame, head): the whole K and V (257 x 64 each) are fetched with ONE burst of cp.async (~66 KB
+// in flight per CTA, two CTAs per SM -- the op is a pure HBM stream of the batched K/V projection), the four warps split the
+// keys in 16-key groups, each computes S / softmax partials / P.V for all 32 queries over its keys with mma.sync, and the
+// partial (max, sum, O) triples are merged through shared memory.  No loop-carried barriers, no running rescale.
+constexpr int XQ_MAXG = 5;                    // 16-key groups per warp: Lk <= 4 * 5 * 16 = 320
+template <typename T>
+__global__ void __launch_bounds__(128) attn_xq_kernel(const AttnParams p) {
+  constexpr int HD = 64, LDS = HD + 8, LQ = 32;
+  extern __shared__ __align__(16) uint8_t smem_attn[];
+  const int LkP = (p.Lk + 15) & ~15;
+  T* sQ = reinterpret_cast<T*>(smem_attn);
+  T* sK = sQ + LQ * LDS;
+  T* sV = sK + LkP * LDS;
+  const int b = blockIdx.y, h = blockIdx.x;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t4 = lane & 3;
+  const T* gq = static_cast<const T*>(p.q) + b * p.q_bs + static_cast<long long>(h) * HD;
+  const T* gk = static_cast<const T*>(p.k) + b * p.k_bs + static_cast<long long>(h) * HD;
+  const T* gv = static_cast<const T*>(p.v) + b * p.v_bs + static_cast<long long>(h) * HD;
+  for (int i = threadIdx.x; i < LkP * 8; i += 128) {
+    const int r = i >> 3, c = i & 7;
+    const bool ok = r < p.Lk;
+    cp_async16(smem_u32(sK + r * LDS + c * 8), ok ? gk + static_cast<long long>(r) * p.k_rs + c * 8 : gk, ok);
+    cp_async16(smem_u32(sV + r * LDS + c * 8), ok ? gv + static_cast<long long>(r) * p.v_rs + c * 8 : gv, ok);
+  }
+  for (int i = threadIdx.x; i < LQ * 8; i += 128) {
+    const int r = i >> 3, c = i & 7;
+    const bool ok = r < p.Lq;
+    cp_async16(smem_u32(sQ + r * LDS + c * 8), ok ? gq + static_cast<long long>(r) * p.q_rs + c * 8 : gq, ok);
+  }
+  cp_async_commit();
+  cp_async_wait<0>();
+  __syncthreads();
+
+  // this warp's contiguous range of 16-key groups
+  const int NG = LkP >> 4, base = NG >> 2, rem = NG & 3;
+  const int ng = base + (warp < rem ? 1 : 0);
+  const int g0 = warp * base + min(warp, rem);
+  const T* cK = sK + g0 * 16 * LDS;
+  const T* cV = sV + g0 * 16 * LDS;
+
+  float sc[2][2 * XQ_MAXG][4];
+#pragma unroll
+  for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+    for (int nb = 0; nb < 2 * XQ_MAXG; ++nb) sc[mt][nb][0] = sc[mt][nb][1] = sc[mt][nb][2] = sc[mt][nb][3] = 0.f;
+#pragma unroll
+  for (int kk = 0; kk < HD / 16; ++kk) {
+    uint32_t qf[2][4];
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+      ldsm_x4(qf[mt], smem_u32(sQ + (mt * 16 + (lane & 15)) * LDS + kk * 16 + (lane >> 4) * 8));
+#pragma unroll
+    for (int gi = 0; gi < XQ_MAXG; ++gi) {
+      if (gi < ng) {
+        uint32_t kf[4];
+        ldsm_x4(kf, smem_u32(cK + (gi * 16 + (lane >> 4) * 8 + (lane & 7)) * LDS + kk * 16 + ((lane >> 3) & 1) * 8));
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt) {
+          MmaType<T>::mma(sc[mt][2 * gi], qf[mt], kf[0], kf[1]);
+          MmaType<T>::mma(sc[mt][2 * gi + 1], qf[mt], kf[2], kf[3]);
+        }
+      }
+    }
+  }
+  // softmax partials over this warp's keys (scores in the log2 domain)
+  const float sl2 = p.scale * 1.4426950408889634f;
+  float mx[2][2] = {{-INFINITY, -INFINITY}, {-INFINITY, -INFINITY}}, ls[2][2] = {{0.f, 0.f}, {0.f, 0.f}};
+#pragma unroll
+  for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+    for (int nb = 0; nb < 2 * XQ_MAXG; ++nb) {
+      const int j = (g0 + (nb >> 1)) * 16 + (nb & 1) * 8 + 2 * t4;
+      const bool in = (nb >> 1) < ng;
+      sc[mt][nb][0] = (in && j < p.Lk) ? sc[mt][nb][0] * sl2 : -INFINITY;
+      sc[mt][nb][1] = (in && j + 1 < p.Lk) ? sc[mt][nb][1] * sl2 : -INFINITY;
+      sc[mt][nb][2] = (in && j < p.Lk) ? sc[mt][nb][2] * sl2 : -INFINITY;
+      sc[mt][nb][3] = (in && j + 1 < p.Lk) ? sc[mt][nb][3] * sl2 : -INFINITY;
+      mx[mt][0] = fmaxf(mx[mt][0], fmaxf(sc[mt][nb][0], sc[mt][nb][1]));
+      mx[mt][1] = fmaxf(mx[mt][1], fmaxf(sc[mt][nb][2], sc[mt][nb][3]));
+    }
+#pragma unroll
+  for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      mx[mt][r] = fmaxf(mx[mt][r], __shfl_xor_sync(0xffffffffu, mx[mt][r], 1));
+      mx[mt][r] = fmaxf(mx[mt][r], __shfl_xor_sync(0xffffffffu, mx[mt][r], 2));
+    }
+  uint32_t pf[2][XQ_MAXG][4];
+#pragma unroll
+  for (int mt = 0; mt < 2; ++mt) {
+    const float m0 = mx[mt][0] == -INFINITY ? 0.f : mx[mt][0], m1 = mx[mt][1] == -INFINITY ? 0.f : mx[mt][1];
+#pragma unroll
+    for (int nb = 0; nb < 2 * XQ_MAXG; ++nb) {
+      const float p0 = exp2f(sc[mt][nb][0] - m0), p1 = exp2f(sc[mt][nb][1] - m0);
+      const float p2 = exp2f(sc[mt][nb][2] - m1), p3 = exp2f(sc[mt][nb][3] - m1);
+      ls[mt][0] += p0 + p1;
+      ls[mt][1] += p2 + p3;
+      pf[mt][nb >> 1][(nb & 1) * 2] = MmaType<T>::pack(p0, p1);
+      pf[mt][nb >> 1][(nb & 1) * 2 + 1] = MmaType<T>::pack(p2, p3);
+    }
+  }
+#pragma unroll
+  for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      ls[mt][r] += __shfl_xor_sync(0xffffffffu, ls[mt][r], 1);
+      ls[mt][r] += __shfl_xor_sync(0xffffffffu, ls[mt][r], 2);
+    }
+  // O partial = P V over this warp's keys
+  float oa[2][HD / 8][4];
+#pragma unroll
+  for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+    for (int i = 0; i < HD / 8; ++i) oa[mt][i][0] = oa[mt][i][1] = oa[mt][i][2] = oa[mt][i][3] = 0.f;
+#pragma unroll
+  for (int gi = 0; gi < XQ_MAXG; ++gi) {
+    if (gi < ng) {
+#pragma unroll
+      for (int db = 0; db < HD / 16; ++db) {
+        uint32_t vf[4];
+        ldsm_x4_t(vf, smem_u32(cV + (gi * 16 + ((lane >> 3) & 1) * 8 + (lane & 7)) * LDS + db * 16 + (lane >> 4) * 8));
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt) {
+          MmaType<T>::mma(oa[mt][2 * db], pf[mt][gi], vf[0], vf[1]);
+          MmaType<T>::mma(oa[mt][2 * db + 1], pf[mt][gi], vf[2], vf[3]);
+        }
+      }
+    }
+  }
+  __syncthreads();                               // every warp is done with K / V: reuse their space for the partials
+  constexpr int LDO = HD + 2;
+  float* sO = reinterpret_cast<float*>(sK);      // [4 warps][32 rows][LDO]
+  float* sM = sO + 4 * LQ * LDO;                 // [4][32] running max (log2 domain), [4][32] sums
+  float* sL = sM + 4 * LQ;
+#pragma unroll
+  for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      const int row = mt * 16 + g + r * 8;
+#pragma unroll
+      for (int nb = 0; nb < HD / 8; ++nb)
+        *reinterpret_cast<float2*>(sO + (warp * LQ + row) * LDO + nb * 8 + 2 * t4) = make_float2(oa[mt][nb][2 * r], oa[mt][nb][2 * r + 1]);
+      if (t4 == 0) { sM[warp * LQ + row] = mx[mt][r]; sL[warp * LQ + row] = ls[mt][r]; }
+    }
+  __syncthreads();
+  {
+    const int row = threadIdx.x >> 2, c0 = (threadIdx.x & 3) * 16;
+    if (row < p.Lq) {
+      float m = -INFINITY;
+#pragma unroll
+      for (int w = 0; w < 4; ++w) m = fmaxf(m, sM[w * LQ + row]);
+      float f[4], L = 0.f;
+#pragma unroll
+      for (int w = 0; w < 4; ++w) {
+        const float mw = sM[w * LQ + row];
+        f[w] = mw == -INFINITY ? 0.f : exp2f(mw - m);
+        L += f[w] * sL[w * LQ + row];
+      }
+      const float inv = L > 0.f ? 1.f / L : 0.f;
+      T* go = static_cast<T*>(p.o) + b * p.o_bs + static_cast<long long>(row) * p.o_rs + static_cast<long long>(h) * HD + c0;
+      uint32_t w8[8];
+#pragma unroll
+      for (int c = 0; c < 16; c += 2) {
+        float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+        for (int w = 0; w < 4; ++w) {
+          const float2 v = *reinterpret_cast<const float2*>(sO + (w * LQ + row) * LDO + c0 + c);
+          a0 = fmaf(f[w], v.x, a0);
+          a1 = fmaf(f[w], v.y, a1);
+        }
+        w8[c >> 1] = MmaType<T>::pack(a0 * inv, a1 * inv);
+      }
+      *reinterpret_cast<uint4*>(go) = make_uint4(w8[0], w8[1], w8[2], w8[3]);
+      *reinterpret_cast<uint4*>(go + 8) = make_uint4(w8[4], w8[5], w8[6], w8[7]);
+    }
+  }
+}
+
 // delta[b,h,i] = sum_d dO[b,i,h,d] * O[b,i,h,d]
 template <typename T>
 __global__ void attn_delta_kernel(const AttnParams p) {
@@ -588,6 +768,17 @@ static int launch_fwd(const AttnParams& p, cudaStream_t s) {
   return MRB_OK;
 }
 
+template <typename T>
+static int launch_xq(const AttnParams& p, cudaStream_t s) {
+  const int LkP = (p.Lk + 15) & ~15;
+  const int smem = (32 + 2 * LkP) * (64 + 8) * 2;
+  static int cfg = 0;
+  if (cfg < smem) { if (int rc = set_smem(attn_xq_kernel<T>, smem)) return rc; cfg = smem; }
+  attn_xq_kernel<T><<<dim3(p.H, p.B), 128, smem, s>>>(p);
+  MRB_CHECK_LAUNCH();
+  return MRB_OK;
+}
+
 template <typename T, int HD>
 static int launch_bwd(const AttnParams& p, cudaStream_t s) {
   {
@@ -639,6 +830,12 @@ extern "C" int mrb_attention_fwd(const void* q, long long q_bs, long long q_rs, 
   p.lse = lse;
   if (int rc = check_attn(p, dtype)) return rc;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
+  // few queries x a few hundred keys, no bias / mask (Q-Former cross-attention): one-shot K/V fetch, keys split over the warps
+  static int use_xq = -1;                 // MRB_ATTN_XQ=0 keeps the generic kernel (A/B measurements)
+  if (use_xq < 0) { const char* e = getenv("MRB_ATTN_XQ"); use_xq = (e && e[0] == '0') ? 0 : 1; }
+  if (use_xq && hd == 64 && Lq <= 32 && Lk > 64 && Lk <= 16 * 4 * XQ_MAXG && !bias && !kmask && !causal && !lse && p.kv_div == 1 &&
+      4 * 32 * (64 + 2) * 4 + 8 * 32 * 4 <= ((Lk + 15) & ~15) * (64 + 8) * 2)
+    return dtype == MRB_DT_F16 ? launch_xq<__half>(p, s) : launch_xq<__nv_bfloat16>(p, s);
   if (dtype == MRB_DT_F16) return hd <= 64 ? launch_fwd<__half, 64>(p, s) : launch_fwd<__half, 96>(p, s);
   return hd <= 64 ? launch_fwd<__nv_bfloat16, 64>(p, s) : launch_fwd<__nv_bfloat16, 96>(p, s);
 }

@@ -18,6 +18,8 @@ struct Gemm2Params {
   const float* resid; long long ldr;
   void* out; int out_dtype; long long ldc;
   int row_group;
+  int sem_cluster;          // 1: cluster-scope acquire / release on the mbarrier waits / remote arrives (old behaviour; costs a
+                            //    CCTL.IVALL per wait and a MEMBAR + ERRBAR per arrive: profiles/ncu_gemm2_fc1_r01b); 0: CTA scope
   int tail;                 // 1: the last column tile runs a narrower MMA (MRB_GEMM2_TAIL=0 disables, for A/B runs)
 };
 
@@ -61,8 +63,9 @@ __device__ __forceinline__ void umma2_commit_mc(uint64_t* bar) {   // arrive on 
   asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
                ::"r"(smem_u32(bar)), "h"(static_cast<uint16_t>(3)) : "memory");
 }
-__device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr, int sem_cluster) {
+  if (sem_cluster) asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+  else asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 __device__ __forceinline__ bool mbar_try_wait_cluster(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
@@ -73,7 +76,11 @@ __device__ __forceinline__ bool mbar_try_wait_cluster(uint64_t* bar, uint32_t pa
       : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
   return ok != 0;
 }
-__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
+// The pair's barriers carry no generic-memory data: operands arrive through the async proxy (TMA complete_tx), accumulators
+// through tcgen05.commit / tcgen05.fence.  CTA-scope acquire (the PTX default, what CUTLASS's ClusterBarrier uses) is enough;
+// cluster scope makes every successful wait invalidate L1 (CCTL.IVALL) in the single-thread TMA / MMA issue loops.
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity, int sem_cluster) {
+  if (!sem_cluster) { mbar_wait(bar, parity); return; }
   if (mbar_try_wait_cluster(bar, parity)) return;
   long long t0 = clock64();
   uint32_t spins = 0;
@@ -156,7 +163,7 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         tile_coords2(t, p.m_tiles, p.n_tiles, tm, tn);
         const int b_row = tn * G2_BN + static_cast<int>(rank) * (tile_n_mma(p, tn) / 2);   // this CTA's half of the (tail) tile
         for (int kb = 0; kb < k_blocks; ++kb) {
-          mbar_wait_cluster(&empty_bar[stage], phase ^ 1);
+          mbar_wait_cluster(&empty_bar[stage], phase ^ 1, p.sem_cluster);
           uint8_t* sa = smem + stage * G2_STAGE;
           const uint32_t lbar = map_to_cta(smem_u32(&full_bar[stage]), 0);
           if (leader) mbar_expect_tx(&full_bar[stage], 2 * G2_STAGE);
@@ -180,11 +187,11 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         const uint32_t idesc = n_mma == G2_BN ? idesc_full : umma_idesc_f16(p.dtype == MRB_DT_BF16 ? 1 : 0, 256, n_mma);
         const int as = it & 1;
         const uint32_t aphase = (it >> 1) & 1;
-        mbar_wait_cluster(&tmem_empty[as], aphase ^ 1);
+        mbar_wait_cluster(&tmem_empty[as], aphase ^ 1, p.sem_cluster);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + as * G2_BN;
         for (int kb = 0; kb < k_blocks; ++kb) {
-          mbar_wait_cluster(&full_bar[stage], phase);
+          mbar_wait_cluster(&full_bar[stage], phase, p.sem_cluster);
           tc_fence_after();
           if (lane == 0) {
             const uint32_t a_addr = smem_u32(smem + stage * G2_STAGE);
@@ -218,7 +225,7 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
       const int half = tile_n_mma(p, tn) / 2;             // multiple of 32: each warp group takes half of the tile's columns
       const int c_begin = eg * half, c_end = c_begin + half;
       const int m_base = tm * 256 + static_cast<int>(rank) * G2_BM + quad * 32;
-      mbar_wait_cluster(&tmem_full[as], aphase);
+      mbar_wait_cluster(&tmem_full[as], aphase, p.sem_cluster);
       tc_fence_after();
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + as * G2_BN;
       // One 32 x 32 fp32 chunk: TMEM registers (row per thread) -> XOR-swizzled staging -> 4 rows x 128 B per warp instruction
@@ -283,18 +290,18 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
             epi_prefetch(c_begin + ci * 32, rr, b4);
             tmem_ld_wait();
             if (ci + 1 < nch) tmem_ld_32x32b_x32(t_row + c_begin + (ci + 1) * 32, rb);
-            else { tc_fence_before(); __syncwarp(); if (lane == 0) mbar_arrive_remote(as ? empty_remote1 : empty_remote0); }
+            else { tc_fence_before(); __syncwarp(); if (lane == 0) mbar_arrive_remote(as ? empty_remote1 : empty_remote0, p.sem_cluster); }
             epi_chunk(ra, c_begin + ci * 32, rr, b4);
           }
           if (ci + 1 < nch) {
             epi_prefetch(c_begin + (ci + 1) * 32, rr, b4);
             tmem_ld_wait();
             if (ci + 2 < nch) tmem_ld_32x32b_x32(t_row + c_begin + (ci + 2) * 32, ra);
-            else { tc_fence_before(); __syncwarp(); if (lane == 0) mbar_arrive_remote(as ? empty_remote1 : empty_remote0); }
+            else { tc_fence_before(); __syncwarp(); if (lane == 0) mbar_arrive_remote(as ? empty_remote1 : empty_remote0, p.sem_cluster); }
             epi_chunk(rb, c_begin + (ci + 1) * 32, rr, b4);
           }
         }
-        if (nch == 0) { tc_fence_before(); __syncwarp(); if (lane == 0) mbar_arrive_remote(as ? empty_remote1 : empty_remote0); }
+        if (nch == 0) { tc_fence_before(); __syncwarp(); if (lane == 0) mbar_arrive_remote(as ? empty_remote1 : empty_remote0, p.sem_cluster); }
         continue;
       }
 #pragma unroll 1
@@ -309,7 +316,7 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive_remote(as ? empty_remote1 : empty_remote0);
+      if (lane == 0) mbar_arrive_remote(as ? empty_remote1 : empty_remote0, p.sem_cluster);
     }
   }
 
@@ -337,8 +344,11 @@ extern "C" int mrb_gemm2_launch(const CUtensorMap* tmA, const CUtensorMap* tmB, 
     if (e != cudaSuccess) return mrb_set_error(e);
     configured = true;
   }
-  static int pipe = -1;                   // MRB_GEMM2_EPI=plain selects the unpipelined epilogue (A/B measurements)
-  if (pipe < 0) { const char* e = getenv("MRB_GEMM2_EPI"); pipe = (e && e[0] == 'p' && e[1] == 'l') ? 0 : 1; }
+  static int pipe = -1;                   // MRB_GEMM2_EPI=pipe selects the software-pipelined epilogue (A/B measurements)
+  if (pipe < 0) { const char* e = getenv("MRB_GEMM2_EPI"); pipe = (e && e[0] == 'p' && e[1] == 'i') ? 1 : 0; }
+  static int semc = -1;                   // MRB_GEMM2_SEM=cluster restores cluster-scope barrier semantics (A/B measurements)
+  if (semc < 0) { const char* e = getenv("MRB_GEMM2_SEM"); semc = (e && e[0] == 'c') ? 1 : 0; }
+  p.sem_cluster = semc;
   Gemm2Params p;
   p.M = M; p.N = N; p.K = K;
   p.m_tiles = (M + 255) / 256;
