@@ -109,6 +109,10 @@ int mrb_skinny_wgrad(const void* P, long long ldp, const void* Q, long long ldq,
  * Q needs >= 16 readable columns per row. */
 int mrb_skinny_wgrad_tc(const void* P, long long ldp, const void* Q, long long ldq, int M, int C, float* out,
                         int transposed_out, int dtype, void* stream);
+/* Same pass over P for two adjacent LoRA slots: out += P^T Q[:, 0:8], out2 += P^T Q[:, 8:16] (q|k|v, wi_0|wi_1 and the
+ * cross k|v Linears share one input, so their dA reductions share the read of x). */
+int mrb_skinny_wgrad_tc2(const void* P, long long ldp, const void* Q, long long ldq, int M, int C, float* out, float* out2,
+                         int transposed_out, int dtype, void* stream);
 /* out[m, r] = sum_k x[m,k] W[r,k], r < 32, 16-bit: LoRA down-projection when M is tiny (decoder); larger M use mrb_gemm */
 int mrb_small_down(const void* x, long long ldx, const void* W, long long ldw, int M, int K, void* out, long long ldo,
                    int dtype, void* stream);

@@ -35,6 +35,7 @@ SIGNATURES = {
     "mrb_lora_down": [_p, _ll, _p, _i, _i, _i, _i, _p],
     "mrb_skinny_wgrad": [_p, _ll, _p, _ll, _i, _i, _p, _i, _i, _p],
     "mrb_skinny_wgrad_tc": [_p, _ll, _p, _ll, _i, _i, _p, _i, _i, _p],
+    "mrb_skinny_wgrad_tc2": [_p, _ll, _p, _ll, _i, _i, _p, _p, _i, _i, _p],
     "mrb_lora_pack": [_p, _i, _i, _i, _p],
     "mrb_small_down": [_p, _ll, _p, _ll, _i, _i, _p, _ll, _i, _p],
     "mrb_cast_f32_to_h": [_p, _p, _ll, _i, _p],

@@ -348,7 +348,6 @@ extern "C" int mrb_gemm2_launch(const CUtensorMap* tmA, const CUtensorMap* tmB, 
   if (pipe < 0) { const char* e = getenv("MRB_GEMM2_EPI"); pipe = (e && e[0] == 'p' && e[1] == 'i') ? 1 : 0; }
   static int semc = -1;                   // MRB_GEMM2_SEM=cluster restores cluster-scope barrier semantics (A/B measurements)
   if (semc < 0) { const char* e = getenv("MRB_GEMM2_SEM"); semc = (e && e[0] == 'c') ? 1 : 0; }
-  p.sem_cluster = semc;
   Gemm2Params p;
   p.M = M; p.N = N; p.K = K;
   p.m_tiles = (M + 255) / 256;
@@ -358,6 +357,7 @@ extern "C" int mrb_gemm2_launch(const CUtensorMap* tmA, const CUtensorMap* tmB, 
   static int tail = -1;
   if (tail < 0) { const char* e = getenv("MRB_GEMM2_TAIL"); tail = (e && e[0] == '0') ? 0 : 1; }
   p.tail = tail;
+  p.sem_cluster = semc;
   const int tiles = p.m_tiles * p.n_tiles;
   int pairs = num_sms / 2;
   if (tiles < pairs) pairs = tiles;

@@ -11,6 +11,7 @@ namespace mrb {
 struct WgradParams {
   int M, C, rows_per_cta;
   float* out;
+  float* out2;              // optional: columns 8..15 of Q (the next LoRA slot of the same group) accumulate here
   int transposed_out, dtype;
 };
 
@@ -112,6 +113,14 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constant__
         if (p.transposed_out) atomicAdd(p.out + static_cast<long long>(j) * p.C + c, v);
         else atomicAdd(p.out + static_cast<long long>(c) * 8 + j, v);
       }
+      if (p.out2) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float v = __uint_as_float(r[8 + j]);
+          if (p.transposed_out) atomicAdd(p.out2 + static_cast<long long>(j) * p.C + c, v);
+          else atomicAdd(p.out2 + static_cast<long long>(c) * 8 + j, v);
+        }
+      }
     }
   }
   tc_fence_before();
@@ -155,8 +164,15 @@ static int wg_tmap(CUtensorMap* map, const void* base, int dtype, long long rows
 using namespace mrb;
 
 // Q must have at least 16 readable 16-bit columns per row starting at its pointer (the extended [.., +32] buffers do).
+extern "C" int mrb_skinny_wgrad_tc2(const void* P, long long ldp, const void* Q, long long ldq, int M, int C, float* out,
+                                    float* out2, int transposed_out, int dtype, void* stream);
 extern "C" int mrb_skinny_wgrad_tc(const void* P, long long ldp, const void* Q, long long ldq, int M, int C, float* out,
                                    int transposed_out, int dtype, void* stream) {
+  return mrb_skinny_wgrad_tc2(P, ldp, Q, ldq, M, C, out, nullptr, transposed_out, dtype, stream);
+}
+// Two adjacent LoRA slots in one pass over P: out += P^T Q[:, 0:8], out2 += P^T Q[:, 8:16] (out2 may be NULL).
+extern "C" int mrb_skinny_wgrad_tc2(const void* P, long long ldp, const void* Q, long long ldq, int M, int C, float* out,
+                                    float* out2, int transposed_out, int dtype, void* stream) {
   if (M <= 0 || C <= 0) return MRB_OK;
   if ((ldp & 7) || (ldq & 7) || (C & 7) || ((reinterpret_cast<uintptr_t>(P) | reinterpret_cast<uintptr_t>(Q)) & 15)) return MRB_ERR_ARG;
   static int sms = 0;
@@ -181,7 +197,7 @@ extern "C" int mrb_skinny_wgrad_tc(const void* P, long long ldp, const void* Q, 
   WgradParams p;
   p.M = M; p.C = C;
   p.rows_per_cta = ((k_blocks + splits - 1) / splits) * WG_BK;
-  p.out = out; p.transposed_out = transposed_out; p.dtype = dtype;
+  p.out = out; p.out2 = out2; p.transposed_out = transposed_out; p.dtype = dtype;
   dim3 grid(c_tiles, (M + p.rows_per_cta - 1) / p.rows_per_cta);
   wgrad_tc_kernel<<<grid, 192, WG_SMEM, static_cast<cudaStream_t>(stream)>>>(tmP, tmQ, p);
   MRB_CHECK_LAUNCH();

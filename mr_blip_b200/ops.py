@@ -179,6 +179,11 @@ def skinny_wgrad(P, ldp, Q, ldq, M, C, out, transposed_out, dtype, impl="auto"):
     _lib.call("mrb_skinny_wgrad_tc" if tc else "mrb_skinny_wgrad", P, ldp, Q, ldq, M, C, out.data_ptr(), int(transposed_out), dtype, _stream())
 
 
+def skinny_wgrad_pair(P, ldp, Q, ldq, M, C, out, out2, transposed_out, dtype):
+    """Tensor-core pass over P for two adjacent 8-column slots of Q: out += P^T Q[:, :8], out2 += P^T Q[:, 8:16]."""
+    _lib.call("mrb_skinny_wgrad_tc2", P, ldp, Q, ldq, M, C, out.data_ptr(), out2.data_ptr(), int(transposed_out), dtype, _stream())
+
+
 def down32(x, W, out, M):
     """out[:, :32] = x[:M] . W^T for a 32-row 16-bit W: tensor-core GEMM, or the one-block-per-row kernel for tiny M."""
     if M >= 256:

@@ -119,8 +119,16 @@ class LoraGroup:
             o, n_ = self.offs[j], self.Ns[j]
             ops.skinny_wgrad(dy_ext.data_ptr() + o * es, dy_ext.stride(0), x_ext.data_ptr() + (K + 8 * j) * es,
                              x_ext.stride(0), M, n_, self.dB[j], False, ops.BF16)
-            ops.skinny_wgrad(x_ext.data_ptr(), x_ext.stride(0), dy_ext.data_ptr() + (N + 8 * j) * es,
-                             dy_ext.stride(0), M, K, self.dA[j], True, ops.BF16)
+        j = 0
+        while j < self.n:                                   # dA_j = (dy sB_j)^T x: two slots per pass over x when M is large
+            q = dy_ext.data_ptr() + (N + 8 * j) * es
+            if M >= 1024 and j + 1 < self.n:
+                ops.skinny_wgrad_pair(x_ext.data_ptr(), x_ext.stride(0), q, dy_ext.stride(0), M, K, self.dA[j],
+                                      self.dA[j + 1], True, ops.BF16)
+                j += 2
+            else:
+                ops.skinny_wgrad(x_ext.data_ptr(), x_ext.stride(0), q, dy_ext.stride(0), M, K, self.dA[j], True, ops.BF16)
+                j += 1
         return dx
 
     def zero_grads(self):

@@ -326,6 +326,12 @@ def test_lora_down_and_wgrad(ops):
         ops.skinny_wgrad(dy.data_ptr(), dy.stride(0), xa.data_ptr(), x.stride(0), M, N, o, tr, ops.BF16, impl="tc")
         want = dy.float().t() @ xa.float()
         _close(o.t() if tr else o, want, 2e-3, 2e-3, "dB tc")
+    # two adjacent slots in one pass (dA of q|k, wi_0|wi_1, cross k|v)
+    q16 = _rand((M, 32), torch.bfloat16, 1.0, 43)
+    o1, o2 = torch.zeros((8, N), dtype=torch.float32, device="cuda"), torch.zeros((8, N), dtype=torch.float32, device="cuda")
+    ops.skinny_wgrad_pair(dy.data_ptr(), dy.stride(0), q16.data_ptr() + 16, q16.stride(0), M, N, o1, o2, True, ops.BF16)
+    _close(o1.t(), dy.float().t() @ q16[:, 8:16].float(), 2e-3, 2e-3, "pair slot 0")
+    _close(o2.t(), dy.float().t() @ q16[:, 16:24].float(), 2e-3, 2e-3, "pair slot 1")
     # small-M down-projection kernel
     Wd = _rand((32, K), torch.bfloat16, 0.05, 39)
     xs = x[:56]

@@ -1,6 +1,6 @@
 #!/bin/bash
 # One GPU-box visit: parity tests, GEMM sweeps per kernel variant, step breakdown (graph + eager), bench line,
-# ncu launch list of one graph-replayed step, ncu --set full of the fc1 GEMM.  Everything lands in gpurun_out/.
+# ncu --set full of the fc1 GEMM.  Everything lands in gpurun_out/.
 set -u
 O=gpurun_out
 mkdir -p $O
@@ -9,12 +9,8 @@ tail -5 $O/pytest.log
 ( timeout 300 python tools/gemm_sweep.py default $O/sweep_default.json ) > $O/sweep_default.log 2>&1
 ( MRB_GEMM2_SEM=cluster timeout 300 python tools/gemm_sweep.py sem_cluster $O/sweep_sem_cluster.json ) > $O/sweep_sem_cluster.log 2>&1
 ( MRB_GEMM2_EPI=pipe timeout 300 python tools/gemm_sweep.py epi_pipe $O/sweep_epi_pipe.json ) > $O/sweep_epi_pipe.log 2>&1
-cat $O/sweep_default.log $O/sweep_sem_cluster.log $O/sweep_epi_pipe.log
-( timeout 600 python tools/step_breakdown.py $O/step_breakdown.json 2>&1 | tail -5 ) > $O/breakdown.log 2>&1
-python tools/print_breakdown.py 2>&1 | head -20
+grep -h "vit_\|qf_\|t5_" $O/sweep_default.log $O/sweep_sem_cluster.log $O/sweep_epi_pipe.log
 ( timeout 600 python bench.py --steps 5 --warmup 3 --no-cpu-baseline ) > $O/bench.json 2> $O/bench.err
 cat $O/bench.json; tail -3 $O/bench.err
-( timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off --csv --log-file $O/launches.csv python tools/profile_one_step.py ) > $O/ncu_list.log 2>&1
-tail -2 $O/ncu_list.log; wc -l $O/launches.csv
 ( timeout 600 ncu --set full --clock-control none --import-source on -k regex:gemm2 -s 2 -c 1 -o $O/ncu_fc1 -f python tools/gemm_one.py ) > $O/ncu_fc1.log 2>&1
 tail -3 $O/ncu_fc1.log
