@@ -115,7 +115,10 @@ __device__ __forceinline__ int tile_n_mma(const Gemm2Params& p, int tn) {
   return (rem >= G2_BN || !p.tail) ? G2_BN : ((rem + 63) & ~63);
 }
 
-template <bool PIPE>
+// Epilogue kinds with a specialised fast path (everything else, and every edge tile, takes the generic path)
+enum { EPI_GENERIC = 0, EPI_F16 = 1, EPI_GELU_F16 = 2, EPI_BF16 = 3, EPI_RESID_F32 = 4, EPI_F32 = 5 };
+
+template <int EPI>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(320, 1)
 gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const Gemm2Params p) {
   constexpr uint32_t TMEM_COLS = 512;
@@ -277,31 +280,58 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         b4 = make_float4(0.f, 0.f, 0.f, 0.f);
         if (p.bias && col_ok) b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col));
       };
-      if (PIPE) {
-        // software pipeline over the (up to 4) chunks of this warp: the tcgen05.ld of chunk i+1 is in flight while chunk i
-        // runs its math and stores; the accumulator buffer is handed back to the MMA warp as soon as the last load landed.
-        const int nch = min(half, max(0, p.N - (tn * G2_BN + c_begin)) + 31) / 32;
-        uint32_t ra[32], rb[32];
-        float4 rr[8], b4;
-        if (nch > 0) tmem_ld_32x32b_x32(t_row + c_begin, ra);
+      // ---- fast path (tile rows and columns all inside the matrix, no row remap): the epilogue kind is a template
+      //      parameter, so the per-element code is pure math + one store (no flag tests, no 64-bit index arithmetic, no
+      //      bounds predicates); bias of all four chunks is fetched before the accumulator wait.
+      if (EPI != EPI_GENERIC && p.row_group == 0 && m_base + 32 <= p.M && tn * G2_BN + c_end <= p.N) {
+        constexpr bool GELU = (EPI == EPI_GELU_F16);
+        constexpr bool RESID = (EPI == EPI_RESID_F32);
+        constexpr bool OUT32 = (EPI == EPI_RESID_F32 || EPI == EPI_F32);
+        constexpr int ODT = (EPI == EPI_BF16) ? MRB_DT_BF16 : MRB_DT_F16;
+        const int col0 = tn * G2_BN + c_begin + chunk * 4;
+        const int nch = half >> 5;
+        float4 bz[4];
 #pragma unroll
-        for (int ci = 0; ci < 4; ci += 2) {
+        for (int ci = 0; ci < 4; ++ci)
+          bz[ci] = (p.bias && ci < nch) ? __ldg(reinterpret_cast<const float4*>(p.bias + col0 + ci * 32)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        const long long row0 = m_base + sub_row;
+        const float* rptr = RESID ? p.resid + row0 * p.ldr + col0 : nullptr;
+        char* optr = static_cast<char*>(p.out) + (row0 * p.ldc + col0) * (OUT32 ? 4 : 2);
+        const long long rstep = 4 * p.ldr, ostep = 4 * p.ldc * (OUT32 ? 4 : 2);
+#pragma unroll
+        for (int ci = 0; ci < 4; ++ci) {
           if (ci < nch) {
-            epi_prefetch(c_begin + ci * 32, rr, b4);
+            float4 rr[8];
+            if (RESID) {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) rr[i] = *reinterpret_cast<const float4*>(rptr + i * rstep + ci * 32);
+            }
+            uint32_t r[32];
+            tmem_ld_32x32b_x32(t_row + c_begin + ci * 32, r);
             tmem_ld_wait();
-            if (ci + 1 < nch) tmem_ld_32x32b_x32(t_row + c_begin + (ci + 1) * 32, rb);
-            else { tc_fence_before(); __syncwarp(); if (lane == 0) mbar_arrive_remote(as ? empty_remote1 : empty_remote0, p.sem_cluster); }
-            epi_chunk(ra, c_begin + ci * 32, rr, b4);
-          }
-          if (ci + 1 < nch) {
-            epi_prefetch(c_begin + (ci + 1) * 32, rr, b4);
-            tmem_ld_wait();
-            if (ci + 2 < nch) tmem_ld_32x32b_x32(t_row + c_begin + (ci + 2) * 32, ra);
-            else { tc_fence_before(); __syncwarp(); if (lane == 0) mbar_arrive_remote(as ? empty_remote1 : empty_remote0, p.sem_cluster); }
-            epi_chunk(rb, c_begin + (ci + 1) * 32, rr, b4);
+            __syncwarp();
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              stage4[lane * 8 + (j ^ (lane & 7))] = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]),
+                                                               __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]));
+            __syncwarp();
+            const float4 b4 = bz[ci];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const int rl = i * 4 + sub_row;
+              float4 x = stage4[rl * 8 + (chunk ^ (rl & 7))];
+              x.x += b4.x; x.y += b4.y; x.z += b4.z; x.w += b4.w;
+              if (GELU) { x.x = gelu_erf(x.x); x.y = gelu_erf(x.y); x.z = gelu_erf(x.z); x.w = gelu_erf(x.w); }
+              if (RESID) { x.x += rr[i].x; x.y += rr[i].y; x.z += rr[i].z; x.w += rr[i].w; }
+              char* o = optr + i * ostep + ci * (OUT32 ? 128 : 64);
+              if (OUT32) *reinterpret_cast<float4*>(o) = x;
+              else *reinterpret_cast<uint2*>(o) = make_uint2(pack2(x.x, x.y, ODT), pack2(x.z, x.w, ODT));
+            }
           }
         }
-        if (nch == 0) { tc_fence_before(); __syncwarp(); if (lane == 0) mbar_arrive_remote(as ? empty_remote1 : empty_remote0, p.sem_cluster); }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_remote(as ? empty_remote1 : empty_remote0, p.sem_cluster);
         continue;
       }
 #pragma unroll 1
@@ -328,6 +358,19 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
   }
 }
 
+template <int EPI>
+static int launch2(const CUtensorMap* tmA, const CUtensorMap* tmB, const Gemm2Params& p, int pairs, cudaStream_t st) {
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(gemm2_tcgen05_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, G2_SMEM);
+    if (e != cudaSuccess) return mrb_set_error(e);
+    configured = true;
+  }
+  gemm2_tcgen05_kernel<EPI><<<2 * pairs, 320, G2_SMEM, st>>>(*tmA, *tmB, p);
+  MRB_CHECK_LAUNCH();
+  return MRB_OK;
+}
+
 }  // namespace mrb
 
 using namespace mrb;
@@ -336,18 +379,10 @@ using namespace mrb;
 extern "C" int mrb_gemm2_launch(const CUtensorMap* tmA, const CUtensorMap* tmB, int M, int N, int K, int dtype,
                                 const float* bias, int gelu, const float* resid, long long ldr, void* out, int out_dtype,
                                 long long ldc, int row_group, int num_sms, void* stream) {
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(gemm2_tcgen05_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, G2_SMEM);
-    if (e == cudaSuccess)
-      e = cudaFuncSetAttribute(gemm2_tcgen05_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, G2_SMEM);
-    if (e != cudaSuccess) return mrb_set_error(e);
-    configured = true;
-  }
-  static int pipe = -1;                   // MRB_GEMM2_EPI=pipe selects the software-pipelined epilogue (A/B measurements)
-  if (pipe < 0) { const char* e = getenv("MRB_GEMM2_EPI"); pipe = (e && e[0] == 'p' && e[1] == 'i') ? 1 : 0; }
   static int semc = -1;                   // MRB_GEMM2_SEM=cluster restores cluster-scope barrier semantics (A/B measurements)
   if (semc < 0) { const char* e = getenv("MRB_GEMM2_SEM"); semc = (e && e[0] == 'c') ? 1 : 0; }
+  static int spec = -1;                   // MRB_GEMM2_EPI=generic disables the specialised epilogues (A/B measurements)
+  if (spec < 0) { const char* e = getenv("MRB_GEMM2_EPI"); spec = (e && e[0] == 'g') ? 0 : 1; }
   Gemm2Params p;
   p.M = M; p.N = N; p.K = K;
   p.m_tiles = (M + 255) / 256;
@@ -361,8 +396,21 @@ extern "C" int mrb_gemm2_launch(const CUtensorMap* tmA, const CUtensorMap* tmB, 
   const int tiles = p.m_tiles * p.n_tiles;
   int pairs = num_sms / 2;
   if (tiles < pairs) pairs = tiles;
-  if (pipe) gemm2_tcgen05_kernel<true><<<2 * pairs, 320, G2_SMEM, static_cast<cudaStream_t>(stream)>>>(*tmA, *tmB, p);
-  else gemm2_tcgen05_kernel<false><<<2 * pairs, 320, G2_SMEM, static_cast<cudaStream_t>(stream)>>>(*tmA, *tmB, p);
-  MRB_CHECK_LAUNCH();
-  return MRB_OK;
+  int epi = EPI_GENERIC;
+  if (spec && row_group == 0) {
+    if (resid && !gelu && out_dtype == MRB_DT_F32) epi = EPI_RESID_F32;
+    else if (!resid && !gelu && out_dtype == MRB_DT_F32) epi = EPI_F32;
+    else if (!resid && gelu && out_dtype == MRB_DT_F16) epi = EPI_GELU_F16;
+    else if (!resid && !gelu && out_dtype == MRB_DT_F16) epi = EPI_F16;
+    else if (!resid && !gelu && out_dtype == MRB_DT_BF16) epi = EPI_BF16;
+  }
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  switch (epi) {
+    case EPI_F16: return launch2<EPI_F16>(tmA, tmB, p, pairs, st);
+    case EPI_GELU_F16: return launch2<EPI_GELU_F16>(tmA, tmB, p, pairs, st);
+    case EPI_BF16: return launch2<EPI_BF16>(tmA, tmB, p, pairs, st);
+    case EPI_RESID_F32: return launch2<EPI_RESID_F32>(tmA, tmB, p, pairs, st);
+    case EPI_F32: return launch2<EPI_F32>(tmA, tmB, p, pairs, st);
+    default: return launch2<EPI_GENERIC>(tmA, tmB, p, pairs, st);
+  }
 }

@@ -36,7 +36,8 @@ class LoraGroup:
         backward: dy_ext[:, N:] = dy . B_down^T (= dy.sB) ;  dx = dy_ext . [W^T | A^T]^T   (= dy.W + (dy.sB).A)
     LoRA weight gradients: dB_j = dy_j^T (x A_j^T)  and  dA_j = (dy_j sB_j)^T x  -- both skinny reductions over M."""
 
-    def __init__(self, get, names, scale):
+    def __init__(self, get, names, scale, eng=None):
+        self.eng = eng            # T5Engine: owner of the side stream that runs the weight-gradient reductions
         self.names = names
         Ws = [get(n + ".base_layer.weight") for n in names]
         self.K = K = Ws[0].shape[1]
@@ -113,7 +114,17 @@ class LoraGroup:
         -> dx [M, K] (complete, LoRA term included); accumulates dA_j, dB_j."""
         K, N = self.K, self.N
         ops.down32(dy_ext[:, :N], self.B_down, dy_ext[:, N:], M)
+        if self.eng is not None and self.eng.overlap:
+            # dA / dB feed nothing downstream: reduce them on the side stream while the main stream goes on with dgrad
+            with self.eng.side_block(hold=(dy_ext, x_ext)):
+                self._wgrads(dy_ext, x_ext, M)
+            return ops.gemm(dy_ext, self.ext_b, out=out, resid=resid, out_dtype=out_dtype, M=M)
         dx = ops.gemm(dy_ext, self.ext_b, out=out, resid=resid, out_dtype=out_dtype, M=M)
+        self._wgrads(dy_ext, x_ext, M)
+        return dx
+
+    def _wgrads(self, dy_ext, x_ext, M):
+        K, N = self.K, self.N
         es = 2
         for j in range(self.n):
             o, n_ = self.offs[j], self.Ns[j]
@@ -129,7 +140,6 @@ class LoraGroup:
             else:
                 ops.skinny_wgrad(x_ext.data_ptr(), x_ext.stride(0), q, dy_ext.stride(0), M, K, self.dA[j], True, ops.BF16)
                 j += 1
-        return dx
 
     def zero_grads(self):
         for g in self.dA + self.dB:
@@ -186,8 +196,16 @@ class T5Engine:
         assert self.emb.is_cuda
         self.groups = []
 
+        # Side stream (forked / joined inside the captured step): LoRA weight-gradient reductions and the decoder's
+        # encoder-sized cross-attention K/V GEMMs run next to the latency-bound main chain.  MRB_OVERLAP=0 disables.
+        import os
+        self.overlap = os.environ.get("MRB_OVERLAP", "1") != "0"
+        self.side = torch.cuda.Stream()
+        self._hold = []
+        self._side_open = False
+
         def grp(names):
-            g = LoraGroup(get, names, scale)
+            g = LoraGroup(get, names, scale, self)
             self.groups.append(g)
             return g
 
@@ -218,6 +236,32 @@ class T5Engine:
         self.dec_final_ln = _f(get(prefix + "decoder.final_layer_norm.weight"))
         self.lm_head = grp([prefix + "lm_head"])
         self._pack_table = None
+
+    # ------------------------------------------------------------------ side stream
+    def side_block(self, hold=()):
+        """Context: the enclosed launches go to the side stream, ordered after everything issued so far on the main
+        stream.  `hold` tensors stay referenced until side_join() so the allocator cannot recycle them early."""
+        eng = self
+
+        class _Ctx:
+            def __enter__(self):
+                eng._hold.extend(hold)
+                eng.side.wait_stream(torch.cuda.current_stream())
+                eng._side_open = True
+                self.cm = torch.cuda.stream(eng.side)
+                self.cm.__enter__()
+
+            def __exit__(self, *a):
+                return self.cm.__exit__(*a)
+
+        return _Ctx()
+
+    def side_join(self):
+        """Main stream waits for the side stream; held tensors are released."""
+        if self._side_open:
+            torch.cuda.current_stream().wait_stream(self.side)
+            self._side_open = False
+        self._hold.clear()
 
     # ------------------------------------------------------------------ helpers
     def refresh(self):
@@ -347,6 +391,7 @@ class T5Engine:
                               bias=bias, bias_zero=L - 1, kmask=kmask, causal=False)
             dxn = layer["qkv"].backward(dqkv, s["xn"], M)
             ops.rmsnorm_bwd(s["x"], layer["ln0"], dxn, d.t5_ln_eps, dh)
+            self.side_join()                                 # this layer's weight-gradient reductions are done
             s.clear()
         return dh
 
@@ -358,7 +403,18 @@ class T5Engine:
         h = torch.empty((M, d.d_model), dtype=torch.float32, device="cuda")
         ops.gather_rows(dec_ids.reshape(-1).to(torch.int32), self.emb, None, h)
         bias = self._bias(self.dec_bias, Ld, Ld, False)
-        for layer in self.dec:
+        ckvs, ckv_ready = [], []
+        if self.overlap:
+            # every layer's cross-attention K/V projection of the encoder output (the only encoder-sized GEMMs of the
+            # decoder) depends on enc_ext alone: issue all of them on the side stream, next to the tiny-M main chain
+            ckvs = [self._ext(Me, 2 * inner) for _ in self.dec]
+            with self.side_block(hold=[enc_ext] + ckvs):
+                for layer, ckv in zip(self.dec, ckvs):
+                    layer["ckv"].forward(enc_ext, Me, out=ckv[:, :2 * inner])
+                    ev = torch.cuda.Event()
+                    ev.record()
+                    ckv_ready.append(ev)
+        for li, layer in enumerate(self.dec):
             layer["ln_ff"] = layer["ln2"]
             s = {} if save is not None else None
             xn = self._ext(M, d.d_model)
@@ -375,8 +431,12 @@ class T5Engine:
             ops.norm(h1, layer["ln1"], None, d.t5_ln_eps, 1, out_h=xn2)
             cq = self._ext(M, inner)
             layer["cq"].forward(xn2, M, out=cq[:, :inner])
-            ckv = self._ext(Me, 2 * inner)
-            layer["ckv"].forward(enc_ext, Me, out=ckv[:, :2 * inner])
+            if self.overlap:
+                ckv = ckvs[li]
+                torch.cuda.current_stream().wait_event(ckv_ready[li])
+            else:
+                ckv = self._ext(Me, 2 * inner)
+                layer["ckv"].forward(enc_ext, Me, out=ckv[:, :2 * inner])
             co = self._ext(M, d.d_model)
             lse2 = torch.empty((B, d.t5_heads, Ld), dtype=torch.float32, device="cuda") if save is not None else None
             qs, ks = cq.stride(0), ckv.stride(0)
@@ -391,6 +451,7 @@ class T5Engine:
                 save.append(s)
         out = self._ext(M, d.d_model)
         ops.norm(h, self.dec_final_ln, None, d.t5_ln_eps, 1, out_h=out)
+        self.side_join()
         return out, h, bias
 
     def decoder_backward(self, saves, h_last, d_out, dmask, enc_ext, enc_kmask, B, Ld, Le, bias):
@@ -414,8 +475,17 @@ class T5Engine:
                               d.d_kv, 1.0, (Ld * qs, qs), (Le * ks, ks), (Le * ks, ks),
                               (Ld * s["co"].stride(0), s["co"].stride(0)), (Ld * dco.stride(0), dco.stride(0)), s["lse2"], ws,
                               kmask=enc_kmask)
-            layer["ckv"].down(enc_ext, Me)                   # recompute this layer's x.A^T columns of the shared input
-            layer["ckv"].backward(dckv, enc_ext, Me, out=d_enc, resid=d_enc)     # accumulates over the 24 layers
+            if self.overlap:
+                # encoder-sized dgrad + weight gradients of the cross K/V projection: side stream (in order, d_enc accumulates)
+                with self.side_block(hold=(dckv, enc_ext, d_enc)):
+                    layer["ckv"].down(enc_ext, Me)
+                    g = layer["ckv"]
+                    ops.down32(dckv[:, :g.N], g.B_down, dckv[:, g.N:], Me)
+                    ops.gemm(dckv, g.ext_b, out=d_enc, resid=d_enc, M=Me)
+                    g._wgrads(dckv, enc_ext, Me)
+            else:
+                layer["ckv"].down(enc_ext, Me)               # recompute this layer's x.A^T columns of the shared input
+                layer["ckv"].backward(dckv, enc_ext, Me, out=d_enc, resid=d_enc)     # accumulates over the 24 layers
             dxn2 = layer["cq"].backward(dcq, s["xn2"], M)
             ops.rmsnorm_bwd(s["x1"], layer["ln1"], dxn2, d.t5_ln_eps, dh)
             # self attention
@@ -430,7 +500,9 @@ class T5Engine:
                               bias=bias, bias_zero=Ld - 1, kmask=dmask, causal=True)
             dxn = layer["qkv"].backward(dqkv, s["xn"], M)
             ops.rmsnorm_bwd(s["x"], layer["ln0"], dxn, d.t5_ln_eps, dh)
-            s.clear()
+            if not self.overlap:
+                s.clear()
+        self.side_join()                                     # d_enc is complete; saved activations may go
         return d_enc                                         # (dh = grad of the frozen embedding rows: dropped)
 
     # ------------------------------------------------------------------ loss (+ grads)

@@ -34,6 +34,11 @@ class VitEngine:
         self.patch_w, self.patch_b = pw, _f(get(prefix + "patch_embed.proj.bias"))
         self.cls = _f(get(prefix + "cls_token")).reshape(W)
         self.pos = _f(get(prefix + "pos_embed")).reshape(d.vit_tokens, W)
+        # 257 = 2 x 128 + 1 tokens: the 257th query row runs in a small kernel on a side stream (forked / joined inside the
+        # captured step) next to the tcgen05 kernel that handles the two full tiles.  MRB_OVERLAP=0 disables.
+        import os
+        self.overlap = os.environ.get("MRB_OVERLAP", "1") != "0"
+        self.side = torch.cuda.Stream()
         self.blocks = []
         for i in range(d.vit_depth):
             b = f"{prefix}blocks.{i}."
@@ -69,10 +74,19 @@ class VitEngine:
             rs = 3 * W
             # 257 = 2 x 128 + 1: the first 256 query rows run as two full tcgen05 tiles, the last row in the small kernel
             Tq = (T // 128) * 128 if ops.USE_TC_ATTENTION else 0
+            forked = self.overlap and Tq and Tq == T - 1
+            if forked:
+                main = torch.cuda.current_stream()
+                self.side.wait_stream(main)
+                with torch.cuda.stream(self.side):
+                    ops.attention_row(qkv[Tq:], qkv[:, W:], qkv[:, 2 * W:], ao[Tq:], F_, Hh, T, hd, hd ** -0.5,
+                                      T * rs, (T * rs, rs), (T * rs, rs), T * W)
             if Tq:
                 ops.attention_fwd(qkv, qkv[:, W:], qkv[:, 2 * W:], ao, F_, Hh, Tq, T, hd, hd ** -0.5,
                                   (T * rs, rs), (T * rs, rs), (T * rs, rs), (T * W, W), impl="tc")
-            if Tq == T - 1:
+            if forked:
+                main.wait_stream(self.side)
+            elif Tq == T - 1:
                 ops.attention_row(qkv[Tq:], qkv[:, W:], qkv[:, 2 * W:], ao[Tq:], F_, Hh, T, hd, hd ** -0.5,
                                   T * rs, (T * rs, rs), (T * rs, rs), T * W)
             elif Tq < T:

@@ -67,6 +67,8 @@ def test_gemm_epilogues(ops, M):
     ref = a.float() @ b.float().t() + bias
     _close(ops.gemm(a, b, bias=bias, out_dtype=torch.float32), ref, 2e-3, 2e-3, "bias")
     _close(ops.gemm(a, b, bias=bias, gelu=True, out_dtype=torch.float32), torch.nn.functional.gelu(ref), 2e-3, 2e-3, "gelu")
+    _close(ops.gemm(a, b, bias=bias, gelu=True), torch.nn.functional.gelu(ref), 4e-3, 4e-3, "gelu fp16 out (ViT fc1 epilogue)")
+    _close(ops.gemm(a, b, bias=bias), ref, 4e-3, 4e-3, "bias fp16 out (ViT qkv epilogue)")
     x = resid.clone()
     ops.gemm(a, b, out=x, bias=bias, resid=x)            # in-place fp32 residual stream
     _close(x, resid + ref, 2e-3, 2e-3, "residual in place")
