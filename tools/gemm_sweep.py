@@ -16,6 +16,7 @@ BIG = [  # name, M, N, K, dtype, epilogue
     ("vit_qkv", 61680, 4224, 1408, H, "bias"),
     ("vit_proj", 61680, 1408, 1408, H, "bias_resid"),
     ("vit_fc1", 61680, 6144, 1408, H, "bias_gelu"),
+    ("vit_fc1_nogelu", 61680, 6144, 1408, H, "bias"),
     ("vit_fc2", 61680, 1408, 6144, H, "bias_resid"),
     ("qf_kv6", 61680, 9216, 1408, H, "bias"),
     ("t5_qkv", 8192, 6144, 2080, BF, "plain"),
