@@ -57,21 +57,27 @@ __host__ __device__ constexpr uint32_t idesc_f16(int fmt, int M, int N, int a_mn
          (static_cast<uint32_t>(N >> 3) << 17) | (static_cast<uint32_t>(M >> 4) << 24);
 }
 
-template <int HD>   // 64, or 96 (= 64-wide SW128 atom + 32-wide SW64 atom)
+// G = softmax groups (128 query rows each) per CTA.  G = 2: one CTA per SM, the tensor pipe works on one group while the
+// other runs its softmax, K/V tiles in a 2-stage ring.  G = 1 (short sequences, i.e. the ViT's 257 tokens): half the shared
+// memory and TMEM (one K and one V buffer with their own barriers), so TWO CTAs share an SM and one CTA's load / softmax
+// latency is covered by the other CTA's tensor work.
+template <int HD, int G>   // HD 64, or 96 (= 64-wide SW128 atom + 32-wide SW64 atom)
 struct TcSmem {
   static constexpr bool SPLIT = (HD == 96);
   static constexpr int Q_ONE = TQ * 64 * 2 + (SPLIT ? TQ * 32 * 2 : 0);       // one group's Q tile
   static constexpr int KV_ONE = TKV * 64 * 2 + (SPLIT ? TKV * 32 * 2 : 0);   // one of K or V
   static constexpr int STAGE_BYTES = 2 * KV_ONE;
-  static constexpr int STAGES = 2;
+  static constexpr int STAGES = (G == 1) ? 1 : 2;                              // K+V stages held in shared memory
+  static constexpr int NBARST = 2;                                             // full / empty barrier pairs (G = 1: K and V)
   static constexpr int P_BYTES = TQ * TKV * 2;                                 // two 64-key atoms, per group
   static constexpr int OFF_Q = 0;
-  static constexpr int OFF_KV = 2 * Q_ONE;
+  static constexpr int OFF_KV = G * Q_ONE;
   static constexpr int OFF_P = OFF_KV + STAGES * STAGE_BYTES;
-  static constexpr int OFF_BIAS = OFF_P + 2 * P_BYTES;                         // 8 warps x 160 floats
-  static constexpr int OFF_BAR = OFF_BIAS + 8 * 160 * 4;
-  static constexpr int NBAR = 1 + 2 * STAGES + 6;
+  static constexpr int OFF_BIAS = OFF_P + G * P_BYTES;                         // 4 G warps x 160 floats
+  static constexpr int OFF_BAR = OFF_BIAS + 4 * G * 160 * 4;
+  static constexpr int NBAR = 1 + 2 * NBARST + 6;
   static constexpr int TOTAL = OFF_BAR + NBAR * 8 + 16 + 1024;
+  static constexpr int THREADS = (2 + 4 * G) * 32;
 };
 
 // ---- softmax building blocks (one thread = one query row; all tcgen05.ld calls are warp-uniform) ----
@@ -177,39 +183,40 @@ __device__ __forceinline__ float softmax_tile(const RowCtx& x, int j, int nc32, 
   return rsum;
 }
 
-template <int HD>
-__global__ void __launch_bounds__(320, 1)
+template <int HD, int G>
+__global__ void __launch_bounds__((2 + 4 * G) * 32, G == 1 ? 2 : 1)
 attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                    const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmQ2,
                    const __grid_constant__ CUtensorMap tmK2, const __grid_constant__ CUtensorMap tmV2,
                    const AttnTcParams p) {
-  using S = TcSmem<HD>;
+  using S = TcSmem<HD, G>;
   constexpr bool SPLIT = S::SPLIT;
   constexpr int STAGES = S::STAGES;
-  constexpr uint32_t TMEM_COLS = 512;
-  constexpr int S_COL = 0, O_COL = 256;          // S_A [0,128) S_B [128,256) ; O_A [256,256+HD) O_B [256+HD, 256+2HD)
+  constexpr int NBARST = S::NBARST;
+  constexpr uint32_t TMEM_COLS = (G == 2) ? 512 : 256;
+  constexpr int S_COL = 0, O_COL = G * TKV;      // G = 2: S_A [0,128) S_B [128,256); O_A [256,256+HD) O_B [256+HD, 256+2HD)
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S::OFF_BAR);
   uint64_t* q_full = bars;
   uint64_t* kv_full = bars + 1;
-  uint64_t* kv_empty = kv_full + STAGES;
-  uint64_t* s_full = kv_empty + STAGES;    // [2] per group
+  uint64_t* kv_empty = kv_full + NBARST;
+  uint64_t* s_full = kv_empty + NBARST;    // [2] per group
   uint64_t* p_full = s_full + 2;
   uint64_t* o_full = p_full + 2;
   uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + S::NBAR);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int b = blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * (2 * TQ);
+  const int b = blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * (G * TQ);
   const int bkv = b / p.kv_div;
-  const int n_groups = (q0 + TQ < p.Lq) ? 2 : 1;           // the second 128-row group may be empty
+  const int n_groups = (G == 2 && q0 + TQ < p.Lq) ? 2 : 1; // the second 128-row group may be empty
   int n_kv = (p.Lk + TKV - 1) / TKV;
   if (p.causal) n_kv = min(n_kv, (min(q0 + n_groups * TQ, p.Lq) - 1 + p.q_pos0) / TKV + 1);
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV);
     mbar_init(q_full, 1);
-    for (int s = 0; s < STAGES; ++s) { mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 1); }
+    for (int s = 0; s < NBARST; ++s) { mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 1); }
     for (int g = 0; g < 2; ++g) { mbar_init(&s_full[g], 1); mbar_init(&p_full[g], 4); mbar_init(&o_full[g], 1); }
     fence_barrier_init();
   }
@@ -227,7 +234,23 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         tma_load_4d(smem + S::OFF_Q + g * S::Q_ONE, &tmQ, q_full, 0, h, q0 + g * TQ, b);
         if (SPLIT) tma_load_4d(smem + S::OFF_Q + g * S::Q_ONE + TQ * 128, &tmQ2, q_full, 64, h, q0 + g * TQ, b);
       }
-      for (int j = 0; j < n_kv; ++j) {
+      if (G == 1) {
+        // one K and one V buffer, each with its own full / empty barrier pair ([0] = K, [1] = V): K_{j+1} streams in as
+        // soon as S_j = Q K_j^T has retired (i.e. during softmax j), V_{j+1} as soon as O += P_j V_j has retired
+        uint8_t* sk = smem + S::OFF_KV;
+        uint8_t* sv = sk + S::KV_ONE;
+        for (int j = 0; j < n_kv; ++j) {
+          mbar_wait(&kv_empty[0], (j & 1) ^ 1);
+          mbar_expect_tx(&kv_full[0], S::KV_ONE);
+          tma_load_4d(sk, &tmK, &kv_full[0], 0, h, j * TKV, bkv);
+          if (SPLIT) tma_load_4d(sk + TKV * 128, &tmK2, &kv_full[0], 64, h, j * TKV, bkv);
+          mbar_wait(&kv_empty[1], (j & 1) ^ 1);
+          mbar_expect_tx(&kv_full[1], S::KV_ONE);
+          tma_load_4d(sv, &tmV, &kv_full[1], 0, h, j * TKV, bkv);
+          if (SPLIT) tma_load_4d(sv + TKV * 128, &tmV2, &kv_full[1], 64, h, j * TKV, bkv);
+        }
+      }
+      for (int j = 0; G == 2 && j < n_kv; ++j) {
         const int st = j % STAGES;
         mbar_wait(&kv_empty[st], ((j / STAGES) & 1) ^ 1);
         uint8_t* sk = smem + S::OFF_KV + st * S::STAGE_BYTES;
@@ -287,6 +310,23 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     mbar_wait(q_full, 0);
     mbar_wait(&kv_full[0], 0);
     tc_fence_after();
+    if (G == 1) {
+      if (lane == 0) { issue_qk(0, 0); umma_commit(&kv_empty[0]); }     // K_0 is free once S_0 has retired
+      __syncwarp();
+      for (int j = 0; j < n_kv; ++j) {
+        mbar_wait(&p_full[0], j & 1);                                   // P_j written, S_j consumed
+        mbar_wait(&kv_full[1], j & 1);                                  // V_j landed
+        tc_fence_after();
+        if (lane == 0) { issue_pv(0, j); umma_commit(&kv_empty[1]); }
+        __syncwarp();
+        if (j + 1 < n_kv) {
+          mbar_wait(&kv_full[0], (j + 1) & 1);                          // K_{j+1} landed
+          tc_fence_after();
+          if (lane == 0) { issue_qk(0, j + 1); umma_commit(&kv_empty[0]); }
+          __syncwarp();
+        }
+      }
+    } else {
     if (lane == 0)
       for (int g = 0; g < n_groups; ++g) issue_qk(g, 0);
     __syncwarp();
@@ -302,6 +342,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         }
         __syncwarp();
       }
+    }
     }
   } else {
     // ===================== softmax groups: one thread per query row =====================
@@ -442,17 +483,17 @@ static int make_tmap4(CUtensorMap* map, const void* base, int dtype, int hd, int
   return r == CUDA_SUCCESS ? MRB_OK : MRB_ERR_CUDA;
 }
 
-template <int HD>
+template <int HD, int G>
 static int launch_tc(const CUtensorMap* maps, const AttnTcParams& p, cudaStream_t s) {
-  using S = TcSmem<HD>;
+  using S = TcSmem<HD, G>;
   static bool cfg = false;
   if (!cfg) {
-    cudaError_t e = cudaFuncSetAttribute(attn_fwd_tc_kernel<HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL);
+    cudaError_t e = cudaFuncSetAttribute(attn_fwd_tc_kernel<HD, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL);
     if (e != cudaSuccess) return mrb_set_error(e);
     cfg = true;
   }
-  dim3 grid((p.Lq + 2 * TQ - 1) / (2 * TQ), p.H, p.B);
-  attn_fwd_tc_kernel<HD><<<grid, 320, S::TOTAL, s>>>(maps[0], maps[1], maps[2], maps[3], maps[4], maps[5], p);
+  dim3 grid((p.Lq + G * TQ - 1) / (G * TQ), p.H, p.B);
+  attn_fwd_tc_kernel<HD, G><<<grid, S::THREADS, S::TOTAL, s>>>(maps[0], maps[1], maps[2], maps[3], maps[4], maps[5], p);
   MRB_CHECK_LAUNCH();
   return MRB_OK;
 }
@@ -491,5 +532,9 @@ extern "C" int mrb_attention_fwd_tc(const void* q, long long q_bs, long long q_r
   p.bias = bias; p.bias_len = bias_len; p.bias_zero = bias_zero; p.kmask = kmask; p.kv_div = kv_div;
   p.causal = causal; p.q_pos0 = q_pos0; p.o = o; p.o_bs = o_bs; p.o_rs = o_rs; p.lse = lse;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  return split ? launch_tc<96>(maps, p, s) : launch_tc<64>(maps, p, s);
+  // short sequences (ViT: 257 keys = 3 K/V tiles): one softmax group per CTA, two CTAs per SM (MRB_ATTN_G1=0 disables)
+  static int g1 = -1;
+  if (g1 < 0) { const char* e = getenv("MRB_ATTN_G1"); g1 = (e && e[0] == '0') ? 0 : 1; }
+  if (split) return (g1 && Lk <= 4 * TKV) ? launch_tc<96, 1>(maps, p, s) : launch_tc<96, 2>(maps, p, s);
+  return launch_tc<64, 2>(maps, p, s);
 }
