@@ -68,7 +68,9 @@ struct BwdSmem {
   static constexpr int TOTAL = OFF_BAR + NBAR * 8 + 16 + 1024;
 };
 
-template <int MODE>
+// ENC = the encoder self-attention case that carries almost all of the time (bucketed bias, no causal mask, bf16): those
+// three facts become compile-time constants so the per-element loop has no uniform branches left.
+template <int MODE, bool ENC>
 __global__ void __launch_bounds__(320, 1)
 attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmY,
                    const __grid_constant__ CUtensorMap tmU, const __grid_constant__ CUtensorMap tmW, const AttnBwdParams p) {
@@ -203,6 +205,10 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
       const float LOG2E = 1.4426950408889634f;
       const float sl2 = p.scale * LOG2E;
       const float* bhead = p.bias ? p.bias + static_cast<long long>(h) * p.bias_len : nullptr;
+      const bool has_bias = ENC ? true : (bhead != nullptr);
+      const bool causal = ENC ? false : (p.causal != 0);
+      const int dt = ENC ? MRB_DT_BF16 : p.dtype;
+      const float scale = p.scale;
       const long long stat_off = (static_cast<long long>(b) * p.H + h) * p.Lq;
       float* win = reinterpret_cast<float*>(smem + S::OFF_WIN) + (warp - 2) * S::WIN_FLOATS;
       float* wlse = win + 96;
@@ -223,7 +229,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
         const int u0 = (t_begin + t) * TT;                   // first streamed row (query for DKV, key for DQ)
         __syncwarp();
         // ---- stage the per-warp windows: bias (pre-multiplied by log2 e) and, for DKV, lse / delta of the 64 queries
-        if (bhead) {
+        if (has_bias) {
           // DQ : idx(row i, col j=u0+c) = (u0 + c) - (i + q_pos0) + zero   -> W[k] = bias[w0 + k], w0 from the warp's last row
           // DKV: idx(row j, col i=u0+c) = j - (u0 + c + q_pos0) + zero     -> w0 from the warp's first row and c = 63
           const int w0 = (MODE == MODE_DQ) ? (u0 - (warp_row_last + p.q_pos0) + p.bias_zero)
@@ -260,25 +266,37 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
           const uint32_t cm = c0 == 0 ? cm0 : cm1;
           uint32_t pp[16], pd[16];
 #pragma unroll
-          for (int e = 0; e < 32; e += 2) {
-            float pr[2], ds[2];
-#pragma unroll
-            for (int q = 0; q < 2; ++q) {
-              const int c = c0 + e + q;
-              float s = __uint_as_float(sv[e + q]) * sl2;
-              if (bhead) s += (MODE == MODE_DQ) ? wrow[c] : wrow[-c];
-              const float lse_c = (MODE == MODE_DQ) ? lse_row : wlse[c];
-              const float dl_c = (MODE == MODE_DQ) ? dl_row : wdl[c];
-              float pv = ex2b(s - lse_c);
-              bool ok;
-              if (MODE == MODE_DQ) ok = ((cm >> (e + q)) & 1u) && !(p.causal && u0 + c > row_c + p.q_pos0);
-              else ok = row_key_ok && !(p.causal && row_c > u0 + c + p.q_pos0);
-              pv = ok ? pv : 0.f;
-              pr[q] = pv;
-              ds[q] = pv * (__uint_as_float(dv[e + q]) - dl_c) * p.scale;
+          for (int e8 = 0; e8 < 32; e8 += 8) {
+            // lse / delta of 8 streamed queries (DKV): identical for every lane -> four broadcast 16-byte loads
+            float lse8[8], dl8[8];
+            if (MODE == MODE_DKV) {
+              const float4 la = *reinterpret_cast<const float4*>(wlse + c0 + e8), lb = *reinterpret_cast<const float4*>(wlse + c0 + e8 + 4);
+              const float4 da = *reinterpret_cast<const float4*>(wdl + c0 + e8), db = *reinterpret_cast<const float4*>(wdl + c0 + e8 + 4);
+              lse8[0] = la.x; lse8[1] = la.y; lse8[2] = la.z; lse8[3] = la.w; lse8[4] = lb.x; lse8[5] = lb.y; lse8[6] = lb.z; lse8[7] = lb.w;
+              dl8[0] = da.x; dl8[1] = da.y; dl8[2] = da.z; dl8[3] = da.w; dl8[4] = db.x; dl8[5] = db.y; dl8[6] = db.z; dl8[7] = db.w;
             }
-            pp[e >> 1] = pack2(pr[0], pr[1], p.dtype);
-            pd[e >> 1] = pack2(ds[0], ds[1], p.dtype);
+#pragma unroll
+            for (int e2 = 0; e2 < 8; e2 += 2) {
+              const int e = e8 + e2;
+              float pr[2], ds[2];
+#pragma unroll
+              for (int q = 0; q < 2; ++q) {
+                const int c = c0 + e + q;
+                float s = __uint_as_float(sv[e + q]) * sl2;
+                if (has_bias) s += (MODE == MODE_DQ) ? wrow[c] : wrow[-c];
+                const float lse_c = (MODE == MODE_DQ) ? lse_row : lse8[e2 + q];
+                const float dl_c = (MODE == MODE_DQ) ? dl_row : dl8[e2 + q];
+                float pv = ex2b(s - lse_c);
+                bool ok;
+                if (MODE == MODE_DQ) ok = ((cm >> (e + q)) & 1u) && !(causal && u0 + c > row_c + p.q_pos0);
+                else ok = row_key_ok && !(causal && row_c > u0 + c + p.q_pos0);
+                pv = ok ? pv : 0.f;
+                pr[q] = pv;
+                ds[q] = pv * (__uint_as_float(dv[e + q]) - dl_c) * scale;
+              }
+              pp[e >> 1] = pack2(pr[0], pr[1], dt);
+              pd[e >> 1] = pack2(ds[0], ds[1], dt);
+            }
           }
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
@@ -313,10 +331,10 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
 #pragma unroll
             for (int c = 0; c < 32; c += 8)
               *reinterpret_cast<uint4*>(orow + c0 + c) =
-                  make_uint4(pack2(__uint_as_float(v[c]), __uint_as_float(v[c + 1]), p.dtype),
-                             pack2(__uint_as_float(v[c + 2]), __uint_as_float(v[c + 3]), p.dtype),
-                             pack2(__uint_as_float(v[c + 4]), __uint_as_float(v[c + 5]), p.dtype),
-                             pack2(__uint_as_float(v[c + 6]), __uint_as_float(v[c + 7]), p.dtype));
+                  make_uint4(pack2(__uint_as_float(v[c]), __uint_as_float(v[c + 1]), dt),
+                             pack2(__uint_as_float(v[c + 2]), __uint_as_float(v[c + 3]), dt),
+                             pack2(__uint_as_float(v[c + 4]), __uint_as_float(v[c + 5]), dt),
+                             pack2(__uint_as_float(v[c + 6]), __uint_as_float(v[c + 7]), dt));
           }
         }
       }
@@ -373,19 +391,27 @@ static int make_tmap4b(CUtensorMap* map, const void* base, int dtype, int heads,
   return r == CUDA_SUCCESS ? MRB_OK : MRB_ERR_CUDA;
 }
 
-template <int MODE>
-static int launch_bwd_tc(const CUtensorMap& x, const CUtensorMap& y, const CUtensorMap& u, const CUtensorMap& w,
-                         const AttnBwdParams& p, int Lstat, cudaStream_t s) {
+template <int MODE, bool ENC>
+static int launch_bwd_tc2(const CUtensorMap& x, const CUtensorMap& y, const CUtensorMap& u, const CUtensorMap& w,
+                          const AttnBwdParams& p, int Lstat, cudaStream_t s) {
   static bool cfg = false;
   if (!cfg) {
-    cudaError_t e = cudaFuncSetAttribute(attn_bwd_tc_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, BwdSmem::TOTAL);
+    cudaError_t e = cudaFuncSetAttribute(attn_bwd_tc_kernel<MODE, ENC>, cudaFuncAttributeMaxDynamicSharedMemorySize, BwdSmem::TOTAL);
     if (e != cudaSuccess) return mrb_set_error(e);
     cfg = true;
   }
   dim3 grid((Lstat + 2 * TS - 1) / (2 * TS), p.H, p.B);
-  attn_bwd_tc_kernel<MODE><<<grid, 320, BwdSmem::TOTAL, s>>>(x, y, u, w, p);
+  attn_bwd_tc_kernel<MODE, ENC><<<grid, 320, BwdSmem::TOTAL, s>>>(x, y, u, w, p);
   MRB_CHECK_LAUNCH();
   return MRB_OK;
+}
+template <int MODE>
+static int launch_bwd_tc(const CUtensorMap& x, const CUtensorMap& y, const CUtensorMap& u, const CUtensorMap& w,
+                         const AttnBwdParams& p, int Lstat, cudaStream_t s) {
+  static int spec = -1;                   // MRB_ATTN_BWD_ENC=0 keeps the generic instantiation (A/B measurements)
+  if (spec < 0) { const char* e = getenv("MRB_ATTN_BWD_ENC"); spec = (e && e[0] == '0') ? 0 : 1; }
+  if (spec && p.bias && !p.causal && p.dtype == MRB_DT_BF16) return launch_bwd_tc2<MODE, true>(x, y, u, w, p, Lstat, s);
+  return launch_bwd_tc2<MODE, false>(x, y, u, w, p, Lstat, s);
 }
 
 }  // namespace mrb

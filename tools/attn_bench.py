@@ -42,6 +42,19 @@ def main():
                                                   (L * rs, rs), (L * rs, rs), (L * rs, rs), (L * H * hd, H * hd), bias=bias,
                                                   bias_zero=L - 1, kmask=kmask, impl=impl))
             print("%-14s %-4s %8.3f ms  %7.1f TFLOP/s" % (name, impl, ms, flops / ms / 1e9), flush=True)
+        if name.startswith("t5enc") and "tc" in impls:          # backward (dK/dV kernel + dQ kernel + delta), 10 L^2 d flops
+            q, k, v = qkv[:, :, 0], qkv[:, :, 1], qkv[:, :, 2]
+            lse = torch.empty(B, H, L, device="cuda")
+            ops.attention_fwd(q, k, v, out, B, H, L, L, hd, hd ** -0.5, (L * rs, rs), (L * rs, rs), (L * rs, rs),
+                              (L * H * hd, H * hd), bias=bias, bias_zero=L - 1, kmask=kmask, lse=lse, impl="tc")
+            dout = torch.randn_like(out)
+            dqkv = torch.empty_like(qkv)
+            ws = torch.empty(B * H * L, device="cuda")
+            st, ost = (L * rs, rs), (L * H * hd, H * hd)
+            ms = timeit(lambda: ops.attention_bwd(q, k, v, out, dout, dqkv[:, :, 0], dqkv[:, :, 1], dqkv[:, :, 2], B, H, L, L, hd,
+                                                  hd ** -0.5, st, st, st, ost, ost, lse, ws, bias=bias, bias_zero=L - 1,
+                                                  kmask=kmask, impl="tc"))
+            print("%-14s bwd  %8.3f ms  %7.1f TFLOP/s (algorithmic 2.5x fwd)" % (name, ms, 2.5 * flops / ms / 1e9), flush=True)
 
 
 if __name__ == "__main__":
