@@ -89,13 +89,14 @@ struct RowCtx {
   int ncols, kv0, i_abs, causal;
 };
 
-// raw 32-column slice of this row's S tile -> scores (scale, bias window, masks)
+// raw 32-column slice of this row's S tile -> log2-domain scores minus `sub` (scale, bias window, masks); sub = 0 gives the
+// scores themselves, sub = the row's reference maximum gives the exp2 arguments with ONE FFMA per element
 template <bool HAS_BIAS, bool MASKED>
-__device__ __forceinline__ void scores_from(const RowCtx& x, int c, const uint32_t* v, float* sv) {
+__device__ __forceinline__ void scores_from(const RowCtx& x, int c, const uint32_t* v, float sub, float* sv) {
   const uint32_t mw = (c == 0) ? x.mb[0] : (c == 32) ? x.mb[1] : (c == 64) ? x.mb[2] : x.mb[3];
 #pragma unroll
   for (int e = 0; e < 32; ++e) {
-    float s = HAS_BIAS ? fmaf(__uint_as_float(v[e]), x.sl2, x.wrow[c + e]) : __uint_as_float(v[e]) * x.sl2;
+    float s = HAS_BIAS ? fmaf(__uint_as_float(v[e]), x.sl2, x.wrow[c + e] - sub) : fmaf(__uint_as_float(v[e]), x.sl2, -sub);
     if (MASKED) {
       const bool ok = (c + e < x.ncols) && ((mw >> e) & 1u) && !(x.causal && x.kv0 + c + e > x.i_abs);
       s = ok ? s : -INFINITY;
@@ -104,11 +105,11 @@ __device__ __forceinline__ void scores_from(const RowCtx& x, int c, const uint32
   }
 }
 template <bool HAS_BIAS, bool MASKED>
-__device__ __forceinline__ void load_scores(const RowCtx& x, int c, float* sv) {
+__device__ __forceinline__ void load_scores(const RowCtx& x, int c, float sub, float* sv) {
   uint32_t v[32];
   tmem_ld_32x32b_x32(x.s_addr + c, v);
   tmem_ld_wait();
-  scores_from<HAS_BIAS, MASKED>(x, c, v, sv);
+  scores_from<HAS_BIAS, MASKED>(x, c, v, sub, sv);
 }
 
 template <bool HAS_BIAS, bool MASKED>
@@ -116,7 +117,7 @@ __device__ __forceinline__ float tile_max(const RowCtx& x, int nc32) {
   float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
   for (int c = 0; c < nc32; c += 32) {
     float sv[32];
-    load_scores<HAS_BIAS, MASKED>(x, c, sv);
+    load_scores<HAS_BIAS, MASKED>(x, c, 0.f, sv);
 #pragma unroll
     for (int e = 0; e < 32; e += 4) {
       mx0 = fmaxf(mx0, sv[e]); mx1 = fmaxf(mx1, sv[e + 1]); mx2 = fmaxf(mx2, sv[e + 2]); mx3 = fmaxf(mx3, sv[e + 3]);
@@ -125,58 +126,54 @@ __device__ __forceinline__ float tile_max(const RowCtx& x, int nc32) {
   return fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
 }
 
-// P = exp2(s - mref) -> 16 bit -> SWIZZLE_128B rows of the P tile; returns the row sum, tracks the true tile max
-// exp2(s - mref) of one 32-column slice -> 16 bit -> this row of the SWIZZLE_128B P tile
-template <bool MASKED>
-__device__ __forceinline__ void exp_chunk(const float* sv, int c, int npad, float mref, uint8_t* prow, int r, int dtype,
-                                          float& rs0, float& rs1, float& mx0, float& mx1) {
-  uint32_t pk[16];
-#pragma unroll
-  for (int e = 0; e < 32; e += 2) {
-    mx0 = fmaxf(mx0, sv[e]); mx1 = fmaxf(mx1, sv[e + 1]);
-    const float p0 = ex2(sv[e] - mref), p1 = ex2(sv[e + 1] - mref);
-    rs0 += p0; rs1 += p1;
-    pk[e >> 1] = pack2(p0, p1, dtype);
-  }
-#pragma unroll
-  for (int q = 0; q < 4; ++q) {                  // 4 x 16-byte chunks of 8 keys
-    const int key0 = c + q * 8;
-    if (!MASKED || key0 < npad) {
-      const int atom = key0 >> 6, chunk = (key0 & 63) >> 3;
-      *reinterpret_cast<uint4*>(prow + atom * (TQ * 128) + ((chunk ^ (r & 7)) << 4)) =
-          make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
-    }
-  }
-}
-
-// P = exp2(s - mref) -> 16 bit -> SWIZZLE_128B rows of the P tile; returns the row sum, tracks the true tile max.
+// P = exp2(s - mref) -> 16 bit -> SWIZZLE_128B rows of the P tile; returns the row sum.  Per element: FFMA, MUFU, FADD and
+// half a pack (DT is a compile-time dtype where the launcher knows it, so the pack is not predicated both ways).
 // (Software-pipelining the tcgen05.ld of the next 32 columns under the current exponentials was measured and gained
 // nothing -- 0.381 vs 0.378 ms on the T5 encoder shape -- so the simple load / wait / compute loop stays.)
-template <bool HAS_BIAS, bool MASKED>
-__device__ __forceinline__ float exp_store(const RowCtx& x, int nc32, int npad, float mref, uint8_t* prow, int r, int dtype,
-                                           float& tmax) {
-  float rs0 = 0.f, rs1 = 0.f, mx0 = -INFINITY, mx1 = -INFINITY;
+template <bool HAS_BIAS, bool MASKED, int DT>
+__device__ __forceinline__ float exp_store(const RowCtx& x, int nc32, int npad, float mref, uint8_t* prow, int r, int dtype) {
+  const int dt = DT < 0 ? dtype : DT;
+  float rs0 = 0.f, rs1 = 0.f;
   for (int c = 0; c < nc32; c += 32) {
     float sv[32];
-    load_scores<HAS_BIAS, MASKED>(x, c, sv);
-    exp_chunk<MASKED>(sv, c, npad, mref, prow, r, dtype, rs0, rs1, mx0, mx1);
+    load_scores<HAS_BIAS, MASKED>(x, c, mref, sv);
+    uint32_t pk[16];
+#pragma unroll
+    for (int e = 0; e < 32; e += 2) {
+      const float p0 = ex2(sv[e]), p1 = ex2(sv[e + 1]);
+      rs0 += p0; rs1 += p1;
+      pk[e >> 1] = pack2(p0, p1, dt);
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {                  // 4 x 16-byte chunks of 8 keys
+      const int key0 = c + q * 8;
+      if (!MASKED || key0 < npad) {
+        const int atom = key0 >> 6, chunk = (key0 & 63) >> 3;
+        *reinterpret_cast<uint4*>(prow + atom * (TQ * 128) + ((chunk ^ (r & 7)) << 4)) =
+            make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
+      }
+    }
   }
-  tmax = fmaxf(mx0, mx1);
   return rs0 + rs1;
 }
 
-template <bool HAS_BIAS, bool MASKED>
+// One KV tile of the online softmax for this row.  The first tile is exact (two passes).  Later tiles exponentiate against
+// the STALE reference maximum m_ref in a single pass; no per-element maximum is tracked: a tile holds <= 128 keys, so a row
+// sum above 2^TAU = 256 is the (conservative, warp-voted) sign that some score exceeded the reference by more than TAU --
+// only then the tile maximum is computed, O and l are rescaled and the tile is redone exactly.
+template <bool HAS_BIAS, bool MASKED, int DT>
 __device__ __forceinline__ float softmax_tile(const RowCtx& x, int j, int nc32, int npad, uint8_t* prow, int r, int dtype,
                                               float& m_ref, float& l_run, uint32_t o_addr, int hd_cols) {
   // NOTE: tcgen05.ld is warp-collective (.sync.aligned): every branch around it must be warp-uniform.
-  float tmax, rsum;
+  float rsum;
   if (j == 0) {                                      // no reference yet: exact two-pass tile
     const float mx = tile_max<HAS_BIAS, MASKED>(x, nc32);
     if (mx != -INFINITY) m_ref = mx;
-    rsum = exp_store<HAS_BIAS, MASKED>(x, nc32, npad, mx == -INFINITY ? 0.f : mx, prow, r, dtype, tmax);
+    rsum = exp_store<HAS_BIAS, MASKED, DT>(x, nc32, npad, mx == -INFINITY ? 0.f : mx, prow, r, dtype);
   } else {
-    rsum = exp_store<HAS_BIAS, MASKED>(x, nc32, npad, m_ref == -INFINITY ? 0.f : m_ref, prow, r, dtype, tmax);
-    if (__any_sync(0xffffffffu, tmax > m_ref + TAU)) {   // rare: some row's max jumped; redo the tile exactly
+    rsum = exp_store<HAS_BIAS, MASKED, DT>(x, nc32, npad, m_ref == -INFINITY ? 0.f : m_ref, prow, r, dtype);
+    if (__any_sync(0xffffffffu, !(rsum <= 256.0f))) {    // rare: some row's max jumped (or overflowed); redo the tile exactly
+      const float tmax = tile_max<HAS_BIAS, MASKED>(x, nc32);
       const float m_new = fmaxf(m_ref, tmax);
       const float corr = (m_ref == -INFINITY) ? 0.f : ex2(m_ref - m_new);
       l_run *= corr;
@@ -192,13 +189,13 @@ __device__ __forceinline__ float softmax_tile(const RowCtx& x, int j, int nc32, 
       }
       tmem_st_wait();
       m_ref = m_new;
-      rsum = exp_store<HAS_BIAS, MASKED>(x, nc32, npad, m_ref == -INFINITY ? 0.f : m_ref, prow, r, dtype, tmax);
+      rsum = exp_store<HAS_BIAS, MASKED, DT>(x, nc32, npad, m_ref == -INFINITY ? 0.f : m_ref, prow, r, dtype);
     }
   }
   return rsum;
 }
 
-template <int HD, int G>
+template <int HD, int G, int DT>   // DT: 0 fp16 / 1 bf16 known at compile time, -1 = p.dtype
 __global__ void __launch_bounds__((2 + 4 * G) * 32, G == 1 ? 2 : 1)
 attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                    const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmQ2,
@@ -387,13 +384,22 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         const int nc32 = (ncols + 31) & ~31;
         const int npad = (ncols + 15) & ~15;               // the PV MMA reads keys [0, npad)
         // stage this warp's bias window (pre-multiplied by log2 e) while the QK MMA runs
+        bool bias_const = false;
+        float cbias = 0.f;
         if (bhead) {
           __syncwarp();
           const int w0 = kv0 - i_warp_last + p.bias_zero;
+          bool same = true;
+          float first = 0.f;
           for (int k = lane; k < 160; k += 32) {
             const int idx = w0 + k;
-            wbias[k] = (idx >= 0 && idx < p.bias_len) ? __ldg(bhead + idx) * LOG2E : 0.f;
+            const float bv = (idx >= 0 && idx < p.bias_len) ? __ldg(bhead + idx) * LOG2E : 0.f;
+            wbias[k] = bv;
+            if (k == lane) first = bv; else same = same && (bv == first);
           }
+          const float lane0 = __shfl_sync(0xffffffffu, first, 0);
+          bias_const = __all_sync(0xffffffffu, same && first == lane0);
+          cbias = bias_const ? lane0 : 0.f;
           __syncwarp();
         }
         RowCtx x;
@@ -414,12 +420,16 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         tc_fence_after();
 
         float rsum;
-        if (bhead) {
-          rsum = masked ? softmax_tile<true, true>(x, j, nc32, npad, prow, r, p.dtype, m_ref, l_run, o_addr, HD)
-                        : softmax_tile<true, false>(x, j, nc32, npad, prow, r, p.dtype, m_ref, l_run, o_addr, HD);
+        if (bhead && !bias_const) {
+          rsum = masked ? softmax_tile<true, true, DT>(x, j, nc32, npad, prow, r, p.dtype, m_ref, l_run, o_addr, HD)
+                        : softmax_tile<true, false, DT>(x, j, nc32, npad, prow, r, p.dtype, m_ref, l_run, o_addr, HD);
         } else {
-          rsum = masked ? softmax_tile<false, true>(x, j, nc32, npad, prow, r, p.dtype, m_ref, l_run, o_addr, HD)
-                        : softmax_tile<false, false>(x, j, nc32, npad, prow, r, p.dtype, m_ref, l_run, o_addr, HD);
+          // no bias, or one bias value for the whole tile (T5 buckets saturate 128 positions off the diagonal, i.e. for all but
+          // ~3 of a row block's KV tiles): a constant shift of the scores = a shift of the reference maximum, zero per-element cost
+          m_ref -= cbias;
+          rsum = masked ? softmax_tile<false, true, DT>(x, j, nc32, npad, prow, r, p.dtype, m_ref, l_run, o_addr, HD)
+                        : softmax_tile<false, false, DT>(x, j, nc32, npad, prow, r, p.dtype, m_ref, l_run, o_addr, HD);
+          m_ref += cbias;
         }
         l_run += rsum;
         fence_proxy_async();
@@ -431,6 +441,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       mbar_wait(&o_full[g], (n_kv - 1) & 1);
       tc_fence_after();
       const int i = qg0 + r;
+      const int odt = DT < 0 ? p.dtype : DT;
       const float inv = l_run > 0.f ? 1.f / l_run : 0.f;
       uint16_t* orow = static_cast<uint16_t*>(p.o) + b * p.o_bs + static_cast<long long>(min(i, p.Lq - 1)) * p.o_rs +
                        static_cast<long long>(h) * p.hd;
@@ -444,10 +455,10 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
           for (int c = 0; c < 32; c += 8) {
             if (c0 + c < p.hd) {
               *reinterpret_cast<uint4*>(orow + c0 + c) =
-                  make_uint4(pack2(__uint_as_float(v[c]) * inv, __uint_as_float(v[c + 1]) * inv, p.dtype),
-                             pack2(__uint_as_float(v[c + 2]) * inv, __uint_as_float(v[c + 3]) * inv, p.dtype),
-                             pack2(__uint_as_float(v[c + 4]) * inv, __uint_as_float(v[c + 5]) * inv, p.dtype),
-                             pack2(__uint_as_float(v[c + 6]) * inv, __uint_as_float(v[c + 7]) * inv, p.dtype));
+                  make_uint4(pack2(__uint_as_float(v[c]) * inv, __uint_as_float(v[c + 1]) * inv, odt),
+                             pack2(__uint_as_float(v[c + 2]) * inv, __uint_as_float(v[c + 3]) * inv, odt),
+                             pack2(__uint_as_float(v[c + 4]) * inv, __uint_as_float(v[c + 5]) * inv, odt),
+                             pack2(__uint_as_float(v[c + 6]) * inv, __uint_as_float(v[c + 7]) * inv, odt));
             }
           }
         }
@@ -498,17 +509,17 @@ static int make_tmap4(CUtensorMap* map, const void* base, int dtype, int hd, int
   return r == CUDA_SUCCESS ? MRB_OK : MRB_ERR_CUDA;
 }
 
-template <int HD, int G>
+template <int HD, int G, int DT>
 static int launch_tc(const CUtensorMap* maps, const AttnTcParams& p, cudaStream_t s) {
   using S = TcSmem<HD, G>;
   static bool cfg = false;
   if (!cfg) {
-    cudaError_t e = cudaFuncSetAttribute(attn_fwd_tc_kernel<HD, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL);
+    cudaError_t e = cudaFuncSetAttribute(attn_fwd_tc_kernel<HD, G, DT>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL);
     if (e != cudaSuccess) return mrb_set_error(e);
     cfg = true;
   }
   dim3 grid((p.Lq + G * TQ - 1) / (G * TQ), p.H, p.B);
-  attn_fwd_tc_kernel<HD, G><<<grid, S::THREADS, S::TOTAL, s>>>(maps[0], maps[1], maps[2], maps[3], maps[4], maps[5], p);
+  attn_fwd_tc_kernel<HD, G, DT><<<grid, S::THREADS, S::TOTAL, s>>>(maps[0], maps[1], maps[2], maps[3], maps[4], maps[5], p);
   MRB_CHECK_LAUNCH();
   return MRB_OK;
 }
@@ -550,6 +561,9 @@ extern "C" int mrb_attention_fwd_tc(const void* q, long long q_bs, long long q_r
   // short sequences (ViT: 257 keys = 3 K/V tiles): one softmax group per CTA, two CTAs per SM (MRB_ATTN_G1=0 disables)
   static int g1 = -1;
   if (g1 < 0) { const char* e = getenv("MRB_ATTN_G1"); g1 = (e && e[0] == '0') ? 0 : 1; }
-  if (split) return (g1 && Lk <= 4 * TKV) ? launch_tc<96, 1>(maps, p, s) : launch_tc<96, 2>(maps, p, s);
-  return launch_tc<64, 2>(maps, p, s);
+  if (split) {
+    if (g1 && Lk <= 4 * TKV) return dtype == MRB_DT_F16 ? launch_tc<96, 1, MRB_DT_F16>(maps, p, s) : launch_tc<96, 1, -1>(maps, p, s);
+    return launch_tc<96, 2, -1>(maps, p, s);
+  }
+  return dtype == MRB_DT_BF16 ? launch_tc<64, 2, MRB_DT_BF16>(maps, p, s) : launch_tc<64, 2, -1>(maps, p, s);
 }
