@@ -68,6 +68,70 @@ struct BwdSmem {
   static constexpr int TOTAL = OFF_BAR + NBAR * 8 + 16 + 1024;
 };
 
+// Elementwise core of one streamed tile for one stationary row (thread): P = exp2(S*sl2 + bias - lse) and
+// dS = P * (dP - delta) * scale for 64 streamed columns, written as 16-bit SWIZZLE_128B operand rows.
+//   off   : per-row constant added to every exp2 argument (DQ: [constant tile bias] - lse_row; DKV: 0, the per-column
+//           window wlse[] already holds [constant tile bias] - lse)
+//   dls   : DQ: delta_row * scale;  DKV: unused (wdl[] holds delta * scale)
+// HAS_BIAS = the bias varies inside the tile (window lookup per element); MASKED = some element of the warp's tile is masked.
+// Unmasked constant-bias tiles (all but the ~3 tiles next to the diagonal of a T5 encoder row block) cost
+// FFMA + MUFU + FFMA + FMUL + the packs per element.
+template <int MODE, bool HAS_BIAS, bool MASKED>
+__device__ __forceinline__ void bwd_tile_rows(uint32_t lane_base, const float* wrow, const float* wlse, const float* wdl,
+                                              float off, float dls, float sl2, float scale, uint32_t cm0, uint32_t cm1,
+                                              bool row_key_ok, bool causal, int u0, int row_c, int q_pos0, uint8_t* prow,
+                                              int r, int dt) {
+#pragma unroll
+  for (int c0 = 0; c0 < TT; c0 += 32) {
+    uint32_t sv[32], dv[32];
+    tmem_ld_32x32b_x32(lane_base + c0, sv);
+    tmem_ld_32x32b_x32(lane_base + 64 + c0, dv);
+    tmem_ld_wait();
+    const uint32_t cm = c0 == 0 ? cm0 : cm1;
+    uint32_t pp[16], pd[16];
+#pragma unroll
+    for (int e8 = 0; e8 < 32; e8 += 8) {
+      float off8[8], dl8[8];                  // DKV: (bias const - lse) and delta * scale of 8 streamed queries, broadcast loads
+      if (MODE == MODE_DKV) {
+        const float4 la = *reinterpret_cast<const float4*>(wlse + c0 + e8), lb = *reinterpret_cast<const float4*>(wlse + c0 + e8 + 4);
+        const float4 da = *reinterpret_cast<const float4*>(wdl + c0 + e8), db = *reinterpret_cast<const float4*>(wdl + c0 + e8 + 4);
+        off8[0] = la.x; off8[1] = la.y; off8[2] = la.z; off8[3] = la.w; off8[4] = lb.x; off8[5] = lb.y; off8[6] = lb.z; off8[7] = lb.w;
+        dl8[0] = da.x; dl8[1] = da.y; dl8[2] = da.z; dl8[3] = da.w; dl8[4] = db.x; dl8[5] = db.y; dl8[6] = db.z; dl8[7] = db.w;
+      }
+#pragma unroll
+      for (int e2 = 0; e2 < 8; e2 += 2) {
+        const int e = e8 + e2;
+        float pr[2], ds[2];
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+          const int c = c0 + e + q;
+          float o = (MODE == MODE_DQ) ? off : off8[e2 + q];
+          if (HAS_BIAS) o += (MODE == MODE_DQ) ? wrow[c] : wrow[-c];
+          float pv = ex2b(fmaf(__uint_as_float(sv[e + q]), sl2, o));
+          if (MASKED) {
+            bool ok;
+            if (MODE == MODE_DQ) ok = ((cm >> (e + q)) & 1u) && !(causal && u0 + c > row_c + q_pos0);
+            else ok = row_key_ok && !(causal && row_c > u0 + c + q_pos0);
+            pv = ok ? pv : 0.f;
+          }
+          pr[q] = pv;
+          ds[q] = pv * fmaf(__uint_as_float(dv[e + q]), scale, -((MODE == MODE_DQ) ? dls : dl8[e2 + q]));
+        }
+        if (MODE == MODE_DKV) pp[e >> 1] = pack2(pr[0], pr[1], dt);
+        pd[e >> 1] = pack2(ds[0], ds[1], dt);
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int chunk = (c0 >> 3) + q;
+      const int o16 = (chunk ^ (r & 7)) << 4;
+      if (MODE == MODE_DKV)
+        *reinterpret_cast<uint4*>(prow + o16) = make_uint4(pp[4 * q], pp[4 * q + 1], pp[4 * q + 2], pp[4 * q + 3]);
+      *reinterpret_cast<uint4*>(prow + BwdSmem::X_BYTES + o16) = make_uint4(pd[4 * q], pd[4 * q + 1], pd[4 * q + 2], pd[4 * q + 3]);
+    }
+  }
+}
+
 // ENC = the encoder self-attention case that carries almost all of the time (bucketed bias, no causal mask, bf16): those
 // three facts become compile-time constants so the per-element loop has no uniform branches left.
 template <int MODE, bool ENC>
@@ -229,83 +293,56 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
         const int u0 = (t_begin + t) * TT;                   // first streamed row (query for DKV, key for DQ)
         __syncwarp();
         // ---- stage the per-warp windows: bias (pre-multiplied by log2 e) and, for DKV, lse / delta of the 64 queries
+        bool bias_const = false;
+        float cbias = 0.f;
         if (has_bias) {
           // DQ : idx(row i, col j=u0+c) = (u0 + c) - (i + q_pos0) + zero   -> W[k] = bias[w0 + k], w0 from the warp's last row
           // DKV: idx(row j, col i=u0+c) = j - (u0 + c + q_pos0) + zero     -> w0 from the warp's first row and c = 63
           const int w0 = (MODE == MODE_DQ) ? (u0 - (warp_row_last + p.q_pos0) + p.bias_zero)
                                            : (warp_row_first - (u0 + 63 + p.q_pos0) + p.bias_zero);
+          bool same = true;
+          float first = 0.f;
           for (int k = lane; k < 96; k += 32) {
             const int idx = w0 + k;
-            win[k] = (idx >= 0 && idx < p.bias_len) ? __ldg(bhead + idx) * LOG2E : 0.f;
+            const float bv = (idx >= 0 && idx < p.bias_len) ? __ldg(bhead + idx) * LOG2E : 0.f;
+            win[k] = bv;
+            if (k == lane) first = bv; else same = same && (bv == first);
           }
+          const float lane0 = __shfl_sync(0xffffffffu, first, 0);
+          bias_const = __all_sync(0xffffffffu, same && first == lane0);   // T5 buckets saturate 128 positions off the diagonal
+          cbias = bias_const ? lane0 : 0.f;
         }
         uint32_t cm0 = 0xffffffffu, cm1 = 0xffffffffu;       // per-column validity bits (keys for DQ)
+        bool masked = causal;
         if (MODE == MODE_DKV) {
           for (int k = lane; k < 64; k += 32) {
             const int i = u0 + k;
-            wlse[k] = (i < p.Lq) ? p.lse[stat_off + i] * LOG2E : 0.f;
-            wdl[k] = (i < p.Lq) ? p.delta[stat_off + i] : 0.f;
+            wlse[k] = cbias - ((i < p.Lq) ? p.lse[stat_off + i] * LOG2E : 0.f);     // exp2 argument offset of streamed query k
+            wdl[k] = (i < p.Lq) ? p.delta[stat_off + i] * scale : 0.f;
           }
+          masked = masked || !__all_sync(0xffffffffu, row_key_ok);
         } else {
           const int* mrow = p.kmask ? p.kmask + static_cast<long long>(b) * p.Lk : nullptr;
           const int j0 = u0 + lane, j1 = u0 + 32 + lane;
           cm0 = __ballot_sync(0xffffffffu, j0 < p.Lk && (!mrow || __ldg(mrow + min(j0, p.Lk - 1)) != 0));
           cm1 = __ballot_sync(0xffffffffu, j1 < p.Lk && (!mrow || __ldg(mrow + min(j1, p.Lk - 1)) != 0));
+          masked = masked || (cm0 & cm1) != 0xffffffffu;
         }
         __syncwarp();
         const float* wrow = (MODE == MODE_DQ) ? (win + (warp_row_last - row_c)) : (win + (row_c - warp_row_first) + 63);
+        const float off = (MODE == MODE_DQ) ? (cbias - lse_row) : 0.f;
+        const float dls = dl_row * scale;
+        const bool vbias = has_bias && !bias_const;
 
         mbar_wait(&t_full[g], t & 1);
         tc_fence_after();
-#pragma unroll
-        for (int c0 = 0; c0 < TT; c0 += 32) {
-          uint32_t sv[32], dv[32];
-          tmem_ld_32x32b_x32(lane_base + c0, sv);
-          tmem_ld_32x32b_x32(lane_base + 64 + c0, dv);
-          tmem_ld_wait();
-          const uint32_t cm = c0 == 0 ? cm0 : cm1;
-          uint32_t pp[16], pd[16];
-#pragma unroll
-          for (int e8 = 0; e8 < 32; e8 += 8) {
-            // lse / delta of 8 streamed queries (DKV): identical for every lane -> four broadcast 16-byte loads
-            float lse8[8], dl8[8];
-            if (MODE == MODE_DKV) {
-              const float4 la = *reinterpret_cast<const float4*>(wlse + c0 + e8), lb = *reinterpret_cast<const float4*>(wlse + c0 + e8 + 4);
-              const float4 da = *reinterpret_cast<const float4*>(wdl + c0 + e8), db = *reinterpret_cast<const float4*>(wdl + c0 + e8 + 4);
-              lse8[0] = la.x; lse8[1] = la.y; lse8[2] = la.z; lse8[3] = la.w; lse8[4] = lb.x; lse8[5] = lb.y; lse8[6] = lb.z; lse8[7] = lb.w;
-              dl8[0] = da.x; dl8[1] = da.y; dl8[2] = da.z; dl8[3] = da.w; dl8[4] = db.x; dl8[5] = db.y; dl8[6] = db.z; dl8[7] = db.w;
-            }
-#pragma unroll
-            for (int e2 = 0; e2 < 8; e2 += 2) {
-              const int e = e8 + e2;
-              float pr[2], ds[2];
-#pragma unroll
-              for (int q = 0; q < 2; ++q) {
-                const int c = c0 + e + q;
-                float s = __uint_as_float(sv[e + q]) * sl2;
-                if (has_bias) s += (MODE == MODE_DQ) ? wrow[c] : wrow[-c];
-                const float lse_c = (MODE == MODE_DQ) ? lse_row : lse8[e2 + q];
-                const float dl_c = (MODE == MODE_DQ) ? dl_row : dl8[e2 + q];
-                float pv = ex2b(s - lse_c);
-                bool ok;
-                if (MODE == MODE_DQ) ok = ((cm >> (e + q)) & 1u) && !(causal && u0 + c > row_c + p.q_pos0);
-                else ok = row_key_ok && !(causal && row_c > u0 + c + p.q_pos0);
-                pv = ok ? pv : 0.f;
-                pr[q] = pv;
-                ds[q] = pv * (__uint_as_float(dv[e + q]) - dl_c) * scale;
-              }
-              pp[e >> 1] = pack2(pr[0], pr[1], dt);
-              pd[e >> 1] = pack2(ds[0], ds[1], dt);
-            }
-          }
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const int chunk = (c0 >> 3) + q;
-            const int off = (chunk ^ (r & 7)) << 4;
-            if (MODE == MODE_DKV)
-              *reinterpret_cast<uint4*>(prow + off) = make_uint4(pp[4 * q], pp[4 * q + 1], pp[4 * q + 2], pp[4 * q + 3]);
-            *reinterpret_cast<uint4*>(prow + S::X_BYTES + off) = make_uint4(pd[4 * q], pd[4 * q + 1], pd[4 * q + 2], pd[4 * q + 3]);
-          }
+        // warp-uniform dispatch (tcgen05.ld inside is warp-collective)
+        if (vbias) {
+          if (masked) bwd_tile_rows<MODE, true, true>(lane_base, wrow, wlse, wdl, off, dls, sl2, scale, cm0, cm1, row_key_ok, causal, u0, row_c, p.q_pos0, prow, r, dt);
+          else bwd_tile_rows<MODE, true, false>(lane_base, wrow, wlse, wdl, off, dls, sl2, scale, cm0, cm1, row_key_ok, causal, u0, row_c, p.q_pos0, prow, r, dt);
+        } else {
+          if (masked) bwd_tile_rows<MODE, false, true>(lane_base, wrow, wlse, wdl, off, dls, sl2, scale, cm0, cm1, row_key_ok, causal, u0, row_c, p.q_pos0, prow, r, dt);
+          else bwd_tile_rows<MODE, false, false>(lane_base, wrow, wlse, wdl, off, dls, sl2, scale, cm0, cm1, row_key_ok, causal, u0, row_c, p.q_pos0, prow, r, dt);
         }
         fence_proxy_async();
         tc_fence_before();

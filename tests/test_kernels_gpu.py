@@ -157,14 +157,20 @@ def test_attention_cross_small_q(ops, Lq, Lk, dtype):
 
 
 @pytest.mark.parametrize("impl", ["mma", "tc"])
-@pytest.mark.parametrize("Lq,Lk,causal", [(150, 150, False), (21, 21, True), (21, 333, False), (300, 300, True),
-                                          (257, 400, False), (513, 513, False)])
-def test_attention_t5_bias_mask_fwd_bwd(ops, Lq, Lk, causal, impl):
+@pytest.mark.parametrize("Lq,Lk,causal,sat", [(150, 150, False, 0), (21, 21, True, 0), (21, 333, False, 0), (300, 300, True, 0),
+                                              (257, 400, False, 0), (513, 513, False, 0), (700, 700, False, 128),
+                                              (700, 700, False, 40), (14, 650, False, 128)])
+def test_attention_t5_bias_mask_fwd_bwd(ops, Lq, Lk, causal, sat, impl):
+    """sat > 0: T5-style bias that saturates `sat` positions off the diagonal (bucketed relative positions,
+    modeling_t5.py:393-445), so most KV tiles see one bias value -- the constant-bias fast paths of the tcgen05 kernels."""
     B, H, hd = 2, 32, 64
     dt = torch.bfloat16
     q, k, v = (_rand((B, L, H, hd), dt, 0.5, s) for L, s in ((Lq, 15), (Lk, 16), (Lk, 17)))
     dout = _rand((B, Lq, H, hd), dt, 1.0, 18)
     table = _rand((H, Lq + Lk - 1), torch.float32, 1.0, 19)          # bias by (j - i) + (Lq - 1)
+    if sat:
+        idx = (torch.arange(Lq + Lk - 1, device="cuda") - (Lq - 1)).clamp(-sat, sat) + (Lq - 1)
+        table = table[:, idx.clamp(0, Lq + Lk - 2)].contiguous()
     kmask = torch.ones((B, Lk), dtype=torch.int32, device="cuda")
     kmask[1, Lk - 7:] = 0
     i = torch.arange(Lq, device="cuda")[:, None]
