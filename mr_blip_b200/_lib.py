@@ -4,7 +4,7 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libmrblip_b200.so")
+LIB_PATH = os.path.join(_HERE, "libmrblip_b200%s.so" % os.environ.get("MRB_LIB_VARIANT", ""))   # variants: A/B builds (build.py)
 
 _p, _ll, _i, _f = ctypes.c_void_p, ctypes.c_longlong, ctypes.c_int, ctypes.c_float
 

@@ -33,7 +33,10 @@ def main():
         qkv = (torch.randn(B, L, 3, H, hd, device="cuda") * 0.5).to(dt)
         out = torch.empty(B, L, H, hd, device="cuda", dtype=dt)
         rs = 3 * H * hd
-        bias = torch.randn(H, 2 * L - 1, device="cuda") if with_bias else None
+        bias = None
+        if with_bias:       # T5-style: bucketed relative bias saturates 128 positions off the diagonal (modeling_t5.py:393-445)
+            idx = (torch.arange(2 * L - 1, device="cuda") - (L - 1)).clamp(-128, 128) + (L - 1)
+            bias = torch.randn(H, 2 * L - 1, device="cuda")[:, idx].contiguous()
         kmask = torch.ones(B, L, dtype=torch.int32, device="cuda") if with_bias else None
         flops = 4.0 * B * H * L * L * hd
         for impl in impls:
