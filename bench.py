@@ -27,6 +27,7 @@ METRIC = "video_clips_per_sec_fwd_bwd_qvh60"
 UNIT = "clips/s"
 BATCH, FRAMES, QUERY_WORDS = 4, 60, 32
 FLOPS_PER_CLIP = 44.83e12          # GEMM + attention FLOPs, fwd+bwd, one 60-frame QVH clip
+NCU_FC1_TRAFFIC = 932.5e6          # dram__bytes_read.sum + dram__bytes_write.sum, one fc1 launch (profiles/ncu_gemm2_fc1_r01c.csv)
 
 
 def peaks():
@@ -225,7 +226,8 @@ def run_b200(args):
             "loss": float(last_loss)}
 
     if rank == 0:
-        # ---- roofline of the dominant kernel (gemm_tcgen05_kernel): CUDA events around every launch of one more step
+        # ---- roofline of the dominant kernel (gemm2_tcgen05_kernel, the 2-CTA tcgen05 GEMM, plus its 1-CTA sibling for the
+        #      small shapes): CUDA events around every GEMM launch of one more (eager) step
         qf_engine = model.engines()[1]
         qf_engine.xattn_events = []
         ops.GEMM_PROFILE = []
@@ -242,15 +244,15 @@ def run_b200(args):
         gms = sum(a.elapsed_time(b) for _, _, _, a, b in prof)
         pk, how = peaks()
         ach = flops / (gms / 1e3) / 1e12
-        line["roofline"] = {"kernel": "gemm_tcgen05_kernel", "bound": "tensor", "achieved": ach,
+        line["roofline"] = {"kernel": "gemm2_tcgen05_kernel", "bound": "tensor", "achieved": ach,
                             "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s", "frac": ach / pk["bf16_tflops_sustained"],
                             "peak_source": how + " bf16_tflops_sustained (kernel timed inside a long step)",
                             "launches_per_step": len(prof), "flops_per_launch": flops / max(len(prof), 1),
                             "avg_launch_ms": gms / max(len(prof), 1), "share_of_step": gms / (ms / args.steps),
                             # dram__bytes_read+write of ONE launch of the dominant shape (ViT fc1, M61680 N6144 K1408, bias+GELU)
-                            # from profiles/ncu_gemm2_fc1_r01.csv; its algorithmic bytes (A + B + C once) are 948.9e6
-                            "traffic": 927.3e6, "traffic_algorithmic": 948.9e6,
-                            "traffic_source": "profiles/ncu_gemm2_fc1_r01.csv (ncu --set full, one fc1 launch)"}
+                            # from profiles/ncu_gemm2_fc1_r01c.csv; its algorithmic bytes (A + B + C once) are 948.9e6
+                            "traffic": NCU_FC1_TRAFFIC, "traffic_algorithmic": 948.9e6,
+                            "traffic_source": "profiles/ncu_gemm2_fc1_r01c.csv (ncu --set full, one fc1 launch)"}
         line["qformer_xattn"] = {"what": "Q-Former cross-attention path: batched K/V projection GEMM (6 layers, tcgen05) + 6 attention cores",
                                  "flops_per_step": x_flops, "ms_per_step": x_ms, "achieved": x_flops / (x_ms / 1e3) / 1e12,
                                  "unit": "TFLOP/s", "frac": x_flops / (x_ms / 1e3) / 1e12 / pk["bf16_tflops_sustained"]}

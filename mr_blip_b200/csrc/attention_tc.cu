@@ -378,24 +378,46 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       // (column 0, last row of this warp)
       const int i_warp_last = min(qg0 + quad * 32 + 31, p.Lq - 1) + p.q_pos0;
 
+      float bnext[5] = {0.f, 0.f, 0.f, 0.f, 0.f};     // raw bias window (5 x 32 lanes = 160 floats) of the next tile
+      int mnext[4] = {1, 1, 1, 1};                    // key-mask values (4 x 32 lanes = 128 keys) of the next tile, 0 past Lk
+      auto prefetch_tile = [&](int jn) {
+        const int kvn = jn * TKV;
+        if (bhead) {
+          const int w0 = kvn - i_warp_last + p.bias_zero + lane;
+#pragma unroll
+          for (int t = 0; t < 5; ++t) {
+            const int idx = w0 + 32 * t;
+            bnext[t] = (idx >= 0 && idx < p.bias_len) ? __ldg(bhead + idx) : 0.f;
+          }
+        }
+        if (mrow) {
+#pragma unroll
+          for (int w = 0; w < 4; ++w) {
+            const int jj = kvn + lane + 32 * w;
+            mnext[w] = (jj < p.Lk) ? __ldg(mrow + jj) : 0;
+          }
+        }
+      };
+      prefetch_tile(0);
       for (int j = 0; j < n_kv; ++j) {
         const int kv0 = j * TKV;
         const int ncols = min(TKV, p.Lk - kv0);
         const int nc32 = (ncols + 31) & ~31;
         const int npad = (ncols + 15) & ~15;               // the PV MMA reads keys [0, npad)
         // stage this warp's bias window (pre-multiplied by log2 e) while the QK MMA runs
+        // this tile's bias window / key-mask words were fetched one tile ahead (the L2 round trip of these per-tile global
+        // loads used to sit in front of every softmax); stage them, then start the next tile's fetch
         bool bias_const = false;
         float cbias = 0.f;
         if (bhead) {
           __syncwarp();
-          const int w0 = kv0 - i_warp_last + p.bias_zero;
           bool same = true;
-          float first = 0.f;
-          for (int k = lane; k < 160; k += 32) {
-            const int idx = w0 + k;
-            const float bv = (idx >= 0 && idx < p.bias_len) ? __ldg(bhead + idx) * LOG2E : 0.f;
-            wbias[k] = bv;
-            if (k == lane) first = bv; else same = same && (bv == first);
+          const float first = bnext[0] * LOG2E;
+#pragma unroll
+          for (int t = 0; t < 5; ++t) {
+            const float bv = bnext[t] * LOG2E;
+            wbias[lane + 32 * t] = bv;
+            same = same && (bv == first);
           }
           const float lane0 = __shfl_sync(0xffffffffu, first, 0);
           bias_const = __all_sync(0xffffffffu, same && first == lane0);
@@ -407,12 +429,11 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         x.mb[0] = x.mb[1] = x.mb[2] = x.mb[3] = 0xffffffffu;
         bool masked = (ncols < TKV) || (p.causal && kv0 + TKV - 1 > qg0 + quad * 32 + p.q_pos0);
         if (mrow) {
-          const int jj = kv0 + lane;
 #pragma unroll
-          for (int w = 0; w < 4; ++w)
-            x.mb[w] = __ballot_sync(0xffffffffu, (jj + 32 * w < p.Lk) && __ldg(mrow + min(jj + 32 * w, p.Lk - 1)) != 0);
+          for (int w = 0; w < 4; ++w) x.mb[w] = __ballot_sync(0xffffffffu, mnext[w] != 0);
           masked = masked || ((x.mb[0] & x.mb[1] & x.mb[2] & x.mb[3]) != 0xffffffffu);
         }
+        if (j + 1 < n_kv) prefetch_tile(j + 1);
         // rows of a warp are consecutive: this row's window starts (i_warp_last - i_abs) floats into the warp window
         x.wrow = wbias + (i_warp_last - i_abs);
 

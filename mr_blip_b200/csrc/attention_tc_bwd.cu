@@ -289,24 +289,52 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
       }
       const int warp_row_first = min(xg0 + quad * 32, Lstat - 1), warp_row_last = min(xg0 + quad * 32 + 31, Lstat - 1);
 
+      // per-tile global loads (bias window, lse / delta of the streamed queries, key mask) run one tile ahead of their use
+      float bnext[3] = {0.f, 0.f, 0.f}, lnext[2] = {0.f, 0.f}, dnext[2] = {0.f, 0.f};
+      int mnext[2] = {1, 1};
+      auto prefetch_tile = [&](int tn) {
+        const int un = (t_begin + tn) * TT;
+        if (has_bias) {
+          const int w0 = ((MODE == MODE_DQ) ? (un - (warp_row_last + p.q_pos0) + p.bias_zero)
+                                            : (warp_row_first - (un + 63 + p.q_pos0) + p.bias_zero)) + lane;
+#pragma unroll
+          for (int tt = 0; tt < 3; ++tt) {
+            const int idx = w0 + 32 * tt;
+            bnext[tt] = (idx >= 0 && idx < p.bias_len) ? __ldg(bhead + idx) : 0.f;
+          }
+        }
+        if (MODE == MODE_DKV) {
+#pragma unroll
+          for (int tt = 0; tt < 2; ++tt) {
+            const int i = un + lane + 32 * tt;
+            lnext[tt] = (i < p.Lq) ? p.lse[stat_off + i] : 0.f;
+            dnext[tt] = (i < p.Lq) ? p.delta[stat_off + i] : 0.f;
+          }
+        } else {
+          const int* mrow = p.kmask ? p.kmask + static_cast<long long>(b) * p.Lk : nullptr;
+#pragma unroll
+          for (int tt = 0; tt < 2; ++tt) {
+            const int jn = un + lane + 32 * tt;
+            mnext[tt] = (jn < p.Lk) ? (mrow ? __ldg(mrow + jn) : 1) : 0;
+          }
+        }
+      };
+      prefetch_tile(0);
       for (int t = 0; t < n_t; ++t) {
         const int u0 = (t_begin + t) * TT;                   // first streamed row (query for DKV, key for DQ)
         __syncwarp();
-        // ---- stage the per-warp windows: bias (pre-multiplied by log2 e) and, for DKV, lse / delta of the 64 queries
+        // ---- stage the per-warp windows (their global loads were issued one tile ahead): bias (pre-multiplied by log2 e)
+        //      and, for DKV, lse / delta of the 64 streamed queries
         bool bias_const = false;
         float cbias = 0.f;
         if (has_bias) {
-          // DQ : idx(row i, col j=u0+c) = (u0 + c) - (i + q_pos0) + zero   -> W[k] = bias[w0 + k], w0 from the warp's last row
-          // DKV: idx(row j, col i=u0+c) = j - (u0 + c + q_pos0) + zero     -> w0 from the warp's first row and c = 63
-          const int w0 = (MODE == MODE_DQ) ? (u0 - (warp_row_last + p.q_pos0) + p.bias_zero)
-                                           : (warp_row_first - (u0 + 63 + p.q_pos0) + p.bias_zero);
           bool same = true;
-          float first = 0.f;
-          for (int k = lane; k < 96; k += 32) {
-            const int idx = w0 + k;
-            const float bv = (idx >= 0 && idx < p.bias_len) ? __ldg(bhead + idx) * LOG2E : 0.f;
-            win[k] = bv;
-            if (k == lane) first = bv; else same = same && (bv == first);
+          const float first = bnext[0] * LOG2E;
+#pragma unroll
+          for (int tt = 0; tt < 3; ++tt) {
+            const float bv = bnext[tt] * LOG2E;
+            win[lane + 32 * tt] = bv;
+            same = same && (bv == first);
           }
           const float lane0 = __shfl_sync(0xffffffffu, first, 0);
           bias_const = __all_sync(0xffffffffu, same && first == lane0);   // T5 buckets saturate 128 positions off the diagonal
@@ -315,19 +343,18 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
         uint32_t cm0 = 0xffffffffu, cm1 = 0xffffffffu;       // per-column validity bits (keys for DQ)
         bool masked = causal;
         if (MODE == MODE_DKV) {
-          for (int k = lane; k < 64; k += 32) {
-            const int i = u0 + k;
-            wlse[k] = cbias - ((i < p.Lq) ? p.lse[stat_off + i] * LOG2E : 0.f);     // exp2 argument offset of streamed query k
-            wdl[k] = (i < p.Lq) ? p.delta[stat_off + i] * scale : 0.f;
+#pragma unroll
+          for (int tt = 0; tt < 2; ++tt) {
+            wlse[lane + 32 * tt] = cbias - lnext[tt] * LOG2E;    // exp2 argument offset of streamed query k
+            wdl[lane + 32 * tt] = dnext[tt] * scale;
           }
           masked = masked || !__all_sync(0xffffffffu, row_key_ok);
         } else {
-          const int* mrow = p.kmask ? p.kmask + static_cast<long long>(b) * p.Lk : nullptr;
-          const int j0 = u0 + lane, j1 = u0 + 32 + lane;
-          cm0 = __ballot_sync(0xffffffffu, j0 < p.Lk && (!mrow || __ldg(mrow + min(j0, p.Lk - 1)) != 0));
-          cm1 = __ballot_sync(0xffffffffu, j1 < p.Lk && (!mrow || __ldg(mrow + min(j1, p.Lk - 1)) != 0));
+          cm0 = __ballot_sync(0xffffffffu, mnext[0] != 0);
+          cm1 = __ballot_sync(0xffffffffu, mnext[1] != 0);
           masked = masked || (cm0 & cm1) != 0xffffffffu;
         }
+        if (t + 1 < n_t) prefetch_tile(t + 1);
         __syncwarp();
         const float* wrow = (MODE == MODE_DQ) ? (win + (warp_row_last - row_c)) : (win + (row_c - warp_row_first) + 63);
         const float off = (MODE == MODE_DQ) ? (cbias - lse_row) : 0.f;
