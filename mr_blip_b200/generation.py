@@ -45,8 +45,9 @@ def beam_search(t5, inputs_embeds, attention_mask, num_beams=5, max_new_tokens=5
     done = [False] * B
     tokens = torch.full((B * nb,), start_id, dtype=torch.long, device="cuda")
     cur = 1
+    reorder = None                                                       # beam index each cache row continues from
     while True:
-        logits = t5.decode_step(st, tokens, cur - 1, kmask)              # [B*nb, V] fp32
+        logits = t5.decode_step(st, tokens, cur - 1, kmask, beam_idx=reorder)   # [B*nb, V] fp32 (static buffer)
         scores = torch.log_softmax(logits, dim=-1)
         if cur < min_length:
             scores[:, eos_id] = -float("inf")
@@ -84,7 +85,7 @@ def beam_search(t5, inputs_embeds, attention_mask, num_beams=5, max_new_tokens=5
         cur += 1
         if all(done) or cur >= max_length:
             break
-        t5.reorder_cache(st, flat_idx.cuda())
+        reorder = flat_idx.cuda()
     for b in range(B):
         if done[b]:
             continue

@@ -236,6 +236,9 @@ class T5Engine:
         self.dec_final_ln = _f(get(prefix + "decoder.final_layer_norm.weight"))
         self.lm_head = grp([prefix + "lm_head"])
         self._pack_table = None
+        self._dec_states = {}
+        self._dec_pool = None
+        self.decode_graphs = os.environ.get("MRB_CUDA_GRAPHS", "1") != "0"
 
     # ------------------------------------------------------------------ side stream
     def side_block(self, hold=()):
@@ -556,30 +559,70 @@ class T5Engine:
 
     def init_decode(self, enc_ext, B, Le, beams, max_len):
         """Project the encoder output to every decoder layer's cross K/V ONCE (the reference re-projects it at
-        every step) and allocate the self-attention K/V cache."""
+        every step) into a persistent decode state: static cross K/V buffers, ONE self-attention K/V cache
+        tensor for all layers, static token / beam-index / mask inputs and a logits output.  Static addresses are what let
+        every decode step replay a captured CUDA graph (one graph per position t, captured from the second generate() call
+        of a shape on; MRB_CUDA_GRAPHS=0 keeps eager launches)."""
         d = self.d
         inner = d.t5_heads * d.d_kv
-        st = {"cross": [], "k": [], "v": [], "B": B, "Le": Le, "beams": beams, "max_len": max_len}
-        for layer in self.dec:
-            ckv = self._ext(B * Le, 2 * inner)
+        key = (B, Le, beams, max_len)
+        st = self._dec_states.get(key)
+        if st is None:
+            NB, nl = B * beams, len(self.dec)
+            st = {"key": key, "B": B, "Le": Le, "beams": beams, "max_len": max_len, "uses": 0, "graphs": {},
+                  "cross": [self._ext(B * Le, 2 * inner) for _ in self.dec],
+                  "kv": torch.zeros((2 * nl, NB, max_len, inner), dtype=BF, device="cuda"),
+                  "tokens": torch.zeros((NB,), dtype=torch.int64, device="cuda"),
+                  "beam_idx": torch.arange(NB, dtype=torch.int64, device="cuda"),
+                  "kmask": torch.ones((B, Le), dtype=torch.int32, device="cuda"),
+                  "logits": torch.empty((NB, d.vocab), dtype=torch.float32, device="cuda"),
+                  "bias": self._bias(self.dec_bias, max_len, max_len, False)}
+            st["k"] = [st["kv"][2 * i] for i in range(nl)]
+            st["v"] = [st["kv"][2 * i + 1] for i in range(nl)]
+            self._dec_states = {key: st}                      # one shape at a time (its graphs hold a private pool)
+        for layer, ckv in zip(self.dec, st["cross"]):
             layer["ckv"].forward(enc_ext, B * Le, out=ckv[:, :2 * inner])
-            st["cross"].append(ckv)
-            st["k"].append(torch.zeros((B * beams, max_len, inner), dtype=BF, device="cuda"))
-            st["v"].append(torch.zeros((B * beams, max_len, inner), dtype=BF, device="cuda"))
-        st["bias"] = self._bias(self.dec_bias, max_len, max_len, False)
+        st["uses"] += 1
         return st
 
     def reorder_cache(self, st, beam_idx):
-        for i in range(len(self.dec)):
-            st["k"][i] = st["k"][i].index_select(0, beam_idx)
-            st["v"][i] = st["v"][i].index_select(0, beam_idx)
+        """Beam reorder of the self-attention cache (modeling_t5.py:1923-1954 _reorder_cache), in place."""
+        st["kv"].copy_(st["kv"].index_select(1, beam_idx))
 
-    def decode_step(self, st, token_ids, t, enc_kmask):
-        """One incremental decoder step for token position t: token_ids int64 [B*beams] -> logits fp32 [B*beams, V]."""
+    def decode_step(self, st, token_ids, t, enc_kmask, beam_idx=None):
+        """One incremental decoder step for token position t: token_ids int64 [B*beams] -> logits fp32 [B*beams, V] (a
+        static buffer, overwritten by the next step).  beam_idx (int64 [B*beams]) reorders cache rows [0, t) first."""
+        st["tokens"].copy_(token_ids)
+        if t == 0:
+            st["kmask"].copy_(enc_kmask)
+        reorder = beam_idx is not None and t > 0
+        if reorder:
+            st["beam_idx"].copy_(beam_idx)
+        if not (self.decode_graphs and st["uses"] > 1):
+            self._decode_step_device(st, t, reorder)
+            return st["logits"]
+        g = st["graphs"].get((t, reorder))
+        if g is None:                                        # first sight of this position in graph mode: capture
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, pool=self._dec_pool, capture_error_mode="thread_local"):
+                self._decode_step_device(st, t, reorder)
+            if self._dec_pool is None:
+                self._dec_pool = g.pool()
+            st["graphs"][(t, reorder)] = g
+        g.replay()
+        return st["logits"]
+
+    def _decode_step_device(self, st, t, reorder):
         d = self.d
+        token_ids = st["tokens"]
         NB = token_ids.shape[0]
         inner = d.t5_heads * d.d_kv
         Lm = st["max_len"]
+        enc_kmask = st["kmask"]
+        if reorder:                                          # rows [0, t) of every layer's K and V follow their beams
+            live = st["kv"][:, :, :t]
+            live.copy_(live.index_select(1, st["beam_idx"]))
         h = torch.empty((NB, d.d_model), dtype=torch.float32, device="cuda")
         ops.gather_rows(token_ids.to(torch.int32), self.emb, None, h)
         for li, layer in enumerate(self.dec):
@@ -610,4 +653,4 @@ class T5Engine:
             h = self._ff(layer, h2, NB, None)
         out = self._ext(NB, d.d_model)
         ops.norm(h, self.dec_final_ln, None, d.t5_ln_eps, 1, out_h=out)
-        return self.lm_head.forward(out, NB, out_dtype=torch.float32)
+        self.lm_head.forward(out, NB, out=st["logits"])

@@ -219,6 +219,14 @@ def test_generate_vs_oracle_beam_search(model, tiny_sd):
     want = ob.generate(tiny_sd, TINY, model.t5_tokenizer, samples, post_process, num_beams=5, max_length=8)
     assert out["sequences"].tolist() == want["sequences"].tolist()
     assert out["raw_prediction"] == want["raw_prediction"] and out["prediction"] == want["prediction"]
+    # the same shape again: every decode step now replays a captured CUDA graph (second call captures, third replays)
+    for _ in range(2):
+        again = model.generate(samples, num_beams=5, max_length=8)
+        assert again["sequences"].tolist() == want["sequences"].tolist()
+    other = synth.make_samples(batch=2, frames=3, seed=4)              # new content through the captured graphs
+    got_o = model.generate(other, num_beams=5, max_length=8)
+    want_o = ob.generate(tiny_sd, TINY, model.t5_tokenizer, other, post_process, num_beams=5, max_length=8)
+    assert got_o["sequences"].tolist() == want_o["sequences"].tolist()
     greedy = model.generate(samples, num_beams=1, max_length=6)
     want1 = ob.generate(tiny_sd, TINY, model.t5_tokenizer, samples, post_process, num_beams=1, max_length=6)
     assert greedy["sequences"].tolist() == want1["sequences"].tolist()

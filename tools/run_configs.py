@@ -51,13 +51,14 @@ def main():
         model._steps.clear()
         torch.cuda.empty_cache()
 
-    train_cfg("charades_sta_b8_t20_mean", 8, 20, "mean", 30.0)
+    train_cfg("charades_sta_b8_t20_mean", 8, 20, "mean", 120.0)
     train_cfg("activitynet_b2_t120", 2, 120, None, 180.0)
     model.eval()
     for batch in (4, 16):
         s = synth.make_samples(batch=batch, frames=60, query_words=32, seed=9)
         s["video"] = s["video"].cuda()
-        model.generate(s, num_beams=4, max_length=50)
+        for _ in range(2):                       # eager, then graph capture of every decode position
+            model.generate(s, num_beams=4, max_length=50)
         dt, out = timed(lambda: model.generate(s, num_beams=4, max_length=50), 1)
         res["generate_b%d_t60_beam4" % batch] = {"batch": batch, "s_per_call": round(dt, 3), "clips_per_s": round(batch / dt, 2),
                                                 "new_tokens": int(out["sequences"].shape[1]), "sample": out["raw_prediction"][0][:40]}
