@@ -645,9 +645,12 @@ class T5Engine:
             co = self._ext(NB, d.d_model)
             Le = st["Le"]
             ks = ckv.stride(0)
-            ops.attention_fwd(cq, ckv, ckv[:, inner:], co, NB, d.t5_heads, 1, Le, d.d_kv, 1.0, (inner, inner),
-                              (Le * ks, ks), (Le * ks, ks), (co.stride(0), co.stride(0)),
-                              kmask=enc_kmask, kv_div=st["beams"])
+            # the beams of one clip are the query rows of ONE attention problem over that clip's cross K/V (read once per
+            # clip, not once per beam): batch = clips, Lq = beams
+            nbm = st["beams"]
+            qs, cs = cq.stride(0), co.stride(0)
+            ops.attention_fwd(cq, ckv, ckv[:, inner:], co, NB // nbm, d.t5_heads, nbm, Le, d.d_kv, 1.0, (nbm * qs, qs),
+                              (Le * ks, ks), (Le * ks, ks), (nbm * cs, cs), kmask=enc_kmask)
             h2 = torch.empty_like(h)
             layer["co"].forward(co, NB, out=h2, resid=h1)
             h = self._ff(layer, h2, NB, None)
