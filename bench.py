@@ -30,6 +30,28 @@ FLOPS_PER_CLIP = 44.83e12          # GEMM + attention FLOPs, f
 NCU_FC1_TRAFFIC = 932.5e6          # dram__bytes_read.sum + dram__bytes_write.sum, one fc1 launch (profiles/ncu_gemm2_fc1_r01c.csv)
 
 
+_JSON_FD = None
+
+
+def _reserve_stdout():
+    """Keep stdout for the ONE JSON line: everything else that writes to fd 1 (NCCL prints its version banner there on the
+    first communicator) goes to stderr."""
+    global _JSON_FD
+    if _JSON_FD is None:
+        sys.stdout.flush()
+        _JSON_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line):
+    data = (json.dumps(line) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_JSON_FD, data)
+
+
 def peaks():
     try:
         return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))), "measured"
@@ -132,7 +154,7 @@ def run_reference(args):
                        "sample": sample},
             "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ------------------------------------------------------------------------------------------ B200 arm
@@ -265,7 +287,7 @@ def run_b200(args):
                                     "sample": "oracle port fwd+bwd, 1 clip x %d of %d frames (full-depth model, aliased "
                                               "layer weights), extrapolated linearly in frames; 1 warm-up + 1 timed"
                                               % (args.cpu_frames, FRAMES)}
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         tdist.barrier()
         tdist.destroy_process_group()
@@ -280,6 +302,7 @@ def main():
     ap.add_argument("--cpu-frames", type=int, default=4, help="frames of one clip the CPU baseline sample runs")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
+    _reserve_stdout()
     if args.impl == "reference":
         run_reference(args)
     else:

@@ -233,12 +233,15 @@ __global__ void __launch_bounds__(NTHREADS) attn_fwd_kernel(const AttnParams p) 
 constexpr int XQ_MAXG = 5;                    // 16-key groups per warp: Lk <= 4 * 5 * 16 = 320
 template <typename T>
 __global__ void __launch_bounds__(128) attn_xq_kernel(const AttnParams p) {
-  constexpr int HD = 64, LDS = HD + 8, LQ = 32;
-  extern __shared__ __align__(16) uint8_t smem_attn[];
+  // rows are 128 B (64 x 16 bit), 16-byte chunk c of row r lives at chunk (c ^ (r & 7)): conflict-free ldmatrix without
+  // padding, so Q + K + V of 257 keys take 72 KB and THREE CTAs share an SM
+  constexpr int HD = 64, LDS = HD, LQ = 32;
+  extern __shared__ __align__(128) uint8_t smem_attn[];
   const int LkP = (p.Lk + 15) & ~15;
   T* sQ = reinterpret_cast<T*>(smem_attn);
   T* sK = sQ + LQ * LDS;
   T* sV = sK + LkP * LDS;
+  auto sw = [](int r, int c) { return r * LDS + ((c ^ (r & 7)) << 3); };     // element offset of chunk c in row r
   const int b = blockIdx.y, h = blockIdx.x;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t4 = lane & 3;
   const T* gq = static_cast<const T*>(p.q) + b * p.q_bs + static_cast<long long>(h) * HD;
@@ -247,13 +250,13 @@ __global__ void __launch_bounds__(128) attn_xq_kernel(const AttnParams p) {
   for (int i = threadIdx.x; i < LkP * 8; i += 128) {
     const int r = i >> 3, c = i & 7;
     const bool ok = r < p.Lk;
-    cp_async16(smem_u32(sK + r * LDS + c * 8), ok ? gk + static_cast<long long>(r) * p.k_rs + c * 8 : gk, ok);
-    cp_async16(smem_u32(sV + r * LDS + c * 8), ok ? gv + static_cast<long long>(r) * p.v_rs + c * 8 : gv, ok);
+    cp_async16(smem_u32(sK + sw(r, c)), ok ? gk + static_cast<long long>(r) * p.k_rs + c * 8 : gk, ok);
+    cp_async16(smem_u32(sV + sw(r, c)), ok ? gv + static_cast<long long>(r) * p.v_rs + c * 8 : gv, ok);
   }
   for (int i = threadIdx.x; i < LQ * 8; i += 128) {
     const int r = i >> 3, c = i & 7;
     const bool ok = r < p.Lq;
-    cp_async16(smem_u32(sQ + r * LDS + c * 8), ok ? gq + static_cast<long long>(r) * p.q_rs + c * 8 : gq, ok);
+    cp_async16(smem_u32(sQ + sw(r, c)), ok ? gq + static_cast<long long>(r) * p.q_rs + c * 8 : gq, ok);
   }
   cp_async_commit();
   cp_async_wait<0>();
@@ -263,8 +266,7 @@ __global__ void __launch_bounds__(128) attn_xq_kernel(const AttnParams p) {
   const int NG = LkP >> 4, base = NG >> 2, rem = NG & 3;
   const int ng = base + (warp < rem ? 1 : 0);
   const int g0 = warp * base + min(warp, rem);
-  const T* cK = sK + g0 * 16 * LDS;
-  const T* cV = sV + g0 * 16 * LDS;
+  const int krow0 = g0 * 16;
 
   float sc[2][2 * XQ_MAXG][4];
 #pragma unroll
@@ -276,12 +278,12 @@ __global__ void __launch_bounds__(128) attn_xq_kernel(const AttnParams p) {
     uint32_t qf[2][4];
 #pragma unroll
     for (int mt = 0; mt < 2; ++mt)
-      ldsm_x4(qf[mt], smem_u32(sQ + (mt * 16 + (lane & 15)) * LDS + kk * 16 + (lane >> 4) * 8));
+      ldsm_x4(qf[mt], smem_u32(sQ + sw(mt * 16 + (lane & 15), kk * 2 + (lane >> 4))));
 #pragma unroll
     for (int gi = 0; gi < XQ_MAXG; ++gi) {
       if (gi < ng) {
         uint32_t kf[4];
-        ldsm_x4(kf, smem_u32(cK + (gi * 16 + (lane >> 4) * 8 + (lane & 7)) * LDS + kk * 16 + ((lane >> 3) & 1) * 8));
+        ldsm_x4(kf, smem_u32(sK + sw(krow0 + gi * 16 + (lane >> 4) * 8 + (lane & 7), kk * 2 + ((lane >> 3) & 1))));
 #pragma unroll
         for (int mt = 0; mt < 2; ++mt) {
           MmaType<T>::mma(sc[mt][2 * gi], qf[mt], kf[0], kf[1]);
@@ -346,7 +348,7 @@ __global__ void __launch_bounds__(128) attn_xq_kernel(const AttnParams p) {
 #pragma unroll
       for (int db = 0; db < HD / 16; ++db) {
         uint32_t vf[4];
-        ldsm_x4_t(vf, smem_u32(cV + (gi * 16 + ((lane >> 3) & 1) * 8 + (lane & 7)) * LDS + db * 16 + (lane >> 4) * 8));
+        ldsm_x4_t(vf, smem_u32(sV + sw(krow0 + gi * 16 + ((lane >> 3) & 1) * 8 + (lane & 7), db * 2 + (lane >> 4))));
 #pragma unroll
         for (int mt = 0; mt < 2; ++mt) {
           MmaType<T>::mma(oa[mt][2 * db], pf[mt][gi], vf[0], vf[1]);
@@ -357,7 +359,7 @@ __global__ void __launch_bounds__(128) attn_xq_kernel(const AttnParams p) {
   }
   __syncthreads();                               // every warp is done with K / V: reuse their space for the partials
   constexpr int LDO = HD + 2;
-  float* sO = reinterpret_cast<float*>(sK);      // [4 warps][32 rows][LDO]
+  float* sO = reinterpret_cast<float*>(sK);      // [4 warps][32 rows][LDO]  (K and V regions together hold it)
   float* sM = sO + 4 * LQ * LDO;                 // [4][32] running max (log2 domain), [4][32] sums
   float* sL = sM + 4 * LQ;
 #pragma unroll
@@ -771,7 +773,7 @@ static int launch_fwd(const AttnParams& p, cudaStream_t s) {
 template <typename T>
 static int launch_xq(const AttnParams& p, cudaStream_t s) {
   const int LkP = (p.Lk + 15) & ~15;
-  const int smem = (32 + 2 * LkP) * (64 + 8) * 2;
+  const int smem = (32 + 2 * LkP) * 64 * 2;
   static int cfg = 0;
   if (cfg < smem) { if (int rc = set_smem(attn_xq_kernel<T>, smem)) return rc; cfg = smem; }
   attn_xq_kernel<T><<<dim3(p.H, p.B), 128, smem, s>>>(p);
@@ -834,7 +836,7 @@ extern "C" int mrb_attention_fwd(const void* q, long long q_bs, long long q_rs, 
   static int use_xq = -1;                 // MRB_ATTN_XQ=0 keeps the generic kernel (A/B measurements)
   if (use_xq < 0) { const char* e = getenv("MRB_ATTN_XQ"); use_xq = (e && e[0] == '0') ? 0 : 1; }
   if (use_xq && hd == 64 && Lq <= 32 && Lk > 64 && Lk <= 16 * 4 * XQ_MAXG && !bias && !kmask && !causal && !lse && p.kv_div == 1 &&
-      4 * 32 * (64 + 2) * 4 + 8 * 32 * 4 <= ((Lk + 15) & ~15) * (64 + 8) * 2)
+      4 * 32 * (64 + 2) * 4 + 8 * 32 * 4 <= 2 * ((Lk + 15) & ~15) * 64 * 2)
     return dtype == MRB_DT_F16 ? launch_xq<__half>(p, s) : launch_xq<__nv_bfloat16>(p, s);
   if (dtype == MRB_DT_F16) return hd <= 64 ? launch_fwd<__half, 64>(p, s) : launch_fwd<__half, 96>(p, s);
   return hd <= 64 ? launch_fwd<__nv_bfloat16, 64>(p, s) : launch_fwd<__nv_bfloat16, 96>(p, s);
