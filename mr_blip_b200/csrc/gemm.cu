@@ -316,6 +316,10 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, GemmParam
 
 using namespace mrb;
 
+// Small-M note (decoder steps, M = 56): these launches take ~15 us for K = 2080 and ~55 us for K = 10272 whatever the tile
+// width (32 / 64 / 128) and whatever the ring depth -- a variant with 64-row A stages and an 11-14 stage ring measured
+// 21 us (profiles/gemm_small_m_r01b.log).  The time is 130 (K / 16) serially issued tcgen05.mma per CTA at ~75 ns each, i.e.
+// the single issuing thread, not TMA latency or HBM (floor 1.4 us); only split-K would shorten it (next round).
 // Pick the N tile: minimise (waves over the SMs) x (tile width) x (relative MMA inefficiency of narrow tiles).
 // Narrow tiles win only when the grid would otherwise leave most SMs idle (decoder steps, M <= 128).
 static int pick_bn(int M, int N, int sms) {

@@ -45,6 +45,8 @@ def _close(got, want, rtol, atol, what=""):
     (4100, 2048, 2080, 0),      # T5 linear with LoRA-extended K
     (56, 2048, 2080, 0),        # decoder step: narrow tiles spread over the SMs
     (56, 2048, 2080, 64),
+    (56, 2048, 2080, 32),       # M <= 64: 64-row A stages, deeper TMA ring
+    (64, 2048, 10272, 0),       # decoder wi dgrad: long K at tiny M
     (8132, 32, 2048, 0),        # LoRA down-projection
 ])
 def test_gemm_plain(ops, dtype, M, N, K, bn):
