@@ -262,6 +262,9 @@ def run_b200(args):
         xev, qf_engine.xattn_events = qf_engine.xattn_events, None
         x_ms = sum(a.elapsed_time(b) for a, b in xev)
         x_flops = BATCH * FRAMES * 6 * 1.137e9        # 1.137 GF per frame and cross-attention layer
+        all_ms = sum(a.elapsed_time(b) for _, _, _, a, b in prof)
+        all_flops = sum(2.0 * m * n * k for m, n, k, _, _ in prof)
+        prof = [x for x in prof if x[0] >= 512 and x[1] >= 256]      # the launches mrb_gemm routes to gemm2_tcgen05_kernel
         flops = sum(2.0 * m * n * k for m, n, k, _, _ in prof)
         gms = sum(a.elapsed_time(b) for _, _, _, a, b in prof)
         pk, how = peaks()
@@ -271,6 +274,8 @@ def run_b200(args):
                             "peak_source": how + " bf16_tflops_sustained (kernel timed inside a long step)",
                             "launches_per_step": len(prof), "flops_per_launch": flops / max(len(prof), 1),
                             "avg_launch_ms": gms / max(len(prof), 1), "share_of_step": gms / (ms / args.steps),
+                            "all_gemm_launches": {"ms": all_ms, "tflops": all_flops / (all_ms / 1e3) / 1e12,
+                                                  "note": "incl. the 1-CTA kernel's decoder-sized / N=32 launches"},
                             # dram__bytes_read+write of ONE launch of the dominant shape (ViT fc1, M61680 N6144 K1408, bias+GELU)
                             # from profiles/ncu_gemm2_fc1_r01c.csv; its algorithmic bytes (A + B + C once) are 948.9e6
                             "traffic": NCU_FC1_TRAFFIC, "traffic_algorithmic": 948.9e6,
