@@ -1,14 +1,17 @@
 // tcgen05 flash-attention forward for the two big attention shapes of the path:
 //   * T5 encoder self-attention (modeling_t5.py:561-610): hd 64, L ~ 2037, additive bucketed bias + padding mask
 //   * EVA ViT attention (eva_vit.py:128-145): hd 88 (handled as 64 + 32 with TMA zero fill of d >= 88), 257 tokens
-// One CTA per (128-query tile, head, batch):
-//   warp 0      TMA producer: Q once, then a ring of K/V tiles (4-D tensor maps: d, head, token, batch)
-//   warp 1      single-thread tcgen05.mma issuer:  S_j = Q K_j^T  (128 x BKV x hd, fp32 in TMEM, double buffered)
-//                                                  O_j = P_j V_j   (128 x hd, V read MN-major straight from its [key][d] tile)
-//   warps 2-5   softmax: one thread per query row (TMEM lane): tcgen05.ld S, scale/bias/mask, online max/sum, exp2,
-//               P_j -> bf16/fp16 -> SWIZZLE_128B smem (A operand of the PV MMA), O accumulated in registers from the
-//               per-tile TMEM result so no TMEM read-modify-write hazard exists.
+// One CTA per (G x 128 query rows, head, batch), G softmax groups (template parameter, see TcSmem):
+//   warp 0        TMA producer: Q once, then the K/V tiles (4-D tensor maps: d, head, token, batch)
+//   warp 1        single-thread tcgen05.mma issuer:  S_j = Q K_j^T  (128 x 128 x hd per group, fp32 in TMEM)
+//                                                    O += P_j V_j   (accumulated in TMEM, V read MN-major from its [key][d] tile)
+//   warps 2..     softmax, 4 warps per group, one thread per query row (TMEM lane): tcgen05.ld S, one FFMA per element for
+//                 the exp2 argument (scale, bias, reference maximum folded), exp2, row sum, P_j -> bf16/fp16 -> SWIZZLE_128B
+//                 smem (A operand of the PV MMA).  Single pass against a STALE row maximum; the tile is redone exactly (O and
+//                 l rescaled in TMEM) only when its row sum shows that a score exceeded the reference by more than 2^8.
 // The last KV tile is issued with N = round_up(remaining keys, 16), so 257 keys cost 2 x 128 + 16, not 3 x 128.
+// Measured limits (profiles/): per (128 x 128) tile the softmax side costs 64 KB of tcgen05.ld (TMEM read port 64 B/clk/SM)
+// and 16 K exp2 (16/clk/SM) against 512 clk of tensor work at hd 64 -- these, not the tensor pipe, bound the kernel.
 #include "common.cuh"
 
 namespace mrb {
