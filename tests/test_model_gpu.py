@@ -159,6 +159,7 @@ def test_graphed_step_matches_eager_step(model, agg):
         want_a, want_b = _train_grads(model, a), _train_grads(model, b)
         model.cuda_graphs, model.graph_bucket = True, (16, 4)
         model._steps.clear()
+        model._seen.clear()
         for rnd, (s, want) in enumerate([(a, want_a), (b, want_b), (a, want_a), (b, want_b)]):
             loss, grads = _train_grads(model, s)
             assert abs(loss - want[0]) < 1e-4, (rnd, loss, want[0])
