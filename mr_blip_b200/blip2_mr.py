@@ -251,11 +251,13 @@ class BLIP2_MR(Blip2Base):
     def _timestamps(self, timestamps, durations):
         fmt, table = self.input_time_format, self.annoying_numbers_replacement_dict
         fns = {"seconds_integers": mr_utils.get_timestamps_as_seconds_integers,
+               "seconds_floats": mr_utils.get_timestamps_as_seconds_floats,
                "relative_integers": mr_utils.get_timestamps_as_relative_integers,
+               "relative_floats": mr_utils.get_timestamps_as_relative_floats,
                "framenumbers": mr_utils.get_timestamps_as_framenumbers}
         if fmt not in fns:
-            raise ValueError("Invalid input_time_format, please choose from ['framenumbers', 'relative_integers', "
-                             "'seconds_integers'] (float formats are not implemented)")
+            raise ValueError("Invalid input_time_format, please choose from ['framenumbers', 'relative_floats', "
+                             "'relative_integers', 'seconds_integers', 'seconds_floats']")      # blip2_mr.py:627-630
         return fns[fmt](timestamps, durations, table)
 
     def _clean_ids(self, values):
@@ -527,7 +529,7 @@ class BLIP2_MR(Blip2Base):
         out["duration"] = dur.tolist() if isinstance(dur, torch.Tensor) else dur
         if self.input_time_format in ("relative_integers", "relative_floats"):
             prediction = [self.post_process(p) for p in pred_ans]
-            out["prediction"] = mr_utils.convert_to_absolute_time(prediction, out["duration"])
+            out["prediction"] = mr_utils.convert_to_absolute_time(prediction, out["duration"], self.input_time_format)
         else:
             out["prediction"] = [self.post_process(p) for p in pred_ans]
         out["raw_prediction"] = pred_ans

@@ -87,14 +87,38 @@ def get_timestamps_as_framenumbers(timestamps, durations, annoying_numbers_repla
     return new_ts, durations, prompts
 
 
-def convert_to_absolute_time(predictions, durations):
-    """Percent windows back to seconds.  blip2_mr.py:918-921 calls self.convert_to_absolute_time, which
-    the reference never defines (AttributeError as shipped); this is the evident intent."""
+def get_timestamps_as_seconds_floats(timestamps, durations, annoying_numbers_replacement_dict=None):
+    """Timestamps in seconds rounded to 2 decimals (utils.py:464-484).  The float32 tensor the reference builds is what gets
+    tokenised later (str(t.item()), blip2_mr.py:1576-1578), e.g. 149.6 -> "149.60000610351562"."""
+    new_ts, prompts = [], []
+    for t, d in zip(timestamps, durations):
+        vals = [round(float(x), 2) for x in t]
+        prompts.append(">".join(str(v) for v in vals) + ">" + str(round(float(d))))
+        new_ts.append(torch.tensor(vals))
+    return new_ts, durations, prompts
+
+
+def get_timestamps_as_relative_floats(timestamps, durations, annoying_numbers_replacement_dict=None):
+    """Timestamps as fractions of the duration, 2 decimals (utils.py:487-512): the prompt string drops the last frame and
+    the tensor carries the rounded duration as an extra element, exactly as the reference does."""
+    new_ts, prompts = [], []
+    for t, d in zip(timestamps, durations):
+        dur = float(d)
+        rel = [round(float(x) / dur, 2) for x in t]
+        prompts.append(">".join(str(v) for v in rel[:-1]) + ">" + str(round(dur)))
+        new_ts.append(torch.tensor(rel + [round(dur)]))
+    return new_ts, durations, prompts
+
+
+def convert_to_absolute_time(prediction, duration, input_time_format="relative_integers"):
+    """Relative windows (percent or fraction of the duration) back to seconds, 2 decimals (utils.py:242-297)."""
+    assert input_time_format in ("relative_integers", "relative_floats"), "This function is only used for relative timestamps"
+    div = 100.0 if input_time_format == "relative_integers" else 1.0
     out = []
-    for pred, dur in zip(predictions, durations):
-        windows = moment_str_to_list(pred)
-        out.append(str([[round(w[0] / 100 * float(dur)), round(w[1] / 100 * float(dur))] if w[0] >= 0 else w
-                        for w in windows]))
+    for pred, dur in zip(prediction, duration):
+        dur = float(dur)
+        out.append(str([[round((float(s_) / div) * dur, 2), round((float(e_) / div) * dur, 2)] if s_ != -1 and e_ != -1
+                        else [-1, -1] for s_, e_ in moment_str_to_list(pred)]))
     return out
 
 

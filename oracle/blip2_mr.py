@@ -1,8 +1,8 @@
 """fp32 restatement of BLIP2_MR.forward_mr / prompt_concatenation / generate
 (lavis/models/blip2_mr_models/blip2_mr.py:433-570, 572-824, 826-988) composed around the pinned
 sub-module oracles.  blip2_mr.py itself cannot be imported here (peft / tokenizer files absent), so
-this file follows it line by line; default branch only: input_time_format='seconds_integers',
-interleave_data=True, task='qformer_freeze_lora' (every lavis/projects/mr_BLIP yaml).
+this file follows it line by line: interleave_data=True, task='qformer_freeze_lora' (every lavis/projects/mr_BLIP
+yaml), input_time_format 'seconds_integers' (default) plus the other integer / float formats of utils.py:437-512.
 Test infrastructure only (see oracle/__init__.py)."""
 import torch
 
@@ -16,6 +16,26 @@ def seconds_integers(timestamps, durations, table):
     for t, dur in zip(timestamps, durations):
         ts.append([int(table.get(round(x.item()), round(x.item()))) for x in t])
         ds.append(table.get(round(dur.item()), round(dur.item())))
+    return ts, ds
+
+
+def time_values(fmt, timestamps, durations, table):
+    """Values whose str() the reference tokenises per frame, and per clip for the duration (blip2_mr.py:600-630 dispatch to
+    utils.py:388-529; the float formats go through a float32 tensor, so 149.6 reads back as 149.60000610351562)."""
+    if fmt == "seconds_integers":
+        return seconds_integers(timestamps, durations, table)
+    ts, ds = [], []
+    for t, dur in zip(timestamps, durations):
+        du = dur.item()
+        if fmt == "relative_integers":       # utils.py:437-461
+            ts.append([int(round(x.item() / du, 2) * 100) for x in t])
+        elif fmt == "seconds_floats":        # utils.py:464-484
+            ts.append(torch.tensor([round(x.item(), 2) for x in t]).tolist())
+        elif fmt == "relative_floats":       # utils.py:487-512 (the extra duration element is never indexed)
+            ts.append(torch.tensor([round(x.item() / du, 2) for x in t] + [round(du)]).tolist())
+        else:
+            raise ValueError(fmt)
+        ds.append(torch.as_tensor(durations)[len(ds)].item())      # durations pass through unchanged
     return ts, ds
 
 
@@ -39,11 +59,12 @@ def clean_timestamp_ids(tok, values):
 
 
 def prompt_concatenation(sd, d, tok, timestamps, durations, frames_for_t5, video_prompt_end, query_prompt,
-                         task_prompt, n_per_frame, table=None, max_txt_len=200, prefix=_t5.PREFIX):
+                         task_prompt, n_per_frame, table=None, max_txt_len=200, prefix=_t5.PREFIX,
+                         input_time_format="seconds_integers"):
     """blip2_mr.py:572-824, interleave branch:
        [f_0 (n) | ts_0 | f_1 | ts_1 | ... | '>' | duration] (left-padded) ++ video_prompt_end ++ query+task."""
     emb = sd[prefix + "shared.weight"]
-    ts, ds = seconds_integers(timestamps, durations, table or {})
+    ts, ds = time_values(input_time_format, timestamps, durations, table or {})
     end = tok(video_prompt_end, padding="longest", add_special_tokens=False, truncation=True,
               max_length=max_txt_len, return_tensors="pt")
     text = tok([q + t for q, t in zip(query_prompt, task_prompt)], padding="longest", truncation=True,
@@ -71,13 +92,14 @@ def prompt_concatenation(sd, d, tok, timestamps, durations, frames_for_t5, video
     return inputs, atts
 
 
-def forward_mr(sd, d, tok, samples, frame_token_aggregation=None, table=None, max_txt_len=200):
+def forward_mr(sd, d, tok, samples, frame_token_aggregation=None, table=None, max_txt_len=200,
+               input_time_format="seconds_integers"):
     """blip2_mr.py:433-570 -> dict(loss, logits, inputs_embeds, attention_mask, labels, ...)."""
     f, aux = frame_tokens(sd, d, samples["video"], frame_token_aggregation)
     n = 1 if frame_token_aggregation else d.num_query
     inputs, atts = prompt_concatenation(sd, d, tok, samples["timestamps"], samples["duration"], f,
                                         samples["video_prompt_end"], samples["query_prompt"],
-                                        samples["task_prompt"], n, table, max_txt_len)
+                                        samples["task_prompt"], n, table, max_txt_len, input_time_format=input_time_format)
     ans = tok(samples["relevant_windows"], padding="longest", truncation=True, max_length=max_txt_len,
               return_tensors="pt")
     labels = ans.input_ids.masked_fill(ans.input_ids == tok.pad_token_id, -100)

@@ -66,10 +66,11 @@ def test_full_dims_match_reference_shapes():
     assert (d.d_model, d.d_kv, d.t5_heads, d.d_ff, d.t5_layers, d.vocab) == (2048, 64, 32, 5120, 24, 32128)
 
 
-def test_prompt_table_matches_oracle_layout(tiny_sd):
+@pytest.mark.parametrize("fmt", ["seconds_integers", "seconds_floats", "relative_integers", "relative_floats"])
+def test_prompt_table_matches_oracle_layout(tiny_sd, fmt):
     from mr_blip_b200.blip2_mr import BLIP2_MR
     from oracle import blip2_mr as ob, synth
-    m = BLIP2_MR(dims=TINY, state_dict={k: v for k, v in tiny_sd.items()})
+    m = BLIP2_MR(dims=TINY, state_dict={k: v for k, v in tiny_sd.items()}, input_time_format=fmt)
     s = synth.make_samples(batch=3, frames=4, seed=6)
     s["duration"][2] = 1234.0                             # 4-digit duration -> two tokens -> ragged rows, left padding
     table, atts, prompts = m.build_prompt_table(s["timestamps"], s["duration"], 3, 4, 32, s["video_prompt_end"],
@@ -77,7 +78,8 @@ def test_prompt_table_matches_oracle_layout(tiny_sd):
     frames = torch.arange(3 * 4 * 32 * 4, dtype=torch.float32).view(3, 4 * 32, 4) + 1.0
     sd = {T5_PREFIX + "shared.weight": -torch.arange(32128 * 4, dtype=torch.float32).view(32128, 4) - 1.0}
     want, want_atts = ob.prompt_concatenation(sd, TINY, m.t5_tokenizer, s["timestamps"], s["duration"], frames,
-                                              s["video_prompt_end"], s["query_prompt"], s["task_prompt"], 32)
+                                              s["video_prompt_end"], s["query_prompt"], s["task_prompt"], 32,
+                                              input_time_format=fmt)
     assert table.shape == want.shape[:2] and torch.equal(atts, want_atts)
     emb, fr = sd[T5_PREFIX + "shared.weight"], frames.reshape(-1, 4)
     got = torch.zeros_like(want)
@@ -86,8 +88,11 @@ def test_prompt_table_matches_oracle_layout(tiny_sd):
             i = int(table[b, l])
             got[b, l] = emb[i] if i >= 0 else (0.0 if i == -2 ** 31 else fr[-(i + 1)])
     assert torch.equal(got, want)
-    assert (table[2] == -2 ** 31).sum() == 0 and (table[0] == -2 ** 31).sum() == 1   # shorter rows are left-padded
-    assert prompts[0].startswith(">") and prompts[0].count(">") == 5
+    if fmt == "seconds_integers":
+        assert (table[2] == -2 ** 31).sum() == 0 and (table[0] == -2 ** 31).sum() == 1   # shorter rows are left-padded
+        assert prompts[0].startswith(">") and prompts[0].count(">") == 5
+    else:
+        assert (table == -2 ** 31).any(axis=1).sum() >= 1                                # ragged rows exist and are padded
 
 
 def test_host_phase_bucket_padding_is_masked(tiny_sd):

@@ -122,6 +122,27 @@ def test_forward_backward_vs_oracle(model, tiny_sd, golden_dir, batch, frames, a
     assert not frozen
 
 
+@pytest.mark.parametrize("fmt", ["seconds_floats", "relative_integers", "relative_floats"])
+def test_other_time_formats_vs_oracle(model, tiny_sd, fmt):
+    """input_time_format other than seconds_integers (blip2_mr.py:600-630): several tokens per timestamp, ragged rows."""
+    from oracle import blip2_mr as ob, synth
+    samples = synth.make_samples(batch=2, frames=3, seed=12)
+    samples["duration"][1] = 37.0
+    samples["timestamps"][1] = samples["timestamps"][1] * (37.0 / 143.0)
+    model.train()
+    old, model.input_time_format = model.input_time_format, fmt
+    try:
+        res = model.forward_mr(samples, want_logits=True)
+        o = ob.forward_mr(dict(tiny_sd), TINY, model.t5_tokenizer, samples, input_time_format=fmt)
+    finally:
+        model.input_time_format = old
+    assert res["inputs_embeds"].shape == o["inputs_embeds"].shape
+    assert torch.equal(res["attention_mask"].cpu(), o["attention_mask"])
+    assert _relfro(res["inputs_embeds"], o["inputs_embeds"]) < 1e-3
+    assert abs(res["loss"].item() - o["loss"].item()) < 5e-3
+    assert _relfro(res["logits"], o["logits"]) < 2e-2
+
+
 def test_grad_scaling_and_accumulation(model):
     """scaler.scale(loss).backward() and two accumulated micro-steps (base_task.py:224-236) see scaled / summed grads."""
     from oracle import synth

@@ -108,6 +108,22 @@ def test_string_helpers_match_reference(golden_dir):
     assert o_ts == si["out_ts"] and o_d == si["out_dur"]
 
 
+def test_time_format_helpers_match_reference(golden_dir):
+    """relative_integers / seconds_floats / relative_floats and convert_to_absolute_time against the outputs of the
+    reference's own functions (tests/golden/make_golden_timefmt.py), incl. the strings the timestamps are tokenised from."""
+    gold = json.load(open(os.path.join(golden_dir, "time_formats_golden.json")))
+    ts = [torch.tensor(t) for t in gold["timestamps"]]
+    du = torch.tensor(gold["durations"])
+    for name in ("relative_integers", "seconds_floats", "relative_floats"):
+        t, d, prompts = getattr(mr_utils, "get_timestamps_as_" + name)(ts, du, {})
+        want = gold[name]
+        assert prompts == want["prompt"], name
+        assert [[str(v) for v in x.tolist()] for x in t] == want["ts_str"], name        # what _clean_ids tokenises
+        assert [float(x) for x in d] == want["dur"]
+    for fmt, (preds, want) in gold["absolute"].items():
+        assert mr_utils.convert_to_absolute_time(preds, gold["durations"], fmt) == want, fmt
+
+
 def test_beam_search_degenerates_to_greedy_and_respects_eos():
     V = 12
     table = torch.full((V, V), -5.0)
