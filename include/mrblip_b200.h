@@ -76,6 +76,10 @@ int mrb_rmsnorm_bwd(const float* x, const float* w, const void* dy, int dy_dtype
 /* frames fp32 [F,3,S,S] -> patch matrix [F*(S/P)^2, ldA] (16-bit), zero padded: A operand of the patch-embed GEMM
  * (eva_vit.py:196-203). */
 int mrb_patchify(const float* img, void* out, int dtype, int frames, int img_size, int patch, int ldA, void* stream);
+/* The same from RAW uint8 frames with the video processors' normalisation ((x/255 - mean) / std, CLIP constants of
+ * lavis/processors/blip_processors.py:61-70) fused in: bit-identical patch matrix, a quarter of the PCIe bytes. */
+int mrb_patchify_u8(const unsigned char* img, void* out, int dtype, int frames, int img_size, int patch, int ldA,
+                    float mean0, float mean1, float mean2, float std0, float std1, float std2, void* stream);
 /* x[f, 0, :] = cls_token + pos_embed[0]  (eva_vit.py:328-331) */
 int mrb_cls_pos(const float* cls, const float* pos, float* x, int frames, int tokens, int C, void* stream);
 

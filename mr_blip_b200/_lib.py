@@ -24,6 +24,7 @@ SIGNATURES = {
     "mrb_rmsnorm_bwd": [_p, _p, _p, _i, _ll, _p, _i, _f, _i, _i, _p, _p],
     "mrb_lora_up_add": [_p, _ll, _p, _i, _i, _i, _i, _p, _p],
     "mrb_patchify": [_p, _p, _i, _i, _i, _i, _i, _p],
+    "mrb_patchify_u8": [_p, _p, _i, _i, _i, _i, _i, _f, _f, _f, _f, _f, _f, _p],
     "mrb_cls_pos": [_p, _p, _p, _i, _i, _i, _p],
     "mrb_gated_gelu_fwd": [_p, _p, _i, _i, _ll, _i, _p],
     "mrb_gated_gelu_bwd": [_p, _p, _ll, _p, _ll, _i, _i, _i, _p],

@@ -47,11 +47,11 @@ class _GraphedStep:
     """Static input buffers + the captured CUDA graph of the device half of one training step, for one shape signature
     (clips, frames, encoder length, decoder length).  All small integer inputs travel in ONE pinned int32 buffer."""
 
-    def __init__(self, b, t, Le, Ld, img_size):
+    def __init__(self, b, t, Le, Ld, img_size, video_dtype=torch.float32):
         n = 2 * b * Le + 3 * b * Ld
         self.host = torch.empty(n, dtype=torch.int32).pin_memory()
         self.dev = torch.empty(n, dtype=torch.int32, device="cuda")
-        self.video = torch.empty((b, t, 3, img_size, img_size), dtype=torch.float32, device="cuda")
+        self.video = torch.empty((b, t, 3, img_size, img_size), dtype=video_dtype, device="cuda")
         self.loss = torch.zeros((1,), dtype=torch.float32, device="cuda")
         self.h, self.d = {}, {}
         off = 0
@@ -233,7 +233,10 @@ class BLIP2_MR(Blip2Base):
         if isinstance(image, list):
             image = torch.stack(image)
         b, t = image.shape[:2]
-        img = image.reshape(b * t, *image.shape[2:]).to(device="cuda", dtype=torch.float32, non_blocking=True)
+        img = image.reshape(b * t, *image.shape[2:])
+        # raw uint8 frames stay uint8 (normalisation is fused into the patch extraction); anything else is the reference's fp32
+        img = img.to(device="cuda", non_blocking=True) if img.dtype == torch.uint8 else \
+            img.to(device="cuda", dtype=torch.float32, non_blocking=True)
         x = vit.forward(img)
         h, h16 = qf.forward(x, b * t)
         f = qf.project(h16)
@@ -438,15 +441,17 @@ class BLIP2_MR(Blip2Base):
 
     def _graphed_step(self, samples):
         host = self._host_phase(samples, bucket=self.graph_bucket)
-        key = (host["b"], host["t"], host["Le"], host["Ld"], bool(self.frame_token_aggregation))
+        video = self._video_of(samples)
+        vdt = torch.uint8 if video.dtype == torch.uint8 else torch.float32
+        key = (host["b"], host["t"], host["Le"], host["Ld"], bool(self.frame_token_aggregation), vdt)
         st = self._steps.pop(key, None)
         if st is None:
             while len(self._steps) >= self.max_graphs:       # least recently used shape goes first
                 self._steps.pop(next(iter(self._steps)))
-            st = _GraphedStep(host["b"], host["t"], host["Le"], host["Ld"], self.dims.img_size)
+            st = _GraphedStep(host["b"], host["t"], host["Le"], host["Ld"], self.dims.img_size, vdt)
         self._steps[key] = st
         self.engines()
-        st.stage(host, self._video_of(samples))
+        st.stage(host, video)
         seen = self._seen[key] = self._seen.get(key, 0) + 1
         if st.graph is not None:
             st.graph.replay()
@@ -477,7 +482,9 @@ class BLIP2_MR(Blip2Base):
             return {"loss": _HandOverGrads.apply(loss, self, *self._grad_params)}
         host = self._host_phase(samples)
         dev = {k: torch.from_numpy(host[k]).to("cuda", non_blocking=True) for k in ("idx", "kmask", "labels", "dec_ids", "dmask")}
-        video = self._video_of(samples).to(device="cuda", dtype=torch.float32, non_blocking=True)
+        video = self._video_of(samples)
+        video = video.to(device="cuda", non_blocking=True) if video.dtype == torch.uint8 else \
+            video.to(device="cuda", dtype=torch.float32, non_blocking=True)
         out = self._device_phase(video, dev["idx"], dev["kmask"], dev["labels"].to(torch.int64), dev["dec_ids"].to(torch.int64),
                                  dev["dmask"], need_grad, want_logits)
         loss = out["loss"].reshape(())

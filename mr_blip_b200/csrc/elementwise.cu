@@ -198,6 +198,37 @@ __global__ void patchify_kernel(const float* __restrict__ img, void* __restrict_
   }
 }
 
+// Same patch extraction from RAW uint8 frames [F,3,S,S] with the processors' normalisation fused in
+// (lavis/processors/blip_processors.py:61-70, 355-395: ToTensorVideo x/255, then NormalizeVideo (x - mean) / std, in that
+// operation order so the fp32 value -- and hence the fp16 patch matrix -- is bit-identical to the host-normalised path).
+// A clip then crosses PCIe as 9 MB instead of 36 MB.
+struct NormConst { float mean[3], std[3]; };
+__global__ void patchify_u8_kernel(const uint8_t* __restrict__ img, void* __restrict__ out, int dtype, int F, int S, int P,
+                                   int ldA, NormConst nc) {
+  const int G = S / P;
+  const long long total = static_cast<long long>(F) * G * G * 3 * P;
+  const long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  if (idx >= total) return;
+  const int px = idx % G;
+  long long r = idx / G;
+  const int i = r % P; r /= P;
+  const int c = r % 3; r /= 3;
+  const int py = r % G;
+  const int f = r / G;
+  const uint8_t* src = img + ((static_cast<long long>(f) * 3 + c) * S + (py * P + i)) * S + px * P;
+  uint16_t* dst = static_cast<uint16_t*>(out) + (static_cast<long long>(f) * G * G + py * G + px) * ldA + (c * P + i) * P;
+  const float mean = nc.mean[c], sd = nc.std[c];
+  for (int j = 0; j + 1 < P; j += 2) {
+    const float a = __fdiv_rn(__fdiv_rn(static_cast<float>(src[j]), 255.0f) - mean, sd);
+    const float b = __fdiv_rn(__fdiv_rn(static_cast<float>(src[j + 1]), 255.0f) - mean, sd);
+    *reinterpret_cast<uint32_t*>(dst + j) = pack2(a, b, dtype);
+  }
+  if (P & 1) dst[P - 1] = static_cast<uint16_t>(pack2(__fdiv_rn(__fdiv_rn(static_cast<float>(src[P - 1]), 255.0f) - mean, sd), 0.f, dtype) & 0xffff);
+  if (c == 2 && i == P - 1) {
+    for (int k = 3 * P * P; k < ldA; ++k) dst[k - (c * P + i) * P] = 0;
+  }
+}
+
 // x[f, 0, :] = cls + pos[0]   (eva_vit.py:328-331)
 __global__ void cls_pos_kernel(const float* __restrict__ cls, const float* __restrict__ pos, float* __restrict__ x,
                                int F, int tokens, int C) {
@@ -660,6 +691,19 @@ extern "C" int mrb_patchify(const float* img, void* out, int dtype, int frames, 
   const int G = img_size / patch;
   const long long total = static_cast<long long>(frames) * G * G * 3 * patch;
   patchify_kernel<<<blocks_for(total, 256), 256, 0, STREAM>>>(img, out, dtype, frames, img_size, patch, ldA);
+  MRB_CHECK_LAUNCH();
+  return MRB_OK;
+}
+
+extern "C" int mrb_patchify_u8(const unsigned char* img, void* out, int dtype, int frames, int img_size, int patch, int ldA,
+                               float mean0, float mean1, float mean2, float std0, float std1, float std2, void* stream) {
+  if (frames <= 0) return MRB_OK;
+  if (img_size % patch || (patch & 1) || ldA < 3 * patch * patch || (ldA & 7)) return MRB_ERR_ARG;
+  if (!(std0 > 0.f && std1 > 0.f && std2 > 0.f)) return MRB_ERR_ARG;
+  const int G = img_size / patch;
+  const long long total = static_cast<long long>(frames) * G * G * 3 * patch;
+  NormConst nc{{mean0, mean1, mean2}, {std0, std1, std2}};
+  patchify_u8_kernel<<<blocks_for(total, 256), 256, 0, STREAM>>>(img, out, dtype, frames, img_size, patch, ldA, nc);
   MRB_CHECK_LAUNCH();
   return MRB_OK;
 }

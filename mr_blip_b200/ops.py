@@ -120,6 +120,14 @@ def patchify(img, out, img_size, patch):
               out.stride(0), _stream())
 
 
+def patchify_u8(img, out, img_size, patch, mean, std):
+    """Raw uint8 frames [F,3,S,S] -> normalised 16-bit patch matrix ((x/255 - mean) / std fused)."""
+    _check(img, torch.uint8)
+    assert img.is_contiguous()
+    _lib.call("mrb_patchify_u8", img.data_ptr(), out.data_ptr(), _DT[out.dtype], img.shape[0], img_size, patch, out.stride(0),
+              float(mean[0]), float(mean[1]), float(mean[2]), float(std[0]), float(std[1]), float(std[2]), _stream())
+
+
 def cls_pos(cls, pos, x, frames, tokens, C):
     _lib.call("mrb_cls_pos", cls.data_ptr(), pos.data_ptr(), x.data_ptr(), frames, tokens, C, _stream())
 

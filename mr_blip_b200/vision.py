@@ -51,13 +51,21 @@ class VitEngine:
                 fc1_w=_h(get(b + "mlp.fc1.weight")), fc1_b=_f(get(b + "mlp.fc1.bias")),
                 fc2_w=_h(get(b + "mlp.fc2.weight")), fc2_b=_f(get(b + "mlp.fc2.bias"))))
 
+    # CLIP normalisation of the video processors (lavis/processors/blip_processors.py:61-70), used when raw uint8 frames come in
+    PIXEL_MEAN = (0.48145466, 0.4578275, 0.40821073)
+    PIXEL_STD = (0.26862954, 0.26130258, 0.27577711)
+
     def forward(self, image, return_all=False):
-        """image fp32 [F,3,S,S] (cuda) -> residual stream fp32 [F*257, W]."""
+        """image fp32 [F,3,S,S] (cuda, already normalised as the dataset yields it) or raw uint8 [F,3,S,S] (normalisation
+        fused into the patch extraction) -> residual stream fp32 [F*257, W]."""
         d = self.d
         F_, W, T = image.shape[0], d.vit_width, d.vit_tokens
         M = F_ * T
         A = torch.empty((F_ * d.n_patches, self.k_patch), dtype=H16, device="cuda")
-        ops.patchify(image.contiguous(), A, d.img_size, d.patch)
+        if image.dtype == torch.uint8:
+            ops.patchify_u8(image.contiguous(), A, d.img_size, d.patch, self.PIXEL_MEAN, self.PIXEL_STD)
+        else:
+            ops.patchify(image.contiguous(), A, d.img_size, d.patch)
         x = torch.empty((M, W), dtype=torch.float32, device="cuda")
         ops.cls_pos(self.cls, self.pos, x, F_, T, W)
         ops.gemm(A, self.patch_w, out=x, bias=self.patch_b, resid=self.pos, row_group=d.n_patches)

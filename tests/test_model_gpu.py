@@ -143,6 +143,29 @@ def test_other_time_formats_vs_oracle(model, tiny_sd, fmt):
     assert _relfro(res["logits"], o["logits"]) < 2e-2
 
 
+def test_uint8_frames_equal_host_normalised_frames(model):
+    """samples["video"] as raw uint8 (normalisation fused into the patch extraction, a quarter of the H2D bytes) gives the
+    same loss and gradients as the reference's host-normalised fp32 frames -- eager and graph-replayed."""
+    from oracle import synth
+    from mr_blip_b200.vision import VitEngine
+    s = synth.make_samples(batch=2, frames=3, seed=31)
+    g = torch.Generator().manual_seed(5)
+    u8 = torch.randint(0, 256, s["video"].shape, generator=g, dtype=torch.uint8)
+    mean = torch.tensor(VitEngine.PIXEL_MEAN).view(1, 1, 3, 1, 1)
+    std = torch.tensor(VitEngine.PIXEL_STD).view(1, 1, 3, 1, 1)
+    model.train()
+    s["video"] = (u8.float() / 255.0 - mean) / std
+    want = _train_grads(model, s)
+    s["video"] = u8
+    for _ in range(3):                                       # eager, capture, replay
+        got = _train_grads(model, s)
+        assert abs(got[0] - want[0]) < 1e-6
+        for n, gr in got[1].items():
+            assert _relfro(gr, want[1][n]) < 2e-3, n         # fp32 atomics order only
+    for q in model.parameters():
+        q.grad = None
+
+
 def test_grad_scaling_and_accumulation(model):
     """scaler.scale(loss).backward() and two accumulated micro-steps (base_task.py:224-236) see scaled / summed grads."""
     from oracle import synth
