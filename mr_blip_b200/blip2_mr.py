@@ -182,10 +182,14 @@ class BLIP2_MR(Blip2Base):
             elif path:
                 logging.warning("%s checkpoint %s is not a local file; keeping seeded weights", key, path)
 
+    def reset_graphs(self):
+        """Drop every captured step graph (and the private memory pool they share: a pool handle is only valid while
+        one of its graphs is alive)."""
+        self._steps, self._seen, self._graph_pool = {}, {}, None
+
     def _weights_changed(self):
         self._engines = None
-        self._steps = {}
-        self._seen = {}
+        self.reset_graphs()
 
     # ---------------------------------------------------------------------------------------------
     def _get(self, name):
@@ -203,7 +207,7 @@ class BLIP2_MR(Blip2Base):
             vit, qf, t5 = VitEngine(d, self._get), QFormerEngine(d, self._get), T5Engine(d, self._get)
             self._engines = (vit, qf, t5)
             self._lora_versions = None
-            self._steps, self._seen = {}, {}
+            self.reset_graphs()
             # every trainable gradient lives in one flat fp32 buffer: zeroed / scaled / all-reduced with single launches
             pw, pb = self.t5_proj.weight, self.t5_proj.bias
             n = t5.n_grad_elems()
@@ -448,6 +452,8 @@ class BLIP2_MR(Blip2Base):
         if st is None:
             while len(self._steps) >= self.max_graphs:       # least recently used shape goes first
                 self._steps.pop(next(iter(self._steps)))
+            if not any(x.graph is not None for x in self._steps.values()):
+                self._graph_pool = None                      # no live graph holds the old pool any more
             st = _GraphedStep(host["b"], host["t"], host["Le"], host["Ld"], self.dims.img_size, vdt)
         self._steps[key] = st
         self.engines()

@@ -579,7 +579,8 @@ class T5Engine:
                   "bias": self._bias(self.dec_bias, max_len, max_len, False)}
             st["k"] = [st["kv"][2 * i] for i in range(nl)]
             st["v"] = [st["kv"][2 * i + 1] for i in range(nl)]
-            self._dec_states = {key: st}                      # one shape at a time (its graphs hold a private pool)
+            self._dec_states = {key: st}                      # one shape at a time (its graphs hold a private pool,
+            self._dec_pool = None                             #  which dies with the previous shape's graphs)
         for layer, ckv in zip(self.dec, st["cross"]):
             layer["ckv"].forward(enc_ext, B * Le, out=ckv[:, :2 * inner])
         st["uses"] += 1

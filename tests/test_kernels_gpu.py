@@ -262,17 +262,19 @@ def test_patchify_matches_conv_unfold(ops):
 
 
 def test_patchify_uint8_fused_normalise_is_bit_exact(ops):
-    """Raw uint8 frames + fused (x/255 - mean) / std == the processors' host normalisation followed by the fp32 path."""
+    """Raw uint8 frames + fused (x/255 - mean) / std == the processors' host normalisation followed by the fp32 path.
+    The reference normalises on the CPU (dataloader workers), where torch divides exactly; torch's CUDA `x / 255.0`
+    multiplies by a reciprocal instead and differs in the last bit for half of the byte values."""
     F, S, P = 3, 224, 14
-    g = torch.Generator(device="cuda").manual_seed(77)
-    u8 = torch.randint(0, 256, (F, 3, S, S), generator=g, device="cuda", dtype=torch.uint8)
-    mean = torch.tensor([0.48145466, 0.4578275, 0.40821073], device="cuda").view(1, 3, 1, 1)
-    std = torch.tensor([0.26862954, 0.26130258, 0.27577711], device="cuda").view(1, 3, 1, 1)
-    x = (u8.float() / 255.0 - mean) / std                     # ToTensorVideo + NormalizeVideo (blip_processors.py:355-395)
+    g = torch.Generator().manual_seed(77)
+    u8 = torch.randint(0, 256, (F, 3, S, S), generator=g, dtype=torch.uint8)
+    mean = torch.tensor([0.48145466, 0.4578275, 0.40821073]).view(1, 3, 1, 1)
+    std = torch.tensor([0.26862954, 0.26130258, 0.27577711]).view(1, 3, 1, 1)
+    x = (u8.float() / 255.0 - mean) / std                     # ToTensorVideo + NormalizeVideo (blip_processors.py:355-395), CPU
     a = torch.zeros((F * 256, 592), dtype=torch.float16, device="cuda")
     b = torch.ones((F * 256, 592), dtype=torch.float16, device="cuda")
-    ops.patchify(x.contiguous(), a, S, P)
-    ops.patchify_u8(u8, b, S, P, mean.flatten().tolist(), std.flatten().tolist())
+    ops.patchify(x.cuda().contiguous(), a, S, P)
+    ops.patchify_u8(u8.cuda(), b, S, P, mean.flatten().tolist(), std.flatten().tolist())
     assert torch.equal(a, b)
 
 

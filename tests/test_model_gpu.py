@@ -85,7 +85,9 @@ def test_t5_loss_logits_grads_vs_reference_golden(model, golden_dir):
             assert _relfro(got, gold[k]) < 4e-2, k
 
 
-@pytest.mark.parametrize("batch,frames,agg,seed", [(2, 3, None, 3), (3, 2, None, 5), (2, 4, "mean", 9), (1, 1, None, 1)])
+# (1, 4, None, 4) is BASELINE.json configs[0]: one clip, 4 frames, 8-word query
+@pytest.mark.parametrize("batch,frames,agg,seed", [(2, 3, None, 3), (3, 2, None, 5), (2, 4, "mean", 9), (1, 1, None, 1),
+                                                   (1, 4, None, 4)])
 def test_forward_backward_vs_oracle(model, tiny_sd, golden_dir, batch, frames, agg, seed):
     from oracle import blip2_mr as ob, synth
     samples = synth.make_samples(batch=batch, frames=frames, seed=seed, query_words=8 if seed == 3 else 4 + seed)
@@ -202,8 +204,7 @@ def test_graphed_step_matches_eager_step(model, agg):
         model.cuda_graphs = False
         want_a, want_b = _train_grads(model, a), _train_grads(model, b)
         model.cuda_graphs, model.graph_bucket = True, (16, 4)
-        model._steps.clear()
-        model._seen.clear()
+        model.reset_graphs()
         for rnd, (s, want) in enumerate([(a, want_a), (b, want_b), (a, want_a), (b, want_b)]):
             loss, grads = _train_grads(model, s)
             assert abs(loss - want[0]) < 1e-4, (rnd, loss, want[0])

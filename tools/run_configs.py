@@ -48,8 +48,7 @@ def main():
                      "loss_finite": bool(torch.isfinite(loss))}
         print(name, res[name], flush=True)
         model.frame_token_aggregation = None
-        model._steps.clear()
-        model._seen.clear()
+        model.reset_graphs()
         torch.cuda.empty_cache()
 
     train_cfg("charades_sta_b8_t20_mean", 8, 20, "mean", 120.0)
