@@ -161,7 +161,7 @@ def test_uint8_frames_equal_host_normalised_frames(model):
     s["video"] = u8
     for _ in range(3):                                       # eager, capture, replay
         got = _train_grads(model, s)
-        assert abs(got[0] - want[0]) < 1e-6
+        assert abs(got[0] - want[0]) < 2e-5                  # the loss is an atomic fp32 sum over target rows: order varies
         for n, gr in got[1].items():
             assert _relfro(gr, want[1][n]) < 2e-3, n         # fp32 atomics order only
     for q in model.parameters():
