@@ -27,7 +27,7 @@ METRIC = "video_clips_per_sec_fwd_bwd_qvh60"
 UNIT = "clips/s"
 BATCH, FRAMES, QUERY_WORDS = 4, 60, 32
 FLOPS_PER_CLIP = 44.83e12          # GEMM + attention FLOPs, fwd+bwd, one 60-frame QVH clip
-NCU_FC1_TRAFFIC = 932.5e6          # dram__bytes_read.sum + dram__bytes_write.sum, one fc1 launch (profiles/ncu_gemm2_fc1_r01c.csv)
+NCU_FC1_TRAFFIC = 920.2e6          # dram__bytes_read.sum + dram__bytes_write.sum, one fc1 launch (profiles/ncu_gemm2_fc1_r01c.csv)
 
 
 _JSON_FD = None
