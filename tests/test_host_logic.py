@@ -59,6 +59,24 @@ def test_model_surface_and_state_dict_names(tiny_sd):
     assert not msg.unexpected_keys
 
 
+def test_blip2_t5_surface(tiny_sd):
+    """registry name, plain HF T5 state-dict names (no peft wrapper), trainable split of blip2_t5.py:60-90, no CPU path."""
+    from mr_blip_b200.blip2_t5 import Blip2T5, plain_t5_state_dict
+    from mr_blip_b200.registry import registry
+    assert registry.get_model_class("blip2_t5") is Blip2T5
+    plain = plain_t5_state_dict(tiny_sd)
+    m = Blip2T5(dims=TINY, state_dict=plain)
+    keys = set(m.state_dict())
+    assert keys == set(plain) and not any("lora_" in k or "base_layer" in k or "base_model" in k for k in keys)
+    for k in ("t5_model.shared.weight", "t5_model.encoder.block.0.layer.0.SelfAttention.q.weight", "t5_model.lm_head.weight",
+              "t5_model.decoder.block.1.layer.1.EncDecAttention.v.weight", "Qformer.bert.encoder.layer.0.crossattention.self.key.weight"):
+        assert k in keys, k
+    trainable = {n for n, p in m.named_parameters() if p.requires_grad}
+    assert all(n.startswith(("Qformer.", "t5_proj.")) or n == "query_tokens" for n in trainable) and "t5_proj.weight" in trainable
+    with pytest.raises(RuntimeError, match="no CPU"):
+        m({"image": torch.zeros(1, 3, 224, 224), "text_input": ["a"], "text_output": ["b"]})
+
+
 def test_full_dims_match_reference_shapes():
     d = FULL
     assert (d.vit_width, d.vit_depth, d.vit_heads, d.vit_mlp, d.vit_tokens, d.vit_head_dim) == (1408, 39, 16, 6144, 257, 88)

@@ -277,3 +277,23 @@ def test_generate_vs_oracle_beam_search(model, tiny_sd):
     want1 = ob.generate(tiny_sd, TINY, model.t5_tokenizer, samples, post_process, num_beams=1, max_length=6)
     assert greedy["sequences"].tolist() == want1["sequences"].tolist()
     assert set(out) >= {"prediction", "raw_prediction", "answer", "qid", "duration"}
+
+
+def test_blip2_t5_forward_and_generate_vs_oracle():
+    """BASELINE.json configs[0] family: Blip2T5 (blip2_t5.py:99-255) on the shared kernels vs its fp32 restatement."""
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from mr_blip_b200.blip2_t5 import Blip2T5, plain_t5_state_dict
+    from oracle import blip2_t5 as obt
+    sd0 = init_state_dict(TINY, seed=1234, lora_b_std=0.0)            # zero adapters == the plain frozen T5
+    model = Blip2T5(dims=TINY, state_dict=plain_t5_state_dict(sd0)).cuda().eval()
+    g = torch.Generator().manual_seed(3)
+    samples = {"image": torch.randn(2, 3, 224, 224, generator=g), "text_input": ["a photo of", "Question: what is shown? Answer:"],
+               "text_output": ["a dog in the garden", "two friends"], "prompt": ["a photo of", "Question: what is shown? Answer:"]}
+    got = model(samples)["loss"].item()
+    want = obt.forward(sd0, TINY, model.t5_tokenizer, samples)
+    assert abs(got - want["loss"].item()) < 5e-3
+    assert _relfro(model._last_logits, want["logits"]) < 2e-2
+    text = model.generate(samples, num_beams=3, max_length=6)
+    want_text, want_seqs = obt.generate(sd0, TINY, model.t5_tokenizer, samples, num_beams=3, max_length=6)
+    assert model._last_sequences.tolist() == want_seqs.tolist() and text == want_text
