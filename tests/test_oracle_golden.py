@@ -124,6 +124,25 @@ def test_time_format_helpers_match_reference(golden_dir):
         assert mr_utils.convert_to_absolute_time(preds, gold["durations"], fmt) == want, fmt
 
 
+def test_moment_retrieval_metrics_match_reference(golden_dir):
+    """R1@IoU / mIoU / mAP@IoU / invalid count against the reference's own evaluation code run on synthetic predictions
+    (tests/golden/make_golden_mr_eval.py), plus the task-level report built from window strings."""
+    from mr_blip_b200 import mr_eval
+    gold = json.load(open(os.path.join(golden_dir, "mr_eval_golden.json")))
+    sa = gold["single_ap"]
+    assert np.allclose(mr_eval.average_precision(sa["gt"], sa["pred"]), sa["ap"], atol=1e-12)
+    for case in gold["cases"]:
+        got = mr_eval.moment_retrieval_metrics(case["records"])
+        assert got["MR-mAP"] == case["MR-mAP"] and got["MR-R1"] == case["MR-R1"]
+        assert abs(got["MR-R1-avg"] - case["MR-R1-avg"]) < 1e-9 and abs(got["MR-mIoU"] - case["MR-mIoU"]) < 1e-12
+        assert got["MR-invalid_pred_num"] == case["MR-invalid_pred_num"]
+    recs = gold["cases"][1]["records"]
+    results = [{"qid": r["qid"], "prediction": str(r["pred_relevant_windows"]), "target": str(r["relevant_windows"])} for r in recs]
+    rep = mr_eval.report_metrics(results)
+    assert rep["total"] == len(recs) and rep["r1"] == gold["cases"][1]["MR-R1"] and rep["mAP"] == gold["cases"][1]["MR-mAP"]
+    assert abs(rep["agg_metrics"] - gold["cases"][1]["MR-R1-avg"]) < 1e-9
+
+
 def test_beam_search_degenerates_to_greedy_and_respects_eos():
     V = 12
     table = torch.full((V, V), -5.0)
