@@ -241,9 +241,11 @@ class BLIP2_MR(Blip2Base):
         # raw uint8 frames stay uint8 (normalisation is fused into the patch extraction); anything else is the reference's fp32
         img = img.to(device="cuda", non_blocking=True) if img.dtype == torch.uint8 else \
             img.to(device="cuda", dtype=torch.float32, non_blocking=True)
-        x = vit.forward(img)
-        h, h16 = qf.forward(x, b * t)
-        f = qf.project(h16)
+        with ops.phase("vit"):
+            x = vit.forward(img)
+        with ops.phase("qformer"):
+            h, h16 = qf.forward(x, b * t)
+            f = qf.project(h16)
         n = self.dims.num_query
         if self.frame_token_aggregation:
             assert self.frame_token_aggregation in ["mean"], "Invalid aggregation method, please choose from ['mean']"

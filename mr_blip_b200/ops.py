@@ -1,6 +1,8 @@
 """Torch-tensor front end of the C ABI: checks devices/dtypes/contiguity, passes raw device pointers
 and the current CUDA stream.  PyTorch here is plumbing only (allocation, streams); all arithmetic on
 the hot path happens inside libmrblip_b200.so."""
+import os
+
 import torch
 
 from . import _lib
@@ -10,6 +12,26 @@ _DT = {torch.float16: F16, torch.bfloat16: BF16, torch.float32: F32}
 INT_MIN = -2 ** 31
 USE_TC_ATTENTION = True
 GEMM_PROFILE = None      # set to a list to record (M, N, K, cuda start event, cuda end event) per GEMM launch
+
+
+NVTX = os.environ.get("MRB_NVTX", "0") == "1"     # MRB_NVTX=1: NVTX ranges around the phases of a step (nsys / ncu --nvtx)
+
+
+class phase:
+    """`with ops.phase("vit"):` -- an NVTX range when MRB_NVTX=1, nothing otherwise (the reference has no tracing hooks,
+    SURVEY.md §5; ranges are host-side, so under graph replay they bracket the capture / eager launches only)."""
+
+    def __init__(self, name):
+        self.name = name
+
+    def __enter__(self):
+        if NVTX:
+            torch.cuda.nvtx.range_push("mrb:" + self.name)
+
+    def __exit__(self, *a):
+        if NVTX:
+            torch.cuda.nvtx.range_pop()
+        return False
 
 
 def _stream():

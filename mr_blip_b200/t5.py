@@ -529,8 +529,10 @@ class T5Engine:
         x = inputs_embeds.reshape(B * Le, D).contiguous()
         enc_saves = [] if backward else None
         dec_saves = [] if backward else None
-        enc_ext, enc_h, enc_bias = self.encoder_forward(x, kmask, B, Le, enc_saves)
-        dec_ext, dec_h, dec_bias = self.decoder_forward(dec_ids, dmask, enc_ext, kmask, B, Ld, Le, dec_saves)
+        with ops.phase("t5_encoder_fwd"):
+            enc_ext, enc_h, enc_bias = self.encoder_forward(x, kmask, B, Le, enc_saves)
+        with ops.phase("t5_decoder_fwd"):
+            dec_ext, dec_h, dec_bias = self.decoder_forward(dec_ids, dmask, enc_ext, kmask, B, Ld, Le, dec_saves)
         M = B * Ld
         logits = self.lm_head.forward(dec_ext, M, out_dtype=torch.float32)       # [M, V] fp32
         flat = labels.reshape(-1).contiguous()
@@ -543,9 +545,11 @@ class T5Engine:
             out["logits"] = logits.view(B, Ld, d.vocab)
             out["encoder_last_hidden_state"] = enc_ext[:, :D].float().view(B, Le, D)
         if backward:
-            ddec = self.lm_head.backward(dlogits, dec_ext, M)
-            d_enc = self.decoder_backward(dec_saves, dec_h, ddec, dmask, enc_ext, kmask, B, Ld, Le, dec_bias)
-            d_in = self.encoder_backward(enc_saves, enc_h, d_enc, kmask, B, Le, enc_bias)
+            with ops.phase("t5_decoder_bwd"):
+                ddec = self.lm_head.backward(dlogits, dec_ext, M)
+                d_enc = self.decoder_backward(dec_saves, dec_h, ddec, dmask, enc_ext, kmask, B, Ld, Le, dec_bias)
+            with ops.phase("t5_encoder_bwd"):
+                d_in = self.encoder_backward(enc_saves, enc_h, d_enc, kmask, B, Le, enc_bias)
             self.scale_grads()
             out["d_inputs_embeds"] = d_in.view(B, Le, D)
         return out
