@@ -77,6 +77,51 @@ def test_blip2_t5_surface(tiny_sd):
         m({"image": torch.zeros(1, 3, 224, 224), "text_input": ["a"], "text_output": ["b"]})
 
 
+def test_yaml_recipes_build_models(tmp_path):
+    """Config loader with the merge order of lavis/common/config.py (model defaults <- recipe <- --options), on the shipped
+    mr_BLIP recipes and on a recipe in the reference's own layout; from_config reads the merged model section."""
+    from mr_blip_b200.config import Config, build_model
+    from mr_blip_b200.blip2_mr import BLIP2_MR
+    base = os.path.join(ROOT, "mr_blip_b200", "configs", "projects", "mr_BLIP", "train")
+    frames = {"qvh": (60, 1, 8), "charades": (20, 8, 1), "anet": (60, 1, 4)}          # n_frms, batch, accum of the reference recipes
+    for name, (n_frms, bs, acc) in frames.items():
+        cfg = Config(os.path.join(base, name + ".yaml"))
+        assert cfg.n_frames() == n_frms and cfg.run_cfg.batch_size_train == bs and cfg.run_cfg.accum_grad_iters == acc
+        assert cfg.model_cfg.arch == "blip2_mr" and cfg.model_cfg.t5_model == "google/flan-t5-xl"      # from the model defaults
+        assert cfg.model_cfg.get("num_query_token") == 32 and cfg.model_cfg.task == "qformer_freeze_lora"
+    model, cfg = build_model(os.path.join(base, "charades.yaml"),
+                             options=["model.frame_token_aggregation=mean", "model.input_time_format=relative_integers",
+                                      "run.batch_size_train=4"], dims=TINY)
+    assert isinstance(model, BLIP2_MR) and model.frame_token_aggregation == "mean" and model.input_time_format == "relative_integers"
+    assert cfg.run_cfg.batch_size_train == 4 and model.task == "qformer_freeze_lora"
+    ref_style = tmp_path / "qvh_ref_layout.yaml"
+    ref_style.write_text("""
+model:
+  arch: blip2_mr
+  model_type: pretrain_flant5xl
+  load_finetuned: False # True
+  freeze_vit: True
+  task: qformer_freeze_lora
+  input_time_format: seconds_integers # [seconds_integers | seconds_floats]
+  interleave_data: True
+  frame_token_aggregation: False # [mean | False]
+datasets:
+  qvh: # name of the dataset builder
+    vis_processor:
+        train:
+          name: "blip2_video_train"
+          n_frms: 60
+run:
+  task: moment_retrieval
+  init_lr: 3e-4
+  accum_grad_iters: 8
+""")
+    m2, c2 = build_model(str(ref_style), dims=TINY)
+    assert not m2.frame_token_aggregation and c2.n_frames() == 60 and c2.run_cfg.init_lr == 3e-4 and c2.model_cfg.image_size == 224
+    with pytest.raises(AssertionError):
+        Config(str(ref_style), options=["model.arch=not_a_model"])
+
+
 def test_full_dims_match_reference_shapes():
     d = FULL
     assert (d.vit_width, d.vit_depth, d.vit_heads, d.vit_mlp, d.vit_tokens, d.vit_head_dim) == (1408, 39, 16, 6144, 257, 88)
