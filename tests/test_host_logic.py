@@ -203,3 +203,34 @@ def test_init_is_seed_deterministic():
     c = init_state_dict(TINY, seed=6, parts=("qformer",))
     assert all(torch.equal(a[k], b[k]) for k in a)
     assert not torch.equal(a["t5_proj.weight"], c["t5_proj.weight"])
+
+
+def test_optimizer_groups_and_scheduler_from_recipe():
+    """Stand-alone training set-up from a shipped recipe: the decay / no-decay split of lavis/runners/runner_base.py:108-124
+    on the model's trainable tensors (LoRA factors and t5_proj.weight decay, t5_proj.bias does not, frozen towers are
+    absent), AdamW betas, and the recipe's scheduler stepping the optimiser's lr."""
+    from mr_blip_b200 import optim
+    from mr_blip_b200.config import build_model
+    model, cfg = build_model(os.path.join(ROOT, "mr_blip_b200", "configs", "projects", "mr_BLIP", "train", "charades.yaml"),
+                             dims=TINY)
+    groups, n = optim.param_groups(model, cfg.run_cfg.weight_decay)
+    names = {id(p): k for k, p in model.named_parameters()}
+    wd = {names[id(p)] for p in groups[0]["params"]}
+    no_wd = {names[id(p)] for p in groups[1]["params"]}
+    assert groups[0]["weight_decay"] == 0.05 and groups[1]["weight_decay"] == 0
+    assert no_wd == {"t5_proj.bias"} and "t5_proj.weight" in wd
+    assert all(("lora_" in k) or k == "t5_proj.weight" for k in wd) and any("lora_A" in k for k in wd) and any("lora_B" in k for k in wd)
+    trainable = [p for p in model.parameters() if p.requires_grad]
+    assert n == sum(p.numel() for p in trainable) and len(wd) + len(no_wd) == len(trainable)
+    opt = optim.build_optimizer(model, cfg.run_cfg.init_lr, cfg.run_cfg.weight_decay)
+    assert isinstance(opt, torch.optim.AdamW) and opt.defaults["betas"] == (0.9, 0.999) and opt.defaults["lr"] == 3e-4
+    sched = optim.build_lr_scheduler(opt, cfg.run_cfg)
+    assert isinstance(sched, optim.LinearWarmupCosineLRScheduler) and sched.warmup_steps == 698 and sched.max_epoch == 20
+    sched.step(cur_epoch=0, cur_step=0)
+    assert all(g["lr"] == 1e-8 for g in opt.param_groups)
+    sched.step(cur_epoch=0, cur_step=349)
+    assert all(abs(g["lr"] - (1e-8 + (3e-4 - 1e-8) * 349 / 698)) < 1e-15 for g in opt.param_groups)
+    sched.step(cur_epoch=10, cur_step=0)                                              # past warm-up: half-way down the cosine
+    assert all(abs(g["lr"] - 1.5e-4) < 1e-12 for g in opt.param_groups)
+    with pytest.raises(KeyError):
+        optim.build_lr_scheduler(opt, {"lr_sched": "nope", "max_epoch": 1, "min_lr": 0, "init_lr": 1})
