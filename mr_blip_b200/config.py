@@ -91,6 +91,12 @@ class Config:
             node[parts[-1]] = _parse_value(val)
         return out
 
+    def to_dict(self):
+        """Plain nested dicts {"run", "model", "datasets"} -- what the runner stores in a checkpoint (config.py:165-166)."""
+        def plain(x):
+            return {k: plain(v) for k, v in x.items()} if isinstance(x, dict) else x
+        return {"run": plain(self.run_cfg), "model": plain(self.model_cfg), "datasets": plain(self.datasets_cfg)}
+
     def n_frames(self, split="train"):
         """Frames per clip the video processors of the (single) dataset sample (datasets.*.vis_processor.<split>.n_frms)."""
         for d in self.datasets_cfg.values():

@@ -234,3 +234,49 @@ def test_optimizer_groups_and_scheduler_from_recipe():
     assert all(abs(g["lr"] - 1.5e-4) < 1e-12 for g in opt.param_groups)
     with pytest.raises(KeyError):
         optim.build_lr_scheduler(opt, {"lr_sched": "nope", "max_epoch": 1, "min_lr": 0, "init_lr": 1})
+
+
+def test_checkpoint_wire_format_round_trip(tmp_path, tiny_sd):
+    """save -> resume in the runner's file format (lavis/runners/runner_base.py:572-644): only trainable tensors are
+    written, a second model resumes weights + optimizer state + epoch from the file, frozen towers stay untouched."""
+    from mr_blip_b200 import checkpoint, optim
+    from mr_blip_b200.blip2_mr import BLIP2_MR
+    from mr_blip_b200.config import Config
+    cfg = Config(os.path.join(ROOT, "mr_blip_b200", "configs", "projects", "mr_BLIP", "train", "qvh.yaml"))
+    m = BLIP2_MR(dims=TINY, state_dict=tiny_sd)
+    trainable = {n for n, p in m.named_parameters() if p.requires_grad}
+    g = torch.Generator().manual_seed(3)
+    with torch.no_grad():
+        for n, p in m.named_parameters():
+            if p.requires_grad:
+                p.add_(torch.randn(p.shape, generator=g) * 0.01)
+    opt = optim.build_optimizer(m, 3e-4, 0.05, fused=False)
+    for p in m.parameters():
+        if p.requires_grad:
+            p.grad = torch.full_like(p, 0.5)
+    opt.step()
+    path = checkpoint.save_checkpoint(m, opt, str(tmp_path), cur_epoch=3, config=cfg)
+    assert os.path.basename(path) == "checkpoint_3.pth"
+    assert os.path.basename(checkpoint.save_checkpoint(m, opt, str(tmp_path), 3, is_best=True)) == "checkpoint_best.pth"
+    obj = torch.load(path, map_location="cpu")
+    assert set(obj) == {"model", "optimizer", "config", "scaler", "epoch"} and obj["epoch"] == 3 and obj["scaler"] is None
+    # LoRA + t5_proj, plus the two tied aliases of the frozen T5 embedding: named_parameters() lists a tied tensor once
+    # (as shared.weight), so the reference's filter keeps encoder/decoder.embed_tokens.weight in the file as well
+    assert set(obj["model"]) == trainable | {T5_PREFIX + "encoder.embed_tokens.weight", T5_PREFIX + "decoder.embed_tokens.weight"}
+    assert obj["config"]["run"]["init_lr"] == 3e-4 and obj["config"]["model"]["arch"] == "blip2_mr"
+    assert os.path.getsize(path) < 0.5 * sum(v.numel() * v.element_size() for v in m.state_dict().values())
+    m2 = BLIP2_MR(dims=TINY, state_dict=tiny_sd)
+    opt2 = optim.build_optimizer(m2, 3e-4, 0.05, fused=False)
+    assert checkpoint.resume_checkpoint(m2, opt2, path) == 4
+    sd, sd2 = m.state_dict(), m2.state_dict()
+    assert all(torch.equal(sd[k], sd2[k]) for k in sd)
+    s1, s2 = opt.state_dict()["state"], opt2.state_dict()["state"]
+    assert s1.keys() == s2.keys() and all(torch.equal(s1[k]["exp_avg"], s2[k]["exp_avg"]) for k in s1)
+    msg = m2.load_checkpoint(path)                               # the model-side loader reads the same file
+    assert not msg.unexpected_keys
+    with pytest.raises(RuntimeError, match="invalid"):
+        checkpoint.resume_checkpoint(m2, opt2, str(tmp_path / "missing.pth"))
+    bad = {"model": {"not.a.key": torch.zeros(1)}, "optimizer": None, "epoch": 0}
+    torch.save(bad, str(tmp_path / "bad.pth"))
+    with pytest.raises(RuntimeError, match="unexpected"):
+        checkpoint.resume_checkpoint(m2, None, str(tmp_path / "bad.pth"))
