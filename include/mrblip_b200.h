@@ -29,6 +29,16 @@ int mrb_gemm(const void* A, long long lda, const void* B, long long ldb, int M, 
              const float* bias, int gelu, const float* resid, long long ldr, void* out, int out_dtype, long long ldc,
              int row_group, int force_bn, void* stream);
 
+/* mrb_gemm with a caller-owned fp32 workspace (16-byte aligned).  Problems with a single 128-row tile (decoder steps of
+ * generate / of the training decoder, modeling_t5.py:542-558 at M = B x L_dec) or with 32 output columns (LoRA
+ * down-projections) leave most SMs idle and are bound by what one SM can stream: they are split along K over up to
+ * max_splits (<= 8) CTAs per output tile, partials in ws[splits][M][N] summed in split order by a second launch that applies
+ * the epilogue.  Needs ws_bytes >= splits * M * N * 4; any other problem, or a workspace that is too small, runs exactly as
+ * mrb_gemm.  ws is busy until the call's work has finished on `stream` (one workspace per issuing stream). */
+int mrb_gemm_splitk(const void* A, long long lda, const void* B, long long ldb, int M, int N, int K, int dtype,
+                    const float* bias, int gelu, const float* resid, long long ldr, void* out, int out_dtype, long long ldc,
+                    int row_group, int force_bn, void* ws, long long ws_bytes, int max_splits, void* stream);
+
 /* softmax(scale * Q K^T + bias[h, j - i] + mask) V, scores never written to HBM; optional log-sum-exp for backward.
  * kv_div > 1: query batch b reads K/V/mask batch b / kv_div (beams sharing one encoder output).
  * Replaces eva_vit.py:128-145, Qformer.py:198-268, modeling_t5.py:561-610. */

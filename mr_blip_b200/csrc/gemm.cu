@@ -29,6 +29,10 @@ struct GemmParams {
   long long ldc;
   int epi_direct;       // 16-bit outputs: row-per-thread stores instead of the staged (coalesced) epilogue
   int row_group;        // G > 0: patch-embed row remap  out_row = (m/G)*(G+1)+1+m%G, resid_row = 1+m%G
+  // split-K instantiations only: tile index t = split * (m_tiles * n_tiles) + tile; split s contracts the K blocks
+  // [s * kb_per_split, min(k_blocks, (s + 1) * kb_per_split)) into fp32 partials at out + s * split_stride
+  int splits, kb_per_split;
+  long long split_stride;
 };
 
 constexpr int BM = 128;
@@ -54,7 +58,20 @@ __device__ __forceinline__ void tile_coords(int t, int m_tiles, int n_tiles, int
   tn = r / gm;
 }
 
-template <int BN, int STAGES>
+// Tile t of a split-K launch -> (output tile, split, K-block range); the identity for ordinary launches.
+template <bool SPLIT>
+__device__ __forceinline__ void split_coords(const GemmParams& p, int k_blocks, int t, int& tile, int& split, int& kb0, int& kb1) {
+  tile = t; split = 0; kb0 = 0; kb1 = k_blocks;
+  if (SPLIT) {
+    const int base = p.m_tiles * p.n_tiles;
+    split = t / base;
+    tile = t - split * base;
+    kb0 = split * p.kb_per_split;
+    kb1 = min(k_blocks, kb0 + p.kb_per_split);
+  }
+}
+
+template <int BN, int STAGES, bool SPLIT = false>
 __global__ void __launch_bounds__(320, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
   using S = GemmSmem<BN, STAGES>;
@@ -69,7 +86,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int num_tiles = p.m_tiles * p.n_tiles;
+  const int num_tiles = SPLIT ? p.m_tiles * p.n_tiles * p.splits : p.m_tiles * p.n_tiles;
   const int k_blocks = (p.K + BK - 1) / BK;
 
   if (warp == 0 && lane == 0) {
@@ -97,9 +114,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       int stage = 0;
       uint32_t phase = 0;
       for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-        int tm, tn;
-        tile_coords(t, p.m_tiles, p.n_tiles, tm, tn);
-        for (int kb = 0; kb < k_blocks; ++kb) {
+        int tm, tn, tile, split, kb0, kb1;
+        split_coords<SPLIT>(p, k_blocks, t, tile, split, kb0, kb1);
+        tile_coords(tile, p.m_tiles, p.n_tiles, tm, tn);
+        for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * S::STAGE_BYTES;
           mbar_expect_tx(&full_bar[stage], S::STAGE_BYTES);
@@ -121,7 +139,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       mbar_wait(&tmem_empty[as], aphase ^ 1);
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + as * BN;
-      for (int kb = 0; kb < k_blocks; ++kb) {
+      int tile, split, kb0, kb1;
+      split_coords<SPLIT>(p, k_blocks, t, tile, split, kb0, kb1);
+      for (int kb = kb0; kb < kb1; ++kb) {
         mbar_wait(&full_bar[stage], phase);
         tc_fence_after();
         if (lane == 0) {
@@ -130,10 +150,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k) {
             umma_f16(d_tmem, umma_desc_sw128(a_addr + k * 32), umma_desc_sw128(b_addr + k * 32), idesc,
-                     (kb > 0 || k > 0) ? 1u : 0u);
+                     (kb > kb0 || k > 0) ? 1u : 0u);
           }
           umma_commit(&empty_bar[stage]);                    // frees the smem slot when the MMAs retire
-          if (kb == k_blocks - 1) umma_commit(&tmem_full[as]);  // accumulator complete -> epilogue
+          if (kb == kb1 - 1) umma_commit(&tmem_full[as]);      // accumulator complete -> epilogue
         }
         __syncwarp();
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -152,8 +172,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     const bool direct16 = p.epi_direct && (p.out_dtype != MRB_DT_F32) && (p.resid == nullptr) && (p.row_group == 0);
     int it = 0;
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
-      int tm, tn;
-      tile_coords(t, p.m_tiles, p.n_tiles, tm, tn);
+      int tm, tn, tile, split, kb0, kb1;
+      split_coords<SPLIT>(p, k_blocks, t, tile, split, kb0, kb1);
+      tile_coords(tile, p.m_tiles, p.n_tiles, tm, tn);
+      void* const outp = SPLIT ? static_cast<void*>(static_cast<float*>(p.out) + split * p.split_stride) : p.out;
       const int as = it & 1;
       const uint32_t aphase = (it >> 1) & 1;
       const int m_base = tm * BM + quad * 32;
@@ -189,7 +211,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 #pragma unroll
               for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
             }
-            uint4* op = reinterpret_cast<uint4*>(static_cast<uint16_t*>(p.out) + static_cast<long long>(m) * p.ldc + n0);
+            uint4* op = reinterpret_cast<uint4*>(static_cast<uint16_t*>(outp) + static_cast<long long>(m) * p.ldc + n0);
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
               if (j * 8 < ncols) {
@@ -239,9 +261,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           if (m < p.M && col_ok) {
             const long long orow = p.row_group > 0 ? static_cast<long long>(m / p.row_group) * (p.row_group + 1) + 1 + (m % p.row_group) : m;
             if (p.out_dtype == MRB_DT_F32) {
-              *reinterpret_cast<float4*>(static_cast<float*>(p.out) + orow * p.ldc + col) = x;
+              *reinterpret_cast<float4*>(static_cast<float*>(outp) + orow * p.ldc + col) = x;
             } else {
-              *reinterpret_cast<uint2*>(static_cast<uint16_t*>(p.out) + orow * p.ldc + col) =
+              *reinterpret_cast<uint2*>(static_cast<uint16_t*>(outp) + orow * p.ldc + col) =
                   make_uint2(pack2(x.x, x.y, p.out_dtype), pack2(x.z, x.w, p.out_dtype));
             }
           }
@@ -295,21 +317,85 @@ static int make_tmap(CUtensorMap* map, const void* base, int dtype, long long ro
 
 static int g_num_sms = 0;
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, bool SPLIT = false>
 static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, GemmParams& p, cudaStream_t stream) {
   using S = GemmSmem<BN, STAGES>;
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tcgen05_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL);
+    cudaError_t e = cudaFuncSetAttribute(gemm_tcgen05_kernel<BN, STAGES, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL);
     if (e != cudaSuccess) return mrb_set_error(e);
     configured = true;
   }
   p.n_tiles = (p.N + BN - 1) / BN;
-  const int tiles = p.m_tiles * p.n_tiles;
+  const int tiles = p.m_tiles * p.n_tiles * (SPLIT ? p.splits : 1);
   const int grid = tiles < g_num_sms ? tiles : g_num_sms;
-  gemm_tcgen05_kernel<BN, STAGES><<<grid, 320, S::TOTAL, stream>>>(tmA, tmB, p);
+  gemm_tcgen05_kernel<BN, STAGES, SPLIT><<<grid, 320, S::TOTAL, stream>>>(tmA, tmB, p);
   MRB_CHECK_LAUNCH();
   return MRB_OK;
+}
+
+// ---------------------------------------------------------------- split-K: second pass
+// out = epilogue( sum_s ws[s] ): the partial tiles are summed in split order (deterministic) and the caller's epilogue --
+// bias, exact GELU, fp32 residual, output type -- is applied once, in the order of the fused epilogue above.
+__global__ void __launch_bounds__(256)
+splitk_reduce_kernel(const float* __restrict__ ws, int splits, long long split_stride, int M, int N, const float* __restrict__ bias,
+                     int gelu, const float* resid, long long ldr, void* out, int out_dtype, long long ldc) {
+  const int n4 = N >> 2;
+  const long long total = static_cast<long long>(M) * n4;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int m = static_cast<int>(i / n4);
+    const int col = static_cast<int>(i - static_cast<long long>(m) * n4) * 4;
+    const float* src = ws + static_cast<long long>(m) * N + col;
+    float4 x = *reinterpret_cast<const float4*>(src);
+    for (int sp = 1; sp < splits; ++sp) {
+      const float4 y = *reinterpret_cast<const float4*>(src + sp * split_stride);
+      x.x += y.x; x.y += y.y; x.z += y.z; x.w += y.w;
+    }
+    if (bias) {
+      const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + col));
+      x.x += b4.x; x.y += b4.y; x.z += b4.z; x.w += b4.w;
+    }
+    if (gelu) { x.x = gelu_erf(x.x); x.y = gelu_erf(x.y); x.z = gelu_erf(x.z); x.w = gelu_erf(x.w); }
+    if (resid) {
+      const float4 r4 = *reinterpret_cast<const float4*>(resid + m * ldr + col);
+      x.x += r4.x; x.y += r4.y; x.z += r4.z; x.w += r4.w;
+    }
+    if (out_dtype == MRB_DT_F32) {
+      *reinterpret_cast<float4*>(static_cast<float*>(out) + m * ldc + col) = x;
+    } else {
+      *reinterpret_cast<uint2*>(static_cast<uint16_t*>(out) + m * ldc + col) =
+          make_uint2(pack2(x.x, x.y, out_dtype), pack2(x.z, x.w, out_dtype));
+    }
+  }
+}
+
+// Split-K plan.  Launches with few output tiles are bound by what ONE SM can pull through its TMA / L2 port, not by HBM or
+// the tensor pipe: measured time ~ 2.1 ns x (K blocks per CTA) x (128 + BN) rows per stage over every tile width
+// (profiles/gemm_small_m_r01b.log).  So: pick (BN, splits) that minimises  waves x ceil(k_blocks / splits) x (128 + BN)
+// with tiles x splits CTAs, charging a split launch the fixed cost of its reduce pass.
+struct SplitPlan { int bn, splits, kb_per; };
+
+static SplitPlan plan_split(int M, int N, int K, int sms, int force_bn, int max_splits) {
+  const int k_blocks = (K + BK - 1) / BK;
+  const int m_tiles = (M + BM - 1) / BM;
+  const int cand[4] = {32, 64, 128, 256};
+  SplitPlan best = {0, 1, k_blocks};
+  long long best_cost = -1;
+  for (int i = 0; i < 4; ++i) {
+    const int bn = cand[i];
+    if (force_bn ? bn != force_bn : ((bn == 32) != (N <= 32))) continue;   // 32-wide tiles only for the 32-column problems
+    const long long tiles = static_cast<long long>(m_tiles) * ((N + bn - 1) / bn);
+    for (int sp = 1; sp <= max_splits; ++sp) {
+      const int kb_per = (k_blocks + sp - 1) / sp;
+      if (sp > 1 && (kb_per < 4 || tiles * sp > sms)) break;
+      if ((k_blocks + kb_per - 1) / kb_per != sp) continue;                // this count leaves a split empty
+      const long long waves = (tiles * sp + sms - 1) / sms;
+      const long long cost = waves * kb_per * (128 + bn) + (sp > 1 ? 1500 : 0);
+      if (best_cost < 0 || cost < best_cost) { best_cost = cost; best = {bn, sp, kb_per}; }
+    }
+  }
+  return best;
 }
 
 }  // namespace mrb
@@ -343,9 +429,9 @@ extern "C" int mrb_gemm2_launch(const CUtensorMap* tmA, const CUtensorMap* tmB, 
                                 const float* bias, int gelu, const float* resid, long long ldr, void* out, int out_dtype,
                                 long long ldc, int row_group, int num_sms, void* stream);
 
-extern "C" int mrb_gemm(const void* A, long long lda, const void* B, long long ldb, int M, int N, int K, int dtype,
-                        const float* bias, int gelu, const float* resid, long long ldr, void* out, int out_dtype,
-                        long long ldc, int row_group, int force_bn, void* stream) {
+static int gemm_impl(const void* A, long long lda, const void* B, long long ldb, int M, int N, int K, int dtype,
+                     const float* bias, int gelu, const float* resid, long long ldr, void* out, int out_dtype,
+                     long long ldc, int row_group, int force_bn, void* ws, long long ws_bytes, int max_splits, void* stream) {
   if (M <= 0 || N <= 0 || K <= 0) return MRB_OK;
   if ((dtype != MRB_DT_F16 && dtype != MRB_DT_BF16) || (N & 7) || (lda & 7) || (ldb & 7) || (K & 7)) return MRB_ERR_ARG;
   if ((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(B) | reinterpret_cast<uintptr_t>(out)) & 15) return MRB_ERR_ARG;
@@ -368,7 +454,14 @@ extern "C" int mrb_gemm(const void* A, long long lda, const void* B, long long l
     return mrb_gemm2_launch(&tmA2, &tmB2, M, N, K, dtype, bias, gelu, resid, ldr, out, out_dtype, ldc, row_group,
                             g_num_sms, stream);
   }
-  const int bn = force_bn ? force_bn : pick_bn(M, N, g_num_sms);
+  int bn = force_bn ? force_bn : pick_bn(M, N, g_num_sms);
+  SplitPlan plan = {bn, 1, 0};
+  if (ws && max_splits > 1 && row_group == 0 && (M <= BM || N <= 32)) {
+    if (reinterpret_cast<uintptr_t>(ws) & 15) return MRB_ERR_ARG;
+    max_splits = max_splits < 8 ? max_splits : 8;
+    const SplitPlan sp = plan_split(M, N, K, g_num_sms, force_bn, max_splits);
+    if (sp.splits > 1 && static_cast<long long>(sp.splits) * M * N * 4 <= ws_bytes) { plan = sp; bn = sp.bn; }
+  }
   CUtensorMap tmA, tmB;
   int rc = make_tmap(&tmA, A, dtype, M, K, lda, BM);
   if (rc) return rc;
@@ -381,12 +474,34 @@ extern "C" int mrb_gemm(const void* A, long long lda, const void* B, long long l
   p.dtype = dtype;
   p.bias = bias; p.gelu = gelu; p.resid = resid; p.ldr = ldr;
   p.out = out; p.out_dtype = out_dtype; p.ldc = ldc; p.row_group = row_group;
+  p.splits = 1; p.kb_per_split = 0; p.split_stride = 0;
   {
     static int mode = -1;                 // MRB_GEMM_EPI=direct selects the row-per-thread 16-bit epilogue (A/B measurements)
     if (mode < 0) { const char* e = getenv("MRB_GEMM_EPI"); mode = e ? (e[0] == 'd' ? 1 : 2) : 0; }
     p.epi_direct = mode == 1 ? 1 : 0;
   }
   cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (plan.splits > 1) {
+    // partial sums: fp32 [splits][M][N] in the caller's workspace, no epilogue; the reduce pass applies it
+    p.bias = nullptr; p.gelu = 0; p.resid = nullptr; p.ldr = 0; p.epi_direct = 0;
+    p.out = ws; p.out_dtype = MRB_DT_F32; p.ldc = N;
+    p.splits = plan.splits; p.kb_per_split = plan.kb_per; p.split_stride = static_cast<long long>(M) * N;
+    switch (bn) {
+      case 256: rc = launch_gemm<256, 4, true>(tmA, tmB, p, s); break;
+      case 128: rc = launch_gemm<128, 6, true>(tmA, tmB, p, s); break;
+      case 64: rc = launch_gemm<64, 8, true>(tmA, tmB, p, s); break;
+      case 32: rc = launch_gemm<32, 8, true>(tmA, tmB, p, s); break;
+      default: return MRB_ERR_ARG;
+    }
+    if (rc) return rc;
+    const long long quads = static_cast<long long>(M) * (N >> 2);
+    long long blocks = (quads + 255) / 256;
+    if (blocks > 4LL * g_num_sms) blocks = 4LL * g_num_sms;
+    splitk_reduce_kernel<<<static_cast<int>(blocks), 256, 0, s>>>(static_cast<const float*>(ws), plan.splits, p.split_stride, M, N,
+                                                                  bias, gelu, resid, ldr, out, out_dtype, ldc);
+    MRB_CHECK_LAUNCH();
+    return MRB_OK;
+  }
   switch (bn) {
     case 256: return launch_gemm<256, 4>(tmA, tmB, p, s);
     case 192: return launch_gemm<192, 4>(tmA, tmB, p, s);
@@ -395,4 +510,24 @@ extern "C" int mrb_gemm(const void* A, long long lda, const void* B, long long l
     case 32: return launch_gemm<32, 8>(tmA, tmB, p, s);
     default: return MRB_ERR_ARG;
   }
+}
+
+extern "C" int mrb_gemm(const void* A, long long lda, const void* B, long long ldb, int M, int N, int K, int dtype,
+                        const float* bias, int gelu, const float* resid, long long ldr, void* out, int out_dtype,
+                        long long ldc, int row_group, int force_bn, void* stream) {
+  return gemm_impl(A, lda, B, ldb, M, N, K, dtype, bias, gelu, resid, ldr, out, out_dtype, ldc, row_group, force_bn, nullptr, 0, 1,
+                   stream);
+}
+
+// mrb_gemm with a caller-owned fp32 workspace: problems with one row tile (decoder steps, M <= 128) or 32 columns (LoRA
+// down-projections) whose grid would leave most SMs idle are split along K over up to max_splits CTAs per output tile
+// (partials in `ws`, >= splits * M * N * 4 bytes, 16-byte aligned; summed in split order by a second launch that applies the
+// epilogue).  Everything else, and any problem the workspace is too small for, runs exactly as mrb_gemm.  The workspace is in
+// use until the call's work has finished on `stream`: one workspace per stream that issues such calls.
+extern "C" int mrb_gemm_splitk(const void* A, long long lda, const void* B, long long ldb, int M, int N, int K, int dtype,
+                               const float* bias, int gelu, const float* resid, long long ldr, void* out, int out_dtype,
+                               long long ldc, int row_group, int force_bn, void* ws, long long ws_bytes, int max_splits,
+                               void* stream) {
+  return gemm_impl(A, lda, B, ldb, M, N, K, dtype, bias, gelu, resid, ldr, out, out_dtype, ldc, row_group, force_bn, ws, ws_bytes,
+                   max_splits, stream);
 }

@@ -14,6 +14,28 @@ USE_TC_ATTENTION = True
 GEMM_PROFILE = None      # set to a list to record (M, N, K, cuda start event, cuda end event) per GEMM launch
 
 
+# Split-K for the decoder-sized (M <= 128) and 32-column GEMMs (csrc/gemm.cu mrb_gemm_splitk).  Written after this round's
+# GPU budget was spent: compiled and reviewed but NOT yet run on hardware, hence off unless MRB_GEMM_SPLITK=1.
+SPLITK = os.environ.get("MRB_GEMM_SPLITK", "0") == "1"
+SPLITK_MAX = int(os.environ.get("MRB_GEMM_SPLITK_MAX", "8"))
+SPLITK_WS_BYTES = 48 << 20          # 8 splits x 128 rows x 10240 columns of fp32, rounded up
+_SPLITK_MAIN = None
+_SPLITK_SIDE = {}                   # cuda stream handle -> workspace of that side stream
+
+
+def splitk_register(side_stream=None):
+    """Allocate the split-K workspaces OUTSIDE any graph capture: one for the main chain (whatever stream it runs on; a
+    process issues it from one stream at a time) and one per registered side stream, since a workspace is busy until the
+    GEMM that uses it has finished on its stream."""
+    global _SPLITK_MAIN
+    if not SPLITK:
+        return
+    if _SPLITK_MAIN is None:
+        _SPLITK_MAIN = torch.empty(SPLITK_WS_BYTES // 4, dtype=torch.float32, device="cuda")
+    if side_stream is not None and side_stream.cuda_stream not in _SPLITK_SIDE:
+        _SPLITK_SIDE[side_stream.cuda_stream] = torch.empty(SPLITK_WS_BYTES // 4, dtype=torch.float32, device="cuda")
+
+
 NVTX = os.environ.get("MRB_NVTX", "0") == "1"     # MRB_NVTX=1: NVTX ranges around the phases of a step (nsys / ncu --nvtx)
 
 
@@ -71,9 +93,18 @@ def gemm(a, b, out=None, bias=None, gelu=False, resid=None, out_dtype=None, row_
     if GEMM_PROFILE is not None:
         ev0 = torch.cuda.Event(enable_timing=True)
         ev0.record()
-    _lib.call("mrb_gemm", a.data_ptr(), a.stride(0), b.data_ptr(), b.stride(0), M, N, K, _DT[a.dtype], _ptr(bias),
-              int(gelu), _ptr(resid), resid.stride(0) if resid is not None else 0, out.data_ptr(), _DT[out.dtype],
-              out.stride(0), row_group, force_bn, _stream())
+    if SPLITK and row_group == 0 and (M <= 128 or N <= 32):
+        h = _stream()
+        if _SPLITK_MAIN is None:
+            splitk_register()
+        ws = _SPLITK_SIDE.get(h, _SPLITK_MAIN)
+        _lib.call("mrb_gemm_splitk", a.data_ptr(), a.stride(0), b.data_ptr(), b.stride(0), M, N, K, _DT[a.dtype], _ptr(bias),
+                  int(gelu), _ptr(resid), resid.stride(0) if resid is not None else 0, out.data_ptr(), _DT[out.dtype],
+                  out.stride(0), row_group, force_bn, ws.data_ptr(), ws.numel() * 4, SPLITK_MAX, h)
+    else:
+        _lib.call("mrb_gemm", a.data_ptr(), a.stride(0), b.data_ptr(), b.stride(0), M, N, K, _DT[a.dtype], _ptr(bias),
+                  int(gelu), _ptr(resid), resid.stride(0) if resid is not None else 0, out.data_ptr(), _DT[out.dtype],
+                  out.stride(0), row_group, force_bn, _stream())
     if GEMM_PROFILE is not None:
         ev1 = torch.cuda.Event(enable_timing=True)
         ev1.record()

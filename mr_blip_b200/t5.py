@@ -201,6 +201,7 @@ class T5Engine:
         import os
         self.overlap = os.environ.get("MRB_OVERLAP", "1") != "0"
         self.side = torch.cuda.Stream()
+        ops.splitk_register(self.side)
         self._hold = []
         self._side_open = False
 

@@ -39,6 +39,7 @@ class VitEngine:
         import os
         self.overlap = os.environ.get("MRB_OVERLAP", "1") != "0"
         self.side = torch.cuda.Stream()
+        ops.splitk_register(self.side)
         self.blocks = []
         for i in range(d.vit_depth):
             b = f"{prefix}blocks.{i}."

@@ -72,7 +72,7 @@ def time_graphed(fn, calls=40, reps=5):
 def main():
     tag = sys.argv[1] if len(sys.argv) > 1 else "default"
     res = {"tag": tag, "env": {k: v for k, v in os.environ.items() if k.startswith("MRB_")}, "big": [], "small": []}
-    for name, M, N, K, dt, epi in BIG:
+    for name, M, N, K, dt, epi in (BIG if tag != "splitk" else []):
         a = (torch.randn(M, K, device="cuda") * 0.5).to(dt)
         b = (torch.randn(N, K, device="cuda") * 0.05).to(dt)
         bias = torch.randn(N, device="cuda") if "bias" in epi else None
@@ -83,7 +83,7 @@ def main():
         print(tag, row, flush=True)
         res["big"].append(row)
         del a, b, out, resid
-    if tag == "default":
+    if tag in ("default", "splitk"):            # MRB_GEMM_SPLITK=1 python tools/gemm_sweep.py splitk: the small shapes again, split along K
         for name, M, N, K, dt, bns in SMALL:
             a = (torch.randn(M, K, device="cuda") * 0.5).to(dt)
             # several weight copies so that successive calls do not find their weights in L2 (as in the real step)
