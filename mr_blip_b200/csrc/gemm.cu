@@ -402,10 +402,12 @@ static SplitPlan plan_split(int M, int N, int K, int sms, int force_bn, int max_
 
 using namespace mrb;
 
-// Small-M note (decoder steps, M = 56): these launches take ~15 us for K = 2080 and ~55 us for K = 10272 whatever the tile
-// width (32 / 64 / 128) and whatever the ring depth -- a variant with 64-row A stages and an 11-14 stage ring measured
-// 21 us (profiles/gemm_small_m_r01b.log).  The time is 130 (K / 16) serially issued tcgen05.mma per CTA at ~75 ns each, i.e.
-// the single issuing thread, not TMA latency or HBM (floor 1.4 us); only split-K would shorten it (next round).
+// Small-M note (decoder steps, M = 56): these launches take ~15 us for K = 2080 and ~55 us for K = 10272
+// (profiles/gemm_small_m_r01b.log).  Over every tile width measured the time fits  2.1 ns x K blocks x (128 + BN) rows per
+// stage: 26.4 / 17.7 us for N = 10240 at BN 64 (two waves) / 128, 13-15 us for N = 2048, 55 us for K = 10272 -- i.e. the
+// bytes ONE SM pulls through its TMA / L2 port (~45 B/clk, the same per-SM feed rate that bounds the large GEMMs), with the
+// zero-filled rows of the 128-row A box counted, not HBM (floor 1.4 us) and not the tensor pipe.  With 32-96 CTAs most SMs
+// idle; mrb_gemm_splitk below spreads the K blocks of such problems over the idle SMs.
 // Pick the N tile: minimise (waves over the SMs) x (tile width) x (relative MMA inefficiency of narrow tiles).
 // Narrow tiles win only when the grid would otherwise leave most SMs idle (decoder steps, M <= 128).
 static int pick_bn(int M, int N, int sms) {
