@@ -48,6 +48,16 @@ def _wrap(x):
     return x
 
 
+def _deep_update(dst, src):
+    """Nested merge: --options datasets.qvh.build_info.videos.storage=... must not drop the section's other keys."""
+    for k, v in src.items():
+        if isinstance(v, dict) and isinstance(dst.get(k), dict):
+            _deep_update(dst[k], v)
+        else:
+            dst[k] = v
+    return dst
+
+
 def _parse_value(s):
     return _load_yaml(s)
 
@@ -56,6 +66,7 @@ class Config:
     def __init__(self, cfg_path, options=None):
         with open(cfg_path) as f:
             user = _load_yaml(f.read()) or {}
+        from . import blip2_mr, blip2_t5  # noqa: F401  (register the model classes)
         opts = self._options(options)
         user_model = dict(user.get("model", {}))
         user_model.update(opts.get("model", {}))
@@ -64,7 +75,6 @@ class Config:
         assert model_cls is not None, "Model '%s' has not been registered." % user_model["arch"]
         model_type = user_model.get("model_type", None)
         assert model_type is not None, "Missing model_type."                               # config.py:68
-        import mr_blip_b200.blip2_mr  # noqa: F401  (registers blip2_mr)
         with open(model_cls.default_config_path(model_type)) as f:
             defaults = (_load_yaml(f.read()) or {}).get("model", {})
         merged = dict(defaults)
@@ -74,8 +84,7 @@ class Config:
         run.update(opts.get("run", {}))
         self.run_cfg = _wrap(run)
         ds = {k: dict(v or {}) for k, v in (user.get("datasets", {}) or {}).items()}
-        for k, v in opts.get("datasets", {}).items():
-            ds.setdefault(k, {}).update(v)
+        _deep_update(ds, opts.get("datasets", {}))
         self.datasets_cfg = _wrap(ds)
 
     @staticmethod

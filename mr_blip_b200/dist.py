@@ -33,6 +33,16 @@ def is_dist():
     return dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
 
 
+def barrier():
+    if is_dist():
+        dist.barrier()
+
+
+def cleanup():
+    if dist.is_available() and dist.is_initialized():
+        dist.destroy_process_group()
+
+
 class GradAllReducer:
     """Gradient averaging over the trainable parameters with ONE all-reduce.  When the model keeps its gradients in one
     flat buffer (BLIP2_MR.flat_grads(): every .grad is a view of it) that buffer is reduced in place; otherwise the

@@ -1,6 +1,8 @@
 """CPU-only checks of the host side: C-ABI exports, registry / model surface, prompt table, tokenizer,
 state-dict key names.  No compute call is made (no GPU here)."""
 import ctypes
+import json
+import math
 import os
 import re
 
@@ -280,3 +282,121 @@ def test_checkpoint_wire_format_round_trip(tmp_path, tiny_sd):
     torch.save(bad, str(tmp_path / "bad.pth"))
     with pytest.raises(RuntimeError, match="unexpected"):
         checkpoint.resume_checkpoint(m2, None, str(tmp_path / "bad.pth"))
+
+
+def test_video_processor_decodes_with_opencv(tmp_path):
+    """VideoProcessor + Cv2VideoReader on a synthetic mp4: frame-exact sequential decode at the sampled indices, reference
+    layout (float32 [3,T,H,W], CLIP-normalised) and the uint8 variant the fused device normalisation consumes."""
+    cv2 = pytest.importorskip("cv2")
+    from mr_blip_b200 import data
+    from mr_blip_b200.vision import VitEngine
+    assert data.PIXEL_MEAN == VitEngine.PIXEL_MEAN and data.PIXEL_STD == VitEngine.PIXEL_STD
+    path = str(tmp_path / "clip.mp4")
+    w = cv2.VideoWriter(path, cv2.VideoWriter_fourcc(*"mp4v"), 25.0, (64, 48))
+    if not w.isOpened():
+        pytest.skip("no mp4 encoder in this OpenCV build")
+    n = 90
+    for i in range(n):
+        w.write(np.full((48, 64, 3), 10 + 8 * (i % 30), np.uint8))           # flat grey frame encodes its index mod 30, 8 levels apart
+    w.release()
+    vr = data.Cv2VideoReader(path, height=32, width=32)
+    assert len(vr) == n and abs(vr.get_avg_fps() - 25.0) < 1e-6
+    proc8 = data.VideoProcessor(image_size=32, n_frms=6, sampling="uniform", uint8=True)
+    frames, idx, fps = proc8(path)
+    assert idx == data.sample_frame_indices(n, 25.0, 6) and fps == vr.get_avg_fps()
+    assert frames.dtype == torch.uint8 and tuple(frames.shape) == (3, 6, 32, 32)
+    level = frames.float().mean(dim=(0, 2, 3))
+    assert ((level - torch.tensor([10.0 + 8 * (i % 30) for i in idx])).abs() < 4).all(), (level, idx)    # lossy codec: a few grey levels
+    procf = data.VideoProcessor(image_size=32, n_frms=6, sampling="uniform")
+    ff, idx2, _ = procf(path, clip_proposal=[1.0, 3.0])
+    assert idx2 == data.sample_frame_indices(n, 25.0, 6, "uniform", [1.0, 3.0]) and min(idx2) >= 25 and max(idx2) < 75
+    assert ff.dtype == torch.float32 and tuple(ff.shape) == (3, 6, 32, 32)
+    f8, _, _ = data.VideoProcessor(image_size=32, n_frms=6, uint8=True)(path, clip_proposal=[1.0, 3.0])
+    want = (f8.float() / 255.0 - torch.tensor(data.PIXEL_MEAN).view(3, 1, 1, 1)) / torch.tensor(data.PIXEL_STD).view(3, 1, 1, 1)
+    assert torch.equal(ff, want)
+    # out-of-order and repeated indices come back in request order
+    got = vr.get_batch([40, 3, 40])
+    assert tuple(got.shape) == (3, 32, 32, 3) and torch.equal(got[0], got[2]) and abs(float(got[1].float().mean()) - 34) < 4
+    with pytest.raises(RuntimeError, match="cannot open"):
+        data.Cv2VideoReader(str(tmp_path / "missing.mp4"))
+
+
+def test_standalone_training_loop_mechanics(tmp_path):
+    """mr_blip_b200.train on CPU with a stand-in model: datasets built from a recipe + --options over a synthetic mp4 (OpenCV
+    decode, uint8 frames), the per-iteration lr schedule, gradient accumulation, evaluation -> per-rank result file -> merged
+    metrics, and the checkpoint files.  (The real model's step is covered by the GPU tests.)"""
+    cv2 = pytest.importorskip("cv2")
+    from mr_blip_b200 import train, optim, checkpoint
+    from mr_blip_b200.config import Config
+    vid_dir = tmp_path / "videos"
+    vid_dir.mkdir()
+    for name in ("a", "b", "c"):
+        w = cv2.VideoWriter(str(vid_dir / (name + ".mp4")), cv2.VideoWriter_fourcc(*"mp4v"), 10.0, (32, 32))
+        if not w.isOpened():
+            pytest.skip("no mp4 encoder in this OpenCV build")
+        for i in range(40):
+            w.write(np.full((32, 32, 3), 5 * i, np.uint8))
+        w.release()
+    anns = [{"qid": i, "video": v, "query": "query %d" % i, "duration": 4.0, "relevant_windows": [[1, 3]]}
+            for i, v in enumerate(["a", "b", "c", "a", "b", "c"])]
+    for split in ("train", "val"):
+        (tmp_path / (split + ".json")).write_text(json.dumps(anns))
+    recipe = os.path.join(ROOT, "mr_blip_b200", "configs", "projects", "mr_BLIP", "train", "qvh.yaml")
+    cfg = Config(recipe, ["datasets.qvh.build_info.annotations.train.storage=%s" % (tmp_path / "train.json"),
+                          "datasets.qvh.build_info.annotations.val.storage=%s" % (tmp_path / "val.json"),
+                          "datasets.qvh.build_info.videos.storage=%s" % vid_dir,
+                          "datasets.qvh.vis_processor.train.n_frms=4", "datasets.qvh.vis_processor.eval.n_frms=4",
+                          "datasets.qvh.vis_processor.train.image_size=16", "datasets.qvh.vis_processor.eval.image_size=16",
+                          "run.max_epoch=2", "run.warmup_steps=4", "run.accum_grad_iters=2"])
+    assert cfg.datasets_cfg.qvh.vis_processor.train.name == "blip2_video_train"          # nested override kept the siblings
+    ds = train.build_datasets(cfg, ["train", "val"])
+    assert len(ds["train"]) == 6 and ds["train"].vis_processor.sampling == "random" and ds["val"].vis_processor.sampling == "uniform"
+    s0 = ds["val"][0]
+    assert s0["video"].dtype == torch.uint8 and tuple(s0["video"].shape) == (4, 3, 16, 16) and s0["timestamps"].tolist() == pytest.approx([0.5, 1.5, 2.5, 3.5])
+    loaders = {k: train.build_loader(v, 2, 0, k == "train", 0, 1) for k, v in ds.items()}
+    assert len(loaders["train"]) == 3
+
+    class Standin(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.w = torch.nn.Parameter(torch.zeros(3))
+            self.frozen = torch.nn.Parameter(torch.ones(2), requires_grad=False)
+            self.seen = []
+
+        def forward(self, samples):
+            assert samples["video"].dtype == torch.uint8 and samples["video"].shape[1:] == (4, 3, 16, 16)
+            self.seen.append((samples["epoch"], samples["iters"], samples["num_iters_per_epoch"]))
+            return {"loss": ((self.w - 1.0) ** 2).sum() + samples["video"].float().mean() * 0}
+
+        def generate(self, samples, num_beams=5, max_length=50, min_length=1):
+            assert (num_beams, max_length, min_length) == (5, 200, 8)
+            n = len(samples["query_prompt"])
+            preds = ["[[1, 3]]" if int(q) % 2 == 0 else "no idea" for q in samples["query_id"]]
+            return {"prediction": preds, "raw_prediction": preds, "answer": list(samples["relevant_windows"]),
+                    "qid": samples["query_id"].tolist(), "duration": samples["duration"].tolist()}
+
+    model = Standin()
+    opt = optim.build_optimizer(model, cfg.run_cfg.init_lr, cfg.run_cfg.weight_decay, fused=False)
+    sched = optim.build_lr_scheduler(opt, cfg.run_cfg)
+    steps, lrs = [], []
+    real_step = opt.step
+    opt.step = lambda *a, **k: (steps.append(len(model.seen)), lrs.append(opt.param_groups[0]["lr"]), real_step(*a, **k))[-1]
+    task = train.MomentRetrievalTask()
+    st0 = train.train_epoch(task, model, loaders["train"], opt, sched, 0, "cpu", accum_grad_iters=2)
+    st1 = train.train_epoch(task, model, loaders["train"], opt, sched, 1, "cpu", accum_grad_iters=2)
+    assert model.seen == [(0, 0, 3), (0, 1, 3), (0, 2, 3), (1, 0, 3), (1, 1, 3), (1, 2, 3)]
+    assert steps == [2, 5]                                   # an optimiser step every second micro-step; the odd one is dropped at the epoch end
+    warm = lambda k: 1e-8 + (3e-4 - 1e-8) * k / 4            # noqa: E731  (global step k of a 4-step warm-up)
+    # epoch 1, step 1 counts as global step 1 * 2 + 1 = 3 (the scheduler multiplies by the largest step INDEX seen, optims.py:80-84)
+    assert lrs[0] == pytest.approx(warm(1)) and lrs[1] == pytest.approx(warm(3))
+    sched.step(cur_epoch=1, cur_step=2)
+    assert opt.param_groups[0]["lr"] == pytest.approx(3e-4 * 0.5 * (1 + math.cos(math.pi * 1 / 2)))     # 1*2+2 = 4: cosine of epoch 1 of 2
+    assert st1["loss"] < st0["loss"] and float(model.w.detach().min()) > 0
+    gen = dict(num_beams=int(cfg.run_cfg.num_beams), max_length=int(cfg.run_cfg.max_len), min_length=int(cfg.run_cfg.min_len))
+    results = task.evaluation(model.eval(), loaders["val"], "cpu", **gen)
+    assert len(results) == 6 and results[0]["qid"] == "0_0" and results[1]["qid"] == "1_1" and results[2]["qid"] == "2_0"
+    metrics = task.after_evaluation(results, "val", 1, str(tmp_path / "result"))
+    assert metrics["total"] == 6 and metrics["invalid_predictions"] == pytest.approx(0.5) and metrics["agg_metrics"] == pytest.approx(50.0)
+    assert json.load(open(tmp_path / "result" / "val_epoch1.json"))[0]["target"] == "[[1, 3]]"
+    path = checkpoint.save_checkpoint(model, opt, str(tmp_path / "out"), 1, config=cfg)
+    assert set(torch.load(path)["model"]) == {"w"}

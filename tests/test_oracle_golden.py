@@ -184,3 +184,58 @@ def test_lr_schedules_match_reference(golden_dir):
                 got.append(opt.param_groups[0]["lr"])
         assert got == c["lr"], c["sched"]
     assert optim.LinearWarmupCosineLRScheduler is registry.get_lr_scheduler_class("linear_warmup_cosine_lr")
+
+
+def test_frame_sampling_and_sample_dict_match_reference(golden_dir, tmp_path):
+    """mr_blip_b200.data against the reference's load_video index logic (all three sampling modes, clip proposals, short
+    videos; same `random` seed -> same draws) and MomentRetrievalDataset.__getitem__ / collater output."""
+    import random
+    from mr_blip_b200 import data
+    gold = json.load(open(os.path.join(golden_dir, "data_golden.json")))
+    assert len(gold["indices"]) >= 10
+    for c in gold["indices"]:
+        random.seed(c["seed"])
+        got = data.sample_frame_indices(c["vlen"], c["fps"], c["n_frms"], c["sampling"], c["clip"])
+        assert [int(i) for i in got] == c["indices"], c
+        rng = random.Random(c["seed"])                                       # an explicit generator draws the same stream
+        assert [int(i) for i in data.sample_frame_indices(c["vlen"], c["fps"], c["n_frms"], c["sampling"], c["clip"], rng)] == c["indices"]
+
+    class Reader:                                                            # the stub the golden generator decoded with
+        def __init__(self, uri, height=-1, width=-1):
+            self.h, self.w = height, width
+
+        def __len__(self):
+            return 4500
+
+        def get_avg_fps(self):
+            return 29.97
+
+        def get_batch(self, idx):
+            t = torch.tensor(idx, dtype=torch.float32).remainder(256).view(-1, 1, 1, 1)
+            return t.expand(len(idx), self.h, self.w, 3).to(torch.uint8)
+
+    path = tmp_path / "train.json"
+    path.write_text(json.dumps(gold["annotations"]))
+
+    def vis(video_path, clip_proposal=None):                                 # un-normalised float frames, as the generator's processor
+        vr = Reader(video_path, 4, 4)
+        idx = data.sample_frame_indices(len(vr), vr.get_avg_fps(), 6, "uniform", clip_proposal)
+        return vr.get_batch(idx).permute(3, 0, 1, 2).float(), idx, vr.get_avg_fps()
+
+    ds = data.MomentRetrievalDataset(vis, None, "/data/videos", [str(path)])
+    assert len(ds) == len(gold["samples"])
+    for i, want in enumerate(gold["samples"]):
+        s = ds[i]
+        assert set(s) == {"video", "duration", "query_id", "timestamps", "video_prompt_end", "query_prompt", "task_prompt", "relevant_windows"}
+        for k in ("query_id", "video_prompt_end", "query_prompt", "task_prompt", "relevant_windows"):
+            assert s[k] == want[k], k
+        assert s["timestamps"].tolist() == want["timestamps"] and str(s["timestamps"].dtype) == want["timestamps_dtype"]
+        assert float(s["duration"]) == want["duration"] and str(s["duration"].dtype) == want["duration_dtype"]
+        assert list(s["video"].shape) == want["video_shape"] and str(s["video"].dtype) == want["video_dtype"]
+        assert s["video"][:, 0, 0, 0].tolist() == want["video_frame_values"]
+    b = ds.collater([ds[0], ds[1]])
+    c = gold["collated"]
+    assert list(b["video"].shape) == c["video_shape"] and list(b["timestamps"].shape) == c["timestamps_shape"]
+    assert b["duration"].tolist() == c["duration"] and str(b["duration"].dtype) == c["duration_dtype"]
+    assert b["query_id"].tolist() == c["query_id"] and list(b["relevant_windows"]) == c["relevant_windows"]
+    assert ds.annotation[2]["instance_id"] == "2"
