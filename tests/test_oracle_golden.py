@@ -239,3 +239,58 @@ def test_frame_sampling_and_sample_dict_match_reference(golden_dir, tmp_path):
     assert b["duration"].tolist() == c["duration"] and str(b["duration"].dtype) == c["duration_dtype"]
     assert b["query_id"].tolist() == c["query_id"] and list(b["relevant_windows"]) == c["relevant_windows"]
     assert ds.annotation[2]["instance_id"] == "2"
+
+
+def test_beam_search_matches_transformers_generate():
+    """The oracle's beam search (and through it the product's, tests/test_model_gpu.py) against GenerationMixin.generate of the
+    INSTALLED transformers on random tiny T5s: beams 1-5, min_length, length penalties, padded encoder rows, with and without
+    eos reached.  The reference pins transformers 4.46.1, which is not in this image; this pins the restatement to the
+    library's published algorithm as shipped in the installed version (sequences compared up to the first eos -- the pad
+    value after it differs between versions and is dropped by decoding anyway)."""
+    tf = pytest.importorskip("transformers")
+    if not hasattr(tf.T5ForConditionalGeneration, "generate"):
+        pytest.skip("this transformers build has no T5 generate")
+
+    def trim(row):
+        out = []
+        for t in row.tolist()[1:]:
+            out.append(t)
+            if t == 1:
+                break
+        return out
+
+    n = with_eos = 0
+    for seed in range(8):
+        torch.manual_seed(seed)
+        cfg = tf.T5Config(vocab_size=24, d_model=32, d_kv=8, d_ff=64, num_layers=2, num_decoder_layers=2, num_heads=4,
+                          feed_forward_proj="gated-gelu", tie_word_embeddings=False, pad_token_id=0, eos_token_id=1,
+                          decoder_start_token_id=0, dropout_rate=0.0)
+        m = tf.T5ForConditionalGeneration(cfg).eval()
+        with torch.no_grad():
+            for p in m.parameters():
+                p.mul_(1.5 + 0.25 * (seed % 5))                                       # sharper / flatter next-token distributions
+            if seed % 2:
+                m.lm_head.weight[1] = 1.0 * m.lm_head.weight[3::4].sum(0)                  # make eos competitive
+        B, L = 4, 6
+        emb = torch.randn(B, L, 32)
+        mask = torch.ones(B, L, dtype=torch.long)
+        mask[2, 4:] = 0
+        for nb, mnt, minl, lp in [(5, 12, 1, 1.0), (4, 8, 3, 1.0), (1, 10, 1, 1.0), (3, 15, 1, 2.0), (5, 6, 1, 0.5)]:
+            with torch.no_grad():
+                want = m.generate(inputs_embeds=emb, attention_mask=mask, num_beams=nb, max_new_tokens=mnt, min_length=minl,
+                                  length_penalty=lp, do_sample=False, repetition_penalty=1.0, early_stopping=False)
+                enc = m.encoder(inputs_embeds=emb, attention_mask=mask).last_hidden_state
+
+            def step(ids):
+                k = ids.shape[0] // B
+                with torch.no_grad():
+                    return m(encoder_outputs=(enc.repeat_interleave(k, 0),), attention_mask=mask.repeat_interleave(k, 0),
+                             decoder_input_ids=ids).logits[:, -1]
+
+            got = beam_search(step, batch=B, num_beams=nb, max_new_tokens=mnt, min_length=minl, length_penalty=lp)
+            for b in range(B):
+                a, c = trim(want[b]), trim(got[b])
+                assert a == c, (seed, nb, mnt, minl, lp, b, a, c)
+                n += 1
+                with_eos += a[-1] == 1
+    assert n == 160 and 12 <= with_eos <= 148, with_eos        # both finished and length-capped hypotheses were exercised
