@@ -96,17 +96,30 @@ class Cv2VideoReader:
         return torch.from_numpy(np.stack([got[int(i)] for i in indices]))
 
 
+def random_resized_crop(clip, size, scale=(0.5, 1.0), ratio=(3.0 / 4.0, 4.0 / 3.0), mode="bicubic"):
+    """The train processor's augmentation (blip_processors.py:302-315 -> transforms_video.py:53-83): one random window for
+    the whole clip -- area fraction in `scale`, log-uniform aspect in `ratio`, drawn from torch's global generator by
+    torchvision's RandomResizedCrop.get_params -- resized to size x size with torch's bicubic kernel, then truncated to uint8
+    as ToUint8 does.  clip: [3,T,H,W] (uint8 or float) -> uint8 [3,T,size,size]."""
+    from torchvision.transforms import RandomResizedCrop
+    clip = clip.float()
+    i, j, h, w = RandomResizedCrop.get_params(clip, list(scale), list(ratio))
+    out = torch.nn.functional.interpolate(clip[..., i:i + h, j:j + w], size=(size, size), mode=mode, align_corners=False)
+    return out.to(torch.uint8)
+
+
 class VideoProcessor:
     """Callable (video_path, clip_proposal) -> (frames, indices, fps), the contract of Blip2VideoTrainProcessor /
     BlipVideoEvalProcessor (blip_processors.py:287-393) as the dataset uses it.  Frames are decoded at image_size x image_size;
-    uint8=False returns the reference layout -- float32 [3,T,H,W], scaled to [0,1] and CLIP-normalised; uint8=True returns raw
-    uint8 [3,T,H,W] for the fused normalisation on the device.  (The train processor's RandomResizedCrop augmentation is not
-    restated: frames are used at full view, as in the eval processor.)"""
+    augment=True applies the train processor's RandomResizedCrop (scale 0.5-1, bicubic).  uint8=False returns the reference
+    layout -- float32 [3,T,H,W], scaled to [0,1] and CLIP-normalised; uint8=True returns the uint8 [3,T,H,W] the reference has
+    just before ToTensorVideo, for the fused normalisation on the device (same values, a quarter of the bytes)."""
 
     def __init__(self, image_size=224, n_frms=60, sampling="uniform", uint8=False, reader=Cv2VideoReader, rng=None,
-                 mean=PIXEL_MEAN, std=PIXEL_STD):
+                 mean=PIXEL_MEAN, std=PIXEL_STD, augment=False, min_scale=0.5, max_scale=1.0):
         self.image_size, self.n_frms, self.sampling, self.uint8 = image_size, n_frms, sampling, uint8
         self.reader, self.rng = reader, rng
+        self.augment, self.scale = augment, (min_scale, max_scale)
         self.mean = torch.tensor(mean).view(3, 1, 1, 1)
         self.std = torch.tensor(std).view(3, 1, 1, 1)
 
@@ -115,6 +128,8 @@ class VideoProcessor:
         fps = vr.get_avg_fps()
         indices = sample_frame_indices(len(vr), fps, self.n_frms, self.sampling, clip_proposal, self.rng)
         frames = vr.get_batch(indices).permute(3, 0, 1, 2)                  # T,H,W,C -> C,T,H,W
+        if self.augment:
+            frames = random_resized_crop(frames, self.image_size, self.scale)
         if not self.uint8:
             frames = (frames.float() / 255.0 - self.mean) / self.std        # ToTensorVideo + NormalizeVideo
         return frames, indices, fps

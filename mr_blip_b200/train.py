@@ -122,7 +122,8 @@ def build_datasets(cfg, splits, uint8=True, reader=data.Cv2VideoReader):
         is_train = split == "train"
         vp = ds.get("vis_processor", {}).get("train" if is_train else "eval", {})
         proc = data.VideoProcessor(image_size=vp.get("image_size", 224), n_frms=vp.get("n_frms", 60),
-                                   sampling="random" if is_train else "uniform", uint8=uint8, reader=reader)
+                                   sampling="random" if is_train else "uniform", uint8=uint8, reader=reader, augment=is_train,
+                                   min_scale=vp.get("min_scale", 0.5), max_scale=vp.get("max_scale", 1.0))
         out[split] = data.MomentRetrievalDataset(proc, None, info["videos"]["storage"], [info["annotations"][split]["storage"]])
     return out
 

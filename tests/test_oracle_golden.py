@@ -294,3 +294,26 @@ def test_beam_search_matches_transformers_generate():
                 n += 1
                 with_eos += a[-1] == 1
     assert n == 160 and 12 <= with_eos <= 148, with_eos        # both finished and length-capped hypotheses were exercised
+
+
+def test_train_crop_matches_reference_transform(golden_dir):
+    """data.random_resized_crop against the reference's RandomResizedCropVideo + ToUint8 (bicubic, one window per clip) on the
+    generator's synthetic clip under the same torch seed.  Same crop window required; pixel values may differ by one grey
+    level where another CPU's interpolation rounds a .999 the other way."""
+    import sys
+    sys.path.insert(0, golden_dir)
+    from make_golden_crop import synth_clip
+    from mr_blip_b200 import data
+    gold = np.load(os.path.join(golden_dir, "crop_golden.npz"))
+    clip = synth_clip()
+    for k in range(3):
+        seed, size, s0, s1 = gold["meta%d" % k].tolist()
+        torch.manual_seed(seed)
+        got = data.random_resized_crop(clip, size, scale=(s0 / 1000.0, s1 / 1000.0))
+        want = torch.from_numpy(gold["case%d" % k])
+        assert got.dtype == torch.uint8 and got.shape == want.shape
+        diff = (got.int() - want.int()).abs()
+        assert diff.max().item() <= 1 and (diff > 0).float().mean().item() < 1e-3, (k, diff.max().item())
+        torch.manual_seed(seed)
+        again = data.random_resized_crop(clip.to(torch.uint8), size, scale=(s0 / 1000.0, s1 / 1000.0))     # uint8 frames in, as decoded
+        assert torch.equal(again, got)
