@@ -1,0 +1,20 @@
+#!/bin/bash
+# First GPU call of the next round: everything that was written after round 1's GPU budget ran out, in dependency order.
+#   1. the default GPU suite (must still be green: gemm.cu host dispatch, ops.py and config.py changed since the last GPU run)
+#   2. the experimental split-K tests (tests/test_experimental_gpu.py)
+#   3. small-shape sweep without / with split-K, and the bench line without / with it
+# If 2 is green and 3 shows the gain: flip ops.SPLITK's default, move the tests into tests/test_kernels_gpu.py.
+set -u
+O=gpurun_out
+mkdir -p $O
+( timeout 500 python -m pytest tests -m gpu -q 2>&1 | tail -15 ) > $O/pytest.log 2>&1
+tail -3 $O/pytest.log
+( MRB_TEST_EXPERIMENTAL=1 timeout 300 python -m pytest tests/test_experimental_gpu.py -m gpu -q 2>&1 | tail -25 ) > $O/pytest_experimental.log 2>&1
+tail -5 $O/pytest_experimental.log
+( timeout 200 python tools/gemm_sweep.py default $O/sweep_default.json ) > $O/sweep_default.log 2>&1
+( MRB_GEMM_SPLITK=1 timeout 200 python tools/gemm_sweep.py splitk $O/sweep_splitk.json ) > $O/sweep_splitk.log 2>&1
+grep -h "dec_\|down32\|lm_head" $O/sweep_default.log $O/sweep_splitk.log | cut -c1-220
+( timeout 400 python bench.py --steps 8 --warmup 3 ) > $O/bench.json 2> $O/bench.err
+( MRB_GEMM_SPLITK=1 timeout 400 python bench.py --steps 8 --warmup 3 ) > $O/bench_splitk.json 2> $O/bench_splitk.err
+cut -c1-200 $O/bench.json $O/bench_splitk.json
+( MRB_GEMM_SPLITK=1 timeout 300 python tools/run_configs.py $O/configs_splitk.json 2>&1 | tail -5 ) > $O/configs_splitk.log 2>&1
