@@ -18,3 +18,6 @@ grep -h "dec_\|down32\|lm_head" $O/sweep_default.log $O/sweep_splitk.log | cut -
 ( MRB_GEMM_SPLITK=1 timeout 400 python bench.py --steps 8 --warmup 3 ) > $O/bench_splitk.json 2> $O/bench_splitk.err
 cut -c1-200 $O/bench.json $O/bench_splitk.json
 ( MRB_GEMM_SPLITK=1 timeout 300 python tools/run_configs.py $O/configs_splitk.json 2>&1 | tail -5 ) > $O/configs_splitk.log 2>&1
+# what bounds the operand feed of one SM (decides: 64-row A boxes? multicast? more CTAs per problem?)
+( nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -o /tmp/tma_feed_probe tools/probe/tma_feed_probe.cu -lcuda 2>&1 | grep -v deprecated; timeout 120 /tmp/tma_feed_probe ) > $O/tma_feed_probe.log 2>&1
+tail -45 $O/tma_feed_probe.log
