@@ -34,16 +34,17 @@ def beam_search(t5, inputs_embeds, attention_mask, num_beams=5, max_new_tokens=5
                 eos_id=1, pad_id=0, start_id=0):
     B, Le, _ = inputs_embeds.shape
     nb = num_beams
+    dev = inputs_embeds.device                                           # bookkeeping tensors follow the engine's device
     enc_ext, kmask = t5.encode(inputs_embeds, attention_mask)
     max_length = max_new_tokens + 1
     st = t5.init_decode(enc_ext, B, Le, nb, max_length)
     ids = [[start_id] for _ in range(B * nb)]
-    beam_scores = torch.zeros((B, nb), dtype=torch.float32, device="cuda")
+    beam_scores = torch.zeros((B, nb), dtype=torch.float32, device=dev)
     beam_scores[:, 1:] = -1e9
     beam_scores = beam_scores.view(-1)
     hyps = [_Hyps(nb, length_penalty) for _ in range(B)]
     done = [False] * B
-    tokens = torch.full((B * nb,), start_id, dtype=torch.long, device="cuda")
+    tokens = torch.full((B * nb,), start_id, dtype=torch.long, device=dev)
     cur = 1
     reorder = None                                                       # beam index each cache row continues from
     while True:
@@ -80,12 +81,12 @@ def beam_search(t5, inputs_embeds, attention_mask, num_beams=5, max_new_tokens=5
             done[b] = done[b] or hyps[b].is_done(top_s_c[b].max().item(), cur_len, 1)
         flat_idx = nxt_idx.view(-1)
         ids = [ids[i] + [t] for i, t in zip(flat_idx.tolist(), nxt_tok.view(-1).tolist())]
-        beam_scores = nxt_scores.view(-1).cuda()
-        tokens = nxt_tok.view(-1).cuda()
+        beam_scores = nxt_scores.view(-1).to(dev)
+        tokens = nxt_tok.view(-1).to(dev)
         cur += 1
         if all(done) or cur >= max_length:
             break
-        reorder = flat_idx.cuda()
+        reorder = flat_idx.to(dev)
     for b in range(B):
         if done[b]:
             continue

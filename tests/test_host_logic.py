@@ -400,3 +400,71 @@ def test_standalone_training_loop_mechanics(tmp_path):
     assert json.load(open(tmp_path / "result" / "val_epoch1.json"))[0]["target"] == "[[1, 3]]"
     path = checkpoint.save_checkpoint(model, opt, str(tmp_path / "out"), 1, config=cfg)
     assert set(torch.load(path)["model"]) == {"w"}
+
+
+def test_product_beam_search_bookkeeping_matches_transformers_generate():
+    """mr_blip_b200.generation.beam_search (the PRODUCT's host-side hypothesis bookkeeping: candidate selection, eos handling,
+    incremental cache reorder indices, finalisation) driven by a stand-in engine whose decode_step evaluates a tiny
+    transformers T5 on the CPU, against that model's own generate().  The stand-in keeps per-row token histories exactly as
+    the real engine keeps per-row K/V caches -- reordered by `beam_idx` before the new token is appended -- so a wrong reorder
+    index or score carry-over shows up as a different sequence."""
+    tf = pytest.importorskip("transformers")
+    if not hasattr(tf.T5ForConditionalGeneration, "generate"):
+        pytest.skip("this transformers build has no T5 generate")
+    from mr_blip_b200.generation import beam_search
+
+    class Engine:
+        def __init__(self, model):
+            self.m = model
+
+        def encode(self, inputs_embeds, attention_mask):
+            with torch.no_grad():
+                return self.m.encoder(inputs_embeds=inputs_embeds, attention_mask=attention_mask).last_hidden_state, attention_mask
+
+        def init_decode(self, enc, B, Le, beams, max_len):
+            return {"enc": enc.repeat_interleave(beams, 0), "hist": torch.zeros(B * beams, max_len, dtype=torch.long), "beams": beams}
+
+        def decode_step(self, st, tokens, t, kmask, beam_idx=None):
+            if beam_idx is not None:
+                st["hist"] = st["hist"][beam_idx]
+            st["hist"][:, t] = tokens
+            with torch.no_grad():
+                out = self.m(encoder_outputs=(st["enc"],), attention_mask=kmask.repeat_interleave(st["beams"], 0),
+                             decoder_input_ids=st["hist"][:, :t + 1])
+            return out.logits[:, -1].float()
+
+    def trim(row):
+        out = []
+        for t in row.tolist()[1:]:
+            out.append(t)
+            if t == 1:
+                break
+        return out
+
+    n = with_eos = 0
+    for seed in range(6):
+        torch.manual_seed(100 + seed)
+        cfg = tf.T5Config(vocab_size=24, d_model=32, d_kv=8, d_ff=64, num_layers=2, num_decoder_layers=2, num_heads=4,
+                          feed_forward_proj="gated-gelu", tie_word_embeddings=False, pad_token_id=0, eos_token_id=1,
+                          decoder_start_token_id=0, dropout_rate=0.0)
+        m = tf.T5ForConditionalGeneration(cfg).eval()
+        with torch.no_grad():
+            for p in m.parameters():
+                p.mul_(1.5 + 0.25 * (seed % 5))
+            if seed % 2:
+                m.lm_head.weight[1] = 1.0 * m.lm_head.weight[3::4].sum(0)
+        B, L = 3, 6
+        emb = torch.randn(B, L, 32)
+        mask = torch.ones(B, L, dtype=torch.long)
+        mask[1, 4:] = 0
+        for nb, mnt, minl, lp in [(5, 12, 1, 1.0), (4, 8, 3, 1.0), (1, 10, 1, 1.0), (3, 15, 1, 2.0)]:
+            with torch.no_grad():
+                want = m.generate(inputs_embeds=emb, attention_mask=mask, num_beams=nb, max_new_tokens=mnt, min_length=minl,
+                                  length_penalty=lp, do_sample=False, repetition_penalty=1.0, early_stopping=False)
+            got = beam_search(Engine(m), emb, mask, num_beams=nb, max_new_tokens=mnt, min_length=minl, length_penalty=lp)
+            for b in range(B):
+                a, c = trim(want[b]), trim(got[b])
+                assert a == c, (seed, nb, mnt, minl, lp, b, a, c)
+                n += 1
+                with_eos += a[-1] == 1
+    assert n == 72 and with_eos >= 5, with_eos
