@@ -39,6 +39,10 @@ int mrb_gemm_splitk(const void* A, long long lda, const void* B, long long ldb, 
                     const float* bias, int gelu, const float* resid, long long ldr, void* out, int out_dtype, long long ldc,
                     int row_group, int force_bn, void* ws, long long ws_bytes, int max_splits, void* stream);
 
+/* The (tile width, splits, K blocks of 64 per split) mrb_gemm_splitk would use on a device with `sms` SMs; splits == 1 is
+ * the unsplit path.  Host arithmetic only (no device work): workspace sizing and tests. */
+int mrb_gemm_splitk_plan(int M, int N, int K, int sms, int force_bn, int max_splits, int* bn, int* splits, int* kb_per_split);
+
 /* softmax(scale * Q K^T + bias[h, j - i] + mask) V, scores never written to HBM; optional log-sum-exp for backward.
  * kv_div > 1: query batch b reads K/V/mask batch b / kv_div (beams sharing one encoder output).
  * Replaces eva_vit.py:128-145, Qformer.py:198-268, modeling_t5.py:561-610. */

@@ -11,6 +11,7 @@ _p, _ll, _i, _f = ctypes.c_void_p, ctypes.c_longlong, ctypes.c_int, ctypes.c_flo
 # name -> argument ctypes, in header order (must match include/mrblip_b200.h)
 SIGNATURES = {
     "mrb_gemm": [_p, _ll, _p, _ll, _i, _i, _i, _i, _p, _i, _p, _ll, _p, _i, _ll, _i, _i, _p],
+    "mrb_gemm_splitk_plan": [_i, _i, _i, _i, _i, _i, _p, _p, _p],
     "mrb_gemm_splitk": [_p, _ll, _p, _ll, _i, _i, _i, _i, _p, _i, _p, _ll, _p, _i, _ll, _i, _i, _p, _ll, _i, _p],
     "mrb_attention_fwd": [_p, _ll, _ll, _p, _ll, _ll, _p, _ll, _ll, _p, _ll, _ll, _i, _i, _i, _i, _i, _i, _f, _p, _i, _i,
                           _p, _i, _i, _i, _p, _p],

@@ -521,6 +521,20 @@ extern "C" int mrb_gemm(const void* A, long long lda, const void* B, long long l
                    stream);
 }
 
+// The split-K decision of mrb_gemm_splitk for a problem on a device with `sms` SMs (host arithmetic only; lets callers size
+// workspaces and lets the CPU tests check the plan): *splits == 1 means the unsplit path.
+extern "C" int mrb_gemm_splitk_plan(int M, int N, int K, int sms, int force_bn, int max_splits, int* bn, int* splits,
+                                    int* kb_per_split) {
+  if (M <= 0 || N <= 0 || K <= 0 || sms <= 0 || !bn || !splits || !kb_per_split) return MRB_ERR_ARG;
+  SplitPlan sp = {force_bn ? force_bn : pick_bn(M, N, sms), 1, (K + BK - 1) / BK};
+  if (max_splits > 1 && (M <= BM || N <= 32)) {
+    const SplitPlan cand = plan_split(M, N, K, sms, force_bn, max_splits < 8 ? max_splits : 8);
+    if (cand.splits > 1) sp = cand;
+  }
+  *bn = sp.bn; *splits = sp.splits; *kb_per_split = sp.kb_per;
+  return MRB_OK;
+}
+
 // mrb_gemm with a caller-owned fp32 workspace: problems with one row tile (decoder steps, M <= 128) or 32 columns (LoRA
 // down-projections) whose grid would leave most SMs idle are split along K over up to max_splits CTAs per output tile
 // (partials in `ws`, >= splits * M * N * 4 bytes, 16-byte aligned; summed in split order by a second launch that applies the

@@ -468,3 +468,49 @@ def test_product_beam_search_bookkeeping_matches_transformers_generate():
                 n += 1
                 with_eos += a[-1] == 1
     assert n == 72 and with_eos >= 5, with_eos
+
+
+def test_splitk_plan_covers_k_exactly_and_fits_the_chip():
+    """mrb_gemm_splitk_plan (host arithmetic of the split-K dispatch, callable without a GPU) on the path's decoder-sized and
+    32-column shapes: every K block belongs to exactly one non-empty split, tiles x splits CTAs fit the SM count, problems with
+    enough tiles or short K stay unsplit, and a forced tile width is honoured."""
+    from mr_blip_b200 import _lib
+    if not os.path.exists(_lib.LIB_PATH):
+        import __graft_entry__ as ge
+        ge.build()
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    fn = lib.mrb_gemm_splitk_plan
+    fn.argtypes = [ctypes.c_int] * 6 + [ctypes.POINTER(ctypes.c_int)] * 3
+    fn.restype = ctypes.c_int
+
+    def plan(M, N, K, sms=148, force_bn=0, max_splits=8):
+        bn, sp, per = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
+        assert fn(M, N, K, sms, force_bn, max_splits, ctypes.byref(bn), ctypes.byref(sp), ctypes.byref(per)) == 0
+        return bn.value, sp.value, per.value
+
+    shapes = [(56, 2048, 2080), (56, 6144, 2080), (56, 10240, 2080), (56, 5120, 2080), (64, 2048, 10272), (56, 2048, 5152),
+              (56, 2048, 6176), (56, 2048, 32160), (5, 2048, 2080), (80, 2048, 2080), (128, 4096, 2080),
+              (8132, 32, 2048), (8132, 32, 10240), (8132, 32, 5120), (300, 32, 2048), (7680, 32, 768)]
+    split_any = 0
+    for sms in (148, 132, 74):
+        for M, N, K in shapes:
+            for ms in (2, 4, 8):
+                bn, sp, per = plan(M, N, K, sms, 0, ms)
+                kb = (K + 63) // 64
+                assert bn in (32, 64, 128, 192, 256) and 1 <= sp <= ms
+                assert (bn == 32) == (N <= 32) or sp == 1
+                if sp > 1:
+                    split_any += 1
+                    tiles = ((M + 127) // 128) * ((N + bn - 1) // bn)
+                    assert tiles * sp <= sms, (M, N, K, bn, sp)
+                    assert per >= 4 and (sp - 1) * per < kb <= sp * per, (M, N, K, sp, per, kb)      # last split non-empty, all covered
+                else:
+                    assert per == kb
+    assert split_any > 60
+    assert plan(56, 2048, 2080)[1] > 1 and plan(8132, 32, 2048)[1] == 2
+    assert plan(56, 32128, 2080)[1] == 1                     # lm_head: 126+ tiles already fill the chip
+    assert plan(56, 2048, 192)[1] == 1                       # 3 K blocks: nothing to split
+    assert plan(8132, 2048, 2080)[1] == 1                    # many row tiles: never split
+    assert plan(56, 2048, 2080, max_splits=1)[1] == 1
+    assert plan(56, 2048, 2080, force_bn=64, max_splits=4) == (64, 4, 9)
+    assert fn(0, 8, 8, 148, 0, 8, None, None, None) != 0
