@@ -54,8 +54,9 @@ class MomentRetrievalTask:
         return results
 
     def after_evaluation(self, results, split_name, epoch, result_dir, rank=0, world=1):
-        """Per-rank result files merged by rank 0 (base_task.py:251-288: duplicates from sampler padding dropped by qid),
-        then the metrics of _report_metrics.  Returns the metrics on rank 0, None elsewhere."""
+        """Per-rank result files concatenated by rank 0 (base_task.py:250-288; like the reference's task, which passes no
+        remove_duplicate key, the clips DistributedSampler repeats to even out the ranks are counted twice), then the
+        metrics of _report_metrics.  Returns the metrics on rank 0, None elsewhere."""
         os.makedirs(result_dir, exist_ok=True)
         name = "%s_epoch%s" % (split_name, epoch)
         with open(os.path.join(result_dir, "%s_rank%d.json" % (name, rank)), "w") as f:
@@ -63,12 +64,9 @@ class MomentRetrievalTask:
         mdist.barrier()
         if rank != 0:
             return None
-        merged, seen = [], set()
+        merged = []
         for r in range(world):
-            for rec in json.load(open(os.path.join(result_dir, "%s_rank%d.json" % (name, r)))):
-                if rec["qid"] not in seen:
-                    seen.add(rec["qid"])
-                    merged.append(rec)
+            merged += json.load(open(os.path.join(result_dir, "%s_rank%d.json" % (name, r))))
         path = os.path.join(result_dir, name + ".json")
         with open(path, "w") as f:
             json.dump(merged, f)
