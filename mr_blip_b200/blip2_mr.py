@@ -169,6 +169,13 @@ class BLIP2_MR(Blip2Base):
                     task=get("task", "qformer_freeze_lora"), num_frames_for_answer=get("num_frames_for_answer", 4),
                     resample_frames=get("resample_frames", False), dims=get("dims", None),
                     init_seed=get("init_seed", 1234), lora_b_std=get("lora_b_std", 0.0))
+        # third-party weights the reference fetches from hubs, from local files here: `t5_model` may be a transformers
+        # directory (as it may be for from_pretrained), `vit_weights` an eva_vit_g.pth
+        from . import weights
+        if isinstance(get("t5_model", None), str) and os.path.isdir(get("t5_model")):
+            weights.load_hf_t5(model, get("t5_model"))
+        if get("vit_weights", None):
+            weights.load_eva_vit(model, get("vit_weights"))
         model.load_checkpoint_from_config(cfg)
         return model
 

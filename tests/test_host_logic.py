@@ -514,3 +514,67 @@ def test_splitk_plan_covers_k_exactly_and_fits_the_chip():
     assert plan(56, 2048, 2080, max_splits=1)[1] == 1
     assert plan(56, 2048, 2080, force_bn=64, max_splits=4) == (64, 4, 9)
     assert fn(0, 8, 8, 148, 0, 8, None, None, None) != 0
+
+
+def test_third_party_weight_files_load_into_reference_key_names(tmp_path, tiny_sd):
+    """mr_blip_b200.weights: a sharded transformers T5 directory (safetensors + index) and an eva_vit_g-style .pth map onto the
+    model's peft / visual_encoder names; LoRA adapters and the Q-Former are left alone, incomplete or mis-shaped files raise."""
+    from safetensors.torch import save_file
+    from mr_blip_b200 import weights
+    from mr_blip_b200.blip2_mr import BLIP2_MR
+    m = BLIP2_MR(dims=TINY, state_dict=tiny_sd)
+    before = {k: v.clone() for k, v in m.state_dict().items()}
+    g = torch.Generator().manual_seed(5)
+    # transformers-style T5 state dict: plain names, no adapters
+    hf = {}
+    for k, v in before.items():
+        if k.startswith(T5_PREFIX) and "lora_" not in k:
+            hf[k[len(T5_PREFIX):].replace(".base_layer.", ".")] = (torch.randn(v.shape, generator=g) * 0.02).to(v.dtype)
+    hf["encoder.embed_tokens.weight"] = hf["shared.weight"].clone()          # files repeat the tied tensor
+    hf["decoder.embed_tokens.weight"] = hf["shared.weight"].clone()
+    assert "lm_head.weight" in hf and "encoder.block.0.layer.0.SelfAttention.q.weight" in hf
+    t5_dir = tmp_path / "flan-t5"
+    t5_dir.mkdir()
+    names = sorted(hf)
+    shards = {"model-00001-of-00002.safetensors": names[::2], "model-00002-of-00002.safetensors": names[1::2]}
+    for fn, ks in shards.items():
+        save_file({k: hf[k].contiguous() for k in ks}, str(t5_dir / fn))
+    (t5_dir / "model.safetensors.index.json").write_text(json.dumps({"weight_map": {k: fn for fn, ks in shards.items() for k in ks}}))
+    n, unknown = weights.load_hf_t5(m, str(t5_dir))
+    assert n == len(hf) and unknown == []
+    after = m.state_dict()
+    assert torch.equal(after[T5_PREFIX + "encoder.block.0.layer.0.SelfAttention.q.base_layer.weight"], hf["encoder.block.0.layer.0.SelfAttention.q.weight"])
+    assert torch.equal(after[T5_PREFIX + "lm_head.base_layer.weight"], hf["lm_head.weight"])
+    assert torch.equal(after[T5_PREFIX + "encoder.embed_tokens.weight"], hf["shared.weight"])
+    assert m._get(T5_PREFIX + "decoder.embed_tokens.weight") is m._get(T5_PREFIX + "shared.weight")       # still tied
+    for k in before:
+        if "lora_" in k or k.startswith(("Qformer.", "visual_encoder.", "ln_vision.", "t5_proj.")) or k == "query_tokens":
+            assert torch.equal(after[k], before[k]), k
+    # eva_vit_g-style file: un-prefixed names, one extra block, head and final norm
+    vit = {k[len("visual_encoder."):]: torch.randn(v.shape, generator=g) * 0.02 for k, v in before.items() if k.startswith("visual_encoder.")}
+    vit.update({"blocks.39.attn.qkv.weight": torch.zeros(4, 4), "norm.weight": torch.ones(8), "head.weight": torch.zeros(2, 8)})
+    vpath = str(tmp_path / "eva_vit_g.pth")
+    torch.save(vit, vpath)
+    n, skipped = weights.load_eva_vit(m, vpath)
+    assert sorted(skipped) == ["blocks.39.attn.qkv.weight", "head.weight", "norm.weight"] and n == len(vit) - 3
+    w = m.state_dict()["visual_encoder.blocks.1.mlp.fc1.weight"]
+    assert w.dtype == torch.float16 and torch.equal(w, vit["blocks.1.mlp.fc1.weight"].half())
+    assert torch.equal(m.state_dict()["visual_encoder.pos_embed"], vit["pos_embed"])
+    # failure modes
+    part = dict(hf)
+    del part["decoder.block.1.layer.2.DenseReluDense.wo.weight"]
+    with pytest.raises(RuntimeError, match="incomplete"):
+        weights.load_hf_t5(m, part)
+    bad = dict(hf)
+    bad["lm_head.weight"] = torch.zeros(7, 7)
+    with pytest.raises(RuntimeError, match="shape mismatch"):
+        weights.load_hf_t5(m, bad)
+    with pytest.raises(RuntimeError, match="invalid"):
+        weights.read_state_dict(str(tmp_path / "nope.bin"))
+    # from_config picks both up from the recipe
+    from mr_blip_b200.config import build_model
+    m2, _ = build_model(os.path.join(ROOT, "mr_blip_b200", "configs", "projects", "mr_BLIP", "train", "qvh.yaml"),
+                        options=["model.t5_model=%s" % t5_dir, "model.vit_weights=%s" % vpath], dims=TINY)
+    sd2 = m2.state_dict()
+    assert torch.equal(sd2[T5_PREFIX + "lm_head.base_layer.weight"], hf["lm_head.weight"])
+    assert torch.equal(sd2["visual_encoder.blocks.0.attn.proj.weight"], vit["blocks.0.attn.proj.weight"].half())
