@@ -92,6 +92,11 @@ class Blip2T5(Blip2Base):
                     freeze_vit=get("freeze_vit", True), prompt=get("prompt", ""), max_txt_len=get("max_txt_len", 32),
                     apply_lemmatizer=get("apply_lemmatizer", False), dims=get("dims", None), init_seed=get("init_seed", 1234))
         import os
+        from . import weights
+        if isinstance(get("t5_model", None), str) and os.path.isdir(get("t5_model")):      # local transformers directory
+            weights.load_hf_t5(model, get("t5_model"), prefix=PLAIN_PREFIX)
+        if get("vit_weights", None):
+            weights.load_eva_vit(model, get("vit_weights"))
         for key in ("pretrained", "finetuned") if get("load_finetuned", True) else ("pretrained",):
             path = get(key, None)
             if path and os.path.isfile(path):

@@ -578,3 +578,8 @@ def test_third_party_weight_files_load_into_reference_key_names(tmp_path, tiny_s
     sd2 = m2.state_dict()
     assert torch.equal(sd2[T5_PREFIX + "lm_head.base_layer.weight"], hf["lm_head.weight"])
     assert torch.equal(sd2["visual_encoder.blocks.0.attn.proj.weight"], vit["blocks.0.attn.proj.weight"].half())
+    # the plain-named sibling (blip2_t5) takes the same directory under its own prefix
+    from mr_blip_b200.blip2_t5 import Blip2T5
+    m3 = Blip2T5.from_config({"t5_model": str(t5_dir), "vit_weights": vpath, "dims": TINY})
+    assert torch.equal(m3.state_dict()["t5_model.encoder.block.1.layer.1.DenseReluDense.wi_0.weight"],
+                       hf["encoder.block.1.layer.1.DenseReluDense.wi_0.weight"])
