@@ -85,6 +85,8 @@ struct ScoreCtx {
 
 template <typename T, int HD>
 __global__ void __launch_bounds__(NTHREADS) attn_fwd_kernel(const AttnParams p) {
+  mrb::pdl_trigger();
+  mrb::pdl_wait();      // before the first global access (common.cuh, MRB_PDL)
   constexpr int LDS = HD + 8;
   extern __shared__ __align__(16) uint8_t smem_attn[];
   T* sQ = reinterpret_cast<T*>(smem_attn);
@@ -233,6 +235,8 @@ __global__ void __launch_bounds__(NTHREADS) attn_fwd_kernel(const AttnParams p) 
 constexpr int XQ_MAXG = 5;                    // 16-key groups per warp: Lk <= 4 * 5 * 16 = 320
 template <typename T>
 __global__ void __launch_bounds__(128) attn_xq_kernel(const AttnParams p) {
+  mrb::pdl_trigger();
+  mrb::pdl_wait();      // before the first global access (common.cuh, MRB_PDL)
   // rows are 128 B (64 x 16 bit), 16-byte chunk c of row r lives at chunk (c ^ (r & 7)): conflict-free ldmatrix without
   // padding, so Q + K + V of 257 keys take 72 KB and THREE CTAs share an SM
   constexpr int HD = 64, LDS = HD, LQ = 32;
@@ -409,6 +413,8 @@ __global__ void __launch_bounds__(128) attn_xq_kernel(const AttnParams p) {
 // delta[b,h,i] = sum_d dO[b,i,h,d] * O[b,i,h,d]
 template <typename T>
 __global__ void attn_delta_kernel(const AttnParams p) {
+  mrb::pdl_trigger();
+  mrb::pdl_wait();      // before the first global access (common.cuh, MRB_PDL)
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   const int total = p.B * p.H * p.Lq;
@@ -425,6 +431,8 @@ __global__ void attn_delta_kernel(const AttnParams p) {
 // dQ = scale * sum_j dS_ij K_j   with dS = P * (dO V^T - delta).  One CTA per 64 query rows.
 template <typename T, int HD>
 __global__ void __launch_bounds__(NTHREADS) attn_bwd_dq_kernel(const AttnParams p) {
+  mrb::pdl_trigger();
+  mrb::pdl_wait();      // before the first global access (common.cuh, MRB_PDL)
   constexpr int LDS = HD + 8;
   extern __shared__ __align__(16) uint8_t smem_attn[];
   T* sQ = reinterpret_cast<T*>(smem_attn);
@@ -549,6 +557,8 @@ __global__ void __launch_bounds__(NTHREADS) attn_bwd_dq_kernel(const AttnParams 
 // problem (keys are the MMA M dimension) so P^T / dS^T fragments feed the second MMAs directly.
 template <typename T, int HD>
 __global__ void __launch_bounds__(NTHREADS) attn_bwd_dkv_kernel(const AttnParams p) {
+  mrb::pdl_trigger();
+  mrb::pdl_wait();      // before the first global access (common.cuh, MRB_PDL)
   constexpr int LDS = HD + 8;
   extern __shared__ __align__(16) uint8_t smem_attn[];
   T* sK = reinterpret_cast<T*>(smem_attn);
@@ -692,6 +702,8 @@ __global__ void __launch_bounds__(128) attn_row_kernel(const T* __restrict__ q, 
                                                        long long k_bs, long long k_rs, const T* __restrict__ v, long long v_bs,
                                                        long long v_rs, T* __restrict__ o, long long o_bs, int B, int H, int Lk,
                                                        int hd, float scale) {
+  mrb::pdl_trigger();
+  mrb::pdl_wait();      // before the first global access (common.cuh, MRB_PDL)
   extern __shared__ float sp[];                       // [4 warps][Lk] scores / probabilities
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int bh = blockIdx.x * 4 + warp;
@@ -765,7 +777,7 @@ static int launch_fwd(const AttnParams& p, cudaStream_t s) {
   static bool cfg = false;
   if (!cfg) { if (int rc = set_smem(attn_fwd_kernel<T, HD>, smem)) return rc; cfg = true; }
   dim3 grid((p.Lq + BQ - 1) / BQ, p.H, p.B);
-  attn_fwd_kernel<T, HD><<<grid, NTHREADS, smem, s>>>(p);
+  MRB_LAUNCH((attn_fwd_kernel<T, HD>), grid, NTHREADS, smem, s, p);
   MRB_CHECK_LAUNCH();
   return MRB_OK;
 }
@@ -776,7 +788,7 @@ static int launch_xq(const AttnParams& p, cudaStream_t s) {
   const int smem = (32 + 2 * LkP) * 64 * 2;
   static int cfg = 0;
   if (cfg < smem) { if (int rc = set_smem(attn_xq_kernel<T>, smem)) return rc; cfg = smem; }
-  attn_xq_kernel<T><<<dim3(p.H, p.B), 128, smem, s>>>(p);
+  MRB_LAUNCH((attn_xq_kernel<T>), dim3(p.H, p.B), 128, smem, s, p);
   MRB_CHECK_LAUNCH();
   return MRB_OK;
 }
@@ -785,7 +797,7 @@ template <typename T, int HD>
 static int launch_bwd(const AttnParams& p, cudaStream_t s) {
   {
     const int rows = p.B * p.H * p.Lq;
-    attn_delta_kernel<T><<<(rows + 7) / 8, 256, 0, s>>>(p);
+    MRB_LAUNCH((attn_delta_kernel<T>), (rows + 7) / 8, 256, 0, s, p);
     MRB_CHECK_LAUNCH();
   }
   {
@@ -793,7 +805,7 @@ static int launch_bwd(const AttnParams& p, cudaStream_t s) {
     static bool cfg = false;
     if (!cfg) { if (int rc = set_smem(attn_bwd_dq_kernel<T, HD>, smem)) return rc; cfg = true; }
     dim3 grid((p.Lq + BQ - 1) / BQ, p.H, p.B);
-    attn_bwd_dq_kernel<T, HD><<<grid, NTHREADS, smem, s>>>(p);
+    MRB_LAUNCH((attn_bwd_dq_kernel<T, HD>), grid, NTHREADS, smem, s, p);
     MRB_CHECK_LAUNCH();
   }
   {
@@ -801,7 +813,7 @@ static int launch_bwd(const AttnParams& p, cudaStream_t s) {
     static bool cfg = false;
     if (!cfg) { if (int rc = set_smem(attn_bwd_dkv_kernel<T, HD>, smem)) return rc; cfg = true; }
     dim3 grid((p.Lk + BKV - 1) / BKV, p.H, p.B);
-    attn_bwd_dkv_kernel<T, HD><<<grid, NTHREADS, smem, s>>>(p);
+    MRB_LAUNCH((attn_bwd_dkv_kernel<T, HD>), grid, NTHREADS, smem, s, p);
     MRB_CHECK_LAUNCH();
   }
   return MRB_OK;
@@ -872,10 +884,10 @@ extern "C" int mrb_attention_row(const void* q, long long q_bs, const void* k, l
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const int blocks = (B * H + 3) / 4, smem = 4 * Lk * 4 + 4 * 128 * 4;
   if (dtype == MRB_DT_F16)
-    attn_row_kernel<__half><<<blocks, 128, smem, s>>>(static_cast<const __half*>(q), q_bs, static_cast<const __half*>(k), k_bs, k_rs,
+    MRB_LAUNCH((attn_row_kernel<__half>), blocks, 128, smem, s, static_cast<const __half*>(q), q_bs, static_cast<const __half*>(k), k_bs, k_rs,
                                                      static_cast<const __half*>(v), v_bs, v_rs, static_cast<__half*>(o), o_bs, B, H, Lk, hd, scale);
   else if (dtype == MRB_DT_BF16)
-    attn_row_kernel<__nv_bfloat16><<<blocks, 128, smem, s>>>(static_cast<const __nv_bfloat16*>(q), q_bs, static_cast<const __nv_bfloat16*>(k), k_bs, k_rs,
+    MRB_LAUNCH((attn_row_kernel<__nv_bfloat16>), blocks, 128, smem, s, static_cast<const __nv_bfloat16*>(q), q_bs, static_cast<const __nv_bfloat16*>(k), k_bs, k_rs,
                                                             static_cast<const __nv_bfloat16*>(v), v_bs, v_rs, static_cast<__nv_bfloat16*>(o), o_bs, B, H, Lk, hd, scale);
   else return MRB_ERR_ARG;
   MRB_CHECK_LAUNCH();

@@ -204,6 +204,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
                    const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmQ2,
                    const __grid_constant__ CUtensorMap tmK2, const __grid_constant__ CUtensorMap tmV2,
                    const AttnTcParams p) {
+  mrb::pdl_trigger();   // the successor may become resident and run its set-up; it blocks in its own pdl_wait()
   using S = TcSmem<HD, G>;
   constexpr bool SPLIT = S::SPLIT;
   constexpr int STAGES = S::STAGES;
@@ -240,6 +241,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_holder;
+  mrb::pdl_wait();      // set-up done; nothing above touches global memory (MRB_PDL, common.cuh)
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -543,7 +545,7 @@ static int launch_tc(const CUtensorMap* maps, const AttnTcParams& p, cudaStream_
     cfg = true;
   }
   dim3 grid((p.Lq + G * TQ - 1) / (G * TQ), p.H, p.B);
-  attn_fwd_tc_kernel<HD, G, DT><<<grid, S::THREADS, S::TOTAL, s>>>(maps[0], maps[1], maps[2], maps[3], maps[4], maps[5], p);
+  MRB_LAUNCH((attn_fwd_tc_kernel<HD, G, DT>), grid, S::THREADS, S::TOTAL, s, maps[0], maps[1], maps[2], maps[3], maps[4], maps[5], p);
   MRB_CHECK_LAUNCH();
   return MRB_OK;
 }

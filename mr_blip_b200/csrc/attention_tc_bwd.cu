@@ -138,6 +138,7 @@ template <int MODE, bool ENC>
 __global__ void __launch_bounds__(320, 1)
 attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmY,
                    const __grid_constant__ CUtensorMap tmU, const __grid_constant__ CUtensorMap tmW, const AttnBwdParams p) {
+  mrb::pdl_trigger();   // the successor may become resident and run its set-up; it blocks in its own pdl_wait()
   using S = BwdSmem;
   constexpr int STAGES = S::STAGES;
   constexpr uint32_t TMEM_COLS = 512;
@@ -176,6 +177,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_holder;
+  mrb::pdl_wait();      // set-up done; nothing above touches global memory (MRB_PDL, common.cuh)
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -415,6 +417,8 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
 // delta[b,h,i] = sum_d dO[b,i,h,d] * O[b,i,h,d]  (16-bit inputs, hd = 64: one warp per row, 2 elements per lane)
 __global__ void attn_delta64_kernel(const uint16_t* __restrict__ o, long long o_bs, long long o_rs, const uint16_t* __restrict__ d_o,
                                     long long do_bs, long long do_rs, float* __restrict__ delta, int B, int H, int Lq, int dtype) {
+  mrb::pdl_trigger();
+  mrb::pdl_wait();      // before the first global access (common.cuh, MRB_PDL)
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= B * H * Lq) return;
@@ -465,7 +469,7 @@ static int launch_bwd_tc2(const CUtensorMap& x, const CUtensorMap& y, const CUte
     cfg = true;
   }
   dim3 grid((Lstat + 2 * TS - 1) / (2 * TS), p.H, p.B);
-  attn_bwd_tc_kernel<MODE, ENC><<<grid, 320, BwdSmem::TOTAL, s>>>(x, y, u, w, p);
+  MRB_LAUNCH((attn_bwd_tc_kernel<MODE, ENC>), grid, 320, BwdSmem::TOTAL, s, x, y, u, w, p);
   MRB_CHECK_LAUNCH();
   return MRB_OK;
 }
@@ -496,7 +500,7 @@ extern "C" int mrb_attention_bwd_tc(const void* q, long long q_bs, long long q_r
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   {
     const int rows = B * H * Lq;
-    attn_delta64_kernel<<<(rows + 7) / 8, 256, 0, s>>>(static_cast<const uint16_t*>(o), o_bs, o_rs,
+    MRB_LAUNCH((attn_delta64_kernel), (rows + 7) / 8, 256, 0, s, static_cast<const uint16_t*>(o), o_bs, o_rs,
                                                          static_cast<const uint16_t*>(dout), do_bs, do_rs, delta_ws, B, H, Lq, dtype);
     MRB_CHECK_LAUNCH();
   }

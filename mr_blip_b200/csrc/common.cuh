@@ -237,6 +237,38 @@ __device__ __forceinline__ float unpack_hi(uint32_t w, int dt) {
 
 }  // namespace mrb
 
+// ---------------------------------------------------------------- programmatic dependent launch (build flag -DMRB_PDL)
+// With MRB_PDL every kernel is launched with the programmatic-stream-serialization attribute: it may become resident while
+// its predecessor in the stream is still draining, runs its set-up (barrier init, TMEM allocation, descriptor prefetch) and
+// blocks in pdl_wait() until the predecessor has completed and flushed.  Rule that makes this safe by construction: every
+// kernel executes pdl_wait() before its FIRST global-memory access (reads and writes alike), so completion is transitive
+// along the stream.  pdl_trigger() (all CTAs, at entry) is what allows the successor to be scheduled early.  Without the
+// flag both are empty and launches are ordinary <<< >>> launches: the default build is unchanged.
+namespace mrb {
+#ifdef MRB_PDL
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+template <typename... KArgs, typename... Args>
+inline void launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at; cfg.numAttrs = 1;
+  cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);     // errors surface through MRB_CHECK_LAUNCH
+}
+#else
+__device__ __forceinline__ void pdl_wait() {}
+__device__ __forceinline__ void pdl_trigger() {}
+#endif
+}  // namespace mrb
+#ifdef MRB_PDL
+#define MRB_LAUNCH(kernel, grid, block, smem, stream, ...) mrb::launch_pdl(kernel, grid, block, smem, stream, __VA_ARGS__)
+#else
+#define MRB_LAUNCH(kernel, grid, block, smem, stream, ...) kernel<<<grid, block, smem, stream>>>(__VA_ARGS__)
+#endif
+
 // host-side launch check used by every C-ABI entry point
 #define MRB_CHECK_LAUNCH()                          \
   do {                                              \

@@ -16,6 +16,8 @@ __global__ void __launch_bounds__(256) norm_kernel(const float* __restrict__ x, 
                                                    float eps, int rows, int C, int mode, float* __restrict__ out_f32,
                                                    void* __restrict__ out_h, int h_dtype, long long ld_h,
                                                    float* __restrict__ sum_out) {
+  mrb::pdl_trigger();
+  mrb::pdl_wait();      // before the first global access (common.cuh, MRB_PDL)
   const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= rows) return;
@@ -80,6 +82,8 @@ __global__ void __launch_bounds__(256) rmsnorm_bwd_kernel(const float* __restric
                                                           const void* __restrict__ dy, int dy_dtype, long long ld,
                                                           const float* __restrict__ A, int R, float eps, int rows, int C,
                                                           float* __restrict__ dres) {
+  mrb::pdl_trigger();
+  mrb::pdl_wait();      // before the first global access (common.cuh, MRB_PDL)
   const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= rows) return;
@@ -137,6 +141,8 @@ __global__ void __launch_bounds__(256) rmsnorm_bwd_kernel(const float* __restric
 //   y[m, k] = x[m, k] + sum_r x[m, K + r] * A[r, k];   in place, or accumulated into fp32 acc [M, K] when acc != null
 __global__ void __launch_bounds__(256) lora_up_add_kernel(uint16_t* __restrict__ x, long long ldx, const float* __restrict__ A,
                                                            int R, int M, int K, int dtype, float* __restrict__ acc) {
+  mrb::pdl_trigger();
+  mrb::pdl_wait();      // before the first global access (common.cuh, MRB_PDL)
   const int kv = K >> 3;
   const long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
   if (idx >= static_cast<long long>(M) * kv) return;
@@ -175,6 +181,8 @@ __global__ void __launch_bounds__(256) lora_up_add_kernel(uint16_t* __restrict__
 // order); columns [3*P*P, ldA) are zero.  One thread per (patch, c, i): P contiguous pixels.
 __global__ void patchify_kernel(const float* __restrict__ img, void* __restrict__ out, int dtype, int F, int S, int P,
                                 int ldA) {
+  mrb::pdl_trigger();
+  mrb::pdl_wait();      // before the first global access (common.cuh, MRB_PDL)
   const int G = S / P;
   const long long total = static_cast<long long>(F) * G * G * 3 * P;
   const long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
@@ -205,6 +213,8 @@ __global__ void patchify_kernel(const float* __restrict__ img, void* __restrict_
 struct NormConst { float mean[3], std[3]; };
 __global__ void patchify_u8_kernel(const uint8_t* __restrict__ img, void* __restrict__ out, int dtype, int F, int S, int P,
                                    int ldA, NormConst nc) {
+  mrb::pdl_trigger();
+  mrb::pdl_wait();      // before the first global access (common.cuh, MRB_PDL)
   const int G = S / P;
   const long long total = static_cast<long long>(F) * G * G * 3 * P;
   const long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
@@ -232,6 +242,8 @@ __global__ void patchify_u8_kernel(const uint8_t* __restrict__ img, void* __rest
 // x[f, 0, :] = cls + pos[0]   (eva_vit.py:328-331)
 __global__ void cls_pos_kernel(const float* __restrict__ cls, const float* __restrict__ pos, float* __restrict__ x,
                                int F, int tokens, int C) {
+  mrb::pdl_trigger();
+  mrb::pdl_wait();      // before the first global access (common.cuh, MRB_PDL)
   const long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
   if (idx >= static_cast<long long>(F) * C) return;
   const int c = idx % C;
@@ -243,6 +255,8 @@ __global__ void cls_pos_kernel(const float* __restrict__ cls, const float* __res
 // ab [M, 2F] half (columns [0,F) = wi_0 x, [F,2F) = wi_1 x) -> h [M, ldh] half = gelu(a) * b
 __global__ void gated_gelu_fwd_kernel(const uint4* __restrict__ ab, uint4* __restrict__ h, int M, int F, long long ldh,
                                       int dtype) {
+  mrb::pdl_trigger();
+  mrb::pdl_wait();      // before the first global access (common.cuh, MRB_PDL)
   const int fv = F >> 3;
   const long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
   if (idx >= static_cast<long long>(M) * fv) return;
@@ -260,6 +274,8 @@ __global__ void gated_gelu_fwd_kernel(const uint4* __restrict__ ab, uint4* __res
 // dab[:, :F] = dh * b * gelu'(a) ; dab[:, F:] = dh * gelu(a)
 __global__ void gated_gelu_bwd_kernel(const uint4* __restrict__ ab, const uint4* __restrict__ dh, long long lddh,
                                       uint4* __restrict__ dab, long long lddab, int M, int F, int dtype) {
+  mrb::pdl_trigger();
+  mrb::pdl_wait();      // before the first global access (common.cuh, MRB_PDL)
   const int fv = F >> 3;
   const long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
   if (idx >= static_cast<long long>(M) * fv) return;
@@ -286,6 +302,8 @@ __global__ void gated_gelu_bwd_kernel(const uint4* __restrict__ ab, const uint4*
 //                               idx == INT_MIN -> zeros (left padding)
 __global__ void gather_rows_kernel(const int* __restrict__ idx, const float* __restrict__ emb,
                                    const float* __restrict__ frames, float* __restrict__ out, int rows, int C) {
+  mrb::pdl_trigger();
+  mrb::pdl_wait();      // before the first global access (common.cuh, MRB_PDL)
   const int r = blockIdx.x;
   if (r >= rows) return;
   const int id = idx[r];
@@ -298,6 +316,8 @@ __global__ void gather_rows_kernel(const int* __restrict__ idx, const float* __r
 // backward of the gather w.r.t. the frame tokens: dframes[-(idx+1)] = dout[r]  (each frame row appears once)
 __global__ void scatter_frames_kernel(const int* __restrict__ idx, const float* __restrict__ dout,
                                       float* __restrict__ dframes, int rows, int C) {
+  mrb::pdl_trigger();
+  mrb::pdl_wait();      // before the first global access (common.cuh, MRB_PDL)
   const int r = blockIdx.x;
   if (r >= rows) return;
   const int id = idx[r];
@@ -309,6 +329,8 @@ __global__ void scatter_frames_kernel(const int* __restrict__ idx, const float* 
 
 // mean over groups of n consecutive rows (frame_token_aggregation == "mean", blip2_mr.py:493-498)
 __global__ void group_mean_kernel(const float* __restrict__ x, float* __restrict__ out, int groups, int n, int C) {
+  mrb::pdl_trigger();
+  mrb::pdl_wait();      // before the first global access (common.cuh, MRB_PDL)
   const long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
   if (idx >= static_cast<long long>(groups) * C) return;
   const int c = idx % C;
@@ -318,6 +340,8 @@ __global__ void group_mean_kernel(const float* __restrict__ x, float* __restrict
   out[idx] = s / n;
 }
 __global__ void group_mean_bwd_kernel(const float* __restrict__ dout, float* __restrict__ dx, int groups, int n, int C) {
+  mrb::pdl_trigger();
+  mrb::pdl_wait();      // before the first global access (common.cuh, MRB_PDL)
   const long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
   if (idx >= static_cast<long long>(groups) * n * C) return;
   const int c = idx % C;
@@ -332,6 +356,8 @@ __global__ void __launch_bounds__(1024) ce_kernel(const float* __restrict__ logi
                                                   int rows, int V, float* __restrict__ row_loss, void* __restrict__ dlogits,
                                                   int d_dtype, long long ldd, float gscale,
                                                   float* __restrict__ loss_sum) {
+  mrb::pdl_trigger();
+  mrb::pdl_wait();      // before the first global access (common.cuh, MRB_PDL)
   __shared__ float red[32];
   __shared__ float bval;
   const int row = blockIdx.x;
@@ -393,6 +419,8 @@ __global__ void __launch_bounds__(1024) ce_kernel(const float* __restrict__ logi
 template <int R>
 __global__ void __launch_bounds__(256) lora_down_kernel(uint16_t* __restrict__ x, long long ldx, const float* __restrict__ A,
                                                          int M, int K, int dtype) {
+  mrb::pdl_trigger();
+  mrb::pdl_wait();      // before the first global access (common.cuh, MRB_PDL)
   const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= M) return;
@@ -427,6 +455,8 @@ __global__ void __launch_bounds__(256) skinny_wgrad_kernel(const uint16_t* __res
                                                            const uint16_t* __restrict__ Q, long long ldq, int M, int C,
                                                            float* __restrict__ out, int transposed_out, int dtype,
                                                            int rows_per_block) {
+  mrb::pdl_trigger();
+  mrb::pdl_wait();      // before the first global access (common.cuh, MRB_PDL)
   // thread = (column group of 8 columns, row slice); block = 256 columns x rows_per_block rows.
   // Row slices are combined with shared-memory atomics (layout [i][r][cg]: conflict-free), then one global atomic
   // per output element and block.
@@ -479,6 +509,8 @@ __global__ void __launch_bounds__(256) skinny_wgrad_kernel(const uint16_t* __res
 __global__ void __launch_bounds__(256) skinny_wgrad_small_kernel(const uint16_t* __restrict__ P, long long ldp,
                                                                  const uint16_t* __restrict__ Q, long long ldq, int M, int C,
                                                                  float* __restrict__ out, int transposed_out, int dtype) {
+  mrb::pdl_trigger();
+  mrb::pdl_wait();      // before the first global access (common.cuh, MRB_PDL)
   __shared__ float red[8][64 * 8 + 8];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int c = blockIdx.x * 64 + lane * 2;
@@ -533,6 +565,8 @@ struct LoraPackDesc {
   double scale;
 };
 __global__ void __launch_bounds__(256) lora_pack_kernel(const LoraPackDesc* __restrict__ descs, int dtype) {
+  mrb::pdl_trigger();
+  mrb::pdl_wait();      // before the first global access (common.cuh, MRB_PDL)
   const LoraPackDesc d = descs[blockIdx.x];
   const float s = static_cast<float>(d.scale);
   for (long long i = blockIdx.y * 256 + threadIdx.x; i < max(d.K, d.N); i += static_cast<long long>(gridDim.y) * 256) {
@@ -562,6 +596,8 @@ __global__ void __launch_bounds__(256) lora_pack_kernel(const LoraPackDesc* __re
 __global__ void __launch_bounds__(256) small_down_kernel(const uint16_t* __restrict__ x, long long ldx,
                                                          const uint16_t* __restrict__ W, long long ldw, int K,
                                                          uint16_t* __restrict__ out, long long ldo, int dtype) {
+  mrb::pdl_trigger();
+  mrb::pdl_wait();      // before the first global access (common.cuh, MRB_PDL)
   __shared__ float red[8][32];
   const int m = blockIdx.x;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -598,6 +634,8 @@ __global__ void __launch_bounds__(256) small_down_kernel(const uint16_t* __restr
 
 // ---------------------------------------------------------------- casts / transpose / column sums
 __global__ void cast_f32_to_h_kernel(const float4* __restrict__ in, uint2* __restrict__ out, long long n4, int dtype) {
+  mrb::pdl_trigger();
+  mrb::pdl_wait();      // before the first global access (common.cuh, MRB_PDL)
   const long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
   if (i >= n4) return;
   const float4 v = in[i];
@@ -606,6 +644,8 @@ __global__ void cast_f32_to_h_kernel(const float4* __restrict__ in, uint2* __res
 // 2D strided cast: out[r, c] = in[r, c] for c < cols (ld_in / ld_out element strides)
 __global__ void cast2d_f32_to_h_kernel(const float* __restrict__ in, long long ld_in, uint16_t* __restrict__ out,
                                        long long ld_out, int rows, int cols, int dtype) {
+  mrb::pdl_trigger();
+  mrb::pdl_wait();      // before the first global access (common.cuh, MRB_PDL)
   const long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
   const int cv = cols >> 1;
   if (idx >= static_cast<long long>(rows) * cv) return;
@@ -617,6 +657,8 @@ __global__ void cast2d_f32_to_h_kernel(const float* __restrict__ in, long long l
 // out[c, r] = in[r, c]  (16-bit elements), 32x32 tiles through shared memory
 __global__ void transpose16_kernel(const uint16_t* __restrict__ in, long long ld_in, uint16_t* __restrict__ out,
                                    long long ld_out, int rows, int cols) {
+  mrb::pdl_trigger();
+  mrb::pdl_wait();      // before the first global access (common.cuh, MRB_PDL)
   __shared__ uint16_t tile[32][34];
   const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
   for (int i = threadIdx.y; i < 32; i += blockDim.y) {
@@ -631,6 +673,8 @@ __global__ void transpose16_kernel(const uint16_t* __restrict__ in, long long ld
 }
 // out[c] (+)= sum_r in[r, c]   (fp32), used for the t5_proj bias gradient
 __global__ void colsum_kernel(const float* __restrict__ in, int rows, int C, float* __restrict__ out, int rows_per_block) {
+  mrb::pdl_trigger();
+  mrb::pdl_wait();      // before the first global access (common.cuh, MRB_PDL)
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
   const int r0 = blockIdx.y * rows_per_block, r1 = min(rows, r0 + rows_per_block);
@@ -640,6 +684,8 @@ __global__ void colsum_kernel(const float* __restrict__ in, int rows, int C, flo
 }
 // y = a*x + b*y over fp32 vectors (grad accumulation / residual sums on the flat streams)
 __global__ void axpby_kernel(const float4* __restrict__ x, float4* __restrict__ y, long long n4, float a, float b) {
+  mrb::pdl_trigger();
+  mrb::pdl_wait();      // before the first global access (common.cuh, MRB_PDL)
   const long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
   if (i >= n4) return;
   const float4 xv = x[i];
@@ -659,9 +705,9 @@ extern "C" int mrb_norm(const float* x, const float* add, const float* w, const 
   if (rows <= 0) return MRB_OK;
   if ((C & 3) || C > 2048 || (out_h && (ld_h & 3))) return MRB_ERR_ARG;
   const unsigned grid = blocks_for(rows, 8);
-  if (C <= 1024) norm_kernel<8><<<grid, 256, 0, STREAM>>>(x, add, w, bias, eps, rows, C, mode, out_f32, out_h, h_dtype, ld_h, sum_out);
-  else if (C <= 1536) norm_kernel<12><<<grid, 256, 0, STREAM>>>(x, add, w, bias, eps, rows, C, mode, out_f32, out_h, h_dtype, ld_h, sum_out);
-  else norm_kernel<16><<<grid, 256, 0, STREAM>>>(x, add, w, bias, eps, rows, C, mode, out_f32, out_h, h_dtype, ld_h, sum_out);
+  if (C <= 1024) MRB_LAUNCH((norm_kernel<8>), grid, 256, 0, STREAM, x, add, w, bias, eps, rows, C, mode, out_f32, out_h, h_dtype, ld_h, sum_out);
+  else if (C <= 1536) MRB_LAUNCH((norm_kernel<12>), grid, 256, 0, STREAM, x, add, w, bias, eps, rows, C, mode, out_f32, out_h, h_dtype, ld_h, sum_out);
+  else MRB_LAUNCH((norm_kernel<16>), grid, 256, 0, STREAM, x, add, w, bias, eps, rows, C, mode, out_f32, out_h, h_dtype, ld_h, sum_out);
   MRB_CHECK_LAUNCH();
   return MRB_OK;
 }
@@ -670,7 +716,7 @@ extern "C" int mrb_rmsnorm_bwd(const float* x, const float* w, const void* dy, i
                                const float* lora_A, int R, float eps, int rows, int C, float* dres, void* stream) {
   if (rows <= 0) return MRB_OK;
   if ((C & 3) || C > 2048 || (ld_dy & 3) || R > 32 || (lora_A && dy_dtype == MRB_DT_F32)) return MRB_ERR_ARG;
-  rmsnorm_bwd_kernel<16><<<blocks_for(rows, 8), 256, 0, STREAM>>>(x, w, dy, dy_dtype, ld_dy, lora_A, R, eps, rows, C, dres);
+  MRB_LAUNCH((rmsnorm_bwd_kernel<16>), blocks_for(rows, 8), 256, 0, STREAM, x, w, dy, dy_dtype, ld_dy, lora_A, R, eps, rows, C, dres);
   MRB_CHECK_LAUNCH();
   return MRB_OK;
 }
@@ -679,7 +725,7 @@ extern "C" int mrb_lora_up_add(void* x_ext, long long ldx, const float* A, int R
                                void* stream) {
   if (M <= 0) return MRB_OK;
   if ((K & 7) || (ldx & 7) || (R & 1) || R > 32) return MRB_ERR_ARG;
-  lora_up_add_kernel<<<blocks_for(static_cast<long long>(M) * (K >> 3), 256), 256, 0, STREAM>>>(
+  MRB_LAUNCH((lora_up_add_kernel), blocks_for(static_cast<long long>(M) * (K >> 3), 256), 256, 0, STREAM, 
       static_cast<uint16_t*>(x_ext), ldx, A, R, M, K, dtype, acc);
   MRB_CHECK_LAUNCH();
   return MRB_OK;
@@ -690,7 +736,7 @@ extern "C" int mrb_patchify(const float* img, void* out, int dtype, int frames, 
   if (img_size % patch || (patch & 1) || ldA < 3 * patch * patch || (ldA & 7)) return MRB_ERR_ARG;
   const int G = img_size / patch;
   const long long total = static_cast<long long>(frames) * G * G * 3 * patch;
-  patchify_kernel<<<blocks_for(total, 256), 256, 0, STREAM>>>(img, out, dtype, frames, img_size, patch, ldA);
+  MRB_LAUNCH((patchify_kernel), blocks_for(total, 256), 256, 0, STREAM, img, out, dtype, frames, img_size, patch, ldA);
   MRB_CHECK_LAUNCH();
   return MRB_OK;
 }
@@ -703,14 +749,14 @@ extern "C" int mrb_patchify_u8(const unsigned char* img, void* out, int dtype, i
   const int G = img_size / patch;
   const long long total = static_cast<long long>(frames) * G * G * 3 * patch;
   NormConst nc{{mean0, mean1, mean2}, {std0, std1, std2}};
-  patchify_u8_kernel<<<blocks_for(total, 256), 256, 0, STREAM>>>(img, out, dtype, frames, img_size, patch, ldA, nc);
+  MRB_LAUNCH((patchify_u8_kernel), blocks_for(total, 256), 256, 0, STREAM, img, out, dtype, frames, img_size, patch, ldA, nc);
   MRB_CHECK_LAUNCH();
   return MRB_OK;
 }
 
 extern "C" int mrb_cls_pos(const float* cls, const float* pos, float* x, int frames, int tokens, int C, void* stream) {
   if (frames <= 0) return MRB_OK;
-  cls_pos_kernel<<<blocks_for(static_cast<long long>(frames) * C, 256), 256, 0, STREAM>>>(cls, pos, x, frames, tokens, C);
+  MRB_LAUNCH((cls_pos_kernel), blocks_for(static_cast<long long>(frames) * C, 256), 256, 0, STREAM, cls, pos, x, frames, tokens, C);
   MRB_CHECK_LAUNCH();
   return MRB_OK;
 }
@@ -718,7 +764,7 @@ extern "C" int mrb_cls_pos(const float* cls, const float* pos, float* x, int fra
 extern "C" int mrb_gated_gelu_fwd(const void* ab, void* h, int M, int F, long long ldh, int dtype, void* stream) {
   if (M <= 0) return MRB_OK;
   if ((F & 7) || (ldh & 7)) return MRB_ERR_ARG;
-  gated_gelu_fwd_kernel<<<blocks_for(static_cast<long long>(M) * (F >> 3), 256), 256, 0, STREAM>>>(
+  MRB_LAUNCH((gated_gelu_fwd_kernel), blocks_for(static_cast<long long>(M) * (F >> 3), 256), 256, 0, STREAM, 
       static_cast<const uint4*>(ab), static_cast<uint4*>(h), M, F, ldh, dtype);
   MRB_CHECK_LAUNCH();
   return MRB_OK;
@@ -727,7 +773,7 @@ extern "C" int mrb_gated_gelu_bwd(const void* ab, const void* dh, long long lddh
                                   int dtype, void* stream) {
   if (M <= 0) return MRB_OK;
   if ((F & 7) || (lddh & 7) || (lddab & 7) || lddab < 2 * F) return MRB_ERR_ARG;
-  gated_gelu_bwd_kernel<<<blocks_for(static_cast<long long>(M) * (F >> 3), 256), 256, 0, STREAM>>>(
+  MRB_LAUNCH((gated_gelu_bwd_kernel), blocks_for(static_cast<long long>(M) * (F >> 3), 256), 256, 0, STREAM, 
       static_cast<const uint4*>(ab), static_cast<const uint4*>(dh), lddh, static_cast<uint4*>(dab), lddab, M, F, dtype);
   MRB_CHECK_LAUNCH();
   return MRB_OK;
@@ -736,26 +782,26 @@ extern "C" int mrb_gated_gelu_bwd(const void* ab, const void* dh, long long lddh
 extern "C" int mrb_gather_rows(const int* idx, const float* emb, const float* frames, float* out, int rows, int C, void* stream) {
   if (rows <= 0) return MRB_OK;
   if (C & 3) return MRB_ERR_ARG;
-  gather_rows_kernel<<<rows, 256, 0, STREAM>>>(idx, emb, frames, out, rows, C);
+  MRB_LAUNCH((gather_rows_kernel), rows, 256, 0, STREAM, idx, emb, frames, out, rows, C);
   MRB_CHECK_LAUNCH();
   return MRB_OK;
 }
 extern "C" int mrb_scatter_frames(const int* idx, const float* dout, float* dframes, int rows, int C, void* stream) {
   if (rows <= 0) return MRB_OK;
   if (C & 3) return MRB_ERR_ARG;
-  scatter_frames_kernel<<<rows, 256, 0, STREAM>>>(idx, dout, dframes, rows, C);
+  MRB_LAUNCH((scatter_frames_kernel), rows, 256, 0, STREAM, idx, dout, dframes, rows, C);
   MRB_CHECK_LAUNCH();
   return MRB_OK;
 }
 extern "C" int mrb_group_mean(const float* x, float* out, int groups, int n, int C, void* stream) {
   if (groups <= 0) return MRB_OK;
-  group_mean_kernel<<<blocks_for(static_cast<long long>(groups) * C, 256), 256, 0, STREAM>>>(x, out, groups, n, C);
+  MRB_LAUNCH((group_mean_kernel), blocks_for(static_cast<long long>(groups) * C, 256), 256, 0, STREAM, x, out, groups, n, C);
   MRB_CHECK_LAUNCH();
   return MRB_OK;
 }
 extern "C" int mrb_group_mean_bwd(const float* dout, float* dx, int groups, int n, int C, void* stream) {
   if (groups <= 0) return MRB_OK;
-  group_mean_bwd_kernel<<<blocks_for(static_cast<long long>(groups) * n * C, 256), 256, 0, STREAM>>>(dout, dx, groups, n, C);
+  MRB_LAUNCH((group_mean_bwd_kernel), blocks_for(static_cast<long long>(groups) * n * C, 256), 256, 0, STREAM, dout, dx, groups, n, C);
   MRB_CHECK_LAUNCH();
   return MRB_OK;
 }
@@ -764,7 +810,7 @@ extern "C" int mrb_cross_entropy(const float* logits, const long long* labels, i
                                  void* dlogits, int d_dtype, long long ldd, float gscale, float* loss_sum, void* stream) {
   if (rows <= 0) return MRB_OK;
   if (dlogits && (ldd & 1)) return MRB_ERR_ARG;
-  ce_kernel<<<rows, 1024, 0, STREAM>>>(logits, labels, rows, V, row_loss, dlogits, d_dtype, ldd, gscale, loss_sum);
+  MRB_LAUNCH((ce_kernel), rows, 1024, 0, STREAM, logits, labels, rows, V, row_loss, dlogits, d_dtype, ldd, gscale, loss_sum);
   MRB_CHECK_LAUNCH();
   return MRB_OK;
 }
@@ -775,9 +821,9 @@ extern "C" int mrb_lora_down(void* x_ext, long long ldx, const float* A, int M, 
   const unsigned grid = blocks_for(M, 8);
   uint16_t* x = static_cast<uint16_t*>(x_ext);
   switch (R) {
-    case 8: lora_down_kernel<8><<<grid, 256, 0, STREAM>>>(x, ldx, A, M, K, dtype); break;
-    case 16: lora_down_kernel<16><<<grid, 256, 0, STREAM>>>(x, ldx, A, M, K, dtype); break;
-    case 24: lora_down_kernel<24><<<grid, 256, 0, STREAM>>>(x, ldx, A, M, K, dtype); break;
+    case 8: MRB_LAUNCH((lora_down_kernel<8>), grid, 256, 0, STREAM, x, ldx, A, M, K, dtype); break;
+    case 16: MRB_LAUNCH((lora_down_kernel<16>), grid, 256, 0, STREAM, x, ldx, A, M, K, dtype); break;
+    case 24: MRB_LAUNCH((lora_down_kernel<24>), grid, 256, 0, STREAM, x, ldx, A, M, K, dtype); break;
     default: return MRB_ERR_UNSUPPORTED;
   }
   MRB_CHECK_LAUNCH();
@@ -789,7 +835,7 @@ extern "C" int mrb_skinny_wgrad(const void* P, long long ldp, const void* Q, lon
   if (M <= 0 || C <= 0) return MRB_OK;
   if ((ldq & 7) || (ldp & 7) || (C & 7) || (reinterpret_cast<uintptr_t>(P) & 15) || (reinterpret_cast<uintptr_t>(Q) & 15)) return MRB_ERR_ARG;
   if (M <= 256) {
-    skinny_wgrad_small_kernel<<<blocks_for(C, 64), 256, 0, STREAM>>>(static_cast<const uint16_t*>(P), ldp,
+    MRB_LAUNCH((skinny_wgrad_small_kernel), blocks_for(C, 64), 256, 0, STREAM, static_cast<const uint16_t*>(P), ldp,
                                                                     static_cast<const uint16_t*>(Q), ldq, M, C, out,
                                                                     transposed_out, dtype);
     MRB_CHECK_LAUNCH();
@@ -797,7 +843,7 @@ extern "C" int mrb_skinny_wgrad(const void* P, long long ldp, const void* Q, lon
   }
   const int rows_per_block = 256;
   dim3 grid(blocks_for(C, 256), blocks_for(M, rows_per_block));
-  skinny_wgrad_kernel<<<grid, 256, 0, STREAM>>>(static_cast<const uint16_t*>(P), ldp, static_cast<const uint16_t*>(Q), ldq,
+  MRB_LAUNCH((skinny_wgrad_kernel), grid, 256, 0, STREAM, static_cast<const uint16_t*>(P), ldp, static_cast<const uint16_t*>(Q), ldq,
                                                 M, C, out, transposed_out, dtype, rows_per_block);
   MRB_CHECK_LAUNCH();
   return MRB_OK;
@@ -806,7 +852,7 @@ extern "C" int mrb_skinny_wgrad(const void* P, long long ldp, const void* Q, lon
 extern "C" int mrb_lora_pack(const void* descs, int n, int blocks_per_linear, int dtype, void* stream) {
   if (n <= 0) return MRB_OK;
   if (blocks_per_linear <= 0 || (dtype != MRB_DT_F16 && dtype != MRB_DT_BF16)) return MRB_ERR_ARG;
-  lora_pack_kernel<<<dim3(n, blocks_per_linear), 256, 0, STREAM>>>(static_cast<const LoraPackDesc*>(descs), dtype);
+  MRB_LAUNCH((lora_pack_kernel), dim3(n, blocks_per_linear), 256, 0, STREAM, static_cast<const LoraPackDesc*>(descs), dtype);
   MRB_CHECK_LAUNCH();
   return MRB_OK;
 }
@@ -815,7 +861,7 @@ extern "C" int mrb_small_down(const void* x, long long ldx, const void* W, long 
                               long long ldo, int dtype, void* stream) {
   if (M <= 0) return MRB_OK;
   if ((K & 7) || (ldx & 7) || (ldw & 7)) return MRB_ERR_ARG;
-  small_down_kernel<<<M, 256, 0, STREAM>>>(static_cast<const uint16_t*>(x), ldx, static_cast<const uint16_t*>(W), ldw, K,
+  MRB_LAUNCH((small_down_kernel), M, 256, 0, STREAM, static_cast<const uint16_t*>(x), ldx, static_cast<const uint16_t*>(W), ldw, K,
                                            static_cast<uint16_t*>(out), ldo, dtype);
   MRB_CHECK_LAUNCH();
   return MRB_OK;
@@ -824,7 +870,7 @@ extern "C" int mrb_small_down(const void* x, long long ldx, const void* W, long 
 extern "C" int mrb_cast_f32_to_h(const float* in, void* out, long long n, int dtype, void* stream) {
   if (n <= 0) return MRB_OK;
   if (n & 3) return MRB_ERR_ARG;
-  cast_f32_to_h_kernel<<<blocks_for(n >> 2, 256), 256, 0, STREAM>>>(reinterpret_cast<const float4*>(in),
+  MRB_LAUNCH((cast_f32_to_h_kernel), blocks_for(n >> 2, 256), 256, 0, STREAM, reinterpret_cast<const float4*>(in),
                                                                     static_cast<uint2*>(out), n >> 2, dtype);
   MRB_CHECK_LAUNCH();
   return MRB_OK;
@@ -833,7 +879,7 @@ extern "C" int mrb_cast2d_f32_to_h(const float* in, long long ld_in, void* out, 
                                    int dtype, void* stream) {
   if (rows <= 0 || cols <= 0) return MRB_OK;
   if ((cols & 1) || (ld_in & 1) || (ld_out & 1)) return MRB_ERR_ARG;
-  cast2d_f32_to_h_kernel<<<blocks_for(static_cast<long long>(rows) * (cols >> 1), 256), 256, 0, STREAM>>>(
+  MRB_LAUNCH((cast2d_f32_to_h_kernel), blocks_for(static_cast<long long>(rows) * (cols >> 1), 256), 256, 0, STREAM, 
       in, ld_in, static_cast<uint16_t*>(out), ld_out, rows, cols, dtype);
   MRB_CHECK_LAUNCH();
   return MRB_OK;
@@ -841,21 +887,21 @@ extern "C" int mrb_cast2d_f32_to_h(const float* in, long long ld_in, void* out, 
 extern "C" int mrb_transpose16(const void* in, long long ld_in, void* out, long long ld_out, int rows, int cols, void* stream) {
   if (rows <= 0 || cols <= 0) return MRB_OK;
   dim3 grid(blocks_for(cols, 32), blocks_for(rows, 32)), block(32, 8);
-  transpose16_kernel<<<grid, block, 0, STREAM>>>(static_cast<const uint16_t*>(in), ld_in, static_cast<uint16_t*>(out), ld_out, rows, cols);
+  MRB_LAUNCH((transpose16_kernel), grid, block, 0, STREAM, static_cast<const uint16_t*>(in), ld_in, static_cast<uint16_t*>(out), ld_out, rows, cols);
   MRB_CHECK_LAUNCH();
   return MRB_OK;
 }
 extern "C" int mrb_colsum(const float* in, int rows, int C, float* out, void* stream) {
   if (rows <= 0) return MRB_OK;
   dim3 grid(blocks_for(C, 256), blocks_for(rows, 256));
-  colsum_kernel<<<grid, 256, 0, STREAM>>>(in, rows, C, out, 256);
+  MRB_LAUNCH((colsum_kernel), grid, 256, 0, STREAM, in, rows, C, out, 256);
   MRB_CHECK_LAUNCH();
   return MRB_OK;
 }
 extern "C" int mrb_axpby(const float* x, float* y, long long n, float a, float b, void* stream) {
   if (n <= 0) return MRB_OK;
   if (n & 3) return MRB_ERR_ARG;
-  axpby_kernel<<<blocks_for(n >> 2, 256), 256, 0, STREAM>>>(reinterpret_cast<const float4*>(x), reinterpret_cast<float4*>(y), n >> 2, a, b);
+  MRB_LAUNCH((axpby_kernel), blocks_for(n >> 2, 256), 256, 0, STREAM, reinterpret_cast<const float4*>(x), reinterpret_cast<float4*>(y), n >> 2, a, b);
   MRB_CHECK_LAUNCH();
   return MRB_OK;
 }

@@ -74,6 +74,7 @@ __device__ __forceinline__ void split_coords(const GemmParams& p, int k_blocks, 
 template <int BN, int STAGES, bool SPLIT = false>
 __global__ void __launch_bounds__(320, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
+  mrb::pdl_trigger();   // the successor may become resident and run its set-up; it blocks in its own pdl_wait()
   using S = GemmSmem<BN, STAGES>;
   constexpr uint32_t TMEM_COLS = (2 * BN <= 256) ? 256 : 512;
   extern __shared__ uint8_t smem_raw[];
@@ -107,6 +108,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_holder;
+  mrb::pdl_wait();      // set-up done; nothing above touches global memory (MRB_PDL, common.cuh)
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -329,7 +331,7 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, GemmParam
   p.n_tiles = (p.N + BN - 1) / BN;
   const int tiles = p.m_tiles * p.n_tiles * (SPLIT ? p.splits : 1);
   const int grid = tiles < g_num_sms ? tiles : g_num_sms;
-  gemm_tcgen05_kernel<BN, STAGES, SPLIT><<<grid, 320, S::TOTAL, stream>>>(tmA, tmB, p);
+  MRB_LAUNCH((gemm_tcgen05_kernel<BN, STAGES, SPLIT>), grid, 320, S::TOTAL, stream, tmA, tmB, p);
   MRB_CHECK_LAUNCH();
   return MRB_OK;
 }
@@ -340,6 +342,8 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, GemmParam
 __global__ void __launch_bounds__(256)
 splitk_reduce_kernel(const float* __restrict__ ws, int splits, long long split_stride, int M, int N, const float* __restrict__ bias,
                      int gelu, const float* resid, long long ldr, void* out, int out_dtype, long long ldc) {
+  mrb::pdl_trigger();
+  mrb::pdl_wait();      // before the first global access (common.cuh, MRB_PDL)
   const int n4 = N >> 2;
   const long long total = static_cast<long long>(M) * n4;
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
@@ -499,7 +503,7 @@ static int gemm_impl(const void* A, long long lda, const void* B, long long ldb,
     const long long quads = static_cast<long long>(M) * (N >> 2);
     long long blocks = (quads + 255) / 256;
     if (blocks > 4LL * g_num_sms) blocks = 4LL * g_num_sms;
-    splitk_reduce_kernel<<<static_cast<int>(blocks), 256, 0, s>>>(static_cast<const float*>(ws), plan.splits, p.split_stride, M, N,
+    MRB_LAUNCH((splitk_reduce_kernel), static_cast<int>(blocks), 256, 0, s, static_cast<const float*>(ws), plan.splits, p.split_stride, M, N,
                                                                   bias, gelu, resid, ldr, out, out_dtype, ldc);
     MRB_CHECK_LAUNCH();
     return MRB_OK;

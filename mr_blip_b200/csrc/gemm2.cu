@@ -121,6 +121,7 @@ enum { EPI_GENERIC = 0, EPI_F16 = 1, EPI_GELU_F16 = 2, EPI_BF16 = 3, EPI_RESID_F
 template <int EPI>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(320, 1)
 gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const Gemm2Params p) {
+  mrb::pdl_trigger();   // the successor may become resident and run its set-up; it blocks in its own pdl_wait()
   constexpr uint32_t TMEM_COLS = 512;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -155,6 +156,7 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
   cluster_sync_all();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_holder;
+  mrb::pdl_wait();      // set-up done; nothing above touches global memory (MRB_PDL, common.cuh)
 
   if (warp == 0) {
     // ===================== TMA producer (both CTAs) =====================
@@ -366,7 +368,7 @@ static int launch2(const CUtensorMap* tmA, const CUtensorMap* tmB, const Gemm2Pa
     if (e != cudaSuccess) return mrb_set_error(e);
     configured = true;
   }
-  gemm2_tcgen05_kernel<EPI><<<2 * pairs, 320, G2_SMEM, st>>>(*tmA, *tmB, p);
+  MRB_LAUNCH((gemm2_tcgen05_kernel<EPI>), 2 * pairs, 320, G2_SMEM, st, *tmA, *tmB, p);
   MRB_CHECK_LAUNCH();
   return MRB_OK;
 }

@@ -34,6 +34,7 @@ __device__ __forceinline__ uint64_t wg_desc(uint32_t addr, uint32_t lbo, uint32_
 
 __global__ void __launch_bounds__(192, 1)
 wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constant__ CUtensorMap tmQ, const WgradParams p) {
+  mrb::pdl_trigger();   // the successor may become resident and run its set-up; it blocks in its own pdl_wait()
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + WG_STAGES * WG_STAGE);
@@ -58,6 +59,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constant__
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_holder;
+  mrb::pdl_wait();      // set-up done; nothing above touches global memory (MRB_PDL, common.cuh)
 
   if (warp == 0) {
     if (lane == 0) {
@@ -199,7 +201,7 @@ extern "C" int mrb_skinny_wgrad_tc2(const void* P, long long ldp, const void* Q,
   p.rows_per_cta = ((k_blocks + splits - 1) / splits) * WG_BK;
   p.out = out; p.out2 = out2; p.transposed_out = transposed_out; p.dtype = dtype;
   dim3 grid(c_tiles, (M + p.rows_per_cta - 1) / p.rows_per_cta);
-  wgrad_tc_kernel<<<grid, 192, WG_SMEM, static_cast<cudaStream_t>(stream)>>>(tmP, tmQ, p);
+  MRB_LAUNCH((wgrad_tc_kernel), grid, 192, WG_SMEM, static_cast<cudaStream_t>(stream), tmP, tmQ, p);
   MRB_CHECK_LAUNCH();
   return MRB_OK;
 }

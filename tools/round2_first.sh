@@ -21,3 +21,10 @@ cut -c1-200 $O/bench.json $O/bench_splitk.json
 # what bounds the operand feed of one SM (decides: 64-row A boxes? multicast? more CTAs per problem?)
 ( nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -o /tmp/tma_feed_probe tools/probe/tma_feed_probe.cu -lcuda 2>&1 | grep -v deprecated; timeout 120 /tmp/tma_feed_probe ) > $O/tma_feed_probe.log 2>&1
 tail -45 $O/tma_feed_probe.log
+# programmatic dependent launch (build flag -DMRB_PDL: second library, default build untouched): the whole GPU suite and the
+# bench line on the variant.  Adopt (make it the default build) only if the suite is green and the step gets shorter.
+( python -m mr_blip_b200.build --variant _pdl -DMRB_PDL 2>&1 | tail -1 ) > $O/build_pdl.log 2>&1
+( MRB_LIB_VARIANT=_pdl timeout 500 python -m pytest tests -m gpu -q 2>&1 | tail -15 ) > $O/pytest_pdl.log 2>&1
+tail -3 $O/pytest_pdl.log
+( MRB_LIB_VARIANT=_pdl timeout 400 python bench.py --steps 8 --warmup 3 ) > $O/bench_pdl.json 2> $O/bench_pdl.err
+cut -c1-200 $O/bench_pdl.json
