@@ -39,12 +39,12 @@ def time_values(fmt, timestamps, durations, table):
     return ts, ds
 
 
-def frame_tokens(sd, d, video, frame_token_aggregation=None):
+def frame_tokens(sd, d, video, frame_token_aggregation=None, drop=None):
     """blip2_mr.py:443-510: ViT -> ln_vision -> Q-Former -> t5_proj (-> mean) -> [b, t*n, c]."""
     b, t = video.shape[:2]
     image = video.reshape(-1, *video.shape[2:])
     image_embeds = _vit.ln_vision(sd, d, _vit.vit_forward(sd, d, image))
-    q = _qf.qformer_forward(sd, d, image_embeds)
+    q = _qf.qformer_forward(sd, d, image_embeds, drop=drop)
     f = torch.nn.functional.linear(q, sd["t5_proj.weight"], sd["t5_proj.bias"])
     if frame_token_aggregation:
         f = f.mean(dim=1, keepdim=True)
@@ -93,9 +93,11 @@ def prompt_concatenation(sd, d, tok, timestamps, durations, frames_for_t5, video
 
 
 def forward_mr(sd, d, tok, samples, frame_token_aggregation=None, table=None, max_txt_len=200,
-               input_time_format="seconds_integers"):
-    """blip2_mr.py:433-570 -> dict(loss, logits, inputs_embeds, attention_mask, labels, ...)."""
-    f, aux = frame_tokens(sd, d, samples["video"], frame_token_aggregation)
+               input_time_format="seconds_integers", drop=None):
+    """blip2_mr.py:433-570 -> dict(loss, logits, inputs_embeds, attention_mask, labels, ...).  drop: None = eval mode, a
+    Dropper (oracle/dropout.py) = the train-mode dropout of the Q-Former, T5 and LoRA inputs (the ViT stays in eval mode:
+    blip2_mr.py:136-137)."""
+    f, aux = frame_tokens(sd, d, samples["video"], frame_token_aggregation, drop=drop)
     n = 1 if frame_token_aggregation else d.num_query
     inputs, atts = prompt_concatenation(sd, d, tok, samples["timestamps"], samples["duration"], f,
                                         samples["video_prompt_end"], samples["query_prompt"],
@@ -103,7 +105,7 @@ def forward_mr(sd, d, tok, samples, frame_token_aggregation=None, table=None, ma
     ans = tok(samples["relevant_windows"], padding="longest", truncation=True, max_length=max_txt_len,
               return_tensors="pt")
     labels = ans.input_ids.masked_fill(ans.input_ids == tok.pad_token_id, -100)
-    out = _t5.t5_forward(sd, d, inputs, atts, labels, ans.attention_mask)
+    out = _t5.t5_forward(sd, d, inputs, atts, labels, ans.attention_mask, drop=drop)
     out.update(inputs_embeds=inputs, attention_mask=atts, labels=labels, frames_for_t5=f, **aux)
     return out
 

@@ -317,3 +317,70 @@ def test_train_crop_matches_reference_transform(golden_dir):
         torch.manual_seed(seed)
         again = data.random_resized_crop(clip.to(torch.uint8), size, scale=(s0 / 1000.0, s1 / 1000.0))     # uint8 frames in, as decoded
         assert torch.equal(again, got)
+
+
+def test_train_mode_dropout_placement(tiny_sd, golden_dir):
+    """The reference's Q-Former and T5 run in .train() after torch.manual_seed (tests/golden/make_golden_train_mode.py); the oracle
+    with torch's own dropout at ITS sites consumes the same RNG stream, so it reproduces those outputs only if every mask sits
+    where the reference's nn.Dropout calls sit (same tensors, same shapes, same order)."""
+    import importlib.util
+    from oracle.dropout import Dropper
+    spec = importlib.util.spec_from_file_location("make_golden_train_mode", os.path.join(golden_dir, "make_golden_train_mode.py"))
+    src = open(spec.origin).read()
+    ns = {}
+    exec(src[src.index("def inputs(d):"):src.index("def main():")], {"torch": torch}, ns)     # the seeded inputs, not the reference
+    image_embeds, emb, mask, labels = ns["inputs"](TINY)
+    gold = np.load(os.path.join(golden_dir, "train_mode_tiny.npz"))
+    nthreads = torch.get_num_threads()
+    torch.set_num_threads(1)
+    try:
+        drop = Dropper(seed=0, lora=0.0, torch_rng=True)
+        with torch.no_grad():
+            torch.manual_seed(int(gold["rng_seed"]))
+            q = oqf.qformer_forward(tiny_sd, TINY, image_embeds, drop=drop)
+            torch.manual_seed(int(gold["rng_seed"]))
+            out = ot5.t5_forward(tiny_sd, TINY, emb, mask, labels, (labels != -100).long(), drop=drop)
+    finally:
+        torch.set_num_threads(nthreads)
+    np.testing.assert_allclose(_np(q), gold["qformer_out"], rtol=1e-3, atol=1e-4)
+    assert abs(out["loss"].item() - float(gold["loss"])) < 1e-3
+    np.testing.assert_allclose(_np(torch.logsumexp(out["logits"], -1)), gold["logits_lse"], rtol=1e-3, atol=1e-3)
+    np.testing.assert_allclose(_np(out["logits"][:, :, :64]), gold["logits_head"], rtol=1e-3, atol=2e-3)
+    np.testing.assert_allclose(_np(out["encoder_last_hidden_state"][:, ::4, ::8]), gold["enc_out"], rtol=1e-3, atol=1e-3)
+    # and the eval-mode outputs differ from these by far more than the tolerance (the test can fail)
+    with torch.no_grad():
+        ev = ot5.t5_forward(tiny_sd, TINY, emb, mask, labels, (labels != -100).long())
+    assert abs(ev["loss"].item() - float(gold["loss"])) > 1e-2
+
+
+def test_counter_hash_masks_statistics_and_determinism():
+    """oracle/dropout.py: keep rate = 1 - round(256 p) / 256, E[drop(x)] = x, independent sites / seeds / rows, p = 0 identity."""
+    from oracle import dropout as od
+    for p in (0.1, 0.05):
+        m = od.keep_mask(7, od.site(od.ENC, 3, od.SELF_P), 2048, 2037, p)
+        want = 1.0 - od.thr_of(p) / 256.0
+        assert abs(m.mean() - want) < 5e-4, (p, m.mean(), want)
+        assert abs(m.mean(axis=0) - want).max() < 0.05 and abs(m.mean(axis=1) - want).max() < 0.05
+        assert abs(float(od.scale_of(p)) * want - 1.0) < 1e-6
+    a = od.draws(7, od.site(od.ENC, 0, od.FF_RES), 64, 2048)
+    assert (a == od.draws(7, od.site(od.ENC, 0, od.FF_RES), 64, 2048)).all()
+    for other in (od.draws(8, od.site(od.ENC, 0, od.FF_RES), 64, 2048), od.draws(7, od.site(od.ENC, 1, od.FF_RES), 64, 2048),
+                  od.draws(7, od.site(od.DEC, 0, od.FF_RES), 64, 2048)):
+        c = np.corrcoef(a.ravel().astype(np.float64), other.ravel().astype(np.float64))[0, 1]
+        assert abs(c) < 0.02, c
+    c = np.corrcoef(a[:-1].ravel().astype(np.float64), a[1:].ravel().astype(np.float64))[0, 1]
+    assert abs(c) < 0.02
+    assert len(np.unique(a)) == 256
+    x = torch.randn(5, 3, 44)
+    d = od.Dropper(seed=3)
+    assert d(x, 5, 0.0) is x
+    y = d(x, 5, 0.1)
+    keep = torch.from_numpy(od.keep_mask(3, 5, 15, 44, 0.1)).view(5, 3, 44)
+    assert torch.equal(y != 0, keep & (x != 0)) and torch.allclose(y[keep], x[keep] * float(od.scale_of(0.1)))
+    sites = {od.lora_site(f"t5_model.base_model.model.{s}.block.{i}.layer.{l}.{n}")
+             for s in ("encoder", "decoder") for i in range(24)
+             for l, n in ((0, "SelfAttention.q"), (0, "SelfAttention.k"), (0, "SelfAttention.v"), (0, "SelfAttention.o"),
+                          (1, "EncDecAttention.q"), (1, "EncDecAttention.k"), (1, "EncDecAttention.v"), (1, "EncDecAttention.o"),
+                          (2, "DenseReluDense.wi_0"), (2, "DenseReluDense.wi_1"), (2, "DenseReluDense.wo"))}
+    sites.add(od.lora_site("t5_model.base_model.model.lm_head"))
+    assert len(sites) == 2 * 24 * 11 + 1
