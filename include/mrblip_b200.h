@@ -148,6 +148,62 @@ int mrb_transpose16(const void* in, long long ld_in, void* out, long long ld_out
 int mrb_colsum(const float* in, int rows, int C, float* out, void* stream);
 int mrb_axpby(const float* x, float* y, long long n, float a, float b, void* stream);
 
+/* ---- train-mode dropout (csrc/dropmask.cuh, csrc/dropout.cu) ----------------------------------------------------------------
+ * The reference applies nn.Dropout in train() inside the frozen Q-Former (0.1: Qformer.py:107,258,287,373), T5 (0.1:
+ * modeling_t5.py:327,346,600,652,690,1149,1258) and on every LoRA input (0.05: blip2_mr.py:197).  Masks here are a pure function
+ * keep(seed, site, row, column) (counter hash, four 8-bit draws per 32-bit word; p quantised to 1/256, kept values scaled by
+ * 256 / (256 - round(256 p))): forward and backward kernels and the CPU oracle evaluate the same function, nothing is stored.
+ * `seed` points to ONE device word the host rewrites before every step (a replayed CUDA graph then draws fresh masks);
+ * `site` identifies the dropout call within the step; rows / columns index the 2-D operand the site masks. */
+/* out = drop(x):  (dtype, out_dtype) in {(f32, f32), (f32, 16-bit), (16-bit, same)}; cols % 4 == 0; out may alias x */
+int mrb_dropout(const void* x, long long ldx, void* out, long long ldo, int rows, int cols, int dtype, int out_dtype,
+                const unsigned* seed, unsigned site, float p, void* stream);
+/* out = resid + drop(branch), fp32 [rows, cols] contiguous: hidden + dropout(sublayer) (modeling_t5.py:346,652,690) */
+int mrb_dropout_add(const float* resid, const float* branch, float* out, int rows, int cols, const unsigned* seed,
+                    unsigned site, float p, void* stream);
+/* mrb_gated_gelu_fwd / _bwd with the FF-inner dropout (modeling_t5.py:327): h = drop(gelu(a) * b) */
+int mrb_gated_gelu_fwd_drop(const void* ab, void* h, int M, int F, long long ldh, int dtype, const unsigned* seed,
+                            unsigned site, float p, void* stream);
+int mrb_gated_gelu_bwd_drop(const void* ab, const void* dh, long long lddh, void* dab, long long lddab, int M, int F,
+                            int dtype, const unsigned* seed, unsigned site, float p, void* stream);
+/* peft lora.Linear in train mode, y = W x + B A drop_j(x) with an independent mask per adapted Linear j (site0 + j) of a group
+ * of nlin <= 3 Linears sharing the input x:
+ *   out[m, 8j + r] = scale * sum_k keep_j(m, k) x[m, k] A[8j + r, k]      (out: 32 16-bit columns, zeros from 8 nlin on)
+ *   dA[r, k]      += scale * sum_m keep(m, k) x[m, k] q[m, r]              (q = dy sB_j, 16-bit [M, 8])
+ *   dx[m, k]      += scale * sum_j keep_j(m, k) sum_r q[m, 8j + r] A[8j + r, k]   (dx 16-bit or fp32, read-modify-write) */
+int mrb_lora_down_drop(const void* x, long long ldx, const void* A, long long lda, int M, int K, int nlin, void* out,
+                       long long ldo, int dtype, const unsigned* seed, unsigned site0, float p, void* stream);
+int mrb_lora_wgrad_drop(const void* x, long long ldx, const void* q, long long ldq, int M, int K, float* dA, int dtype,
+                        const unsigned* seed, unsigned site, float p, void* stream);
+int mrb_lora_dx_drop(const void* q, long long ldq, const void* A, long long lda, int nlin, void* dx, long long lddx,
+                     int dx_dtype, int M, int K, int dtype, const unsigned* seed, unsigned site0, float p, void* stream);
+/* Attention with train-mode dropout of the probabilities (modeling_t5.py:600, Qformer.py:258): the contracts of
+ * mrb_attention_fwd / _fwd_tc / _bwd / _bwd_tc plus (seed, site, p); O = drop(softmax(S)) V, lse is that of the undropped scores,
+ * the backward recomputes the mask (row = (b H + h) Lq + i, column = key).  hd <= 64; the tcgen05 versions need bf16 (forward)
+ * and an even round(256 p). */
+int mrb_attention_fwd_drop(const void* q, long long q_bs, long long q_rs, const void* k, long long k_bs, long long k_rs,
+                           const void* v, long long v_bs, long long v_rs, void* o, long long o_bs, long long o_rs,
+                           int B, int H, int Lq, int Lk, int hd, int dtype, float scale, const float* bias,
+                           int bias_len, int bias_zero, const int* kmask, int kv_div, int causal, int q_pos0, float* lse,
+                           const unsigned* seed, unsigned site, float p, void* stream);
+int mrb_attention_fwd_tc_drop(const void* q, long long q_bs, long long q_rs, const void* k, long long k_bs, long long k_rs,
+                              const void* v, long long v_bs, long long v_rs, void* o, long long o_bs, long long o_rs,
+                              int B, int H, int Lq, int Lk, int hd, int dtype, float scale, const float* bias,
+                              int bias_len, int bias_zero, const int* kmask, int kv_div, int causal, int q_pos0, float* lse,
+                              const unsigned* seed, unsigned site, float p, void* stream);
+int mrb_attention_bwd_drop(const void* q, long long q_bs, long long q_rs, const void* k, long long k_bs, long long k_rs,
+                           const void* v, long long v_bs, long long v_rs, const void* o, long long o_bs, long long o_rs,
+                           const void* dout, long long do_bs, long long do_rs, void* dq, void* dk, void* dv,
+                           int B, int H, int Lq, int Lk, int hd, int dtype, float scale, const float* bias,
+                           int bias_len, int bias_zero, const int* kmask, int causal, int q_pos0, const float* lse,
+                           float* delta_ws, const unsigned* seed, unsigned site, float p, void* stream);
+int mrb_attention_bwd_tc_drop(const void* q, long long q_bs, long long q_rs, const void* k, long long k_bs, long long k_rs,
+                              const void* v, long long v_bs, long long v_rs, const void* o, long long o_bs, long long o_rs,
+                              const void* dout, long long do_bs, long long do_rs, void* dq, void* dk, void* dv,
+                              int B, int H, int Lq, int Lk, int hd, int dtype, float scale, const float* bias,
+                              int bias_len, int bias_zero, const int* kmask, int causal, int q_pos0, const float* lse,
+                              float* delta_ws, const unsigned* seed, unsigned site, float p, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

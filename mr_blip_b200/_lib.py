@@ -6,7 +6,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libmrblip_b200%s.so" % os.environ.get("MRB_LIB_VARIANT", ""))   # variants: A/B builds (build.py)
 
-_p, _ll, _i, _f = ctypes.c_void_p, ctypes.c_longlong, ctypes.c_int, ctypes.c_float
+_p, _ll, _i, _f, _u = ctypes.c_void_p, ctypes.c_longlong, ctypes.c_int, ctypes.c_float, ctypes.c_uint
 
 # name -> argument ctypes, in header order (must match include/mrblip_b200.h)
 SIGNATURES = {
@@ -46,11 +46,26 @@ SIGNATURES = {
     "mrb_transpose16": [_p, _ll, _p, _ll, _i, _i, _p],
     "mrb_colsum": [_p, _i, _i, _p, _p],
     "mrb_axpby": [_p, _p, _ll, _f, _f, _p],
+    "mrb_attention_fwd_drop": [_p, _ll, _ll, _p, _ll, _ll, _p, _ll, _ll, _p, _ll, _ll, _i, _i, _i, _i, _i, _i, _f, _p, _i, _i,
+                               _p, _i, _i, _i, _p, _p, _u, _f, _p],
+    "mrb_attention_fwd_tc_drop": [_p, _ll, _ll, _p, _ll, _ll, _p, _ll, _ll, _p, _ll, _ll, _i, _i, _i, _i, _i, _i, _f, _p, _i, _i,
+                               _p, _i, _i, _i, _p, _p, _u, _f, _p],
+    "mrb_attention_bwd_drop": [_p, _ll, _ll, _p, _ll, _ll, _p, _ll, _ll, _p, _ll, _ll, _p, _ll, _ll, _p, _p, _p,
+                               _i, _i, _i, _i, _i, _i, _f, _p, _i, _i, _p, _i, _i, _p, _p, _p, _u, _f, _p],
+    "mrb_attention_bwd_tc_drop": [_p, _ll, _ll, _p, _ll, _ll, _p, _ll, _ll, _p, _ll, _ll, _p, _ll, _ll, _p, _p, _p,
+                               _i, _i, _i, _i, _i, _i, _f, _p, _i, _i, _p, _i, _i, _p, _p, _p, _u, _f, _p],
+    "mrb_dropout": [_p, _ll, _p, _ll, _i, _i, _i, _i, _p, _u, _f, _p],
+    "mrb_dropout_add": [_p, _p, _p, _i, _i, _p, _u, _f, _p],
+    "mrb_gated_gelu_fwd_drop": [_p, _p, _i, _i, _ll, _i, _p, _u, _f, _p],
+    "mrb_gated_gelu_bwd_drop": [_p, _p, _ll, _p, _ll, _i, _i, _i, _p, _u, _f, _p],
+    "mrb_lora_down_drop": [_p, _ll, _p, _ll, _i, _i, _i, _p, _ll, _i, _p, _u, _f, _p],
+    "mrb_lora_wgrad_drop": [_p, _ll, _p, _ll, _i, _i, _p, _i, _p, _u, _f, _p],
+    "mrb_lora_dx_drop": [_p, _ll, _p, _ll, _i, _p, _ll, _i, _i, _i, _i, _p, _u, _f, _p],
 }
 
 _lib = None
 launch_count = 0     # kernels launched through the C ABI so far (bench.py reports the delta as gpu_launches)
-_KERNELS_PER_CALL = {"mrb_attention_bwd": 3, "mrb_attention_bwd_tc": 3}
+_KERNELS_PER_CALL = {"mrb_attention_bwd": 3, "mrb_attention_bwd_tc": 3, "mrb_attention_bwd_drop": 3, "mrb_attention_bwd_tc_drop": 3}
 
 
 class MrbError(RuntimeError):

@@ -5,6 +5,7 @@
 // Scores never touch HBM.  This first version drives the tensor cores through mma.sync m16n8k16
 // (HMMA); the tcgen05 port of the long-sequence T5 case is tracked in DESIGN.md.
 #include "common.cuh"
+#include "dropmask.cuh"
 
 namespace mrb {
 
@@ -25,6 +26,14 @@ struct AttnParams {
   const float* delta;       // [B, H, Lq] rowsum(dO * O)
   void* dq; void* dk; void* dv;   // same layout/strides as q/k/v
 };
+// DROP instantiations only: train-mode dropout of the attention probabilities (modeling_t5.py:600, Qformer.py:258); masks of
+// dropmask.cuh with row = (b H + h) Lq + i, column = key j.  O = (m s P) V with s = 1 / (1 - p) folded into the final 1 / l;
+// backward: dV = s (m P)^T dO, dS = P * (s m dP - delta) * scale.
+struct AttnDropParams : AttnParams {
+  const uint32_t* drop_seed; uint32_t drop_site, drop_thr; float drop_scale;
+};
+template <bool DROP> struct AttnParamsOf { typedef AttnParams type; };
+template <> struct AttnParamsOf<true> { typedef AttnDropParams type; };
 
 constexpr int BQ = 64, BKV = 64, NTHREADS = 128;
 
@@ -83,8 +92,8 @@ struct ScoreCtx {
   }
 };
 
-template <typename T, int HD>
-__global__ void __launch_bounds__(NTHREADS) attn_fwd_kernel(const AttnParams p) {
+template <typename T, int HD, bool DROP = false>
+__global__ void __launch_bounds__(NTHREADS) attn_fwd_kernel(const typename AttnParamsOf<DROP>::type p) {
   mrb::pdl_trigger();
   mrb::pdl_wait();      // before the first global access (common.cuh, MRB_PDL)
   constexpr int LDS = HD + 8;
@@ -114,6 +123,16 @@ __global__ void __launch_bounds__(NTHREADS) attn_fwd_kernel(const AttnParams p) 
   float m_run[2] = {-INFINITY, -INFINITY}, l_run[2] = {0.f, 0.f};
   uint32_t qf[HD / 16][4];
   const float LOG2E = 1.4426950408889634f;
+  uint32_t dkey = 0, drow[2] = {0u, 0u}, dthr = 0;
+  float dscale = 1.f;
+  if constexpr (DROP) {
+    dkey = drop_key(*p.drop_seed, p.drop_site);
+    dthr = p.drop_thr; dscale = p.drop_scale;
+#pragma unroll
+    for (int r = 0; r < 2; ++r)
+      drow[r] = (static_cast<uint32_t>(b * p.H + h) * static_cast<uint32_t>(p.Lq) +
+                 static_cast<uint32_t>(min(q0 + warp * 16 + g + 8 * r, p.Lq - 1))) * drop_groups(static_cast<uint32_t>(p.Lk));
+  }
 
   for (int kv = 0; kv < n_kv; ++kv) {
     const int buf = kv & 1;
@@ -180,6 +199,13 @@ __global__ void __launch_bounds__(NTHREADS) attn_fwd_kernel(const AttnParams p) 
       const float p2 = exp2f(s[nb][2] * LOG2E - msc[1]), p3 = exp2f(s[nb][3] * LOG2E - msc[1]);
       l_run[0] += p0 + p1;
       l_run[1] += p2 + p3;
+      if constexpr (DROP) {                      // the row sums stay those of the undropped P
+        const int j = kv * BKV + nb * 8 + 2 * t4;
+        const uint32_t w0 = drop_word(dkey, drow[0], j >> 2), w1 = drop_word(dkey, drow[1], j >> 2);
+        pf[nb >> 1][(nb & 1) * 2] = MmaType<T>::pack(drop_keep(w0, j, dthr) ? p0 : 0.f, drop_keep(w0, j + 1, dthr) ? p1 : 0.f);
+        pf[nb >> 1][(nb & 1) * 2 + 1] = MmaType<T>::pack(drop_keep(w1, j, dthr) ? p2 : 0.f, drop_keep(w1, j + 1, dthr) ? p3 : 0.f);
+        continue;
+      }
       pf[nb >> 1][(nb & 1) * 2] = MmaType<T>::pack(p0, p1);
       pf[nb >> 1][(nb & 1) * 2 + 1] = MmaType<T>::pack(p2, p3);
     }
@@ -212,7 +238,7 @@ __global__ void __launch_bounds__(NTHREADS) attn_fwd_kernel(const AttnParams p) 
   for (int r = 0; r < 2; ++r) {
     const int i = q0 + warp * 16 + g + r * 8;
     if (i >= p.Lq) continue;
-    const float inv = l_run[r] > 0.f ? 1.f / l_run[r] : 0.f;
+    const float inv = (l_run[r] > 0.f ? 1.f / l_run[r] : 0.f) * dscale;
 #pragma unroll
     for (int nb = 0; nb < HD / 8; ++nb) {
       const int c = nb * 8 + 2 * t4;
@@ -429,8 +455,8 @@ __global__ void attn_delta_kernel(const AttnParams p) {
 }
 
 // dQ = scale * sum_j dS_ij K_j   with dS = P * (dO V^T - delta).  One CTA per 64 query rows.
-template <typename T, int HD>
-__global__ void __launch_bounds__(NTHREADS) attn_bwd_dq_kernel(const AttnParams p) {
+template <typename T, int HD, bool DROP = false>
+__global__ void __launch_bounds__(NTHREADS) attn_bwd_dq_kernel(const typename AttnParamsOf<DROP>::type p) {
   mrb::pdl_trigger();
   mrb::pdl_wait();      // before the first global access (common.cuh, MRB_PDL)
   constexpr int LDS = HD + 8;
@@ -468,6 +494,16 @@ __global__ void __launch_bounds__(NTHREADS) attn_bwd_dq_kernel(const AttnParams 
 #pragma unroll
   for (int i = 0; i < HD / 8; ++i) dq_acc[i][0] = dq_acc[i][1] = dq_acc[i][2] = dq_acc[i][3] = 0.f;
   uint32_t qf[HD / 16][4], dof[HD / 16][4];
+  uint32_t dkey = 0, drow[2] = {0u, 0u}, dthr = 0;
+  float dscale = 1.f;
+  if constexpr (DROP) {
+    dkey = drop_key(*p.drop_seed, p.drop_site);
+    dthr = p.drop_thr; dscale = p.drop_scale;
+#pragma unroll
+    for (int r = 0; r < 2; ++r)
+      drow[r] = (static_cast<uint32_t>(b * p.H + h) * static_cast<uint32_t>(p.Lq) +
+                 static_cast<uint32_t>(min(q0 + warp * 16 + g + 8 * r, p.Lq - 1))) * drop_groups(static_cast<uint32_t>(p.Lk));
+  }
 
   for (int kv = 0; kv < n_kv; ++kv) {
     const int buf = kv & 1;
@@ -520,7 +556,9 @@ __global__ void __launch_bounds__(NTHREADS) attn_bwd_dq_kernel(const AttnParams 
         const int r = e >> 1;
         const float sv = sc.apply(s[nb][e], i0 + r * 8, j + (e & 1));
         const float pr = (sv == -INFINITY) ? 0.f : __expf(sv - lse[r]);
-        ds[e] = pr * (dp[nb][e] - dl[r]) * p.scale;
+        float dpe = dp[nb][e];
+        if constexpr (DROP) dpe = drop_keep(drop_word(dkey, drow[r], j >> 2), j + (e & 1), dthr) ? dpe * dscale : 0.f;
+        ds[e] = pr * (dpe - dl[r]) * p.scale;
       }
       dsf[nb >> 1][(nb & 1) * 2] = MmaType<T>::pack(ds[0], ds[1]);
       dsf[nb >> 1][(nb & 1) * 2 + 1] = MmaType<T>::pack(ds[2], ds[3]);
@@ -555,8 +593,8 @@ __global__ void __launch_bounds__(NTHREADS) attn_bwd_dq_kernel(const AttnParams 
 
 // dK_j = scale * sum_i dS_ij Q_i,  dV_j = sum_i P_ij dO_i.  One CTA per 64 keys; works on the transposed
 // problem (keys are the MMA M dimension) so P^T / dS^T fragments feed the second MMAs directly.
-template <typename T, int HD>
-__global__ void __launch_bounds__(NTHREADS) attn_bwd_dkv_kernel(const AttnParams p) {
+template <typename T, int HD, bool DROP = false>
+__global__ void __launch_bounds__(NTHREADS) attn_bwd_dkv_kernel(const typename AttnParamsOf<DROP>::type p) {
   mrb::pdl_trigger();
   mrb::pdl_wait();      // before the first global access (common.cuh, MRB_PDL)
   constexpr int LDS = HD + 8;
@@ -601,6 +639,14 @@ __global__ void __launch_bounds__(NTHREADS) attn_bwd_dkv_kernel(const AttnParams
     dv_acc[i][0] = dv_acc[i][1] = dv_acc[i][2] = dv_acc[i][3] = 0.f;
   }
   uint32_t kf_a[HD / 16][4], vf_a[HD / 16][4];
+  uint32_t dkey = 0, dhead = 0, dng = 0, dthr = 0;
+  float dscale = 1.f;
+  if constexpr (DROP) {
+    dkey = drop_key(*p.drop_seed, p.drop_site);
+    dthr = p.drop_thr; dscale = p.drop_scale;
+    dhead = static_cast<uint32_t>(b * p.H + h) * static_cast<uint32_t>(p.Lq);
+    dng = drop_groups(static_cast<uint32_t>(p.Lk));
+  }
 
   for (int qt = q_begin; qt < n_q; ++qt) {
     const int buf = (qt - q_begin) & 1;
@@ -654,7 +700,14 @@ __global__ void __launch_bounds__(NTHREADS) attn_bwd_dkv_kernel(const AttnParams
         const int j = j0 + (e >> 1) * 8;
         const float sv = (i < p.Lq) ? sc.apply(st[nb][e], i, j) : -INFINITY;
         pr[e] = (sv == -INFINITY) ? 0.f : __expf(sv - sLse[buf * BQ + il]);
-        ds[e] = pr[e] * (dpt[nb][e] - sDl[buf * BQ + il]) * p.scale;
+        float dpe = dpt[nb][e];
+        bool keep = true;
+        if constexpr (DROP) {
+          keep = drop_keep(drop_word(dkey, (dhead + static_cast<uint32_t>(min(i, p.Lq - 1))) * dng, static_cast<uint32_t>(j) >> 2), j, dthr);
+          dpe = keep ? dpe * dscale : 0.f;
+        }
+        ds[e] = pr[e] * (dpe - sDl[buf * BQ + il]) * p.scale;
+        if constexpr (DROP) pr[e] = keep ? pr[e] : 0.f;      // P^T operand of dV: dropped; 1 / (1 - p) is applied to dV at the end
       }
       ptf[nb >> 1][(nb & 1) * 2] = MmaType<T>::pack(pr[0], pr[1]);
       ptf[nb >> 1][(nb & 1) * 2 + 1] = MmaType<T>::pack(pr[2], pr[3]);
@@ -689,7 +742,8 @@ __global__ void __launch_bounds__(NTHREADS) attn_bwd_dkv_kernel(const AttnParams
       const int c = nb * 8 + 2 * t4;
       if (c < p.hd) {
         *reinterpret_cast<uint32_t*>(gdk + static_cast<long long>(j) * p.k_rs + c) = MmaType<T>::pack(dk_acc[nb][2 * r], dk_acc[nb][2 * r + 1]);
-        *reinterpret_cast<uint32_t*>(gdv + static_cast<long long>(j) * p.v_rs + c) = MmaType<T>::pack(dv_acc[nb][2 * r], dv_acc[nb][2 * r + 1]);
+        *reinterpret_cast<uint32_t*>(gdv + static_cast<long long>(j) * p.v_rs + c) =
+            MmaType<T>::pack(dv_acc[nb][2 * r] * dscale, dv_acc[nb][2 * r + 1] * dscale);
       }
     }
   }
@@ -771,13 +825,13 @@ static int set_smem(K kernel, int bytes) {
   return e == cudaSuccess ? MRB_OK : mrb_set_error(e);
 }
 
-template <typename T, int HD>
-static int launch_fwd(const AttnParams& p, cudaStream_t s) {
+template <typename T, int HD, bool DROP = false>
+static int launch_fwd(const typename AttnParamsOf<DROP>::type& p, cudaStream_t s) {
   const int smem = (BQ + 4 * BKV) * (HD + 8) * 2;
   static bool cfg = false;
-  if (!cfg) { if (int rc = set_smem(attn_fwd_kernel<T, HD>, smem)) return rc; cfg = true; }
+  if (!cfg) { if (int rc = set_smem(attn_fwd_kernel<T, HD, DROP>, smem)) return rc; cfg = true; }
   dim3 grid((p.Lq + BQ - 1) / BQ, p.H, p.B);
-  MRB_LAUNCH((attn_fwd_kernel<T, HD>), grid, NTHREADS, smem, s, p);
+  MRB_LAUNCH((attn_fwd_kernel<T, HD, DROP>), grid, NTHREADS, smem, s, p);
   MRB_CHECK_LAUNCH();
   return MRB_OK;
 }
@@ -793,27 +847,27 @@ static int launch_xq(const AttnParams& p, cudaStream_t s) {
   return MRB_OK;
 }
 
-template <typename T, int HD>
-static int launch_bwd(const AttnParams& p, cudaStream_t s) {
+template <typename T, int HD, bool DROP = false>
+static int launch_bwd(const typename AttnParamsOf<DROP>::type& p, cudaStream_t s) {
   {
     const int rows = p.B * p.H * p.Lq;
-    MRB_LAUNCH((attn_delta_kernel<T>), (rows + 7) / 8, 256, 0, s, p);
+    MRB_LAUNCH((attn_delta_kernel<T>), (rows + 7) / 8, 256, 0, s, static_cast<const AttnParams&>(p));
     MRB_CHECK_LAUNCH();
   }
   {
     const int smem = (2 * BQ + 4 * BKV) * (HD + 8) * 2;
     static bool cfg = false;
-    if (!cfg) { if (int rc = set_smem(attn_bwd_dq_kernel<T, HD>, smem)) return rc; cfg = true; }
+    if (!cfg) { if (int rc = set_smem(attn_bwd_dq_kernel<T, HD, DROP>, smem)) return rc; cfg = true; }
     dim3 grid((p.Lq + BQ - 1) / BQ, p.H, p.B);
-    MRB_LAUNCH((attn_bwd_dq_kernel<T, HD>), grid, NTHREADS, smem, s, p);
+    MRB_LAUNCH((attn_bwd_dq_kernel<T, HD, DROP>), grid, NTHREADS, smem, s, p);
     MRB_CHECK_LAUNCH();
   }
   {
     const int smem = (2 * BKV + 4 * BQ) * (HD + 8) * 2 + 4 * BQ * 4;
     static bool cfg = false;
-    if (!cfg) { if (int rc = set_smem(attn_bwd_dkv_kernel<T, HD>, smem)) return rc; cfg = true; }
+    if (!cfg) { if (int rc = set_smem(attn_bwd_dkv_kernel<T, HD, DROP>, smem)) return rc; cfg = true; }
     dim3 grid((p.Lk + BKV - 1) / BKV, p.H, p.B);
-    MRB_LAUNCH((attn_bwd_dkv_kernel<T, HD>), grid, NTHREADS, smem, s, p);
+    MRB_LAUNCH((attn_bwd_dkv_kernel<T, HD, DROP>), grid, NTHREADS, smem, s, p);
     MRB_CHECK_LAUNCH();
   }
   return MRB_OK;
@@ -830,13 +884,13 @@ static int check_attn(const AttnParams& p, int dtype) {
   return MRB_OK;
 }
 
-extern "C" int mrb_attention_fwd(const void* q, long long q_bs, long long q_rs, const void* k, long long k_bs, long long k_rs,
-                                 const void* v, long long v_bs, long long v_rs, void* o, long long o_bs, long long o_rs,
-                                 int B, int H, int Lq, int Lk, int hd, int dtype, float scale, const float* bias,
-                                 int bias_len, int bias_zero, const int* kmask, int kv_div, int causal, int q_pos0, float* lse,
-                                 void* stream) {
+static int attention_fwd_impl(const void* q, long long q_bs, long long q_rs, const void* k, long long k_bs, long long k_rs,
+                              const void* v, long long v_bs, long long v_rs, void* o, long long o_bs, long long o_rs,
+                              int B, int H, int Lq, int Lk, int hd, int dtype, float scale, const float* bias,
+                              int bias_len, int bias_zero, const int* kmask, int kv_div, int causal, int q_pos0, float* lse,
+                              const unsigned* drop_seed, unsigned drop_site, float drop_p, void* stream) {
   if (B <= 0 || H <= 0 || Lq <= 0 || Lk <= 0) return MRB_OK;
-  AttnParams p{};
+  AttnDropParams p{};
   p.q = q; p.k = k; p.v = v; p.o = o;
   p.q_bs = q_bs; p.q_rs = q_rs; p.k_bs = k_bs; p.k_rs = k_rs; p.v_bs = v_bs; p.v_rs = v_rs; p.o_bs = o_bs; p.o_rs = o_rs;
   p.B = B; p.H = H; p.Lq = Lq; p.Lk = Lk; p.hd = hd; p.scale = scale;
@@ -844,6 +898,12 @@ extern "C" int mrb_attention_fwd(const void* q, long long q_bs, long long q_rs, 
   p.lse = lse;
   if (int rc = check_attn(p, dtype)) return rc;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (drop_seed && drop_p > 0.f) {
+    if (hd > 64 || drop_p >= 1.f) return MRB_ERR_UNSUPPORTED;
+    const DropSpec d = make_drop(drop_seed, drop_site, drop_p);
+    p.drop_seed = d.seed; p.drop_site = d.site; p.drop_thr = d.thr; p.drop_scale = d.scale;
+    return dtype == MRB_DT_F16 ? launch_fwd<__half, 64, true>(p, s) : launch_fwd<__nv_bfloat16, 64, true>(p, s);
+  }
   // few queries x a few hundred keys, no bias / mask (Q-Former cross-attention): one-shot K/V fetch, keys split over the warps
   static int use_xq = -1;                 // MRB_ATTN_XQ=0 keeps the generic kernel (A/B measurements)
   if (use_xq < 0) { const char* e = getenv("MRB_ATTN_XQ"); use_xq = (e && e[0] == '0') ? 0 : 1; }
@@ -854,14 +914,33 @@ extern "C" int mrb_attention_fwd(const void* q, long long q_bs, long long q_rs, 
   return hd <= 64 ? launch_fwd<__nv_bfloat16, 64>(p, s) : launch_fwd<__nv_bfloat16, 96>(p, s);
 }
 
-extern "C" int mrb_attention_bwd(const void* q, long long q_bs, long long q_rs, const void* k, long long k_bs, long long k_rs,
-                                 const void* v, long long v_bs, long long v_rs, const void* o, long long o_bs, long long o_rs,
-                                 const void* dout, long long do_bs, long long do_rs, void* dq, void* dk, void* dv,
+extern "C" int mrb_attention_fwd(const void* q, long long q_bs, long long q_rs, const void* k, long long k_bs, long long k_rs,
+                                 const void* v, long long v_bs, long long v_rs, void* o, long long o_bs, long long o_rs,
                                  int B, int H, int Lq, int Lk, int hd, int dtype, float scale, const float* bias,
-                                 int bias_len, int bias_zero, const int* kmask, int causal, int q_pos0, const float* lse,
-                                 float* delta_ws, void* stream) {
+                                 int bias_len, int bias_zero, const int* kmask, int kv_div, int causal, int q_pos0, float* lse,
+                                 void* stream) {
+  return attention_fwd_impl(q, q_bs, q_rs, k, k_bs, k_rs, v, v_bs, v_rs, o, o_bs, o_rs, B, H, Lq, Lk, hd, dtype, scale, bias, bias_len,
+                            bias_zero, kmask, kv_div, causal, q_pos0, lse, nullptr, 0u, 0.f, stream);
+}
+// mrb_attention_fwd with train-mode dropout of the attention probabilities (hd <= 64): O = drop(softmax(S)) V, lse unchanged
+extern "C" int mrb_attention_fwd_drop(const void* q, long long q_bs, long long q_rs, const void* k, long long k_bs, long long k_rs,
+                                      const void* v, long long v_bs, long long v_rs, void* o, long long o_bs, long long o_rs,
+                                      int B, int H, int Lq, int Lk, int hd, int dtype, float scale, const float* bias,
+                                      int bias_len, int bias_zero, const int* kmask, int kv_div, int causal, int q_pos0, float* lse,
+                                      const unsigned* seed, unsigned site, float p, void* stream) {
+  if (!seed) return MRB_ERR_ARG;
+  return attention_fwd_impl(q, q_bs, q_rs, k, k_bs, k_rs, v, v_bs, v_rs, o, o_bs, o_rs, B, H, Lq, Lk, hd, dtype, scale, bias, bias_len,
+                            bias_zero, kmask, kv_div, causal, q_pos0, lse, seed, site, p, stream);
+}
+
+static int attention_bwd_impl(const void* q, long long q_bs, long long q_rs, const void* k, long long k_bs, long long k_rs,
+                              const void* v, long long v_bs, long long v_rs, const void* o, long long o_bs, long long o_rs,
+                              const void* dout, long long do_bs, long long do_rs, void* dq, void* dk, void* dv,
+                              int B, int H, int Lq, int Lk, int hd, int dtype, float scale, const float* bias,
+                              int bias_len, int bias_zero, const int* kmask, int causal, int q_pos0, const float* lse,
+                              float* delta_ws, const unsigned* drop_seed, unsigned drop_site, float drop_p, void* stream) {
   if (B <= 0 || H <= 0 || Lq <= 0 || Lk <= 0) return MRB_OK;
-  AttnParams p{};
+  AttnDropParams p{};
   p.q = q; p.k = k; p.v = v; p.o = const_cast<void*>(o);
   p.q_bs = q_bs; p.q_rs = q_rs; p.k_bs = k_bs; p.k_rs = k_rs; p.v_bs = v_bs; p.v_rs = v_rs; p.o_bs = o_bs; p.o_rs = o_rs;
   p.B = B; p.H = H; p.Lq = Lq; p.Lk = Lk; p.hd = hd; p.scale = scale;
@@ -871,8 +950,35 @@ extern "C" int mrb_attention_bwd(const void* q, long long q_bs, long long q_rs, 
   if (int rc = check_attn(p, dtype)) return rc;
   if (hd > 64 || ((do_bs | do_rs) & 7)) return MRB_ERR_UNSUPPORTED;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (drop_seed && drop_p > 0.f) {
+    if (drop_p >= 1.f) return MRB_ERR_UNSUPPORTED;
+    const DropSpec d = make_drop(drop_seed, drop_site, drop_p);
+    p.drop_seed = d.seed; p.drop_site = d.site; p.drop_thr = d.thr; p.drop_scale = d.scale;
+    return dtype == MRB_DT_F16 ? launch_bwd<__half, 64, true>(p, s) : launch_bwd<__nv_bfloat16, 64, true>(p, s);
+  }
   if (dtype == MRB_DT_F16) return launch_bwd<__half, 64>(p, s);
   return launch_bwd<__nv_bfloat16, 64>(p, s);
+}
+
+extern "C" int mrb_attention_bwd(const void* q, long long q_bs, long long q_rs, const void* k, long long k_bs, long long k_rs,
+                                 const void* v, long long v_bs, long long v_rs, const void* o, long long o_bs, long long o_rs,
+                                 const void* dout, long long do_bs, long long do_rs, void* dq, void* dk, void* dv,
+                                 int B, int H, int Lq, int Lk, int hd, int dtype, float scale, const float* bias,
+                                 int bias_len, int bias_zero, const int* kmask, int causal, int q_pos0, const float* lse,
+                                 float* delta_ws, void* stream) {
+  return attention_bwd_impl(q, q_bs, q_rs, k, k_bs, k_rs, v, v_bs, v_rs, o, o_bs, o_rs, dout, do_bs, do_rs, dq, dk, dv, B, H, Lq, Lk, hd, dtype,
+                            scale, bias, bias_len, bias_zero, kmask, causal, q_pos0, lse, delta_ws, nullptr, 0u, 0.f, stream);
+}
+// Backward of mrb_attention_fwd_drop (same seed word, site and p: the mask is recomputed)
+extern "C" int mrb_attention_bwd_drop(const void* q, long long q_bs, long long q_rs, const void* k, long long k_bs, long long k_rs,
+                                      const void* v, long long v_bs, long long v_rs, const void* o, long long o_bs, long long o_rs,
+                                      const void* dout, long long do_bs, long long do_rs, void* dq, void* dk, void* dv,
+                                      int B, int H, int Lq, int Lk, int hd, int dtype, float scale, const float* bias,
+                                      int bias_len, int bias_zero, const int* kmask, int causal, int q_pos0, const float* lse,
+                                      float* delta_ws, const unsigned* seed, unsigned site, float p, void* stream) {
+  if (!seed) return MRB_ERR_ARG;
+  return attention_bwd_impl(q, q_bs, q_rs, k, k_bs, k_rs, v, v_bs, v_rs, o, o_bs, o_rs, dout, do_bs, do_rs, dq, dk, dv, B, H, Lq, Lk, hd, dtype,
+                            scale, bias, bias_len, bias_zero, kmask, causal, q_pos0, lse, delta_ws, seed, site, p, stream);
 }
 
 // One query row per (batch, head): q/o point at that row of batch 0 (batch strides apply).  No bias / mask.

@@ -13,6 +13,7 @@
 // Measured limits (profiles/): per (128 x 128) tile the softmax side costs 64 KB of tcgen05.ld (TMEM read port 64 B/clk/SM)
 // and 16 K exp2 (16/clk/SM) against 512 clk of tensor work at hd 64 -- these, not the tensor pipe, bound the kernel.
 #include "common.cuh"
+#include "dropmask.cuh"
 
 namespace mrb {
 
@@ -25,7 +26,19 @@ struct AttnTcParams {
   int kv_div, causal, q_pos0;
   void* o; long long o_bs, o_rs;
   float* lse;                                    // [B, H, Lq] or null
+  // DROP instantiations only: attention-probability dropout (modeling_t5.py:600), masks of dropmask.cuh with
+  // row = (b H + h) Lq + i, column = key j; thr7 = (round(256 p) / 2) * 0x01010101 (the SWAR compare below needs an even threshold)
+  const uint32_t* drop_seed; uint32_t drop_site, drop_thr7; float drop_scale;
 };
+
+// Keep-masks of four consecutive keys as two AND-masks over the packed 16-bit pairs (keys 0,1 | keys 2,3):  draw >= thr with an
+// even thr  <=>  (draw >> 1) >= thr / 2, evaluated for the four bytes at once -- (draw >> 1) | 0x80 minus thr / 2 keeps bit 7 of
+// its byte exactly when the draw passes (no borrow crosses a byte) -- and PRMT replicates those sign bits over the half words.
+__device__ __forceinline__ void drop_pair_masks(uint32_t w, uint32_t thr7, uint32_t& m01, uint32_t& m23) {
+  const uint32_t t = (((w >> 1) & 0x7f7f7f7fu) | 0x80808080u) - thr7;
+  asm("prmt.b32 %0, %1, %2, %3;" : "=r"(m01) : "r"(t), "r"(0u), "r"(0x9988u));
+  asm("prmt.b32 %0, %1, %2, %3;" : "=r"(m23) : "r"(t), "r"(0u), "r"(0xBBAAu));
+}
 
 constexpr int TQ = 128, TKV = 128;     // per softmax group: 128 query rows; a CTA runs two groups (256 rows)
 constexpr float TAU = 8.0f;            // stale-max slack (log2 domain): P entries stay below 2^8
@@ -90,6 +103,7 @@ struct RowCtx {
   const float* wrow;        // this row's bias window in shared memory (already * log2 e), column c -> wrow[c]
   uint32_t mb[4];           // attendable-key bits of the tile
   int ncols, kv0, i_abs, causal;
+  uint32_t dkey, drow, dthr7;   // DROP: site key, row base = ((b H + h) Lq + i) * ceil(Lk / 4), replicated threshold
 };
 
 // raw 32-column slice of this row's S tile -> log2-domain scores minus `sub` (scale, bias window, masks); sub = 0 gives the
@@ -133,7 +147,7 @@ __device__ __forceinline__ float tile_max(const RowCtx& x, int nc32) {
 // half a pack (DT is a compile-time dtype where the launcher knows it, so the pack is not predicated both ways).
 // (Software-pipelining the tcgen05.ld of the next 32 columns under the current exponentials was measured and gained
 // nothing -- 0.381 vs 0.378 ms on the T5 encoder shape -- so the simple load / wait / compute loop stays.)
-template <bool HAS_BIAS, bool MASKED, int DT>
+template <bool HAS_BIAS, bool MASKED, int DT, bool DROP = false>
 __device__ __forceinline__ float exp_store(const RowCtx& x, int nc32, int npad, float mref, uint8_t* prow, int r, int dtype) {
   const int dt = DT < 0 ? dtype : DT;
   float rs0 = 0.f, rs1 = 0.f;
@@ -146,6 +160,15 @@ __device__ __forceinline__ float exp_store(const RowCtx& x, int nc32, int npad, 
       const float p0 = ex2(sv[e]), p1 = ex2(sv[e + 1]);
       rs0 += p0; rs1 += p1;
       pk[e >> 1] = pack2(p0, p1, dt);
+    }
+    if (DROP) {                                    // the row sum above is of the undropped P; 1 / (1 - p) is folded into the final 1 / l
+#pragma unroll
+      for (int g4 = 0; g4 < 8; ++g4) {
+        uint32_t m01, m23;
+        drop_pair_masks(drop_word(x.dkey, x.drow, static_cast<uint32_t>((x.kv0 + c) >> 2) + g4), x.dthr7, m01, m23);
+        pk[2 * g4] &= m01;
+        pk[2 * g4 + 1] &= m23;
+      }
     }
 #pragma unroll
     for (int q = 0; q < 4; ++q) {                  // 4 x 16-byte chunks of 8 keys
@@ -164,7 +187,7 @@ __device__ __forceinline__ float exp_store(const RowCtx& x, int nc32, int npad, 
 // the STALE reference maximum m_ref in a single pass; no per-element maximum is tracked: a tile holds <= 128 keys, so a row
 // sum above 2^TAU = 256 is the (conservative, warp-voted) sign that some score exceeded the reference by more than TAU --
 // only then the tile maximum is computed, O and l are rescaled and the tile is redone exactly.
-template <bool HAS_BIAS, bool MASKED, int DT>
+template <bool HAS_BIAS, bool MASKED, int DT, bool DROP = false>
 __device__ __forceinline__ float softmax_tile(const RowCtx& x, int j, int nc32, int npad, uint8_t* prow, int r, int dtype,
                                               float& m_ref, float& l_run, uint32_t o_addr, int hd_cols) {
   // NOTE: tcgen05.ld is warp-collective (.sync.aligned): every branch around it must be warp-uniform.
@@ -172,9 +195,9 @@ __device__ __forceinline__ float softmax_tile(const RowCtx& x, int j, int nc32, 
   if (j == 0) {                                      // no reference yet: exact two-pass tile
     const float mx = tile_max<HAS_BIAS, MASKED>(x, nc32);
     if (mx != -INFINITY) m_ref = mx;
-    rsum = exp_store<HAS_BIAS, MASKED, DT>(x, nc32, npad, mx == -INFINITY ? 0.f : mx, prow, r, dtype);
+    rsum = exp_store<HAS_BIAS, MASKED, DT, DROP>(x, nc32, npad, mx == -INFINITY ? 0.f : mx, prow, r, dtype);
   } else {
-    rsum = exp_store<HAS_BIAS, MASKED, DT>(x, nc32, npad, m_ref == -INFINITY ? 0.f : m_ref, prow, r, dtype);
+    rsum = exp_store<HAS_BIAS, MASKED, DT, DROP>(x, nc32, npad, m_ref == -INFINITY ? 0.f : m_ref, prow, r, dtype);
     if (__any_sync(0xffffffffu, !(rsum <= 256.0f))) {    // rare: some row's max jumped (or overflowed); redo the tile exactly
       const float tmax = tile_max<HAS_BIAS, MASKED>(x, nc32);
       const float m_new = fmaxf(m_ref, tmax);
@@ -192,13 +215,13 @@ __device__ __forceinline__ float softmax_tile(const RowCtx& x, int j, int nc32, 
       }
       tmem_st_wait();
       m_ref = m_new;
-      rsum = exp_store<HAS_BIAS, MASKED, DT>(x, nc32, npad, m_ref == -INFINITY ? 0.f : m_ref, prow, r, dtype);
+      rsum = exp_store<HAS_BIAS, MASKED, DT, DROP>(x, nc32, npad, m_ref == -INFINITY ? 0.f : m_ref, prow, r, dtype);
     }
   }
   return rsum;
 }
 
-template <int HD, int G, int DT>   // DT: 0 fp16 / 1 bf16 known at compile time, -1 = p.dtype
+template <int HD, int G, int DT, bool DROP = false>   // DT: 0 fp16 / 1 bf16 known at compile time, -1 = p.dtype
 __global__ void __launch_bounds__((2 + 4 * G) * 32, G == 1 ? 2 : 1)
 attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                    const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmQ2,
@@ -379,6 +402,12 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       float* wbias = reinterpret_cast<float*>(smem + S::OFF_BIAS) + (warp - 2) * 160;   // this warp's bias window
       uint8_t* prow = smem + S::OFF_P + g * S::P_BYTES + r * 128;
       float m_ref = -INFINITY, l_run = 0.f;
+      uint32_t dkey = 0, drow = 0;
+      if (DROP) {
+        dkey = drop_key(*p.drop_seed, p.drop_site);
+        drow = (static_cast<uint32_t>(b * p.H + h) * static_cast<uint32_t>(p.Lq) + static_cast<uint32_t>(min(qg0 + r, p.Lq - 1))) *
+               drop_groups(static_cast<uint32_t>(p.Lk));
+      }
       // window index for (row r, column c): (kv0 + c) - i_abs + zero = w0 + (31 - lane) + c, w0 = bias index of
       // (column 0, last row of this warp)
       const int i_warp_last = min(qg0 + quad * 32 + 31, p.Lq - 1) + p.q_pos0;
@@ -432,6 +461,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         RowCtx x;
         x.s_addr = s_addr; x.sl2 = sl2; x.ncols = ncols; x.kv0 = kv0; x.i_abs = i_abs; x.causal = p.causal;
         x.mb[0] = x.mb[1] = x.mb[2] = x.mb[3] = 0xffffffffu;
+        if (DROP) { x.dkey = dkey; x.drow = drow; x.dthr7 = p.drop_thr7; }
         bool masked = (ncols < TKV) || (p.causal && kv0 + TKV - 1 > qg0 + quad * 32 + p.q_pos0);
         if (mrow) {
 #pragma unroll
@@ -447,14 +477,14 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 
         float rsum;
         if (bhead && !bias_const) {
-          rsum = masked ? softmax_tile<true, true, DT>(x, j, nc32, npad, prow, r, p.dtype, m_ref, l_run, o_addr, HD)
-                        : softmax_tile<true, false, DT>(x, j, nc32, npad, prow, r, p.dtype, m_ref, l_run, o_addr, HD);
+          rsum = masked ? softmax_tile<true, true, DT, DROP>(x, j, nc32, npad, prow, r, p.dtype, m_ref, l_run, o_addr, HD)
+                        : softmax_tile<true, false, DT, DROP>(x, j, nc32, npad, prow, r, p.dtype, m_ref, l_run, o_addr, HD);
         } else {
           // no bias, or one bias value for the whole tile (T5 buckets saturate 128 positions off the diagonal, i.e. for all but
           // ~3 of a row block's KV tiles): a constant shift of the scores = a shift of the reference maximum, zero per-element cost
           m_ref -= cbias;
-          rsum = masked ? softmax_tile<false, true, DT>(x, j, nc32, npad, prow, r, p.dtype, m_ref, l_run, o_addr, HD)
-                        : softmax_tile<false, false, DT>(x, j, nc32, npad, prow, r, p.dtype, m_ref, l_run, o_addr, HD);
+          rsum = masked ? softmax_tile<false, true, DT, DROP>(x, j, nc32, npad, prow, r, p.dtype, m_ref, l_run, o_addr, HD)
+                        : softmax_tile<false, false, DT, DROP>(x, j, nc32, npad, prow, r, p.dtype, m_ref, l_run, o_addr, HD);
           m_ref += cbias;
         }
         l_run += rsum;
@@ -468,7 +498,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       tc_fence_after();
       const int i = qg0 + r;
       const int odt = DT < 0 ? p.dtype : DT;
-      const float inv = l_run > 0.f ? 1.f / l_run : 0.f;
+      const float inv = (l_run > 0.f ? 1.f / l_run : 0.f) * (DROP ? p.drop_scale : 1.f);
       uint16_t* orow = static_cast<uint16_t*>(p.o) + b * p.o_bs + static_cast<long long>(min(i, p.Lq - 1)) * p.o_rs +
                        static_cast<long long>(h) * p.hd;
 #pragma unroll
@@ -535,17 +565,17 @@ static int make_tmap4(CUtensorMap* map, const void* base, int dtype, int hd, int
   return r == CUDA_SUCCESS ? MRB_OK : MRB_ERR_CUDA;
 }
 
-template <int HD, int G, int DT>
+template <int HD, int G, int DT, bool DROP = false>
 static int launch_tc(const CUtensorMap* maps, const AttnTcParams& p, cudaStream_t s) {
   using S = TcSmem<HD, G>;
   static bool cfg = false;
   if (!cfg) {
-    cudaError_t e = cudaFuncSetAttribute(attn_fwd_tc_kernel<HD, G, DT>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL);
+    cudaError_t e = cudaFuncSetAttribute(attn_fwd_tc_kernel<HD, G, DT, DROP>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL);
     if (e != cudaSuccess) return mrb_set_error(e);
     cfg = true;
   }
   dim3 grid((p.Lq + G * TQ - 1) / (G * TQ), p.H, p.B);
-  MRB_LAUNCH((attn_fwd_tc_kernel<HD, G, DT>), grid, S::THREADS, S::TOTAL, s, maps[0], maps[1], maps[2], maps[3], maps[4], maps[5], p);
+  MRB_LAUNCH((attn_fwd_tc_kernel<HD, G, DT, DROP>), grid, S::THREADS, S::TOTAL, s, maps[0], maps[1], maps[2], maps[3], maps[4], maps[5], p);
   MRB_CHECK_LAUNCH();
   return MRB_OK;
 }
@@ -555,11 +585,11 @@ static int launch_tc(const CUtensorMap* maps, const AttnTcParams& p, cudaStream_
 using namespace mrb;
 
 // Same contract as mrb_attention_fwd (include/mrblip_b200.h); requires hd == 64 or 64 < hd <= 96 with hd % 8 == 0.
-extern "C" int mrb_attention_fwd_tc(const void* q, long long q_bs, long long q_rs, const void* k, long long k_bs, long long k_rs,
-                                    const void* v, long long v_bs, long long v_rs, void* o, long long o_bs, long long o_rs,
-                                    int B, int H, int Lq, int Lk, int hd, int dtype, float scale, const float* bias,
-                                    int bias_len, int bias_zero, const int* kmask, int kv_div, int causal, int q_pos0,
-                                    float* lse, void* stream) {
+static int attention_fwd_tc_impl(const void* q, long long q_bs, long long q_rs, const void* k, long long k_bs, long long k_rs,
+                                 const void* v, long long v_bs, long long v_rs, void* o, long long o_bs, long long o_rs,
+                                 int B, int H, int Lq, int Lk, int hd, int dtype, float scale, const float* bias,
+                                 int bias_len, int bias_zero, const int* kmask, int kv_div, int causal, int q_pos0,
+                                 float* lse, const unsigned* drop_seed, unsigned drop_site, float drop_p, void* stream) {
   if (B <= 0 || H <= 0 || Lq <= 0 || Lk <= 0) return MRB_OK;
   if (dtype != MRB_DT_F16 && dtype != MRB_DT_BF16) return MRB_ERR_ARG;
   if (!(hd == 64 || (hd > 64 && hd <= 96 && (hd & 7) == 0))) return MRB_ERR_UNSUPPORTED;
@@ -584,6 +614,13 @@ extern "C" int mrb_attention_fwd_tc(const void* q, long long q_bs, long long q_r
   p.bias = bias; p.bias_len = bias_len; p.bias_zero = bias_zero; p.kmask = kmask; p.kv_div = kv_div;
   p.causal = causal; p.q_pos0 = q_pos0; p.o = o; p.o_bs = o_bs; p.o_rs = o_rs; p.lse = lse;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (drop_seed && drop_p > 0.f) {
+    // T5 in train mode: hd 64, bf16.  The SWAR mask compare needs an even threshold (p = 0.1 -> 26 / 256).
+    const DropSpec d = make_drop(drop_seed, drop_site, drop_p);
+    if (split || dtype != MRB_DT_BF16 || (d.thr & 1u) || drop_p >= 1.f) return MRB_ERR_UNSUPPORTED;
+    p.drop_seed = d.seed; p.drop_site = d.site; p.drop_thr7 = (d.thr >> 1) * 0x01010101u; p.drop_scale = d.scale;
+    return launch_tc<64, 2, MRB_DT_BF16, true>(maps, p, s);
+  }
   // short sequences (ViT: 257 keys = 3 K/V tiles): one softmax group per CTA, two CTAs per SM (MRB_ATTN_G1=0 disables)
   static int g1 = -1;
   if (g1 < 0) { const char* e = getenv("MRB_ATTN_G1"); g1 = (e && e[0] == '0') ? 0 : 1; }
@@ -592,4 +629,25 @@ extern "C" int mrb_attention_fwd_tc(const void* q, long long q_bs, long long q_r
     return launch_tc<96, 2, -1>(maps, p, s);
   }
   return dtype == MRB_DT_BF16 ? launch_tc<64, 2, MRB_DT_BF16>(maps, p, s) : launch_tc<64, 2, -1>(maps, p, s);
+}
+
+extern "C" int mrb_attention_fwd_tc(const void* q, long long q_bs, long long q_rs, const void* k, long long k_bs, long long k_rs,
+                                    const void* v, long long v_bs, long long v_rs, void* o, long long o_bs, long long o_rs,
+                                    int B, int H, int Lq, int Lk, int hd, int dtype, float scale, const float* bias,
+                                    int bias_len, int bias_zero, const int* kmask, int kv_div, int causal, int q_pos0,
+                                    float* lse, void* stream) {
+  return attention_fwd_tc_impl(q, q_bs, q_rs, k, k_bs, k_rs, v, v_bs, v_rs, o, o_bs, o_rs, B, H, Lq, Lk, hd, dtype, scale, bias, bias_len,
+                               bias_zero, kmask, kv_div, causal, q_pos0, lse, nullptr, 0u, 0.f, stream);
+}
+
+// mrb_attention_fwd_tc with train-mode dropout of the attention probabilities (modeling_t5.py:600): O = drop(softmax(S)) V, lse
+// unchanged.  hd 64, bf16, round(256 p) even.  Mask: dropmask.cuh with row = (b H + h) Lq + i, column = key index.
+extern "C" int mrb_attention_fwd_tc_drop(const void* q, long long q_bs, long long q_rs, const void* k, long long k_bs, long long k_rs,
+                                         const void* v, long long v_bs, long long v_rs, void* o, long long o_bs, long long o_rs,
+                                         int B, int H, int Lq, int Lk, int hd, int dtype, float scale, const float* bias,
+                                         int bias_len, int bias_zero, const int* kmask, int kv_div, int causal, int q_pos0,
+                                         float* lse, const unsigned* seed, unsigned site, float p, void* stream) {
+  if (!seed) return MRB_ERR_ARG;
+  return attention_fwd_tc_impl(q, q_bs, q_rs, k, k_bs, k_rs, v, v_bs, v_rs, o, o_bs, o_rs, B, H, Lq, Lk, hd, dtype, scale, bias, bias_len,
+                               bias_zero, kmask, kv_div, causal, q_pos0, lse, seed, site, p, stream);
 }

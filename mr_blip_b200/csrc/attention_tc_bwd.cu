@@ -10,6 +10,7 @@
 // one thread per TMEM lane).  The B operands of the accumulating MMAs (dO_t, Q_t, K_t) are read MN-major straight from
 // their [row][d] tiles, so nothing is transposed in memory.
 #include "common.cuh"
+#include "dropmask.cuh"
 
 namespace mrb {
 
@@ -23,6 +24,29 @@ struct AttnBwdParams {
   void* out1; long long o1_bs, o1_rs;            // DKV: dK ; DQ: dQ
   void* out2; long long o2_bs, o2_rs;            // DKV: dV
 };
+struct AttnBwdDropParams : AttnBwdParams {
+  // DROP instantiations only (attention-probability dropout, modeling_t5.py:600; masks of dropmask.cuh, row = (b H + h) Lq + i,
+  // column = key j).  With keep mask m and s = 1 / (1 - p):  dV = s (m P)^T dO,  dS = P * (s m dP - delta) * scale  (delta is
+  // rowsum(dO * O) of the DROPPED output, which is what the forward saved), dK / dQ from dS as before.
+  const uint32_t* drop_seed; uint32_t drop_site, drop_thr; float drop_scale;
+};
+
+template <bool DROP> struct BwdParamsOf { typedef AttnBwdParams type; };
+template <> struct BwdParamsOf<true> { typedef AttnBwdDropParams type; };
+
+// what the element loop needs to recompute the mask (DROP only)
+struct BwdDrop {
+  uint32_t key, thr, thr7, ng;
+  uint32_t rowbase;        // DQ: ((b H + h) Lq + i) * ng of this thread's query row;  DKV: ((b H + h) Lq) * ng of the head
+  uint32_t jg, sh;         // DKV: word index (key >> 2) and bit offset 8 * (key & 3) of this thread's key
+};
+// 0xffffffff if bit 8 i + 7 of t is set (t from the SWAR compare of four draws, attention_tc.cu drop_pair_masks), else 0
+template <int I>
+__device__ __forceinline__ uint32_t sign_mask(uint32_t t) {
+  uint32_t m;
+  asm("prmt.b32 %0, %1, %2, %3;" : "=r"(m) : "r"(t), "r"(0u), "r"(0x8888u + 0x1111u * I));
+  return m;
+}
 
 constexpr int MODE_DKV = 0, MODE_DQ = 1;
 constexpr int TS = 128;      // stationary rows per group
@@ -76,11 +100,11 @@ struct BwdSmem {
 // HAS_BIAS = the bias varies inside the tile (window lookup per element); MASKED = some element of the warp's tile is masked.
 // Unmasked constant-bias tiles (all but the ~3 tiles next to the diagonal of a T5 encoder row block) cost
 // FFMA + MUFU + FFMA + FMUL + the packs per element.
-template <int MODE, bool HAS_BIAS, bool MASKED>
+template <int MODE, bool HAS_BIAS, bool MASKED, bool DROP = false>
 __device__ __forceinline__ void bwd_tile_rows(uint32_t lane_base, const float* wrow, const float* wlse, const float* wdl,
                                               float off, float dls, float sl2, float scale, uint32_t cm0, uint32_t cm1,
                                               bool row_key_ok, bool causal, int u0, int row_c, int q_pos0, uint8_t* prow,
-                                              int r, int dt) {
+                                              int r, int dt, const BwdDrop& dd = BwdDrop()) {
 #pragma unroll
   for (int c0 = 0; c0 < TT; c0 += 32) {
     uint32_t sv[32], dv[32];
@@ -98,6 +122,14 @@ __device__ __forceinline__ void bwd_tile_rows(uint32_t lane_base, const float* w
         off8[0] = la.x; off8[1] = la.y; off8[2] = la.z; off8[3] = la.w; off8[4] = lb.x; off8[5] = lb.y; off8[6] = lb.z; off8[7] = lb.w;
         dl8[0] = da.x; dl8[1] = da.y; dl8[2] = da.z; dl8[3] = da.w; dl8[4] = db.x; dl8[5] = db.y; dl8[6] = db.z; dl8[7] = db.w;
       }
+      uint32_t t8[2] = {0u, 0u};              // DROP, DQ: SWAR compare results of this thread's keys c0 + e8 .. + 7 (two words)
+      if (DROP && MODE == MODE_DQ) {
+#pragma unroll
+        for (int w2 = 0; w2 < 2; ++w2) {
+          const uint32_t w = drop_word(dd.key, dd.rowbase, static_cast<uint32_t>((u0 + c0 + e8) >> 2) + w2);
+          t8[w2] = (((w >> 1) & 0x7f7f7f7fu) | 0x80808080u) - dd.thr7;
+        }
+      }
 #pragma unroll
       for (int e2 = 0; e2 < 8; e2 += 2) {
         const int e = e8 + e2;
@@ -105,6 +137,17 @@ __device__ __forceinline__ void bwd_tile_rows(uint32_t lane_base, const float* w
 #pragma unroll
         for (int q = 0; q < 2; ++q) {
           const int c = c0 + e + q;
+          uint32_t keepm = 0xffffffffu;
+          if (DROP) {
+            if (MODE == MODE_DQ) {
+              const uint32_t t = t8[(e2 + q) >> 2];
+              keepm = ((e2 + q) & 3) == 0 ? sign_mask<0>(t) : ((e2 + q) & 3) == 1 ? sign_mask<1>(t) : ((e2 + q) & 3) == 2 ? sign_mask<2>(t)
+                                                                                                                     : sign_mask<3>(t);
+            } else {                            // streamed query u0 + c, this thread's key: one word per element
+              const uint32_t w = drop_word(dd.key, dd.rowbase + static_cast<uint32_t>(u0 + c) * dd.ng, dd.jg);
+              keepm = (((w >> dd.sh) & 0xffu) >= dd.thr) ? 0xffffffffu : 0u;
+            }
+          }
           float o = (MODE == MODE_DQ) ? off : off8[e2 + q];
           if (HAS_BIAS) o += (MODE == MODE_DQ) ? wrow[c] : wrow[-c];
           float pv = ex2b(fmaf(__uint_as_float(sv[e + q]), sl2, o));
@@ -114,8 +157,8 @@ __device__ __forceinline__ void bwd_tile_rows(uint32_t lane_base, const float* w
             else ok = row_key_ok && !(causal && row_c > u0 + c + q_pos0);
             pv = ok ? pv : 0.f;
           }
-          pr[q] = pv;
-          ds[q] = pv * fmaf(__uint_as_float(dv[e + q]), scale, -((MODE == MODE_DQ) ? dls : dl8[e2 + q]));
+          pr[q] = DROP ? __uint_as_float(__float_as_uint(pv) & keepm) : pv;       // P^T operand of dV (DKV): dropped, unscaled
+          ds[q] = pv * fmaf(__uint_as_float(DROP ? (dv[e + q] & keepm) : dv[e + q]), scale, -((MODE == MODE_DQ) ? dls : dl8[e2 + q]));
         }
         if (MODE == MODE_DKV) pp[e >> 1] = pack2(pr[0], pr[1], dt);
         pd[e >> 1] = pack2(ds[0], ds[1], dt);
@@ -134,10 +177,11 @@ __device__ __forceinline__ void bwd_tile_rows(uint32_t lane_base, const float* w
 
 // ENC = the encoder self-attention case that carries almost all of the time (bucketed bias, no causal mask, bf16): those
 // three facts become compile-time constants so the per-element loop has no uniform branches left.
-template <int MODE, bool ENC>
+template <int MODE, bool ENC, bool DROP = false>
 __global__ void __launch_bounds__(320, 1)
 attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmY,
-                   const __grid_constant__ CUtensorMap tmU, const __grid_constant__ CUtensorMap tmW, const AttnBwdParams p) {
+                   const __grid_constant__ CUtensorMap tmU, const __grid_constant__ CUtensorMap tmW,
+                   const typename BwdParamsOf<DROP>::type p) {
   mrb::pdl_trigger();   // the successor may become resident and run its set-up; it blocks in its own pdl_wait()
   using S = BwdSmem;
   constexpr int STAGES = S::STAGES;
@@ -290,6 +334,17 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
         row_key_ok = __ldg(p.kmask + static_cast<long long>(b) * p.Lk + row_c) != 0;
       }
       const int warp_row_first = min(xg0 + quad * 32, Lstat - 1), warp_row_last = min(xg0 + quad * 32 + 31, Lstat - 1);
+      BwdDrop dd = BwdDrop();
+      float tile_scale = scale;                                          // multiplies dP only (delta * scale is staged separately)
+      if constexpr (DROP) {
+        tile_scale = scale * p.drop_scale;
+        dd.key = drop_key(*p.drop_seed, p.drop_site);
+        dd.thr = p.drop_thr; dd.thr7 = (p.drop_thr >> 1) * 0x01010101u;
+        dd.ng = drop_groups(static_cast<uint32_t>(p.Lk));
+        const uint32_t head_row = static_cast<uint32_t>(b * p.H + h) * static_cast<uint32_t>(p.Lq);
+        dd.rowbase = (MODE == MODE_DQ) ? (head_row + static_cast<uint32_t>(row_c)) * dd.ng : head_row * dd.ng;
+        dd.jg = static_cast<uint32_t>(row_c) >> 2; dd.sh = 8u * (static_cast<uint32_t>(row_c) & 3u);
+      }
 
       // per-tile global loads (bias window, lse / delta of the streamed queries, key mask) run one tile ahead of their use
       float bnext[3] = {0.f, 0.f, 0.f}, lnext[2] = {0.f, 0.f}, dnext[2] = {0.f, 0.f};
@@ -367,11 +422,11 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
         tc_fence_after();
         // warp-uniform dispatch (tcgen05.ld inside is warp-collective)
         if (vbias) {
-          if (masked) bwd_tile_rows<MODE, true, true>(lane_base, wrow, wlse, wdl, off, dls, sl2, scale, cm0, cm1, row_key_ok, causal, u0, row_c, p.q_pos0, prow, r, dt);
-          else bwd_tile_rows<MODE, true, false>(lane_base, wrow, wlse, wdl, off, dls, sl2, scale, cm0, cm1, row_key_ok, causal, u0, row_c, p.q_pos0, prow, r, dt);
+          if (masked) bwd_tile_rows<MODE, true, true, DROP>(lane_base, wrow, wlse, wdl, off, dls, sl2, tile_scale, cm0, cm1, row_key_ok, causal, u0, row_c, p.q_pos0, prow, r, dt, dd);
+          else bwd_tile_rows<MODE, true, false, DROP>(lane_base, wrow, wlse, wdl, off, dls, sl2, tile_scale, cm0, cm1, row_key_ok, causal, u0, row_c, p.q_pos0, prow, r, dt, dd);
         } else {
-          if (masked) bwd_tile_rows<MODE, false, true>(lane_base, wrow, wlse, wdl, off, dls, sl2, scale, cm0, cm1, row_key_ok, causal, u0, row_c, p.q_pos0, prow, r, dt);
-          else bwd_tile_rows<MODE, false, false>(lane_base, wrow, wlse, wdl, off, dls, sl2, scale, cm0, cm1, row_key_ok, causal, u0, row_c, p.q_pos0, prow, r, dt);
+          if (masked) bwd_tile_rows<MODE, false, true, DROP>(lane_base, wrow, wlse, wdl, off, dls, sl2, tile_scale, cm0, cm1, row_key_ok, causal, u0, row_c, p.q_pos0, prow, r, dt, dd);
+          else bwd_tile_rows<MODE, false, false, DROP>(lane_base, wrow, wlse, wdl, off, dls, sl2, tile_scale, cm0, cm1, row_key_ok, causal, u0, row_c, p.q_pos0, prow, r, dt, dd);
         }
         fence_proxy_async();
         tc_fence_before();
@@ -393,6 +448,12 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
           uint32_t v[32];
           tmem_ld_32x32b_x32(lane_base + 128 + a * 64 + c0, v);
           tmem_ld_wait();
+          if constexpr (DROP) {
+            if (MODE == MODE_DKV && a == 0) {                   // dV = 1 / (1 - p) * (m P)^T dO
+#pragma unroll
+              for (int c = 0; c < 32; ++c) v[c] = __float_as_uint(__uint_as_float(v[c]) * p.drop_scale);
+            }
+          }
           if (row < Lstat) {
 #pragma unroll
             for (int c = 0; c < 32; c += 8)
@@ -459,25 +520,30 @@ static int make_tmap4b(CUtensorMap* map, const void* base, int dtype, int heads,
   return r == CUDA_SUCCESS ? MRB_OK : MRB_ERR_CUDA;
 }
 
-template <int MODE, bool ENC>
+template <int MODE, bool ENC, bool DROP = false>
 static int launch_bwd_tc2(const CUtensorMap& x, const CUtensorMap& y, const CUtensorMap& u, const CUtensorMap& w,
-                          const AttnBwdParams& p, int Lstat, cudaStream_t s) {
+                          const AttnBwdDropParams& p, int Lstat, cudaStream_t s) {
   static bool cfg = false;
   if (!cfg) {
-    cudaError_t e = cudaFuncSetAttribute(attn_bwd_tc_kernel<MODE, ENC>, cudaFuncAttributeMaxDynamicSharedMemorySize, BwdSmem::TOTAL);
+    cudaError_t e = cudaFuncSetAttribute(attn_bwd_tc_kernel<MODE, ENC, DROP>, cudaFuncAttributeMaxDynamicSharedMemorySize, BwdSmem::TOTAL);
     if (e != cudaSuccess) return mrb_set_error(e);
     cfg = true;
   }
   dim3 grid((Lstat + 2 * TS - 1) / (2 * TS), p.H, p.B);
-  MRB_LAUNCH((attn_bwd_tc_kernel<MODE, ENC>), grid, 320, BwdSmem::TOTAL, s, x, y, u, w, p);
+  MRB_LAUNCH((attn_bwd_tc_kernel<MODE, ENC, DROP>), grid, 320, BwdSmem::TOTAL, s, x, y, u, w,
+             static_cast<const typename BwdParamsOf<DROP>::type&>(p));
   MRB_CHECK_LAUNCH();
   return MRB_OK;
 }
 template <int MODE>
 static int launch_bwd_tc(const CUtensorMap& x, const CUtensorMap& y, const CUtensorMap& u, const CUtensorMap& w,
-                         const AttnBwdParams& p, int Lstat, cudaStream_t s) {
+                         const AttnBwdDropParams& p, int Lstat, cudaStream_t s) {
   static int spec = -1;                   // MRB_ATTN_BWD_ENC=0 keeps the generic instantiation (A/B measurements)
   if (spec < 0) { const char* e = getenv("MRB_ATTN_BWD_ENC"); spec = (e && e[0] == '0') ? 0 : 1; }
+  if (p.drop_seed) {                      // train-mode dropout of the probabilities: same two specialisations
+    if (p.bias && !p.causal && p.dtype == MRB_DT_BF16) return launch_bwd_tc2<MODE, true, true>(x, y, u, w, p, Lstat, s);
+    return launch_bwd_tc2<MODE, false, true>(x, y, u, w, p, Lstat, s);
+  }
   if (spec && p.bias && !p.causal && p.dtype == MRB_DT_BF16) return launch_bwd_tc2<MODE, true>(x, y, u, w, p, Lstat, s);
   return launch_bwd_tc2<MODE, false>(x, y, u, w, p, Lstat, s);
 }
@@ -486,13 +552,12 @@ static int launch_bwd_tc(const CUtensorMap& x, const CUtensorMap& y, const CUten
 
 using namespace mrb;
 
-// Same contract as mrb_attention_bwd; hd must be 64.
-extern "C" int mrb_attention_bwd_tc(const void* q, long long q_bs, long long q_rs, const void* k, long long k_bs, long long k_rs,
-                                    const void* v, long long v_bs, long long v_rs, const void* o, long long o_bs, long long o_rs,
-                                    const void* dout, long long do_bs, long long do_rs, void* dq, void* dk, void* dv,
-                                    int B, int H, int Lq, int Lk, int hd, int dtype, float scale, const float* bias,
-                                    int bias_len, int bias_zero, const int* kmask, int causal, int q_pos0, const float* lse,
-                                    float* delta_ws, void* stream) {
+static int attention_bwd_tc_impl(const void* q, long long q_bs, long long q_rs, const void* k, long long k_bs, long long k_rs,
+                                 const void* v, long long v_bs, long long v_rs, const void* o, long long o_bs, long long o_rs,
+                                 const void* dout, long long do_bs, long long do_rs, void* dq, void* dk, void* dv,
+                                 int B, int H, int Lq, int Lk, int hd, int dtype, float scale, const float* bias,
+                                 int bias_len, int bias_zero, const int* kmask, int causal, int q_pos0, const float* lse,
+                                 float* delta_ws, const unsigned* drop_seed, unsigned drop_site, float drop_p, void* stream) {
   if (B <= 0 || H <= 0 || Lq <= 0 || Lk <= 0) return MRB_OK;
   if (hd != 64) return MRB_ERR_UNSUPPORTED;
   if (dtype != MRB_DT_F16 && dtype != MRB_DT_BF16) return MRB_ERR_ARG;
@@ -504,10 +569,15 @@ extern "C" int mrb_attention_bwd_tc(const void* q, long long q_bs, long long q_r
                                                          static_cast<const uint16_t*>(dout), do_bs, do_rs, delta_ws, B, H, Lq, dtype);
     MRB_CHECK_LAUNCH();
   }
-  AttnBwdParams p{};
+  AttnBwdDropParams p{};
   p.B = B; p.H = H; p.Lq = Lq; p.Lk = Lk; p.dtype = dtype; p.scale = scale;
   p.bias = bias; p.bias_len = bias_len; p.bias_zero = bias_zero; p.kmask = kmask; p.causal = causal; p.q_pos0 = q_pos0;
   p.lse = lse; p.delta = delta_ws;
+  if (drop_seed && drop_p > 0.f) {
+    const DropSpec d = make_drop(drop_seed, drop_site, drop_p);
+    if ((d.thr & 1u) || drop_p >= 1.f) return MRB_ERR_UNSUPPORTED;        // the SWAR compare of the dQ kernel needs an even threshold
+    p.drop_seed = d.seed; p.drop_site = d.site; p.drop_thr = d.thr; p.drop_scale = d.scale;
+  }
   CUtensorMap mq128, mk128, mv128, mdo128, mq64, mk64, mv64, mdo64;
   int rc = make_tmap4b(&mq128, q, dtype, H, Lq, B, q_rs, q_bs, TS);
   if (!rc) rc = make_tmap4b(&mk128, k, dtype, H, Lk, B, k_rs, k_bs, TS);
@@ -525,4 +595,27 @@ extern "C" int mrb_attention_bwd_tc(const void* q, long long q_bs, long long q_r
   // dQ: stationary Q, dO; streamed K, V
   p.out1 = dq; p.o1_bs = q_bs; p.o1_rs = q_rs; p.out2 = nullptr;
   return launch_bwd_tc<MODE_DQ>(mq128, mdo128, mk64, mv64, p, Lq, s);
+}
+
+// Same contract as mrb_attention_bwd; hd must be 64.
+extern "C" int mrb_attention_bwd_tc(const void* q, long long q_bs, long long q_rs, const void* k, long long k_bs, long long k_rs,
+                                    const void* v, long long v_bs, long long v_rs, const void* o, long long o_bs, long long o_rs,
+                                    const void* dout, long long do_bs, long long do_rs, void* dq, void* dk, void* dv,
+                                    int B, int H, int Lq, int Lk, int hd, int dtype, float scale, const float* bias,
+                                    int bias_len, int bias_zero, const int* kmask, int causal, int q_pos0, const float* lse,
+                                    float* delta_ws, void* stream) {
+  return attention_bwd_tc_impl(q, q_bs, q_rs, k, k_bs, k_rs, v, v_bs, v_rs, o, o_bs, o_rs, dout, do_bs, do_rs, dq, dk, dv, B, H, Lq, Lk, hd,
+                               dtype, scale, bias, bias_len, bias_zero, kmask, causal, q_pos0, lse, delta_ws, nullptr, 0u, 0.f, stream);
+}
+
+// Backward of mrb_attention_fwd_tc_drop (same seed word, site and p: the mask is recomputed, nothing was stored).
+extern "C" int mrb_attention_bwd_tc_drop(const void* q, long long q_bs, long long q_rs, const void* k, long long k_bs, long long k_rs,
+                                         const void* v, long long v_bs, long long v_rs, const void* o, long long o_bs, long long o_rs,
+                                         const void* dout, long long do_bs, long long do_rs, void* dq, void* dk, void* dv,
+                                         int B, int H, int Lq, int Lk, int hd, int dtype, float scale, const float* bias,
+                                         int bias_len, int bias_zero, const int* kmask, int causal, int q_pos0, const float* lse,
+                                         float* delta_ws, const unsigned* seed, unsigned site, float p, void* stream) {
+  if (!seed) return MRB_ERR_ARG;
+  return attention_bwd_tc_impl(q, q_bs, q_rs, k, k_bs, k_rs, v, v_bs, v_rs, o, o_bs, o_rs, dout, do_bs, do_rs, dq, dk, dv, B, H, Lq, Lk, hd,
+                               dtype, scale, bias, bias_len, bias_zero, kmask, causal, q_pos0, lse, delta_ws, seed, site, p, stream);
 }

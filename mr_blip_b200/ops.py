@@ -113,18 +113,25 @@ def gemm(a, b, out=None, bias=None, gelu=False, resid=None, out_dtype=None, row_
 
 
 def attention_fwd(q, k, v, out, B, H, Lq, Lk, hd, scale, q_strides, k_strides, v_strides, o_strides, bias=None,
-                  bias_zero=0, kmask=None, causal=False, q_pos0=0, lse=None, kv_div=1, impl="auto"):
+                  bias_zero=0, kmask=None, causal=False, q_pos0=0, lse=None, kv_div=1, impl="auto", drop=None):
     """q/k/v/out: tensors whose data_ptr is row 0 / head 0; *_strides = (batch stride, row stride) in elements.
-    impl: "tc" = tcgen05 kernel, "mma" = mma.sync kernel, "auto" = tcgen05 for >= 128 query rows and hd 64 / 72..96."""
+    impl: "tc" = tcgen05 kernel, "mma" = mma.sync kernel, "auto" = tcgen05 for >= 128 query rows and hd 64 / 72..96.
+    drop: None, or (seed word tensor, site, p) = train-mode dropout of the attention probabilities."""
     _check(q, torch.float16, torch.bfloat16)
     if kmask is not None:
         _check(kmask, torch.int32)
     tc_ok = (hd == 64 or (64 < hd <= 96 and hd % 8 == 0))
     use_tc = impl == "tc" or (impl == "auto" and USE_TC_ATTENTION and tc_ok and (Lq >= 128 or Lk >= 512))
-    _lib.call("mrb_attention_fwd_tc" if use_tc else "mrb_attention_fwd", q.data_ptr(), q_strides[0], q_strides[1], k.data_ptr(), k_strides[0], k_strides[1],
-              v.data_ptr(), v_strides[0], v_strides[1], out.data_ptr(), o_strides[0], o_strides[1], B, H, Lq, Lk, hd,
-              _DT[q.dtype], float(scale), _ptr(bias), bias.shape[1] if bias is not None else 0, bias_zero, _ptr(kmask),
-              kv_div, int(causal), q_pos0, _ptr(lse), _stream())
+    args = (q.data_ptr(), q_strides[0], q_strides[1], k.data_ptr(), k_strides[0], k_strides[1],
+            v.data_ptr(), v_strides[0], v_strides[1], out.data_ptr(), o_strides[0], o_strides[1], B, H, Lq, Lk, hd,
+            _DT[q.dtype], float(scale), _ptr(bias), bias.shape[1] if bias is not None else 0, bias_zero, _ptr(kmask),
+            kv_div, int(causal), q_pos0, _ptr(lse))
+    if drop is not None:
+        use_tc = use_tc and hd == 64 and q.dtype == torch.bfloat16
+        _lib.call("mrb_attention_fwd_tc_drop" if use_tc else "mrb_attention_fwd_drop", *args, drop[0].data_ptr(), drop[1],
+                  float(drop[2]), _stream())
+    else:
+        _lib.call("mrb_attention_fwd_tc" if use_tc else "mrb_attention_fwd", *args, _stream())
     return out
 
 
@@ -135,13 +142,19 @@ def attention_row(q, k, v, out, B, H, Lk, hd, scale, q_bs, k_strides, v_strides,
 
 
 def attention_bwd(q, k, v, o, dout, dq, dk, dv, B, H, Lq, Lk, hd, scale, q_strides, k_strides, v_strides, o_strides,
-                  do_strides, lse, delta_ws, bias=None, bias_zero=0, kmask=None, causal=False, q_pos0=0, impl="auto"):
+                  do_strides, lse, delta_ws, bias=None, bias_zero=0, kmask=None, causal=False, q_pos0=0, impl="auto", drop=None):
+    """drop: the (seed word tensor, site, p) the forward call was given, or None."""
     use_tc = impl == "tc" or (impl == "auto" and USE_TC_ATTENTION and hd == 64 and (Lq >= 128 or Lk >= 512))
-    _lib.call("mrb_attention_bwd_tc" if use_tc else "mrb_attention_bwd", q.data_ptr(), q_strides[0], q_strides[1], k.data_ptr(), k_strides[0], k_strides[1],
-              v.data_ptr(), v_strides[0], v_strides[1], o.data_ptr(), o_strides[0], o_strides[1], dout.data_ptr(),
-              do_strides[0], do_strides[1], dq.data_ptr(), dk.data_ptr(), dv.data_ptr(), B, H, Lq, Lk, hd, _DT[q.dtype],
-              float(scale), _ptr(bias), bias.shape[1] if bias is not None else 0, bias_zero, _ptr(kmask), int(causal),
-              q_pos0, lse.data_ptr(), delta_ws.data_ptr(), _stream())
+    args = (q.data_ptr(), q_strides[0], q_strides[1], k.data_ptr(), k_strides[0], k_strides[1],
+            v.data_ptr(), v_strides[0], v_strides[1], o.data_ptr(), o_strides[0], o_strides[1], dout.data_ptr(),
+            do_strides[0], do_strides[1], dq.data_ptr(), dk.data_ptr(), dv.data_ptr(), B, H, Lq, Lk, hd, _DT[q.dtype],
+            float(scale), _ptr(bias), bias.shape[1] if bias is not None else 0, bias_zero, _ptr(kmask), int(causal),
+            q_pos0, lse.data_ptr(), delta_ws.data_ptr())
+    if drop is not None:
+        _lib.call("mrb_attention_bwd_tc_drop" if use_tc else "mrb_attention_bwd_drop", *args, drop[0].data_ptr(), drop[1],
+                  float(drop[2]), _stream())
+    else:
+        _lib.call("mrb_attention_bwd_tc" if use_tc else "mrb_attention_bwd", *args, _stream())
 
 
 def norm(x, w, bias, eps, mode, add=None, out_f32=None, out_h=None, sum_out=None, ld_h=None):
@@ -275,3 +288,51 @@ def colsum(x, out):
 
 def axpby(x, y, a, b):
     _lib.call("mrb_axpby", x.data_ptr(), y.data_ptr(), x.numel(), float(a), float(b), _stream())
+
+
+# ---------------------------------------------------------------------------------------------- train-mode dropout
+# (csrc/dropmask.cuh, csrc/dropout.cu, mr_blip_b200/dropout.py).  `seed` is a one-element int32 / uint32 CUDA tensor the host
+# rewrites before each step; `site` the id of the dropout call; p the drop probability.
+def dropout(x, out, rows, cols, seed, site, p):
+    """out = drop(x): fp32 -> fp32 / 16-bit, or 16-bit -> same type; 2-D operands with unit column stride (out may be x)."""
+    _lib.call("mrb_dropout", x.data_ptr(), x.stride(0), out.data_ptr(), out.stride(0), rows, cols, _DT[x.dtype], _DT[out.dtype],
+              seed.data_ptr(), site, float(p), _stream())
+    return out
+
+
+def dropout_add(resid, branch, out, seed, site, p):
+    """out = resid + drop(branch): fp32 [rows, cols], all contiguous."""
+    assert resid.is_contiguous() and branch.is_contiguous() and out.is_contiguous()
+    rows, cols = branch.shape
+    _lib.call("mrb_dropout_add", resid.data_ptr(), branch.data_ptr(), out.data_ptr(), rows, cols, seed.data_ptr(), site, float(p),
+              _stream())
+    return out
+
+
+def gated_gelu_fwd_drop(ab, h, M, F, seed, site, p):
+    _lib.call("mrb_gated_gelu_fwd_drop", ab.data_ptr(), h.data_ptr(), M, F, h.stride(0), _DT[ab.dtype], seed.data_ptr(), site,
+              float(p), _stream())
+
+
+def gated_gelu_bwd_drop(ab, dh, dab, M, F, seed, site, p):
+    _lib.call("mrb_gated_gelu_bwd_drop", ab.data_ptr(), dh.data_ptr(), dh.stride(0), dab.data_ptr(), dab.stride(0), M, F,
+              _DT[ab.dtype], seed.data_ptr(), site, float(p), _stream())
+
+
+def lora_down_drop(x, A_down, out, M, K, nlin, seed, site0, p):
+    """out[:M, :32] = [drop_j(x) . A_j^T]_j (16-bit): x [M, >=K], A_down [32, K] = the group's stacked lora_A."""
+    _lib.call("mrb_lora_down_drop", x.data_ptr(), x.stride(0), A_down.data_ptr(), A_down.stride(0), M, K, nlin, out.data_ptr(),
+              out.stride(0), _DT[x.dtype], seed.data_ptr(), site0, float(p), _stream())
+    return out
+
+
+def lora_wgrad_drop(x, ldx, q, ldq, M, K, dA, dtype, seed, site, p):
+    """dA[8, K] += (q[M, 8])^T drop(x[M, K]); x / q are raw device addresses (column offsets applied by the caller)."""
+    _lib.call("mrb_lora_wgrad_drop", x, ldx, q, ldq, M, K, dA.data_ptr(), dtype, seed.data_ptr(), site, float(p), _stream())
+
+
+def lora_dx_drop(q, A_down, nlin, dx, M, K, seed, site0, p):
+    """dx[:M, :K] += sum_j mask_j * (q[:, 8j:8j+8] . A_j): q = the 32 extension columns of the dgrad operand."""
+    _lib.call("mrb_lora_dx_drop", q.data_ptr(), q.stride(0), A_down.data_ptr(), A_down.stride(0), nlin, dx.data_ptr(), dx.stride(0),
+              _DT[dx.dtype], M, K, _DT[q.dtype], seed.data_ptr(), site0, float(p), _stream())
+    return dx

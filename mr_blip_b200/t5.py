@@ -12,12 +12,14 @@ Data layout (HBM):
     (bf16 [N, K+32]), so base(x) + B(A x) is ONE tcgen05 GEMM.  Backward mirrors this with
     [M, N+32] gradient buffers and [W^T | A^T | 0] weights (see LoraGroup).
   * LoRA A/B change every optimiser step: refresh() re-copies them into their 8-column slots.
-Dropout (T5 0.1, LoRA 0.05) is not applied: see DESIGN.md "Out of scope / gaps".
+Train-mode dropout (T5 0.1, LoRA inputs 0.05): off unless T5Engine.drop is a dropout.DropState (BLIP2_MR sets it in train mode
+when built with train_dropout=True / MRB_TRAIN_DROPOUT=1); masks are the counter hash of csrc/dropmask.cuh.
 """
 import math
 
 import torch
 
+from . import dropout as dr
 from . import ops
 from .dims import Dims, T5_PREFIX
 
@@ -44,6 +46,8 @@ class LoraGroup:
         self.Ns = [w.shape[0] for w in Ws]
         self.N = N = sum(self.Ns)
         self.n = len(names)
+        self.site0 = dr.lora_site(names[0])                   # LoRA input dropout: Linear j of the group draws at site0 + j
+        assert [dr.lora_site(n) for n in names] == [self.site0 + j for j in range(self.n)]
         self.scale = scale
         self.A_params = [get(n + ".lora_A.default.weight") for n in names]
         self.B_params = [get(n + ".lora_B.default.weight") for n in names]
@@ -101,9 +105,27 @@ class LoraGroup:
             off += nB
         return off
 
+    def _drop(self):
+        dp = self.eng.drop if self.eng is not None else None
+        return dp if (dp is not None and dp.lora > 0.0) else None
+
     def down(self, x_ext, M):
-        """x_ext[:, K:K+32] = x_ext[:, :K] . A_down^T  (the LoRA down-projections of the Linears in this group)."""
-        ops.down32(x_ext[:, :self.K], self.A_down, x_ext[:, self.K:], M)
+        """x_ext[:, K:K+32] = x_ext[:, :K] . A_down^T  (the LoRA down-projections of the Linears in this group); in train mode
+        every Linear j sees its own drop_j(x) (peft: lora_B(lora_A(dropout(x))))."""
+        dp = self._drop()
+        if dp is not None:
+            ops.lora_down_drop(x_ext[:, :self.K], self.A_down, x_ext[:, self.K:], M, self.K, self.n, dp.word, self.site0, dp.lora)
+        else:
+            ops.down32(x_ext[:, :self.K], self.A_down, x_ext[:, self.K:], M)
+
+    def dgrad(self, dy_ext, M, out=None, resid=None, out_dtype=BF):
+        """dx = dy . W + sum_j mask_j * ((dy sB_j) . A_j): one GEMM over the extended K in eval mode; with LoRA dropout the dense
+        part is the GEMM over K = N and the rank-8 terms are added under their masks (mrb_lora_dx_drop)."""
+        dp = self._drop()
+        if dp is None:
+            return ops.gemm(dy_ext, self.ext_b, out=out, resid=resid, out_dtype=out_dtype, M=M)
+        dx = ops.gemm(dy_ext, self.ext_b, out=out, resid=resid, out_dtype=out_dtype, M=M, K=self.N)
+        return ops.lora_dx_drop(dy_ext[:, self.N:], self.A_down, self.n, dx, M, self.K, dp.word, self.site0, dp.lora)
 
     def forward(self, x_ext, M, out=None, resid=None, out_dtype=BF):
         self.down(x_ext, M)
@@ -118,8 +140,8 @@ class LoraGroup:
             # dA / dB feed nothing downstream: reduce them on the side stream while the main stream goes on with dgrad
             with self.eng.side_block(hold=(dy_ext, x_ext)):
                 self._wgrads(dy_ext, x_ext, M)
-            return ops.gemm(dy_ext, self.ext_b, out=out, resid=resid, out_dtype=out_dtype, M=M)
-        dx = ops.gemm(dy_ext, self.ext_b, out=out, resid=resid, out_dtype=out_dtype, M=M)
+            return self.dgrad(dy_ext, M, out=out, resid=resid, out_dtype=out_dtype)
+        dx = self.dgrad(dy_ext, M, out=out, resid=resid, out_dtype=out_dtype)
         self._wgrads(dy_ext, x_ext, M)
         return dx
 
@@ -130,6 +152,12 @@ class LoraGroup:
             o, n_ = self.offs[j], self.Ns[j]
             ops.skinny_wgrad(dy_ext.data_ptr() + o * es, dy_ext.stride(0), x_ext.data_ptr() + (K + 8 * j) * es,
                              x_ext.stride(0), M, n_, self.dB[j], False, ops.BF16)
+        dp = self._drop()
+        if dp is not None:                                  # dA_j = (dy sB_j)^T drop_j(x): the mask is recomputed per Linear
+            for j in range(self.n):
+                ops.lora_wgrad_drop(x_ext.data_ptr(), x_ext.stride(0), dy_ext.data_ptr() + (N + 8 * j) * es, dy_ext.stride(0), M, K,
+                                    self.dA[j], ops.BF16, dp.word, self.site0 + j, dp.lora)
+            return
         j = 0
         while j < self.n:                                   # dA_j = (dy sB_j)^T x: two slots per pass over x when M is large
             q = dy_ext.data_ptr() + (N + 8 * j) * es
@@ -195,6 +223,7 @@ class T5Engine:
         self.emb = get(prefix + "shared.weight")          # fp32 [V, D] (embed_tokens is tied to it)
         assert self.emb.is_cuda
         self.groups = []
+        self.drop = None                                  # dropout.DropState while a train-mode step with dropout runs
 
         # Side stream (forked / joined inside the captured step): LoRA weight-gradient reductions and the decoder's
         # encoder-sized cross-attention K/V GEMMs run next to the latency-bound main chain.  MRB_OVERLAP=0 disables.
@@ -220,6 +249,7 @@ class T5Engine:
             L.update(ln0=_f(get(b + "layer.0.layer_norm.weight")), ln1=_f(get(b + "layer.1.layer_norm.weight")),
                      wi=grp([b + "layer.1.DenseReluDense.wi_0", b + "layer.1.DenseReluDense.wi_1"]),
                      wo=grp([b + "layer.1.DenseReluDense.wo"]))
+            L["stack"], L["li"] = dr.ENC, i
             self.enc.append(L)
         self.enc_bias = _f(get(prefix + "encoder.block.0.layer.0.SelfAttention.relative_attention_bias.weight"))
         self.enc_final_ln = _f(get(prefix + "encoder.final_layer_norm.weight"))
@@ -232,6 +262,7 @@ class T5Engine:
                      cq=grp([c + ".q"]), ckv=grp([c + ".k", c + ".v"]), co=grp([c + ".o"]),
                      wi=grp([b + "layer.2.DenseReluDense.wi_0", b + "layer.2.DenseReluDense.wi_1"]),
                      wo=grp([b + "layer.2.DenseReluDense.wo"]))
+            L["stack"], L["li"] = dr.DEC, i
             self.dec.append(L)
         self.dec_bias = _f(get(prefix + "decoder.block.0.layer.0.SelfAttention.relative_attention_bias.weight"))
         self.dec_final_ln = _f(get(prefix + "decoder.final_layer_norm.weight"))
@@ -309,19 +340,49 @@ class T5Engine:
     def _ext(self, M, K):
         return torch.empty((M, K + EXT), dtype=BF, device="cuda")
 
-    def _self_attn(self, qkv, out_ext, B, L, bias, kmask, causal, lse):
+    def _pdrop(self, site):
+        """Attention-probability dropout (modeling_t5.py:600) of one attention call: (seed word, site, p) or None."""
+        return self.drop.attn(site, self.drop.t5) if self.drop is not None else None
+
+    def _self_attn(self, qkv, out_ext, B, L, bias, kmask, causal, lse, site=None):
         d = self.d
         inner = d.t5_heads * d.d_kv
         rs = qkv.stride(0)
         ops.attention_fwd(qkv, qkv[:, inner:], qkv[:, 2 * inner:], out_ext, B, d.t5_heads, L, L, d.d_kv, 1.0,
                           (L * rs, rs), (L * rs, rs), (L * rs, rs), (L * out_ext.stride(0), out_ext.stride(0)),
-                          bias=bias, bias_zero=L - 1, kmask=kmask, causal=causal, lse=lse)
+                          bias=bias, bias_zero=L - 1, kmask=kmask, causal=causal, lse=lse, drop=self._pdrop(site))
 
-    def _grad_ext(self, dh, M):
-        """fp32 residual-stream gradient -> 16-bit extended dgrad operand [M, d_model + 32]."""
+    def _site(self, L, slot):
+        return dr.site(L["stack"], L["li"], slot)
+
+    def _p(self):
+        """T5's dropout_rate while a train-mode step with dropout runs, else 0."""
+        return self.drop.t5 if self.drop is not None else 0.0
+
+    def _grad_ext(self, dh, M, site=None):
+        """fp32 residual-stream gradient -> 16-bit extended dgrad operand [M, d_model + 32]; with `site` it is the gradient
+        of hidden + dropout(branch) w.r.t. the branch, i.e. dh under that site's mask."""
         dy = self._ext(M, self.d.d_model)
-        ops.cast2d(dh, dy, M, self.d.d_model)
+        if site is not None and self._p() > 0.0:
+            ops.dropout(dh, dy, M, self.d.d_model, self.drop.word, site, self._p())
+        else:
+            ops.cast2d(dh, dy, M, self.d.d_model)
         return dy
+
+    def _branch(self, grp, x_ext, M, h, site):
+        """h + dropout(Linear(x)) (modeling_t5.py:346,652,690) -> new fp32 residual stream.  Eval mode: the residual add is
+        the GEMM's epilogue; train mode: the branch leaves the GEMM in fp32 and one pass applies mask and add."""
+        out = torch.empty_like(h)
+        if self._p() > 0.0:
+            br = grp.forward(x_ext, M, out_dtype=torch.float32)
+            return ops.dropout_add(h, br, out, self.drop.word, site, self._p())
+        grp.forward(x_ext, M, out=out, resid=h)
+        return out
+
+    def _drop_inplace(self, t, rows, cols, site):
+        if self._p() > 0.0:
+            ops.dropout(t, t, rows, cols, self.drop.word, site, self._p())
+        return t
 
     def _ff(self, L, h, M, save):
         d = self.d
@@ -329,9 +390,11 @@ class T5Engine:
         ops.norm(h, L["ln_ff"], None, d.t5_ln_eps, 1, out_h=xn)
         ab = L["wi"].forward(xn, M)
         hm = self._ext(M, d.d_ff)
-        ops.gated_gelu_fwd(ab, hm, M, d.d_ff)
-        h2 = torch.empty_like(h)
-        L["wo"].forward(hm, M, out=h2, resid=h)
+        if self._p() > 0.0:
+            ops.gated_gelu_fwd_drop(ab, hm, M, d.d_ff, self.drop.word, self._site(L, dr.FF_INNER), self._p())
+        else:
+            ops.gated_gelu_fwd(ab, hm, M, d.d_ff)
+        h2 = self._branch(L["wo"], hm, M, h, self._site(L, dr.FF_RES))
         if save is not None:
             save.update(ff_x=h, ff_xn=xn, ff_ab=ab, ff_hm=hm)
         return h2
@@ -339,9 +402,12 @@ class T5Engine:
     def _ff_bwd(self, L, s, dh, M):
         """dh (fp32 residual-stream gradient) is updated in place."""
         d = self.d
-        dhm = L["wo"].backward(self._grad_ext(dh, M), s["ff_hm"], M)          # [M, d_ff]
+        dhm = L["wo"].backward(self._grad_ext(dh, M, self._site(L, dr.FF_RES)), s["ff_hm"], M)          # [M, d_ff]
         dab = self._ext(M, 2 * d.d_ff)
-        ops.gated_gelu_bwd(s["ff_ab"], dhm, dab, M, d.d_ff)
+        if self._p() > 0.0:
+            ops.gated_gelu_bwd_drop(s["ff_ab"], dhm, dab, M, d.d_ff, self.drop.word, self._site(L, dr.FF_INNER), self._p())
+        else:
+            ops.gated_gelu_bwd(s["ff_ab"], dhm, dab, M, d.d_ff)
         dxn = L["wi"].backward(dab, s["ff_xn"], M)
         ops.rmsnorm_bwd(s["ff_x"], L["ln_ff"], dxn, d.t5_ln_eps, dh)
 
@@ -353,6 +419,8 @@ class T5Engine:
         inner = d.t5_heads * d.d_kv
         bias = self._bias(self.enc_bias, L, L, True)
         h = x
+        if self._p() > 0.0:                                  # hidden_states = dropout(inputs_embeds), modeling_t5.py:1149
+            h = ops.dropout(x, torch.empty_like(x), M, d.d_model, self.drop.word, dr.site(dr.ENC, 0, dr.EMB), self._p())
         for li, layer in enumerate(self.enc):
             layer["ln_ff"] = layer["ln1"]
             s = {} if save is not None else None
@@ -362,9 +430,8 @@ class T5Engine:
             layer["qkv"].forward(xn, M, out=qkv[:, :3 * inner])
             ao = self._ext(M, d.d_model)
             lse = torch.empty((B, d.t5_heads, L), dtype=torch.float32, device="cuda") if save is not None else None
-            self._self_attn(qkv, ao, B, L, bias, kmask, False, lse)
-            h1 = torch.empty_like(h)
-            layer["o"].forward(ao, M, out=h1, resid=h)
+            self._self_attn(qkv, ao, B, L, bias, kmask, False, lse, self._site(layer, dr.SELF_P))
+            h1 = self._branch(layer["o"], ao, M, h, self._site(layer, dr.SELF_RES))
             if s is not None:
                 s.update(x=h, xn=xn, qkv=qkv, ao=ao, lse=lse)
             h = self._ff(layer, h1, M, s)
@@ -372,6 +439,7 @@ class T5Engine:
                 save.append(s)
         out = self._ext(M, d.d_model)
         ops.norm(h, self.enc_final_ln, None, d.t5_ln_eps, 1, out_h=out)
+        self._drop_inplace(out[:, :d.d_model], M, d.d_model, dr.site(dr.ENC, 0, dr.FINAL))      # modeling_t5.py:1258
         return out, h, bias
 
     def encoder_backward(self, saves, h_last, d_enc_out, kmask, B, L, bias):
@@ -379,12 +447,13 @@ class T5Engine:
         d = self.d
         M = B * L
         dh = torch.zeros((M, d.d_model), dtype=torch.float32, device="cuda")
+        self._drop_inplace(d_enc_out, M, d.d_model, dr.site(dr.ENC, 0, dr.FINAL))
         ops.rmsnorm_bwd(h_last, self.enc_final_ln, d_enc_out, d.t5_ln_eps, dh)
         inner = d.t5_heads * d.d_kv
         ws = torch.empty((B * d.t5_heads * L,), dtype=torch.float32, device="cuda")
         for layer, s in zip(reversed(self.enc), reversed(saves)):
             self._ff_bwd(layer, s, dh, M)
-            dao = layer["o"].backward(self._grad_ext(dh, M), s["ao"], M)       # [M, D] = dO of the attention
+            dao = layer["o"].backward(self._grad_ext(dh, M, self._site(layer, dr.SELF_RES)), s["ao"], M)   # [M, D] = dO of the attention
             qkv = s["qkv"]
             rs = qkv.stride(0)
             dqkv = torch.empty_like(qkv)
@@ -392,12 +461,12 @@ class T5Engine:
             ops.attention_bwd(qkv, qkv[:, inner:], qkv[:, 2 * inner:], s["ao"], dao, dqkv, dqkv[:, inner:],
                               dqkv[:, 2 * inner:], B, d.t5_heads, L, L, d.d_kv, 1.0, st, st, st,
                               (L * s["ao"].stride(0), s["ao"].stride(0)), (L * dao.stride(0), dao.stride(0)), s["lse"], ws,
-                              bias=bias, bias_zero=L - 1, kmask=kmask, causal=False)
+                              bias=bias, bias_zero=L - 1, kmask=kmask, causal=False, drop=self._pdrop(self._site(layer, dr.SELF_P)))
             dxn = layer["qkv"].backward(dqkv, s["xn"], M)
             ops.rmsnorm_bwd(s["x"], layer["ln0"], dxn, d.t5_ln_eps, dh)
             self.side_join()                                 # this layer's weight-gradient reductions are done
             s.clear()
-        return dh
+        return self._drop_inplace(dh, M, d.d_model, dr.site(dr.ENC, 0, dr.EMB))      # d inputs_embeds through the input dropout
 
     # ------------------------------------------------------------------ decoder (teacher forced)
     def decoder_forward(self, dec_ids, dmask, enc_ext, enc_kmask, B, Ld, Le, save=None):
@@ -406,6 +475,7 @@ class T5Engine:
         inner = d.t5_heads * d.d_kv
         h = torch.empty((M, d.d_model), dtype=torch.float32, device="cuda")
         ops.gather_rows(dec_ids.reshape(-1).to(torch.int32), self.emb, None, h)
+        self._drop_inplace(h, M, d.d_model, dr.site(dr.DEC, 0, dr.EMB))
         bias = self._bias(self.dec_bias, Ld, Ld, False)
         ckvs, ckv_ready = [], []
         if self.overlap:
@@ -427,9 +497,8 @@ class T5Engine:
             layer["qkv"].forward(xn, M, out=qkv[:, :3 * inner])
             ao = self._ext(M, d.d_model)
             lse = torch.empty((B, d.t5_heads, Ld), dtype=torch.float32, device="cuda") if save is not None else None
-            self._self_attn(qkv, ao, B, Ld, bias, dmask, True, lse)
-            h1 = torch.empty_like(h)
-            layer["o"].forward(ao, M, out=h1, resid=h)
+            self._self_attn(qkv, ao, B, Ld, bias, dmask, True, lse, self._site(layer, dr.SELF_P))
+            h1 = self._branch(layer["o"], ao, M, h, self._site(layer, dr.SELF_RES))
             # cross attention
             xn2 = self._ext(M, d.d_model)
             ops.norm(h1, layer["ln1"], None, d.t5_ln_eps, 1, out_h=xn2)
@@ -445,9 +514,9 @@ class T5Engine:
             lse2 = torch.empty((B, d.t5_heads, Ld), dtype=torch.float32, device="cuda") if save is not None else None
             qs, ks = cq.stride(0), ckv.stride(0)
             ops.attention_fwd(cq, ckv, ckv[:, inner:], co, B, d.t5_heads, Ld, Le, d.d_kv, 1.0, (Ld * qs, qs),
-                              (Le * ks, ks), (Le * ks, ks), (Ld * co.stride(0), co.stride(0)), kmask=enc_kmask, lse=lse2)
-            h2 = torch.empty_like(h)
-            layer["co"].forward(co, M, out=h2, resid=h1)
+                              (Le * ks, ks), (Le * ks, ks), (Ld * co.stride(0), co.stride(0)), kmask=enc_kmask, lse=lse2,
+                              drop=self._pdrop(self._site(layer, dr.CROSS_P)))
+            h2 = self._branch(layer["co"], co, M, h1, self._site(layer, dr.CROSS_RES))
             if s is not None:
                 s.update(x=h, xn=xn, qkv=qkv, ao=ao, lse=lse, x1=h1, xn2=xn2, cq=cq, ckv=ckv, co=co, lse2=lse2)
             h = self._ff(layer, h2, M, s)
@@ -455,6 +524,7 @@ class T5Engine:
                 save.append(s)
         out = self._ext(M, d.d_model)
         ops.norm(h, self.dec_final_ln, None, d.t5_ln_eps, 1, out_h=out)
+        self._drop_inplace(out[:, :d.d_model], M, d.d_model, dr.site(dr.DEC, 0, dr.FINAL))
         self.side_join()
         return out, h, bias
 
@@ -465,27 +535,28 @@ class T5Engine:
         M, Me = B * Ld, B * Le
         inner = d.t5_heads * d.d_kv
         dh = torch.zeros((M, d.d_model), dtype=torch.float32, device="cuda")
+        self._drop_inplace(d_out[:, :d.d_model], M, d.d_model, dr.site(dr.DEC, 0, dr.FINAL))
         ops.rmsnorm_bwd(h_last, self.dec_final_ln, d_out, d.t5_ln_eps, dh)
         d_enc = torch.zeros((Me, d.d_model), dtype=torch.float32, device="cuda")
         ws = torch.empty((B * d.t5_heads * Ld,), dtype=torch.float32, device="cuda")
         for layer, s in zip(reversed(self.dec), reversed(saves)):
             self._ff_bwd(layer, s, dh, M)
             # cross attention
-            dco = layer["co"].backward(self._grad_ext(dh, M), s["co"], M)
+            dco = layer["co"].backward(self._grad_ext(dh, M, self._site(layer, dr.CROSS_RES)), s["co"], M)
             cq, ckv = s["cq"], s["ckv"]
             dcq, dckv = torch.empty_like(cq), torch.empty_like(ckv)
             qs, ks = cq.stride(0), ckv.stride(0)
             ops.attention_bwd(cq, ckv, ckv[:, inner:], s["co"], dco, dcq, dckv, dckv[:, inner:], B, d.t5_heads, Ld, Le,
                               d.d_kv, 1.0, (Ld * qs, qs), (Le * ks, ks), (Le * ks, ks),
                               (Ld * s["co"].stride(0), s["co"].stride(0)), (Ld * dco.stride(0), dco.stride(0)), s["lse2"], ws,
-                              kmask=enc_kmask)
+                              kmask=enc_kmask, drop=self._pdrop(self._site(layer, dr.CROSS_P)))
             if self.overlap:
                 # encoder-sized dgrad + weight gradients of the cross K/V projection: side stream (in order, d_enc accumulates)
                 with self.side_block(hold=(dckv, enc_ext, d_enc)):
                     layer["ckv"].down(enc_ext, Me)
                     g = layer["ckv"]
                     ops.down32(dckv[:, :g.N], g.B_down, dckv[:, g.N:], Me)
-                    ops.gemm(dckv, g.ext_b, out=d_enc, resid=d_enc, M=Me)
+                    g.dgrad(dckv, Me, out=d_enc, resid=d_enc)
                     g._wgrads(dckv, enc_ext, Me)
             else:
                 layer["ckv"].down(enc_ext, Me)               # recompute this layer's x.A^T columns of the shared input
@@ -493,7 +564,7 @@ class T5Engine:
             dxn2 = layer["cq"].backward(dcq, s["xn2"], M)
             ops.rmsnorm_bwd(s["x1"], layer["ln1"], dxn2, d.t5_ln_eps, dh)
             # self attention
-            dao = layer["o"].backward(self._grad_ext(dh, M), s["ao"], M)
+            dao = layer["o"].backward(self._grad_ext(dh, M, self._site(layer, dr.SELF_RES)), s["ao"], M)
             qkv = s["qkv"]
             rs = qkv.stride(0)
             dqkv = torch.empty_like(qkv)
@@ -501,7 +572,7 @@ class T5Engine:
             ops.attention_bwd(qkv, qkv[:, inner:], qkv[:, 2 * inner:], s["ao"], dao, dqkv, dqkv[:, inner:],
                               dqkv[:, 2 * inner:], B, d.t5_heads, Ld, Ld, d.d_kv, 1.0, st, st, st,
                               (Ld * s["ao"].stride(0), s["ao"].stride(0)), (Ld * dao.stride(0), dao.stride(0)), s["lse"], ws,
-                              bias=bias, bias_zero=Ld - 1, kmask=dmask, causal=True)
+                              bias=bias, bias_zero=Ld - 1, kmask=dmask, causal=True, drop=self._pdrop(self._site(layer, dr.SELF_P)))
             dxn = layer["qkv"].backward(dqkv, s["xn"], M)
             ops.rmsnorm_bwd(s["x"], layer["ln0"], dxn, d.t5_ln_eps, dh)
             if not self.overlap:

@@ -583,3 +583,41 @@ def test_third_party_weight_files_load_into_reference_key_names(tmp_path, tiny_s
     m3 = Blip2T5.from_config({"t5_model": str(t5_dir), "vit_weights": vpath, "dims": TINY})
     assert torch.equal(m3.state_dict()["t5_model.encoder.block.1.layer.1.DenseReluDense.wi_0.weight"],
                        hf["encoder.block.1.layer.1.DenseReluDense.wi_0.weight"])
+
+
+def test_dropout_mask_header_matches_numpy_restatement(tmp_path):
+    """csrc/dropmask.cuh (what the kernels evaluate) compiled as plain C++ vs oracle/dropout.py (what the oracle evaluates)."""
+    import ctypes
+    import subprocess
+    import numpy as np
+    from oracle import dropout as od
+    src = tmp_path / "h.cpp"
+    src.write_text('#include "dropmask.cuh"\n'
+                   'extern "C" void draws(unsigned seed, unsigned site, int rows, int cols, unsigned char* out) {\n'
+                   '  const uint32_t key = mrb::drop_key(seed, site), ng = mrb::drop_groups(cols);\n'
+                   '  for (int r = 0; r < rows; ++r) for (int c = 0; c < cols; ++c)\n'
+                   '    out[(long long)r * cols + c] = (mrb::drop_word(key, (uint32_t)r * ng, c >> 2) >> (8 * (c & 3))) & 0xff;\n'
+                   '}\n'
+                   'extern "C" void keeps(unsigned seed, unsigned site, int rows, int cols, float p, unsigned char* out, float* scale) {\n'
+                   '  const mrb::DropSpec d = mrb::make_drop(nullptr, site, p);\n'
+                   '  const uint32_t key = mrb::drop_key(seed, d.site), ng = mrb::drop_groups(cols);\n'
+                   '  for (int r = 0; r < rows; ++r) for (int c = 0; c < cols; ++c)\n'
+                   '    out[(long long)r * cols + c] = mrb::drop_keep(mrb::drop_word(key, (uint32_t)r * ng, c >> 2), c, d.thr);\n'
+                   '  *scale = d.scale;\n'
+                   '}\n')
+    so = tmp_path / "h.so"
+    csrc = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "mr_blip_b200", "csrc")
+    subprocess.check_call(["g++", "-O1", "-shared", "-fPIC", "-x", "c++", "-I", csrc, str(src), "-o", str(so)])
+    lib = ctypes.CDLL(str(so))
+    for seed, site, rows, cols in ((0, 0, 3, 8), (123456789, od.site(od.DEC, 23, od.CROSS_P), 130, 2037),
+                                   (0xFFFFFFFF, od.lora_site("x.encoder.block.7.layer.1.DenseReluDense.wo"), 77, 5120),
+                                   (42, od.site(od.ENC, 5, od.SELF_P), 70000, 61)):          # row * groups wraps past 2^20 ...
+        out = np.empty((rows, cols), dtype=np.uint8)
+        lib.draws(ctypes.c_uint(seed), ctypes.c_uint(site), rows, cols, out.ctypes.data_as(ctypes.c_void_p))
+        assert (out == od.draws(seed, site, rows, cols)).all(), (seed, site, rows, cols)
+    for p in (0.1, 0.05, 0.0):
+        out = np.empty((64, 100), dtype=np.uint8)
+        sc = ctypes.c_float()
+        lib.keeps(ctypes.c_uint(5), ctypes.c_uint(9), 64, 100, ctypes.c_float(p), out.ctypes.data_as(ctypes.c_void_p), ctypes.byref(sc))
+        assert (out.astype(bool) == od.keep_mask(5, 9, 64, 100, p)).all()
+        assert sc.value == float(od.scale_of(p))
