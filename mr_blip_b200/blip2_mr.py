@@ -86,7 +86,8 @@ class BLIP2_MR(Blip2Base):
                  max_txt_len=200, apply_lemmatizer=False, input_time_format="seconds_integers",
                  interleave_data=True, frame_token_aggregation=None, task="qformer_freeze_lora",
                  num_frames_for_answer=4, resample_frames=False, dims: Dims = None, init_seed=1234,
-                 lora_b_std=0.0, state_dict=None, tokenizer=None, cuda_graphs=True, graph_bucket=(32, 8)):
+                 lora_b_std=0.0, state_dict=None, tokenizer=None, cuda_graphs=True, graph_bucket=(32, 8),
+                 train_dropout=None, dropout_seed=0):
         super().__init__()
         self.dims = d = dims or FULL
         assert img_size == d.img_size and num_query_token == d.num_query
@@ -152,6 +153,12 @@ class BLIP2_MR(Blip2Base):
         self._seen = {}                                      # shape signature -> times seen (survives LRU eviction)
         self._graph_pool = None
         self._in_device_step = False
+        # Train-mode dropout (the reference's train() step: Q-Former / T5 0.1, LoRA inputs 0.05; mr_blip_b200/dropout.py).  Written
+        # after round 1's GPU budget was spent -- compiled and reviewed but not yet run on hardware -- hence opt-in:
+        # train_dropout=True or MRB_TRAIN_DROPOUT=1.  Off: train() steps run the eval() arithmetic as before.
+        self.train_dropout = (os.environ.get("MRB_TRAIN_DROPOUT", "0") == "1") if train_dropout is None else bool(train_dropout)
+        self.dropout_seed = int(dropout_seed)
+        self.drop_state = None
 
     # ---------------------------------------------------------------------------------------------
     @classmethod
@@ -226,6 +233,9 @@ class BLIP2_MR(Blip2Base):
             self._g_projb = self._gflat[n + pw.numel():].view(pb.shape)
             self._grad_params = [p for p, _ in t5.param_grads()] + [pw, pb]
         vit, qf, t5 = self._engines
+        if self.train_dropout and self.drop_state is None:
+            from .dropout import DropState
+            self.drop_state = DropState(base_seed=self.dropout_seed)
         if self._in_device_step:                             # (captured) device step: LoRA re-pack is part of the step itself
             return vit, qf, t5
         vers = tuple(p._version for g in t5.groups for p in g.A_params + g.B_params)
@@ -456,7 +466,8 @@ class BLIP2_MR(Blip2Base):
         host = self._host_phase(samples, bucket=self.graph_bucket)
         video = self._video_of(samples)
         vdt = torch.uint8 if video.dtype == torch.uint8 else torch.float32
-        key = (host["b"], host["t"], host["Le"], host["Ld"], bool(self.frame_token_aggregation), vdt)
+        key = (host["b"], host["t"], host["Le"], host["Ld"], bool(self.frame_token_aggregation), vdt,
+               self._engines[2].drop is not None)
         st = self._steps.pop(key, None)
         if st is None:
             while len(self._steps) >= self.max_graphs:       # least recently used shape goes first
@@ -488,9 +499,20 @@ class BLIP2_MR(Blip2Base):
         self._lora_versions = None                           # the step re-packed LoRA itself; eager callers re-check
         return st.loss
 
+    def _set_dropout(self, on, advance=True):
+        """Switch the engines' train-mode dropout for the calls that follow; a step that uses it draws a new seed word first
+        (outside any graph capture: the captured kernels read the word from device memory)."""
+        _, qf, t5 = self.engines()
+        st = self.drop_state if (on and self.train_dropout) else None
+        qf.drop = t5.drop = st
+        if st is not None and advance:
+            st.advance()
+        return st is not None
+
     def forward_mr(self, samples, want_logits=False):
         """blip2_mr.py:433-570."""
         self.engines()
+        self._set_dropout(self.training)                     # nn.Dropout follows module.training, with or without grad
         need_grad = self.training and torch.is_grad_enabled()
         if need_grad and self.cuda_graphs and not want_logits:
             loss = self._graphed_step(samples).reshape(())
@@ -538,6 +560,7 @@ class BLIP2_MR(Blip2Base):
         if use_nucleus_sampling:
             raise NotImplementedError("nucleus sampling is not used by the moment-retrieval task (moment_retrieval.py:33-36)")
         _, _, t5 = self.engines()
+        self._set_dropout(False)                             # the task calls generate under model.eval() (moment_retrieval.py:33-36)
         frames, frames_atts = self.get_frame_embeddings_and_attentions(samples["video"])
         inputs, atts, video_prompt = self.prompt_concatenation(samples["timestamps"], samples["duration"], frames,
                                                                frames_atts, samples["video_prompt_end"],

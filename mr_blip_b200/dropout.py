@@ -42,11 +42,11 @@ class DropState:
     """Probabilities + the device word that holds the step seed.  `advance()` before every training step (outside any graph
     capture); `set_seed(v)` pins the word for a parity test against oracle.dropout.Dropper(seed=v)."""
 
-    def __init__(self, t5=0.1, lora=0.05, qformer=0.1, base_seed=0, attention=True):
+    def __init__(self, t5=0.1, lora=0.05, qformer=0.1, base_seed=0, attention=True, device="cuda"):
         self.t5, self.lora, self.qformer = float(t5), float(lora), float(qformer)
         self.attention = attention               # False: skip the attention-probability sites (A/B runs)
         self.base_seed, self.step = int(base_seed), 0
-        self.word = torch.zeros(1, dtype=torch.int32, device="cuda")
+        self.word = torch.zeros(1, dtype=torch.int32, device=device)
         self.seed = 0
         self.set_seed(_mix(self.base_seed))
 

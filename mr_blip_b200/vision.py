@@ -8,6 +8,7 @@ frozen under task=qformer_freeze_lora except t5_proj, so only forward kernels ex
 """
 import torch
 
+from . import dropout as dr
 from . import ops
 from .dims import Dims, qf_has_cross
 
@@ -148,6 +149,8 @@ class QFormerEngine:
         self.proj_w16 = None
         self.proj_b = None
         self.xattn_events = None     # set to a list to time the cross-attention path (K/V projection GEMM + attention cores)
+        self.drop = None             # dropout.DropState while a train-mode step with dropout runs (the frozen Q-Former stays in
+                                     # train mode in the reference: hidden / attention-probability dropout 0.1, Qformer.py:107,258,287,373)
 
     def set_t5_proj(self, weight, bias):
         """t5_proj is trainable (blip2_mr.py:291 only sets an attribute on the Module): refresh per step."""
@@ -156,11 +159,20 @@ class QFormerEngine:
         ops.cast_to(weight.detach().contiguous(), self.proj_w16)
         self.proj_b = bias.detach()
 
-    def _attn_block(self, ctx, o, ln, h, h16, M):
+    def _attn_block(self, ctx, o, ln, h, h16, M, site=None):
+        """LayerNorm(dropout(dense(ctx)) + h) (BertSelfOutput / BertOutput, Qformer.py:278-289,366-375) -> h, h16 in place."""
         d = self.d
         t = torch.empty((M, d.qf_hidden), dtype=torch.float32, device="cuda")
-        ops.gemm(ctx, o[0], out=t, bias=o[1], resid=h)
+        p = self.drop.qformer if self.drop is not None else 0.0
+        if p > 0.0:
+            br = ops.gemm(ctx, o[0], bias=o[1], out_dtype=torch.float32)
+            ops.dropout_add(h, br, t, self.drop.word, site, p)
+        else:
+            ops.gemm(ctx, o[0], out=t, bias=o[1], resid=h)
         ops.norm(t, ln[0], ln[1], d.qf_ln_eps, 0, out_f32=h, out_h=h16)
+
+    def _pdrop(self, site):
+        return self.drop.attn(site, self.drop.qformer) if self.drop is not None else None
 
     def forward(self, vit_out, frames, return_all=False):
         """vit_out fp32 [F*257, 1408] -> (last_hidden fp32 [F*32, 768], fp16 copy, image_embeds fp16)."""
@@ -182,6 +194,8 @@ class QFormerEngine:
         q0 = torch.empty((nq, Hq), dtype=torch.float32, device="cuda")
         ops.norm(self.query_tokens, self.emb_ln[0], self.emb_ln[1], d.qf_ln_eps, 0, out_f32=q0)
         h = q0.unsqueeze(0).expand(frames, nq, Hq).reshape(M, Hq).contiguous()
+        if self.drop is not None and self.drop.qformer > 0.0:        # every frame draws its own mask over the shared embeddings
+            ops.dropout(h, h, M, Hq, self.drop.word, dr.site(dr.QF, 0, dr.EMB), self.drop.qformer)
         h16 = torch.empty((M, Hq), dtype=H16, device="cuda")
         ops.cast_to(h, h16)
         qkv = torch.empty((M, 3 * Hq), dtype=H16, device="cuda")
@@ -189,12 +203,12 @@ class QFormerEngine:
         qc = torch.empty((M, Hq), dtype=H16, device="cuda")
         inter = torch.empty((M, d.qf_inter), dtype=H16, device="cuda")
         outs = [h.clone()] if return_all else None
-        for L in self.layers:
+        for li, L in enumerate(self.layers):
             ops.gemm(h16, L["self_qkv_w"], out=qkv, bias=L["self_qkv_b"])
             rs = 3 * Hq
             ops.attention_fwd(qkv, qkv[:, Hq:], qkv[:, 2 * Hq:], ctx, frames, heads, nq, nq, hd, hd ** -0.5,
-                              (nq * rs, rs), (nq * rs, rs), (nq * rs, rs), (nq * Hq, Hq))
-            self._attn_block(ctx, L["self_o"], L["self_ln"], h, h16, M)
+                              (nq * rs, rs), (nq * rs, rs), (nq * rs, rs), (nq * Hq, Hq), drop=self._pdrop(dr.site(dr.QF, li, dr.SELF_P)))
+            self._attn_block(ctx, L["self_o"], L["self_ln"], h, h16, M, dr.site(dr.QF, li, dr.SELF_RES))
             c = L["cross"]
             if c is not None:
                 ops.gemm(h16, c["q"][0], out=qc, bias=c["q"][1])
@@ -202,12 +216,13 @@ class QFormerEngine:
                 if ev is not None:
                     e0 = torch.cuda.Event(enable_timing=True); e0.record()
                 ops.attention_fwd(qc, kbase, kbase[:, Hq:], ctx, frames, heads, nq, T, hd, hd ** -0.5,
-                                  (nq * Hq, Hq), (T * kv_rs, kv_rs), (T * kv_rs, kv_rs), (nq * Hq, Hq))
+                                  (nq * Hq, Hq), (T * kv_rs, kv_rs), (T * kv_rs, kv_rs), (nq * Hq, Hq),
+                                  drop=self._pdrop(dr.site(dr.QF, li, dr.CROSS_P)))
                 if ev is not None:
                     e1 = torch.cuda.Event(enable_timing=True); e1.record(); ev.append((e0, e1))
-                self._attn_block(ctx, c["o"], c["ln"], h, h16, M)
+                self._attn_block(ctx, c["o"], c["ln"], h, h16, M, dr.site(dr.QF, li, dr.CROSS_RES))
             ops.gemm(h16, L["ffn_i"][0], out=inter, bias=L["ffn_i"][1], gelu=True)
-            self._attn_block(inter, L["ffn_o"], L["ffn_ln"], h, h16, M)
+            self._attn_block(inter, L["ffn_o"], L["ffn_ln"], h, h16, M, dr.site(dr.QF, li, dr.FF_RES))
             if return_all:
                 outs.append(h.clone())
         if return_all:

@@ -621,3 +621,99 @@ def test_dropout_mask_header_matches_numpy_restatement(tmp_path):
         lib.keeps(ctypes.c_uint(5), ctypes.c_uint(9), 64, 100, ctypes.c_float(p), out.ctypes.data_as(ctypes.c_void_p), ctypes.byref(sc))
         assert (out.astype(bool) == od.keep_mask(5, 9, 64, 100, p)).all()
         assert sc.value == float(od.scale_of(p))
+
+
+def _t5_case(d):
+    g = torch.Generator().manual_seed(11)
+    emb = torch.randn(2, 40, d.d_model, generator=g) * 2.0
+    mask = torch.ones(2, 40, dtype=torch.long)
+    mask[1, 33:] = 0
+    labels = torch.randint(2, 1000, (2, 7), generator=g)
+    labels[:, -1] = 1
+    labels[1, 5:] = -100
+    labels[1, 4] = 1
+    return emb, mask, labels
+
+
+def _relfro(got, want):
+    got, want = torch.as_tensor(got).float(), torch.as_tensor(want).float()
+    assert got.shape == want.shape, (got.shape, want.shape)
+    return ((got - want).norm() / want.norm().clamp_min(1e-30)).item()
+
+
+@pytest.mark.parametrize("mode", ["eval", "train_dropout", "train_dropout_no_attention_sites"])
+def test_t5_engine_host_logic_with_emulated_ops(tiny_sd, monkeypatch, mode):
+    """T5Engine (op sequence, extended-K LoRA layout, the hand-written backward, and in train mode every dropout site incl. the
+    LoRA-dropout decomposition dx = dy W + sum_j mask_j (dy sB_j) A_j) run on the CPU over torch stand-ins of the C-ABI ops
+    (tests/cpu_ops_emulation.py) against the oracle: loss, logits, d inputs_embeds and every LoRA gradient.  The stand-ins keep
+    the buffers' 16-bit types, so the tolerances are those of the GPU tests."""
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    import cpu_ops_emulation as emu
+    from mr_blip_b200.dims import TINY, T5_PREFIX
+    from mr_blip_b200.dropout import DropState
+    from oracle import t5 as ot5
+    from oracle.dropout import Dropper
+    monkeypatch.setenv("MRB_OVERLAP", "0")
+    t5mod = emu.load_engine_module("t5")
+    params = {k: v.clone() for k, v in tiny_sd.items()}
+    eng = t5mod.T5Engine(TINY, params.__getitem__)
+    emb, mask, labels = _t5_case(TINY)
+    dmask = (labels != -100).long()
+    drop = None
+    if mode != "eval":
+        eng.drop = DropState(device="cpu", attention=(mode == "train_dropout"))
+        seed = eng.drop.set_seed(0xC0FFEE11)
+        drop = Dropper(seed)
+        if mode != "train_dropout":
+            inner = Dropper(seed)
+            drop = lambda x, site, p: x if (site & 31) in (1, 3) else inner(x, site, p)      # SELF_P / CROSS_P sites off
+            drop.t5, drop.lora, drop.qformer = inner.t5, inner.lora, inner.qformer
+    eng.zero_grads()
+    out = eng.loss(emb.clone(), mask, labels, dmask, backward=True, want_logits=True)
+    sd = dict(tiny_sd)
+    leaves = {k: sd[k].clone().requires_grad_(True) for k in sd if "lora_" in k}
+    sd.update(leaves)
+    e = emb.clone().requires_grad_(True)
+    o = ot5.t5_forward(sd, TINY, e, mask, labels, dmask, drop=drop)
+    o["loss"].backward()
+    assert abs(out["loss"].item() - o["loss"].item()) < 5e-3
+    assert _relfro(out["logits"], o["logits"]) < 2e-2
+    assert _relfro(out["d_inputs_embeds"], e.grad) < 4e-2
+    grads = {id(p): g for p, g in eng.param_grads()}
+    for k, leaf in leaves.items():
+        assert _relfro(grads[id(params[k])], leaf.grad) < 4e-2, k
+    if mode != "eval":
+        with torch.no_grad():
+            ev = ot5.t5_forward(dict(tiny_sd), TINY, emb, mask, labels, dmask)
+        assert abs(ev["loss"].item() - o["loss"].item()) > 1e-2          # the masks matter: the comparison above can fail
+
+
+@pytest.mark.parametrize("train", [False, True])
+def test_qformer_engine_host_logic_with_emulated_ops(tiny_sd, train):
+    """QFormerEngine (ln_vision, batched cross K/V projection, 12 layers, in train mode the frozen Q-Former's hidden and
+    attention-probability dropout) on the CPU over the op stand-ins against the oracle."""
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    import cpu_ops_emulation as emu
+    from mr_blip_b200.dims import TINY
+    from mr_blip_b200.dropout import DropState
+    from oracle import qformer as oqf, vit as ovit
+    from oracle.dropout import Dropper
+    vmod = emu.load_engine_module("vision")
+    params = {k: v.clone() for k, v in tiny_sd.items()}
+    eng = vmod.QFormerEngine(TINY, params.__getitem__)
+    frames = 3
+    g = torch.Generator().manual_seed(5)
+    vit_out = torch.randn(frames * TINY.vit_tokens, TINY.vit_width, generator=g)
+    drop = None
+    if train:
+        eng.drop = DropState(device="cpu")
+        drop = Dropper(eng.drop.set_seed(0xBEEF))
+    h, h16 = eng.forward(vit_out, frames)
+    with torch.no_grad():
+        ie = ovit.ln_vision(tiny_sd, TINY, vit_out.view(frames, TINY.vit_tokens, -1))
+        want = oqf.qformer_forward(tiny_sd, TINY, ie, drop=drop)
+        other = oqf.qformer_forward(tiny_sd, TINY, ie, drop=None if train else Dropper(1))
+    assert _relfro(h.view(frames, TINY.num_query, -1), want) < 2e-3
+    assert _relfro(h.view(frames, TINY.num_query, -1), other) > 2e-2
