@@ -171,7 +171,9 @@ def run_b200(args):
     d = FULL
     t_build = time.time()
     sd = init_state_dict(d, seed=1234, lora_b_std=0.02, device="cuda")
-    model = BLIP2_MR(dims=d, state_dict=sd).to(dev).train()
+    # --train-dropout (or MRB_TRAIN_DROPOUT=1): the reference's train() dropout (Q-Former / T5 0.1, LoRA inputs 0.05) inside the
+    # step; off by default until that path has run on hardware, and the workload string says which one ran
+    model = BLIP2_MR(dims=d, state_dict=sd, train_dropout=True if args.train_dropout else None).to(dev).train()
     del sd
     trainable = [p for p in model.parameters() if p.requires_grad]
     opt = torch.optim.AdamW(trainable, lr=1e-5, weight_decay=0.05, fused=True)
@@ -242,8 +244,10 @@ def run_b200(args):
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16", "data": "synthetic",
             "config": {"workload": "QVH: batch 4 per GPU, 60 frames, 32 Q-Former queries, ViT-g (fp16) + FlanT5-XL (bf16) "
-                                   "LoRA r=8, fwd+bwd + fused AdamW step, eval-mode dropout; the device half of the step "
-                                   "replays one captured CUDA graph",
+                                   "LoRA r=8, fwd+bwd + fused AdamW step, %s; the device half of the step "
+                                   "replays one captured CUDA graph" % (
+                                       "train-mode dropout (Q-Former / T5 0.1, LoRA 0.05, counter-hash masks drawn per step)"
+                                       if model.train_dropout else "eval-mode dropout"),
                        "l2": "working set per step (GBs of activations, 144.5 MB frame tensor) exceeds the 126 MB L2",
                        "parallelism": "dp%d" % world, "weights": "seeded random init (device RNG)",
                        "model_build_s": round(build_s, 1)},
@@ -316,6 +320,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--cpu-frames", type=int, default=4, help="frames of one clip the CPU baseline sample runs")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--train-dropout", action="store_true", help="run the step with train-mode dropout (mr_blip_b200/dropout.py)")
     args = ap.parse_args()
     _reserve_stdout()
     if args.impl == "reference":

@@ -175,7 +175,8 @@ class BLIP2_MR(Blip2Base):
                     interleave_data=get("interleave_data", True), frame_token_aggregation=get("frame_token_aggregation", None),
                     task=get("task", "qformer_freeze_lora"), num_frames_for_answer=get("num_frames_for_answer", 4),
                     resample_frames=get("resample_frames", False), dims=get("dims", None),
-                    init_seed=get("init_seed", 1234), lora_b_std=get("lora_b_std", 0.0))
+                    init_seed=get("init_seed", 1234), lora_b_std=get("lora_b_std", 0.0),
+                    train_dropout=get("train_dropout", None), dropout_seed=get("dropout_seed", 0))
         # third-party weights the reference fetches from hubs, from local files here: `t5_model` may be a transformers
         # directory (as it may be for from_pretrained), `vit_weights` an eva_vit_g.pth
         from . import weights
@@ -235,7 +236,9 @@ class BLIP2_MR(Blip2Base):
         vit, qf, t5 = self._engines
         if self.train_dropout and self.drop_state is None:
             from .dropout import DropState
-            self.drop_state = DropState(base_seed=self.dropout_seed)
+            import torch.distributed as tdist
+            rank = tdist.get_rank() if (tdist.is_available() and tdist.is_initialized()) else 0
+            self.drop_state = DropState(base_seed=self.dropout_seed + rank)      # per-rank masks (reference: train.py:57-58, seed + get_rank())
         if self._in_device_step:                             # (captured) device step: LoRA re-pack is part of the step itself
             return vit, qf, t5
         vers = tuple(p._version for g in t5.groups for p in g.A_params + g.B_params)

@@ -2,6 +2,8 @@
 # First GPU call of the next round: everything that was written after round 1's GPU budget ran out, in dependency order.
 #   1. the default GPU suite (must still be green: gemm.cu host dispatch, ops.py and config.py changed since the last GPU run)
 #   2. the experimental split-K tests (tests/test_experimental_gpu.py)
+#   2b. the train-mode dropout path (tests/test_dropout_gpu.py: every kernel against the oracle's masks, engines, model, graphs),
+#       then the bench line with it -- if green: make train_dropout the default and the bench workload
 #   3. small-shape sweep without / with split-K, and the bench line without / with it
 # If 2 is green and 3 shows the gain: flip ops.SPLITK's default, move the tests into tests/test_kernels_gpu.py.
 set -u
@@ -11,6 +13,10 @@ mkdir -p $O
 tail -3 $O/pytest.log
 ( MRB_TEST_EXPERIMENTAL=1 timeout 300 python -m pytest tests/test_experimental_gpu.py -m gpu -q 2>&1 | tail -25 ) > $O/pytest_experimental.log 2>&1
 tail -5 $O/pytest_experimental.log
+( MRB_TEST_EXPERIMENTAL=1 timeout 900 python -m pytest tests/test_dropout_gpu.py -m gpu -q 2>&1 | tail -60 ) > $O/pytest_dropout.log 2>&1
+tail -8 $O/pytest_dropout.log
+( timeout 400 python bench.py --steps 8 --warmup 3 --train-dropout ) > $O/bench_dropout.json 2> $O/bench_dropout.err
+cut -c1-200 $O/bench_dropout.json
 ( timeout 200 python tools/gemm_sweep.py default $O/sweep_default.json ) > $O/sweep_default.log 2>&1
 ( MRB_GEMM_SPLITK=1 timeout 200 python tools/gemm_sweep.py splitk $O/sweep_splitk.json ) > $O/sweep_splitk.log 2>&1
 grep -h "dec_\|down32\|lm_head" $O/sweep_default.log $O/sweep_splitk.log | cut -c1-220
