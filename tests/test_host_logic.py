@@ -717,3 +717,133 @@ def test_qformer_engine_host_logic_with_emulated_ops(tiny_sd, train):
         other = oqf.qformer_forward(tiny_sd, TINY, ie, drop=None if train else Dropper(1))
     assert _relfro(h.view(frames, TINY.num_query, -1), want) < 2e-3
     assert _relfro(h.view(frames, TINY.num_query, -1), other) > 2e-2
+
+
+@pytest.fixture(scope="module")
+def dropout_kernels_on_host(tmp_path_factory):
+    """csrc/dropout.cu (the kernel source itself, unmodified) compiled as C++20 over tests/cuda_host_shim/common.cuh: one OS
+    thread per CUDA thread, barriers for __syncthreads / warp shuffles.  -> ctypes library with the C-ABI entry points."""
+    import ctypes
+    import shutil
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    d = tmp_path_factory.mktemp("shim")
+    shutil.copy(os.path.join(root, "tests", "cuda_host_shim", "common.cuh"), d)
+    for f in ("dropout.cu", "dropmask.cuh"):
+        shutil.copy(os.path.join(root, "mr_blip_b200", "csrc", f), d)
+    so = os.path.join(d, "dropout_host.so")
+    subprocess.check_call(["g++", "-std=c++20", "-O1", "-pthread", "-shared", "-fPIC", "-Wno-unknown-pragmas", "-x", "c++",
+                           os.path.join(d, "dropout.cu"), "-o", so])
+    return ctypes.CDLL(so)
+
+
+def _bf16(t):
+    return t.to(torch.bfloat16)
+
+
+def _cp(t):
+    import ctypes
+    return ctypes.c_void_p(t.data_ptr())
+
+
+def test_dropout_kernel_source_runs_on_host_shim_and_matches_oracle(dropout_kernels_on_host):
+    """Index arithmetic, shared-memory layouts, shuffles and atomics of every kernel in csrc/dropout.cu, executed on the CPU
+    through the host shim, against the oracle's masks (what tests/test_dropout_gpu.py checks on the device)."""
+    import ctypes
+    from oracle import dropout as od
+    lib = dropout_kernels_on_host
+    c_i, c_ll, c_u, c_f = ctypes.c_int, ctypes.c_longlong, ctypes.c_uint, ctypes.c_float
+    seed = 0x9E3779B1
+    word = torch.tensor([seed - (1 << 32)], dtype=torch.int32)
+    BF, F32 = 1, 2
+
+    def mask(site, rows, cols, p):
+        return torch.from_numpy(od.keep_mask(seed, site, rows, cols, p)).float() * float(od.scale_of(p))
+
+    g = torch.Generator().manual_seed(3)
+    # ---- mrb_dropout: fp32 -> fp32, fp32 -> bf16, bf16 in place on a strided buffer
+    rows, cols, site, p = 37, 264, 0x1234, 0.1
+    x = torch.randn(rows, cols, generator=g)
+    m = mask(site, rows, cols, p)
+    out = torch.empty_like(x)
+    assert lib.mrb_dropout(_cp(x), c_ll(cols), _cp(out), c_ll(cols), rows, cols, F32, F32, _cp(word), c_u(site), c_f(p), None) == 0
+    assert torch.equal(out, x * m)
+    o16 = torch.empty((rows, cols), dtype=torch.bfloat16)
+    assert lib.mrb_dropout(_cp(x), c_ll(cols), _cp(o16), c_ll(cols), rows, cols, F32, BF, _cp(word), c_u(site), c_f(p), None) == 0
+    assert torch.equal(o16, _bf16(x * m))
+    big = torch.zeros((rows, cols + 32), dtype=torch.bfloat16)
+    big[:, :cols] = _bf16(x)
+    want = _bf16(big[:, :cols].float() * m)
+    assert lib.mrb_dropout(_cp(big), c_ll(cols + 32), _cp(big), c_ll(cols + 32), rows, cols, BF, BF, _cp(word), c_u(site), c_f(p), None) == 0
+    assert torch.equal(big[:, :cols], want) and big[:, cols:].abs().max().item() == 0
+    assert lib.mrb_dropout(_cp(x), c_ll(cols), _cp(out), c_ll(cols), rows, cols - 2, F32, F32, _cp(word), c_u(site), c_f(p), None) == -1
+    # ---- mrb_dropout_add
+    r = torch.randn(rows, cols, generator=g)
+    assert lib.mrb_dropout_add(_cp(r), _cp(x), _cp(out), rows, cols, _cp(word), c_u(site), c_f(p), None) == 0
+    assert torch.allclose(out, r + x * m, rtol=1e-6, atol=1e-6)
+    # ---- gated GELU with the inner dropout, forward and backward
+    M, Fd, site = 9, 512, 77
+    ab = _bf16(torch.randn(M, 2 * Fd, generator=g))
+    m = mask(site, M, Fd, p)
+    a, b = ab[:, :Fd].float().requires_grad_(True), ab[:, Fd:].float().requires_grad_(True)
+    want = torch.nn.functional.gelu(a) * b * m
+    h = torch.zeros((M, Fd + 32), dtype=torch.bfloat16)
+    assert lib.mrb_gated_gelu_fwd_drop(_cp(ab), _cp(h), M, Fd, c_ll(Fd + 32), BF, _cp(word), c_u(site), c_f(p), None) == 0
+    assert _relfro(h[:, :Fd], want) < 4e-3 and h[:, Fd:].abs().max().item() == 0
+    dh = _bf16(torch.randn(M, Fd, generator=g))
+    want.backward(dh.float())
+    dab = torch.zeros((M, 2 * Fd + 32), dtype=torch.bfloat16)
+    assert lib.mrb_gated_gelu_bwd_drop(_cp(ab), _cp(dh), c_ll(Fd), _cp(dab), c_ll(2 * Fd + 32), M, Fd, BF, _cp(word), c_u(site), c_f(p), None) == 0
+    assert _relfro(dab[:, :Fd], a.grad) < 6e-3 and _relfro(dab[:, Fd:2 * Fd], b.grad) < 6e-3
+    # ---- LoRA input dropout: forward down-projection (both lane layouts), dA, dx (16-bit and fp32)
+    p, site0 = 0.05, 0x2108
+    for M, K, nlin in ((21, 520, 3), (2051, 264, 2), (70, 256, 1)):          # K not a multiple of the 256-column tile; M over / under 2048
+        x_ext = torch.zeros((M, K + 32), dtype=torch.bfloat16)
+        x_ext[:, :K] = _bf16(torch.randn(M, K, generator=g))
+        A = torch.zeros((32, K), dtype=torch.bfloat16)
+        A[:8 * nlin] = _bf16(torch.randn(8 * nlin, K, generator=g) / K ** 0.5)
+        xf = x_ext[:, :K].float()
+        masks = [mask(site0 + j, M, K, p) for j in range(nlin)]
+        x_ext[:, K:] = 7.0
+        u = x_ext[:, K:]
+        assert lib.mrb_lora_down_drop(_cp(x_ext), c_ll(K + 32), _cp(A), c_ll(K), M, K, nlin, ctypes.c_void_p(u.data_ptr()), c_ll(K + 32),
+                                      BF, _cp(word), c_u(site0), c_f(p), None) == 0
+        for j in range(nlin):
+            assert _relfro(u[:, 8 * j:8 * j + 8], (xf * masks[j]) @ A[8 * j:8 * j + 8].float().t()) < 5e-3, (M, K, j)
+        assert u[:, 8 * nlin:].abs().max().item() == 0
+        q = torch.zeros((M, 32), dtype=torch.bfloat16)
+        q[:, :8 * nlin] = _bf16(torch.randn(M, 8 * nlin, generator=g))
+        for j in range(nlin):
+            dA = torch.ones((8, K))
+            assert lib.mrb_lora_wgrad_drop(_cp(x_ext), c_ll(K + 32), ctypes.c_void_p(q.data_ptr() + 16 * j), c_ll(32), M, K, _cp(dA), BF,
+                                           _cp(word), c_u(site0 + j), c_f(p), None) == 0
+            assert _relfro(dA - 1.0, q[:, 8 * j:8 * j + 8].float().t() @ (xf * masks[j])) < 2e-3, (M, K, j)
+        want = sum(masks[j] * (q[:, 8 * j:8 * j + 8].float() @ A[8 * j:8 * j + 8].float()) for j in range(nlin))
+        base = torch.randn(M, K, generator=g)
+        d32 = base.clone()
+        assert lib.mrb_lora_dx_drop(_cp(q), c_ll(32), _cp(A), c_ll(K), nlin, _cp(d32), c_ll(K), F32, M, K, BF, _cp(word), c_u(site0),
+                                    c_f(p), None) == 0
+        assert _relfro(d32 - base, want) < 1e-3, (M, K)
+        d16 = torch.zeros((M, K + 32), dtype=torch.bfloat16)
+        d16[:, :K] = _bf16(base)
+        assert lib.mrb_lora_dx_drop(_cp(q), c_ll(32), _cp(A), c_ll(K), nlin, _cp(d16), c_ll(K + 32), BF, M, K, BF, _cp(word), c_u(site0),
+                                    c_f(p), None) == 0
+        assert _relfro(d16[:, :K], _bf16(base).float() + want) < 4e-3 and d16[:, K:].abs().max().item() == 0
+
+
+def test_swar_keep_compare_of_the_tcgen05_attention_kernels():
+    """attention_tc.cu drop_pair_masks / attention_tc_bwd.cu: bit 7 of every byte of ((w >> 1) & 0x7f7f7f7f | 0x80808080) - (thr / 2)
+    * 0x01010101 must equal `draw >= thr` for that byte when thr is even (restated here; PRMT then spreads those sign bits)."""
+    import numpy as np
+    from oracle import dropout as od
+    rng = np.random.default_rng(0)
+    w = np.concatenate([rng.integers(0, 1 << 32, 200000, dtype=np.uint64), np.array([0, 0xFFFFFFFF, 0x19191919, 0x1a1a1a1a, 0x1b1b1b1b,
+                                                                                     0x00ff19ff, 0x1aff001a], dtype=np.uint64)])
+    for p in (0.1, 0.5, 0.0):
+        thr = od.thr_of(p)
+        assert thr % 2 == 0
+        t = ((((w >> np.uint64(1)) & np.uint64(0x7f7f7f7f)) | np.uint64(0x80808080)) - np.uint64((thr // 2) * 0x01010101)) & np.uint64(0xFFFFFFFF)
+        for i in range(4):
+            draw = (w >> np.uint64(8 * i)) & np.uint64(0xFF)
+            assert (((t >> np.uint64(8 * i + 7)) & np.uint64(1)) == (draw >= thr)).all(), (p, i)
+    assert od.thr_of(0.05) % 2 == 1          # LoRA's 0.05 is odd: it never reaches these kernels (byte compare in csrc/dropout.cu)
