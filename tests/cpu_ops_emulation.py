@@ -21,6 +21,8 @@ from oracle import dropout as od
 F16, BF16, F32 = 0, 1, 2
 _TDT = {F16: torch.float16, BF16: torch.bfloat16, F32: torch.float32}
 SPLITK = False
+USE_TC_ATTENTION = False          # VitEngine then sends all 257 query rows through one attention_fwd call
+GEMM_PROFILE = None
 INT_MIN = -(1 << 31)
 
 
@@ -53,7 +55,6 @@ def _mask(word, site, rows, cols, p):
 
 # ---------------------------------------------------------------------------------------------- GEMM family
 def gemm(a, b, out=None, bias=None, gelu=False, resid=None, out_dtype=None, row_group=0, out_rows=None, force_bn=0, M=None, K=None):
-    assert row_group == 0
     M = a.shape[0] if M is None else M
     K = a.shape[1] if K is None else K
     N = b.shape[0]
@@ -62,12 +63,65 @@ def gemm(a, b, out=None, bias=None, gelu=False, resid=None, out_dtype=None, row_
         y = y + bias
     if gelu:
         y = F.gelu(y)
+    if row_group > 0:                                        # patch embed: token 0 of every frame is the cls row, written elsewhere
+        m = torch.arange(M)
+        orow = (m // row_group) * (row_group + 1) + 1 + m % row_group
+        if resid is not None:
+            y = y + resid[1 + m % row_group, :N]
+        out[orow, :N] = y.to(out.dtype)
+        return out
     if resid is not None:
         y = y + resid[:M, :N]
     if out is None:
         out = torch.empty((out_rows or M, N), dtype=out_dtype or a.dtype)
     out[:M, :N] = y.to(out.dtype)
     return out
+
+
+def patchify(img, out, img_size, patch):
+    Fr, g = img.shape[0], img_size // patch
+    x = img.view(Fr, 3, g, patch, g, patch).permute(0, 2, 4, 1, 3, 5).reshape(Fr * g * g, 3 * patch * patch)
+    out.zero_()
+    out[:, :3 * patch * patch] = x.to(out.dtype)
+
+
+def cls_pos(cls, pos, x, frames, tokens, C):
+    x.view(frames, tokens, C)[:, 0] = cls + pos[0]
+
+
+def scatter_frames(idx, dout, dframes):
+    idx = idx.long()
+    neg = (idx < 0) & (idx != INT_MIN)
+    dframes.index_add_(0, -(idx[neg] + 1), dout[neg])
+
+
+def group_mean(x, out, groups, n, C):
+    out.copy_(x.view(groups, n, C).mean(1))
+
+
+def group_mean_bwd(dout, dx, groups, n, C):
+    dx.view(groups, n, C).copy_((dout / n)[:, None, :].expand(groups, n, C))
+
+
+def colsum(x, out):
+    out += x.sum(0)
+
+
+def axpby(x, y, a, b):
+    y.copy_(a * x + b * y)
+
+
+def lora_pack(table, n, blocks_per_linear):
+    """LoraPackDesc records (csrc/elementwise.cu): A [8,K] / B [N,8] fp32 -> their four bf16 operand slots."""
+    for rec in table.tolist():
+        a_p, b_p, ext_p, ext_ld, bd_p, bd_ld, ad_p, ad_ld, eb_p, eb_ld, K, N, sbits = rec
+        scale = float(np.int64(sbits).view(np.float64))
+        A = _from_ptr(a_p, 8, K, K, torch.float32)
+        B = _from_ptr(b_p, N, 8, 8, torch.float32) * scale
+        _from_ptr(ext_p, N, 8, ext_ld, torch.bfloat16).copy_(B.to(torch.bfloat16))
+        _from_ptr(bd_p, 8, N, bd_ld, torch.bfloat16).copy_(B.t().to(torch.bfloat16))
+        _from_ptr(ad_p, 8, K, ad_ld, torch.bfloat16).copy_(A.to(torch.bfloat16))
+        _from_ptr(eb_p, K, 8, eb_ld, torch.bfloat16).copy_(A.t().to(torch.bfloat16))
 
 
 def down32(x, W, out, M):
@@ -284,14 +338,25 @@ def load_engine_module(name):
     import sys
     path = os.path.join(os.path.dirname(mr_blip_b200.__file__), name + ".py")
     src = open(path).read()
-    for a, b in (('device="cuda"', 'device="cpu"'), ('.to("cuda")', '.to("cpu")'), ('.to(device="cuda"', '.to(device="cpu"'),
-                 ("assert self.emb.is_cuda", "pass"), ("torch.cuda.Stream()", "_NoStream()")):
+    for a, b in (('device="cuda"', 'device="cpu"'), ('.to("cuda"', '.to("cpu"'), ('.to(device="cuda"', '.to(device="cpu"'),
+                 ("assert self.emb.is_cuda", "pass"), ("torch.cuda.Stream()", "_NoStream()"),
+                 ("torch.cuda.is_available()", "True"), ('self.device.type != "cuda"', "False"), (".pin_memory()", ""),
+                 ('@registry.register_model("blip2_mr")', ""), ("DropState(base_seed=", 'DropState(device="cpu", base_seed=')):
         src = src.replace(a, b)
-    assert '"cuda"' not in src, [l for l in src.splitlines() if '"cuda"' in l]
+    assert 'device="cuda"' not in src and '.to("cuda"' not in src, [l for l in src.splitlines() if '"cuda"' in l]
     spec = importlib.util.spec_from_loader("mr_blip_b200._%s_cpu" % name, loader=None)
     mod = importlib.util.module_from_spec(spec)
     mod.__package__ = "mr_blip_b200"
     mod.__dict__["_NoStream"] = _NoStream
     exec(compile(src, path + " (cpu emulation)", "exec"), mod.__dict__)
     mod.ops = sys.modules[__name__]
+    return mod
+
+
+def load_model_module():
+    """mr_blip_b200/blip2_mr.py on the CPU: its engines are the CPU-compiled engine modules, its ops this module.  Build the model
+    with cuda_graphs=False (graph capture is CUDA-only)."""
+    vision, t5 = load_engine_module("vision"), load_engine_module("t5")
+    mod = load_engine_module("blip2_mr")
+    mod.VitEngine, mod.QFormerEngine, mod.T5Engine = vision.VitEngine, vision.QFormerEngine, t5.T5Engine
     return mod

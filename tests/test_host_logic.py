@@ -847,3 +847,50 @@ def test_swar_keep_compare_of_the_tcgen05_attention_kernels():
             draw = (w >> np.uint64(8 * i)) & np.uint64(0xFF)
             assert (((t >> np.uint64(8 * i + 7)) & np.uint64(1)) == (draw >= thr)).all(), (p, i)
     assert od.thr_of(0.05) % 2 == 1          # LoRA's 0.05 is odd: it never reaches these kernels (byte compare in csrc/dropout.cu)
+
+
+@pytest.mark.parametrize("train_dropout,agg", [(False, None), (True, None), (True, "mean")])
+def test_whole_model_train_step_host_logic_with_emulated_ops(tiny_sd, monkeypatch, train_dropout, agg):
+    """BLIP2_MR.forward in train() -- host phase, ViT / Q-Former / interleave gather / T5 loss, the hand-written backward into the
+    flat gradient buffer, t5_proj gradients, the gradient hand-over to autograd, and with train_dropout the per-step seed word and
+    every dropout site -- run on the CPU over the op stand-ins against the oracle (same checks as tests/test_model_gpu.py::
+    test_forward_backward_vs_oracle and tests/test_dropout_gpu.py do on the device)."""
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    import cpu_ops_emulation as emu
+    from mr_blip_b200.dims import TINY
+    from oracle import blip2_mr as ob, synth
+    from oracle.dropout import Dropper
+    monkeypatch.setenv("MRB_OVERLAP", "0")
+    mod = emu.load_model_module()
+    model = mod.BLIP2_MR(dims=TINY, state_dict=tiny_sd, cuda_graphs=False, train_dropout=train_dropout)
+    model.frame_token_aggregation = agg
+    model.train()
+    samples = synth.make_samples(batch=2, frames=2, seed=3)
+    samples["duration"][1] = 37.0
+    samples["timestamps"][1] = samples["timestamps"][1] * (37.0 / 143.0)
+    res = model.forward_mr(samples, want_logits=True)
+    res["loss"].backward()
+    drop = Dropper(model.drop_state.seed) if train_dropout else None
+    sd = dict(tiny_sd)
+    leaves = {k: sd[k].clone().requires_grad_(True) for k in sd if "lora_" in k or k.startswith("t5_proj.")}
+    sd.update(leaves)
+    o = ob.forward_mr(sd, TINY, model.t5_tokenizer, samples, frame_token_aggregation=agg, drop=drop)
+    o["loss"].backward()
+    assert torch.equal(res["attention_mask"], o["attention_mask"]) and torch.equal(res["labels"], o["labels"])
+    assert _relfro(res["qformer"], o["qformer"]) < 2e-3
+    assert _relfro(res["inputs_embeds"], o["inputs_embeds"]) < 2e-3
+    assert abs(res["loss"].item() - o["loss"].item()) < 5e-3
+    assert _relfro(res["logits"], o["logits"]) < 2e-2
+    for k, leaf in leaves.items():
+        got = model._get(k).grad
+        assert got is not None and _relfro(got, leaf.grad) < 4e-2, k
+    if train_dropout:
+        seed = model.drop_state.seed
+        l2 = model.forward_mr(samples)["loss"].item()                      # the next step draws other masks
+        assert model.drop_state.seed != seed and abs(l2 - res["loss"].item()) > 1e-4
+        model.eval()
+        with torch.no_grad():                                                # eval() is the eval-mode arithmetic
+            ev = model.forward_mr(samples, want_logits=True)
+            oe = ob.forward_mr(dict(tiny_sd), TINY, model.t5_tokenizer, samples, frame_token_aggregation=agg)
+        assert abs(ev["loss"].item() - oe["loss"].item()) < 5e-3
