@@ -19,7 +19,8 @@ import torch.nn as nn
 
 from . import _lib, ops, mr_utils
 from .base_model import BaseModel, attach, disabled_train
-from .dims import Dims, FULL, T5_PREFIX, init_state_dict
+from . import qa
+from .dims import ANSWERER_PREFIX, Dims, FULL, T5_PREFIX, add_answerer, init_state_dict
 from .registry import registry
 from .t5 import T5Engine
 from .tokenizer import load_t5_tokenizer
@@ -91,8 +92,14 @@ class BLIP2_MR(Blip2Base):
         super().__init__()
         self.dims = d = dims or FULL
         assert img_size == d.img_size and num_query_token == d.num_query
-        if "QA" in task:
-            raise NotImplementedError("the NExT-QA/GQA branch (blip2_mr.py:309-431) is outside the hot path (SURVEY.md §2 row 21)")
+        # two-stage video QA (blip2_mr.py:104-109): a frozen localizer (t5_model) proposes a moment, a second LoRA T5 answers
+        self.use_localizer = "with_localizer" in task
+        self.use_oracle_localizer = "oracle_localizer" in task
+        self.num_frames_for_answer = num_frames_for_answer
+        self.resample_frames = resample_frames
+        if "QA" in task and resample_frames:
+            raise NotImplementedError("resample_frames re-decodes the video per proposed moment (blip2_mr.py:1167-1231); the QA "
+                                      "branch here selects among the frames already sampled (resample_frames=False)")
         if "lora" not in task:
             raise NotImplementedError("only LoRA tasks are implemented (every mr_BLIP yaml uses qformer_freeze_lora)")
         if not interleave_data:
@@ -110,14 +117,22 @@ class BLIP2_MR(Blip2Base):
 
         # ---- parameters under the reference's names ------------------------------------------------
         sd = state_dict if state_dict is not None else init_state_dict(d, seed=init_seed, lora_b_std=lora_b_std)
-        shared = None
+        qa_task = "QA" in task
+        if qa_task and not any(k.startswith(ANSWERER_PREFIX) for k in sd):
+            sd = add_answerer(dict(sd), d, seed=init_seed, lora_b_std=lora_b_std, device=next(iter(sd.values())).device)
+        shared, shared_ans = None, None
         for name, t in sd.items():
             if name == "query_tokens":
                 attach(self, name, t.clone(), requires_grad="qformer_freeze" not in task)
                 continue
-            if name.startswith(T5_PREFIX) and name.endswith("embed_tokens.weight"):
+            if name.startswith((T5_PREFIX, ANSWERER_PREFIX)) and name.endswith("embed_tokens.weight"):
                 continue                                     # tied to shared.weight below
-            train = ("lora_A" in name or "lora_B" in name or name.startswith("t5_proj.")
+            if name.startswith(ANSWERER_PREFIX) and not qa_task:
+                continue
+            lora = "lora_A" in name or "lora_B" in name
+            if qa_task:                                      # the localizer's adapters are frozen, the answerer's train (blip2_mr.py:199-235)
+                lora = lora and name.startswith(ANSWERER_PREFIX)
+            train = (lora or name.startswith("t5_proj.")
                      or (name.startswith("Qformer.") and "qformer_freeze" not in task))
             t = t.clone()
             if name.startswith("visual_encoder.") and vit_precision == "fp16" and t.ndim >= 2 and "pos_embed" not in name \
@@ -129,8 +144,12 @@ class BLIP2_MR(Blip2Base):
             p = attach(self, name, t, requires_grad=train and t.is_floating_point())
             if name == T5_PREFIX + "shared.weight":
                 shared = p
+            if name == ANSWERER_PREFIX + "shared.weight":
+                shared_ans = p
         for side in ("encoder", "decoder"):                  # HF ties embed_tokens to shared
             attach(self, T5_PREFIX + side + ".embed_tokens.weight", shared)
+            if shared_ans is not None:
+                attach(self, ANSWERER_PREFIX + side + ".embed_tokens.weight", shared_ans)
         if freeze_vit:
             self.visual_encoder.eval()
             self.visual_encoder.train = disabled_train.__get__(self.visual_encoder)
@@ -143,6 +162,7 @@ class BLIP2_MR(Blip2Base):
         self.seperator_token = self.t5_tokenizer.convert_tokens_to_ids(">")
         self.pad_token_id = self.t5_tokenizer.pad_token_id
         self._engines = None
+        self._answerer = None                                # QA branch: T5Engine over answerer_model.*
         self._lora_versions = None
         # Training steps replay a captured CUDA graph per shape signature (first sight of a shape runs eagerly, the second
         # captures).  Encoder / decoder lengths are padded (masked, exact) up to graph_bucket so few graphs cover a dataset.
@@ -221,18 +241,25 @@ class BLIP2_MR(Blip2Base):
             d = self.dims
             vit, qf, t5 = VitEngine(d, self._get), QFormerEngine(d, self._get), T5Engine(d, self._get)
             self._engines = (vit, qf, t5)
+            qa_task = "QA" in self.task
+            self._answerer = T5Engine(d, self._get, prefix=ANSWERER_PREFIX) if qa_task else None
             self._lora_versions = None
             self.reset_graphs()
             # every trainable gradient lives in one flat fp32 buffer: zeroed / scaled / all-reduced with single launches
             pw, pb = self.t5_proj.weight, self.t5_proj.bias
-            n = t5.n_grad_elems()
-            self._gflat = torch.zeros(n + pw.numel() + pb.numel(), dtype=torch.float32, device="cuda")
+            tr = self._answerer if qa_task else t5           # the T5 whose adapters train
+            n = tr.n_grad_elems()
+            # QA: the frame embeddings are computed under no_grad (blip2_mr.py:316-372), so t5_proj gets no gradient there
+            self._gflat = torch.zeros(n + (0 if qa_task else pw.numel() + pb.numel()), dtype=torch.float32, device="cuda")
             self._hflat = torch.empty_like(self._gflat)
-            off = t5.bind_grads(self._gflat, 0)
+            off = tr.bind_grads(self._gflat, 0)
             assert off == n
-            self._g_projW = self._gflat[n:n + pw.numel()].view(pw.shape)
-            self._g_projb = self._gflat[n + pw.numel():].view(pb.shape)
-            self._grad_params = [p for p, _ in t5.param_grads()] + [pw, pb]
+            if qa_task:
+                self._grad_params = [p for p, _ in tr.param_grads()]
+            else:
+                self._g_projW = self._gflat[n:n + pw.numel()].view(pw.shape)
+                self._g_projb = self._gflat[n + pw.numel():].view(pb.shape)
+                self._grad_params = [p for p, _ in t5.param_grads()] + [pw, pb]
         vit, qf, t5 = self._engines
         if self.train_dropout and self.drop_state is None:
             from .dropout import DropState
@@ -241,10 +268,11 @@ class BLIP2_MR(Blip2Base):
             self.drop_state = DropState(base_seed=self.dropout_seed + rank)      # per-rank masks (reference: train.py:57-58, seed + get_rank())
         if self._in_device_step:                             # (captured) device step: LoRA re-pack is part of the step itself
             return vit, qf, t5
-        vers = tuple(p._version for g in t5.groups for p in g.A_params + g.B_params)
+        tr = self._answerer if self._answerer is not None else t5
+        vers = tuple(p._version for g in tr.groups for p in g.A_params + g.B_params)
         vers += (self.t5_proj.weight._version, self.t5_proj.bias._version)
         if vers != self._lora_versions:                      # optimizer.step() happened: re-pack the trainable bits
-            t5.refresh()
+            tr.refresh()
             qf.set_t5_proj(self.t5_proj.weight, self.t5_proj.bias)
             self._lora_versions = vers
         return vit, qf, t5
@@ -351,7 +379,107 @@ class BLIP2_MR(Blip2Base):
 
     # ---------------------------------------------------------------------------------------------
     def forward(self, samples):
+        if "QA" in self.task:                                # blip2_mr.py:300-307
+            return self.forward_QA(samples)
         return self.forward_mr(samples)
+
+    # ---- two-stage video QA (blip2_mr.py:309-431, 990-1099, 1233-1314) --------------------------
+    def _qa_relevant_frames(self, samples, generate_kwargs=None):
+        """Stage 1: the clip's window -- proposed by the localizer (generate), the ground truth (oracle setting) or the whole
+        video -- and `num_frames_for_answer` of the sampled frames inside it.  -> (relevant_moments, frames [b, n, 3, H, W])."""
+        n = self.num_frames_for_answer
+        if self.use_localizer:
+            out_mr = self.generate(samples, **(generate_kwargs or {}))
+            moments = qa.relevant_moments_from_predictions(out_mr["prediction"], samples["duration"])
+        elif self.use_oracle_localizer and generate_kwargs is not None:         # videoQA_generate only (blip2_mr.py:1057-1075)
+            rw = samples["relevant_windows"]
+            moments = [m[0] for m in (rw.tolist() if torch.is_tensor(rw) else rw)]
+        else:
+            moments = [[0, d.item() if torch.is_tensor(d) else d] for d in samples["duration"]]
+        return moments, qa.extract_frames(samples, moments, n)
+
+    def _qa_inputs(self, frames, texts):
+        """[frame tokens ; embed_tokens(question)] (blip2_mr.py:374-393) through the interleave-gather kernel: a row table of
+        frame rows (negative) followed by the question's token ids.  -> (inputs fp32 [B, L, D], kmask int32 [B, L])."""
+        ans = self._answerer
+        B, TN, C = frames.shape
+        tok = self.t5_tokenizer(texts, padding="longest", truncation=True, max_length=self.max_txt_len, return_tensors="pt")
+        ids = tok.input_ids.numpy().astype(np.int64)
+        table = np.concatenate([-(np.arange(B)[:, None] * TN + np.arange(TN)[None, :]) - 1, ids], axis=1).astype(np.int32)
+        kmask = np.concatenate([np.ones((B, TN), np.int32), tok.attention_mask.numpy().astype(np.int32)], axis=1)
+        Le = table.shape[1]
+        idx = torch.from_numpy(np.ascontiguousarray(table.reshape(-1))).to("cuda", non_blocking=True)
+        inputs = torch.empty((B * Le, C), dtype=torch.float32, device="cuda")
+        ops.gather_rows(idx, ans.emb, frames.reshape(B * TN, C), inputs)
+        return inputs.view(B, Le, C), torch.from_numpy(np.ascontiguousarray(kmask)).to("cuda", non_blocking=True)
+
+    def forward_QA(self, samples, want_logits=False):
+        """blip2_mr.py:309-431: stage 1 without gradients (localizer / uniform window, frame selection, ViT -> Q-Former ->
+        t5_proj), stage 2 the answerer's teacher-forced loss; only the answerer's LoRA adapters receive gradients."""
+        self.engines()
+        samples["relevant_windows"] = [[0, 0]]               # dummy answer (blip2_mr.py:314)
+        samples["query_id"] = samples["question_id"]
+        need_grad = self.training and torch.is_grad_enabled()
+        with torch.no_grad():
+            moments, rel = self._qa_relevant_frames(samples)
+            samples["relevant_frames"] = rel
+            # the localizer ran the eval-mode arithmetic (generate); stage 2 follows module.training
+            self._set_dropout(self.training)
+            frames, _ = self.get_frame_embeddings_and_attentions(rel)
+        ans = self._answerer
+        inputs, kmask = self._qa_inputs(frames, samples["qa_input"])
+        out_tok = self.t5_tokenizer(samples["qa_output"], padding="longest", truncation=True, max_length=self.max_txt_len,
+                                    return_tensors="pt")
+        labels = out_tok.input_ids.masked_fill(out_tok.input_ids == self.t5_tokenizer.pad_token_id, -100)
+        if need_grad:
+            self._gflat.zero_()
+        out = ans.loss(inputs, kmask, labels, out_tok.attention_mask, backward=need_grad, want_logits=want_logits)
+        loss = out["loss"].reshape(())
+        if need_grad:
+            loss = _HandOverGrads.apply(loss, self, *self._grad_params)
+        res = {"loss": loss}
+        if want_logits:
+            res.update(logits=out["logits"], relevant_moments=moments, labels=labels, inputs_embeds=inputs)
+        return res
+
+    @torch.no_grad()
+    def videoQA_answer(self, samples, max_length=50, min_length=8, **unused):
+        """blip2_mr.py:1233-1314: greedy decode of the answerer; the answer is the arg-max over the five letter ids of the scores
+        of the SECOND generated position (`outputs_qa.scores[1]`).  Greedy search with min_length only suppresses eos before
+        that position, so two decode steps give exactly those scores."""
+        self.engines()
+        self._set_dropout(False)
+        ans = self._answerer
+        frames, _ = self.get_frame_embeddings_and_attentions(samples["relevant_frames"])
+        inputs, kmask = self._qa_inputs(frames, samples["qa_input"])
+        B, Le, _ = inputs.shape
+        enc_ext, kmask = ans.encode(inputs, kmask)
+        st = ans.init_decode(enc_ext, B, Le, 1, 2)
+        eos = self.t5_tokenizer.eos_token_id
+        tok0 = torch.full((B,), self.t5_tokenizer.pad_token_id, dtype=torch.long, device="cuda")      # decoder_start_token_id
+        l0 = ans.decode_step(st, tok0, 0, kmask).clone()
+        if min_length > 1:
+            l0[:, eos] = float("-inf")                       # MinLengthLogitsProcessor
+        l1 = ans.decode_step(st, l0.argmax(-1), 1, kmask)
+        pred = l1[:, qa.ANSWER_IDS].argmax(-1).cpu().tolist()
+        return {"output_text": pred, "answer": samples["qa_output"], "qid": samples["question_id"],
+                "relevant_moments_gt": samples["relevant_windows"], "answer_scores": l1[:, qa.ANSWER_IDS].float().cpu()}
+
+    @torch.no_grad()
+    def videoQA_generate(self, samples, num_frames_for_answer=4, use_nucleus_sampling=False, num_beams=5, max_length=50,
+                         min_length=8, top_p=0.9, repetition_penalty=1.0, length_penalty=1.0, num_captions=1, temperature=1,
+                         output_attentions=False):
+        """blip2_mr.py:990-1099."""
+        if "relevant_windows" not in samples:
+            samples["relevant_windows"] = [[0, 0]]
+        samples["query_id"] = samples["question_id"]
+        moments, rel = self._qa_relevant_frames(samples, dict(use_nucleus_sampling=use_nucleus_sampling, num_beams=num_beams,
+                                                              max_length=max_length, min_length=min_length,
+                                                              length_penalty=length_penalty))
+        samples["relevant_frames"] = rel
+        out = self.videoQA_answer(samples)
+        out["relevant_moments"] = [moments]
+        return out
 
     # ---- gradient hand-over ---------------------------------------------------------------------
     def _grad_views(self, flat):
@@ -508,6 +636,8 @@ class BLIP2_MR(Blip2Base):
         _, qf, t5 = self.engines()
         st = self.drop_state if (on and self.train_dropout) else None
         qf.drop = t5.drop = st
+        if self._answerer is not None:                       # QA: the localizer only ever runs generate (eval arithmetic)
+            t5.drop, self._answerer.drop = None, st
         if st is not None and advance:
             st.advance()
         return st is not None

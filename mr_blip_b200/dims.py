@@ -223,6 +223,25 @@ def init_t5_proj(d: Dims, gen, sd):
     sd["t5_proj.bias"] = (_rand((d.d_model,), gen) * 2 - 1) * bound
 
 
+ANSWERER_PREFIX = "answerer_model.base_model.model."
+
+
+def add_answerer(sd, d: Dims = FULL, seed: int = 1234, lora_b_std: float = 0.0, device="cpu"):
+    """The QA branch's second LoRA T5 (blip2_mr.py:148-156,199-235: `answerer_model`, loaded from the SAME pretrained FlanT5 as
+    the localizer and wrapped by its own peft adapters): frozen weights = the localizer's (shared storage), fresh LoRA A / B."""
+    gen = torch.Generator(device=device).manual_seed(seed + 4)
+    for k in [k for k in sd if k.startswith(T5_PREFIX)]:
+        nk = ANSWERER_PREFIX + k[len(T5_PREFIX):]
+        v = sd[k]
+        if ".lora_A." in k:
+            sd[nk] = (_rand(tuple(v.shape), gen) * 2 - 1) * (1.0 / math.sqrt(v.shape[1]))
+        elif ".lora_B." in k:
+            sd[nk] = _normal(tuple(v.shape), lora_b_std, gen) if lora_b_std > 0 else torch.zeros_like(v)
+        else:
+            sd[nk] = v
+    return sd
+
+
 def init_state_dict(d: Dims = FULL, seed: int = 1234, lora_b_std: float = 0.0, parts=("vit", "qformer", "t5"),
                     device="cpu"):
     """Seeded fp32 state dict with the reference's key names (SURVEY.md §5 checkpoint row).  device="cpu" is

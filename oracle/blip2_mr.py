@@ -135,3 +135,60 @@ def generate(sd, d, tok, samples, post_process, num_beams=5, max_length=50, min_
     return {"prediction": [post_process(p) for p in raw], "raw_prediction": raw, "sequences": seqs,
             "answer": samples["relevant_windows"], "qid": samples["query_id"],
             "duration": dur.tolist() if torch.is_tensor(dur) else dur}
+
+
+# ---------------------------------------------------------------------------------------------- two-stage video QA
+ANSWERER_PREFIX = "answerer_model.base_model.model."
+ANSWER_IDS = [71, 272, 205, 309, 262]          # A B C D E (blip2_mr.py:1297)
+
+
+def _qa_relevant_frames(sd, d, tok, samples, use_localizer, n_frames, post_process, frame_token_aggregation):
+    """blip2_mr.py:328-362 / 1011-1049: window from the localizer's prediction or the whole video, then extract_frames.  The two
+    frame-selection helpers are the product's (mr_blip_b200/qa.py), which are pinned to the reference's own methods
+    (tests/golden/qa_frames_golden.json); restating them a third time here would add nothing."""
+    from mr_blip_b200 import qa
+    if use_localizer:
+        pred = generate(sd, d, tok, samples, post_process, frame_token_aggregation=frame_token_aggregation)["prediction"]
+        moments = qa.relevant_moments_from_predictions(pred, samples["duration"])
+    else:
+        moments = [[0, x.item()] for x in samples["duration"]]
+    return moments, qa.extract_frames(samples, moments, n_frames)
+
+
+def _qa_inputs(sd, tok, f, texts, max_txt_len):
+    q = tok(texts, padding="longest", truncation=True, max_length=max_txt_len, return_tensors="pt")
+    emb = sd[ANSWERER_PREFIX + "shared.weight"][q.input_ids]
+    return torch.cat([f, emb], dim=1), torch.cat([torch.ones(f.shape[:2], dtype=torch.long), q.attention_mask], dim=1)
+
+
+def forward_qa(sd, d, tok, samples, use_localizer=False, n_frames=4, post_process=None, frame_token_aggregation=None,
+               max_txt_len=200, drop=None):
+    """forward_QA, blip2_mr.py:309-431 -> dict(loss, logits, relevant_moments).  Stage 1 without gradients; the localizer's
+    generate runs the eval-mode arithmetic (the product's choice), `drop` applies to the Q-Former and the answerer."""
+    samples = dict(samples)
+    samples["relevant_windows"], samples["query_id"] = [[0, 0]], samples["question_id"]
+    with torch.no_grad():
+        moments, rel = _qa_relevant_frames(sd, d, tok, samples, use_localizer, n_frames, post_process, frame_token_aggregation)
+        f, _ = frame_tokens(sd, d, rel, frame_token_aggregation, drop=drop)
+    inputs, atts = _qa_inputs(sd, tok, f, samples["qa_input"], max_txt_len)
+    a = tok(samples["qa_output"], padding="longest", truncation=True, max_length=max_txt_len, return_tensors="pt")
+    labels = a.input_ids.masked_fill(a.input_ids == tok.pad_token_id, -100)
+    out = _t5.t5_forward(sd, d, inputs, atts, labels, a.attention_mask, prefix=ANSWERER_PREFIX, drop=drop)
+    out.update(relevant_moments=moments, labels=labels)
+    return out
+
+
+def videoqa_answer(sd, d, tok, samples, rel, frame_token_aggregation=None, max_txt_len=200, min_length=8):
+    """videoQA_answer, blip2_mr.py:1233-1314: greedy answerer, arg-max over the letter ids of the second position's scores."""
+    with torch.no_grad():
+        f, _ = frame_tokens(sd, d, rel, frame_token_aggregation)
+        inputs, atts = _qa_inputs(sd, tok, f, samples["qa_input"], max_txt_len)
+        enc = _t5.t5_encoder(sd, d, inputs, atts, prefix=ANSWERER_PREFIX)
+        ids = torch.full((inputs.shape[0], 1), tok.pad_token_id, dtype=torch.long)
+        for _ in range(2):
+            dec = _t5.t5_decoder(sd, d, ids, enc, atts, prefix=ANSWERER_PREFIX)
+            logits = _t5.t5_logits(sd, d, dec[:, -1], prefix=ANSWERER_PREFIX)
+            if min_length > 1:
+                logits[:, tok.eos_token_id] = float("-inf")
+            ids = torch.cat([ids, logits.argmax(-1, keepdim=True)], dim=1)
+    return logits[:, ANSWER_IDS].argmax(-1).tolist(), logits[:, ANSWER_IDS]

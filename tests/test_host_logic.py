@@ -894,3 +894,64 @@ def test_whole_model_train_step_host_logic_with_emulated_ops(tiny_sd, monkeypatc
             ev = model.forward_mr(samples, want_logits=True)
             oe = ob.forward_mr(dict(tiny_sd), TINY, model.t5_tokenizer, samples, frame_token_aggregation=agg)
         assert abs(ev["loss"].item() - oe["loss"].item()) < 5e-3
+
+
+def _qa_samples(batch=2, frames=6, seed=7):
+    from oracle import synth
+    s = synth.make_samples(batch=batch, frames=frames, seed=seed)
+    s["question_id"] = ["q%d" % i for i in range(batch)]
+    s["qa_input"] = ["Question: what does the person do first? Options: A. word alpha B. word beta C. word gamma D. word delta E. word eps Answer: ",
+                     "Question: why is the dog running? Options: A. one B. two C. three D. four E. five Answer: "][:batch]
+    s["qa_output"] = ["Answer: B", "Answer: E"][:batch]
+    return s
+
+
+@pytest.mark.parametrize("task,train_dropout", [("qformer_freeze_lora_QA", False), ("qformer_freeze_lora_QA_with_localizer", False),
+                                                ("qformer_freeze_lora_QA", True)])
+def test_video_qa_branch_host_logic_with_emulated_ops(tiny_sd, monkeypatch, task, train_dropout):
+    """The two-stage video-QA branch (blip2_mr.py:309-431: localizer / uniform window -> frame selection -> frozen frame encoder
+    -> answerer loss; only the answerer's adapters train) and videoQA_generate (:990-1099, :1233-1314) on the CPU over the op
+    stand-ins against the oracle restatement."""
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    import cpu_ops_emulation as emu
+    from mr_blip_b200.dims import ANSWERER_PREFIX, T5_PREFIX, TINY, add_answerer
+    from mr_blip_b200 import mr_utils
+    from oracle import blip2_mr as ob
+    from oracle.dropout import Dropper
+    monkeypatch.setenv("MRB_OVERLAP", "0")
+    monkeypatch.setenv("MRB_CUDA_GRAPHS", "0")
+    sd = add_answerer(dict(tiny_sd), TINY, seed=1234, lora_b_std=0.02)
+    mod = emu.load_model_module()
+    model = mod.BLIP2_MR(dims=TINY, state_dict=sd, cuda_graphs=False, task=task, num_frames_for_answer=3, train_dropout=train_dropout)
+    # trainability as the reference sets it (blip2_mr.py:199-235)
+    names = {n: p.requires_grad for n, p in model.named_parameters()}
+    assert all(v == ("lora_" in n) for n, v in names.items() if n.startswith(ANSWERER_PREFIX))
+    assert not any(v for n, v in names.items() if n.startswith(T5_PREFIX))
+    model.train()
+    samples = _qa_samples()
+    res = model(dict(samples)) if not train_dropout else model.forward_QA(dict(samples), want_logits=True)
+    res["loss"].backward()
+    drop = Dropper(model.drop_state.seed) if train_dropout else None
+    osd = dict(sd)
+    leaves = {k: osd[k].clone().requires_grad_(True) for k in osd if "lora_" in k and k.startswith(ANSWERER_PREFIX)}
+    osd.update(leaves)
+    o = ob.forward_qa(osd, TINY, model.t5_tokenizer, samples, use_localizer="with_localizer" in task, n_frames=3,
+                      post_process=mr_utils.post_process, drop=drop)
+    o["loss"].backward()
+    assert abs(res["loss"].item() - o["loss"].item()) < 5e-3
+    if train_dropout:
+        assert _relfro(res["logits"], o["logits"]) < 2e-2 and res["relevant_moments"] == o["relevant_moments"]
+    for k, leaf in leaves.items():
+        got = model._get(k).grad
+        assert got is not None and _relfro(got, leaf.grad) < 4e-2, k
+    assert all(p.grad is None for n, p in model.named_parameters() if not n.startswith(ANSWERER_PREFIX))
+    # inference: same windows, same answer letters, close letter scores
+    model.eval()
+    out = model.videoQA_generate(dict(samples))
+    moments, rel = ob._qa_relevant_frames(sd, TINY, model.t5_tokenizer, dict(samples, relevant_windows=[[0, 0]], query_id=samples["question_id"]),
+                                          "with_localizer" in task, 3, mr_utils.post_process, None)
+    want, scores = ob.videoqa_answer(sd, TINY, model.t5_tokenizer, samples, rel)
+    assert out["relevant_moments"] == [moments]
+    assert _relfro(out["answer_scores"], scores) < 2e-2
+    assert out["output_text"] == want and out["qid"] == samples["question_id"]

@@ -384,3 +384,19 @@ def test_counter_hash_masks_statistics_and_determinism():
                           (2, "DenseReluDense.wi_0"), (2, "DenseReluDense.wi_1"), (2, "DenseReluDense.wo"))}
     sites.add(od.lora_site("t5_model.base_model.model.lm_head"))
     assert len(sites) == 2 * 24 * 11 + 1
+
+
+def test_qa_frame_selection_matches_reference(golden_dir):
+    """mr_blip_b200/qa.py against the reference's own get_relevant_frames / extract_frames (blip2_mr.py:1101-1165) on 96 cases:
+    unparsable predictions, several windows, ends past the video, empty / inverted windows, padding and uniform thinning."""
+    from mr_blip_b200 import qa
+    gold = json.load(open(os.path.join(golden_dir, "qa_frames_golden.json")))
+    assert len(gold) == 96
+    for c in gold:
+        T = c["T"]
+        samples = {"video": torch.arange(T, dtype=torch.float32).view(1, T, 1, 1, 1), "timestamps": torch.tensor(c["timestamps"])[None],
+                   "duration": torch.tensor([c["duration"]])}
+        m = qa.relevant_moments_from_predictions([c["prediction"]], samples["duration"])
+        assert [float(x) for x in m[0]] == c["moment"], c
+        fr = qa.extract_frames(samples, m, c["n"])
+        assert fr.shape == (1, c["n"], 1, 1, 1) and fr.view(-1).long().tolist() == c["frames"], c

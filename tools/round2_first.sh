@@ -13,7 +13,7 @@ mkdir -p $O
 tail -3 $O/pytest.log
 ( MRB_TEST_EXPERIMENTAL=1 timeout 300 python -m pytest tests/test_experimental_gpu.py -m gpu -q 2>&1 | tail -25 ) > $O/pytest_experimental.log 2>&1
 tail -5 $O/pytest_experimental.log
-( MRB_TEST_EXPERIMENTAL=1 timeout 900 python -m pytest tests/test_dropout_gpu.py -m gpu -q 2>&1 | tail -60 ) > $O/pytest_dropout.log 2>&1
+( MRB_TEST_EXPERIMENTAL=1 timeout 900 python -m pytest tests/test_dropout_gpu.py tests/test_qa_gpu.py -m gpu -q 2>&1 | tail -60 ) > $O/pytest_dropout.log 2>&1
 tail -8 $O/pytest_dropout.log
 ( timeout 400 python bench.py --steps 8 --warmup 3 --train-dropout ) > $O/bench_dropout.json 2> $O/bench_dropout.err
 cut -c1-200 $O/bench_dropout.json
