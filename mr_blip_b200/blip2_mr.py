@@ -97,9 +97,10 @@ class BLIP2_MR(Blip2Base):
         self.use_oracle_localizer = "oracle_localizer" in task
         self.num_frames_for_answer = num_frames_for_answer
         self.resample_frames = resample_frames
-        if "QA" in task and resample_frames:
-            raise NotImplementedError("resample_frames re-decodes the video per proposed moment (blip2_mr.py:1167-1231); the QA "
-                                      "branch here selects among the frames already sampled (resample_frames=False)")
+        self.video_processor_answerer_eval = None
+        if "QA" in task and resample_frames:                 # blip2_mr.py:111-116: the answerer's own eval processor (n frames)
+            from .data import VideoProcessor
+            self.video_processor_answerer_eval = VideoProcessor(image_size=img_size, n_frms=num_frames_for_answer)
         if "lora" not in task:
             raise NotImplementedError("only LoRA tasks are implemented (every mr_BLIP yaml uses qformer_freeze_lora)")
         if not interleave_data:
@@ -390,10 +391,14 @@ class BLIP2_MR(Blip2Base):
         n = self.num_frames_for_answer
         if self.use_localizer:
             out_mr = self.generate(samples, **(generate_kwargs or {}))
+            if self.resample_frames:                         # re-decode inside the proposed window (blip2_mr.py:340-348)
+                return qa.relevant_frames_resampled(samples, out_mr["prediction"], self.video_processor_answerer_eval)
             moments = qa.relevant_moments_from_predictions(out_mr["prediction"], samples["duration"])
         elif self.use_oracle_localizer and generate_kwargs is not None:         # videoQA_generate only (blip2_mr.py:1057-1075)
             rw = samples["relevant_windows"]
             moments = [m[0] for m in (rw.tolist() if torch.is_tensor(rw) else rw)]
+            if self.resample_frames:
+                return qa.relevant_frames_resampled(samples, moments, self.video_processor_answerer_eval)
         else:
             moments = [[0, d.item() if torch.is_tensor(d) else d] for d in samples["duration"]]
         return moments, qa.extract_frames(samples, moments, n)

@@ -55,3 +55,29 @@ def extract_frames(samples, relevant_moments, n):
         idx = frame_indices(samples["timestamps"][i], samples["duration"][i], start, end, n)
         out.append(video[i][idx.to(video.device)])
     return torch.stack(out)
+
+
+def relevant_frames_resampled(samples, relevant_moments, processor):
+    """get_relevant_frames_resampled, blip2_mr.py:1167-1231: the answerer's frames are RE-DECODED from samples["video_path"]
+    inside the proposed window by the answerer's eval video processor (already set to num_frames_for_answer frames) instead of
+    being picked among the clip's sampled frames.  relevant_moments: the localizer's strings, or [start, end] pairs.
+    -> (moments, frames [b, n, 3, H, W] on the device of samples["video"])."""
+    if isinstance(relevant_moments[0], str):
+        moments = []
+        for i, text in enumerate(relevant_moments):
+            m = mr_utils.moment_str_to_list(text)
+            dur = _item(samples["duration"][i])
+            m = [0, round(dur)] if m == [[-1, -1]] else m[0]
+            if m[1] > dur:
+                m[1] = round(dur)
+            moments.append(m)
+    else:
+        moments = relevant_moments
+    assert len(moments) == samples["video"].shape[0]
+    out = []
+    for i, (start, end) in enumerate(moments):
+        if start >= end:
+            end = _item(samples["duration"][i])
+        frames, _, _ = processor(samples["video_path"][i], clip_proposal=[start, end])      # c, n, h, w
+        out.append(frames.permute(1, 0, 2, 3))
+    return moments, torch.stack(out).to(samples["video"].device)

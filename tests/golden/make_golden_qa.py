@@ -26,9 +26,9 @@ def reference_methods():
     cls = next(n for n in tree.body if isinstance(n, ast.ClassDef) and n.name == "BLIP2_MR")
     ns = {"torch": torch, "moment_str_to_list": ref_shim.load_reference_utils().moment_str_to_list}
     for fn in cls.body:
-        if isinstance(fn, ast.FunctionDef) and fn.name in ("get_relevant_frames", "extract_frames"):
+        if isinstance(fn, ast.FunctionDef) and fn.name in ("get_relevant_frames", "extract_frames", "get_relevant_frames_resampled"):
             exec(textwrap.dedent(ast.get_source_segment(src, fn)), ns)
-    return ns["get_relevant_frames"], ns["extract_frames"]
+    return ns["get_relevant_frames"], ns["extract_frames"], ns["get_relevant_frames_resampled"]
 
 
 def cases():
@@ -42,7 +42,7 @@ def cases():
 
 
 def main():
-    get_relevant_frames, extract_frames = reference_methods()
+    get_relevant_frames, extract_frames, get_resampled = reference_methods()
 
     class Self:
         pass
@@ -58,9 +58,24 @@ def main():
                 moments, frames = get_relevant_frames(self, samples, [pred], n)
                 gold.append({"T": T, "duration": dur, "timestamps": ts.tolist(), "n": n, "prediction": pred,
                              "moment": [float(x) for x in moments[0]], "frames": frames.view(-1).long().tolist()})
+    # resample_frames=True: which windows the answerer's video processor is asked to decode (a recording stub stands for it)
+    calls = []
+
+    def processor(path, clip_proposal=None):
+        calls.append([path, [float(x) for x in clip_proposal]])
+        return torch.full((3, 2, 1, 1), float(len(calls))), None, None
+    self.video_processor_answerer_eval = processor
+    resampled = []
+    for dur in (31.4, 150.0, 3.2):
+        for m in preds + [[4, 9], [9, 4], [2, 400]]:
+            del calls[:]
+            samples = {"video": torch.zeros(1, 5, 3, 1, 1), "duration": torch.tensor([dur]), "video_path": ["v%d.mp4" % len(resampled)]}
+            moments, frames = get_resampled(self, samples, [m], 2)
+            resampled.append({"duration": dur, "moment_in": m, "video_path": samples["video_path"][0],
+                              "moment": [float(x) for x in moments[0]], "calls": [list(c) for c in calls], "shape": list(frames.shape)})
     with open(os.path.join(HERE, "qa_frames_golden.json"), "w") as f:
-        json.dump(gold, f)
-    print(len(gold), "cases")
+        json.dump({"selected": gold, "resampled": resampled}, f)
+    print(len(gold), "+", len(resampled), "cases")
 
 
 if __name__ == "__main__":

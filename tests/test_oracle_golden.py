@@ -390,8 +390,19 @@ def test_qa_frame_selection_matches_reference(golden_dir):
     """mr_blip_b200/qa.py against the reference's own get_relevant_frames / extract_frames (blip2_mr.py:1101-1165) on 96 cases:
     unparsable predictions, several windows, ends past the video, empty / inverted windows, padding and uniform thinning."""
     from mr_blip_b200 import qa
-    gold = json.load(open(os.path.join(golden_dir, "qa_frames_golden.json")))
-    assert len(gold) == 96
+    both = json.load(open(os.path.join(golden_dir, "qa_frames_golden.json")))
+    gold = both["selected"]
+    assert len(gold) == 96 and len(both["resampled"]) == 33
+    for c in both["resampled"]:                              # resample_frames=True: windows handed to the answerer's video processor
+        calls = []
+
+        def processor(path, clip_proposal=None):
+            calls.append([path, [float(x) for x in clip_proposal]])
+            return torch.full((3, 2, 1, 1), float(len(calls))), None, None
+        samples = {"video": torch.zeros(1, 5, 3, 1, 1), "duration": torch.tensor([c["duration"]]), "video_path": [c["video_path"]]}
+        m_in = c["moment_in"]
+        moments, frames = qa.relevant_frames_resampled(samples, [m_in if isinstance(m_in, str) else list(m_in)], processor)
+        assert [float(x) for x in moments[0]] == c["moment"] and calls == c["calls"] and list(frames.shape) == c["shape"], c
     for c in gold:
         T = c["T"]
         samples = {"video": torch.arange(T, dtype=torch.float32).view(1, T, 1, 1, 1), "timestamps": torch.tensor(c["timestamps"])[None],
