@@ -955,3 +955,99 @@ def test_video_qa_branch_host_logic_with_emulated_ops(tiny_sd, monkeypatch, task
     assert out["relevant_moments"] == [moments]
     assert _relfro(out["answer_scores"], scores) < 2e-2
     assert out["output_text"] == want and out["qid"] == samples["question_id"]
+
+
+def test_ops_wrappers_pass_what_the_c_abi_declares(monkeypatch):
+    """Every ops.py wrapper touched by the dropout work (incl. the default attention wrappers) hands _lib.call exactly the
+    argument list its SIGNATURES entry (= include/mrblip_b200.h) declares, with values ctypes can convert to the declared types.
+    No kernel runs: _lib.call is replaced by a checker and the tensors live on the CPU."""
+    import ctypes
+    from mr_blip_b200 import _lib, ops
+    seen = []
+
+    def call(name, *args):
+        sig = _lib.SIGNATURES[name]
+        assert len(args) == len(sig), (name, len(args), len(sig))
+        for i, (a, t) in enumerate(zip(args, sig)):
+            if t is ctypes.c_void_p:
+                assert a is None or isinstance(a, int), (name, i, a)
+            elif t is ctypes.c_float:
+                assert isinstance(a, float), (name, i, a)
+            else:
+                assert isinstance(a, int) and not isinstance(a, bool), (name, i, a)
+                t(a)
+        seen.append(name)
+
+    monkeypatch.setattr(_lib, "call", call)
+    monkeypatch.setattr(ops, "_check", lambda t, *d: t)
+    monkeypatch.setattr(ops, "_stream", lambda: 0)
+    B, H, L, hd = 2, 4, 16, 64
+    q = torch.zeros((B * L, 3 * H * hd), dtype=torch.bfloat16)
+    o = torch.zeros((B * L, H * hd), dtype=torch.bfloat16)
+    lse = torch.zeros((B, H, L))
+    bias = torch.zeros((H, 2 * L - 1))
+    km = torch.ones((B, L), dtype=torch.int32)
+    word = torch.zeros(1, dtype=torch.int32)
+    rs = q.stride(0)
+    for drop in (None, (word, 33, 0.1)):
+        for impl in ("mma", "tc"):
+            ops.attention_fwd(q, q[:, H * hd:], q[:, 2 * H * hd:], o, B, H, L, L, hd, 1.0, (L * rs, rs), (L * rs, rs), (L * rs, rs),
+                              (L * o.stride(0), o.stride(0)), bias=bias, bias_zero=L - 1, kmask=km, causal=True, lse=lse, impl=impl, drop=drop)
+            ops.attention_bwd(q, q[:, H * hd:], q[:, 2 * H * hd:], o, o, q, q[:, H * hd:], q[:, 2 * H * hd:], B, H, L, L, hd, 1.0,
+                              (L * rs, rs), (L * rs, rs), (L * rs, rs), (L * o.stride(0), o.stride(0)), (L * o.stride(0), o.stride(0)),
+                              lse, lse.view(-1), bias=bias, bias_zero=L - 1, kmask=km, causal=True, impl=impl, drop=drop)
+    x = torch.zeros((8, 64))
+    xe = torch.zeros((8, 64 + 32), dtype=torch.bfloat16)
+    A = torch.zeros((32, 64), dtype=torch.bfloat16)
+    ops.dropout(x, xe[:, :64], 8, 64, word, 5, 0.1)
+    ops.dropout_add(x, x, torch.empty_like(x), word, 5, 0.1)
+    ab = torch.zeros((8, 128 + 32), dtype=torch.bfloat16)
+    ops.gated_gelu_fwd_drop(ab, xe, 8, 64, word, 5, 0.1)
+    ops.gated_gelu_bwd_drop(ab, xe, ab, 8, 64, word, 5, 0.1)
+    ops.lora_down_drop(xe[:, :64], A, xe[:, 64:], 8, 64, 3, word, 5, 0.05)
+    ops.lora_wgrad_drop(xe.data_ptr(), xe.stride(0), xe.data_ptr() + 128, xe.stride(0), 8, 64, torch.zeros((8, 64)), ops.BF16, word, 5, 0.05)
+    ops.lora_dx_drop(xe[:, 64:], A, 3, x, 8, 64, word, 5, 0.05)
+    ops.gemm(xe, A, out=torch.zeros((8, 32)), M=8, K=64)
+    assert {"mrb_attention_fwd", "mrb_attention_fwd_tc", "mrb_attention_fwd_drop", "mrb_attention_fwd_tc_drop", "mrb_attention_bwd",
+            "mrb_attention_bwd_tc", "mrb_attention_bwd_drop", "mrb_attention_bwd_tc_drop", "mrb_dropout", "mrb_dropout_add",
+            "mrb_gated_gelu_fwd_drop", "mrb_gated_gelu_bwd_drop", "mrb_lora_down_drop", "mrb_lora_wgrad_drop", "mrb_lora_dx_drop",
+            "mrb_gemm"} <= set(seen)
+
+
+def test_ctypes_signatures_match_header_and_source_prototypes():
+    """_lib.SIGNATURES (what ctypes converts to) against the C prototypes -- in include/mrblip_b200.h AND in the definitions
+    under csrc/ -- argument by argument: pointer / long long / int / unsigned / float."""
+    from mr_blip_b200 import _lib
+
+    def kinds(arglist):
+        out = []
+        for a in arglist.split(","):
+            a = " ".join(a.split())
+            if "*" in a or a.startswith("CUtensorMap"):
+                out.append(ctypes.c_void_p)
+            elif a.startswith("long long"):
+                out.append(ctypes.c_longlong)
+            elif a.startswith("unsigned"):
+                out.append(ctypes.c_uint)
+            elif a.startswith("float"):
+                out.append(ctypes.c_float)
+            elif a.startswith("int"):
+                out.append(ctypes.c_int)
+            else:
+                raise AssertionError("unparsed argument: " + a)
+        return out
+
+    hdr = open(os.path.join(ROOT, "include", "mrblip_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    protos = dict(re.findall(r"\bint\s+(mrb_\w+)\s*\(([^)]*)\)\s*;", hdr))
+    for name, sig in _lib.SIGNATURES.items():
+        assert kinds(protos[name]) == sig, name
+    defs = {}
+    csrc = os.path.join(ROOT, "mr_blip_b200", "csrc")
+    for f in os.listdir(csrc):
+        if f.endswith(".cu"):
+            src = re.sub(r"//[^\n]*", "", open(os.path.join(csrc, f)).read())
+            for name, args in re.findall(r'extern "C" int\s+(mrb_\w+)\s*\(([^)]*)\)\s*\{', src):
+                defs[name] = args
+    for name, sig in _lib.SIGNATURES.items():
+        assert name in defs and kinds(defs[name]) == sig, name
