@@ -259,8 +259,8 @@ __global__ void __launch_bounds__(NTHREADS) attn_fwd_kernel(const typename AttnP
 // keys in 16-key groups, each computes S / softmax partials / P.V for all 32 queries over its keys with mma.sync, and the
 // partial (max, sum, O) triples are merged through shared memory.  No loop-carried barriers, no running rescale.
 constexpr int XQ_MAXG = 5;                    // 16-key groups per warp: Lk <= 4 * 5 * 16 = 320
-template <typename T>
-__global__ void __launch_bounds__(128) attn_xq_kernel(const AttnParams p) {
+template <typename T, bool DROP = false>
+__global__ void __launch_bounds__(128) attn_xq_kernel(const typename AttnParamsOf<DROP>::type p) {
   mrb::pdl_trigger();
   mrb::pdl_wait();      // before the first global access (common.cuh, MRB_PDL)
   // rows are 128 B (64 x 16 bit), 16-byte chunk c of row r lives at chunk (c ^ (r & 7)): conflict-free ldmatrix without
@@ -346,6 +346,14 @@ __global__ void __launch_bounds__(128) attn_xq_kernel(const AttnParams p) {
       mx[mt][r] = fmaxf(mx[mt][r], __shfl_xor_sync(0xffffffffu, mx[mt][r], 2));
     }
   uint32_t pf[2][XQ_MAXG][4];
+  uint32_t dkey = 0, dhead = 0, dng = 0, dthr = 0;
+  float dscale = 1.f;
+  if constexpr (DROP) {                          // Qformer.py:258 in train mode: masks of dropmask.cuh, row = (b H + h) Lq + i
+    dkey = drop_key(*p.drop_seed, p.drop_site);
+    dthr = p.drop_thr; dscale = p.drop_scale;
+    dhead = static_cast<uint32_t>(b * p.H + h) * static_cast<uint32_t>(p.Lq);
+    dng = drop_groups(static_cast<uint32_t>(p.Lk));
+  }
 #pragma unroll
   for (int mt = 0; mt < 2; ++mt) {
     const float m0 = mx[mt][0] == -INFINITY ? 0.f : mx[mt][0], m1 = mx[mt][1] == -INFINITY ? 0.f : mx[mt][1];
@@ -355,6 +363,15 @@ __global__ void __launch_bounds__(128) attn_xq_kernel(const AttnParams p) {
       const float p2 = exp2f(sc[mt][nb][2] - m1), p3 = exp2f(sc[mt][nb][3] - m1);
       ls[mt][0] += p0 + p1;
       ls[mt][1] += p2 + p3;
+      if constexpr (DROP) {                      // the sums stay those of the undropped P; 1 / (1 - p) goes into the final 1 / L
+        const int j = (g0 + (nb >> 1)) * 16 + (nb & 1) * 8 + 2 * t4;
+        const uint32_t r0 = static_cast<uint32_t>(min(mt * 16 + g, p.Lq - 1)), r1 = static_cast<uint32_t>(min(mt * 16 + g + 8, p.Lq - 1));
+        const uint32_t w0 = drop_word(dkey, (dhead + r0) * dng, static_cast<uint32_t>(j) >> 2);
+        const uint32_t w1 = drop_word(dkey, (dhead + r1) * dng, static_cast<uint32_t>(j) >> 2);
+        pf[mt][nb >> 1][(nb & 1) * 2] = MmaType<T>::pack(drop_keep(w0, j, dthr) ? p0 : 0.f, drop_keep(w0, j + 1, dthr) ? p1 : 0.f);
+        pf[mt][nb >> 1][(nb & 1) * 2 + 1] = MmaType<T>::pack(drop_keep(w1, j, dthr) ? p2 : 0.f, drop_keep(w1, j + 1, dthr) ? p3 : 0.f);
+        continue;
+      }
       pf[mt][nb >> 1][(nb & 1) * 2] = MmaType<T>::pack(p0, p1);
       pf[mt][nb >> 1][(nb & 1) * 2 + 1] = MmaType<T>::pack(p2, p3);
     }
@@ -416,7 +433,7 @@ __global__ void __launch_bounds__(128) attn_xq_kernel(const AttnParams p) {
         f[w] = mw == -INFINITY ? 0.f : exp2f(mw - m);
         L += f[w] * sL[w * LQ + row];
       }
-      const float inv = L > 0.f ? 1.f / L : 0.f;
+      const float inv = (L > 0.f ? 1.f / L : 0.f) * dscale;
       T* go = static_cast<T*>(p.o) + b * p.o_bs + static_cast<long long>(row) * p.o_rs + static_cast<long long>(h) * HD + c0;
       uint32_t w8[8];
 #pragma unroll
@@ -836,13 +853,13 @@ static int launch_fwd(const typename AttnParamsOf<DROP>::type& p, cudaStream_t s
   return MRB_OK;
 }
 
-template <typename T>
-static int launch_xq(const AttnParams& p, cudaStream_t s) {
+template <typename T, bool DROP = false>
+static int launch_xq(const typename AttnParamsOf<DROP>::type& p, cudaStream_t s) {
   const int LkP = (p.Lk + 15) & ~15;
   const int smem = (32 + 2 * LkP) * 64 * 2;
   static int cfg = 0;
-  if (cfg < smem) { if (int rc = set_smem(attn_xq_kernel<T>, smem)) return rc; cfg = smem; }
-  MRB_LAUNCH((attn_xq_kernel<T>), dim3(p.H, p.B), 128, smem, s, p);
+  if (cfg < smem) { if (int rc = set_smem(attn_xq_kernel<T, DROP>, smem)) return rc; cfg = smem; }
+  MRB_LAUNCH((attn_xq_kernel<T, DROP>), dim3(p.H, p.B), 128, smem, s, p);
   MRB_CHECK_LAUNCH();
   return MRB_OK;
 }
@@ -898,18 +915,19 @@ static int attention_fwd_impl(const void* q, long long q_bs, long long q_rs, con
   p.lse = lse;
   if (int rc = check_attn(p, dtype)) return rc;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
+  // few queries x a few hundred keys, no bias / mask (Q-Former cross-attention): one-shot K/V fetch, keys split over the warps
+  static int use_xq = -1;                 // MRB_ATTN_XQ=0 keeps the generic kernel (A/B measurements)
+  if (use_xq < 0) { const char* e = getenv("MRB_ATTN_XQ"); use_xq = (e && e[0] == '0') ? 0 : 1; }
+  const bool xq_shape = use_xq && hd == 64 && Lq <= 32 && Lk > 64 && Lk <= 16 * 4 * XQ_MAXG && !bias && !kmask && !causal && !lse &&
+                        p.kv_div == 1 && 4 * 32 * (64 + 2) * 4 + 8 * 32 * 4 <= 2 * ((Lk + 15) & ~15) * 64 * 2;
   if (drop_seed && drop_p > 0.f) {
     if (hd > 64 || drop_p >= 1.f) return MRB_ERR_UNSUPPORTED;
     const DropSpec d = make_drop(drop_seed, drop_site, drop_p);
     p.drop_seed = d.seed; p.drop_site = d.site; p.drop_thr = d.thr; p.drop_scale = d.scale;
+    if (xq_shape) return dtype == MRB_DT_F16 ? launch_xq<__half, true>(p, s) : launch_xq<__nv_bfloat16, true>(p, s);
     return dtype == MRB_DT_F16 ? launch_fwd<__half, 64, true>(p, s) : launch_fwd<__nv_bfloat16, 64, true>(p, s);
   }
-  // few queries x a few hundred keys, no bias / mask (Q-Former cross-attention): one-shot K/V fetch, keys split over the warps
-  static int use_xq = -1;                 // MRB_ATTN_XQ=0 keeps the generic kernel (A/B measurements)
-  if (use_xq < 0) { const char* e = getenv("MRB_ATTN_XQ"); use_xq = (e && e[0] == '0') ? 0 : 1; }
-  if (use_xq && hd == 64 && Lq <= 32 && Lk > 64 && Lk <= 16 * 4 * XQ_MAXG && !bias && !kmask && !causal && !lse && p.kv_div == 1 &&
-      4 * 32 * (64 + 2) * 4 + 8 * 32 * 4 <= 2 * ((Lk + 15) & ~15) * 64 * 2)
-    return dtype == MRB_DT_F16 ? launch_xq<__half>(p, s) : launch_xq<__nv_bfloat16>(p, s);
+  if (xq_shape) return dtype == MRB_DT_F16 ? launch_xq<__half>(p, s) : launch_xq<__nv_bfloat16>(p, s);
   if (dtype == MRB_DT_F16) return hd <= 64 ? launch_fwd<__half, 64>(p, s) : launch_fwd<__half, 96>(p, s);
   return hd <= 64 ? launch_fwd<__nv_bfloat16, 64>(p, s) : launch_fwd<__nv_bfloat16, 96>(p, s);
 }

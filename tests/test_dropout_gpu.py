@@ -187,6 +187,12 @@ def test_attention_probability_dropout_fwd_bwd(word, impl, dtype, B, H, Lq, Lk, 
     ops.attention_fwd(q.detach(), k.detach(), v.detach(), out, B, H, Lq, Lk, hd, scale, (Lq * rs, rs), (Lk * rs, rs), (Lk * rs, rs),
                       (Lq * rs, rs), bias=bias, bias_zero=Lq - 1, kmask=kmask, causal=causal, lse=lse, impl=impl, drop=drop)
     assert _relfro(out, want) < 1e-2
+    if impl == "mma" and not (has_bias or has_mask or causal) and Lq <= 32 and Lk > 64:
+        # forward-only call without lse: the one-shot Q-Former cross-attention kernel (attn_xq_kernel<T, DROP>)
+        o2 = torch.empty_like(out)
+        ops.attention_fwd(q.detach(), k.detach(), v.detach(), o2, B, H, Lq, Lk, hd, scale, (Lq * rs, rs), (Lk * rs, rs), (Lk * rs, rs),
+                          (Lq * rs, rs), impl=impl, drop=drop)
+        assert _relfro(o2, want) < 1e-2
     dq, dk, dv = (torch.empty_like(t) for t in (q, k, v))
     ws = torch.empty((B * H * Lq,), dtype=torch.float32, device="cuda")
     ops.attention_bwd(q.detach(), k.detach(), v.detach(), out, dout, dq, dk, dv, B, H, Lq, Lk, hd, scale, (Lq * rs, rs), (Lk * rs, rs),

@@ -26,7 +26,7 @@ def main(old, new):
     for k, v in b.items():
         def stem(n, strip):
             n = n.split("EEv")[0]                                 # template name + arguments, without the parameter types
-            return re.sub(r"ELb0E$", "E", n) if strip else n
+            return re.sub(r"Lb0E$", "", n) if strip else n
         hit = next((o for strip in (False, True) for o in a if stem(o, False) == stem(k, strip)), None)
         if hit is None:
             print("new      %6d  %s" % (len(v), k[:110]))
