@@ -130,6 +130,15 @@ __device__ __forceinline__ void bwd_tile_rows(uint32_t lane_base, const float* w
           t8[w2] = (((w >> 1) & 0x7f7f7f7fu) | 0x80808080u) - dd.thr7;
         }
       }
+      // DROP, DKV: a thread owns one KEY and walks over queries, i.e. over mask rows: one word per element.  The four lanes of a
+      // key group (keys 4m .. 4m+3 share their words) split the hashing -- lane k of the group evaluates the words of queries
+      // c0 + e8 + k and c0 + e8 + 4 + k -- and exchange them by shuffles (the call is warp-uniform, every lane takes part).
+      uint32_t wq[2] = {0u, 0u};
+      if (DROP && MODE == MODE_DKV) {
+#pragma unroll
+        for (int w2 = 0; w2 < 2; ++w2)
+          wq[w2] = drop_word(dd.key, dd.rowbase + static_cast<uint32_t>(u0 + c0 + e8 + 4 * w2 + (r & 3)) * dd.ng, dd.jg);
+      }
 #pragma unroll
       for (int e2 = 0; e2 < 8; e2 += 2) {
         const int e = e8 + e2;
@@ -143,8 +152,8 @@ __device__ __forceinline__ void bwd_tile_rows(uint32_t lane_base, const float* w
               const uint32_t t = t8[(e2 + q) >> 2];
               keepm = ((e2 + q) & 3) == 0 ? sign_mask<0>(t) : ((e2 + q) & 3) == 1 ? sign_mask<1>(t) : ((e2 + q) & 3) == 2 ? sign_mask<2>(t)
                                                                                                                      : sign_mask<3>(t);
-            } else {                            // streamed query u0 + c, this thread's key: one word per element
-              const uint32_t w = drop_word(dd.key, dd.rowbase + static_cast<uint32_t>(u0 + c) * dd.ng, dd.jg);
+            } else {                            // streamed query u0 + c, this thread's key
+              const uint32_t w = __shfl_sync(0xffffffffu, wq[(e2 + q) >> 2], (r & 28) | ((e2 + q) & 3));
               keepm = (((w >> dd.sh) & 0xffu) >= dd.thr) ? 0xffffffffu : 0u;
             }
           }
