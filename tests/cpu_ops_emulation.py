@@ -341,7 +341,8 @@ def load_engine_module(name):
     for a, b in (('device="cuda"', 'device="cpu"'), ('.to("cuda"', '.to("cpu"'), ('.to(device="cuda"', '.to(device="cpu"'),
                  ("assert self.emb.is_cuda", "pass"), ("torch.cuda.Stream()", "_NoStream()"),
                  ("torch.cuda.is_available()", "True"), ('self.device.type != "cuda"', "False"), (".pin_memory()", ""),
-                 ('@registry.register_model("blip2_mr")', ""), ("DropState(base_seed=", 'DropState(device="cpu", base_seed=')):
+                 ('@registry.register_model("blip2_mr")', ""), ('@registry.register_model("blip2_t5")', ""),
+                 ("DropState(base_seed=", 'DropState(device="cpu", base_seed=')):
         src = src.replace(a, b)
     assert 'device="cuda"' not in src and '.to("cuda"' not in src, [l for l in src.splitlines() if '"cuda"' in l]
     spec = importlib.util.spec_from_loader("mr_blip_b200._%s_cpu" % name, loader=None)
@@ -358,5 +359,13 @@ def load_model_module():
     with cuda_graphs=False (graph capture is CUDA-only)."""
     vision, t5 = load_engine_module("vision"), load_engine_module("t5")
     mod = load_engine_module("blip2_mr")
+    mod.VitEngine, mod.QFormerEngine, mod.T5Engine = vision.VitEngine, vision.QFormerEngine, t5.T5Engine
+    return mod
+
+
+def load_blip2_t5_module():
+    """mr_blip_b200/blip2_t5.py (the thin `blip2_t5` sibling) on the CPU, same arrangement."""
+    vision, t5 = load_engine_module("vision"), load_engine_module("t5")
+    mod = load_engine_module("blip2_t5")
     mod.VitEngine, mod.QFormerEngine, mod.T5Engine = vision.VitEngine, vision.QFormerEngine, t5.T5Engine
     return mod

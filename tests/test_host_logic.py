@@ -1051,3 +1051,28 @@ def test_ctypes_signatures_match_header_and_source_prototypes():
                 defs[name] = args
     for name, sig in _lib.SIGNATURES.items():
         assert name in defs and kinds(defs[name]) == sig, name
+
+
+def test_blip2_t5_host_logic_with_emulated_ops(monkeypatch):
+    """The thin `blip2_t5` sibling (BASELINE.json configs[0] family) over the op stand-ins: loss, logits and beam-search output
+    against its oracle restatement (what tests/test_model_gpu.py::test_blip2_t5_forward_and_generate_vs_oracle checks on the
+    device)."""
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    import cpu_ops_emulation as emu
+    from oracle import blip2_t5 as obt
+    monkeypatch.setenv("MRB_OVERLAP", "0")
+    monkeypatch.setenv("MRB_CUDA_GRAPHS", "0")
+    mod = emu.load_blip2_t5_module()
+    sd0 = init_state_dict(TINY, seed=1234, lora_b_std=0.0)
+    model = mod.Blip2T5(dims=TINY, state_dict=mod.plain_t5_state_dict(sd0)).eval()
+    g = torch.Generator().manual_seed(3)
+    samples = {"image": torch.randn(2, 3, 224, 224, generator=g), "text_input": ["a photo of", "Question: what is shown? Answer:"],
+               "text_output": ["a dog in the garden", "two friends"], "prompt": ["a photo of", "Question: what is shown? Answer:"]}
+    got = model(samples)["loss"].item()
+    want = obt.forward(sd0, TINY, model.t5_tokenizer, samples)
+    assert abs(got - want["loss"].item()) < 5e-3
+    assert _relfro(model._last_logits, want["logits"]) < 2e-2
+    text = model.generate(samples, num_beams=3, max_length=6)
+    want_text, want_seqs = obt.generate(sd0, TINY, model.t5_tokenizer, samples, num_beams=3, max_length=6)
+    assert model._last_sequences.tolist() == want_seqs.tolist() and text == want_text
