@@ -1076,3 +1076,23 @@ def test_blip2_t5_host_logic_with_emulated_ops(monkeypatch):
     text = model.generate(samples, num_beams=3, max_length=6)
     want_text, want_seqs = obt.generate(sd0, TINY, model.t5_tokenizer, samples, num_beams=3, max_length=6)
     assert model._last_sequences.tolist() == want_seqs.tolist() and text == want_text
+
+
+def test_generate_host_logic_with_emulated_ops(tiny_sd, monkeypatch):
+    """BLIP2_MR.generate (prefix, cached incremental decoder, in-place beam reorder, beam-search bookkeeping, post-processing)
+    over the op stand-ins against the oracle's no-cache beam search: token-for-token."""
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    import cpu_ops_emulation as emu
+    from mr_blip_b200.mr_utils import post_process
+    from oracle import blip2_mr as ob, synth
+    monkeypatch.setenv("MRB_OVERLAP", "0")
+    monkeypatch.setenv("MRB_CUDA_GRAPHS", "0")
+    mod = emu.load_model_module()
+    model = mod.BLIP2_MR(dims=TINY, state_dict=tiny_sd, cuda_graphs=False).eval()
+    samples = synth.make_samples(batch=2, frames=2, seed=3)
+    out = model.generate(samples, num_beams=4, max_length=7)
+    want = ob.generate(tiny_sd, TINY, model.t5_tokenizer, samples, post_process, num_beams=4, max_length=7)
+    assert out["sequences"].tolist() == want["sequences"].tolist()
+    assert out["raw_prediction"] == want["raw_prediction"] and out["prediction"] == want["prediction"]
+    assert set(out) >= {"prediction", "raw_prediction", "answer", "qid", "duration"}
