@@ -1,4 +1,6 @@
-"""Time the attention kernels (tcgen05 vs mma.sync) on the path's two big shapes. python tools/attn_bench.py"""
+"""Time the attention kernels (tcgen05 vs mma.sync) on the path's two big shapes. python tools/attn_bench.py [shape] [impl]
+MRB_ATTN_BENCH_DROP=1 adds the train-mode (probability dropout 0.1) variants of the T5 shapes next to the eval-mode ones."""
+import os
 import sys
 
 import torch
@@ -21,7 +23,13 @@ def timeit(fn, iters=5):
     return sorted(ts)[len(ts) // 2]
 
 
+DROP = os.environ.get("MRB_ATTN_BENCH_DROP", "0") == "1"
+WORD = None
+
+
 def main():
+    global WORD
+    WORD = torch.tensor([12345], dtype=torch.int32, device="cuda")
     only = sys.argv[1] if len(sys.argv) > 1 else None
     impls = (sys.argv[2],) if len(sys.argv) > 2 else ("mma", "tc")
     for name, B, H, L, hd, dt, with_bias in [("vit", 240, 16, 257, 88, torch.float16, False),
@@ -45,6 +53,11 @@ def main():
                                                   (L * rs, rs), (L * rs, rs), (L * rs, rs), (L * H * hd, H * hd), bias=bias,
                                                   bias_zero=L - 1, kmask=kmask, impl=impl))
             print("%-14s %-4s %8.3f ms  %7.1f TFLOP/s" % (name, impl, ms, flops / ms / 1e9), flush=True)
+            if DROP and dt == torch.bfloat16:
+                ms = timeit(lambda: ops.attention_fwd(qkv[:, :, 0], qkv[:, :, 1], qkv[:, :, 2], out, B, H, Lq, L, hd, hd ** -0.5,
+                                                      (L * rs, rs), (L * rs, rs), (L * rs, rs), (L * H * hd, H * hd), bias=bias,
+                                                      bias_zero=L - 1, kmask=kmask, impl=impl, drop=(WORD, 0x41, 0.1)))
+                print("%-14s %-4s %8.3f ms  %7.1f TFLOP/s  (dropout 0.1)" % (name, impl, ms, flops / ms / 1e9), flush=True)
         if name.startswith("t5enc") and "tc" in impls:          # backward (dK/dV kernel + dQ kernel + delta), 10 L^2 d flops
             q, k, v = qkv[:, :, 0], qkv[:, :, 1], qkv[:, :, 2]
             lse = torch.empty(B, H, L, device="cuda")
@@ -58,6 +71,14 @@ def main():
                                                   hd ** -0.5, st, st, st, ost, ost, lse, ws, bias=bias, bias_zero=L - 1,
                                                   kmask=kmask, impl="tc"))
             print("%-14s bwd  %8.3f ms  %7.1f TFLOP/s (algorithmic 2.5x fwd)" % (name, ms, 2.5 * flops / ms / 1e9), flush=True)
+            if DROP:
+                drop = (WORD, 0x41, 0.1)
+                ops.attention_fwd(q, k, v, out, B, H, L, L, hd, hd ** -0.5, (L * rs, rs), (L * rs, rs), (L * rs, rs),
+                                  (L * H * hd, H * hd), bias=bias, bias_zero=L - 1, kmask=kmask, lse=lse, impl="tc", drop=drop)
+                ms = timeit(lambda: ops.attention_bwd(q, k, v, out, dout, dqkv[:, :, 0], dqkv[:, :, 1], dqkv[:, :, 2], B, H, L, L, hd,
+                                                      hd ** -0.5, st, st, st, ost, ost, lse, ws, bias=bias, bias_zero=L - 1,
+                                                      kmask=kmask, impl="tc", drop=drop))
+                print("%-14s bwd  %8.3f ms  %7.1f TFLOP/s (dropout 0.1)" % (name, ms, 2.5 * flops / ms / 1e9), flush=True)
 
 
 if __name__ == "__main__":

@@ -20,6 +20,8 @@ cut -c1-200 $O/bench_dropout.json
 # where the dropout step's extra time goes: launch list of one graph-replayed step with dropout on (compare with launch_summary_r01b.csv)
 ( MRB_TRAIN_DROPOUT=1 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off --csv --log-file $O/launches_dropout.csv python tools/profile_one_step.py ) > $O/ncu_list_dropout.log 2>&1
 python tools/summarize_launches.py $O/launches_dropout.csv $O/launch_summary_dropout.csv
+( MRB_ATTN_BENCH_DROP=1 timeout 200 python tools/attn_bench.py "" tc ) > $O/attn_bench_dropout.log 2>&1
+grep -h "dropout\|bwd" $O/attn_bench_dropout.log | cut -c1-120
 ( timeout 200 python tools/gemm_sweep.py default $O/sweep_default.json ) > $O/sweep_default.log 2>&1
 ( MRB_GEMM_SPLITK=1 timeout 200 python tools/gemm_sweep.py splitk $O/sweep_splitk.json ) > $O/sweep_splitk.log 2>&1
 grep -h "dec_\|down32\|lm_head" $O/sweep_default.log $O/sweep_splitk.log | cut -c1-220
