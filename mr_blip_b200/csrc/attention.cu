@@ -40,31 +40,56 @@ constexpr int BQ = 64, BKV = 64, NTHREADS = 128;
 template <typename T> struct MmaType;
 template <> struct MmaType<__half> {
   static __device__ __forceinline__ void mma(float* c, const uint32_t* a, uint32_t b0, uint32_t b1) {
+#ifdef MRB_HOST_SHIM      // tests/cuda_host_shim: the CPU suite runs these kernels with an emulated warp (no effect on the CUDA build)
+    shim::mma_m16n8k16(c, a, b0, b1, MRB_DT_F16);
+#else
     asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
                  : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3]) : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+#endif
   }
   static __device__ __forceinline__ uint32_t pack(float x, float y) { __half2 h = __floats2half2_rn(x, y); return *reinterpret_cast<uint32_t*>(&h); }
 };
 template <> struct MmaType<__nv_bfloat16> {
   static __device__ __forceinline__ void mma(float* c, const uint32_t* a, uint32_t b0, uint32_t b1) {
+#ifdef MRB_HOST_SHIM
+    shim::mma_m16n8k16(c, a, b0, b1, MRB_DT_BF16);
+#else
     asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
                  : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3]) : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+#endif
   }
   static __device__ __forceinline__ uint32_t pack(float x, float y) { __nv_bfloat162 h = __floats2bfloat162_rn(x, y); return *reinterpret_cast<uint32_t*>(&h); }
 };
 
 __device__ __forceinline__ void ldsm_x4(uint32_t* r, uint32_t addr) {
+#ifdef MRB_HOST_SHIM
+  shim::ldsm_x4(r, addr, false);
+#else
   asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+#endif
 }
 __device__ __forceinline__ void ldsm_x4_t(uint32_t* r, uint32_t addr) {
+#ifdef MRB_HOST_SHIM
+  shim::ldsm_x4(r, addr, true);
+#else
   asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+#endif
 }
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, bool valid) {
   const int sz = valid ? 16 : 0;
+#ifdef MRB_HOST_SHIM
+  shim::cp_async16(dst, src, sz);
+#else
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(sz) : "memory");
+#endif
 }
+#ifdef MRB_HOST_SHIM      // the emulated copies complete at once
+__device__ __forceinline__ void cp_async_commit() {}
+template <int N> __device__ __forceinline__ void cp_async_wait() {}
+#else
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+#endif
 
 // Load a [ROWS x HD] tile (row stride HD+8 elements in smem) of a [L, *] matrix; rows >= L and columns >= hd zero-filled.
 template <typename T, int HD, int ROWS>

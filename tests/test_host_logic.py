@@ -1096,3 +1096,103 @@ def test_generate_host_logic_with_emulated_ops(tiny_sd, monkeypatch):
     assert out["sequences"].tolist() == want["sequences"].tolist()
     assert out["raw_prediction"] == want["raw_prediction"] and out["prediction"] == want["prediction"]
     assert set(out) >= {"prediction", "raw_prediction", "answer", "qid", "duration"}
+
+
+@pytest.fixture(scope="module")
+def attention_kernels_on_host(tmp_path_factory):
+    """csrc/attention.cu (the mma.sync flash kernels, forward / backward, eval and DROP instantiations, and the one-shot Q-Former
+    cross-attention kernel) compiled as C++20 over the host shim: mma.sync m16n8k16, ldmatrix(.trans) and cp.async are emulated
+    from their PTX fragment layouts (tests/cuda_host_shim/common.cuh), everything else is the kernel source itself."""
+    import re as _re
+    import shutil
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    d = tmp_path_factory.mktemp("shim_attn")
+    shutil.copy(os.path.join(root, "tests", "cuda_host_shim", "common.cuh"), d)
+    shutil.copy(os.path.join(root, "mr_blip_b200", "csrc", "dropmask.cuh"), d)
+    src = open(os.path.join(root, "mr_blip_b200", "csrc", "attention.cu")).read()
+    src, n1 = _re.subn(r"extern __shared__ __align__\(\d+\) uint8_t smem_attn\[\];", "", src)      # the shim owns the buffer
+    src, n2 = _re.subn(r"extern __shared__ float sp\[\];", "float* sp = reinterpret_cast<float*>(smem_attn);", src)
+    assert n1 >= 4 and n2 == 1
+    open(os.path.join(d, "attention.cu"), "w").write(src)
+    so = os.path.join(d, "attention_host.so")
+    subprocess.check_call(["g++", "-std=c++20", "-O1", "-pthread", "-shared", "-fPIC", "-Wno-unknown-pragmas", "-x", "c++",
+                           os.path.join(d, "attention.cu"), "-o", so])
+    return ctypes.CDLL(so)
+
+
+def _ref_attn(q, k, v, scale, bias, kmask, causal, mask):
+    qf, kf, vf = (t.float().permute(0, 2, 1, 3) for t in (q, k, v))
+    s = torch.matmul(qf, kf.transpose(-1, -2)) * scale
+    B, H, Lq, Lk = s.shape
+    i, j = torch.arange(Lq)[:, None], torch.arange(Lk)[None, :]
+    if bias is not None:
+        s = s + bias[:, (j - i) + (Lq - 1)][None]
+    if kmask is not None:
+        s = s.masked_fill(kmask[:, None, None, :] == 0, float("-inf"))
+    if causal:
+        s = s.masked_fill(j > i, float("-inf"))
+    pr = torch.softmax(s, -1)
+    if mask is not None:
+        pr = pr * mask.view(B, H, Lq, Lk)
+    return torch.matmul(pr, vf).permute(0, 2, 1, 3), torch.logsumexp(s, -1)
+
+
+@pytest.mark.parametrize("dtype,B,H,Lq,Lk,has_bias,has_mask,causal,p", [
+    (torch.bfloat16, 2, 2, 72, 72, True, True, False, 0.1),      # tiny-config T5 encoder
+    (torch.bfloat16, 2, 2, 72, 72, True, True, False, 0.0),      # eval-mode kernels through the same harness
+    (torch.bfloat16, 2, 2, 9, 9, True, True, True, 0.1),         # decoder self-attention
+    (torch.bfloat16, 1, 2, 9, 130, False, True, False, 0.1),     # decoder cross-attention, three key tiles
+    (torch.float16, 2, 3, 32, 32, False, False, False, 0.1),     # Q-Former self-attention
+    (torch.float16, 2, 3, 32, 257, False, False, False, 0.1),    # Q-Former cross-attention (one-shot kernel when no lse is asked)
+    (torch.float16, 2, 3, 32, 257, False, False, False, 0.0),
+])
+def test_attention_kernel_source_runs_on_host_shim(attention_kernels_on_host, dtype, B, H, Lq, Lk, has_bias, has_mask, causal, p):
+    """Forward (O, lse) and backward (dQ, dK, dV) of the mma.sync attention kernels -- with p > 0 their DROP instantiations --
+    executed on the CPU against a torch reference that applies the oracle's mask to the probabilities."""
+    from oracle import dropout as od
+    lib = attention_kernels_on_host
+    c_ll, c_u, c_f = ctypes.c_longlong, ctypes.c_uint, ctypes.c_float
+    hd, site, seed = 64, 0x1041, 0x9E3779B1
+    DT = 1 if dtype == torch.bfloat16 else 0
+    scale = 1.0 if dtype == torch.bfloat16 else hd ** -0.5
+    g = torch.Generator().manual_seed(17)
+    q = (torch.randn(B, Lq, H, hd, generator=g) * 0.5).to(dtype).requires_grad_(True)
+    k = (torch.randn(B, Lk, H, hd, generator=g) * 0.5).to(dtype).requires_grad_(True)
+    v = torch.randn(B, Lk, H, hd, generator=g).to(dtype).requires_grad_(True)
+    bias = torch.randn(H, Lq + Lk - 1, generator=g) if has_bias else None
+    kmask = None
+    if has_mask:
+        kmask = torch.ones((B, Lk), dtype=torch.int32)
+        kmask[-1, Lk - max(1, Lk // 6):] = 0
+    word = torch.tensor([seed - (1 << 32)], dtype=torch.int32)
+    mask = (torch.from_numpy(od.keep_mask(seed, site, B * H * Lq, Lk, p)).float() * float(od.scale_of(p))) if p > 0 else None
+    want, want_lse = _ref_attn(q, k, v, scale, bias, kmask, causal, mask)
+    dout = torch.randn(B, Lq, H, hd, generator=g).to(dtype)
+    want.backward(dout.float())
+    rs = H * hd
+    P = lambda t: ctypes.c_void_p(t.data_ptr()) if t is not None else None
+    out = torch.empty((B, Lq, H, hd), dtype=dtype)
+    lse = torch.empty((B, H, Lq))
+
+    def fwd(o, l):
+        args = [P(q), c_ll(Lq * rs), c_ll(rs), P(k), c_ll(Lk * rs), c_ll(rs), P(v), c_ll(Lk * rs), c_ll(rs), P(o), c_ll(Lq * rs), c_ll(rs),
+                B, H, Lq, Lk, hd, DT, c_f(scale), P(bias), (Lq + Lk - 1) if has_bias else 0, Lq - 1, P(kmask), 1, int(causal), 0, P(l)]
+        if p > 0:
+            return lib.mrb_attention_fwd_drop(*args, P(word), c_u(site), c_f(p), None)
+        return lib.mrb_attention_fwd(*args, None)
+
+    assert fwd(out, lse) == 0
+    assert _relfro(out, want) < 1e-2
+    assert _relfro(lse, want_lse) < 1e-3
+    if not (has_bias or has_mask or causal) and Lq <= 32 and Lk > 64:      # no lse asked: attn_xq_kernel
+        o2 = torch.empty_like(out)
+        assert fwd(o2, None) == 0 and _relfro(o2, want) < 1e-2
+    dq, dk, dv = (torch.empty_like(t) for t in (q, k, v))
+    ws = torch.empty((B * H * Lq,))
+    args = [P(q), c_ll(Lq * rs), c_ll(rs), P(k), c_ll(Lk * rs), c_ll(rs), P(v), c_ll(Lk * rs), c_ll(rs), P(out), c_ll(Lq * rs), c_ll(rs),
+            P(dout), c_ll(Lq * rs), c_ll(rs), P(dq), P(dk), P(dv), B, H, Lq, Lk, hd, DT, c_f(scale), P(bias),
+            (Lq + Lk - 1) if has_bias else 0, Lq - 1, P(kmask), int(causal), 0, P(lse), P(ws)]
+    rc = lib.mrb_attention_bwd_drop(*args, P(word), c_u(site), c_f(p), None) if p > 0 else lib.mrb_attention_bwd(*args, None)
+    assert rc == 0
+    assert _relfro(dv, v.grad) < 1.5e-2 and _relfro(dq, q.grad) < 2e-2 and _relfro(dk, k.grad) < 2e-2
