@@ -62,6 +62,7 @@ struct Block {
   std::vector<std::unique_ptr<std::barrier<>>> warp;
   std::vector<uint32_t> xchg;
   std::vector<uint32_t> regs;        // [warp][32 lanes][8]: register exchange of the emulated mma.sync / ldmatrix
+  std::atomic<int> count{0};         // __syncthreads_count
 };
 inline Block* g_block = nullptr;
 inline thread_local int t_linear = 0;
@@ -97,6 +98,18 @@ void launch(dim3 grid, dim3 block, F&& body) {
 }  // namespace shim
 
 inline void __syncthreads() { shim::g_block->all->arrive_and_wait(); }
+inline int __syncthreads_count(int pred) {
+  shim::Block& b = *shim::g_block;
+  if (pred) b.count.fetch_add(1);
+  b.all->arrive_and_wait();
+  const int r = b.count.load();
+  b.all->arrive_and_wait();
+  if (shim::t_linear == 0) b.count.store(0);
+  b.all->arrive_and_wait();
+  return r;
+}
+inline float rsqrtf(float x) { return 1.0f / sqrtf(x); }
+inline float __fdiv_rn(float a, float b) { return a / b; }
 inline void __syncwarp() { shim::g_block->warp[shim::t_linear >> 5]->arrive_and_wait(); }
 inline uint32_t shim_shfl_xor_bits(uint32_t v, int o) {
   shim::Block& b = *shim::g_block;
@@ -135,6 +148,7 @@ alignas(1024) inline uint8_t smem_attn[512 * 1024];
 struct __half { uint16_t x; };
 struct __nv_bfloat16 { uint16_t x; };
 struct __half2 { uint16_t x, y; };
+inline __half __ushort_as_half(unsigned short u) { return {u}; }
 struct __nv_bfloat162 { uint16_t x, y; };
 
 inline float atomicAdd(float* p, float v) { return std::atomic_ref<float>(*p).fetch_add(v, std::memory_order_relaxed); }
@@ -183,6 +197,7 @@ inline float gelu_erf_grad(float x) {
 }
 }  // namespace mrb
 
+inline float __half2float(__half h) { return mrb::f16_to_f(h.x); }
 inline __half2 __floats2half2_rn(float a, float b) { return {mrb::f16_rn(a), mrb::f16_rn(b)}; }
 inline __nv_bfloat162 __floats2bfloat162_rn(float a, float b) { return {mrb::bf16_rn(a), mrb::bf16_rn(b)}; }
 

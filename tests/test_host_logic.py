@@ -1196,3 +1196,134 @@ def test_attention_kernel_source_runs_on_host_shim(attention_kernels_on_host, dt
     rc = lib.mrb_attention_bwd_drop(*args, P(word), c_u(site), c_f(p), None) if p > 0 else lib.mrb_attention_bwd(*args, None)
     assert rc == 0
     assert _relfro(dv, v.grad) < 1.5e-2 and _relfro(dq, q.grad) < 2e-2 and _relfro(dk, k.grad) < 2e-2
+
+
+@pytest.fixture(scope="module")
+def elementwise_kernels_on_host(tmp_path_factory):
+    """csrc/elementwise.cu (norms, gated GELU, interleave gather, cross-entropy, LoRA helpers, casts ...) over the host shim."""
+    import shutil
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    d = tmp_path_factory.mktemp("shim_elt")
+    shutil.copy(os.path.join(root, "tests", "cuda_host_shim", "common.cuh"), d)
+    for f in ("elementwise.cu", "dropmask.cuh"):
+        shutil.copy(os.path.join(root, "mr_blip_b200", "csrc", f), d)
+    so = os.path.join(d, "elementwise_host.so")
+    subprocess.check_call(["g++", "-std=c++20", "-O1", "-pthread", "-shared", "-fPIC", "-Wno-unknown-pragmas", "-x", "c++",
+                           os.path.join(d, "elementwise.cu"), "-o", so])
+    return ctypes.CDLL(so)
+
+
+def test_elementwise_kernel_source_runs_on_host_shim(elementwise_kernels_on_host):
+    """The HBM-bound kernels of the path executed on the CPU through the host shim against torch (the checks
+    tests/test_kernels_gpu.py makes on the device): a regression guard for their index arithmetic that needs no GPU."""
+    lib = elementwise_kernels_on_host
+    c_ll, c_f = ctypes.c_longlong, ctypes.c_float
+    P = lambda t: ctypes.c_void_p(t.data_ptr()) if t is not None else None
+    BF, F16 = 1, 0
+    g = torch.Generator().manual_seed(9)
+    # ---- norms: LayerNorm (+16-bit strided out), RMSNorm, RMSNorm backward
+    rows, C = 19, 768
+    x, w, b = torch.randn(rows, C, generator=g), torch.randn(C, generator=g), torch.randn(C, generator=g)
+    o32, oh = torch.empty(rows, C), torch.zeros((rows, C + 32), dtype=torch.float16)
+    assert lib.mrb_norm(P(x), None, P(w), P(b), c_f(1e-6), rows, C, 0, P(o32), P(oh), F16, c_ll(C + 32), None, None) == 0
+    want = torch.nn.functional.layer_norm(x, (C,), w, b, 1e-6)
+    assert _relfro(o32, want) < 1e-5 and _relfro(oh[:, :C], want) < 1e-3 and oh[:, C:].abs().max().item() == 0
+    C = 2048
+    x, w = torch.randn(rows, C, generator=g), torch.randn(C, generator=g)
+    ob = torch.zeros((rows, C + 32), dtype=torch.bfloat16)
+    assert lib.mrb_norm(P(x), None, P(w), None, c_f(1e-6), rows, C, 1, None, P(ob), BF, c_ll(C + 32), None, None) == 0
+    xr = x.clone().requires_grad_(True)
+    y = w * (xr * torch.rsqrt(xr.pow(2).mean(-1, keepdim=True) + 1e-6))
+    assert _relfro(ob[:, :C], y) < 4e-3
+    dy = torch.randn(rows, C, generator=g).to(torch.bfloat16)
+    y.backward(dy.float())
+    dres = torch.ones(rows, C)
+    assert lib.mrb_rmsnorm_bwd(P(x), P(w), P(dy), BF, c_ll(C), None, 0, c_f(1e-6), rows, C, P(dres), None) == 0
+    assert _relfro(dres - 1.0, xr.grad) < 1e-4
+    # ---- gated GELU forward / backward
+    M, Fd = 7, 5120
+    ab = torch.randn(M, 2 * Fd, generator=g).to(torch.bfloat16)
+    a, bb = ab[:, :Fd].float().requires_grad_(True), ab[:, Fd:].float().requires_grad_(True)
+    want = torch.nn.functional.gelu(a) * bb
+    h = torch.zeros((M, Fd + 32), dtype=torch.bfloat16)
+    assert lib.mrb_gated_gelu_fwd(P(ab), P(h), M, Fd, c_ll(Fd + 32), BF, None) == 0
+    assert _relfro(h[:, :Fd], want) < 4e-3
+    dh = torch.randn(M, Fd, generator=g).to(torch.bfloat16)
+    want.backward(dh.float())
+    dab = torch.zeros((M, 2 * Fd + 32), dtype=torch.bfloat16)
+    assert lib.mrb_gated_gelu_bwd(P(ab), P(dh), c_ll(Fd), P(dab), c_ll(2 * Fd + 32), M, Fd, BF, None) == 0
+    assert _relfro(dab[:, :Fd], a.grad) < 6e-3 and _relfro(dab[:, Fd:2 * Fd], bb.grad) < 6e-3
+    # ---- interleave gather / scatter, frame-token mean
+    C = 2048
+    emb, frames = torch.randn(50, C, generator=g), torch.randn(12, C, generator=g)
+    idx = torch.tensor([3, -1, -12, -(1 << 31), 49, -5, 0, -5], dtype=torch.int32)
+    out = torch.full((8, C), 7.0)
+    assert lib.mrb_gather_rows(P(idx), P(emb), P(frames), P(out), 8, C, None) == 0
+    want = torch.stack([emb[3], frames[0], frames[11], torch.zeros(C), emb[49], frames[4], emb[0], frames[4]])
+    assert torch.equal(out, want)
+    dout, dfr = torch.randn(8, C, generator=g), torch.zeros(12, C)
+    assert lib.mrb_scatter_frames(P(idx), P(dout), P(dfr), 8, C, None) == 0
+    wfr = torch.zeros(12, C)
+    wfr[0], wfr[11] = dout[1], dout[2]                     # a frame token sits in exactly one row of the table: plain stores ...
+    assert torch.equal(dfr[[0, 11]], wfr[[0, 11]]) and dfr[[1, 2, 3, 5, 6, 7, 8, 9, 10]].abs().max().item() == 0
+    assert torch.equal(dfr[4], dout[5]) or torch.equal(dfr[4], dout[7])      # ... (a duplicated index keeps one of its rows)
+    xm, om = torch.randn(3 * 32, C, generator=g), torch.empty(3, C)
+    assert lib.mrb_group_mean(P(xm), P(om), 3, 32, C, None) == 0 and _relfro(om, xm.view(3, 32, C).mean(1)) < 1e-6
+    # ---- cross-entropy with ignored targets, mean over the valid ones taken inside the kernel
+    V = 32128
+    lg = (torch.randn(5, V, generator=g) * 2).requires_grad_(True)
+    lab = torch.tensor([5, -100, 31000, 1, -100], dtype=torch.int64)
+    loss = torch.nn.functional.cross_entropy(lg, lab, ignore_index=-100)
+    loss.backward()
+    ls, dl = torch.zeros(1), torch.zeros((5, V + 32), dtype=torch.bfloat16)
+    assert lib.mrb_cross_entropy(P(lg.detach()), P(lab), 5, V, None, P(dl), BF, c_ll(V + 32), c_f(-1.0), P(ls), None) == 0
+    assert abs(ls.item() - loss.item()) < 1e-5 and _relfro(dl[:, :V], lg.grad) < 5e-3
+    # ---- LoRA helpers: weight-gradient reduction (both kernels), tiny-M down-projection, operand re-pack
+    for M in (40, 700):
+        Pm = torch.randn(M, 264, generator=g).to(torch.bfloat16)
+        Q = torch.randn(M, 16, generator=g).to(torch.bfloat16)
+        for tr in (0, 1):
+            o = torch.ones((8, 264) if tr else (264, 8))
+            assert lib.mrb_skinny_wgrad(P(Pm), c_ll(264), ctypes.c_void_p(Q.data_ptr() + 16), c_ll(16), M, 264, P(o), tr, BF, None) == 0
+            want = Pm.float().t() @ Q[:, 8:16].float()
+            assert _relfro((o - 1.0).t() if tr else o - 1.0, want) < 1e-4, (M, tr)
+    xs, Wd = torch.randn(5, 2048 + 32, generator=g).to(torch.bfloat16), torch.randn(32, 2048, generator=g).to(torch.bfloat16)
+    od = torch.zeros((5, 32), dtype=torch.bfloat16)
+    assert lib.mrb_small_down(P(xs), c_ll(2048 + 32), P(Wd), c_ll(2048), 5, 2048, P(od), c_ll(32), BF, None) == 0
+    assert _relfro(od, xs[:, :2048].float() @ Wd.float().t()) < 4e-3
+    K, N, scale = 264, 520, 0.5
+    A, B = torch.randn(8, K, generator=g), torch.randn(N, 8, generator=g)
+    ext = torch.zeros((N, K + 32), dtype=torch.bfloat16)
+    bdn, adn = torch.zeros((32, N), dtype=torch.bfloat16), torch.zeros((32, K), dtype=torch.bfloat16)
+    extb = torch.zeros((K, N + 32), dtype=torch.bfloat16)
+    es = 2
+    rec = [A.data_ptr(), B.data_ptr(), ext.data_ptr() + (K + 8) * es, K + 32, bdn.data_ptr() + 8 * N * es, N, adn.data_ptr() + 8 * K * es, K,
+           extb.data_ptr() + (N + 8) * es, N + 32, K, N, int(np.float64(scale).view(np.int64))]
+    table = torch.from_numpy(np.asarray([rec], dtype=np.int64))
+    assert lib.mrb_lora_pack(P(table), 1, 1, BF, None) == 0
+    sB = (B * scale).to(torch.bfloat16)
+    assert torch.equal(ext[:, K + 8:K + 16], sB) and torch.equal(bdn[8:16], sB.t()) and ext[:, :K + 8].abs().max().item() == 0
+    assert torch.equal(adn[8:16], A.to(torch.bfloat16)) and torch.equal(extb[:, N + 8:N + 16], A.to(torch.bfloat16).t())
+    # ---- plumbing: strided cast, 16-bit transpose, column sums; patch extraction from fp32 and (fused normalisation) from uint8
+    xin = torch.randn(9, 300, generator=g)
+    oc = torch.zeros((9, 296 + 32), dtype=torch.bfloat16)
+    assert lib.mrb_cast2d_f32_to_h(P(xin), c_ll(300), P(oc), c_ll(296 + 32), 9, 296, BF, None) == 0
+    assert torch.equal(oc[:, :296], xin[:, :296].to(torch.bfloat16)) and oc[:, 296:].abs().max().item() == 0
+    t_in = torch.randn(37, 70, generator=g).to(torch.bfloat16)
+    t_out = torch.zeros((70, 40), dtype=torch.bfloat16)
+    assert lib.mrb_transpose16(P(t_in), c_ll(70), P(t_out), c_ll(40), 37, 70, None) == 0
+    assert torch.equal(t_out[:, :37], t_in.t()) and t_out[:, 37:].abs().max().item() == 0
+    cs = torch.zeros(300)
+    assert lib.mrb_colsum(P(xin), 9, 300, P(cs), None) == 0 and torch.allclose(cs, xin.sum(0), atol=1e-5)
+    Fr, S, Pp = 2, 28, 14
+    u8 = torch.randint(0, 256, (Fr, 3, S, S), generator=g, dtype=torch.uint8)
+    mean, std = (0.48145466, 0.4578275, 0.40821073), (0.26862954, 0.26130258, 0.27577711)
+    img = (u8.float() / 255.0 - torch.tensor(mean).view(1, 3, 1, 1)) / torch.tensor(std).view(1, 3, 1, 1)
+    ld = 592
+    a1, a2 = torch.zeros((Fr * 4, ld), dtype=torch.float16), torch.ones((Fr * 4, ld), dtype=torch.float16)
+    assert lib.mrb_patchify(P(img), P(a1), F16, Fr, S, Pp, ld, None) == 0
+    assert lib.mrb_patchify_u8(P(u8), P(a2), F16, Fr, S, Pp, ld, *(c_f(v) for v in mean + std), None) == 0
+    want = img.view(Fr, 3, 2, Pp, 2, Pp).permute(0, 2, 4, 1, 3, 5).reshape(Fr * 4, 588).to(torch.float16)
+    assert torch.equal(a1[:, :588], want) and a1[:, 588:].abs().max().item() == 0
+    assert _relfro(a2[:, :588], want) < 1e-3 and a2[:, 588:].abs().max().item() == 0
