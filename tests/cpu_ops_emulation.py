@@ -332,8 +332,9 @@ class _NoStream:
         pass
 
 
-def load_engine_module(name):
-    """mr_blip_b200/<name>.py compiled with its device strings pointing at the CPU and `ops` bound to this module."""
+def load_engine_module(name, ops_module=None):
+    """mr_blip_b200/<name>.py compiled with its device strings pointing at the CPU and `ops` bound to this module (or to
+    `ops_module`, e.g. the product's own ops.py over a HostCAbi)."""
     import mr_blip_b200
     import sys
     path = os.path.join(os.path.dirname(mr_blip_b200.__file__), name + ".py")
@@ -350,8 +351,50 @@ def load_engine_module(name):
     mod.__package__ = "mr_blip_b200"
     mod.__dict__["_NoStream"] = _NoStream
     exec(compile(src, path + " (cpu emulation)", "exec"), mod.__dict__)
-    mod.ops = sys.modules[__name__]
+    mod.ops = ops_module if ops_module is not None else sys.modules[__name__]
     return mod
+
+
+class HostCAbi:
+    """Stands in for mr_blip_b200._lib.call on the CPU: every C-ABI entry point whose kernels are not tcgen05 / TMA code is
+    served by the KERNEL SOURCE itself, compiled over tests/cuda_host_shim (csrc/elementwise.cu, dropout.cu, attention.cu); the
+    tcgen05 entry points are mapped onto their same-contract siblings (attention_*_tc -> the mma.sync kernels, skinny_wgrad_tc ->
+    the CUDA-core kernel) and the GEMM onto a torch matmul over the raw pointers.  With the product's ops.py on top this runs
+    wrapper -> ctypes signature -> C entry point -> kernel source end to end without a GPU."""
+    ALIAS = {"mrb_attention_fwd_tc": "mrb_attention_fwd", "mrb_attention_bwd_tc": "mrb_attention_bwd",
+             "mrb_attention_fwd_tc_drop": "mrb_attention_fwd_drop", "mrb_attention_bwd_tc_drop": "mrb_attention_bwd_drop",
+             "mrb_skinny_wgrad_tc": "mrb_skinny_wgrad"}
+
+    def __init__(self, libs):
+        from mr_blip_b200 import _lib
+        self.libs, self.sigs, self.calls = libs, _lib.SIGNATURES, {}
+
+    def _gemm(self, A, lda, B, ldb, M, N, K, dtype, bias, gelu, resid, ldr, out, out_dtype, ldc, row_group, force_bn, stream):
+        assert row_group == 0
+        y = _from_ptr(A, M, K, lda, _TDT[dtype]).float() @ _from_ptr(B, N, K, ldb, _TDT[dtype]).float().t()
+        if bias:
+            y = y + _from_ptr(bias, 1, N, N, torch.float32)
+        if gelu:
+            y = F.gelu(y)
+        if resid:
+            y = y + _from_ptr(resid, M, N, ldr, torch.float32)
+        o = _from_ptr(out, M, N, ldc, _TDT[out_dtype])
+        o.copy_(y.to(o.dtype))
+
+    def call(self, name, *args):
+        self.calls[name] = self.calls.get(name, 0) + 1
+        if name == "mrb_gemm":
+            return self._gemm(*args)
+        if name == "mrb_skinny_wgrad_tc2":
+            P, ldp, Q, ldq, M, C, out, out2, tr, dt, st = args
+            self.call("mrb_skinny_wgrad", P, ldp, Q, ldq, M, C, out, tr, dt, st)
+            return self.call("mrb_skinny_wgrad", P, ldp, Q + 16, ldq, M, C, out2, tr, dt, st)
+        sym = self.ALIAS.get(name, name)
+        fn = next((getattr(l, sym) for l in self.libs if hasattr(l, sym)), None)
+        assert fn is not None, "no host build of " + sym
+        fn.argtypes, fn.restype = self.sigs[name], ctypes.c_int
+        rc = fn(*args)
+        assert rc == 0, (name, rc)
 
 
 def load_model_module():

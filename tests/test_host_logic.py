@@ -1327,3 +1327,57 @@ def test_elementwise_kernel_source_runs_on_host_shim(elementwise_kernels_on_host
     want = img.view(Fr, 3, 2, Pp, 2, Pp).permute(0, 2, 4, 1, 3, 5).reshape(Fr * 4, 588).to(torch.float16)
     assert torch.equal(a1[:, :588], want) and a1[:, 588:].abs().max().item() == 0
     assert _relfro(a2[:, :588], want) < 1e-3 and a2[:, 588:].abs().max().item() == 0
+
+
+@pytest.mark.parametrize("train_dropout", [False, True])
+def test_t5_engine_through_the_real_c_abi_on_host_kernels(monkeypatch, train_dropout, elementwise_kernels_on_host,
+                                                          dropout_kernels_on_host, attention_kernels_on_host):
+    """T5Engine.loss (forward + hand-written backward) through the PRODUCT's ops.py wrappers and ctypes signatures into the
+    kernel sources compiled for the host (every launch except the tcgen05 GEMM, which is a torch matmul over the same pointers):
+    loss, logits, d inputs_embeds and all LoRA gradients against the oracle -- in train mode with every dropout site on.
+    A narrow T5 (d_model 256, 4 heads of 64, d_ff 512, one layer per stack): one OS thread per CUDA thread is slow -- the
+    full-width 2-layer config takes 6 minutes per case here (it passed); the widths do not change which code runs."""
+    from dataclasses import replace
+    NARROW = replace(FULL, t5_layers=1, t5_dec_layers=1, d_model=256, t5_heads=4, d_ff=512, vocab=1024)
+    tiny_sd = init_state_dict(NARROW, seed=77, lora_b_std=0.02, parts=("t5",))
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    import cpu_ops_emulation as emu
+    from mr_blip_b200 import _lib, ops
+    from mr_blip_b200.dropout import DropState
+    from oracle import t5 as ot5
+    from oracle.dropout import Dropper
+    monkeypatch.setenv("MRB_OVERLAP", "0")
+    abi = emu.HostCAbi([elementwise_kernels_on_host, dropout_kernels_on_host, attention_kernels_on_host])
+    monkeypatch.setattr(_lib, "call", abi.call)
+    monkeypatch.setattr(ops, "_check", lambda t, *d: t)
+    monkeypatch.setattr(ops, "_stream", lambda: None)
+    t5mod = emu.load_engine_module("t5", ops_module=ops)
+    params = {k: v.clone() for k, v in tiny_sd.items()}
+    eng = t5mod.T5Engine(NARROW, params.__getitem__)
+    emb, mask, labels = _t5_case(NARROW)
+    dmask = (labels != -100).long()
+    drop = None
+    if train_dropout:
+        eng.drop = DropState(device="cpu")
+        drop = Dropper(eng.drop.set_seed(0xC0FFEE11))
+    eng.zero_grads()
+    out = eng.loss(emb.clone(), mask, labels, dmask, backward=True, want_logits=True)
+    sd = dict(tiny_sd)
+    leaves = {k: sd[k].clone().requires_grad_(True) for k in sd if "lora_" in k}
+    sd.update(leaves)
+    e = emb.clone().requires_grad_(True)
+    o = ot5.t5_forward(sd, NARROW, e, mask, labels, dmask, drop=drop)
+    o["loss"].backward()
+    assert abs(out["loss"].item() - o["loss"].item()) < 5e-3
+    assert _relfro(out["logits"], o["logits"]) < 2e-2
+    assert _relfro(out["d_inputs_embeds"], e.grad) < 4e-2
+    grads = {id(p): g for p, g in eng.param_grads()}
+    for k, leaf in leaves.items():
+        assert _relfro(grads[id(params[k])], leaf.grad) < 4e-2, k
+    want_calls = {"mrb_gemm", "mrb_norm", "mrb_rmsnorm_bwd", "mrb_attention_fwd", "mrb_attention_bwd", "mrb_cross_entropy", "mrb_gather_rows"}
+    if train_dropout:
+        want_calls = (want_calls - {"mrb_attention_fwd", "mrb_attention_bwd"}) | {
+            "mrb_attention_fwd_drop", "mrb_attention_bwd_drop", "mrb_dropout", "mrb_dropout_add", "mrb_gated_gelu_fwd_drop",
+            "mrb_gated_gelu_bwd_drop", "mrb_lora_down_drop", "mrb_lora_wgrad_drop", "mrb_lora_dx_drop"}
+    assert want_calls <= set(abi.calls), sorted(set(abi.calls))
