@@ -1,5 +1,10 @@
-"""CPU-only checks of the host side: C-ABI exports, registry / model surface, prompt table, tokenizer,
-state-dict key names.  No compute call is made (no GPU here)."""
+"""CPU-only checks of the host side: C-ABI exports and signatures, registry / model surface, prompt table, tokenizer,
+state-dict key names, recipes, training loop mechanics -- and, without a GPU, as much of the device path as a CPU can run:
+  * the engines and the whole model over torch stand-ins of the C-ABI ops (tests/cpu_ops_emulation.py) against the oracle;
+  * the kernel SOURCES that are not tcgen05 / TMA code (csrc/elementwise.cu, dropout.cu, attention.cu) compiled as C++20 over a
+    host shim of the CUDA execution model (tests/cuda_host_shim/common.cuh) against torch / the oracle;
+  * both stacked: T5Engine through the product's ops.py and ctypes signatures into those host-built kernels.
+No call into libmrblip_b200.so computes anything here; kernel arithmetic on the device is the `-m gpu` suite's job."""
 import ctypes
 import json
 import math
