@@ -103,8 +103,6 @@ class BLIP2_MR(Blip2Base):
             self.video_processor_answerer_eval = VideoProcessor(image_size=img_size, n_frms=num_frames_for_answer)
         if "lora" not in task:
             raise NotImplementedError("only LoRA tasks are implemented (every mr_BLIP yaml uses qformer_freeze_lora)")
-        if not interleave_data:
-            raise NotImplementedError("non-interleaved prompt design is not used by any mr_BLIP recipe")
         self.task = task
         self.use_lora = True
         self.post_process = mr_utils.post_process
@@ -339,6 +337,14 @@ class BLIP2_MR(Blip2Base):
         else:
             text_prompt = [q + t for q, t in zip(query_prompt, task_prompt)]
         text = tok(text_prompt, padding="longest", truncation=True, max_length=self.max_txt_len, return_tensors="pt")
+        if not self.interleave_data:
+            # blip2_mr.py:784-822: [video_prompt (the timestamps as text) | all frame tokens | video_prompt_end | query + task]
+            vp = tok(video_prompt, padding="longest", add_special_tokens=False, truncation=True, max_length=self.max_txt_len,
+                     return_tensors="pt")
+            frame_rows = -(np.arange(B)[:, None] * (T * n) + np.arange(T * n)[None, :]) - 1
+            table = np.concatenate([vp.input_ids.numpy(), frame_rows, end.input_ids.numpy(), text.input_ids.numpy()], axis=1)
+            atts = torch.cat([vp.attention_mask, torch.ones((B, T * n), dtype=torch.long), end.attention_mask, text.attention_mask], dim=1)
+            return table.astype(np.int32), atts, [p_ + "frames" + e_ for p_, e_ in zip(video_prompt, video_prompt_end)]
         rows = []
         for j in range(B):
             ts_ids = self._clean_ids(ts_list[j].tolist())

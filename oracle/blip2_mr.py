@@ -60,10 +60,26 @@ def clean_timestamp_ids(tok, values):
 
 def prompt_concatenation(sd, d, tok, timestamps, durations, frames_for_t5, video_prompt_end, query_prompt,
                          task_prompt, n_per_frame, table=None, max_txt_len=200, prefix=_t5.PREFIX,
-                         input_time_format="seconds_integers"):
+                         input_time_format="seconds_integers", interleave_data=True):
     """blip2_mr.py:572-824, interleave branch:
-       [f_0 (n) | ts_0 | f_1 | ts_1 | ... | '>' | duration] (left-padded) ++ video_prompt_end ++ query+task."""
+       [f_0 (n) | ts_0 | f_1 | ts_1 | ... | '>' | duration] (left-padded) ++ video_prompt_end ++ query+task;
+    interleave_data=False (:784-822): video_prompt (the timestamps as text) ++ all frame tokens ++ video_prompt_end ++ query+task."""
     emb = sd[prefix + "shared.weight"]
+    if not interleave_data:
+        # the prompt string comes from the reference-pinned helpers (mr_utils_golden.json / time_formats_golden.json)
+        from mr_blip_b200 import mr_utils
+        fn = {"seconds_integers": mr_utils.get_timestamps_as_seconds_integers, "seconds_floats": mr_utils.get_timestamps_as_seconds_floats,
+              "relative_integers": mr_utils.get_timestamps_as_relative_integers, "relative_floats": mr_utils.get_timestamps_as_relative_floats,
+              "framenumbers": mr_utils.get_timestamps_as_framenumbers}[input_time_format]
+        video_prompt = fn(torch.as_tensor(timestamps), torch.as_tensor(durations), table or {})[2]
+        kw = dict(padding="longest", truncation=True, max_length=max_txt_len, return_tensors="pt")
+        vp = tok(video_prompt, add_special_tokens=False, **kw)
+        end = tok(video_prompt_end, add_special_tokens=False, **kw)
+        text = tok([q + t for q, t in zip(query_prompt, task_prompt)], **kw)
+        inputs = torch.cat([emb[vp.input_ids], frames_for_t5, emb[end.input_ids], emb[text.input_ids]], dim=1)
+        atts = torch.cat([vp.attention_mask, torch.ones(frames_for_t5.shape[:2], dtype=torch.long), end.attention_mask,
+                          text.attention_mask], dim=1)
+        return inputs, atts
     ts, ds = time_values(input_time_format, timestamps, durations, table or {})
     end = tok(video_prompt_end, padding="longest", add_special_tokens=False, truncation=True,
               max_length=max_txt_len, return_tensors="pt")
@@ -93,7 +109,7 @@ def prompt_concatenation(sd, d, tok, timestamps, durations, frames_for_t5, video
 
 
 def forward_mr(sd, d, tok, samples, frame_token_aggregation=None, table=None, max_txt_len=200,
-               input_time_format="seconds_integers", drop=None):
+               input_time_format="seconds_integers", drop=None, interleave_data=True):
     """blip2_mr.py:433-570 -> dict(loss, logits, inputs_embeds, attention_mask, labels, ...).  drop: None = eval mode, a
     Dropper (oracle/dropout.py) = the train-mode dropout of the Q-Former, T5 and LoRA inputs (the ViT stays in eval mode:
     blip2_mr.py:136-137)."""
@@ -101,7 +117,8 @@ def forward_mr(sd, d, tok, samples, frame_token_aggregation=None, table=None, ma
     n = 1 if frame_token_aggregation else d.num_query
     inputs, atts = prompt_concatenation(sd, d, tok, samples["timestamps"], samples["duration"], f,
                                         samples["video_prompt_end"], samples["query_prompt"],
-                                        samples["task_prompt"], n, table, max_txt_len, input_time_format=input_time_format)
+                                        samples["task_prompt"], n, table, max_txt_len, input_time_format=input_time_format,
+                                        interleave_data=interleave_data)
     ans = tok(samples["relevant_windows"], padding="longest", truncation=True, max_length=max_txt_len,
               return_tensors="pt")
     labels = ans.input_ids.masked_fill(ans.input_ids == tok.pad_token_id, -100)

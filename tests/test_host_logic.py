@@ -854,8 +854,9 @@ def test_swar_keep_compare_of_the_tcgen05_attention_kernels():
     assert od.thr_of(0.05) % 2 == 1          # LoRA's 0.05 is odd: it never reaches these kernels (byte compare in csrc/dropout.cu)
 
 
-@pytest.mark.parametrize("train_dropout,agg", [(False, None), (True, None), (True, "mean")])
-def test_whole_model_train_step_host_logic_with_emulated_ops(tiny_sd, monkeypatch, train_dropout, agg):
+@pytest.mark.parametrize("train_dropout,agg,interleave", [(False, None, True), (True, None, True), (True, "mean", True),
+                                                         (False, None, False)])
+def test_whole_model_train_step_host_logic_with_emulated_ops(tiny_sd, monkeypatch, train_dropout, agg, interleave):
     """BLIP2_MR.forward in train() -- host phase, ViT / Q-Former / interleave gather / T5 loss, the hand-written backward into the
     flat gradient buffer, t5_proj gradients, the gradient hand-over to autograd, and with train_dropout the per-step seed word and
     every dropout site -- run on the CPU over the op stand-ins against the oracle (same checks as tests/test_model_gpu.py::
@@ -868,7 +869,7 @@ def test_whole_model_train_step_host_logic_with_emulated_ops(tiny_sd, monkeypatc
     from oracle.dropout import Dropper
     monkeypatch.setenv("MRB_OVERLAP", "0")
     mod = emu.load_model_module()
-    model = mod.BLIP2_MR(dims=TINY, state_dict=tiny_sd, cuda_graphs=False, train_dropout=train_dropout)
+    model = mod.BLIP2_MR(dims=TINY, state_dict=tiny_sd, cuda_graphs=False, train_dropout=train_dropout, interleave_data=interleave)
     model.frame_token_aggregation = agg
     model.train()
     samples = synth.make_samples(batch=2, frames=2, seed=3)
@@ -880,7 +881,8 @@ def test_whole_model_train_step_host_logic_with_emulated_ops(tiny_sd, monkeypatc
     sd = dict(tiny_sd)
     leaves = {k: sd[k].clone().requires_grad_(True) for k in sd if "lora_" in k or k.startswith("t5_proj.")}
     sd.update(leaves)
-    o = ob.forward_mr(sd, TINY, model.t5_tokenizer, samples, frame_token_aggregation=agg, drop=drop)
+    o = ob.forward_mr(sd, TINY, model.t5_tokenizer, samples, frame_token_aggregation=agg, drop=drop, table=model.annoying_numbers_replacement_dict,
+                      interleave_data=interleave)
     o["loss"].backward()
     assert torch.equal(res["attention_mask"], o["attention_mask"]) and torch.equal(res["labels"], o["labels"])
     assert _relfro(res["qformer"], o["qformer"]) < 2e-3
