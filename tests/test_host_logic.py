@@ -1388,3 +1388,45 @@ def test_t5_engine_through_the_real_c_abi_on_host_kernels(monkeypatch, train_dro
             "mrb_attention_fwd_drop", "mrb_attention_bwd_drop", "mrb_dropout", "mrb_dropout_add", "mrb_gated_gelu_fwd_drop",
             "mrb_gated_gelu_bwd_drop", "mrb_lora_down_drop", "mrb_lora_wgrad_drop", "mrb_lora_dx_drop"}
     assert want_calls <= set(abi.calls), sorted(set(abi.calls))
+
+
+@pytest.mark.parametrize("train", [False, True])
+def test_qformer_engine_through_the_real_c_abi_on_host_kernels(monkeypatch, train, elementwise_kernels_on_host, dropout_kernels_on_host,
+                                                               attention_kernels_on_host):
+    """QFormerEngine.forward (ln_vision, batched cross K/V projection, self / cross attention incl. the one-shot kernel, FFN, and
+    in train mode the frozen Q-Former's dropout) through ops.py and the ctypes signatures into the host-compiled kernel sources,
+    against the oracle.  Narrow widths (hidden 128 = 2 heads of 64, 2 layers, encoder width 176) for the same reason as above."""
+    import sys
+    from dataclasses import replace
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    import cpu_ops_emulation as emu
+    from mr_blip_b200 import _lib, ops
+    from mr_blip_b200.dropout import DropState
+    from oracle import qformer as oqf, vit as ovit
+    from oracle.dropout import Dropper
+    NARROW = replace(FULL, vit_width=176, vit_heads=2, vit_mlp=352, vit_depth=1, qf_hidden=128, qf_heads=2, qf_inter=256, qf_layers=2,
+                     d_model=256, t5_heads=4, d_ff=512, vocab=1024, t5_layers=1, t5_dec_layers=1)
+    sd = init_state_dict(NARROW, seed=78, parts=("qformer",))
+    g = torch.Generator().manual_seed(6)
+    sd["ln_vision.weight"], sd["ln_vision.bias"] = 1.0 + 0.1 * torch.randn(176, generator=g), 0.1 * torch.randn(176, generator=g)
+    abi = emu.HostCAbi([elementwise_kernels_on_host, dropout_kernels_on_host, attention_kernels_on_host])
+    monkeypatch.setattr(_lib, "call", abi.call)
+    monkeypatch.setattr(ops, "_check", lambda t, *d: t)
+    monkeypatch.setattr(ops, "_stream", lambda: None)
+    vmod = emu.load_engine_module("vision", ops_module=ops)
+    eng = vmod.QFormerEngine(NARROW, {k: v.clone() for k, v in sd.items()}.__getitem__)
+    frames = 2
+    vit_out = torch.randn(frames * NARROW.vit_tokens, NARROW.vit_width, generator=g)
+    drop = None
+    if train:
+        eng.drop = DropState(device="cpu")
+        drop = Dropper(eng.drop.set_seed(0xBEEF))
+    h, _ = eng.forward(vit_out, frames)
+    with torch.no_grad():
+        ie = ovit.ln_vision(sd, NARROW, vit_out.view(frames, NARROW.vit_tokens, -1))
+        want = oqf.qformer_forward(sd, NARROW, ie, drop=drop)
+    assert _relfro(h.view(frames, NARROW.num_query, -1), want) < 3e-3
+    want_calls = {"mrb_gemm", "mrb_norm", "mrb_attention_fwd", "mrb_cast_f32_to_h"}
+    if train:
+        want_calls = (want_calls - {"mrb_attention_fwd"}) | {"mrb_attention_fwd_drop", "mrb_dropout", "mrb_dropout_add"}
+    assert want_calls <= set(abi.calls), sorted(set(abi.calls))
