@@ -370,12 +370,19 @@ class HostCAbi:
         self.libs, self.sigs, self.calls = libs, _lib.SIGNATURES, {}
 
     def _gemm(self, A, lda, B, ldb, M, N, K, dtype, bias, gelu, resid, ldr, out, out_dtype, ldc, row_group, force_bn, stream):
-        assert row_group == 0
         y = _from_ptr(A, M, K, lda, _TDT[dtype]).float() @ _from_ptr(B, N, K, ldb, _TDT[dtype]).float().t()
         if bias:
             y = y + _from_ptr(bias, 1, N, N, torch.float32)
         if gelu:
             y = F.gelu(y)
+        if row_group > 0:            # patch embed: out_row = (m / G) * (G + 1) + 1 + m % G, resid_row = 1 + m % G
+            m = torch.arange(M)
+            orow = (m // row_group) * (row_group + 1) + 1 + m % row_group
+            if resid:
+                y = y + _from_ptr(resid, row_group + 1, N, ldr, torch.float32)[1 + m % row_group]
+            o = _from_ptr(out, (M // row_group) * (row_group + 1), N, ldc, _TDT[out_dtype])
+            o[orow] = y.to(o.dtype)
+            return
         if resid:
             y = y + _from_ptr(resid, M, N, ldr, torch.float32)
         o = _from_ptr(out, M, N, ldc, _TDT[out_dtype])

@@ -1430,3 +1430,33 @@ def test_qformer_engine_through_the_real_c_abi_on_host_kernels(monkeypatch, trai
     if train:
         want_calls = (want_calls - {"mrb_attention_fwd"}) | {"mrb_attention_fwd_drop", "mrb_dropout", "mrb_dropout_add"}
     assert want_calls <= set(abi.calls), sorted(set(abi.calls))
+
+
+def test_vit_engine_through_the_real_c_abi_on_host_kernels(monkeypatch, elementwise_kernels_on_host, dropout_kernels_on_host,
+                                                           attention_kernels_on_host):
+    """VitEngine.forward (patch extraction, cls / pos rows, patch-embed GEMM with the row remap, LayerNorm, the 256 + 1 split of
+    the 257 query rows over the tile kernel and the single-row kernel, head dim 88, MLP) through ops.py and the ctypes
+    signatures into the host-compiled kernel sources against the oracle.  One narrow block (width 176 = 2 heads of 88)."""
+    import sys
+    from dataclasses import replace
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    import cpu_ops_emulation as emu
+    from mr_blip_b200 import _lib, ops
+    from oracle import vit as ovit
+    NARROW = replace(FULL, vit_width=176, vit_heads=2, vit_mlp=352, vit_depth=1)
+    sd = init_state_dict(NARROW, seed=79, parts=("vit",))
+    abi = emu.HostCAbi([elementwise_kernels_on_host, dropout_kernels_on_host, attention_kernels_on_host])
+    monkeypatch.setattr(_lib, "call", abi.call)
+    monkeypatch.setattr(ops, "_check", lambda t, *d: t)
+    monkeypatch.setattr(ops, "_stream", lambda: None)
+    monkeypatch.setenv("MRB_OVERLAP", "0")
+    vmod = emu.load_engine_module("vision", ops_module=ops)
+    half = {k: (v.half() if (v.ndim >= 2 and "pos_embed" not in k and "cls_token" not in k) else v) for k, v in sd.items()}
+    eng = vmod.VitEngine(NARROW, half.__getitem__)
+    g = torch.Generator().manual_seed(8)
+    frames = torch.randn(2, 3, 224, 224, generator=g)
+    x = eng.forward(frames)
+    with torch.no_grad():
+        want = ovit.vit_forward(sd, NARROW, frames)
+    assert _relfro(x.view(2, NARROW.vit_tokens, -1), want) < 2e-3
+    assert {"mrb_patchify", "mrb_cls_pos", "mrb_gemm", "mrb_norm", "mrb_attention_fwd_tc", "mrb_attention_row"} <= set(abi.calls), sorted(abi.calls)
