@@ -404,11 +404,11 @@ class HostCAbi:
         assert rc == 0, (name, rc)
 
 
-def load_model_module():
-    """mr_blip_b200/blip2_mr.py on the CPU: its engines are the CPU-compiled engine modules, its ops this module.  Build the model
-    with cuda_graphs=False (graph capture is CUDA-only)."""
-    vision, t5 = load_engine_module("vision"), load_engine_module("t5")
-    mod = load_engine_module("blip2_mr")
+def load_model_module(ops_module=None):
+    """mr_blip_b200/blip2_mr.py on the CPU: its engines are the CPU-compiled engine modules, its ops this module (or
+    `ops_module`).  Build the model with cuda_graphs=False (graph capture is CUDA-only)."""
+    vision, t5 = load_engine_module("vision", ops_module), load_engine_module("t5", ops_module)
+    mod = load_engine_module("blip2_mr", ops_module)
     mod.VitEngine, mod.QFormerEngine, mod.T5Engine = vision.VitEngine, vision.QFormerEngine, t5.T5Engine
     return mod
 

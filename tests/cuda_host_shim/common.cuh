@@ -12,7 +12,9 @@
 #include <algorithm>
 #include <atomic>
 #include <barrier>
+#include <condition_variable>
 #include <functional>
+#include <mutex>
 #include <memory>
 #include <thread>
 #include <vector>
@@ -67,6 +69,46 @@ struct Block {
 inline Block* g_block = nullptr;
 inline thread_local int t_linear = 0;
 
+// worker threads are created once and reused by every launch (thread creation dominated the run time of the engine-level tests)
+struct Pool {
+  std::vector<std::thread> th;
+  std::mutex m;
+  std::condition_variable cv, done_cv;
+  std::function<void(int)> job;
+  int nactive = 0, generation = 0, remaining = 0;
+  void worker(int id, int seen) {
+    for (;;) {
+      bool mine;
+      {
+        std::unique_lock<std::mutex> lk(m);
+        cv.wait(lk, [&] { return generation != seen; });
+        seen = generation;
+        mine = id < nactive;
+      }
+      if (mine) {
+        job(id);
+        std::lock_guard<std::mutex> lk(m);
+        if (--remaining == 0) done_cv.notify_one();
+      }
+    }
+  }
+  void run(int n, std::function<void(int)> f) {
+    {
+      std::lock_guard<std::mutex> lk(m);
+      while (static_cast<int>(th.size()) < n) {
+        const int id = static_cast<int>(th.size()), seen = generation;
+        th.emplace_back([this, id, seen] { worker(id, seen); });
+        th.back().detach();
+      }
+      job = std::move(f); nactive = n; remaining = n; ++generation;
+    }
+    cv.notify_all();
+    std::unique_lock<std::mutex> lk(m);
+    done_cv.wait(lk, [&] { return remaining == 0; });
+  }
+};
+inline Pool& pool() { static Pool* p = new Pool(); return *p; }      // never destroyed: its threads are parked for good at exit
+
 template <typename F>
 void launch(dim3 grid, dim3 block, F&& body) {
   const int nthr = static_cast<int>(block.x * block.y * block.z);
@@ -77,9 +119,8 @@ void launch(dim3 grid, dim3 block, F&& body) {
   blk.xchg.assign(nwarp * 32, 0u);
   blk.regs.assign(nwarp * 32 * 8, 0u);
   g_block = &blk;
-  std::vector<std::thread> pool;
-  for (int t = 0; t < nthr; ++t) {
-    pool.emplace_back([&, t] {
+  pool().run(nthr, [&](int t) {
+    {
       t_linear = t;
       blockDim = block; gridDim = grid;
       threadIdx = {static_cast<unsigned>(t) % block.x, (static_cast<unsigned>(t) / block.x) % block.y, static_cast<unsigned>(t) / (block.x * block.y)};
@@ -90,9 +131,8 @@ void launch(dim3 grid, dim3 block, F&& body) {
             body();
             blk.all->arrive_and_wait();          // blocks run one after another (static __shared__ storage is reused)
           }
-    });
-  }
-  for (auto& th : pool) th.join();
+    }
+  });
   g_block = nullptr;
 }
 }  // namespace shim

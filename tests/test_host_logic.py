@@ -1336,7 +1336,7 @@ def test_elementwise_kernel_source_runs_on_host_shim(elementwise_kernels_on_host
     assert _relfro(a2[:, :588], want) < 1e-3 and a2[:, 588:].abs().max().item() == 0
 
 
-@pytest.mark.parametrize("train_dropout", [False, True])
+@pytest.mark.parametrize("train_dropout", [False] + ([True] if os.environ.get("MRB_TEST_SLOW", "0") == "1" else []))   # train mode: the whole-model test below
 def test_t5_engine_through_the_real_c_abi_on_host_kernels(monkeypatch, train_dropout, elementwise_kernels_on_host,
                                                           dropout_kernels_on_host, attention_kernels_on_host):
     """T5Engine.loss (forward + hand-written backward) through the PRODUCT's ops.py wrappers and ctypes signatures into the
@@ -1460,3 +1460,45 @@ def test_vit_engine_through_the_real_c_abi_on_host_kernels(monkeypatch, elementw
         want = ovit.vit_forward(sd, NARROW, frames)
     assert _relfro(x.view(2, NARROW.vit_tokens, -1), want) < 2e-3
     assert {"mrb_patchify", "mrb_cls_pos", "mrb_gemm", "mrb_norm", "mrb_attention_fwd_tc", "mrb_attention_row"} <= set(abi.calls), sorted(abi.calls)
+
+
+def test_whole_model_train_step_through_the_real_c_abi_on_host_kernels(monkeypatch, elementwise_kernels_on_host, dropout_kernels_on_host,
+                                                                       attention_kernels_on_host):
+    """BLIP2_MR.forward in train() with train_dropout -- the whole step: frames -> ViT -> Q-Former -> t5_proj -> interleave gather ->
+    T5 loss -> hand-written backward -> t5_proj gradients -> gradient hand-over -- through ops.py, the ctypes signatures and the
+    host-compiled kernel sources (only the tcgen05 GEMM is a torch matmul), against the oracle with the same seed word.
+    Narrow widths, one layer per stack, full vocabulary (the synthetic tokenizer's ids)."""
+    import sys
+    from dataclasses import replace
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    import cpu_ops_emulation as emu
+    from mr_blip_b200 import _lib, ops
+    from oracle import blip2_mr as ob, synth
+    from oracle.dropout import Dropper
+    NARROW = replace(FULL, vit_width=176, vit_heads=2, vit_mlp=352, vit_depth=1, qf_hidden=128, qf_heads=2, qf_inter=256, qf_layers=2,
+                     d_model=256, t5_heads=4, d_ff=512, t5_layers=1, t5_dec_layers=1)
+    sd = init_state_dict(NARROW, seed=80, lora_b_std=0.02)
+    abi = emu.HostCAbi([elementwise_kernels_on_host, dropout_kernels_on_host, attention_kernels_on_host])
+    monkeypatch.setattr(_lib, "call", abi.call)
+    monkeypatch.setattr(ops, "_check", lambda t, *d: t)
+    monkeypatch.setattr(ops, "_stream", lambda: None)
+    monkeypatch.setenv("MRB_OVERLAP", "0")
+    mod = emu.load_model_module(ops_module=ops)
+    model = mod.BLIP2_MR(dims=NARROW, state_dict=sd, cuda_graphs=False, train_dropout=True).train()
+    samples = synth.make_samples(batch=1, frames=2, seed=3)
+    res = model.forward_mr(samples, want_logits=True)
+    res["loss"].backward()
+    osd = dict(sd)
+    leaves = {k: osd[k].clone().requires_grad_(True) for k in osd if "lora_" in k or k.startswith("t5_proj.")}
+    osd.update(leaves)
+    o = ob.forward_mr(osd, NARROW, model.t5_tokenizer, samples, drop=Dropper(model.drop_state.seed))
+    o["loss"].backward()
+    assert _relfro(res["qformer"], o["qformer"]) < 3e-3
+    assert _relfro(res["inputs_embeds"], o["inputs_embeds"]) < 3e-3
+    assert abs(res["loss"].item() - o["loss"].item()) < 5e-3
+    assert _relfro(res["logits"], o["logits"]) < 2e-2
+    for k, leaf in leaves.items():
+        got = model._get(k).grad
+        assert got is not None and _relfro(got, leaf.grad) < 4e-2, k
+    assert {"mrb_lora_pack", "mrb_patchify", "mrb_gather_rows", "mrb_scatter_frames", "mrb_colsum", "mrb_transpose16",
+            "mrb_attention_fwd_drop", "mrb_attention_bwd_drop", "mrb_lora_dx_drop"} <= set(abi.calls), sorted(abi.calls)
