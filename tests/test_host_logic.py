@@ -1502,3 +1502,16 @@ def test_whole_model_train_step_through_the_real_c_abi_on_host_kernels(monkeypat
         assert got is not None and _relfro(got, leaf.grad) < 4e-2, k
     assert {"mrb_lora_pack", "mrb_patchify", "mrb_gather_rows", "mrb_scatter_frames", "mrb_colsum", "mrb_transpose16",
             "mrb_attention_fwd_drop", "mrb_attention_bwd_drop", "mrb_lora_dx_drop"} <= set(abi.calls), sorted(abi.calls)
+
+
+def test_dropout_seed_word_per_step_and_rank():
+    """DropState: a new seed word every step, different streams for different base seeds (BLIP2_MR adds the rank, as the
+    reference's setup_seeds(seed + rank) does, train.py:57-58), reproducible from (base seed, step)."""
+    from mr_blip_b200.dropout import DropState
+    a, b, c = DropState(device="cpu", base_seed=0), DropState(device="cpu", base_seed=1), DropState(device="cpu", base_seed=0)
+    sa = [a.advance() for _ in range(50)]
+    sb = [b.advance() for _ in range(50)]
+    sc = [c.advance() for _ in range(50)]
+    assert sa == sc and len(set(sa)) == 50 and not set(sa) & set(sb)
+    assert (a.word.item() & 0xFFFFFFFF) == sa[-1]
+    assert a.attn(5, 0.1) == (a.word, 5, 0.1) and a.attn(5, 0.0) is None and DropState(device="cpu", attention=False).attn(5, 0.1) is None
