@@ -1515,3 +1515,34 @@ def test_dropout_seed_word_per_step_and_rank():
     assert sa == sc and len(set(sa)) == 50 and not set(sa) & set(sb)
     assert (a.word.item() & 0xFFFFFFFF) == sa[-1]
     assert a.attn(5, 0.1) == (a.word, 5, 0.1) and a.attn(5, 0.0) is None and DropState(device="cpu", attention=False).attn(5, 0.1) is None
+
+
+@pytest.mark.skipif(os.environ.get("MRB_TEST_SLOW", "0") != "1", reason="one more minute of host-shim time: set MRB_TEST_SLOW=1")
+def test_generate_through_the_real_c_abi_on_host_kernels(monkeypatch, elementwise_kernels_on_host, dropout_kernels_on_host,
+                                                         attention_kernels_on_host):
+    """BLIP2_MR.generate (prefix + cached incremental decoder: attention over the K/V cache with a query offset, beams of a clip
+    as query rows of one cross-attention problem, tiny-M down-projections) through ops.py and the host-compiled kernel sources:
+    token-for-token against the oracle's no-cache beam search.  Narrow widths."""
+    import sys
+    from dataclasses import replace
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    import cpu_ops_emulation as emu
+    from mr_blip_b200 import _lib, ops
+    from mr_blip_b200.mr_utils import post_process
+    from oracle import blip2_mr as ob, synth
+    NARROW = replace(FULL, vit_width=176, vit_heads=2, vit_mlp=352, vit_depth=1, qf_hidden=128, qf_heads=2, qf_inter=256, qf_layers=2,
+                     d_model=256, t5_heads=4, d_ff=512, t5_layers=1, t5_dec_layers=1)
+    sd = init_state_dict(NARROW, seed=80, lora_b_std=0.02)
+    abi = emu.HostCAbi([elementwise_kernels_on_host, dropout_kernels_on_host, attention_kernels_on_host])
+    monkeypatch.setattr(_lib, "call", abi.call)
+    monkeypatch.setattr(ops, "_check", lambda t, *d: t)
+    monkeypatch.setattr(ops, "_stream", lambda: None)
+    monkeypatch.setenv("MRB_OVERLAP", "0")
+    monkeypatch.setenv("MRB_CUDA_GRAPHS", "0")
+    mod = emu.load_model_module(ops_module=ops)
+    model = mod.BLIP2_MR(dims=NARROW, state_dict=sd, cuda_graphs=False).eval()
+    samples = synth.make_samples(batch=1, frames=2, seed=3)
+    out = model.generate(samples, num_beams=3, max_length=5)
+    want = ob.generate(sd, NARROW, model.t5_tokenizer, samples, post_process, num_beams=3, max_length=5)
+    assert out["sequences"].tolist() == want["sequences"].tolist() and out["raw_prediction"] == want["raw_prediction"]
+    assert "mrb_small_down" in abi.calls
