@@ -1546,3 +1546,41 @@ def test_generate_through_the_real_c_abi_on_host_kernels(monkeypatch, elementwis
     want = ob.generate(sd, NARROW, model.t5_tokenizer, samples, post_process, num_beams=3, max_length=5)
     assert out["sequences"].tolist() == want["sequences"].tolist() and out["raw_prediction"] == want["raw_prediction"]
     assert "mrb_small_down" in abi.calls
+
+
+def test_splitk_reduce_kernel_source_runs_on_host_shim(tmp_path):
+    """The second pass of mrb_gemm_splitk (csrc/gemm.cu splitk_reduce_kernel: ordered sum of the fp32 partials, then bias, exact
+    GELU, fp32 residual, output type) cut out of its translation unit -- the rest of gemm.cu is tcgen05 / TMA code -- and run on the
+    host shim against torch.  (The planner is covered by test_gemm_splitk_plan...; the partial-sum GEMM itself needs the GPU.)"""
+    import shutil
+    import subprocess
+    src = open(os.path.join(ROOT, "mr_blip_b200", "csrc", "gemm.cu")).read()
+    i = src.index("__global__ void __launch_bounds__(256)\nsplitk_reduce_kernel(")
+    j = src.index("// Split-K plan.")
+    kernel = src[i:j]
+    shutil.copy(os.path.join(ROOT, "tests", "cuda_host_shim", "common.cuh"), tmp_path)
+    tu = tmp_path / "reduce.cu"
+    tu.write_text('#include "common.cuh"\nnamespace mrb {\n' + kernel + '}\nusing namespace mrb;\n'
+                  'extern "C" int run(const float* ws, int splits, long long stride, int M, int N, const float* bias, int gelu,\n'
+                  '                   const float* resid, long long ldr, void* out, int out_dtype, long long ldc, int blocks) {\n'
+                  '  MRB_LAUNCH((splitk_reduce_kernel), blocks, 256, 0, nullptr, ws, splits, stride, M, N, bias, gelu, resid, ldr, out, out_dtype, ldc);\n'
+                  '  return 0;\n}\n')
+    so = str(tmp_path / "reduce.so")
+    subprocess.check_call(["g++", "-std=c++20", "-O1", "-pthread", "-shared", "-fPIC", "-Wno-unknown-pragmas", "-x", "c++", str(tu), "-o", so])
+    lib = ctypes.CDLL(so)
+    P = lambda t: ctypes.c_void_p(t.data_ptr()) if t is not None else None
+    g = torch.Generator().manual_seed(2)
+    M, N, splits = 56, 264, 5
+    ws = torch.randn(splits, M, N, generator=g)
+    bias, resid = torch.randn(N, generator=g), torch.randn(M, N + 8, generator=g)
+    total = ws[0].clone()
+    for sp in range(1, splits):
+        total += ws[sp]                                   # the kernel's summation order
+    out = torch.full((M, N + 4), 7.0)
+    assert lib.run(P(ws), splits, ctypes.c_longlong(M * N), M, N, P(bias), 1, P(resid), ctypes.c_longlong(N + 8), P(out), 2,
+                   ctypes.c_longlong(N + 4), 3) == 0
+    assert torch.allclose(out[:, :N], torch.nn.functional.gelu(total + bias) + resid[:, :N], rtol=1e-5, atol=1e-5)
+    assert (out[:, N:] == 7.0).all()
+    o16 = torch.zeros((M, N), dtype=torch.bfloat16)
+    assert lib.run(P(ws), splits, ctypes.c_longlong(M * N), M, N, None, 0, None, ctypes.c_longlong(0), P(o16), 1, ctypes.c_longlong(N), 40) == 0
+    assert torch.equal(o16, total.to(torch.bfloat16))
