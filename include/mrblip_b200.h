@@ -61,6 +61,14 @@ int mrb_attention_fwd_tc(const void* q, long long q_bs, long long q_rs, const vo
                          const void* v, long long v_bs, long long v_rs, void* o, long long o_bs, long long o_rs,
                          int B, int H, int Lq, int Lk, int hd, int dtype, float scale, const float* bias, int bias_len,
                          int bias_zero, const int* kmask, int kv_div, int causal, int q_pos0, float* lse, void* stream);
+/* Self-attention of the EVA ViT over every (frame, head) -- Attention.forward of lavis/models/eva_vit.py:128-145 between the qkv
+ * and proj Linears (no relative position bias at eva_vit.py:416-428) -- as ONE persistent tcgen05 kernel specialised for
+ * L = 257 tokens (CLS + 256 patches) and 64 < hd <= 96 (hd % 8 == 0; ViT-g: 88): per item S = Q K^T is a 128 x 256 MMA per
+ * query group, P is written back into tensor memory and O += P V reads it from there, the CLS token (as key and as query) is
+ * rank-1 work on CUDA cores (csrc/attention_vit.cu).  q / k / v / o point at token 0, head 0 of frame 0; strides in elements. */
+int mrb_attention_vit(const void* q, long long q_bs, long long q_rs, const void* k, long long k_bs, long long k_rs,
+                      const void* v, long long v_bs, long long v_rs, void* o, long long o_bs, long long o_rs,
+                      int frames, int H, int L, int hd, int dtype, float scale, void* stream);
 /* dQ, dK, dV of the above (autograd of modeling_t5.py:561-610); hd <= 64. delta_ws: fp32 [B*H*Lq] workspace. */
 int mrb_attention_bwd(const void* q, long long q_bs, long long q_rs, const void* k, long long k_bs, long long k_rs,
                       const void* v, long long v_bs, long long v_rs, const void* o, long long o_bs, long long o_rs,

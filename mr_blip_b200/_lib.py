@@ -16,6 +16,7 @@ SIGNATURES = {
     "mrb_attention_fwd": [_p, _ll, _ll, _p, _ll, _ll, _p, _ll, _ll, _p, _ll, _ll, _i, _i, _i, _i, _i, _i, _f, _p, _i, _i,
                           _p, _i, _i, _i, _p, _p],
     "mrb_attention_row": [_p, _ll, _p, _ll, _ll, _p, _ll, _ll, _p, _ll, _i, _i, _i, _i, _i, _f, _p],
+    "mrb_attention_vit": [_p, _ll, _ll, _p, _ll, _ll, _p, _ll, _ll, _p, _ll, _ll, _i, _i, _i, _i, _i, _f, _p],
     "mrb_attention_fwd_tc": [_p, _ll, _ll, _p, _ll, _ll, _p, _ll, _ll, _p, _ll, _ll, _i, _i, _i, _i, _i, _i, _f, _p, _i, _i,
                              _p, _i, _i, _i, _p, _p],
     "mrb_attention_bwd": [_p, _ll, _ll, _p, _ll, _ll, _p, _ll, _ll, _p, _ll, _ll, _p, _ll, _ll, _p, _p, _p,

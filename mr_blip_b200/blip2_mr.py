@@ -64,11 +64,16 @@ class _GraphedStep:
         self.graph = None
         self.calls = 0
         self.n_launch = 0
+        self.staged = None                                   # event: the previous step's H2D copy of the pinned buffer has run
 
     def stage(self, host, video):
+        if self.staged is not None:
+            self.staged.synchronize()                        # the pinned buffer is still the source of an in-flight async copy
         for name in self.h:
             self.h[name].copy_(torch.from_numpy(host[name]).view(self.h[name].shape))
         self.dev.copy_(self.host, non_blocking=True)
+        self.staged = torch.cuda.Event()
+        self.staged.record()
         self.video.copy_(video.reshape(self.video.shape), non_blocking=True)
 
 
@@ -88,7 +93,7 @@ class BLIP2_MR(Blip2Base):
                  interleave_data=True, frame_token_aggregation=None, task="qformer_freeze_lora",
                  num_frames_for_answer=4, resample_frames=False, dims: Dims = None, init_seed=1234,
                  lora_b_std=0.0, state_dict=None, tokenizer=None, cuda_graphs=True, graph_bucket=(32, 8),
-                 train_dropout=None, dropout_seed=0):
+                 train_dropout=None, dropout_seed=0, allow_synthetic=True):
         super().__init__()
         self.dims = d = dims or FULL
         assert img_size == d.img_size and num_query_token == d.num_query
@@ -155,7 +160,7 @@ class BLIP2_MR(Blip2Base):
             logging.info("freeze vision encoder")
 
         # ---- tokenizer + number-token hygiene (blip2_mr.py:143,165-168) ----------------------------
-        self.t5_tokenizer = tokenizer or load_t5_tokenizer(t5_model)
+        self.t5_tokenizer = tokenizer or load_t5_tokenizer(t5_model, allow_synthetic=allow_synthetic)
         self.annoying_numbers, _ = mr_utils.find_annoying_numbers(self.t5_tokenizer, 200)
         self.annoying_numbers_replacement_dict = mr_utils.find_annoying_numbers_replacement_dict(self.annoying_numbers)
         self.seperator_token = self.t5_tokenizer.convert_tokens_to_ids(">")
@@ -172,19 +177,28 @@ class BLIP2_MR(Blip2Base):
         self._seen = {}                                      # shape signature -> times seen (survives LRU eviction)
         self._graph_pool = None
         self._in_device_step = False
-        # Train-mode dropout (the reference's train() step: Q-Former / T5 0.1, LoRA inputs 0.05; mr_blip_b200/dropout.py).  Written
-        # after round 1's GPU budget was spent -- compiled and reviewed but not yet run on hardware -- hence opt-in:
-        # train_dropout=True or MRB_TRAIN_DROPOUT=1.  Off: train() steps run the eval() arithmetic as before.
-        self.train_dropout = (os.environ.get("MRB_TRAIN_DROPOUT", "0") == "1") if train_dropout is None else bool(train_dropout)
+        # Train-mode dropout (the reference's train() step: Q-Former / T5 0.1, LoRA inputs 0.05; mr_blip_b200/dropout.py): ON by
+        # default, as in the reference, where module.train() switches every nn.Dropout on.  train_dropout=False (or
+        # MRB_TRAIN_DROPOUT=0) makes train() steps run the eval() arithmetic -- rate 0 -- which is what the parity tests of the
+        # hand-written backward against the (mask-free) golden gradients use.
+        self.train_dropout = (os.environ.get("MRB_TRAIN_DROPOUT", "1") != "0") if train_dropout is None else bool(train_dropout)
         self.dropout_seed = int(dropout_seed)
         self.drop_state = None
 
     # ---------------------------------------------------------------------------------------------
     @classmethod
     def from_config(cls, cfg):
-        """Same keys as blip2_mr.py:1420-1464.  `pretrained` / `finetuned` are loaded when they are local files;
-        otherwise the seeded synthetic weights stay (no network in this environment)."""
+        """Same keys as blip2_mr.py:1420-1464.  The third-party pieces the reference fetches from hubs (tokenizer, FlanT5, EVA ViT,
+        BLIP-2 / Mr. BLIP checkpoints) must be LOCAL files here (no network).  When one of them is missing this raises -- a run on the
+        synthetic tokenizer and seeded random weights would train and evaluate on garbage without ever failing -- unless the recipe says
+        `allow_synthetic: true` (dry runs, tests, benchmarks)."""
         get = cfg.get
+        synth = bool(get("allow_synthetic", False))
+        if not synth:
+            t5 = get("t5_model", "google/flan-t5-xl")
+            if not (isinstance(t5, str) and os.path.isdir(t5)):
+                raise RuntimeError("model.t5_model=%r is not a local FlanT5 directory: the T5 weights would stay seeded random values. "
+                                   "Set model.t5_model to a local directory, or model.allow_synthetic: true for a dry run" % (t5,))
         model = cls(img_size=get("image_size", 224), drop_path_rate=get("drop_path_rate", 0),
                     use_grad_checkpoint=get("use_grad_checkpoint", False), vit_precision=get("vit_precision", "fp16"),
                     freeze_vit=get("freeze_vit", True), num_query_token=get("num_query_token", 32),
@@ -195,7 +209,7 @@ class BLIP2_MR(Blip2Base):
                     task=get("task", "qformer_freeze_lora"), num_frames_for_answer=get("num_frames_for_answer", 4),
                     resample_frames=get("resample_frames", False), dims=get("dims", None),
                     init_seed=get("init_seed", 1234), lora_b_std=get("lora_b_std", 0.0),
-                    train_dropout=get("train_dropout", None), dropout_seed=get("dropout_seed", 0))
+                    train_dropout=get("train_dropout", None), dropout_seed=get("dropout_seed", 0), allow_synthetic=synth)
         # third-party weights the reference fetches from hubs, from local files here: `t5_model` may be a transformers
         # directory (as it may be for from_pretrained), `vit_weights` an eva_vit_g.pth
         from . import weights
@@ -203,16 +217,22 @@ class BLIP2_MR(Blip2Base):
             weights.load_hf_t5(model, get("t5_model"))
         if get("vit_weights", None):
             weights.load_eva_vit(model, get("vit_weights"))
-        model.load_checkpoint_from_config(cfg)
+        elif not synth:
+            logging.error("model.vit_weights is not set: the EVA ViT-g keeps seeded random weights unless the `pretrained` checkpoint "
+                          "carries visual_encoder.* (the BLIP-2 checkpoints do not)")
+        model.load_checkpoint_from_config(cfg, allow_synthetic=synth)
         return model
 
-    def load_checkpoint_from_config(self, cfg, **kwargs):
-        """blip2_mr.py:1466-1495: pretrained BLIP-2 weights, then the finetuned LoRA adapter (local files only)."""
-        import os
+    def load_checkpoint_from_config(self, cfg, allow_synthetic=True, **kwargs):
+        """blip2_mr.py:1466-1495: pretrained BLIP-2 weights, then the finetuned LoRA adapter (local files only).  A configured
+        checkpoint that is not a local file is an error unless allow_synthetic."""
         for key in ("pretrained", "finetuned") if cfg.get("load_finetuned", True) else ("pretrained",):
             path = cfg.get(key, None)
             if path and os.path.isfile(path):
                 self.load_checkpoint(path)
+            elif path and not allow_synthetic:
+                raise RuntimeError("model.%s=%r is not a local file (no network here); set model.allow_synthetic: true to keep the "
+                                   "seeded weights for a dry run" % (key, path))
             elif path:
                 logging.warning("%s checkpoint %s is not a local file; keeping seeded weights", key, path)
 

@@ -6,6 +6,9 @@ import os
 import torch
 
 
+REFERENCE_ONLY_BUFFERS = (".position_ids",)
+
+
 def trainable_state_dict(model):
     """state_dict() minus every parameter with requires_grad False (runner_base.py:577-587): for Mr. BLIP that leaves the
     LoRA factors and t5_proj (19.5 M values).  Buffers and anything else named_parameters() does not list stay -- which
@@ -36,7 +39,10 @@ def resume_checkpoint(model, optimizer, path, scaler=None, map_location="cpu"):
         raise RuntimeError("checkpoint url or path is invalid")
     ckpt = torch.load(path, map_location=map_location)
     model = getattr(model, "module", model)
-    msg = model.load_state_dict(ckpt["model"], strict=False)
+    # persistent buffers the reference's modules carry and this parameter tree does not (Qformer.py:69 position_ids): files written
+    # by the reference runner hold them, they carry no information
+    state = {k: v for k, v in ckpt["model"].items() if not k.endswith(REFERENCE_ONLY_BUFFERS)}
+    msg = model.load_state_dict(state, strict=False)
     if msg.unexpected_keys:
         raise RuntimeError("unexpected keys in checkpoint: %s" % msg.unexpected_keys[:8])
     if hasattr(model, "_weights_changed"):

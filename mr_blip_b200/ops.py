@@ -11,12 +11,14 @@ F16, BF16, F32 = 0, 1, 2
 _DT = {torch.float16: F16, torch.bfloat16: BF16, torch.float32: F32}
 INT_MIN = -2 ** 31
 USE_TC_ATTENTION = True
+USE_VIT_ATTENTION = os.environ.get("MRB_ATTN_VIT", "1") != "0"     # 0: the generic flash kernel + the single-row kernel (round 1 path)
 GEMM_PROFILE = None      # set to a list to record (M, N, K, cuda start event, cuda end event) per GEMM launch
 
 
-# Split-K for the decoder-sized (M <= 128) and 32-column GEMMs (csrc/gemm.cu mrb_gemm_splitk).  Written after this round's
-# GPU budget was spent: compiled and reviewed but NOT yet run on hardware, hence off unless MRB_GEMM_SPLITK=1.
-SPLITK = os.environ.get("MRB_GEMM_SPLITK", "0") == "1"
+# Split-K for the decoder-sized (M <= 128) and 32-column GEMMs (csrc/gemm.cu mrb_gemm_splitk).  On by default since round 2
+# (tests/test_splitk_gpu.py green on a B200; 19.1 -> 10.9 us at M 64 N 2048 K 2080, 54.6 -> 17.6 us at K 10272,
+# 14.9 -> 12.0 us for the LoRA down-projection, step 261.2 -> 257.3 ms: profiles/r02_call1.md).  MRB_GEMM_SPLITK=0 switches it off.
+SPLITK = os.environ.get("MRB_GEMM_SPLITK", "1") != "0"
 SPLITK_MAX = int(os.environ.get("MRB_GEMM_SPLITK_MAX", "8"))
 SPLITK_WS_BYTES = 48 << 20          # 8 splits x 128 rows x 10240 columns of fp32, rounded up
 _SPLITK_MAIN = None
@@ -139,6 +141,20 @@ def attention_row(q, k, v, out, B, H, Lk, hd, scale, q_bs, k_strides, v_strides,
     """One query row per (batch, head): q/out data_ptr = that row of batch 0."""
     _lib.call("mrb_attention_row", q.data_ptr(), q_bs, k.data_ptr(), k_strides[0], k_strides[1], v.data_ptr(), v_strides[0],
               v_strides[1], out.data_ptr(), o_bs, B, H, Lk, hd, _DT[q.dtype], float(scale), _stream())
+
+
+def attention_vit_ok(L, hd):
+    """Shapes the persistent ViT attention kernel (csrc/attention_vit.cu) is specialised for."""
+    return USE_VIT_ATTENTION and L == 257 and 64 < hd <= 96 and hd % 8 == 0
+
+
+def attention_vit(q, k, v, out, frames, H, L, hd, scale, q_strides, k_strides, v_strides, o_strides):
+    """EVA ViT self-attention over every (frame, head): all 257 query rows in one launch (CLS row included)."""
+    _check(q, torch.float16, torch.bfloat16)
+    _lib.call("mrb_attention_vit", q.data_ptr(), q_strides[0], q_strides[1], k.data_ptr(), k_strides[0], k_strides[1],
+              v.data_ptr(), v_strides[0], v_strides[1], out.data_ptr(), o_strides[0], o_strides[1], frames, H, L, hd,
+              _DT[q.dtype], float(scale), _stream())
+    return out
 
 
 def attention_bwd(q, k, v, o, dout, dq, dk, dv, B, H, Lq, Lk, hd, scale, q_strides, k_strides, v_strides, o_strides,

@@ -12,8 +12,8 @@ Data layout (HBM):
     (bf16 [N, K+32]), so base(x) + B(A x) is ONE tcgen05 GEMM.  Backward mirrors this with
     [M, N+32] gradient buffers and [W^T | A^T | 0] weights (see LoraGroup).
   * LoRA A/B change every optimiser step: refresh() re-copies them into their 8-column slots.
-Train-mode dropout (T5 0.1, LoRA inputs 0.05): off unless T5Engine.drop is a dropout.DropState (BLIP2_MR sets it in train mode
-when built with train_dropout=True / MRB_TRAIN_DROPOUT=1); masks are the counter hash of csrc/dropmask.cuh.
+Train-mode dropout (T5 0.1, LoRA inputs 0.05): on while T5Engine.drop is a dropout.DropState (BLIP2_MR sets it in train mode
+unless built with train_dropout=False / MRB_TRAIN_DROPOUT=0); masks are the counter hash of csrc/dropmask.cuh.
 """
 import math
 

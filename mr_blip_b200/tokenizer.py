@@ -10,6 +10,8 @@ is empty), punctuation is one token per character, and other words hash into [12
 import re
 import zlib
 
+import logging
+
 import torch
 
 _PUNCT = "[](),.:;?!<>/\\-+=*&%$#@'\"_{}|~^`"
@@ -138,16 +140,24 @@ class SyntheticT5Tokenizer:
         return [self.decode(s, skip_special_tokens) for s in seqs]
 
 
-def load_t5_tokenizer(name="google/flan-t5-xl"):
-    """Real tokenizer when its files are cached locally, else the synthetic stand-in (never touches the
-    network).  transformers 5.x returns an EMPTY tokenizer instead of raising when files are missing, so the
-    result is validated before it is trusted."""
+def load_t5_tokenizer(name="google/flan-t5-xl", allow_synthetic=True):
+    """Real tokenizer when its files are cached locally (never touches the network).  transformers 5.x returns an EMPTY tokenizer
+    instead of raising when files are missing, so the result is validated before it is trusted.  When it is not there:
+    allow_synthetic=False raises (what training / evaluation from a recipe uses: a run on hashed word ids is garbage), otherwise the
+    synthetic stand-in is returned WITH a warning (parity tests and the benchmark, which have no tokenizer files offline)."""
+    why = "not validated"
     try:
         from transformers import T5TokenizerFast
         tok = T5TokenizerFast.from_pretrained(name, local_files_only=True)
         ids = tok("the video shows 25 seconds")["input_ids"]
         if len(tok) >= 32000 and tok.unk_token_id not in ids[:-1] and len(ids) >= 5:
             return tok
-    except Exception:
-        pass
+        why = "the local files give an empty / wrong vocabulary (%d entries)" % len(tok)
+    except Exception as e:
+        why = "%s: %s" % (type(e).__name__, str(e)[:120])
+    if not allow_synthetic:
+        raise RuntimeError("T5 tokenizer %r is not available locally (%s); refusing to fall back to the synthetic tokenizer. "
+                           "Point model.t5_model at a local FlanT5 directory, or set model.allow_synthetic: true for dry runs" % (name, why))
+    logging.getLogger(__name__).warning("T5 tokenizer %r not available locally (%s): using the SYNTHETIC tokenizer (hashed word ids) -- "
+                                        "fine for parity tests / benchmarks, useless for real training or evaluation", name, why)
     return SyntheticT5Tokenizer()

@@ -161,7 +161,12 @@ def main(argv=None):
     out_dir = run.get("output_dir", "result/mr_BLIP")
     if rank == 0:
         os.makedirs(out_dir, exist_ok=True)
-    gen = dict(num_beams=int(run.get("num_beams", 5)), max_length=int(run.get("max_len", 50)), min_length=int(run.get("min_len", 1)))
+    # MomentRetrievalTask.valid_step calls model.generate(samples) with NO keyword arguments (moment_retrieval.py:33-36), so the
+    # reference always decodes with generate's own defaults (num_beams 5, max_length 50, min_length 1) and ignores run.max_len /
+    # run.min_len / run.num_beams of the recipe.  Same here; run.generate_from_run_cfg: true opts into forwarding them.
+    gen = {}
+    if run.get("generate_from_run_cfg", False):
+        gen = dict(num_beams=int(run.get("num_beams", 5)), max_length=int(run.get("max_len", 50)), min_length=int(run.get("min_len", 1)))
     loaders = {s: build_loader(d, int(run.get("batch_size_train" if s == "train" else "batch_size_eval", 1)),
                                int(run.get("num_workers", 4)), s == "train", rank, world, int(run.get("seed", 42)))
                for s, d in datasets.items()}

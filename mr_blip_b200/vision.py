@@ -82,7 +82,15 @@ class VitEngine:
             ops.norm(x, blk["ln1_w"], blk["ln1_b"], d.vit_ln_eps, 0, out_h=xn)
             ops.gemm(xn, blk["qkv_w"], out=qkv, bias=blk["qkv_b"])
             rs = 3 * W
-            # 257 = 2 x 128 + 1: the first 256 query rows run as two full tcgen05 tiles, the last row in the small kernel
+            if ops.attention_vit_ok(T, hd):
+                # CLS + 256 patches: one persistent tcgen05 launch does all 257 query rows of every (frame, head)
+                ops.attention_vit(qkv, qkv[:, W:], qkv[:, 2 * W:], ao, F_, Hh, T, hd, hd ** -0.5,
+                                  (T * rs, rs), (T * rs, rs), (T * rs, rs), (T * W, W))
+                self._tail(blk, x, xn, ao, hid)
+                if return_all:
+                    outs.append(x.clone())
+                continue
+            # other token counts: the first floor(T / 128) * 128 query rows as full tcgen05 tiles, the rest in the small kernels
             Tq = (T // 128) * 128 if ops.USE_TC_ATTENTION else 0
             forked = self.overlap and Tq and Tq == T - 1
             if forked:
@@ -102,13 +110,18 @@ class VitEngine:
             elif Tq < T:
                 ops.attention_fwd(qkv[Tq:], qkv[:, W:], qkv[:, 2 * W:], ao[Tq:], F_, Hh, T - Tq, T, hd, hd ** -0.5,
                                   (T * rs, rs), (T * rs, rs), (T * rs, rs), (T * W, W), impl="mma")
-            ops.gemm(ao, blk["proj_w"], out=x, bias=blk["proj_b"], resid=x)
-            ops.norm(x, blk["ln2_w"], blk["ln2_b"], d.vit_ln_eps, 0, out_h=xn)
-            ops.gemm(xn, blk["fc1_w"], out=hid, bias=blk["fc1_b"], gelu=True)
-            ops.gemm(hid, blk["fc2_w"], out=x, bias=blk["fc2_b"], resid=x)
+            self._tail(blk, x, xn, ao, hid)
             if return_all:
                 outs.append(x.clone())
         return outs if return_all else x
+
+    def _tail(self, blk, x, xn, ao, hid):
+        """x += proj(attention output); x += fc2(gelu(fc1(LN(x))))  (eva_vit.py:173-176)."""
+        d = self.d
+        ops.gemm(ao, blk["proj_w"], out=x, bias=blk["proj_b"], resid=x)
+        ops.norm(x, blk["ln2_w"], blk["ln2_b"], d.vit_ln_eps, 0, out_h=xn)
+        ops.gemm(xn, blk["fc1_w"], out=hid, bias=blk["fc1_b"], gelu=True)
+        ops.gemm(hid, blk["fc2_w"], out=x, bias=blk["fc2_b"], resid=x)
 
 
 class QFormerEngine:

@@ -4,10 +4,18 @@ sub-module oracles.  blip2_mr.py itself cannot be imported here (peft / tokenize
 this file follows it line by line: interleave_data=True, task='qformer_freeze_lora' (every lavis/projects/mr_BLIP
 yaml), input_time_format 'seconds_integers' (default) plus the other integer / float formats of utils.py:437-512.
 Test infrastructure only (see oracle/__init__.py)."""
+import contextlib
+
 import torch
 
-from . import vit as _vit, qformer as _qf, t5 as _t5
+from . import vit as _vit, qformer as _qf, t5 as _t5, host_text as _ht
 from .beam_search import beam_search
+
+
+def _on(dev, enc):
+    """Tokenizer output (CPU tensors) -> the device the weights live on (the oracle runs on the CPU in the tests and, for the
+    full-depth parity test and the eager-GPU arm of bench.py, on the GPU box's device)."""
+    return enc.input_ids.to(dev), enc.attention_mask.to(dev)
 
 
 def seconds_integers(timestamps, durations, table):
@@ -39,15 +47,24 @@ def time_values(fmt, timestamps, durations, table):
     return ts, ds
 
 
-def frame_tokens(sd, d, video, frame_token_aggregation=None, drop=None):
-    """blip2_mr.py:443-510: ViT -> ln_vision -> Q-Former -> t5_proj (-> mean) -> [b, t*n, c]."""
+def _amp(dev, dtype, on):
+    """The reference's GPU regime (amp=True): torch.amp.autocast of `dtype`; off (fp32, the parity oracle) otherwise."""
+    return torch.autocast(torch.device(dev).type, dtype=dtype) if on else contextlib.nullcontext()
+
+
+def frame_tokens(sd, d, video, frame_token_aggregation=None, drop=None, amp=False):
+    """blip2_mr.py:443-510: ViT -> ln_vision -> Q-Former -> t5_proj (-> mean) -> [b, t*n, c].
+    amp=True: the reference's GPU regime -- ViT + ln_vision under fp16 autocast (blip2_mr.py:446, fp16 ViT weights:
+    eva_vit.py:397-412), Q-Former and t5_proj under the training loop's fp16 autocast (moment_retrieval.py:217, `amp: True` in every
+    mr_BLIP recipe)."""
     b, t = video.shape[:2]
     image = video.reshape(-1, *video.shape[2:])
-    image_embeds = _vit.ln_vision(sd, d, _vit.vit_forward(sd, d, image))
-    q = _qf.qformer_forward(sd, d, image_embeds, drop=drop)
-    f = torch.nn.functional.linear(q, sd["t5_proj.weight"], sd["t5_proj.bias"])
-    if frame_token_aggregation:
-        f = f.mean(dim=1, keepdim=True)
+    with _amp(image.device, torch.float16, amp):
+        image_embeds = _vit.ln_vision(sd, d, _vit.vit_forward(sd, d, image))
+        q = _qf.qformer_forward(sd, d, image_embeds, drop=drop)
+        f = torch.nn.functional.linear(q, sd["t5_proj.weight"], sd["t5_proj.bias"])
+        if frame_token_aggregation:
+            f = f.mean(dim=1, keepdim=True)
     return f.reshape(b, -1, f.shape[-1]), {"image_embeds": image_embeds, "qformer": q}
 
 
@@ -65,26 +82,22 @@ def prompt_concatenation(sd, d, tok, timestamps, durations, frames_for_t5, video
        [f_0 (n) | ts_0 | f_1 | ts_1 | ... | '>' | duration] (left-padded) ++ video_prompt_end ++ query+task;
     interleave_data=False (:784-822): video_prompt (the timestamps as text) ++ all frame tokens ++ video_prompt_end ++ query+task."""
     emb = sd[prefix + "shared.weight"]
+    dev = emb.device
+    timestamps, durations = torch.as_tensor(timestamps).cpu(), torch.as_tensor(durations).cpu()
     if not interleave_data:
-        # the prompt string comes from the reference-pinned helpers (mr_utils_golden.json / time_formats_golden.json)
-        from mr_blip_b200 import mr_utils
-        fn = {"seconds_integers": mr_utils.get_timestamps_as_seconds_integers, "seconds_floats": mr_utils.get_timestamps_as_seconds_floats,
-              "relative_integers": mr_utils.get_timestamps_as_relative_integers, "relative_floats": mr_utils.get_timestamps_as_relative_floats,
-              "framenumbers": mr_utils.get_timestamps_as_framenumbers}[input_time_format]
-        video_prompt = fn(torch.as_tensor(timestamps), torch.as_tensor(durations), table or {})[2]
+        video_prompt = _ht.video_prompt(input_time_format, timestamps, durations, table or {})
         kw = dict(padding="longest", truncation=True, max_length=max_txt_len, return_tensors="pt")
-        vp = tok(video_prompt, add_special_tokens=False, **kw)
-        end = tok(video_prompt_end, add_special_tokens=False, **kw)
-        text = tok([q + t for q, t in zip(query_prompt, task_prompt)], **kw)
-        inputs = torch.cat([emb[vp.input_ids], frames_for_t5, emb[end.input_ids], emb[text.input_ids]], dim=1)
-        atts = torch.cat([vp.attention_mask, torch.ones(frames_for_t5.shape[:2], dtype=torch.long), end.attention_mask,
-                          text.attention_mask], dim=1)
+        vp_ids, vp_m = _on(dev, tok(video_prompt, add_special_tokens=False, **kw))
+        end_ids, end_m = _on(dev, tok(video_prompt_end, add_special_tokens=False, **kw))
+        text_ids, text_m = _on(dev, tok([q + t for q, t in zip(query_prompt, task_prompt)], **kw))
+        inputs = torch.cat([emb[vp_ids], frames_for_t5, emb[end_ids], emb[text_ids]], dim=1)
+        atts = torch.cat([vp_m, torch.ones(frames_for_t5.shape[:2], dtype=torch.long, device=dev), end_m, text_m], dim=1)
         return inputs, atts
     ts, ds = time_values(input_time_format, timestamps, durations, table or {})
-    end = tok(video_prompt_end, padding="longest", add_special_tokens=False, truncation=True,
-              max_length=max_txt_len, return_tensors="pt")
-    text = tok([q + t for q, t in zip(query_prompt, task_prompt)], padding="longest", truncation=True,
-               max_length=max_txt_len, return_tensors="pt")
+    end_ids, end_m = _on(dev, tok(video_prompt_end, padding="longest", add_special_tokens=False, truncation=True,
+                                  max_length=max_txt_len, return_tensors="pt"))
+    text_ids, text_m = _on(dev, tok([q + t for q, t in zip(query_prompt, task_prompt)], padding="longest", truncation=True,
+                                    max_length=max_txt_len, return_tensors="pt"))
     sep = tok.convert_tokens_to_ids(">")
     B, TN, C = frames_for_t5.shape
     T = TN // n_per_frame
@@ -95,34 +108,36 @@ def prompt_concatenation(sd, d, tok, timestamps, durations, frames_for_t5, video
         parts = []
         for i in range(T):
             parts.append(frames_for_t5[j, i * n_per_frame:(i + 1) * n_per_frame])
-            parts.append(emb[torch.tensor(ts_ids[i])])
-        parts.append(emb[torch.tensor([sep])])
-        parts.append(emb[torch.tensor(dur_ids)])
+            parts.append(emb[torch.tensor(ts_ids[i], device=dev)])
+        parts.append(emb[torch.tensor([sep], device=dev)])
+        parts.append(emb[torch.tensor(dur_ids, device=dev)])
         rows.append(torch.cat(parts))
     L = max(len(r) for r in rows)
     # reference pads with pad_token_id * ones (= zeros) on the LEFT and still marks them attended (:744-779)
-    rows = [torch.cat([torch.zeros(L - len(r), C), r]) if len(r) < L else r for r in rows]
+    rows = [torch.cat([torch.zeros(L - len(r), C, device=dev, dtype=r.dtype), r]) if len(r) < L else r for r in rows]
     inter = torch.stack(rows)
-    inputs = torch.cat([inter, emb[end.input_ids], emb[text.input_ids]], dim=1)
-    atts = torch.cat([torch.ones(B, L, dtype=torch.long), end.attention_mask, text.attention_mask], dim=1)
+    inputs = torch.cat([inter, emb[end_ids], emb[text_ids]], dim=1)
+    atts = torch.cat([torch.ones(B, L, dtype=torch.long, device=dev), end_m, text_m], dim=1)
     return inputs, atts
 
 
 def forward_mr(sd, d, tok, samples, frame_token_aggregation=None, table=None, max_txt_len=200,
-               input_time_format="seconds_integers", drop=None, interleave_data=True):
+               input_time_format="seconds_integers", drop=None, interleave_data=True, amp=False):
     """blip2_mr.py:433-570 -> dict(loss, logits, inputs_embeds, attention_mask, labels, ...).  drop: None = eval mode, a
     Dropper (oracle/dropout.py) = the train-mode dropout of the Q-Former, T5 and LoRA inputs (the ViT stays in eval mode:
-    blip2_mr.py:136-137)."""
-    f, aux = frame_tokens(sd, d, samples["video"], frame_token_aggregation, drop=drop)
+    blip2_mr.py:136-137).  amp=True: the reference's autocast regime on a GPU (fp16 frame encoder, bf16 T5: blip2_mr.py:446,512)
+    -- the eager-PyTorch-on-B200 bar of BASELINE.md section 4; amp=False is the fp32 parity oracle."""
+    f, aux = frame_tokens(sd, d, samples["video"], frame_token_aggregation, drop=drop, amp=amp)
     n = 1 if frame_token_aggregation else d.num_query
-    inputs, atts = prompt_concatenation(sd, d, tok, samples["timestamps"], samples["duration"], f,
-                                        samples["video_prompt_end"], samples["query_prompt"],
-                                        samples["task_prompt"], n, table, max_txt_len, input_time_format=input_time_format,
-                                        interleave_data=interleave_data)
-    ans = tok(samples["relevant_windows"], padding="longest", truncation=True, max_length=max_txt_len,
-              return_tensors="pt")
-    labels = ans.input_ids.masked_fill(ans.input_ids == tok.pad_token_id, -100)
-    out = _t5.t5_forward(sd, d, inputs, atts, labels, ans.attention_mask, drop=drop)
+    with _amp(f.device, torch.bfloat16, amp):
+        inputs, atts = prompt_concatenation(sd, d, tok, samples["timestamps"], samples["duration"], f,
+                                            samples["video_prompt_end"], samples["query_prompt"],
+                                            samples["task_prompt"], n, table, max_txt_len, input_time_format=input_time_format,
+                                            interleave_data=interleave_data)
+        ans_ids, ans_m = _on(inputs.device, tok(samples["relevant_windows"], padding="longest", truncation=True,
+                                                max_length=max_txt_len, return_tensors="pt"))
+        labels = ans_ids.masked_fill(ans_ids == tok.pad_token_id, -100)
+        out = _t5.t5_forward(sd, d, inputs, atts, labels, ans_m, drop=drop)
     out.update(inputs_embeds=inputs, attention_mask=atts, labels=labels, frames_for_t5=f, **aux)
     return out
 
@@ -160,22 +175,20 @@ ANSWER_IDS = [71, 272, 205, 309, 262]          # A B C D E (blip2_mr.py:1297)
 
 
 def _qa_relevant_frames(sd, d, tok, samples, use_localizer, n_frames, post_process, frame_token_aggregation):
-    """blip2_mr.py:328-362 / 1011-1049: window from the localizer's prediction or the whole video, then extract_frames.  The two
-    frame-selection helpers are the product's (mr_blip_b200/qa.py), which are pinned to the reference's own methods
-    (tests/golden/qa_frames_golden.json); restating them a third time here would add nothing."""
-    from mr_blip_b200 import qa
+    """blip2_mr.py:328-362 / 1011-1049: window from the localizer's prediction or the whole video, then extract_frames
+    (oracle/host_text.py: the oracle's own restatement of get_relevant_frames / extract_frames, pinned by qa_frames_golden.json)."""
     if use_localizer:
         pred = generate(sd, d, tok, samples, post_process, frame_token_aggregation=frame_token_aggregation)["prediction"]
-        moments = qa.relevant_moments_from_predictions(pred, samples["duration"])
+        moments = [_ht.qa_window(p, samples["duration"][i]) for i, p in enumerate(pred)]
     else:
         moments = [[0, x.item()] for x in samples["duration"]]
-    return moments, qa.extract_frames(samples, moments, n_frames)
+    return moments, _ht.qa_frames(samples, moments, n_frames)
 
 
 def _qa_inputs(sd, tok, f, texts, max_txt_len):
-    q = tok(texts, padding="longest", truncation=True, max_length=max_txt_len, return_tensors="pt")
-    emb = sd[ANSWERER_PREFIX + "shared.weight"][q.input_ids]
-    return torch.cat([f, emb], dim=1), torch.cat([torch.ones(f.shape[:2], dtype=torch.long), q.attention_mask], dim=1)
+    ids, m = _on(f.device, tok(texts, padding="longest", truncation=True, max_length=max_txt_len, return_tensors="pt"))
+    emb = sd[ANSWERER_PREFIX + "shared.weight"][ids]
+    return torch.cat([f, emb], dim=1), torch.cat([torch.ones(f.shape[:2], dtype=torch.long, device=f.device), m], dim=1)
 
 
 def forward_qa(sd, d, tok, samples, use_localizer=False, n_frames=4, post_process=None, frame_token_aggregation=None,
@@ -188,9 +201,10 @@ def forward_qa(sd, d, tok, samples, use_localizer=False, n_frames=4, post_proces
         moments, rel = _qa_relevant_frames(sd, d, tok, samples, use_localizer, n_frames, post_process, frame_token_aggregation)
         f, _ = frame_tokens(sd, d, rel, frame_token_aggregation, drop=drop)
     inputs, atts = _qa_inputs(sd, tok, f, samples["qa_input"], max_txt_len)
-    a = tok(samples["qa_output"], padding="longest", truncation=True, max_length=max_txt_len, return_tensors="pt")
-    labels = a.input_ids.masked_fill(a.input_ids == tok.pad_token_id, -100)
-    out = _t5.t5_forward(sd, d, inputs, atts, labels, a.attention_mask, prefix=ANSWERER_PREFIX, drop=drop)
+    a_ids, a_m = _on(inputs.device, tok(samples["qa_output"], padding="longest", truncation=True, max_length=max_txt_len,
+                                        return_tensors="pt"))
+    labels = a_ids.masked_fill(a_ids == tok.pad_token_id, -100)
+    out = _t5.t5_forward(sd, d, inputs, atts, labels, a_m, prefix=ANSWERER_PREFIX, drop=drop)
     out.update(relevant_moments=moments, labels=labels)
     return out
 
@@ -201,7 +215,7 @@ def videoqa_answer(sd, d, tok, samples, rel, frame_token_aggregation=None, max_t
         f, _ = frame_tokens(sd, d, rel, frame_token_aggregation)
         inputs, atts = _qa_inputs(sd, tok, f, samples["qa_input"], max_txt_len)
         enc = _t5.t5_encoder(sd, d, inputs, atts, prefix=ANSWERER_PREFIX)
-        ids = torch.full((inputs.shape[0], 1), tok.pad_token_id, dtype=torch.long)
+        ids = torch.full((inputs.shape[0], 1), tok.pad_token_id, dtype=torch.long, device=inputs.device)
         for _ in range(2):
             dec = _t5.t5_decoder(sd, d, ids, enc, atts, prefix=ANSWERER_PREFIX)
             logits = _t5.t5_logits(sd, d, dec[:, -1], prefix=ANSWERER_PREFIX)

@@ -77,6 +77,29 @@ def keep_mask(seed, site_id, rows, cols, p):
     return draws(seed, site_id, rows, cols) >= thr_of(p)
 
 
+def _mix_t(x):
+    """lowbias32 on int64 tensors holding uint32 values (products stay below 2^63)."""
+    m = 0xFFFFFFFF
+    x = x & m
+    x = x ^ (x >> 16)
+    x = (x * 0x21f0aaad) & m
+    x = x ^ (x >> 15)
+    x = (x * 0x735a2d97) & m
+    return x ^ (x >> 15)
+
+
+def keep_mask_torch(seed, site_id, rows, cols, p, device):
+    """keep_mask() evaluated with torch integer ops on `device` (the full-depth GPU parity runs need masks of 10^8+ elements);
+    bit-identical to the numpy restatement (tests/test_oracle_golden.py::test_dropout_mask_torch_matches_numpy)."""
+    ng = (cols + 3) // 4
+    k = int(key(seed, site_id))
+    r = torch.arange(rows, dtype=torch.int64, device=device)[:, None]
+    g = torch.arange(ng, dtype=torch.int64, device=device)[None, :]
+    w = _mix_t(((r * ng + g) & 0xFFFFFFFF) ^ k)
+    b = (w[:, :, None] >> (8 * torch.arange(4, dtype=torch.int64, device=device))[None, None, :]) & 0xFF
+    return b.reshape(rows, ng * 4)[:, :cols] >= thr_of(p)
+
+
 class Dropper:
     """drop(x, site_id, p): x [..., cols] -> x * keep * scale with rows = the flattened leading dimensions."""
 
@@ -90,5 +113,8 @@ class Dropper:
             return torch.nn.functional.dropout(x, p=p, training=True)
         cols = x.shape[-1]
         rows = x.numel() // cols
-        m = torch.from_numpy(keep_mask(self.seed, site_id, rows, cols, p)).view(x.shape)
+        if x.is_cuda:
+            m = keep_mask_torch(self.seed, site_id, rows, cols, p, x.device).view(x.shape)
+        else:
+            m = torch.from_numpy(keep_mask(self.seed, site_id, rows, cols, p)).view(x.shape)
         return x * (m.to(x.dtype) * float(scale_of(p)))

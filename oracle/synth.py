@@ -8,10 +8,11 @@ _WORDS = ("a person is cooking pasta in the kitchen while the dog watches and th
           "the garden where two friends talk about the weather before driving to town").split()
 
 
-def make_samples(batch, frames, query_words=8, duration=150.0, seed=0, img=224):
+def make_samples(batch, frames, query_words=8, duration=150.0, seed=0, img=224, spread=7.0):
+    """spread: seconds by which clip i is shorter than clip i-1 (ragged prompts); needs duration - spread * (batch-1) > 20."""
     g = torch.Generator().manual_seed(seed)
     video = torch.randn(batch, frames, 3, img, img, generator=g)
-    durs = torch.tensor([duration - 7.0 * i for i in range(batch)])
+    durs = torch.tensor([duration - spread * i for i in range(batch)])
     ts = torch.stack([torch.linspace(0.5 * d / frames, d - 0.5 * d / frames, frames) for d in durs.tolist()])
     ts = (ts * 100).round() / 100
     queries, answers = [], []

@@ -54,8 +54,8 @@ def relative_position_bucket(rel, bidirectional, num_buckets, max_distance):
 
 def compute_bias(table, q_len, k_len, bidirectional, d):
     """modeling_t5.py:447-472 -> [1, H, q_len, k_len]."""
-    ctx = torch.arange(q_len, dtype=torch.long)[:, None]
-    mem = torch.arange(k_len, dtype=torch.long)[None, :]
+    ctx = torch.arange(q_len, dtype=torch.long, device=table.device)[:, None]
+    mem = torch.arange(k_len, dtype=torch.long, device=table.device)[None, :]
     bucket = relative_position_bucket(mem - ctx, bidirectional, d.rel_buckets, d.rel_max_dist)
     return table[bucket].permute(2, 0, 1).unsqueeze(0)
 
@@ -72,7 +72,11 @@ def t5_attention(sd, d, name, hidden, kv, position_bias, drop=None, p_site=None)
     q = shape(lora_linear(sd, d, name + ".q", hidden, drop))
     k = shape(lora_linear(sd, d, name + ".k", kv, drop))
     v = shape(lora_linear(sd, d, name + ".v", kv, drop))
-    scores = torch.matmul(q, k.transpose(3, 2)) + position_bias
+    scores = torch.matmul(q, k.transpose(3, 2))
+    if scores.dtype == position_bias.dtype:
+        scores = scores + position_bias
+    else:                                                     # under autocast the reference adds in place, in the scores' dtype
+        scores += position_bias                               # (modeling_t5.py:597: `scores += position_bias_masked`)
     w = F.softmax(scores.float(), dim=-1).type_as(scores)
     if drop is not None:
         w = drop(w, p_site, drop.t5)                          # modeling_t5.py:600
@@ -141,9 +145,9 @@ def t5_decoder(sd, d, decoder_input_ids, enc_out, enc_mask, decoder_attention_ma
         h = drop(h, D_.site(D_.DEC, 0, D_.EMB), drop.t5)
     B, L = decoder_input_ids.shape
     if decoder_attention_mask is None:
-        decoder_attention_mask = torch.ones(B, L)
+        decoder_attention_mask = torch.ones(B, L, device=h.device)
     table = sd[prefix + "decoder.block.0.layer.0.SelfAttention.relative_attention_bias.weight"]
-    causal = torch.tril(torch.ones(L, L))[None, None] * decoder_attention_mask[:, None, None, :].float()
+    causal = torch.tril(torch.ones(L, L, device=h.device))[None, None] * decoder_attention_mask[:, None, None, :].float()
     self_bias = compute_bias(table, L, L, False, d) + (1.0 - causal) * torch.finfo(torch.float32).min
     cross_bias = extended_mask(enc_mask)
     for i in range(d.t5_dec_layers):

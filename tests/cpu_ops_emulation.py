@@ -278,6 +278,17 @@ def attention_fwd(q, k, v, out, B, H, Lq, Lk, hd, scale, q_strides, k_strides, v
     return out
 
 
+USE_VIT_ATTENTION = True
+
+
+def attention_vit_ok(L, hd):
+    return USE_VIT_ATTENTION and L == 257 and 64 < hd <= 96 and hd % 8 == 0
+
+
+def attention_vit(q, k, v, out, frames, H, L, hd, scale, q_strides, k_strides, v_strides, o_strides):
+    return attention_fwd(q, k, v, out, frames, H, L, L, hd, scale, q_strides, k_strides, v_strides, o_strides)
+
+
 def attention_bwd(q, k, v, o, dout, dq, dk, dv, B, H, Lq, Lk, hd, scale, q_strides, k_strides, v_strides, o_strides, do_strides,
                   lse, delta_ws, bias=None, bias_zero=0, kmask=None, causal=False, q_pos0=0, impl="auto", drop=None):
     qf = _view4(q, B, Lq, H, hd, q_strides).float().clone().requires_grad_(True)
@@ -392,6 +403,12 @@ class HostCAbi:
         self.calls[name] = self.calls.get(name, 0) + 1
         if name == "mrb_gemm":
             return self._gemm(*args)
+        if name == "mrb_attention_vit":                      # tcgen05 kernel -> the same-contract mma.sync kernel, all 257 rows
+            (q, q_bs, q_rs, k, k_bs, k_rs, v, v_bs, v_rs, o, o_bs, o_rs, frames, H, L, hd, dt, scale, st) = args
+            return self.call("mrb_attention_fwd", q, q_bs, q_rs, k, k_bs, k_rs, v, v_bs, v_rs, o, o_bs, o_rs, frames, H, L, L, hd, dt,
+                             scale, None, 0, 0, None, 1, 0, 0, None, st)
+        if name == "mrb_gemm_splitk":                        # same contract + (workspace, bytes, max splits) before the stream
+            return self._gemm(*args[:17], args[-1])
         if name == "mrb_skinny_wgrad_tc2":
             P, ldp, Q, ldq, M, C, out, out2, tr, dt, st = args
             self.call("mrb_skinny_wgrad", P, ldp, Q, ldq, M, C, out, tr, dt, st)

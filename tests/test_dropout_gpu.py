@@ -2,12 +2,7 @@
 kernels, T5Engine / QFormerEngine / BLIP2_MR with train_dropout) against the CPU oracle, which evaluates the SAME counter-hash
 masks (oracle/dropout.py) -- so every comparison is elementwise, not statistical.
 
-The path was written after round 1's GPU budget was spent: compiled, reviewed, the default kernels' SASS checked unchanged, but
-NOT yet run on hardware.  Hence skipped unless MRB_TEST_EXPERIMENTAL=1 (first GPU call of the next round):
-
-    MRB_TEST_EXPERIMENTAL=1 python -m pytest tests/test_dropout_gpu.py -m gpu -q
-
-Once green: drop the skip, make train_dropout the default of BLIP2_MR in train mode and of bench.py's workload.
+First run on a B200 in round 2 (profiles/r02_call1.md: green); train-mode dropout is the default of BLIP2_MR.train() since.
 """
 import math
 import os
@@ -16,8 +11,7 @@ import numpy as np
 import pytest
 import torch
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("MRB_TEST_EXPERIMENTAL", "0") != "1", reason="experimental paths: set MRB_TEST_EXPERIMENTAL=1")]
+pytestmark = [pytest.mark.gpu]
 
 from mr_blip_b200.dims import TINY, T5_PREFIX  # noqa: E402
 
@@ -258,7 +252,8 @@ def test_t5_engine_train_mode_vs_oracle(model, tiny_sd):
     # eval-mode oracle is far away: the comparison above can fail
     with torch.no_grad():
         ev = ot5.t5_forward(dict(tiny_sd), TINY, emb, mask, labels, (labels != -100).long())
-    assert abs(ev["loss"].item() - o["loss"].item()) > 1e-2
+    # (the two losses sit within 1e-2 of each other on these random weights -- both ~ ln(vocab) -- so the distance is taken on the logits)
+    assert _relfro(ev["logits"], o["logits"]) > 0.3
 
 
 @pytest.mark.parametrize("agg", [None, "mean"])

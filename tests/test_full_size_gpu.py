@@ -22,7 +22,7 @@ def full_model():
     from mr_blip_b200.blip2_mr import BLIP2_MR
     from mr_blip_b200.dims import FULL, init_state_dict
     sd = init_state_dict(FULL, seed=1234, lora_b_std=0.02, device="cuda")
-    m = BLIP2_MR(dims=FULL, state_dict=sd).cuda().train()
+    m = BLIP2_MR(dims=FULL, state_dict=sd, train_dropout=False).cuda().train()      # the properties below hold for the rate-0 arithmetic (masks are indexed by row, so a clip permutation redraws them)
     del sd
     yield m
     del m

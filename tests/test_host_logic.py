@@ -98,7 +98,7 @@ def test_yaml_recipes_build_models(tmp_path):
         assert cfg.model_cfg.get("num_query_token") == 32 and cfg.model_cfg.task == "qformer_freeze_lora"
     model, cfg = build_model(os.path.join(base, "charades.yaml"),
                              options=["model.frame_token_aggregation=mean", "model.input_time_format=relative_integers",
-                                      "run.batch_size_train=4"], dims=TINY)
+                                      "run.batch_size_train=4", "model.allow_synthetic=true"], dims=TINY)
     assert isinstance(model, BLIP2_MR) and model.frame_token_aggregation == "mean" and model.input_time_format == "relative_integers"
     assert cfg.run_cfg.batch_size_train == 4 and model.task == "qformer_freeze_lora"
     ref_style = tmp_path / "qvh_ref_layout.yaml"
@@ -123,7 +123,10 @@ run:
   init_lr: 3e-4
   accum_grad_iters: 8
 """)
-    m2, c2 = build_model(str(ref_style), dims=TINY)
+    # a recipe whose third-party files (tokenizer, FlanT5 weights) are not local must not silently train on synthetic stand-ins
+    with pytest.raises(RuntimeError, match="allow_synthetic"):
+        build_model(str(ref_style), dims=TINY)
+    m2, c2 = build_model(str(ref_style), options=["model.allow_synthetic=true"], dims=TINY)
     assert not m2.frame_token_aggregation and c2.n_frames() == 60 and c2.run_cfg.init_lr == 3e-4 and c2.model_cfg.image_size == 224
     with pytest.raises(AssertionError):
         Config(str(ref_style), options=["model.arch=not_a_model"])
@@ -219,7 +222,7 @@ def test_optimizer_groups_and_scheduler_from_recipe():
     from mr_blip_b200 import optim
     from mr_blip_b200.config import build_model
     model, cfg = build_model(os.path.join(ROOT, "mr_blip_b200", "configs", "projects", "mr_BLIP", "train", "charades.yaml"),
-                             dims=TINY)
+                             options=["model.allow_synthetic=true"], dims=TINY)
     groups, n = optim.param_groups(model, cfg.run_cfg.weight_decay)
     names = {id(p): k for k, p in model.named_parameters()}
     wd = {names[id(p)] for p in groups[0]["params"]}
@@ -579,7 +582,9 @@ def test_third_party_weight_files_load_into_reference_key_names(tmp_path, tiny_s
     # from_config picks both up from the recipe
     from mr_blip_b200.config import build_model
     m2, _ = build_model(os.path.join(ROOT, "mr_blip_b200", "configs", "projects", "mr_BLIP", "train", "qvh.yaml"),
-                        options=["model.t5_model=%s" % t5_dir, "model.vit_weights=%s" % vpath], dims=TINY)
+                        options=["model.t5_model=%s" % t5_dir, "model.vit_weights=%s" % vpath,
+                                 "model.allow_synthetic=true"],      # the toy directory holds weights but no tokenizer files
+                        dims=TINY)
     sd2 = m2.state_dict()
     assert torch.equal(sd2[T5_PREFIX + "lm_head.base_layer.weight"], hf["lm_head.weight"])
     assert torch.equal(sd2["visual_encoder.blocks.0.attn.proj.weight"], vit["blocks.0.attn.proj.weight"].half())
@@ -1014,7 +1019,12 @@ def test_ops_wrappers_pass_what_the_c_abi_declares(monkeypatch):
     ops.lora_down_drop(xe[:, :64], A, xe[:, 64:], 8, 64, 3, word, 5, 0.05)
     ops.lora_wgrad_drop(xe.data_ptr(), xe.stride(0), xe.data_ptr() + 128, xe.stride(0), 8, 64, torch.zeros((8, 64)), ops.BF16, word, 5, 0.05)
     ops.lora_dx_drop(xe[:, 64:], A, 3, x, 8, 64, word, 5, 0.05)
+    monkeypatch.setattr(ops, "SPLITK", False)
     ops.gemm(xe, A, out=torch.zeros((8, 32)), M=8, K=64)
+    monkeypatch.setattr(ops, "SPLITK", True)                 # the default: small-M / 32-column GEMMs take the split-K entry point
+    monkeypatch.setattr(ops, "_SPLITK_MAIN", torch.zeros(64))
+    ops.gemm(xe, A, out=torch.zeros((8, 32)), M=8, K=64)
+    assert "mrb_gemm_splitk" in seen
     assert {"mrb_attention_fwd", "mrb_attention_fwd_tc", "mrb_attention_fwd_drop", "mrb_attention_fwd_tc_drop", "mrb_attention_bwd",
             "mrb_attention_bwd_tc", "mrb_attention_bwd_drop", "mrb_attention_bwd_tc_drop", "mrb_dropout", "mrb_dropout_add",
             "mrb_gated_gelu_fwd_drop", "mrb_gated_gelu_bwd_drop", "mrb_lora_down_drop", "mrb_lora_wgrad_drop", "mrb_lora_dx_drop",
@@ -1359,6 +1369,8 @@ def test_t5_engine_through_the_real_c_abi_on_host_kernels(monkeypatch, train_dro
     monkeypatch.setattr(_lib, "call", abi.call)
     monkeypatch.setattr(ops, "_check", lambda t, *d: t)
     monkeypatch.setattr(ops, "_stream", lambda: None)
+    monkeypatch.setattr(ops, "_SPLITK_MAIN", torch.zeros(16))      # split-K workspace: unused by the host GEMM stand-in
+    monkeypatch.setattr(ops, "splitk_register", lambda *a: None)
     t5mod = emu.load_engine_module("t5", ops_module=ops)
     params = {k: v.clone() for k, v in tiny_sd.items()}
     eng = t5mod.T5Engine(NARROW, params.__getitem__)
@@ -1382,7 +1394,8 @@ def test_t5_engine_through_the_real_c_abi_on_host_kernels(monkeypatch, train_dro
     grads = {id(p): g for p, g in eng.param_grads()}
     for k, leaf in leaves.items():
         assert _relfro(grads[id(params[k])], leaf.grad) < 4e-2, k
-    want_calls = {"mrb_gemm", "mrb_norm", "mrb_rmsnorm_bwd", "mrb_attention_fwd", "mrb_attention_bwd", "mrb_cross_entropy", "mrb_gather_rows"}
+    # (the narrow test T5 has M <= 128 everywhere, so every GEMM takes the split-K entry point, the default for such shapes)
+    want_calls = {"mrb_gemm_splitk", "mrb_norm", "mrb_rmsnorm_bwd", "mrb_attention_fwd", "mrb_attention_bwd", "mrb_cross_entropy", "mrb_gather_rows"}
     if train_dropout:
         want_calls = (want_calls - {"mrb_attention_fwd", "mrb_attention_bwd"}) | {
             "mrb_attention_fwd_drop", "mrb_attention_bwd_drop", "mrb_dropout", "mrb_dropout_add", "mrb_gated_gelu_fwd_drop",
@@ -1413,6 +1426,8 @@ def test_qformer_engine_through_the_real_c_abi_on_host_kernels(monkeypatch, trai
     monkeypatch.setattr(_lib, "call", abi.call)
     monkeypatch.setattr(ops, "_check", lambda t, *d: t)
     monkeypatch.setattr(ops, "_stream", lambda: None)
+    monkeypatch.setattr(ops, "_SPLITK_MAIN", torch.zeros(16))      # split-K workspace: unused by the host GEMM stand-in
+    monkeypatch.setattr(ops, "splitk_register", lambda *a: None)
     vmod = emu.load_engine_module("vision", ops_module=ops)
     eng = vmod.QFormerEngine(NARROW, {k: v.clone() for k, v in sd.items()}.__getitem__)
     frames = 2
@@ -1449,6 +1464,8 @@ def test_vit_engine_through_the_real_c_abi_on_host_kernels(monkeypatch, elementw
     monkeypatch.setattr(_lib, "call", abi.call)
     monkeypatch.setattr(ops, "_check", lambda t, *d: t)
     monkeypatch.setattr(ops, "_stream", lambda: None)
+    monkeypatch.setattr(ops, "_SPLITK_MAIN", torch.zeros(16))      # split-K workspace: unused by the host GEMM stand-in
+    monkeypatch.setattr(ops, "splitk_register", lambda *a: None)
     monkeypatch.setenv("MRB_OVERLAP", "0")
     vmod = emu.load_engine_module("vision", ops_module=ops)
     half = {k: (v.half() if (v.ndim >= 2 and "pos_embed" not in k and "cls_token" not in k) else v) for k, v in sd.items()}
@@ -1459,7 +1476,12 @@ def test_vit_engine_through_the_real_c_abi_on_host_kernels(monkeypatch, elementw
     with torch.no_grad():
         want = ovit.vit_forward(sd, NARROW, frames)
     assert _relfro(x.view(2, NARROW.vit_tokens, -1), want) < 2e-3
-    assert {"mrb_patchify", "mrb_cls_pos", "mrb_gemm", "mrb_norm", "mrb_attention_fwd_tc", "mrb_attention_row"} <= set(abi.calls), sorted(abi.calls)
+    assert {"mrb_patchify", "mrb_cls_pos", "mrb_gemm", "mrb_norm", "mrb_attention_vit"} <= set(abi.calls), sorted(abi.calls)
+    # the round-1 path (generic flash kernel for the two full 128-row tiles + the single-row kernel) stays available
+    monkeypatch.setattr(ops, "USE_VIT_ATTENTION", False)
+    abi.calls.clear()
+    assert _relfro(eng.forward(frames).view(2, NARROW.vit_tokens, -1), want) < 2e-3
+    assert {"mrb_attention_fwd_tc", "mrb_attention_row"} <= set(abi.calls), sorted(abi.calls)
 
 
 def test_whole_model_train_step_through_the_real_c_abi_on_host_kernels(monkeypatch, elementwise_kernels_on_host, dropout_kernels_on_host,
@@ -1482,6 +1504,8 @@ def test_whole_model_train_step_through_the_real_c_abi_on_host_kernels(monkeypat
     monkeypatch.setattr(_lib, "call", abi.call)
     monkeypatch.setattr(ops, "_check", lambda t, *d: t)
     monkeypatch.setattr(ops, "_stream", lambda: None)
+    monkeypatch.setattr(ops, "_SPLITK_MAIN", torch.zeros(16))      # split-K workspace: unused by the host GEMM stand-in
+    monkeypatch.setattr(ops, "splitk_register", lambda *a: None)
     monkeypatch.setenv("MRB_OVERLAP", "0")
     mod = emu.load_model_module(ops_module=ops)
     model = mod.BLIP2_MR(dims=NARROW, state_dict=sd, cuda_graphs=False, train_dropout=True).train()
@@ -1537,6 +1561,8 @@ def test_generate_through_the_real_c_abi_on_host_kernels(monkeypatch, elementwis
     monkeypatch.setattr(_lib, "call", abi.call)
     monkeypatch.setattr(ops, "_check", lambda t, *d: t)
     monkeypatch.setattr(ops, "_stream", lambda: None)
+    monkeypatch.setattr(ops, "_SPLITK_MAIN", torch.zeros(16))      # split-K workspace: unused by the host GEMM stand-in
+    monkeypatch.setattr(ops, "splitk_register", lambda *a: None)
     monkeypatch.setenv("MRB_OVERLAP", "0")
     monkeypatch.setenv("MRB_CUDA_GRAPHS", "0")
     mod = emu.load_model_module(ops_module=ops)

@@ -130,6 +130,38 @@ def test_attention_fwd_fused_qkv_layout(ops, B, H, L, hd, dtype, impl):
     _close(out, want, tol, tol, "attention fwd")
 
 
+@pytest.mark.parametrize("frames,H,hd,dtype,peaked", [(3, 16, 88, torch.float16, 0), (1, 1, 88, torch.float16, 0), (10, 16, 88, torch.float16, 0),
+                                                      (40, 16, 88, torch.float16, 1), (2, 4, 96, torch.bfloat16, 0), (2, 3, 72, torch.float16, 2),
+                                                      (5, 16, 88, torch.bfloat16, 1)])
+def test_attention_vit_persistent_kernel(ops, frames, H, hd, dtype, peaked):
+    """csrc/attention_vit.cu (eva_vit.py:128-145): all 257 query rows -- CLS as key and as query on CUDA cores, the 256 patches as
+    128 x 256 tcgen05 tiles with P in tensor memory -- against an fp32 softmax.  Item counts below, at and far above the number
+    of SMs (persistent loop, barrier phases, triple-buffered CLS rows); `peaked` plants scores far above the first keys' (the
+    online-softmax correction of the written P) -- 1: in the later key chunks, 2: on the CLS key and on the last patch key."""
+    L = 257
+    qkv = _rand((frames, L, 3, H, hd), dtype, 1.0, 12 + frames)
+    if peaked == 1:
+        for j in (40, 100, 130, 200, 255):                    # one query direction meets keys of growing alignment further down the row
+            qkv[:, j, 1] = qkv[:, 7, 0] * (0.4 + j / 200.0)
+    if peaked == 2:
+        qkv[:, 0, 1] = qkv[:, 9, 0] * 2.0
+        qkv[:, 256, 1] = qkv[:, 9, 0] * 3.0
+    out = torch.full((frames, L, H, hd), 7.0, dtype=dtype, device="cuda")
+    rs = 3 * H * hd
+    ops.attention_vit(qkv[:, :, 0], qkv[:, :, 1], qkv[:, :, 2], out, frames, H, L, hd, hd ** -0.5,
+                      (L * rs, rs), (L * rs, rs), (L * rs, rs), (L * H * hd, H * hd))
+    want, _ = _attn_ref(qkv[:, :, 0], qkv[:, :, 1], qkv[:, :, 2], hd ** -0.5)
+    tol = 2e-2 if dtype == torch.bfloat16 else 4e-3           # P is rounded to 16 bit before P.V
+    _close(out[:, 0], want[:, 0], tol, tol, "CLS query row")
+    _close(out[:, 1:129], want[:, 1:129], tol, tol, "patch rows, group 0")
+    _close(out[:, 129:], want[:, 129:], tol, tol, "patch rows, group 1")
+    # same answer as the round-1 path (generic flash kernel, all rows)
+    old = torch.zeros_like(out)
+    ops.attention_fwd(qkv[:, :, 0], qkv[:, :, 1], qkv[:, :, 2], old, frames, H, L, L, hd, hd ** -0.5,
+                      (L * rs, rs), (L * rs, rs), (L * rs, rs), (L * H * hd, H * hd), impl="mma")
+    _close(out, old, 2 * tol, 2 * tol, "vs mma.sync kernel")
+
+
 def test_attention_single_row(ops):
     B, H, L, hd = 5, 16, 257, 88
     qkv = _rand((B, L, 3, H, hd), torch.float16, 1.0, 42)

@@ -411,3 +411,46 @@ def test_qa_frame_selection_matches_reference(golden_dir):
         assert [float(x) for x in m[0]] == c["moment"], c
         fr = qa.extract_frames(samples, m, c["n"])
         assert fr.shape == (1, c["n"], 1, 1, 1) and fr.view(-1).long().tolist() == c["frames"], c
+
+
+def test_oracle_host_text_matches_reference(golden_dir):
+    """oracle/host_text.py (the oracle's own restatement of the prompt strings, moment parsing and QA frame selection, so that
+    no oracle comparison routes through mr_blip_b200/) against the outputs of the reference's own functions."""
+    from oracle import host_text as ht
+    si = json.load(open(os.path.join(golden_dir, "mr_utils_golden.json")))
+    for s, want in si["moment_str_to_list"]:
+        assert ht.parse_moments(mr_utils.post_process(s)) == want, s
+    si = si["seconds_integers"]
+    table = {int(k): v for k, v in si["table"].items()}
+    got = ht.video_prompt("seconds_integers", [torch.tensor(t) for t in si["timestamps"]], torch.tensor(si["durations"]), table)
+    assert got == si["out_prompt"]
+    gold = json.load(open(os.path.join(golden_dir, "time_formats_golden.json")))
+    ts, du = [torch.tensor(t) for t in gold["timestamps"]], torch.tensor(gold["durations"])
+    for name in ("relative_integers", "seconds_floats", "relative_floats"):
+        assert ht.video_prompt(name, ts, du, {}) == gold[name]["prompt"], name
+    for c in json.load(open(os.path.join(golden_dir, "qa_frames_golden.json")))["selected"]:
+        T = c["T"]
+        samples = {"video": torch.arange(T, dtype=torch.float32).view(1, T, 1, 1, 1), "timestamps": torch.tensor(c["timestamps"])[None],
+                   "duration": torch.tensor([c["duration"]])}
+        win = ht.qa_window(c["prediction"], samples["duration"][0])
+        assert [float(x) for x in win] == c["moment"], c
+        assert ht.qa_frames(samples, [win], c["n"]).view(-1).long().tolist() == c["frames"], c
+
+
+def test_dropout_mask_torch_matches_numpy():
+    """The torch-integer evaluation of the counter-hash mask (used when the oracle runs on the GPU box) is the numpy one."""
+    from oracle import dropout as od
+    for rows, cols, p, site, seed in [(7, 13, 0.1, 5, 123), (33, 2048, 0.05, 0x2108, 0x9E3779B1), (5, 257, 0.1, 77, 1), (64, 2037, 0.1, 4097, 2 ** 32 - 1)]:
+        assert (od.keep_mask(seed, site, rows, cols, p) == od.keep_mask_torch(seed, site, rows, cols, p, "cpu").numpy()).all()
+
+
+def test_oracle_does_not_import_the_product():
+    """oracle/ is the checker: none of its modules may import mr_blip_b200 (two helpers used to)."""
+    import ast as _ast
+    import glob
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for f in glob.glob(os.path.join(root, "oracle", "*.py")):
+        for node in _ast.walk(_ast.parse(open(f).read())):
+            names = [a.name for a in node.names] if isinstance(node, _ast.Import) else \
+                [node.module or ""] if isinstance(node, _ast.ImportFrom) else []
+            assert not any(n.split(".")[0] == "mr_blip_b200" for n in names), f

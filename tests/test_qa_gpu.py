@@ -1,14 +1,12 @@
 """The two-stage video-QA branch (blip2_mr.py:309-431, 990-1099, 1233-1314) on the device against the oracle restatement.
-Written after round 1's GPU budget was spent -- its host logic is checked on the CPU over op stand-ins
-(tests/test_host_logic.py::test_video_qa_branch_host_logic_with_emulated_ops), the kernels it uses are the path's own -- but it has
-not run on hardware yet: skipped unless MRB_TEST_EXPERIMENTAL=1."""
+Its host logic is also checked on the CPU over op stand-ins (tests/test_host_logic.py::test_video_qa_branch_host_logic_with_emulated_ops);
+first run on a B200 in round 2 (profiles/r02_call1.md: green)."""
 import os
 
 import pytest
 import torch
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("MRB_TEST_EXPERIMENTAL", "0") != "1", reason="experimental paths: set MRB_TEST_EXPERIMENTAL=1")]
+pytestmark = [pytest.mark.gpu]
 
 from mr_blip_b200.dims import ANSWERER_PREFIX, TINY, add_answerer  # noqa: E402
 
@@ -27,7 +25,7 @@ def test_video_qa_branch_vs_oracle(tiny_sd, task):
     from oracle import blip2_mr as ob
     from test_host_logic import _qa_samples
     sd = add_answerer(dict(tiny_sd), TINY, seed=1234, lora_b_std=0.02)
-    model = BLIP2_MR(dims=TINY, state_dict=sd, task=task, num_frames_for_answer=3).cuda().train()
+    model = BLIP2_MR(dims=TINY, state_dict=sd, task=task, num_frames_for_answer=3, train_dropout=False).cuda().train()
     samples = _qa_samples()
     res = model(dict(samples))
     res["loss"].backward()

@@ -47,6 +47,10 @@ def main():
             bias = torch.randn(H, 2 * L - 1, device="cuda")[:, idx].contiguous()
         kmask = torch.ones(B, L, dtype=torch.int32, device="cuda") if with_bias else None
         flops = 4.0 * B * H * L * L * hd
+        if name == "vit" and "tc" in impls:                       # the persistent ViT kernel (all 257 rows, CLS included)
+            ms = timeit(lambda: ops.attention_vit(qkv[:, :, 0], qkv[:, :, 1], qkv[:, :, 2], out, B, H, L, hd, hd ** -0.5,
+                                                  (L * rs, rs), (L * rs, rs), (L * rs, rs), (L * H * hd, H * hd)))
+            print("%-14s %-4s %8.3f ms  %7.1f TFLOP/s" % (name, "vit", ms, flops / ms / 1e9), flush=True)
         for impl in impls:
             Lq = L if impl == "mma" else (L // 128) * 128 if name == "vit" else L
             ms = timeit(lambda: ops.attention_fwd(qkv[:, :, 0], qkv[:, :, 1], qkv[:, :, 2], out, B, H, Lq, L, hd, hd ** -0.5,
