@@ -4,8 +4,10 @@
 // bucketed relative bias, padding / causal mask), plus the T5 backward (dQ and dK/dV kernels).
 // Scores never touch HBM.  This first version drives the tensor cores through mma.sync m16n8k16
 // (HMMA); the tcgen05 port of the long-sequence T5 case is tracked in DESIGN.md.
+#include <type_traits>
 #include "common.cuh"
 #include "dropmask.cuh"
+#include "attn_delta.cuh"
 
 namespace mrb {
 
@@ -891,7 +893,18 @@ static int launch_xq(const typename AttnParamsOf<DROP>::type& p, cudaStream_t s)
 
 template <typename T, int HD, bool DROP = false>
 static int launch_bwd(const typename AttnParamsOf<DROP>::type& p, cudaStream_t s) {
-  {
+  if (HD == 64 && p.Lq <= DELTA_EXACT_MAX_LQ) {
+    // few query rows (T5 decoder): delta = sum_j P_ij dP_ij recomputed exactly, see attn_delta.cuh
+    DeltaExactParams d{};
+    d.q = static_cast<const uint16_t*>(p.q); d.k = static_cast<const uint16_t*>(p.k); d.v = static_cast<const uint16_t*>(p.v);
+    d.dout = static_cast<const uint16_t*>(p.dout);
+    d.q_bs = p.q_bs; d.q_rs = p.q_rs; d.k_bs = p.k_bs; d.k_rs = p.k_rs; d.v_bs = p.v_bs; d.v_rs = p.v_rs; d.do_bs = p.do_bs; d.do_rs = p.do_rs;
+    d.B = p.B; d.H = p.H; d.Lq = p.Lq; d.Lk = p.Lk; d.dtype = sizeof(T) == 2 && std::is_same<T, __half>::value ? MRB_DT_F16 : MRB_DT_BF16;
+    d.scale = p.scale; d.bias = p.bias; d.bias_len = p.bias_len; d.bias_zero = p.bias_zero; d.kmask = p.kmask; d.causal = p.causal;
+    d.q_pos0 = p.q_pos0; d.lse = p.lse; d.delta = const_cast<float*>(p.delta);
+    if constexpr (DROP) { d.drop_seed = p.drop_seed; d.drop_site = p.drop_site; d.drop_thr = p.drop_thr; d.drop_scale = p.drop_scale; }
+    if (int rc = launch_delta_exact(d, s)) return rc;
+  } else {
     const int rows = p.B * p.H * p.Lq;
     MRB_LAUNCH((attn_delta_kernel<T>), (rows + 7) / 8, 256, 0, s, static_cast<const AttnParams&>(p));
     MRB_CHECK_LAUNCH();

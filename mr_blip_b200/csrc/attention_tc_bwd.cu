@@ -11,6 +11,7 @@
 // their [row][d] tiles, so nothing is transposed in memory.
 #include "common.cuh"
 #include "dropmask.cuh"
+#include "attn_delta.cuh"
 
 namespace mrb {
 
@@ -572,7 +573,20 @@ static int attention_bwd_tc_impl(const void* q, long long q_bs, long long q_rs, 
   if (dtype != MRB_DT_F16 && dtype != MRB_DT_BF16) return MRB_ERR_ARG;
   if ((q_rs | k_rs | v_rs | o_rs | do_rs | q_bs | k_bs | v_bs | o_bs | do_bs) & 7) return MRB_ERR_ARG;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  {
+  if (Lq <= DELTA_EXACT_MAX_LQ) {
+    // few query rows (the decoder's cross-attention): delta = sum_j P_ij dP_ij recomputed exactly, see attn_delta.cuh
+    DeltaExactParams d{};
+    d.q = static_cast<const uint16_t*>(q); d.k = static_cast<const uint16_t*>(k); d.v = static_cast<const uint16_t*>(v);
+    d.dout = static_cast<const uint16_t*>(dout);
+    d.q_bs = q_bs; d.q_rs = q_rs; d.k_bs = k_bs; d.k_rs = k_rs; d.v_bs = v_bs; d.v_rs = v_rs; d.do_bs = do_bs; d.do_rs = do_rs;
+    d.B = B; d.H = H; d.Lq = Lq; d.Lk = Lk; d.dtype = dtype; d.scale = scale; d.bias = bias; d.bias_len = bias_len; d.bias_zero = bias_zero;
+    d.kmask = kmask; d.causal = causal; d.q_pos0 = q_pos0; d.lse = lse; d.delta = delta_ws;
+    if (drop_seed && drop_p > 0.f) {
+      const DropSpec ds = make_drop(drop_seed, drop_site, drop_p);
+      d.drop_seed = ds.seed; d.drop_site = ds.site; d.drop_thr = ds.thr; d.drop_scale = ds.scale;
+    }
+    if (int rc = launch_delta_exact(d, s)) return rc;
+  } else {
     const int rows = B * H * Lq;
     MRB_LAUNCH((attn_delta64_kernel), (rows + 7) / 8, 256, 0, s, static_cast<const uint16_t*>(o), o_bs, o_rs,
                                                          static_cast<const uint16_t*>(dout), do_bs, do_rs, delta_ws, B, H, Lq, dtype);

@@ -13,8 +13,9 @@
 //     and O += P V takes its A operand from TMEM (tcgen05.mma, A in tensor memory), V read MN-major from its [key][d] tile;
 //     O then reuses the dead upper half of the S columns;
 //   * the CLS token is rank-1 work on CUDA cores: as a KEY its score q_i . k_0 is one 88-long dot product per row thread and
-//     its PV term p_i0 * v_0 is added in the epilogue; as a QUERY (one row against 257 keys) two spare warps compute it from
-//     the K / V tiles already in shared memory.  No padding to 384 rows, no second kernel.
+//     its PV term p_i0 * v_0 is added in the epilogue; as a QUERY (one row against 257 keys) every row thread also forms the
+//     score of ITS OWN key, q_0 . k_j (the K tile row it already sits next to), and two spare warps do that row's softmax and
+//     its P V from the V tile in shared memory.  No padding to 384 rows, no second kernel.
 // Softmax: single pass against the exact maximum of the row's first 32 patch scores and its CLS score; a later 32-key chunk
 // whose sum exceeds 2^13 (a score more than ~8 above the reference, log2 domain) raises the reference and rescales what
 // was written so far -- the usual online-softmax correction, applied to the 16-bit P in TMEM (warp-voted, rare).
@@ -44,11 +45,12 @@ struct VitSmem {
   static constexpr int OFF_V = OFF_K + K1 + K2;
   static constexpr int OFF_X = OFF_V + K1 + K2;                  // 3 x [q0 | k0 | v0] fp32, 96 each (triple buffered by item)
   static constexpr int X_ONE = 3 * VT_HD * 4;
-  static constexpr int OFF_PROB = OFF_X + 3 * X_ONE;             // CLS query row: 257 probabilities (+ pad)
-  static constexpr int OFF_PART = OFF_PROB + 264 * 4;            // 5 x 96 partial O rows
+  static constexpr int OFF_PROB = OFF_X + 3 * X_ONE;             // CLS query row: 2 x 257 scores -> probabilities (+ pad), by item parity
+  static constexpr int PROB_ONE = 264 * 4;
+  static constexpr int OFF_PART = OFF_PROB + 2 * PROB_ONE;       // 5 x 96 partial O rows
   static constexpr int OFF_RED = OFF_PART + 5 * VT_HD * 4;       // cross-warp max / sum
   static constexpr int OFF_BAR = OFF_RED + 64;
-  static constexpr int NBAR = 3 + 3 + 2 + 2 + 2 + 2 + 3;         // q/k/v full, q/k/v empty, s_full, p_full, o_full, o_empty, x_full
+  static constexpr int NBAR = 3 + 3 + 2 + 2 + 2 + 2 + 3 + 1;     // q/k/v full, q/k/v empty, s_full, p_full, o_full, o_empty, x_full, c_full
   static constexpr int TOTAL = OFF_BAR + NBAR * 8 + 16 + 1024;
   static constexpr int THREADS = 12 * 32;                        // TMA, MMA, 2 x 4 softmax, 2 CLS-row warps
 };
@@ -108,6 +110,7 @@ __device__ __forceinline__ float vt_dot8(uint4 x, const float* w, int dt) {
 }
 __device__ __forceinline__ void vt_bar_rows() { asm volatile("bar.sync 1, 64;" ::: "memory"); }   // the two CLS-row warps
 
+template <int DT>      // MRB_DT_F16 / MRB_DT_BF16 at compile time: the unpack / pack sequences are not predicated both ways
 __global__ void __launch_bounds__(VitSmem::THREADS, 1)
 attn_vit_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                 const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmQ2,
@@ -121,18 +124,21 @@ attn_vit_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   uint64_t* q_empty = bars + 3; uint64_t* k_empty = bars + 4; uint64_t* v_empty = bars + 5;
   uint64_t* s_full = bars + 6;  uint64_t* p_full = bars + 8;  uint64_t* o_full = bars + 10; uint64_t* o_empty = bars + 12;
   uint64_t* x_full = bars + 14;      // [3]
+  uint64_t* c_full = bars + 17;      // the 256 patch-key scores of the CLS query row are in shared memory
   uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + S::NBAR);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_items = p.frames * p.H;
-  const int dt = p.dtype;
+  constexpr int dt = DT;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV);
     tma_prefetch_desc(&tmQ2); tma_prefetch_desc(&tmK2); tma_prefetch_desc(&tmV2);
     mbar_init(q_full, 1); mbar_init(k_full, 1); mbar_init(v_full, 1);
     mbar_init(q_empty, 1 + 8);          // S MMAs retired + the 8 softmax warps read their Q rows (CLS-key score)
-    mbar_init(k_empty, 1 + 2);          // S MMAs retired + the 2 CLS-row warps read K
+    mbar_init(k_empty, 1 + 8 + 2);      // S MMAs retired + the 8 softmax warps read their K rows (score of the CLS query) + the CLS-row
+                                        // warps took those scores (keeps c_full at most one phase ahead of them)
+    mbar_init(c_full, 8);
     mbar_init(v_empty, 1 + 2);          // PV MMAs retired + the 2 CLS-row warps read V
     for (int g = 0; g < 2; ++g) { mbar_init(&s_full[g], 1); mbar_init(&p_full[g], 4); mbar_init(&o_full[g], 1); mbar_init(&o_empty[g], 4); }
     for (int x = 0; x < 3; ++x) mbar_init(&x_full[x], 2);
@@ -241,17 +247,41 @@ attn_vit_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       const uint32_t ph = n & 1;
       const float* xk0 = reinterpret_cast<const float*>(smem + S::OFF_X + (n % 3) * S::X_ONE) + VT_HD;
       const float* xv0 = xk0 + VT_HD;
-      // ---- score of the CLS key: q_r . k_0 on CUDA cores (Q row from the swizzled tile, k_0 broadcast)
+      // ---- the two rank-1 pieces on CUDA cores: the score of the CLS KEY for this thread's query row, q_r . k_0, and the score
+      //      of this thread's KEY (tile row g * 128 + r) for the CLS QUERY, q_0 . k_j -- 16-byte chunks of the swizzled tiles
+      //      against fp32 vectors broadcast from shared memory, four independent partial sums each
       mbar_wait(&x_full[n % 3], (n / 3) & 1);
       mbar_wait(q_full, ph);
-      float t_cls = 0.f;
+      mbar_wait(k_full, ph);
+      const float* xq0 = xk0 - VT_HD;
+      const uint8_t* k1 = sK;
+      const uint8_t* k2 = sK + S::K1;
+      const int jr = g * VT_ROWS + r;
+      float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f, b0 = 0.f, b1 = 0.f, b2 = 0.f, b3 = 0.f;
 #pragma unroll
-      for (int c = 0; c < 8; ++c) t_cls += vt_dot8(*vt_chunk128(q1, r, c), xk0 + c * 8, dt);
-#pragma unroll
-      for (int c = 0; c < 4; ++c) t_cls += vt_dot8(*vt_chunk64(q2, r, c), xk0 + VT_D1 + c * 8, dt);
-      t_cls *= sl2;
+      for (int c = 0; c < 8; c += 4) {
+        a0 += vt_dot8(*vt_chunk128(q1, r, c), xk0 + c * 8, dt);
+        a1 += vt_dot8(*vt_chunk128(q1, r, c + 1), xk0 + c * 8 + 8, dt);
+        a2 += vt_dot8(*vt_chunk128(q1, r, c + 2), xk0 + c * 8 + 16, dt);
+        a3 += vt_dot8(*vt_chunk128(q1, r, c + 3), xk0 + c * 8 + 24, dt);
+        b0 += vt_dot8(*vt_chunk128(k1, jr, c), xq0 + c * 8, dt);
+        b1 += vt_dot8(*vt_chunk128(k1, jr, c + 1), xq0 + c * 8 + 8, dt);
+        b2 += vt_dot8(*vt_chunk128(k1, jr, c + 2), xq0 + c * 8 + 16, dt);
+        b3 += vt_dot8(*vt_chunk128(k1, jr, c + 3), xq0 + c * 8 + 24, dt);
+      }
+      a0 += vt_dot8(*vt_chunk64(q2, r, 0), xk0 + VT_D1, dt);
+      a1 += vt_dot8(*vt_chunk64(q2, r, 1), xk0 + VT_D1 + 8, dt);
+      a2 += vt_dot8(*vt_chunk64(q2, r, 2), xk0 + VT_D1 + 16, dt);
+      a3 += vt_dot8(*vt_chunk64(q2, r, 3), xk0 + VT_D1 + 24, dt);
+      b0 += vt_dot8(*vt_chunk64(k2, jr, 0), xq0 + VT_D1, dt);
+      b1 += vt_dot8(*vt_chunk64(k2, jr, 1), xq0 + VT_D1 + 8, dt);
+      b2 += vt_dot8(*vt_chunk64(k2, jr, 2), xq0 + VT_D1 + 16, dt);
+      b3 += vt_dot8(*vt_chunk64(k2, jr, 3), xq0 + VT_D1 + 24, dt);
+      a0 += a2; a1 += a3; b0 += b2; b1 += b3;
+      const float t_cls = (a0 + a1) * sl2;
+      reinterpret_cast<float*>(smem + S::OFF_PROB + (n & 1) * S::PROB_ONE)[1 + jr] = (b0 + b1) * sl2;
       __syncwarp();
-      if (lane == 0) mbar_arrive(q_empty);
+      if (lane == 0) { mbar_arrive(q_empty); mbar_arrive(k_empty); mbar_arrive(c_full); }
 
       mbar_wait(&s_full[g], ph);
       tc_fence_after();
@@ -346,7 +376,6 @@ attn_vit_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     // ===================== CLS query row: 1 x 257 attention on CUDA cores from the tiles in shared memory =====================
     const int t = threadIdx.x - 10 * 32;                            // 0..63
     const int rw = warp - 10;
-    float* prob = reinterpret_cast<float*>(smem + S::OFF_PROB);     // [0] = CLS key, [1 + j] = patch key j
     float* part = reinterpret_cast<float*>(smem + S::OFF_PART);
     float* red = reinterpret_cast<float*>(smem + S::OFF_RED);
     const float sl2 = p.scale * 1.4426950408889634f;
@@ -382,25 +411,16 @@ attn_vit_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         if (lane == 0) mbar_arrive(&x_full[(n + 1) % 3]);
       }
       vt_bar_rows();                                               // this item's x buffer is complete for both warps (item 0: written above)
-      // ---- scores: thread t owns patch keys t, t + 64, t + 128, t + 192
-      mbar_wait(k_full, ph);
-      float sc[4];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int j = t + 64 * i;
-        float acc = 0.f;
-#pragma unroll
-        for (int c = 0; c < 8; ++c) acc += vt_dot8(*vt_chunk128(sK, j, c), xq0 + c * 8, dt);
-#pragma unroll
-        for (int c = 0; c < 4; ++c) acc += vt_dot8(*vt_chunk64(sK + S::K1, j, c), xq0 + VT_D1 + c * 8, dt);
-        sc[i] = acc * sl2;
-      }
+      // ---- scores of the 256 patch keys come from the softmax threads (one key each); thread t takes t, t + 64, t + 128, t + 192
+      float* prob = reinterpret_cast<float*>(smem + S::OFF_PROB + (n & 1) * S::PROB_ONE);     // [0] = CLS key, [1 + j] = patch key j
+      float s0 = xq0[lane] * xk0[lane] + xq0[lane + 32] * xk0[lane + 32] + xq0[lane + 64] * xk0[lane + 64];
+      s0 = warp_sum(s0) * sl2;                                     // CLS query against the CLS key
+      mbar_wait(c_full, ph);
       __syncwarp();
       if (lane == 0) mbar_arrive(k_empty);
-      float s0 = 0.f;
-#pragma unroll 8
-      for (int d = 0; d < VT_HD; ++d) s0 += xq0[d] * xk0[d];
-      s0 *= sl2;
+      float sc[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) sc[i] = prob[1 + t + 64 * i];
       float mx = fmaxf(fmaxf(fmaxf(sc[0], sc[1]), fmaxf(sc[2], sc[3])), s0);
       mx = warp_max(mx);
       if (lane == 0) red[rw] = mx;
@@ -414,7 +434,7 @@ attn_vit_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         sum += e;
       }
       const float e0 = vt_ex2(s0 - mx);
-      if (t == 0) { prob[0] = e0; sum += e0; }
+      if (t == 0) sum += e0;
       sum = warp_sum(sum);
       if (lane == 0) red[2 + rw] = sum;
       vt_bar_rows();
@@ -424,8 +444,10 @@ attn_vit_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       const int dc = t % 12, kp = t / 12;
       if (kp < 5) {
         float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        const uint8_t* vt = dc < 8 ? sV : sV + S::K1;
+#pragma unroll 4
         for (int j = kp; j < VT_KEYS; j += 5) {
-          const uint4 x = dc < 8 ? *vt_chunk128(sV, j, dc) : *vt_chunk64(sV + S::K1, j, dc - 8);
+          const uint4 x = dc < 8 ? *vt_chunk128(vt, j, dc) : *vt_chunk64(vt, j, dc - 8);
           const float pj = prob[1 + j];
           acc[0] = fmaf(pj, unpack_lo(x.x, dt), acc[0]); acc[1] = fmaf(pj, unpack_hi(x.x, dt), acc[1]);
           acc[2] = fmaf(pj, unpack_lo(x.y, dt), acc[2]); acc[3] = fmaf(pj, unpack_hi(x.y, dt), acc[3]);
@@ -440,7 +462,7 @@ attn_vit_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       vt_bar_rows();
       uint16_t* orow = p.o + b * p.o_bs + static_cast<long long>(h) * p.hd;       // token 0
       for (int d = t; d < p.hd; d += 64) {
-        float o = prob[0] * xv0[d];
+        float o = e0 * xv0[d];
 #pragma unroll
         for (int q5 = 0; q5 < 5; ++q5) o += part[q5 * VT_HD + d];
         o *= inv;
@@ -523,13 +545,17 @@ extern "C" int mrb_attention_vit(const void* q, long long q_bs, long long q_rs, 
     int dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    cudaError_t e = cudaFuncSetAttribute(attn_vit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, VitSmem::TOTAL);
+    cudaError_t e = cudaFuncSetAttribute(attn_vit_kernel<MRB_DT_F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, VitSmem::TOTAL);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(attn_vit_kernel<MRB_DT_BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, VitSmem::TOTAL);
     if (e != cudaSuccess) { sms = 0; return mrb_set_error(e); }
   }
   const int items = frames * H;
   const int grid = items < sms ? items : sms;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  MRB_LAUNCH((attn_vit_kernel), grid, VitSmem::THREADS, VitSmem::TOTAL, s, maps[0], maps[1], maps[2], maps[3], maps[4], maps[5], p);
+  if (dtype == MRB_DT_F16)
+    MRB_LAUNCH((attn_vit_kernel<MRB_DT_F16>), grid, VitSmem::THREADS, VitSmem::TOTAL, s, maps[0], maps[1], maps[2], maps[3], maps[4], maps[5], p);
+  else
+    MRB_LAUNCH((attn_vit_kernel<MRB_DT_BF16>), grid, VitSmem::THREADS, VitSmem::TOTAL, s, maps[0], maps[1], maps[2], maps[3], maps[4], maps[5], p);
   MRB_CHECK_LAUNCH();
   return MRB_OK;
 }

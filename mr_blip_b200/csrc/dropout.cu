@@ -7,6 +7,7 @@
 //             dx   += sum_j mask_j * ((dy sB_j) A_j)          (mrb_lora_dx_drop; the dense dy W part stays one tcgen05 GEMM over K = N)
 // dB_j = dy_j^T u_j needs no change: u_j already carries the mask.  Every backward kernel recomputes its mask from
 // (seed, site, row, column).
+#include <stdlib.h>
 #include "common.cuh"
 #include "dropmask.cuh"
 
@@ -311,10 +312,274 @@ __global__ void __launch_bounds__(256) lora_dx_drop_kernel(const uint16_t* __res
   }
 }
 
+
+// ================================================================ tensor-core versions of the three LoRA-dropout kernels
+// The CUDA-core kernels above spend 24 FMAs + the mask arithmetic per element and ran at 77 / 39 / 35 us per encoder-sized call
+// (28.5 ms of a 283 ms step: profiles/launch_summary_r02a_dropout.csv).  The products below are rank-8 contractions, i.e. tensor
+// core work (mma.sync m16n8k16 -- three Linears x 8 ranks is far too thin a problem for a tcgen05 tile); what stays on the CUDA
+// cores is the mask itself: one hash per four elements and Linear, applied to PACKED 16-bit pairs with two AND masks per word.
+// All three take the operand straight from global memory in the layout they find it: the fragment slots of an mma are permuted
+// so that a thread's 8 or 16 consecutive bytes of a row ARE its fragment (a dot product does not care in which order k runs).
+__device__ __forceinline__ void mma16816(float* c, const uint32_t* a, uint32_t b0, uint32_t b1, int dt) {
+#ifdef MRB_HOST_SHIM      // tests/cuda_host_shim: the CPU suite runs this source with an emulated warp
+  shim::mma_m16n8k16(c, a, b0, b1, dt);
+#else
+  if (dt == MRB_DT_F16)
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3]) : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+  else
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3]) : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+#endif
+}
+// m16n8k8: the dx kernel contracts over the 8 LoRA ranks only
+__device__ __forceinline__ void mma1688(float* c, uint32_t a0, uint32_t a1, uint32_t b0, int dt) {
+#ifdef MRB_HOST_SHIM
+  const uint32_t a[4] = {a0, a1, 0u, 0u};
+  shim::mma_m16n8k16(c, a, b0, 0u, dt);
+#else
+  if (dt == MRB_DT_F16)
+    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5}, {%6}, {%0,%1,%2,%3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3]) : "r"(a0), "r"(a1), "r"(b0));
+  else
+    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5}, {%6}, {%0,%1,%2,%3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3]) : "r"(a0), "r"(a1), "r"(b0));
+#endif
+}
+// The four draws of a mask word against ANY threshold, as AND masks over the two packed 16-bit pairs they cover (columns 0,1 and
+// 2,3 of the word's group).  draw >= thr <=> draw + (256 - thr) carries into bit 8; even and odd bytes are summed separately so no
+// carry crosses a draw.  add = (256 - thr) * 0x00010001.
+__device__ __forceinline__ void pair_masks(uint32_t w, uint32_t add, uint32_t& m01, uint32_t& m23) {
+  const uint32_t te = (w & 0x00ff00ffu) + add;                  // bit 8: draw 0 kept, bit 24: draw 2 kept
+  const uint32_t to = ((w >> 8) & 0x00ff00ffu) + add;           // bit 8: draw 1 kept, bit 24: draw 3 kept
+#ifdef MRB_HOST_SHIM
+  m01 = (((te >> 8) & 1u) ? 0x0000ffffu : 0u) | (((to >> 8) & 1u) ? 0xffff0000u : 0u);
+  m23 = (((te >> 24) & 1u) ? 0x0000ffffu : 0u) | (((to >> 24) & 1u) ? 0xffff0000u : 0u);
+#else
+  const uint32_t e7 = te << 7, o7 = to << 7;                    // the flags are now the sign bits of bytes 1 and 3
+  asm("prmt.b32 %0, %1, %2, %3;" : "=r"(m01) : "r"(e7), "r"(o7), "r"(0xDD99u));
+  asm("prmt.b32 %0, %1, %2, %3;" : "=r"(m23) : "r"(e7), "r"(o7), "r"(0xFFBBu));
+#endif
+}
+__device__ __forceinline__ uint32_t flag_mask(uint32_t t, int bit) { return 0u - ((t >> bit) & 1u); }   // 0xffffffff if the bit is set
+
+// ---- forward: u[m, 8j + r] = scale * sum_k keep_j(m,k) x[m,k] A[8j + r, k].  Block = 16 rows, its 8 warps split K; lane (g, t)
+//      loads 16 bytes of rows g and g + 8 (columns k0 + 8t ..): fragment slots (2t, 2t+1 | 2t+8, 2t+9) of two mma's are those 8
+//      columns, and the B fragment is the matching 16 bytes of A row 8j + g.  Partial sums of the warps meet in shared memory.
+template <int NL>
+__global__ void __launch_bounds__(256) lora_down_drop_mma_kernel(const uint16_t* __restrict__ x, long long ldx, const uint16_t* __restrict__ A,
+                                                                 long long lda, int M, int K, uint16_t* __restrict__ out, long long ldo,
+                                                                 int dtype, const DropSpec d) {
+  pdl_trigger();
+  pdl_wait();
+  __shared__ float red[8 * NL * 16 * 8];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  const int m0 = blockIdx.x * 16, r0 = m0 + g, r1 = r0 + 8;
+  const bool ok0 = r0 < M, ok1 = r1 < M;
+  const int steps = (K + 31) >> 5, per = (steps + 7) >> 3;
+  const int ks = warp * per * 32, ke = min(K, ks + per * 32);
+  const uint32_t ng = static_cast<uint32_t>(K >> 2), rb0 = static_cast<uint32_t>(r0) * ng, rb1 = static_cast<uint32_t>(r1) * ng;
+  const uint32_t add = (256u - d.thr) * 0x00010001u;
+  uint32_t key[NL];
+  float acc[NL][4];
+#pragma unroll
+  for (int j = 0; j < NL; ++j) {
+    key[j] = drop_key(*d.seed, d.site + j);
+    acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.f;
+  }
+  const uint4 zero4 = make_uint4(0u, 0u, 0u, 0u);
+  for (int k0 = ks; k0 < ke; k0 += 32) {
+    const int kk = k0 + 8 * t;
+    const bool inb = kk < K;
+    const uint4 xa = (ok0 && inb) ? *reinterpret_cast<const uint4*>(x + static_cast<long long>(r0) * ldx + kk) : zero4;
+    const uint4 xb = (ok1 && inb) ? *reinterpret_cast<const uint4*>(x + static_cast<long long>(r1) * ldx + kk) : zero4;
+    const uint32_t gq = static_cast<uint32_t>(kk) >> 2;
+#pragma unroll
+    for (int j = 0; j < NL; ++j) {
+      const uint4 aj = inb ? *reinterpret_cast<const uint4*>(A + static_cast<long long>(8 * j + g) * lda + kk) : zero4;
+      uint32_t a01, a23, a45, a67, b01, b23, b45, b67;
+      pair_masks(drop_word(key[j], rb0, gq), add, a01, a23);
+      pair_masks(drop_word(key[j], rb0, gq + 1u), add, a45, a67);
+      pair_masks(drop_word(key[j], rb1, gq), add, b01, b23);
+      pair_masks(drop_word(key[j], rb1, gq + 1u), add, b45, b67);
+      const uint32_t f1[4] = {xa.x & a01, xb.x & b01, xa.y & a23, xb.y & b23};
+      mma16816(acc[j], f1, aj.x, aj.y, dtype);
+      const uint32_t f2[4] = {xa.z & a45, xb.z & b45, xa.w & a67, xb.w & b67};
+      mma16816(acc[j], f2, aj.z, aj.w, dtype);
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < NL; ++j) {
+    float* rj = red + ((warp * NL + j) * 16) * 8;
+    rj[g * 8 + 2 * t] = acc[j][0]; rj[g * 8 + 2 * t + 1] = acc[j][1];
+    rj[(g + 8) * 8 + 2 * t] = acc[j][2]; rj[(g + 8) * 8 + 2 * t + 1] = acc[j][3];
+  }
+  __syncthreads();
+  for (int idx = threadIdx.x; idx < 16 * 16; idx += 256) {        // (row, pair of output columns): 16 rows x 16 pairs = 32 columns
+    const int row = idx >> 4, c2 = (idx & 15) * 2, m = m0 + row;
+    if (m >= M) continue;
+    float s0 = 0.f, s1 = 0.f;
+    if (c2 < 8 * NL) {
+      const int j = c2 >> 3, n = c2 & 7;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) {
+        s0 += red[((w * NL + j) * 16 + row) * 8 + n];
+        s1 += red[((w * NL + j) * 16 + row) * 8 + n + 1];
+      }
+    }
+    *reinterpret_cast<uint32_t*>(out + static_cast<long long>(m) * ldo + c2) = pack2(s0 * d.scale, s1 * d.scale, dtype);
+  }
+}
+
+// ---- weight gradient: dA[r, k] += scale * sum_m keep(m,k) x[m,k] q[m,r].  The contraction runs over ROWS of x, whose pairs are
+//      not adjacent in memory; so the two halves of a B register (x[m,k], x[m,k+1]) are made two different OUTPUT columns instead:
+//      the 16 output rows of the mma are (rank r, parity), the A fragment holds q[m, r] in the half that matches its parity and 0 in
+//      the other, and one mma contracts 8 rows of x for 16 columns.  Lane (g, t) loads 8 bytes of rows m + t and m + 4 + t (columns
+//      kc0 + 4g ..): one mask word per load.  Block = 32 columns x rows_per_block rows, its 8 warps split the rows and meet in
+//      shared memory: one fp32 atomic per output element and block.
+__global__ void __launch_bounds__(256) lora_wgrad_drop_mma_kernel(const uint16_t* __restrict__ x, long long ldx, const uint16_t* __restrict__ q,
+                                                                  long long ldq, int M, int K, float* __restrict__ dA, int dtype,
+                                                                  int rows_per_block, const DropSpec d) {
+  pdl_trigger();
+  pdl_wait();
+  __shared__ float red[8 * 8 * 32];                              // [warp][rank][column]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  const int kc0 = blockIdx.x * 32, kk = kc0 + 4 * g;
+  const bool inb = kk < K;                                       // K is a multiple of 8, kk of 4: the 8-byte load is in or out as a whole
+  const int per_warp = rows_per_block >> 3;                      // multiple of 8
+  const int m0 = blockIdx.y * rows_per_block + warp * per_warp, m1 = min(M, m0 + per_warp);
+  const uint32_t key = drop_key(*d.seed, d.site), ng = static_cast<uint32_t>(K >> 2), gq = static_cast<uint32_t>(kk) >> 2;
+  const uint32_t add = (256u - d.thr) * 0x00010001u;
+  const int ra = g >> 1, sh = (g & 1) * 16;                      // rank of output row g (row g + 8: rank ra + 4), parity -> half
+  float c1[4] = {0.f, 0.f, 0.f, 0.f}, c2[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 4
+  for (int mm = m0; mm < m1; mm += 8) {
+    const int ma = mm + t, mb = mm + 4 + t;
+    const bool oka = ma < m1, okb = mb < m1;
+    uint2 xa = make_uint2(0u, 0u), xb = make_uint2(0u, 0u);
+    uint4 qa = make_uint4(0u, 0u, 0u, 0u), qb = make_uint4(0u, 0u, 0u, 0u);
+    if (oka) { qa = *reinterpret_cast<const uint4*>(q + static_cast<long long>(ma) * ldq); if (inb) xa = *reinterpret_cast<const uint2*>(x + static_cast<long long>(ma) * ldx + kk); }
+    if (okb) { qb = *reinterpret_cast<const uint4*>(q + static_cast<long long>(mb) * ldq); if (inb) xb = *reinterpret_cast<const uint2*>(x + static_cast<long long>(mb) * ldx + kk); }
+    uint32_t a01, a23, b01, b23;
+    pair_masks(drop_word(key, static_cast<uint32_t>(ma) * ng, gq), add, a01, a23);
+    pair_masks(drop_word(key, static_cast<uint32_t>(mb) * ng, gq), add, b01, b23);
+    // q[m, ra] and q[m, ra + 4] (ranks 0..3 live in words x, y; 4..7 in z, w), moved into the half of this row's parity
+    const uint32_t qa_lo = (((ra & 2) ? qa.y : qa.x) >> ((ra & 1) * 16)) & 0xffffu, qa_hi = (((ra & 2) ? qa.w : qa.z) >> ((ra & 1) * 16)) & 0xffffu;
+    const uint32_t qb_lo = (((ra & 2) ? qb.y : qb.x) >> ((ra & 1) * 16)) & 0xffffu, qb_hi = (((ra & 2) ? qb.w : qb.z) >> ((ra & 1) * 16)) & 0xffffu;
+    const uint32_t af[4] = {qa_lo << sh, qa_hi << sh, qb_lo << sh, qb_hi << sh};
+    mma16816(c1, af, xa.x & a01, xb.x & b01, dtype);             // columns kc0 + 4n + parity
+    mma16816(c2, af, xa.y & a23, xb.y & b23, dtype);             // columns kc0 + 4n + 2 + parity
+  }
+  // thread holds output rows g (rank ra) and g + 8 (rank ra + 4), mma columns n = 2t, 2t + 1 -> column 4n + parity (+ 2)
+  const int par = g & 1;
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const int r = ra + (e >> 1) * 4, n = 2 * t + (e & 1);
+    red[(warp * 8 + r) * 32 + 4 * n + par] = c1[e];
+    red[(warp * 8 + r) * 32 + 4 * n + par + 2] = c2[e];
+  }
+  __syncthreads();
+  {
+    const int r = threadIdx.x >> 5, c = threadIdx.x & 31;          // 8 ranks x 32 columns = 256 threads
+    float sum = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) sum += red[(w * 8 + r) * 32 + c];
+    if (kc0 + c < K) atomicAdd(dA + static_cast<long long>(r) * K + kc0 + c, sum * d.scale);
+  }
+}
+
+// ---- input gradient: dx[m,k] += scale * sum_j keep_j(m,k) (q_j[m,:] . A_j[:,k]).  One mma per (16 rows, 8 columns, Linear) with the 8
+//      ranks in the lower half of its k slots; the 8 mma columns are permuted (n -> 4 (n / 2) + n % 2, second tile + 2) so that a
+//      thread's accumulators of a tile pair are 4 CONSECUTIVE columns of rows g and g + 8: one mask word, one 8 / 16-byte
+//      read-modify-write (mma m16n8k8: the k slots are exactly the 8 ranks).  A^T of the block's 256 columns sits in shared memory ([Linear][column][rank], 16 bit).
+template <int NL, bool F32OUT>
+__global__ void __launch_bounds__(256) lora_dx_drop_mma_kernel(const uint16_t* __restrict__ q, long long ldq, const uint16_t* __restrict__ A,
+                                                               long long lda, void* __restrict__ dx, long long lddx, int M, int K, int dtype,
+                                                               int rows_per_block, const DropSpec d) {
+  pdl_trigger();
+  pdl_wait();
+  __shared__ __align__(16) uint16_t At[NL * 256 * 8];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  const int cb = blockIdx.x * 256;
+  for (int i = threadIdx.x; i < NL * 8 * 32; i += 256) {          // one 16-byte chunk (8 columns) of one A row -> 8 transposed entries
+    const int r = i >> 5, c8 = (i & 31) * 8;                       // r = 8 j + rank
+    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+    if (cb + c8 < K) v = *reinterpret_cast<const uint4*>(A + static_cast<long long>(r) * lda + cb + c8);
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+    uint16_t* dst = At + ((r >> 3) * 256 + c8) * 8 + (r & 7);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) { dst[(2 * e) * 8] = static_cast<uint16_t>(w[e] & 0xffffu); dst[(2 * e + 1) * 8] = static_cast<uint16_t>(w[e] >> 16); }
+  }
+  __syncthreads();
+  const int kc0 = cb + warp * 32;
+  if (kc0 >= K) return;
+  const int m0 = blockIdx.y * rows_per_block, m1 = min(M, m0 + rows_per_block);
+  const uint32_t ng = static_cast<uint32_t>(K >> 2), add = (256u - d.thr) * 0x00010001u;
+  uint32_t key[NL];
+#pragma unroll
+  for (int j = 0; j < NL; ++j) key[j] = drop_key(*d.seed, d.site + j);
+  const int coln = 4 * (g >> 1) + (g & 1);                          // column (inside a 16-column tile pair) that mma column g stands for
+  for (int mm = m0; mm < m1; mm += 16) {
+    const int r0 = mm + g, r1 = mm + g + 8;
+    const bool ok0 = r0 < m1, ok1 = r1 < m1;
+    uint32_t qf[NL][2];
+#pragma unroll
+    for (int j = 0; j < NL; ++j) {
+      qf[j][0] = ok0 ? *reinterpret_cast<const uint32_t*>(q + static_cast<long long>(r0) * ldq + 8 * j + 2 * t) : 0u;
+      qf[j][1] = ok1 ? *reinterpret_cast<const uint32_t*>(q + static_cast<long long>(r1) * ldq + 8 * j + 2 * t) : 0u;
+    }
+#pragma unroll
+    for (int pr = 0; pr < 2; ++pr) {                                // two 16-column tile pairs of the warp's 32 columns
+      const int kp0 = kc0 + 16 * pr, kth = kp0 + 4 * t;             // this thread's 4 output columns
+      float s0[4] = {0.f, 0.f, 0.f, 0.f}, s1[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int j = 0; j < NL; ++j) {
+        const uint16_t* at = At + (j * 256 + (kp0 - cb) + coln) * 8 + 2 * t;
+        const uint32_t bA = *reinterpret_cast<const uint32_t*>(at), bB = *reinterpret_cast<const uint32_t*>(at + 2 * 8);
+        float ca[4] = {0.f, 0.f, 0.f, 0.f}, cc[4] = {0.f, 0.f, 0.f, 0.f};
+        mma1688(ca, qf[j][0], qf[j][1], bA, dtype);                 // columns kth, kth + 1   (rows g: ca[0..1], g + 8: ca[2..3])
+        mma1688(cc, qf[j][0], qf[j][1], bB, dtype);                 // columns kth + 2, kth + 3
+        const uint32_t w0 = drop_word(key[j], static_cast<uint32_t>(r0) * ng, static_cast<uint32_t>(kth) >> 2);
+        const uint32_t w1 = drop_word(key[j], static_cast<uint32_t>(r1) * ng, static_cast<uint32_t>(kth) >> 2);
+        const uint32_t e0 = (w0 & 0x00ff00ffu) + add, o0 = ((w0 >> 8) & 0x00ff00ffu) + add;
+        const uint32_t e1 = (w1 & 0x00ff00ffu) + add, o1 = ((w1 >> 8) & 0x00ff00ffu) + add;
+        s0[0] += __uint_as_float(__float_as_uint(ca[0]) & flag_mask(e0, 8));  s0[1] += __uint_as_float(__float_as_uint(ca[1]) & flag_mask(o0, 8));
+        s0[2] += __uint_as_float(__float_as_uint(cc[0]) & flag_mask(e0, 24)); s0[3] += __uint_as_float(__float_as_uint(cc[1]) & flag_mask(o0, 24));
+        s1[0] += __uint_as_float(__float_as_uint(ca[2]) & flag_mask(e1, 8));  s1[1] += __uint_as_float(__float_as_uint(ca[3]) & flag_mask(o1, 8));
+        s1[2] += __uint_as_float(__float_as_uint(cc[2]) & flag_mask(e1, 24)); s1[3] += __uint_as_float(__float_as_uint(cc[3]) & flag_mask(o1, 24));
+      }
+      if (kth >= K) continue;                                       // K is a multiple of 8 and kth of 4: all four columns in or out
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int r = h ? r1 : r0;
+        if (!(h ? ok1 : ok0)) continue;
+        const float* sv = h ? s1 : s0;
+        if (F32OUT) {
+          float4* pp = reinterpret_cast<float4*>(static_cast<float*>(dx) + static_cast<long long>(r) * lddx + kth);
+          float4 a = *pp;
+          a.x += sv[0] * d.scale; a.y += sv[1] * d.scale; a.z += sv[2] * d.scale; a.w += sv[3] * d.scale;
+          *pp = a;
+        } else {
+          uint2* pp = reinterpret_cast<uint2*>(static_cast<uint16_t*>(dx) + static_cast<long long>(r) * lddx + kth);
+          const uint2 v = *pp;
+          *pp = make_uint2(pack2(unpack_lo(v.x, dtype) + sv[0] * d.scale, unpack_hi(v.x, dtype) + sv[1] * d.scale, dtype),
+                           pack2(unpack_lo(v.y, dtype) + sv[2] * d.scale, unpack_hi(v.y, dtype) + sv[3] * d.scale, dtype));
+        }
+      }
+    }
+  }
+}
+
 }  // namespace mrb
 
 using namespace mrb;
 #define STREAM static_cast<cudaStream_t>(stream)
+// MRB_LORA_DROP_MMA=0 keeps the CUDA-core LoRA-dropout kernels of round 1 (A/B measurements)
+static bool lora_drop_mma() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("MRB_LORA_DROP_MMA"); v = (e && e[0] == '0') ? 0 : 1; }
+  return v != 0;
+}
 static inline unsigned blocks_for(long long n, int per) { return static_cast<unsigned>((n + per - 1) / per); }
 static inline bool bad16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) != 0; }
 static inline bool half_dt(int dt) { return dt == MRB_DT_F16 || dt == MRB_DT_BF16; }
@@ -396,6 +661,17 @@ extern "C" int mrb_lora_down_drop(const void* x, long long ldx, const void* A, l
   const uint16_t* xp = static_cast<const uint16_t*>(x);
   const uint16_t* Ap = static_cast<const uint16_t*>(A);
   uint16_t* op = static_cast<uint16_t*>(out);
+  if (lora_drop_mma()) {
+    const unsigned grid = blocks_for(M, 16);
+    switch (nlin) {
+      case 1: MRB_LAUNCH((lora_down_drop_mma_kernel<1>), grid, 256, 0, STREAM, xp, ldx, Ap, lda, M, K, op, ldo, dtype, d); break;
+      case 2: MRB_LAUNCH((lora_down_drop_mma_kernel<2>), grid, 256, 0, STREAM, xp, ldx, Ap, lda, M, K, op, ldo, dtype, d); break;
+      case 3: MRB_LAUNCH((lora_down_drop_mma_kernel<3>), grid, 256, 0, STREAM, xp, ldx, Ap, lda, M, K, op, ldo, dtype, d); break;
+      default: return MRB_ERR_ARG;
+    }
+    MRB_CHECK_LAUNCH();
+    return MRB_OK;
+  }
   // few rows (decoder steps): a warp per row so that the launch still covers the SMs; otherwise 8 lanes per row
   if (M <= 2048) return launch_down<32>(nlin, blocks_for(M, 4), STREAM, xp, ldx, Ap, lda, M, K, op, ldo, dtype, d);
   return launch_down<8>(nlin, blocks_for(M, 16), STREAM, xp, ldx, Ap, lda, M, K, op, ldo, dtype, d);
@@ -406,6 +682,14 @@ extern "C" int mrb_lora_wgrad_drop(const void* x, long long ldx, const void* q, 
   if (M <= 0 || K <= 0) return MRB_OK;
   if (!seed || (K & 7) || (ldx & 7) || (ldq & 7) || !half_dt(dtype) || bad16(x) || bad16(q) || p < 0.f || p >= 1.f) return MRB_ERR_ARG;
   const DropSpec d = make_drop(seed, site, p);
+  if (lora_drop_mma()) {
+    const int rpb = M <= 512 ? 64 : (M <= 4096 ? 512 : 2048);       // 8 warps x (rpb / 8) rows; a multiple of 64
+    dim3 grid(blocks_for(K, 32), blocks_for(M, rpb));
+    MRB_LAUNCH((lora_wgrad_drop_mma_kernel), grid, 256, 0, STREAM, static_cast<const uint16_t*>(x), ldx, static_cast<const uint16_t*>(q), ldq,
+               M, K, dA, dtype, rpb, d);
+    MRB_CHECK_LAUNCH();
+    return MRB_OK;
+  }
   const int rows_per_block = M <= 1024 ? 64 : 256;
   dim3 grid(blocks_for(K, 256), blocks_for(M, rows_per_block));
   MRB_LAUNCH((lora_wgrad_drop_kernel), grid, 256, 0, STREAM, static_cast<const uint16_t*>(x), ldx, static_cast<const uint16_t*>(q), ldq, M, K,
@@ -425,6 +709,21 @@ extern "C" int mrb_lora_dx_drop(const void* q, long long ldq, const void* A, lon
   dim3 grid(blocks_for(K, 256), blocks_for(M, rows_per_block));
   const uint16_t* qp = static_cast<const uint16_t*>(q);
   const uint16_t* Ap = static_cast<const uint16_t*>(A);
+  if (lora_drop_mma()) {
+#define MRB_DXM(NLV)                                                                                                               \
+  if (dx_dtype == MRB_DT_F32) MRB_LAUNCH((lora_dx_drop_mma_kernel<NLV, true>), grid, 256, 0, STREAM, qp, ldq, Ap, lda, dx, lddx, M, K,   \
+                                         dtype, rows_per_block, d);                                                               \
+  else MRB_LAUNCH((lora_dx_drop_mma_kernel<NLV, false>), grid, 256, 0, STREAM, qp, ldq, Ap, lda, dx, lddx, M, K, dtype, rows_per_block, d)
+    switch (nlin) {
+      case 1: MRB_DXM(1); break;
+      case 2: MRB_DXM(2); break;
+      case 3: MRB_DXM(3); break;
+      default: return MRB_ERR_ARG;
+    }
+#undef MRB_DXM
+    MRB_CHECK_LAUNCH();
+    return MRB_OK;
+  }
 #define MRB_DX(NLV)                                                                                                                \
   if (dx_dtype == MRB_DT_F32) MRB_LAUNCH((lora_dx_drop_kernel<NLV, true>), grid, 256, 0, STREAM, qp, ldq, Ap, lda, dx, lddx, M, K, dtype, \
                                          rows_per_block, d);                                                                      \

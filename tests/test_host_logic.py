@@ -1127,6 +1127,7 @@ def attention_kernels_on_host(tmp_path_factory):
     d = tmp_path_factory.mktemp("shim_attn")
     shutil.copy(os.path.join(root, "tests", "cuda_host_shim", "common.cuh"), d)
     shutil.copy(os.path.join(root, "mr_blip_b200", "csrc", "dropmask.cuh"), d)
+    shutil.copy(os.path.join(root, "mr_blip_b200", "csrc", "attn_delta.cuh"), d)
     src = open(os.path.join(root, "mr_blip_b200", "csrc", "attention.cu")).read()
     src, n1 = _re.subn(r"extern __shared__ __align__\(\d+\) uint8_t smem_attn\[\];", "", src)      # the shim owns the buffer
     src, n2 = _re.subn(r"extern __shared__ float sp\[\];", "float* sp = reinterpret_cast<float*>(smem_attn);", src)
