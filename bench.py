@@ -292,18 +292,6 @@ def workload(cfg, model):
                    "half of the step replays one captured CUDA graph" % drop)
 
 
-FAMILIES = (("gemm", ("mrb_gemm", "mrb_small_down", "mrb_lora_down")), ("attention", ("mrb_attention",)),
-            ("norm", ("mrb_norm", "mrb_rmsnorm_bwd")), ("lora_wgrad", ("mrb_skinny_wgrad", "mrb_lora_wgrad")),
-            ("dropout", ("mrb_dropout", "mrb_lora_dx_drop")), ("gated_gelu", ("mrb_gated_gelu",)))
-
-
-def family_of(name):
-    for fam, prefixes in FAMILIES:
-        if name.startswith(prefixes):
-            return fam
-    return "other"
-
-
 def run_b200(args, cfg_name, cfg):
     from mr_blip_b200 import _lib, ops, dist as mdist
     from mr_blip_b200.blip2_mr import BLIP2_MR
@@ -394,6 +382,27 @@ def run_b200(args, cfg_name, cfg):
         step(video_u8, True)
     ms_u8, _, _ = timed(video_u8, True, args.steps)
     log("e2e uint8 region done")
+    # the gradient exchange alone (N > 1): CUDA events around the all-reduce of a few more steps, max over ranks
+    ar_ms = None
+    if train and world > 1:
+        ts = []
+        for _ in range(3):
+            samples["video"] = video_dev
+            loss = model(samples)["loss"]
+            loss.backward()
+            a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize()
+            tdist.barrier()
+            a0.record()
+            reducer()
+            a1.record()
+            torch.cuda.synchronize()
+            ts.append(a0.elapsed_time(a1))
+            opt.step()
+            opt.zero_grad(set_to_none=True)
+        t = torch.tensor([sorted(ts)[1]], device=dev)
+        tdist.all_reduce(t, op=tdist.ReduceOp.MAX)
+        ar_ms = t.item()
     clips = B * world * args.steps
     value = clips / (ms / 1e3)
     e2e = clips / (ms_e2e / 1e3)
@@ -418,6 +427,10 @@ def run_b200(args, cfg_name, cfg):
     if train:
         line["loss"] = float(last)
         line["config"].update(L_enc=host["Le"], L_dec=host["Ld"])
+    if ar_ms is not None:
+        line["grad_allreduce"] = {"ms": ar_ms, "bytes": int(sum(p.numel() for p in trainable) * 4), "share_of_step": ar_ms / (ms / args.steps),
+                                  "what": "one in-place NCCL all-reduce (AVG) of the flat fp32 gradient buffer after backward, timed alone "
+                                          "(barrier first), median of 3, max over ranks"}
 
     if rank == 0:
         # ---- roofline of the dominant kernel (gemm2_tcgen05_kernel, the 2-CTA tcgen05 GEMM, plus its 1-CTA sibling for the
@@ -425,7 +438,6 @@ def run_b200(args, cfg_name, cfg):
         qf_engine = model.engines()[1]
         qf_engine.xattn_events = []
         ops.GEMM_PROFILE = []
-        _lib.PROFILE = []
         samples["video"] = video_dev
         model.cuda_graphs = False                  # per-launch CUDA events need the eager launch sequence
         t5_engine = model.engines()[2]
@@ -437,7 +449,6 @@ def run_b200(args, cfg_name, cfg):
         torch.cuda.synchronize()
         model.cuda_graphs, t5_engine.decode_graphs = True, dg
         prof, ops.GEMM_PROFILE = ops.GEMM_PROFILE, None
-        calls, _lib.PROFILE = _lib.PROFILE, None
         xev, qf_engine.xattn_events = qf_engine.xattn_events, None
         x_ms = sum(a.elapsed_time(b) for a, b in xev)
         x_flops = B * cfg["frames"] * 6 * 1.137e9     # 1.137 GF per frame and cross-attention layer
@@ -460,14 +471,6 @@ def run_b200(args, cfg_name, cfg):
                             "traffic": NCU_FC1_TRAFFIC, "traffic_algorithmic": 948.9e6,
                             "traffic_source": "profiles/ncu_gemm2_fc1_r01c.csv (ncu --set full, one fc1 launch; constant, not "
                                               "measured in this run)"}
-        # every C-ABI call of that pass by kernel family: the part of the step the roofline object does not describe
-        fam = {}
-        for name, a, b in calls:
-            f = fam.setdefault(family_of(name), {"ms": 0.0, "calls": 0})
-            f["ms"] += a.elapsed_time(b)
-            f["calls"] += 1
-        line["kernel_families"] = {"note": "CUDA-event time per C-ABI call of one eager pass (events serialise the side streams)",
-                                   **{k: {"ms": round(v["ms"], 2), "calls": v["calls"]} for k, v in sorted(fam.items())}}
         line["qformer_xattn"] = {"what": "Q-Former cross-attention path: batched K/V projection GEMM (6 layers, tcgen05) + 6 attention cores",
                                  "flops_per_step": x_flops, "ms_per_step": x_ms, "achieved": x_flops / (x_ms / 1e3) / 1e12,
                                  "unit": "TFLOP/s", "frac": x_flops / (x_ms / 1e3) / 1e12 / pk["bf16_tflops_sustained"]}

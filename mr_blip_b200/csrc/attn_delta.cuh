@@ -44,20 +44,21 @@ __device__ __forceinline__ void delta_mma(float* c, const uint32_t* a, uint32_t 
 #endif
 }
 
-// Block = (chunk of DELTA_KEYS_PER_BLOCK keys, head, batch), 4 warps; a warp takes 8-key tiles and, per 16-row query tile, forms
+// Block = (head, batch), 8 warps; a warp takes every 8th 8-key tile and, per 16-row query tile, forms
 // S = Q K^T and dP = dO V^T with mma.sync m16n8k16 (hd = 64 = 4 k-steps).  The k slots are permuted so that a lane's fragment of a
 // K / V / Q / dO row is the 32 consecutive bytes [32 t, 32 t + 32) of that row (two 16-byte loads; a dot product does not care in
-// which order d runs): K and V of a head are read from L2 exactly once per launch.  (A first version with one block per query
-// row re-read them Lq times: 1 GB of L2 traffic, 106 us per decoder layer.)  Partial sums go to delta with one atomic per
-// (row, warp); the launcher zeroes delta first.
-constexpr int DELTA_KEYS_PER_BLOCK = 256;
+// which order d runs): K and V of a head are read from L2 exactly once per query tile.  (A first version with one block per query
+// row re-read them Lq times: 1 GB of L2 traffic, 106 us per decoder layer.)  The warps' partial sums meet in shared memory in a
+// fixed order: no atomics, the result is bit-reproducible from run to run (graph replay vs eager launches compare exactly).
+constexpr int DELTA_WARPS = 8;
 
-static __global__ void __launch_bounds__(128) attn_delta_exact_kernel(const DeltaExactParams p) {
+static __global__ void __launch_bounds__(DELTA_WARPS * 32) attn_delta_exact_kernel(const DeltaExactParams p) {
   pdl_trigger();
   pdl_wait();
-  const int h = blockIdx.y, b = blockIdx.z;
+  __shared__ float red[DELTA_WARPS][16];
+  const int h = blockIdx.x, b = blockIdx.y;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
-  const int key_lo = blockIdx.x * DELTA_KEYS_PER_BLOCK, key_hi = min(p.Lk, key_lo + DELTA_KEYS_PER_BLOCK);
+  const int key_lo = 0, key_hi = p.Lk;
   const float LOG2E = 1.4426950408889634f;
   const float sl2 = p.scale * LOG2E;
   const float* bhead = p.bias ? p.bias + static_cast<long long>(h) * p.bias_len : nullptr;
@@ -80,7 +81,7 @@ static __global__ void __launch_bounds__(128) attn_delta_exact_kernel(const Delt
     }
     const float lse_a = oka ? p.lse[row0 + ia] * LOG2E : 0.f, lse_b = okb ? p.lse[row0 + ib] * LOG2E : 0.f;
     float acc_a = 0.f, acc_b = 0.f;
-    for (int j0 = key_lo + 8 * warp; j0 < key_hi; j0 += 32) {
+    for (int j0 = key_lo + 8 * warp; j0 < key_hi; j0 += 8 * DELTA_WARPS) {
       // B fragments: key j0 + g, bytes [32 t, 32 t + 32) of its K and V rows
       const int jk = j0 + g;
       const bool okk = jk < key_hi;
@@ -125,23 +126,20 @@ static __global__ void __launch_bounds__(128) attn_delta_exact_kernel(const Delt
     // the four lanes of a row group hold partial sums of the same two rows
     acc_a += __shfl_xor_sync(0xffffffffu, acc_a, 1); acc_a += __shfl_xor_sync(0xffffffffu, acc_a, 2);
     acc_b += __shfl_xor_sync(0xffffffffu, acc_b, 1); acc_b += __shfl_xor_sync(0xffffffffu, acc_b, 2);
-    if (t == 0) {
-      if (oka) atomicAdd(p.delta + row0 + ia, acc_a);
-      if (okb) atomicAdd(p.delta + row0 + ib, acc_b);
+    __syncthreads();                                             // the previous query tile's sums have been read
+    if (t == 0) { red[warp][g] = acc_a; red[warp][g + 8] = acc_b; }
+    __syncthreads();
+    if (threadIdx.x < 16 && i0 + threadIdx.x < p.Lq) {
+      float sum = 0.f;
+#pragma unroll
+      for (int w = 0; w < DELTA_WARPS; ++w) sum += red[w][threadIdx.x];
+      p.delta[row0 + i0 + threadIdx.x] = sum;
     }
   }
 }
 
-// zero delta, then one launch over (key chunks, heads, batch)
 static inline int launch_delta_exact(const DeltaExactParams& d, cudaStream_t s) {
-#ifndef MRB_HOST_SHIM
-  cudaError_t e = cudaMemsetAsync(d.delta, 0, sizeof(float) * static_cast<size_t>(d.B) * d.H * d.Lq, s);
-  if (e != cudaSuccess) return mrb_set_error(e);
-#else
-  for (long long i = 0; i < static_cast<long long>(d.B) * d.H * d.Lq; ++i) d.delta[i] = 0.f;
-#endif
-  const int chunks = (d.Lk + DELTA_KEYS_PER_BLOCK - 1) / DELTA_KEYS_PER_BLOCK;
-  MRB_LAUNCH((attn_delta_exact_kernel), dim3(chunks, d.H, d.B), 128, 0, s, d);
+  MRB_LAUNCH((attn_delta_exact_kernel), dim3(d.H, d.B), DELTA_WARPS * 32, 0, s, d);
   MRB_CHECK_LAUNCH();
   return MRB_OK;
 }
