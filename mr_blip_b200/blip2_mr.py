@@ -108,6 +108,14 @@ class BLIP2_MR(Blip2Base):
             self.video_processor_answerer_eval = VideoProcessor(image_size=img_size, n_frms=num_frames_for_answer)
         if "lora" not in task:
             raise NotImplementedError("only LoRA tasks are implemented (every mr_BLIP yaml uses qformer_freeze_lora)")
+        if not freeze_vit or "qformer_freeze" not in task:
+            # the reference would train the ViT / the Q-Former here; this path has forward kernels only for both (every mr_BLIP
+            # recipe freezes them: SURVEY.md section 3.1) -- refuse instead of silently training something else
+            raise NotImplementedError("freeze_vit=False / a task without 'qformer_freeze' needs ViT / Q-Former backward kernels, "
+                                      "which this path does not have")
+        # use_grad_checkpoint (eva_vit.py:352: torch.utils.checkpoint over the ViT blocks) only trades memory for time in a ViT
+        # that stores activations; the frozen ViT here stores none, so the flag is accepted and changes nothing
+        self.use_grad_checkpoint = bool(use_grad_checkpoint)
         self.task = task
         self.use_lora = True
         self.post_process = mr_utils.post_process

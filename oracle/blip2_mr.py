@@ -77,13 +77,15 @@ def clean_timestamp_ids(tok, values):
 
 def prompt_concatenation(sd, d, tok, timestamps, durations, frames_for_t5, video_prompt_end, query_prompt,
                          task_prompt, n_per_frame, table=None, max_txt_len=200, prefix=_t5.PREFIX,
-                         input_time_format="seconds_integers", interleave_data=True):
+                         input_time_format="seconds_integers", interleave_data=True, task="qformer_freeze_lora"):
     """blip2_mr.py:572-824, interleave branch:
        [f_0 (n) | ts_0 | f_1 | ts_1 | ... | '>' | duration] (left-padded) ++ video_prompt_end ++ query+task;
     interleave_data=False (:784-822): video_prompt (the timestamps as text) ++ all frame tokens ++ video_prompt_end ++ query+task."""
     emb = sd[prefix + "shared.weight"]
     dev = emb.device
     timestamps, durations = torch.as_tensor(timestamps).cpu(), torch.as_tensor(durations).cpu()
+    if "no_task_prompt" in task:                              # blip2_mr.py:651-654: the query alone
+        task_prompt = [""] * len(query_prompt)
     if not interleave_data:
         video_prompt = _ht.video_prompt(input_time_format, timestamps, durations, table or {})
         kw = dict(padding="longest", truncation=True, max_length=max_txt_len, return_tensors="pt")
@@ -122,7 +124,7 @@ def prompt_concatenation(sd, d, tok, timestamps, durations, frames_for_t5, video
 
 
 def forward_mr(sd, d, tok, samples, frame_token_aggregation=None, table=None, max_txt_len=200,
-               input_time_format="seconds_integers", drop=None, interleave_data=True, amp=False):
+               input_time_format="seconds_integers", drop=None, interleave_data=True, amp=False, task="qformer_freeze_lora"):
     """blip2_mr.py:433-570 -> dict(loss, logits, inputs_embeds, attention_mask, labels, ...).  drop: None = eval mode, a
     Dropper (oracle/dropout.py) = the train-mode dropout of the Q-Former, T5 and LoRA inputs (the ViT stays in eval mode:
     blip2_mr.py:136-137).  amp=True: the reference's autocast regime on a GPU (fp16 frame encoder, bf16 T5: blip2_mr.py:446,512)
@@ -133,7 +135,7 @@ def forward_mr(sd, d, tok, samples, frame_token_aggregation=None, table=None, ma
         inputs, atts = prompt_concatenation(sd, d, tok, samples["timestamps"], samples["duration"], f,
                                             samples["video_prompt_end"], samples["query_prompt"],
                                             samples["task_prompt"], n, table, max_txt_len, input_time_format=input_time_format,
-                                            interleave_data=interleave_data)
+                                            interleave_data=interleave_data, task=task)
         ans_ids, ans_m = _on(inputs.device, tok(samples["relevant_windows"], padding="longest", truncation=True,
                                                 max_length=max_txt_len, return_tensors="pt"))
         labels = ans_ids.masked_fill(ans_ids == tok.pad_token_id, -100)

@@ -1611,3 +1611,33 @@ def test_splitk_reduce_kernel_source_runs_on_host_shim(tmp_path):
     o16 = torch.zeros((M, N), dtype=torch.bfloat16)
     assert lib.run(P(ws), splits, ctypes.c_longlong(M * N), M, N, None, 0, None, ctypes.c_longlong(0), P(o16), 1, ctypes.c_longlong(N), 40) == 0
     assert torch.equal(o16, total.to(torch.bfloat16))
+
+
+def test_no_task_prompt_variant_matches_oracle(tiny_sd):
+    """task '..._no_task_prompt' (blip2_mr.py:651-654: the text prompt is the query alone): the product's row table against the
+    oracle's prompt_concatenation, and the unsupported trainable-ViT / trainable-Q-Former settings refuse to run."""
+    from mr_blip_b200.blip2_mr import BLIP2_MR
+    from oracle import blip2_mr as ob, synth
+    m = BLIP2_MR(dims=TINY, state_dict=tiny_sd, task="qformer_freeze_lora_no_task_prompt")
+    s = synth.make_samples(batch=2, frames=3, seed=6)
+    n = TINY.num_query
+    table, atts, _ = m.build_prompt_table(s["timestamps"], s["duration"], 2, 3, n, s["video_prompt_end"], s["query_prompt"], s["task_prompt"])
+    frames = torch.randn(2, 3 * n, TINY.d_model)
+    inputs, oatts = ob.prompt_concatenation(tiny_sd, TINY, m.t5_tokenizer, s["timestamps"], s["duration"], frames, s["video_prompt_end"],
+                                            s["query_prompt"], s["task_prompt"], n, m.annoying_numbers_replacement_dict,
+                                            task="qformer_freeze_lora_no_task_prompt")
+    assert table.shape[1] == inputs.shape[1] and torch.equal(atts, oatts)
+    emb = tiny_sd[T5_PREFIX + "shared.weight"]
+    for b in range(2):
+        for j in range(table.shape[1]):
+            v = int(table[b, j])
+            want = emb[v] if v >= 0 else (torch.zeros(TINY.d_model) if v == -2 ** 31 else frames.reshape(-1, TINY.d_model)[-v - 1])
+            assert torch.equal(inputs[b, j], want), (b, j, v)
+    full, _, _ = BLIP2_MR(dims=TINY, state_dict=tiny_sd).build_prompt_table(s["timestamps"], s["duration"], 2, 3, n, s["video_prompt_end"],
+                                                                          s["query_prompt"], s["task_prompt"])
+    assert full.shape[1] > table.shape[1]                    # the task prompt is gone
+    with pytest.raises(NotImplementedError):
+        BLIP2_MR(dims=TINY, state_dict=tiny_sd, freeze_vit=False)
+    with pytest.raises(NotImplementedError):
+        BLIP2_MR(dims=TINY, state_dict=tiny_sd, task="lora")
+    assert BLIP2_MR(dims=TINY, state_dict=tiny_sd, use_grad_checkpoint=True).use_grad_checkpoint
