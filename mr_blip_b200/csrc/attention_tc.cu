@@ -267,32 +267,41 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   mrb::pdl_wait();      // set-up done; nothing above touches global memory (MRB_PDL, common.cuh)
 
   if (warp == 0) {
-    // ===================== TMA producer =====================
-    if (lane == 0) {
+    // ===================== TMA producer (converged warp, one elected lane issues: elect_one, common.cuh) =====================
+    if (elect_one()) {
       mbar_expect_tx(q_full, n_groups * S::Q_ONE);
       for (int g = 0; g < n_groups; ++g) {
         tma_load_4d(smem + S::OFF_Q + g * S::Q_ONE, &tmQ, q_full, 0, h, q0 + g * TQ, b);
         if (SPLIT) tma_load_4d(smem + S::OFF_Q + g * S::Q_ONE + TQ * 128, &tmQ2, q_full, 64, h, q0 + g * TQ, b);
       }
-      if (G == 1) {
-        // one K and one V buffer, each with its own full / empty barrier pair ([0] = K, [1] = V): K_{j+1} streams in as
-        // soon as S_j = Q K_j^T has retired (i.e. during softmax j), V_{j+1} as soon as O += P_j V_j has retired
-        uint8_t* sk = smem + S::OFF_KV;
-        uint8_t* sv = sk + S::KV_ONE;
-        for (int j = 0; j < n_kv; ++j) {
-          mbar_wait(&kv_empty[0], (j & 1) ^ 1);
+    }
+    __syncwarp();
+    if (G == 1) {
+      // one K and one V buffer, each with its own full / empty barrier pair ([0] = K, [1] = V): K_{j+1} streams in as
+      // soon as S_j = Q K_j^T has retired (i.e. during softmax j), V_{j+1} as soon as O += P_j V_j has retired
+      uint8_t* sk = smem + S::OFF_KV;
+      uint8_t* sv = sk + S::KV_ONE;
+      for (int j = 0; j < n_kv; ++j) {
+        mbar_wait(&kv_empty[0], (j & 1) ^ 1);
+        if (elect_one()) {
           mbar_expect_tx(&kv_full[0], S::KV_ONE);
           tma_load_4d(sk, &tmK, &kv_full[0], 0, h, j * TKV, bkv);
           if (SPLIT) tma_load_4d(sk + TKV * 128, &tmK2, &kv_full[0], 64, h, j * TKV, bkv);
-          mbar_wait(&kv_empty[1], (j & 1) ^ 1);
+        }
+        __syncwarp();
+        mbar_wait(&kv_empty[1], (j & 1) ^ 1);
+        if (elect_one()) {
           mbar_expect_tx(&kv_full[1], S::KV_ONE);
           tma_load_4d(sv, &tmV, &kv_full[1], 0, h, j * TKV, bkv);
           if (SPLIT) tma_load_4d(sv + TKV * 128, &tmV2, &kv_full[1], 64, h, j * TKV, bkv);
         }
+        __syncwarp();
       }
-      for (int j = 0; G == 2 && j < n_kv; ++j) {
-        const int st = j % STAGES;
-        mbar_wait(&kv_empty[st], ((j / STAGES) & 1) ^ 1);
+    }
+    for (int j = 0; G == 2 && j < n_kv; ++j) {
+      const int st = j % STAGES;
+      mbar_wait(&kv_empty[st], ((j / STAGES) & 1) ^ 1);
+      if (elect_one()) {
         uint8_t* sk = smem + S::OFF_KV + st * S::STAGE_BYTES;
         uint8_t* sv = sk + S::KV_ONE;
         mbar_expect_tx(&kv_full[st], S::STAGE_BYTES);
@@ -303,47 +312,60 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
           tma_load_4d(sv + TKV * 128, &tmV2, &kv_full[st], 64, h, j * TKV, bkv);
         }
       }
+      __syncwarp();
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
+    // Converged warp, one elected lane issues; descriptors = kernel-lifetime bases + small offsets in the 14-bit address field
+    // (16-byte units): K-major SWIZZLE_128B tiles step 2 per 16-element K step, the MN-major V tile steps 128 (SW128 atom,
+    // 16 keys = 2048 B) or 64 (SW64 atom, 1024 B).  `if (lane == 0)` + descriptors rebuilt from addresses cost ~20 dependent
+    // uniform-datapath instructions and an ELECT / BRA.U.ANY loop per tcgen05.mma (profiles/ncu_attn_issue_r02d.md).
     const int fmt = p.dtype == MRB_DT_BF16 ? 1 : 0;
+    const uint32_t sb = smem_u32(smem);
+    const uint64_t dk128 = umma_desc(sb, 16, 1024, LAYOUT_SW128);             // K-major, 64-wide atom
+    const uint64_t dk64 = umma_desc(sb, 16, 512, LAYOUT_SW64);                // K-major, 32-wide atom (d 64..95)
+    const uint64_t dv128 = umma_desc(sb, TKV * 128, 1024, LAYOUT_SW128);      // V [key][d] read MN-major
+    const uint64_t dv64 = umma_desc(sb, TKV * 64, 512, LAYOUT_SW64);
+    const uint32_t id64 = idesc_f16(fmt, TQ, 64, 0, 1);
+    const uint32_t id32 = idesc_f16(fmt, TQ, 32, 0, 1);
     auto tail_n = [&](int j) {   // keys in KV tile j, rounded up to the UMMA N granularity (16)
       const int rem = p.Lk - j * TKV;
       return rem >= TKV ? TKV : ((rem + 15) & ~15);
     };
     auto issue_qk = [&](int g, int j) {
       const int st = j % STAGES;
-      const uint32_t q_addr = smem_u32(smem + S::OFF_Q + g * S::Q_ONE);
-      const uint32_t k_addr = smem_u32(smem + S::OFF_KV + st * S::STAGE_BYTES);
+      const uint32_t qo = static_cast<uint32_t>((S::OFF_Q + g * S::Q_ONE) >> 4), ko = static_cast<uint32_t>((S::OFF_KV + st * S::STAGE_BYTES) >> 4);
+      const uint64_t qd = dk128 + qo, kd = dk128 + ko;
       const uint32_t d_s = tmem_base + S_COL + g * TKV;
       const uint32_t ids = idesc_f16(fmt, TQ, tail_n(j), 0, 0);
 #pragma unroll
-      for (int k = 0; k < 4; ++k)
-        umma_f16(d_s, umma_desc(q_addr + k * 32, 16, 1024, LAYOUT_SW128), umma_desc(k_addr + k * 32, 16, 1024, LAYOUT_SW128),
-                 ids, k > 0 ? 1u : 0u);
+      for (int k = 0; k < 4; ++k) umma_f16(d_s, qd + 2 * k, kd + 2 * k, ids, k > 0 ? 1u : 0u);
       if (SPLIT) {
+        const uint64_t qd2 = dk64 + (qo + ((TQ * 128) >> 4)), kd2 = dk64 + (ko + ((TKV * 128) >> 4));
 #pragma unroll
-        for (int k = 0; k < 2; ++k)
-          umma_f16(d_s, umma_desc(q_addr + TQ * 128 + k * 32, 16, 512, LAYOUT_SW64),
-                   umma_desc(k_addr + TKV * 128 + k * 32, 16, 512, LAYOUT_SW64), ids, 1u);
+        for (int k = 0; k < 2; ++k) umma_f16(d_s, qd2 + 2 * k, kd2 + 2 * k, ids, 1u);
       }
       umma_commit(&s_full[g]);
     };
     auto issue_pv = [&](int g, int j) {
       const int st = j % STAGES;
-      const uint32_t p_addr = smem_u32(smem + S::OFF_P + g * S::P_BYTES);
-      const uint32_t v_addr = smem_u32(smem + S::OFF_KV + st * S::STAGE_BYTES + S::KV_ONE);
+      const uint32_t po = static_cast<uint32_t>((S::OFF_P + g * S::P_BYTES) >> 4);
+      const uint32_t vo = static_cast<uint32_t>((S::OFF_KV + st * S::STAGE_BYTES + S::KV_ONE) >> 4);
+      const uint64_t pd = dk128 + po, vd = dv128 + vo, vd2 = dv64 + (vo + ((TKV * 128) >> 4));
       const uint32_t d_o = tmem_base + O_COL + g * HD;
       const int ksteps = tail_n(j) / 16;
-      const uint32_t id64 = idesc_f16(fmt, TQ, 64, 0, 1);
-      const uint32_t id32 = idesc_f16(fmt, TQ, 32, 0, 1);
-      for (int k = 0; k < ksteps; ++k) {
-        // A = P (K-major, SW128): 64-key atom (k/4), 32-byte step inside the atom
-        const uint64_t a = umma_desc(p_addr + (k >> 2) * (TQ * 128) + (k & 3) * 32, 16, 1024, LAYOUT_SW128);
-        // B = V [key][d] read MN-major: 16 keys = two 8-key groups of 1024 B (SW128) / 512 B (SW64)
-        umma_f16(d_o, a, umma_desc(v_addr + k * 2048, TKV * 128, 1024, LAYOUT_SW128), id64, (k > 0 || j > 0) ? 1u : 0u);
-        if (SPLIT)
-          umma_f16(d_o + 64, a, umma_desc(v_addr + TKV * 128 + k * 1024, TKV * 64, 512, LAYOUT_SW64), id32, (k > 0 || j > 0) ? 1u : 0u);
+      const uint32_t acc0 = j > 0 ? 1u : 0u;
+      auto step = [&](int k) {
+        // A = P (K-major, SW128): 64-key atom (k / 4) is TQ * 128 B further, 32-byte step inside the atom
+        const uint64_t a = pd + static_cast<uint32_t>((k >> 2) * ((TQ * 128) >> 4) + (k & 3) * 2);
+        umma_f16(d_o, a, vd + static_cast<uint32_t>(k * 128), id64, k > 0 ? 1u : acc0);
+        if (SPLIT) umma_f16(d_o + 64, a, vd2 + static_cast<uint32_t>(k * 64), id32, k > 0 ? 1u : acc0);
+      };
+      if (ksteps == TKV / 16) {
+#pragma unroll
+        for (int k = 0; k < TKV / 16; ++k) step(k);
+      } else {
+        for (int k = 0; k < ksteps; ++k) step(k);
       }
       umma_commit(&o_full[g]);
     };
@@ -351,23 +373,23 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     mbar_wait(&kv_full[0], 0);
     tc_fence_after();
     if (G == 1) {
-      if (lane == 0) { issue_qk(0, 0); umma_commit(&kv_empty[0]); }     // K_0 is free once S_0 has retired
+      if (elect_one()) { issue_qk(0, 0); umma_commit(&kv_empty[0]); }     // K_0 is free once S_0 has retired
       __syncwarp();
       for (int j = 0; j < n_kv; ++j) {
         mbar_wait(&p_full[0], j & 1);                                   // P_j written, S_j consumed
         mbar_wait(&kv_full[1], j & 1);                                  // V_j landed
         tc_fence_after();
-        if (lane == 0) { issue_pv(0, j); umma_commit(&kv_empty[1]); }
+        if (elect_one()) { issue_pv(0, j); umma_commit(&kv_empty[1]); }
         __syncwarp();
         if (j + 1 < n_kv) {
           mbar_wait(&kv_full[0], (j + 1) & 1);                          // K_{j+1} landed
           tc_fence_after();
-          if (lane == 0) { issue_qk(0, j + 1); umma_commit(&kv_empty[0]); }
+          if (elect_one()) { issue_qk(0, j + 1); umma_commit(&kv_empty[0]); }
           __syncwarp();
         }
       }
     } else {
-    if (lane == 0)
+    if (elect_one())
       for (int g = 0; g < n_groups; ++g) issue_qk(g, 0);
     __syncwarp();
     for (int j = 0; j < n_kv; ++j) {
@@ -375,7 +397,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         mbar_wait(&p_full[g], j & 1);
         if (g == 0 && j + 1 < n_kv) mbar_wait(&kv_full[(j + 1) % STAGES], ((j + 1) / STAGES) & 1);
         tc_fence_after();
-        if (lane == 0) {
+        if (elect_one()) {
           issue_pv(g, j);
           if (g == n_groups - 1) umma_commit(&kv_empty[j % STAGES]);   // K_j / V_j fully consumed
           if (j + 1 < n_kv) issue_qk(g, j + 1);

@@ -234,83 +234,88 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
   mrb::pdl_wait();      // set-up done; nothing above touches global memory (MRB_PDL, common.cuh)
 
   if (warp == 0) {
-    // ===================== TMA producer =====================
-    if (lane == 0) {
+    // ===================== TMA producer (converged warp, one elected lane issues) =====================
+    if (elect_one()) {
       mbar_expect_tx(x_full, n_groups * 2 * S::X_BYTES);
       for (int g = 0; g < n_groups; ++g) {
         tma_load_4d_b(smem + S::OFF_X + (2 * g) * S::X_BYTES, &tmX, x_full, 0, h, x0 + g * TS, b);
         tma_load_4d_b(smem + S::OFF_X + (2 * g + 1) * S::X_BYTES, &tmY, x_full, 0, h, x0 + g * TS, b);
       }
-      for (int t = 0; t < n_t; ++t) {
-        const int st = t % STAGES;
-        mbar_wait(&st_empty[st], ((t / STAGES) & 1) ^ 1);
+    }
+    __syncwarp();
+    int st = 0;
+    uint32_t ph = 0;
+    for (int t = 0; t < n_t; ++t) {
+      mbar_wait(&st_empty[st], ph ^ 1);
+      if (elect_one()) {
         uint8_t* su = smem + S::OFF_U + st * 2 * S::U_BYTES;
         mbar_expect_tx(&st_full[st], 2 * S::U_BYTES);
         tma_load_4d_b(su, &tmU, &st_full[st], 0, h, (t_begin + t) * TT, b);
         tma_load_4d_b(su + S::U_BYTES, &tmW, &st_full[st], 0, h, (t_begin + t) * TT, b);
       }
+      __syncwarp();
+      if (++st == STAGES) { st = 0; ph ^= 1; }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
+    // The whole warp runs this code converged and ONE elected lane issues (elect_one, common.cuh); every descriptor is a
+    // kernel-lifetime base plus a small offset (the 14-bit address field counts 16-byte units: + 2 per 16-element K step of a
+    // K-major tile, + 128 per 16-row step of an MN-major one).  With `if (lane == 0)` and descriptors rebuilt from addresses each
+    // tcgen05.mma cost ~20 dependent uniform-datapath instructions plus an ELECT / BRA.U.ANY loop -- ~150 clk per instruction that
+    // keeps the tensor pipe busy for 32 clk: the issuing warp, not ex2 or tensor memory, was what bounded the kernel
+    // (profiles/ncu_attn_issue_r02d.md).
     const int fmt = p.dtype == MRB_DT_BF16 ? 1 : 0;
     const uint32_t id_t = idesc_b(fmt, TS, TT, 0);          // 128 x 64, both operands K-major (contraction over d)
     const uint32_t id_a = idesc_b(fmt, TS, BHD, 1);         // 128 x 64(d), B MN-major (contraction over streamed rows)
-    auto issue_T = [&](int g, int t) {
-      const int st = t % STAGES;
-      const uint32_t x_addr = smem_u32(smem + S::OFF_X + (2 * g) * S::X_BYTES);
-      const uint32_t y_addr = x_addr + S::X_BYTES;
-      const uint32_t u_addr = smem_u32(smem + S::OFF_U + st * 2 * S::U_BYTES);
-      const uint32_t w_addr = u_addr + S::U_BYTES;
+    const uint64_t dk0 = udesc(smem_u32(smem), 16, 1024);         // K-major SWIZZLE_128B tile at the start of shared memory
+    const uint64_t dm0 = udesc(smem_u32(smem), TT * 128, 1024);   // MN-major view of a streamed [row][d] tile
+    auto issue_T = [&](int g, int st) {
+      const uint64_t xd = dk0 + static_cast<uint32_t>((S::OFF_X + (2 * g) * S::X_BYTES) >> 4), yd = xd + (S::X_BYTES >> 4);
+      const uint64_t ud = dk0 + static_cast<uint32_t>((S::OFF_U + st * 2 * S::U_BYTES) >> 4), wd = ud + (S::U_BYTES >> 4);
       const uint32_t d1 = tmem_base + g * 256, d2 = d1 + 64;
 #pragma unroll
-      for (int k = 0; k < 4; ++k)
-        umma_f16(d1, udesc(x_addr + k * 32, 16, 1024), udesc(u_addr + k * 32, 16, 1024), id_t, k > 0 ? 1u : 0u);
+      for (int k = 0; k < 4; ++k) umma_f16(d1, xd + 2 * k, ud + 2 * k, id_t, k > 0 ? 1u : 0u);
 #pragma unroll
-      for (int k = 0; k < 4; ++k)
-        umma_f16(d2, udesc(y_addr + k * 32, 16, 1024), udesc(w_addr + k * 32, 16, 1024), id_t, k > 0 ? 1u : 0u);
+      for (int k = 0; k < 4; ++k) umma_f16(d2, yd + 2 * k, wd + 2 * k, id_t, k > 0 ? 1u : 0u);
       umma_commit(&t_full[g]);
     };
-    auto issue_acc = [&](int g, int t) {
-      const int st = t % STAGES;
-      const uint32_t e_addr = smem_u32(smem + S::OFF_E + (2 * g) * S::X_BYTES);      // P tile, then dS tile
-      const uint32_t u_addr = smem_u32(smem + S::OFF_U + st * 2 * S::U_BYTES);
-      const uint32_t w_addr = u_addr + S::U_BYTES;
+    auto issue_acc = [&](int g, int st, uint32_t acc) {
+      const uint64_t pd = dk0 + static_cast<uint32_t>((S::OFF_E + (2 * g) * S::X_BYTES) >> 4), sd = pd + (S::X_BYTES >> 4);   // P, dS
+      const uint64_t um = dm0 + static_cast<uint32_t>((S::OFF_U + st * 2 * S::U_BYTES) >> 4), wm = um + (S::U_BYTES >> 4);
       const uint32_t a1 = tmem_base + g * 256 + 128, a2 = a1 + 64;
-      const uint32_t acc = t > 0 ? 1u : 0u;
       if (MODE == MODE_DKV) {
 #pragma unroll
-        for (int k = 0; k < 4; ++k)      // dV += P^T dO_t
-          umma_f16(a1, udesc(e_addr + k * 32, 16, 1024), udesc(w_addr + k * 2048, TT * 128, 1024), id_a, (k > 0) ? 1u : acc);
+        for (int k = 0; k < 4; ++k) umma_f16(a1, pd + 2 * k, wm + 128 * k, id_a, (k > 0) ? 1u : acc);      // dV += P^T dO_t
 #pragma unroll
-        for (int k = 0; k < 4; ++k)      // dK += dS^T Q_t
-          umma_f16(a2, udesc(e_addr + S::X_BYTES + k * 32, 16, 1024), udesc(u_addr + k * 2048, TT * 128, 1024), id_a,
-                   (k > 0) ? 1u : acc);
+        for (int k = 0; k < 4; ++k) umma_f16(a2, sd + 2 * k, um + 128 * k, id_a, (k > 0) ? 1u : acc);      // dK += dS^T Q_t
       } else {
 #pragma unroll
-        for (int k = 0; k < 4; ++k)      // dQ += dS K_t
-          umma_f16(a1, udesc(e_addr + S::X_BYTES + k * 32, 16, 1024), udesc(u_addr + k * 2048, TT * 128, 1024), id_a,
-                   (k > 0) ? 1u : acc);
+        for (int k = 0; k < 4; ++k) umma_f16(a1, sd + 2 * k, um + 128 * k, id_a, (k > 0) ? 1u : acc);      // dQ += dS K_t
       }
     };
     mbar_wait(x_full, 0);
     mbar_wait(&st_full[0], 0);
     tc_fence_after();
-    if (lane == 0)
+    if (elect_one())
       for (int g = 0; g < n_groups; ++g) issue_T(g, 0);
     __syncwarp();
+    int st = 0, st_next = (STAGES > 1) ? 1 : 0;              // t % STAGES, (t + 1) % STAGES
+    uint32_t ph_next = 0;                                    // ((t + 1) / STAGES) & 1
     for (int t = 0; t < n_t; ++t) {
       for (int g = 0; g < n_groups; ++g) {
         mbar_wait(&e_full[g], t & 1);
-        if (g == 0 && t + 1 < n_t) mbar_wait(&st_full[(t + 1) % STAGES], ((t + 1) / STAGES) & 1);
+        if (g == 0 && t + 1 < n_t) mbar_wait(&st_full[st_next], ph_next);
         tc_fence_after();
-        if (lane == 0) {
-          issue_acc(g, t);
-          if (g == n_groups - 1) umma_commit(&st_empty[t % STAGES]);
-          if (t + 1 < n_t) issue_T(g, t + 1);
+        if (elect_one()) {
+          issue_acc(g, st, t > 0 ? 1u : 0u);
+          if (g == n_groups - 1) umma_commit(&st_empty[st]);
+          if (t + 1 < n_t) issue_T(g, st_next);
           else umma_commit(&acc_full[g]);
         }
         __syncwarp();
       }
+      st = st_next;
+      if (++st_next == STAGES) { st_next = 0; ph_next ^= 1; }
     }
   } else {
     // ===================== elementwise groups: one thread per stationary row =====================

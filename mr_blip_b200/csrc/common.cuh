@@ -67,6 +67,14 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     }
   }
 }
+// True in exactly one lane of the converged warp (elect.sync).  Single-thread tcgen05 / TMA issue goes under `if (elect_one())`
+// inside a loop the WHOLE warp runs: the compiler then knows that one thread is active and that the operands are warp-uniform;
+// `if (lane == 0)` made it wrap every tcgen05.mma in an ELECT / R2UR.BROADCAST / BRA.U.ANY loop (profiles/ncu_gemm2_issue_r02d.md).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void fence_barrier_init() {
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 }

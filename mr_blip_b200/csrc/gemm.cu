@@ -111,27 +111,30 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   mrb::pdl_wait();      // set-up done; nothing above touches global memory (MRB_PDL, common.cuh)
 
   if (warp == 0) {
-    // ===================== TMA producer =====================
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-        int tm, tn, tile, split, kb0, kb1;
-        split_coords<SPLIT>(p, k_blocks, t, tile, split, kb0, kb1);
-        tile_coords(tile, p.m_tiles, p.n_tiles, tm, tn);
-        for (int kb = kb0; kb < kb1; ++kb) {
-          mbar_wait(&empty_bar[stage], phase ^ 1);
-          uint8_t* sa = smem + stage * S::STAGE_BYTES;
+    // ===================== TMA producer: converged warp, one elected lane issues (see gemm2.cu) =====================
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+      int tm, tn, tile, split, kb0, kb1;
+      split_coords<SPLIT>(p, k_blocks, t, tile, split, kb0, kb1);
+      tile_coords(tile, p.m_tiles, p.n_tiles, tm, tn);
+      for (int kb = kb0; kb < kb1; ++kb) {
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        uint8_t* sa = smem + stage * S::STAGE_BYTES;
+        if (elect_one()) {
           mbar_expect_tx(&full_bar[stage], S::STAGE_BYTES);
           tma_load_2d(sa, &tmA, &full_bar[stage], kb * BK, tm * BM);
           tma_load_2d(sa + S::A_BYTES, &tmB, &full_bar[stage], kb * BK, tn * BN);
-          if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
+        __syncwarp();
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer =====================
+    // ===================== MMA issuer: converged warp, uniform descriptors, one elected lane issues =====================
     const uint32_t idesc = umma_idesc_f16(p.dtype == MRB_DT_BF16 ? 1 : 0, BM, BN);
+    const uint64_t a_desc0 = umma_desc_sw128(smem_u32(smem));
+    const uint64_t b_desc0 = umma_desc_sw128(smem_u32(smem) + S::A_BYTES);
     int stage = 0;
     uint32_t phase = 0;
     int it = 0;
@@ -146,14 +149,12 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       for (int kb = kb0; kb < kb1; ++kb) {
         mbar_wait(&full_bar[stage], phase);
         tc_fence_after();
-        if (lane == 0) {
-          const uint32_t a_addr = smem_u32(smem + stage * S::STAGE_BYTES);
-          const uint32_t b_addr = a_addr + S::A_BYTES;
+        const uint64_t a_desc = a_desc0 + static_cast<uint32_t>(stage * (S::STAGE_BYTES >> 4));
+        const uint64_t b_desc = b_desc0 + static_cast<uint32_t>(stage * (S::STAGE_BYTES >> 4));
+        if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < BK / 16; ++k) {
-            umma_f16(d_tmem, umma_desc_sw128(a_addr + k * 32), umma_desc_sw128(b_addr + k * 32), idesc,
-                     (kb > kb0 || k > 0) ? 1u : 0u);
-          }
+          for (int k = 0; k < BK / 16; ++k)
+            umma_f16(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
           umma_commit(&empty_bar[stage]);                    // frees the smem slot when the MMAs retire
           if (kb == kb1 - 1) umma_commit(&tmem_full[as]);      // accumulator complete -> epilogue
         }

@@ -23,7 +23,13 @@ struct Gemm2Params {
   int tail;                 // 1: the last column tile runs a narrower MMA (MRB_GEMM2_TAIL=0 disables, for A/B runs)
 };
 
-constexpr int G2_BM = 128, G2_BN = 256, G2_BK = 64, G2_STAGES = 6, G2_GROUP_M = 8;
+// Diagnostic builds (python -m mr_blip_b200.build --variant _x -DMRB_G2_...; never the default library): MRB_G2_STAGES=n ring depth,
+// MRB_G2_NOEPI the epilogue warps release the accumulator without reading it (main loop alone), MRB_G2_NOTMA the producer
+// signals "full" without loading anything (MMA issue rate alone, operands are whatever shared memory holds).
+#ifndef MRB_G2_STAGES
+#define MRB_G2_STAGES 6
+#endif
+constexpr int G2_BM = 128, G2_BN = 256, G2_BK = 64, G2_STAGES = MRB_G2_STAGES, G2_GROUP_M = 8;
 constexpr int G2_A_BYTES = G2_BM * G2_BK * 2;            // 16 KB: this CTA's 128 rows
 constexpr int G2_B_BYTES = (G2_BN / 2) * G2_BK * 2;      // 16 KB: this CTA's half of the B tile
 constexpr int G2_STAGE = G2_A_BYTES + G2_B_BYTES;
@@ -108,6 +114,12 @@ __device__ __forceinline__ void tile_coords2(int t, int m_tiles, int n_tiles, in
   tn = r / gm;
 }
 
+__device__ __forceinline__ int tile_col2(int t, int m_tiles, int n_tiles) {
+  int tm, tn;
+  tile_coords2(t, m_tiles, n_tiles, tm, tn);
+  return tn;
+}
+
 // Width of the MMA for column tile tn: 256, or the remaining columns rounded up to 64 for the last tile (N = 1408 = 5 x 256
 // + 128 in the ViT proj / fc2 GEMMs: the tail tile then costs half the tensor time).  Each CTA supplies n_mma / 2 rows of B.
 __device__ __forceinline__ int tile_n_mma(const Gemm2Params& p, int tn) {
@@ -159,52 +171,66 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
   mrb::pdl_wait();      // set-up done; nothing above touches global memory (MRB_PDL, common.cuh)
 
   if (warp == 0) {
-    // ===================== TMA producer (both CTAs) =====================
-    if (lane == 0) {
+    // ===================== TMA producer (both CTAs): converged warp, one elected lane issues =====================
+    {
       int stage = 0;
       uint32_t phase = 0;
       for (int t = pair; t < num_tiles; t += n_pairs) {
         int tm, tn;
         tile_coords2(t, p.m_tiles, p.n_tiles, tm, tn);
+        const int a_row = tm * 256 + static_cast<int>(rank) * G2_BM;
         const int b_row = tn * G2_BN + static_cast<int>(rank) * (tile_n_mma(p, tn) / 2);   // this CTA's half of the (tail) tile
         for (int kb = 0; kb < k_blocks; ++kb) {
-          mbar_wait_cluster(&empty_bar[stage], phase ^ 1, p.sem_cluster);
+          mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * G2_STAGE;
-          const uint32_t lbar = map_to_cta(smem_u32(&full_bar[stage]), 0);
-          if (leader) mbar_expect_tx(&full_bar[stage], 2 * G2_STAGE);
-          tma2_load_2d(sa, &tmA, lbar, kb * G2_BK, tm * 256 + static_cast<int>(rank) * G2_BM);
-          tma2_load_2d(sa + G2_A_BYTES, &tmB, lbar, kb * G2_BK, b_row);
+          if (elect_one()) {
+#ifdef MRB_G2_NOTMA
+            (void)sa; (void)a_row; (void)b_row;
+            if (leader) mbar_arrive(&full_bar[stage]);
+#else
+            const uint32_t lbar = map_to_cta(smem_u32(&full_bar[stage]), 0);
+            if (leader) mbar_expect_tx(&full_bar[stage], 2 * G2_STAGE);
+            tma2_load_2d(sa, &tmA, lbar, kb * G2_BK, a_row);
+            tma2_load_2d(sa + G2_A_BYTES, &tmB, lbar, kb * G2_BK, b_row);
+#endif
+          }
+          __syncwarp();
           if (++stage == G2_STAGES) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer (leader CTA only) =====================
+    // The whole warp runs the loop converged (every quantity below is warp-uniform, so it lives in uniform registers) and ONE
+    // elected lane issues: with `if (lane == 0)` the compiler had to move every tcgen05.mma operand through an
+    // ELECT / R2UR.BROADCAST loop -- ~200 instructions, ~700 clk per 64-wide K block against 512 clk of tensor work
+    // (profiles/ncu_gemm2_issue_r02d.md): the issue loop, not the operand feed, was what held the tensor pipe at 58-70 %.
     if (leader) {
-      const uint32_t idesc_full = umma_idesc_f16(p.dtype == MRB_DT_BF16 ? 1 : 0, 256, G2_BN);
+      const int fmt = p.dtype == MRB_DT_BF16 ? 1 : 0;
+      const uint32_t idesc_full = umma_idesc_f16(fmt, 256, G2_BN);
+      const uint64_t a_desc0 = umma_desc_sw128(smem_u32(smem));               // stage 0, k step 0; stage s adds s * G2_STAGE / 16,
+      const uint64_t b_desc0 = umma_desc_sw128(smem_u32(smem) + G2_A_BYTES);  // k step k adds 2 k to the (14-bit) address field
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
       for (int t = pair; t < num_tiles; t += n_pairs, ++it) {
-        int tm, tn;
-        tile_coords2(t, p.m_tiles, p.n_tiles, tm, tn);
+        const int tn = tile_col2(t, p.m_tiles, p.n_tiles);
         const int n_mma = tile_n_mma(p, tn);
-        const uint32_t idesc = n_mma == G2_BN ? idesc_full : umma_idesc_f16(p.dtype == MRB_DT_BF16 ? 1 : 0, 256, n_mma);
+        const uint32_t idesc = n_mma == G2_BN ? idesc_full : umma_idesc_f16(fmt, 256, n_mma);
         const int as = it & 1;
         const uint32_t aphase = (it >> 1) & 1;
-        mbar_wait_cluster(&tmem_empty[as], aphase ^ 1, p.sem_cluster);
+        mbar_wait(&tmem_empty[as], aphase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + as * G2_BN;
         for (int kb = 0; kb < k_blocks; ++kb) {
-          mbar_wait_cluster(&full_bar[stage], phase, p.sem_cluster);
+          mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
-          if (lane == 0) {
-            const uint32_t a_addr = smem_u32(smem + stage * G2_STAGE);
-            const uint32_t b_addr = a_addr + G2_A_BYTES;
+          const uint64_t a_desc = a_desc0 + static_cast<uint32_t>(stage * (G2_STAGE >> 4));
+          const uint64_t b_desc = b_desc0 + static_cast<uint32_t>(stage * (G2_STAGE >> 4));
+          if (elect_one()) {
 #pragma unroll
             for (int k = 0; k < G2_BK / 16; ++k)
-              umma2_f16(d_tmem, umma_desc_sw128(a_addr + k * 32), umma_desc_sw128(b_addr + k * 32), idesc,
-                        (kb > 0 || k > 0) ? 1u : 0u);
+              umma2_f16(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
             umma2_commit_mc(&empty_bar[stage]);
             if (kb == k_blocks - 1) umma2_commit_mc(&tmem_full[as]);
           }
@@ -232,6 +258,13 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
       const int m_base = tm * 256 + static_cast<int>(rank) * G2_BM + quad * 32;
       mbar_wait_cluster(&tmem_full[as], aphase, p.sem_cluster);
       tc_fence_after();
+#ifdef MRB_G2_NOEPI
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_remote(as ? empty_remote1 : empty_remote0, p.sem_cluster);
+      (void)half; (void)c_begin; (void)c_end; (void)m_base; (void)stage4; (void)sub_row; (void)chunk;
+      continue;
+#endif
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + as * G2_BN;
       // One 32 x 32 fp32 chunk: TMEM registers (row per thread) -> XOR-swizzled staging -> 4 rows x 128 B per warp instruction
       // (coalesced residual reads / output writes), bias + GELU + residual in between.

@@ -61,39 +61,38 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constant__
   const uint32_t tmem_base = *tmem_holder;
   mrb::pdl_wait();      // set-up done; nothing above touches global memory (MRB_PDL, common.cuh)
 
-  if (warp == 0) {
-    if (lane == 0) {
-      int stage = 0; uint32_t phase = 0;
-      for (int kb = 0; kb < k_blocks; ++kb) {
-        mbar_wait(&empty_bar[stage], phase ^ 1);
+  if (warp == 0) {       // TMA producer: converged warp, one elected lane issues (elect_one, common.cuh)
+    int stage = 0; uint32_t phase = 0;
+    for (int kb = 0; kb < k_blocks; ++kb) {
+      mbar_wait(&empty_bar[stage], phase ^ 1);
+      if (elect_one()) {
         uint8_t* sa = smem + stage * WG_STAGE;
         mbar_expect_tx(&full_bar[stage], WG_STAGE);
         const int m = m0 + kb * WG_BK;
         tma_load_2d(sa, &tmP, &full_bar[stage], c0, m);
         tma_load_2d(sa + WG_BK * 128, &tmP, &full_bar[stage], c0 + 64, m);
         tma_load_2d(sa + WG_A_BYTES, &tmQ, &full_bar[stage], 0, m);
-        if (++stage == WG_STAGES) { stage = 0; phase ^= 1; }
       }
+      __syncwarp();
+      if (++stage == WG_STAGES) { stage = 0; phase ^= 1; }
     }
-  } else if (warp == 1) {
+  } else if (warp == 1) {  // MMA issuer: same pattern, descriptors = bases + offsets of the 14-bit address field (16-byte units)
     const uint32_t fmt = p.dtype == MRB_DT_BF16 ? 1u : 0u;
     // fp32 accumulate, A and B both MN-major, M = 128, N = 16
     const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | (1u << 15) | (1u << 16) | ((16u >> 3) << 17) | ((128u >> 4) << 24);
+    // A: 16 rows = two 8-row groups (SBO 1024 B); the second 64-column atom sits LBO = 8192 B further
+    const uint64_t ad0 = wg_desc(smem_u32(smem), WG_BK * 128, 1024, 2);
+    // B: 16 rows x 32 B, SWIZZLE_32B: 8-row groups of 256 B
+    const uint64_t bd0 = wg_desc(smem_u32(smem) + WG_A_BYTES, WG_BK * 32, 256, 6);
     int stage = 0; uint32_t phase = 0;
     for (int kb = 0; kb < k_blocks; ++kb) {
       mbar_wait(&full_bar[stage], phase);
       tc_fence_after();
-      if (lane == 0) {
-        const uint32_t a_addr = smem_u32(smem + stage * WG_STAGE);
-        const uint32_t b_addr = a_addr + WG_A_BYTES;
+      const uint32_t so = static_cast<uint32_t>(stage * (WG_STAGE >> 4));
+      if (elect_one()) {
 #pragma unroll
-        for (int k = 0; k < WG_BK / 16; ++k) {
-          // A: 16 rows = two 8-row groups (SBO 1024 B); the second 64-column atom sits LBO = 8192 B further
-          const uint64_t ad = wg_desc(a_addr + k * 2048, WG_BK * 128, 1024, 2);
-          // B: 16 rows x 32 B, SWIZZLE_32B: 8-row groups of 256 B
-          const uint64_t bd = wg_desc(b_addr + k * 512, WG_BK * 32, 256, 6);
-          umma_f16(tmem_base, ad, bd, idesc, (kb > 0 || k > 0) ? 1u : 0u);
-        }
+        for (int k = 0; k < WG_BK / 16; ++k)
+          umma_f16(tmem_base, ad0 + (so + k * 128), bd0 + (so + k * 32), idesc, (kb > 0 || k > 0) ? 1u : 0u);
         umma_commit(&empty_bar[stage]);
         if (kb == k_blocks - 1) umma_commit(acc_bar);
       }
