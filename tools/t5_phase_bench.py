@@ -60,15 +60,13 @@ def main():
         t5.side_join()
 
     res = {}
-    pool = None
     for name, fn in (("enc_fwd", enc_fwd), ("dec_chain", dec_chain), ("enc_fwd_bwd", enc_bwd)):
         for _ in range(2):
             fn()
         torch.cuda.synchronize()
         gr = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(gr, pool=pool, capture_error_mode="thread_local"):
+        with torch.cuda.graph(gr, capture_error_mode="thread_local"):
             fn()
-        pool = gr.pool()
         for _ in range(3):
             gr.replay()
         torch.cuda.synchronize()
