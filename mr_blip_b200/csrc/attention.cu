@@ -863,6 +863,396 @@ __global__ void __launch_bounds__(128) attn_row_kernel(const T* __restrict__ q, 
   }
 }
 
+// ---------------------------------------------------------------- few query rows x thousands of keys (T5 decoder cross-attention)
+// modeling_t5.py:474-620 with key_value_states = the encoder output: the ~16 target tokens of a clip attend to its ~2000 encoder
+// positions.  The long-sequence kernels tile the QUERY rows over CTAs and walk the keys serially, so this shape ran on one CTA per
+// (clip, head) with 16 of its 128 / 256 rows in use: 49 us forward, 77 + 73 us backward per decoder layer on the step's latency-
+// bound chain.  Here the KEYS are split instead: a cluster of FQ_SPLIT CTAs per (16-row block, head, clip), every CTA streams its
+// share of the 64-key tiles through a 3-deep cp.async ring, its four warps take 16 keys of a tile each (mma.sync m16n8k16, the 16
+// query rows are the M dimension), and the partial results -- (max, sum, O) triples in the forward, dQ in the backward -- meet in
+// shared memory inside the CTA and through distributed shared memory inside the cluster, always in the same order (no atomics: run-
+// to-run reproducible).  dK / dV of this shape come from attn_bwd_dkv_kernel, which already tiles the keys over CTAs.
+#ifdef MRB_HOST_SHIM          // tests/cuda_host_shim has no clusters: one CTA takes all keys, the merge code below runs with one part
+constexpr int FQ_SPLIT = 1;
+#define MRB_FQ_CLUSTER
+__device__ __forceinline__ void fq_cluster_sync() { __syncthreads(); }      // what the cluster barrier is for ONE CTA
+__device__ __forceinline__ float fq_ld_part(const float* local, int) { return *local; }
+#else
+constexpr int FQ_SPLIT = 4;
+#define MRB_FQ_CLUSTER __cluster_dims__(FQ_SPLIT, 1, 1)
+__device__ __forceinline__ void fq_cluster_sync() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ float fq_ld_part(const float* local, int rank) {     // the same shared-memory variable in CTA `rank` of the cluster
+  uint32_t remote;
+  float v;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(smem_u32(local)), "r"(rank));
+  asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(v) : "r"(remote) : "memory");
+  return v;
+}
+#endif
+constexpr int FQ_ROWS = 16, FQ_ST = 3;
+
+// shared-memory layout of both kernels: Q (and dO) tile(s), then the K / V ring; once the key loop is over the ring is dead and holds
+// the warps' partial results [4][16][64] (+ max / sum [4][16] each) and the CTA's partial [16][64] (+ [16] + [16])
+struct FqSmem {
+  static constexpr int LDS = 64 + 8;
+  static constexpr int RING = FQ_ST * BKV * LDS;                      // elements, one of K / V
+  static constexpr int W_O = 0, W_M = 4 * FQ_ROWS * 64, W_L = W_M + 4 * FQ_ROWS, C_O = W_L + 4 * FQ_ROWS, C_M = C_O + FQ_ROWS * 64,
+                       C_L = C_M + FQ_ROWS, PART_FLOATS = C_L + FQ_ROWS;
+  static_assert(PART_FLOATS * 4 <= RING * 2, "partials must fit into the K ring");
+  static constexpr int bytes(int q_tiles) { return (q_tiles * FQ_ROWS * LDS + 2 * RING) * 2; }
+};
+
+template <typename T, bool DROP = false>
+__global__ void MRB_FQ_CLUSTER __launch_bounds__(NTHREADS) attn_fq_fwd_kernel(const typename AttnParamsOf<DROP>::type p) {
+  mrb::pdl_trigger();
+  mrb::pdl_wait();      // before the first global access (common.cuh, MRB_PDL)
+  constexpr int HD = 64, LDS = FqSmem::LDS;
+  extern __shared__ __align__(16) uint8_t smem_attn[];
+  T* sQ = reinterpret_cast<T*>(smem_attn);
+  T* sK = sQ + FQ_ROWS * LDS;
+  T* sV = sK + FqSmem::RING;
+  float* part = reinterpret_cast<float*>(sK);
+  const int split = blockIdx.x, h = blockIdx.y;
+  const int n_rb = (p.Lq + FQ_ROWS - 1) / FQ_ROWS, b = blockIdx.z / n_rb, q0 = (blockIdx.z % n_rb) * FQ_ROWS;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t4 = lane & 3;
+  const T* gq = static_cast<const T*>(p.q) + b * p.q_bs + static_cast<long long>(h) * p.hd;
+  const T* gk = static_cast<const T*>(p.k) + (b / p.kv_div) * p.k_bs + static_cast<long long>(h) * p.hd;
+  const T* gv = static_cast<const T*>(p.v) + (b / p.kv_div) * p.v_bs + static_cast<long long>(h) * p.hd;
+  ScoreCtx sc{p.scale, p.bias ? p.bias + static_cast<long long>(h) * p.bias_len : nullptr, p.bias_zero,
+              p.kmask ? p.kmask + static_cast<long long>(b / p.kv_div) * p.Lk : nullptr, p.causal, p.q_pos0, p.Lk, p.Lq};
+  const int n_kv = (p.Lk + BKV - 1) / BKV, per = (n_kv + FQ_SPLIT - 1) / FQ_SPLIT;
+  const int t0 = split * per, n_t = max(0, min(n_kv, t0 + per) - t0);
+
+  auto load_kv = [&](int i) {              // tile i of this CTA's share -> ring slot i % FQ_ST (one commit group per call, possibly empty)
+    if (i < n_t) {
+      load_tile<T, HD, BKV>(smem_u32(sK + (i % FQ_ST) * BKV * LDS), gk, p.k_rs, (t0 + i) * BKV, p.Lk, p.hd);
+      load_tile<T, HD, BKV>(smem_u32(sV + (i % FQ_ST) * BKV * LDS), gv, p.v_rs, (t0 + i) * BKV, p.Lk, p.hd);
+    }
+    cp_async_commit();
+  };
+  load_tile<T, HD, FQ_ROWS>(smem_u32(sQ), gq, p.q_rs, q0, p.Lq, p.hd);
+  load_kv(0);
+  load_kv(1);
+
+  float o_acc[HD / 8][4];
+#pragma unroll
+  for (int i = 0; i < HD / 8; ++i) o_acc[i][0] = o_acc[i][1] = o_acc[i][2] = o_acc[i][3] = 0.f;
+  float m_run[2] = {-INFINITY, -INFINITY}, l_run[2] = {0.f, 0.f};
+  uint32_t qf[HD / 16][4];
+  const float LOG2E = 1.4426950408889634f;
+  uint32_t dkey = 0, drow[2] = {0u, 0u}, dthr = 0;
+  float dscale = 1.f;
+  if constexpr (DROP) {
+    dkey = drop_key(*p.drop_seed, p.drop_site);
+    dthr = p.drop_thr; dscale = p.drop_scale;
+#pragma unroll
+    for (int r = 0; r < 2; ++r)
+      drow[r] = (static_cast<uint32_t>(b * p.H + h) * static_cast<uint32_t>(p.Lq) +
+                 static_cast<uint32_t>(min(q0 + g + 8 * r, p.Lq - 1))) * drop_groups(static_cast<uint32_t>(p.Lk));
+  }
+
+  for (int i = 0; i < n_t; ++i) {
+    load_kv(i + 2);
+    cp_async_wait<2>();
+    __syncthreads();
+    if (i == 0) {
+#pragma unroll
+      for (int kk = 0; kk < HD / 16; ++kk) ldsm_x4(qf[kk], smem_u32(sQ + (lane & 15) * LDS + kk * 16 + (lane >> 4) * 8));
+    }
+    const T* cK = sK + (i % FQ_ST) * BKV * LDS;
+    const T* cV = sV + (i % FQ_ST) * BKV * LDS;
+    // S = Q K^T for this warp's 16 keys of the tile
+    float s[2][4];
+#pragma unroll
+    for (int n = 0; n < 2; ++n) s[n][0] = s[n][1] = s[n][2] = s[n][3] = 0.f;
+#pragma unroll
+    for (int kk = 0; kk < HD / 16; ++kk) {
+      uint32_t kf[4];
+      ldsm_x4(kf, smem_u32(cK + (warp * 16 + (lane >> 4) * 8 + (lane & 7)) * LDS + kk * 16 + ((lane >> 3) & 1) * 8));
+      MmaType<T>::mma(s[0], qf[kk], kf[0], kf[1]);
+      MmaType<T>::mma(s[1], qf[kk], kf[2], kf[3]);
+    }
+    const int i0 = q0 + g, jw = (t0 + i) * BKV + warp * 16;
+    float m_new[2] = {m_run[0], m_run[1]};
+#pragma unroll
+    for (int n = 0; n < 2; ++n) {
+      const int j = jw + n * 8 + 2 * t4;
+      s[n][0] = sc.apply(s[n][0], i0, j);
+      s[n][1] = sc.apply(s[n][1], i0, j + 1);
+      s[n][2] = sc.apply(s[n][2], i0 + 8, j);
+      s[n][3] = sc.apply(s[n][3], i0 + 8, j + 1);
+      m_new[0] = fmaxf(m_new[0], fmaxf(s[n][0], s[n][1]));
+      m_new[1] = fmaxf(m_new[1], fmaxf(s[n][2], s[n][3]));
+    }
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      m_new[r] = fmaxf(m_new[r], __shfl_xor_sync(0xffffffffu, m_new[r], 1));
+      m_new[r] = fmaxf(m_new[r], __shfl_xor_sync(0xffffffffu, m_new[r], 2));
+    }
+    float corr[2], msc[2];
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      msc[r] = (m_new[r] == -INFINITY) ? 0.f : m_new[r] * LOG2E;
+      corr[r] = (m_run[r] == -INFINITY) ? 0.f : exp2f(m_run[r] * LOG2E - msc[r]);
+      m_run[r] = m_new[r];
+      l_run[r] *= corr[r];
+    }
+    uint32_t pf[4];
+#pragma unroll
+    for (int n = 0; n < 2; ++n) {
+      const float p0 = exp2f(s[n][0] * LOG2E - msc[0]), p1 = exp2f(s[n][1] * LOG2E - msc[0]);
+      const float p2 = exp2f(s[n][2] * LOG2E - msc[1]), p3 = exp2f(s[n][3] * LOG2E - msc[1]);
+      l_run[0] += p0 + p1;
+      l_run[1] += p2 + p3;
+      if constexpr (DROP) {                      // the row sums stay those of the undropped P
+        const int j = jw + n * 8 + 2 * t4;
+        const uint32_t w0 = drop_word(dkey, drow[0], j >> 2), w1 = drop_word(dkey, drow[1], j >> 2);
+        pf[2 * n] = MmaType<T>::pack(drop_keep(w0, j, dthr) ? p0 : 0.f, drop_keep(w0, j + 1, dthr) ? p1 : 0.f);
+        pf[2 * n + 1] = MmaType<T>::pack(drop_keep(w1, j, dthr) ? p2 : 0.f, drop_keep(w1, j + 1, dthr) ? p3 : 0.f);
+      } else {
+        pf[2 * n] = MmaType<T>::pack(p0, p1);
+        pf[2 * n + 1] = MmaType<T>::pack(p2, p3);
+      }
+    }
+#pragma unroll
+    for (int d = 0; d < HD / 8; ++d) {
+      o_acc[d][0] *= corr[0]; o_acc[d][1] *= corr[0];
+      o_acc[d][2] *= corr[1]; o_acc[d][3] *= corr[1];
+    }
+    // O += P V over the same 16 keys
+#pragma unroll
+    for (int db = 0; db < HD / 16; ++db) {
+      uint32_t vf[4];
+      ldsm_x4_t(vf, smem_u32(cV + (warp * 16 + ((lane >> 3) & 1) * 8 + (lane & 7)) * LDS + db * 16 + (lane >> 4) * 8));
+      MmaType<T>::mma(o_acc[2 * db], pf, vf[0], vf[1]);
+      MmaType<T>::mma(o_acc[2 * db + 1], pf, vf[2], vf[3]);
+    }
+    __syncthreads();                             // the slot is refilled by the next iteration's load_kv
+  }
+  cp_async_wait<0>();
+  __syncthreads();
+  // ---- warp partials -> shared memory (the ring is dead)
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    l_run[r] += __shfl_xor_sync(0xffffffffu, l_run[r], 1);
+    l_run[r] += __shfl_xor_sync(0xffffffffu, l_run[r], 2);
+    const int row = g + 8 * r;
+    if (t4 == 0) {
+      part[FqSmem::W_M + warp * FQ_ROWS + row] = m_run[r];
+      part[FqSmem::W_L + warp * FQ_ROWS + row] = l_run[r];
+    }
+#pragma unroll
+    for (int d = 0; d < HD / 8; ++d)
+      *reinterpret_cast<float2*>(part + FqSmem::W_O + (warp * FQ_ROWS + row) * 64 + d * 8 + 2 * t4) = make_float2(o_acc[d][2 * r], o_acc[d][2 * r + 1]);
+  }
+  __syncthreads();
+  // ---- CTA partial: thread = (row, 8 columns); softmax partials merge with exp2((m_w - M) log2 e) weights
+  const int row = threadIdx.x >> 3, c0 = (threadIdx.x & 7) * 8;
+  {
+    float M = -INFINITY;
+#pragma unroll
+    for (int w = 0; w < 4; ++w) M = fmaxf(M, part[FqSmem::W_M + w * FQ_ROWS + row]);
+    float L = 0.f, acc[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) acc[c] = 0.f;
+#pragma unroll
+    for (int w = 0; w < 4; ++w) {
+      const float mw = part[FqSmem::W_M + w * FQ_ROWS + row];
+      const float f = (mw == -INFINITY) ? 0.f : exp2f((mw - M) * LOG2E);
+      L += f * part[FqSmem::W_L + w * FQ_ROWS + row];
+#pragma unroll
+      for (int c = 0; c < 8; ++c) acc[c] += f * part[FqSmem::W_O + (w * FQ_ROWS + row) * 64 + c0 + c];
+    }
+#pragma unroll
+    for (int c = 0; c < 8; ++c) part[FqSmem::C_O + row * 64 + c0 + c] = acc[c];
+    if ((threadIdx.x & 7) == 0) { part[FqSmem::C_M + row] = M; part[FqSmem::C_L + row] = L; }
+  }
+  fq_cluster_sync();
+  // ---- cluster: CTA 0 merges the FQ_SPLIT partials in rank order and writes O / lse
+  if (split == 0) {
+    float M = -INFINITY;
+#pragma unroll
+    for (int sp = 0; sp < FQ_SPLIT; ++sp) M = fmaxf(M, fq_ld_part(part + FqSmem::C_M + row, sp));
+    float L = 0.f, acc[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) acc[c] = 0.f;
+#pragma unroll
+    for (int sp = 0; sp < FQ_SPLIT; ++sp) {
+      const float ms = fq_ld_part(part + FqSmem::C_M + row, sp);
+      const float f = (ms == -INFINITY) ? 0.f : exp2f((ms - M) * LOG2E);
+      L += f * fq_ld_part(part + FqSmem::C_L + row, sp);
+#pragma unroll
+      for (int c = 0; c < 8; ++c) acc[c] += f * fq_ld_part(part + FqSmem::C_O + row * 64 + c0 + c, sp);
+    }
+    const int i = q0 + row;
+    if (i < p.Lq) {
+      const float inv = (L > 0.f ? 1.f / L : 0.f) * dscale;
+      T* go = static_cast<T*>(p.o) + b * p.o_bs + static_cast<long long>(i) * p.o_rs + static_cast<long long>(h) * p.hd + c0;
+      *reinterpret_cast<uint4*>(go) = make_uint4(MmaType<T>::pack(acc[0] * inv, acc[1] * inv), MmaType<T>::pack(acc[2] * inv, acc[3] * inv),
+                                                 MmaType<T>::pack(acc[4] * inv, acc[5] * inv), MmaType<T>::pack(acc[6] * inv, acc[7] * inv));
+      if (p.lse && (threadIdx.x & 7) == 0) p.lse[(static_cast<long long>(b) * p.H + h) * p.Lq + i] = M + logf(L);
+    }
+  }
+  fq_cluster_sync();                            // the other CTAs' shared memory stays alive until CTA 0 has read it
+}
+
+// dQ of the same shape: dQ_i = scale * sum_j P_ij (dP_ij - delta_i) K_j, keys split as in the forward; partial dQ tiles are summed.
+template <typename T, bool DROP = false>
+__global__ void MRB_FQ_CLUSTER __launch_bounds__(NTHREADS) attn_fq_dq_kernel(const typename AttnParamsOf<DROP>::type p) {
+  mrb::pdl_trigger();
+  mrb::pdl_wait();      // before the first global access (common.cuh, MRB_PDL)
+  constexpr int HD = 64, LDS = FqSmem::LDS;
+  extern __shared__ __align__(16) uint8_t smem_attn[];
+  T* sQ = reinterpret_cast<T*>(smem_attn);
+  T* sdO = sQ + FQ_ROWS * LDS;
+  T* sK = sdO + FQ_ROWS * LDS;
+  T* sV = sK + FqSmem::RING;
+  float* part = reinterpret_cast<float*>(sK);
+  const int split = blockIdx.x, h = blockIdx.y;
+  const int n_rb = (p.Lq + FQ_ROWS - 1) / FQ_ROWS, b = blockIdx.z / n_rb, q0 = (blockIdx.z % n_rb) * FQ_ROWS;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t4 = lane & 3;
+  const T* gq = static_cast<const T*>(p.q) + b * p.q_bs + static_cast<long long>(h) * p.hd;
+  const T* gk = static_cast<const T*>(p.k) + (b / p.kv_div) * p.k_bs + static_cast<long long>(h) * p.hd;
+  const T* gv = static_cast<const T*>(p.v) + (b / p.kv_div) * p.v_bs + static_cast<long long>(h) * p.hd;
+  const T* gdo = static_cast<const T*>(p.dout) + b * p.do_bs + static_cast<long long>(h) * p.hd;
+  ScoreCtx sc{p.scale, p.bias ? p.bias + static_cast<long long>(h) * p.bias_len : nullptr, p.bias_zero,
+              p.kmask ? p.kmask + static_cast<long long>(b / p.kv_div) * p.Lk : nullptr, p.causal, p.q_pos0, p.Lk, p.Lq};
+  const int n_kv = (p.Lk + BKV - 1) / BKV, per = (n_kv + FQ_SPLIT - 1) / FQ_SPLIT;
+  const int t0 = split * per, n_t = max(0, min(n_kv, t0 + per) - t0);
+
+  auto load_kv = [&](int i) {
+    if (i < n_t) {
+      load_tile<T, HD, BKV>(smem_u32(sK + (i % FQ_ST) * BKV * LDS), gk, p.k_rs, (t0 + i) * BKV, p.Lk, p.hd);
+      load_tile<T, HD, BKV>(smem_u32(sV + (i % FQ_ST) * BKV * LDS), gv, p.v_rs, (t0 + i) * BKV, p.Lk, p.hd);
+    }
+    cp_async_commit();
+  };
+  load_tile<T, HD, FQ_ROWS>(smem_u32(sQ), gq, p.q_rs, q0, p.Lq, p.hd);
+  load_tile<T, HD, FQ_ROWS>(smem_u32(sdO), gdo, p.do_rs, q0, p.Lq, p.hd);
+  load_kv(0);
+  load_kv(1);
+
+  const long long stat = (static_cast<long long>(b) * p.H + h) * p.Lq;
+  float lse[2], dl[2];
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    const int i = q0 + g + r * 8;
+    lse[r] = i < p.Lq ? p.lse[stat + i] : 0.f;
+    dl[r] = i < p.Lq ? p.delta[stat + i] : 0.f;
+  }
+  float dq_acc[HD / 8][4];
+#pragma unroll
+  for (int i = 0; i < HD / 8; ++i) dq_acc[i][0] = dq_acc[i][1] = dq_acc[i][2] = dq_acc[i][3] = 0.f;
+  uint32_t qf[HD / 16][4], dof[HD / 16][4];
+  uint32_t dkey = 0, drow[2] = {0u, 0u}, dthr = 0;
+  float dscale = 1.f;
+  if constexpr (DROP) {
+    dkey = drop_key(*p.drop_seed, p.drop_site);
+    dthr = p.drop_thr; dscale = p.drop_scale;
+#pragma unroll
+    for (int r = 0; r < 2; ++r)
+      drow[r] = (static_cast<uint32_t>(b * p.H + h) * static_cast<uint32_t>(p.Lq) +
+                 static_cast<uint32_t>(min(q0 + g + 8 * r, p.Lq - 1))) * drop_groups(static_cast<uint32_t>(p.Lk));
+  }
+
+  for (int i = 0; i < n_t; ++i) {
+    load_kv(i + 2);
+    cp_async_wait<2>();
+    __syncthreads();
+    if (i == 0) {
+#pragma unroll
+      for (int kk = 0; kk < HD / 16; ++kk) {
+        ldsm_x4(qf[kk], smem_u32(sQ + (lane & 15) * LDS + kk * 16 + (lane >> 4) * 8));
+        ldsm_x4(dof[kk], smem_u32(sdO + (lane & 15) * LDS + kk * 16 + (lane >> 4) * 8));
+      }
+    }
+    const T* cK = sK + (i % FQ_ST) * BKV * LDS;
+    const T* cV = sV + (i % FQ_ST) * BKV * LDS;
+    float s[2][4], dp[2][4];
+#pragma unroll
+    for (int n = 0; n < 2; ++n) {
+      s[n][0] = s[n][1] = s[n][2] = s[n][3] = 0.f;
+      dp[n][0] = dp[n][1] = dp[n][2] = dp[n][3] = 0.f;
+    }
+#pragma unroll
+    for (int kk = 0; kk < HD / 16; ++kk) {
+      uint32_t kf[4], vf[4];
+      const int off = (warp * 16 + (lane >> 4) * 8 + (lane & 7)) * LDS + kk * 16 + ((lane >> 3) & 1) * 8;
+      ldsm_x4(kf, smem_u32(cK + off));
+      ldsm_x4(vf, smem_u32(cV + off));
+      MmaType<T>::mma(s[0], qf[kk], kf[0], kf[1]);
+      MmaType<T>::mma(s[1], qf[kk], kf[2], kf[3]);
+      MmaType<T>::mma(dp[0], dof[kk], vf[0], vf[1]);
+      MmaType<T>::mma(dp[1], dof[kk], vf[2], vf[3]);
+    }
+    const int i0 = q0 + g, jw = (t0 + i) * BKV + warp * 16;
+    uint32_t dsf[4];
+#pragma unroll
+    for (int n = 0; n < 2; ++n) {
+      const int j = jw + n * 8 + 2 * t4;
+      float ds[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int r = e >> 1;
+        const float sv = sc.apply(s[n][e], i0 + r * 8, j + (e & 1));
+        const float pr = (sv == -INFINITY) ? 0.f : __expf(sv - lse[r]);
+        float dpe = dp[n][e];
+        if constexpr (DROP) dpe = drop_keep(drop_word(dkey, drow[r], j >> 2), j + (e & 1), dthr) ? dpe * dscale : 0.f;
+        ds[e] = pr * (dpe - dl[r]) * p.scale;
+      }
+      dsf[2 * n] = MmaType<T>::pack(ds[0], ds[1]);
+      dsf[2 * n + 1] = MmaType<T>::pack(ds[2], ds[3]);
+    }
+    // dQ += dS K over this warp's 16 keys (B operand = K [key x d] -> transposed ldmatrix)
+#pragma unroll
+    for (int db = 0; db < HD / 16; ++db) {
+      uint32_t kf[4];
+      ldsm_x4_t(kf, smem_u32(cK + (warp * 16 + ((lane >> 3) & 1) * 8 + (lane & 7)) * LDS + db * 16 + (lane >> 4) * 8));
+      MmaType<T>::mma(dq_acc[2 * db], dsf, kf[0], kf[1]);
+      MmaType<T>::mma(dq_acc[2 * db + 1], dsf, kf[2], kf[3]);
+    }
+    __syncthreads();
+  }
+  cp_async_wait<0>();
+  __syncthreads();
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    const int row = g + 8 * r;
+#pragma unroll
+    for (int d = 0; d < HD / 8; ++d)
+      *reinterpret_cast<float2*>(part + FqSmem::W_O + (warp * FQ_ROWS + row) * 64 + d * 8 + 2 * t4) = make_float2(dq_acc[d][2 * r], dq_acc[d][2 * r + 1]);
+  }
+  __syncthreads();
+  const int row = threadIdx.x >> 3, c0 = (threadIdx.x & 7) * 8;
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    float a = 0.f;
+#pragma unroll
+    for (int w = 0; w < 4; ++w) a += part[FqSmem::W_O + (w * FQ_ROWS + row) * 64 + c0 + c];
+    part[FqSmem::C_O + row * 64 + c0 + c] = a;
+  }
+  fq_cluster_sync();
+  if (split == 0) {
+    float acc[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      acc[c] = 0.f;
+#pragma unroll
+      for (int sp = 0; sp < FQ_SPLIT; ++sp) acc[c] += fq_ld_part(part + FqSmem::C_O + row * 64 + c0 + c, sp);
+    }
+    const int i = q0 + row;
+    if (i < p.Lq) {
+      T* gdq = static_cast<T*>(p.dq) + b * p.q_bs + static_cast<long long>(i) * p.q_rs + static_cast<long long>(h) * p.hd + c0;
+      *reinterpret_cast<uint4*>(gdq) = make_uint4(MmaType<T>::pack(acc[0], acc[1]), MmaType<T>::pack(acc[2], acc[3]),
+                                                  MmaType<T>::pack(acc[4], acc[5]), MmaType<T>::pack(acc[6], acc[7]));
+    }
+  }
+  fq_cluster_sync();
+}
+
 template <typename K>
 static int set_smem(K kernel, int bytes) {
   cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
@@ -891,6 +1281,33 @@ static int launch_xq(const typename AttnParamsOf<DROP>::type& p, cudaStream_t s)
   return MRB_OK;
 }
 
+// few query rows x >= 512 keys (the T5 decoder's cross-attention), hd = 64
+static inline bool fq_shape(int Lq, int Lk, int hd) {
+  static int use = -1;                    // MRB_ATTN_FQ=0 keeps the generic kernels (A/B measurements)
+  if (use < 0) { const char* e = getenv("MRB_ATTN_FQ"); use = (e && e[0] == '0') ? 0 : 1; }
+  return use && hd == 64 && Lq <= 2 * FQ_ROWS && Lk >= 512;
+}
+template <typename T, bool DROP = false>
+static int launch_fq_fwd(const typename AttnParamsOf<DROP>::type& p, cudaStream_t s) {
+  const int smem = FqSmem::bytes(1);
+  static bool cfg = false;
+  if (!cfg) { if (int rc = set_smem(attn_fq_fwd_kernel<T, DROP>, smem)) return rc; cfg = true; }
+  dim3 grid(FQ_SPLIT, p.H, p.B * ((p.Lq + FQ_ROWS - 1) / FQ_ROWS));
+  MRB_LAUNCH((attn_fq_fwd_kernel<T, DROP>), grid, NTHREADS, smem, s, p);
+  MRB_CHECK_LAUNCH();
+  return MRB_OK;
+}
+template <typename T, bool DROP = false>
+static int launch_fq_dq(const typename AttnParamsOf<DROP>::type& p, cudaStream_t s) {
+  const int smem = FqSmem::bytes(2);
+  static bool cfg = false;
+  if (!cfg) { if (int rc = set_smem(attn_fq_dq_kernel<T, DROP>, smem)) return rc; cfg = true; }
+  dim3 grid(FQ_SPLIT, p.H, p.B * ((p.Lq + FQ_ROWS - 1) / FQ_ROWS));
+  MRB_LAUNCH((attn_fq_dq_kernel<T, DROP>), grid, NTHREADS, smem, s, p);
+  MRB_CHECK_LAUNCH();
+  return MRB_OK;
+}
+
 template <typename T, int HD, bool DROP = false>
 static int launch_bwd(const typename AttnParamsOf<DROP>::type& p, cudaStream_t s) {
   if (HD == 64 && p.Lq <= DELTA_EXACT_MAX_LQ) {
@@ -909,7 +1326,9 @@ static int launch_bwd(const typename AttnParamsOf<DROP>::type& p, cudaStream_t s
     MRB_LAUNCH((attn_delta_kernel<T>), (rows + 7) / 8, 256, 0, s, static_cast<const AttnParams&>(p));
     MRB_CHECK_LAUNCH();
   }
-  {
+  if (HD == 64 && fq_shape(p.Lq, p.Lk, p.hd)) {          // keys split over a cluster (attn_fq_dq_kernel)
+    if (int rc = launch_fq_dq<T, DROP>(p, s)) return rc;
+  } else {
     const int smem = (2 * BQ + 4 * BKV) * (HD + 8) * 2;
     static bool cfg = false;
     if (!cfg) { if (int rc = set_smem(attn_bwd_dq_kernel<T, HD, DROP>, smem)) return rc; cfg = true; }
@@ -958,13 +1377,16 @@ static int attention_fwd_impl(const void* q, long long q_bs, long long q_rs, con
   if (use_xq < 0) { const char* e = getenv("MRB_ATTN_XQ"); use_xq = (e && e[0] == '0') ? 0 : 1; }
   const bool xq_shape = use_xq && hd == 64 && Lq <= 32 && Lk > 64 && Lk <= 16 * 4 * XQ_MAXG && !bias && !kmask && !causal && !lse &&
                         p.kv_div == 1 && 4 * 32 * (64 + 2) * 4 + 8 * 32 * 4 <= 2 * ((Lk + 15) & ~15) * 64 * 2;
+  const bool fq = fq_shape(Lq, Lk, hd);   // few query rows x thousands of keys (T5 decoder cross-attention): keys split over a cluster
   if (drop_seed && drop_p > 0.f) {
     if (hd > 64 || drop_p >= 1.f) return MRB_ERR_UNSUPPORTED;
     const DropSpec d = make_drop(drop_seed, drop_site, drop_p);
     p.drop_seed = d.seed; p.drop_site = d.site; p.drop_thr = d.thr; p.drop_scale = d.scale;
+    if (fq) return dtype == MRB_DT_F16 ? launch_fq_fwd<__half, true>(p, s) : launch_fq_fwd<__nv_bfloat16, true>(p, s);
     if (xq_shape) return dtype == MRB_DT_F16 ? launch_xq<__half, true>(p, s) : launch_xq<__nv_bfloat16, true>(p, s);
     return dtype == MRB_DT_F16 ? launch_fwd<__half, 64, true>(p, s) : launch_fwd<__nv_bfloat16, 64, true>(p, s);
   }
+  if (fq) return dtype == MRB_DT_F16 ? launch_fq_fwd<__half>(p, s) : launch_fq_fwd<__nv_bfloat16>(p, s);
   if (xq_shape) return dtype == MRB_DT_F16 ? launch_xq<__half>(p, s) : launch_xq<__nv_bfloat16>(p, s);
   if (dtype == MRB_DT_F16) return hd <= 64 ? launch_fwd<__half, 64>(p, s) : launch_fwd<__half, 96>(p, s);
   return hd <= 64 ? launch_fwd<__nv_bfloat16, 64>(p, s) : launch_fwd<__nv_bfloat16, 96>(p, s);

@@ -156,51 +156,38 @@ attn_vit_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   uint8_t* sV = smem + S::OFF_V;
 
   if (warp == 0) {
-    // ===================== TMA producer (converged warp, one elected lane issues: elect_one, common.cuh) =====================
-    int n = 0;
-    for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++n) {
-      const int b = item / p.H, h = item % p.H;
-      const uint32_t ph = (n & 1) ^ 1;                       // parity of the PREVIOUS item's "empty" phase (first wait passes)
-      mbar_wait(q_empty, ph);
-      if (elect_one()) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int n = 0;
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++n) {
+        const int b = item / p.H, h = item % p.H;
+        const uint32_t ph = (n & 1) ^ 1;                       // parity of the PREVIOUS item's "empty" phase (first wait passes)
+        mbar_wait(q_empty, ph);
         mbar_expect_tx(q_full, 2 * (S::Q1 + S::Q2));
         for (int g = 0; g < 2; ++g) {
           vt_tma_4d(sQ + g * (S::Q1 + S::Q2), &tmQ, q_full, 0, h, 1 + g * VT_ROWS, b);
           vt_tma_4d(sQ + g * (S::Q1 + S::Q2) + S::Q1, &tmQ2, q_full, VT_D1, h, 1 + g * VT_ROWS, b);
         }
-      }
-      __syncwarp();
-      mbar_wait(k_empty, ph);
-      if (elect_one()) {
+        mbar_wait(k_empty, ph);
         mbar_expect_tx(k_full, S::K1 + S::K2);
         for (int g = 0; g < 2; ++g) {
           vt_tma_4d(sK + g * (VT_ROWS * 128), &tmK, k_full, 0, h, 1 + g * VT_ROWS, b);
           vt_tma_4d(sK + S::K1 + g * (VT_ROWS * 64), &tmK2, k_full, VT_D1, h, 1 + g * VT_ROWS, b);
         }
-      }
-      __syncwarp();
-      mbar_wait(v_empty, ph);
-      if (elect_one()) {
+        mbar_wait(v_empty, ph);
         mbar_expect_tx(v_full, S::K1 + S::K2);
         for (int g = 0; g < 2; ++g) {
           vt_tma_4d(sV + g * (VT_ROWS * 128), &tmV, v_full, 0, h, 1 + g * VT_ROWS, b);
           vt_tma_4d(sV + S::K1 + g * (VT_ROWS * 64), &tmV2, v_full, VT_D1, h, 1 + g * VT_ROWS, b);
         }
       }
-      __syncwarp();
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    // Converged warp, one elected lane issues, descriptors = kernel-lifetime bases + small offsets of the 14-bit address field
-    // (16-byte units): 76 tcgen05.mma per (frame, head) item, of which 64 keep the tensor pipe busy for 16-32 clk each --
-    // rebuilding descriptors from addresses under `if (lane == 0)` cost more per instruction than that (attention_tc.cu).
     const int fmt = dt == MRB_DT_BF16 ? 1 : 0;
     const uint32_t id_s = vt_idesc(fmt, VT_ROWS, VT_KEYS, 0);      // S = Q K^T: 128 x 256, both K-major
     const uint32_t id_o1 = vt_idesc(fmt, VT_ROWS, VT_D1, 1);       // O[:, :64] += P V: B = V MN-major
     const uint32_t id_o2 = vt_idesc(fmt, VT_ROWS, VT_D2, 1);
-    const uint64_t kd1 = vt_desc(smem_u32(sK), 16, 1024, VT_SW128), kd2 = vt_desc(smem_u32(sK + S::K1), 16, 512, VT_SW64);
-    const uint64_t qd1 = vt_desc(smem_u32(sQ), 16, 1024, VT_SW128), qd2 = vt_desc(smem_u32(sQ + S::Q1), 16, 512, VT_SW64);
-    const uint64_t vd1 = vt_desc(smem_u32(sV), VT_KEYS * 128, 1024, VT_SW128), vd2 = vt_desc(smem_u32(sV + S::K1), VT_KEYS * 64, 512, VT_SW64);
     int n = 0;
     for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++n) {
       const uint32_t ph = n & 1;
@@ -209,39 +196,40 @@ attn_vit_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       for (int g = 0; g < 2; ++g) {
         if (n > 0) mbar_wait(&o_empty[g], ph ^ 1);                 // the previous item's O of this group has been read out
         tc_fence_after();
-        if (elect_one()) {
-          const uint32_t qo = static_cast<uint32_t>((g * (S::Q1 + S::Q2)) >> 4);
+        if (lane == 0) {
+          const uint32_t q_addr = smem_u32(sQ + g * (S::Q1 + S::Q2));
+          const uint32_t k_addr = smem_u32(sK);
           const uint32_t d_s = tmem_base + g * 256;
 #pragma unroll
-          for (int k = 0; k < 4; ++k) umma_f16(d_s, qd1 + (qo + 2 * k), kd1 + 2 * k, id_s, k > 0 ? 1u : 0u);
+          for (int k = 0; k < 4; ++k)
+            umma_f16(d_s, vt_desc(q_addr + k * 32, 16, 1024, VT_SW128), vt_desc(k_addr + k * 32, 16, 1024, VT_SW128), id_s, k > 0 ? 1u : 0u);
 #pragma unroll
-          for (int k = 0; k < 2; ++k) umma_f16(d_s, qd2 + (qo + 2 * k), kd2 + 2 * k, id_s, 1u);
+          for (int k = 0; k < 2; ++k)
+            umma_f16(d_s, vt_desc(q_addr + S::Q1 + k * 32, 16, 512, VT_SW64), vt_desc(k_addr + S::K1 + k * 32, 16, 512, VT_SW64), id_s, 1u);
           umma_commit(&s_full[g]);
         }
         __syncwarp();
       }
-      if (elect_one()) { umma_commit(q_empty); umma_commit(k_empty); }
+      if (lane == 0) { umma_commit(q_empty); umma_commit(k_empty); }
       __syncwarp();
       mbar_wait(v_full, ph);
       for (int g = 0; g < 2; ++g) {
         mbar_wait(&p_full[g], ph);
         tc_fence_after();
-        if (elect_one()) {
+        if (lane == 0) {
+          const uint32_t v_addr = smem_u32(sV);
           const uint32_t a_p = tmem_base + g * 256;                 // P: keys 2c, 2c+1 in column c
           const uint32_t d_o = tmem_base + g * 256 + 128;
-          uint64_t v1 = vd1, v2 = vd2;
-          asm volatile("" : "+l"(v1), "+l"(v2));                    // opaque: the 32 descriptors are formed here, next to their use,
-                                                                    // not hoisted into 64 registers for the kernel's lifetime
-#pragma unroll
+#pragma unroll 4
           for (int k = 0; k < VT_KEYS / 16; ++k) {
-            umma_f16_ts(d_o, a_p + k * 8, v1 + 128 * k, id_o1, k > 0 ? 1u : 0u);
-            umma_f16_ts(d_o + VT_D1, a_p + k * 8, v2 + 64 * k, id_o2, k > 0 ? 1u : 0u);
+            umma_f16_ts(d_o, a_p + k * 8, vt_desc(v_addr + k * 2048, VT_KEYS * 128, 1024, VT_SW128), id_o1, k > 0 ? 1u : 0u);
+            umma_f16_ts(d_o + VT_D1, a_p + k * 8, vt_desc(v_addr + S::K1 + k * 1024, VT_KEYS * 64, 512, VT_SW64), id_o2, k > 0 ? 1u : 0u);
           }
           umma_commit(&o_full[g]);
         }
         __syncwarp();
       }
-      if (elect_one()) umma_commit(v_empty);
+      if (lane == 0) umma_commit(v_empty);
       __syncwarp();
     }
   } else if (warp < 10) {

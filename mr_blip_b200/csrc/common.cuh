@@ -262,7 +262,12 @@ inline void launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t s
   cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
   cudaLaunchAttribute at[1];
   at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+#ifdef MRB_PDL_MAX_BLOCKS   // early launch only for small grids (the decoder's latency-bound chain); big kernels launch as usual
+  at[0].val.programmaticStreamSerializationAllowed =
+      (static_cast<unsigned long long>(grid.x) * grid.y * grid.z <= static_cast<unsigned long long>(MRB_PDL_MAX_BLOCKS)) ? 1 : 0;
+#else
   at[0].val.programmaticStreamSerializationAllowed = 1;
+#endif
   cfg.attrs = at; cfg.numAttrs = 1;
   cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);     // errors surface through MRB_CHECK_LAUNCH
 }

@@ -18,7 +18,7 @@ __global__ void __launch_bounds__(256) norm_kernel(const float* __restrict__ x, 
                                                    float* __restrict__ sum_out) {
   mrb::pdl_trigger();
   mrb::pdl_wait();      // before the first global access (common.cuh, MRB_PDL)
-  const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);      // 8 warps per block; 1 for decoder-sized inputs (norm_warps)
   const int lane = threadIdx.x & 31;
   if (row >= rows) return;
   const int nv = C >> 2;
@@ -84,7 +84,7 @@ __global__ void __launch_bounds__(256) rmsnorm_bwd_kernel(const float* __restric
                                                           float* __restrict__ dres) {
   mrb::pdl_trigger();
   mrb::pdl_wait();      // before the first global access (common.cuh, MRB_PDL)
-  const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= rows) return;
   const int nv = C >> 2;
@@ -699,15 +699,19 @@ __global__ void axpby_kernel(const float4* __restrict__ x, float4* __restrict__ 
 using namespace mrb;
 #define STREAM static_cast<cudaStream_t>(stream)
 static inline unsigned blocks_for(long long n, int per) { return static_cast<unsigned>((n + per - 1) / per); }
+// Row kernels (one warp per row): 8 rows per block, but decoder-sized inputs (64 rows) would then sit on 8 of the 148 SMs and run
+// at the latency of 8 serial row passes per SM -- one row per block spreads them.
+static inline int norm_warps(int rows) { return rows <= 2 * 148 ? 1 : 8; }
 
 extern "C" int mrb_norm(const float* x, const float* add, const float* w, const float* bias, float eps, int rows, int C,
                         int mode, float* out_f32, void* out_h, int h_dtype, long long ld_h, float* sum_out, void* stream) {
   if (rows <= 0) return MRB_OK;
   if ((C & 3) || C > 2048 || (out_h && (ld_h & 3))) return MRB_ERR_ARG;
-  const unsigned grid = blocks_for(rows, 8);
-  if (C <= 1024) MRB_LAUNCH((norm_kernel<8>), grid, 256, 0, STREAM, x, add, w, bias, eps, rows, C, mode, out_f32, out_h, h_dtype, ld_h, sum_out);
-  else if (C <= 1536) MRB_LAUNCH((norm_kernel<12>), grid, 256, 0, STREAM, x, add, w, bias, eps, rows, C, mode, out_f32, out_h, h_dtype, ld_h, sum_out);
-  else MRB_LAUNCH((norm_kernel<16>), grid, 256, 0, STREAM, x, add, w, bias, eps, rows, C, mode, out_f32, out_h, h_dtype, ld_h, sum_out);
+  const int nw = norm_warps(rows);
+  const unsigned grid = blocks_for(rows, nw);
+  if (C <= 1024) MRB_LAUNCH((norm_kernel<8>), grid, 32 * nw, 0, STREAM, x, add, w, bias, eps, rows, C, mode, out_f32, out_h, h_dtype, ld_h, sum_out);
+  else if (C <= 1536) MRB_LAUNCH((norm_kernel<12>), grid, 32 * nw, 0, STREAM, x, add, w, bias, eps, rows, C, mode, out_f32, out_h, h_dtype, ld_h, sum_out);
+  else MRB_LAUNCH((norm_kernel<16>), grid, 32 * nw, 0, STREAM, x, add, w, bias, eps, rows, C, mode, out_f32, out_h, h_dtype, ld_h, sum_out);
   MRB_CHECK_LAUNCH();
   return MRB_OK;
 }
@@ -716,7 +720,7 @@ extern "C" int mrb_rmsnorm_bwd(const float* x, const float* w, const void* dy, i
                                const float* lora_A, int R, float eps, int rows, int C, float* dres, void* stream) {
   if (rows <= 0) return MRB_OK;
   if ((C & 3) || C > 2048 || (ld_dy & 3) || R > 32 || (lora_A && dy_dtype == MRB_DT_F32)) return MRB_ERR_ARG;
-  MRB_LAUNCH((rmsnorm_bwd_kernel<16>), blocks_for(rows, 8), 256, 0, STREAM, x, w, dy, dy_dtype, ld_dy, lora_A, R, eps, rows, C, dres);
+  MRB_LAUNCH((rmsnorm_bwd_kernel<16>), blocks_for(rows, norm_warps(rows)), 32 * norm_warps(rows), 0, STREAM, x, w, dy, dy_dtype, ld_dy, lora_A, R, eps, rows, C, dres);
   MRB_CHECK_LAUNCH();
   return MRB_OK;
 }

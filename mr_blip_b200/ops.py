@@ -11,6 +11,7 @@ F16, BF16, F32 = 0, 1, 2
 _DT = {torch.float16: F16, torch.bfloat16: BF16, torch.float32: F32}
 INT_MIN = -2 ** 31
 USE_TC_ATTENTION = True
+USE_FQ_ATTENTION = os.environ.get("MRB_ATTN_FQ", "1") != "0"       # 0: decoder cross-attention through the tcgen05 kernels (round-2 first path)
 USE_VIT_ATTENTION = os.environ.get("MRB_ATTN_VIT", "1") != "0"     # 0: the generic flash kernel + the single-row kernel (round 1 path)
 GEMM_PROFILE = None      # set to a list to record (M, N, K, cuda start event, cuda end event) per GEMM launch
 
@@ -114,6 +115,13 @@ def gemm(a, b, out=None, bias=None, gelu=False, resid=None, out_dtype=None, row_
     return out
 
 
+def few_queries(Lq, Lk, hd):
+    """<= 32 query rows against >= 512 keys, hd 64 (the T5 decoder's cross-attention over the encoder output): the mma.sync entry
+    points split the KEYS over a thread-block cluster for this shape (csrc/attention.cu attn_fq_*_kernel; MRB_ATTN_FQ=0 disables),
+    the tcgen05 kernels would run one CTA per (clip, head) with 16 of their 256 rows in use."""
+    return USE_FQ_ATTENTION and hd == 64 and Lq <= 32 and Lk >= 512
+
+
 def attention_fwd(q, k, v, out, B, H, Lq, Lk, hd, scale, q_strides, k_strides, v_strides, o_strides, bias=None,
                   bias_zero=0, kmask=None, causal=False, q_pos0=0, lse=None, kv_div=1, impl="auto", drop=None):
     """q/k/v/out: tensors whose data_ptr is row 0 / head 0; *_strides = (batch stride, row stride) in elements.
@@ -123,7 +131,7 @@ def attention_fwd(q, k, v, out, B, H, Lq, Lk, hd, scale, q_strides, k_strides, v
     if kmask is not None:
         _check(kmask, torch.int32)
     tc_ok = (hd == 64 or (64 < hd <= 96 and hd % 8 == 0))
-    use_tc = impl == "tc" or (impl == "auto" and USE_TC_ATTENTION and tc_ok and (Lq >= 128 or Lk >= 512))
+    use_tc = impl == "tc" or (impl == "auto" and USE_TC_ATTENTION and tc_ok and (Lq >= 128 or Lk >= 512) and not few_queries(Lq, Lk, hd))
     args = (q.data_ptr(), q_strides[0], q_strides[1], k.data_ptr(), k_strides[0], k_strides[1],
             v.data_ptr(), v_strides[0], v_strides[1], out.data_ptr(), o_strides[0], o_strides[1], B, H, Lq, Lk, hd,
             _DT[q.dtype], float(scale), _ptr(bias), bias.shape[1] if bias is not None else 0, bias_zero, _ptr(kmask),
@@ -160,7 +168,7 @@ def attention_vit(q, k, v, out, frames, H, L, hd, scale, q_strides, k_strides, v
 def attention_bwd(q, k, v, o, dout, dq, dk, dv, B, H, Lq, Lk, hd, scale, q_strides, k_strides, v_strides, o_strides,
                   do_strides, lse, delta_ws, bias=None, bias_zero=0, kmask=None, causal=False, q_pos0=0, impl="auto", drop=None):
     """drop: the (seed word tensor, site, p) the forward call was given, or None."""
-    use_tc = impl == "tc" or (impl == "auto" and USE_TC_ATTENTION and hd == 64 and (Lq >= 128 or Lk >= 512))
+    use_tc = impl == "tc" or (impl == "auto" and USE_TC_ATTENTION and hd == 64 and (Lq >= 128 or Lk >= 512) and not few_queries(Lq, Lk, hd))
     args = (q.data_ptr(), q_strides[0], q_strides[1], k.data_ptr(), k_strides[0], k_strides[1],
             v.data_ptr(), v_strides[0], v_strides[1], o.data_ptr(), o_strides[0], o_strides[1], dout.data_ptr(),
             do_strides[0], do_strides[1], dq.data_ptr(), dk.data_ptr(), dv.data_ptr(), B, H, Lq, Lk, hd, _DT[q.dtype],

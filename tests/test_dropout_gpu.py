@@ -156,6 +156,9 @@ def _ref_attention(q, k, v, scale, bias, kmask, causal, mask):
     ("tc", torch.bfloat16, 2, 4, 300, 300, True, True, False),      # tcgen05 encoder: ragged last tiles
     ("tc", torch.bfloat16, 1, 8, 2037, 2037, True, True, False),    # QVH encoder length
     ("tc", torch.bfloat16, 2, 4, 16, 600, False, True, False),      # decoder cross-attention over a long encoder
+    ("auto", torch.bfloat16, 2, 4, 16, 2037, False, True, False),   # the same through the few-query kernels (keys split over a cluster)
+    ("auto", torch.bfloat16, 1, 3, 21, 700, False, True, False),    #   two 16-row blocks
+    ("mma", torch.float16, 1, 2, 5, 515, False, False, False),
     ("tc", torch.bfloat16, 2, 4, 200, 200, True, False, True),      # causal
 ])
 def test_attention_probability_dropout_fwd_bwd(word, impl, dtype, B, H, Lq, Lk, has_bias, has_mask, causal):

@@ -1164,6 +1164,9 @@ def _ref_attn(q, k, v, scale, bias, kmask, causal, mask):
     (torch.float16, 2, 3, 32, 32, False, False, False, 0.1),     # Q-Former self-attention
     (torch.float16, 2, 3, 32, 257, False, False, False, 0.1),    # Q-Former cross-attention (one-shot kernel when no lse is asked)
     (torch.float16, 2, 3, 32, 257, False, False, False, 0.0),
+    (torch.bfloat16, 1, 2, 9, 530, False, True, False, 0.1),     # decoder cross-attention over a long encoder: the few-query kernels
+    (torch.bfloat16, 1, 1, 20, 600, True, True, False, 0.0),     #   (keys split over the warps; two 16-row blocks, bias window)
+    (torch.float16, 1, 1, 16, 515, False, False, False, 0.0),
 ])
 def test_attention_kernel_source_runs_on_host_shim(attention_kernels_on_host, dtype, B, H, Lq, Lk, has_bias, has_mask, causal, p):
     """Forward (O, lse) and backward (dQ, dK, dV) of the mma.sync attention kernels -- with p > 0 their DROP instantiations --

@@ -193,7 +193,8 @@ def test_attention_cross_small_q(ops, Lq, Lk, dtype):
 @pytest.mark.parametrize("impl", ["mma", "tc"])
 @pytest.mark.parametrize("Lq,Lk,causal,sat", [(150, 150, False, 0), (21, 21, True, 0), (21, 333, False, 0), (300, 300, True, 0),
                                               (257, 400, False, 0), (513, 513, False, 0), (700, 700, False, 128),
-                                              (700, 700, False, 40), (14, 650, False, 128)])
+                                              (700, 700, False, 40), (14, 650, False, 128), (16, 2037, False, 0),
+                                              (30, 1000, False, 0)])
 def test_attention_t5_bias_mask_fwd_bwd(ops, Lq, Lk, causal, sat, impl):
     """sat > 0: T5-style bias that saturates `sat` positions off the diagonal (bucketed relative positions,
     modeling_t5.py:393-445), so most KV tiles see one bias value -- the constant-bias fast paths of the tcgen05 kernels."""

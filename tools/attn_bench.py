@@ -85,5 +85,41 @@ def main():
                 print("%-14s bwd  %8.3f ms  %7.1f TFLOP/s (dropout 0.1)" % (name, ms, 2.5 * flops / ms / 1e9), flush=True)
 
 
+def cross():
+    """The T5 decoder's cross-attention (16 target rows x 2037 encoder keys per clip, 32 heads, kmask, bf16), forward and backward,
+    24 calls (= the decoder's layers) per CUDA-graph replay: us per call in-graph, few-query kernels (auto) vs the tcgen05 kernels."""
+    B, H, Lq, Lk, hd = 4, 32, 16, 2037, 64
+    word = torch.tensor([12345], dtype=torch.int32, device="cuda")
+    q = (torch.randn(B, Lq, H, hd, device="cuda") * 0.5).bfloat16()
+    kv = [(torch.randn(B, Lk, 2, H, hd, device="cuda") * 0.5).bfloat16() for _ in range(24)]       # one K/V per layer: 1.6 GB, not L2-resident
+    out, dout = torch.empty_like(q), torch.randn_like(q)
+    dq, dkv = torch.empty_like(q), torch.empty_like(kv[0])
+    kmask = torch.ones(B, Lk, dtype=torch.int32, device="cuda")
+    lse = torch.empty(B, H, Lq, device="cuda")
+    ws = torch.empty(B * H * Lq, device="cuda")
+    qs, ks = (Lq * H * hd, H * hd), (Lk * 2 * H * hd, 2 * H * hd)
+    for drop in ((None, (word, 0x41, 0.1)) if DROP else (None,)):
+        for impl in ("auto", "tc"):
+            def fwd():
+                for t in kv:
+                    ops.attention_fwd(q, t[:, :, 0], t[:, :, 1], out, B, H, Lq, Lk, hd, 1.0, qs, ks, ks, qs, kmask=kmask, lse=lse, impl=impl, drop=drop)
+
+            def bwd():
+                for t in kv:
+                    ops.attention_bwd(q, t[:, :, 0], t[:, :, 1], out, dout, dq, dkv[:, :, 0], dkv[:, :, 1], B, H, Lq, Lk, hd, 1.0, qs, ks, ks,
+                                      qs, qs, lse, ws, kmask=kmask, impl=impl, drop=drop)
+            for nm, fn in (("fwd", fwd), ("bwd", bwd)):
+                fn()
+                torch.cuda.synchronize()
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    fn()
+                ms = timeit(g.replay)
+                print("t5dec_cross    %-4s %-4s %8.1f us per layer%s" % (impl, nm, ms * 1e3 / len(kv), "  (dropout 0.1)" if drop else ""), flush=True)
+
+
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "cross":
+        cross()
+    else:
+        main()
