@@ -398,15 +398,9 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         if (g == 0 && j + 1 < n_kv) mbar_wait(&kv_full[(j + 1) % STAGES], ((j + 1) / STAGES) & 1);
         tc_fence_after();
         if (elect_one()) {
-#ifdef MRB_ATTN_S_FIRST      // experiment: S_{j+1} ahead of O += P_j V_j (lost 5 % while the issue path was the bottleneck: DESIGN.md section 8)
-          if (j + 1 < n_kv) issue_qk(g, j + 1);
-          issue_pv(g, j);
-          if (g == n_groups - 1) umma_commit(&kv_empty[j % STAGES]);
-#else
           issue_pv(g, j);
           if (g == n_groups - 1) umma_commit(&kv_empty[j % STAGES]);   // K_j / V_j fully consumed
           if (j + 1 < n_kv) issue_qk(g, j + 1);
-#endif
         }
         __syncwarp();
       }

@@ -307,17 +307,10 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
         if (g == 0 && t + 1 < n_t) mbar_wait(&st_full[st_next], ph_next);
         tc_fence_after();
         if (elect_one()) {
-#ifdef MRB_ATTN_S_FIRST      // experiment: S^T / dP^T of the next streamed tile ahead of the accumulating MMAs
-          if (t + 1 < n_t) issue_T(g, st_next);
-          issue_acc(g, st, t > 0 ? 1u : 0u);
-          if (g == n_groups - 1) umma_commit(&st_empty[st]);
-          if (t + 1 >= n_t) umma_commit(&acc_full[g]);
-#else
           issue_acc(g, st, t > 0 ? 1u : 0u);
           if (g == n_groups - 1) umma_commit(&st_empty[st]);
           if (t + 1 < n_t) issue_T(g, st_next);
           else umma_commit(&acc_full[g]);
-#endif
         }
         __syncwarp();
       }

@@ -108,8 +108,11 @@ __global__ void gated_gelu_bwd_drop_kernel(const uint4* __restrict__ ab, const u
     const float b0 = unpack_lo(bw[i], dtype), b1 = unpack_hi(bw[i], dtype);
     const float d0 = drop1(unpack_lo(dw[i], dtype), w[i >> 1], (2 * i) & 3, d);
     const float d1 = drop1(unpack_hi(dw[i], dtype), w[i >> 1], (2 * i + 1) & 3, d);
-    oa[i] = pack2(d0 * b0 * gelu_erf_grad(a0), d1 * b1 * gelu_erf_grad(a1), dtype);
-    ob[i] = pack2(d0 * gelu_erf(a0), d1 * gelu_erf(a1), dtype);
+    float g0, g1, dg0, dg1;
+    gelu_erf_both(a0, g0, dg0);
+    gelu_erf_both(a1, g1, dg1);
+    oa[i] = pack2(d0 * b0 * dg0, d1 * b1 * dg1, dtype);
+    ob[i] = pack2(d0 * g0, d1 * g1, dtype);
   }
   dab[m * (lddab >> 3) + c] = make_uint4(oa[0], oa[1], oa[2], oa[3]);
   dab[m * (lddab >> 3) + fv + c] = make_uint4(ob[0], ob[1], ob[2], ob[3]);
@@ -532,6 +535,19 @@ __global__ void __launch_bounds__(256) lora_dx_drop_mma_kernel(const uint16_t* _
     for (int pr = 0; pr < 2; ++pr) {                                // two 16-column tile pairs of the warp's 32 columns
       const int kp0 = kc0 + 16 * pr, kth = kp0 + 4 * t;             // this thread's 4 output columns
       float s0[4] = {0.f, 0.f, 0.f, 0.f}, s1[4] = {0.f, 0.f, 0.f, 0.f};
+      // the read half of the read-modify-write goes out BEFORE the mask / mma work below (it used to follow it: every warp then sat
+      // on one exposed global round trip per 16 x 16 outputs)
+      float4 old32[2] = {make_float4(0.f, 0.f, 0.f, 0.f), make_float4(0.f, 0.f, 0.f, 0.f)};
+      uint2 old16[2] = {make_uint2(0u, 0u), make_uint2(0u, 0u)};
+      if (kth < K) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int r = h ? r1 : r0;
+          if (!(h ? ok1 : ok0)) continue;
+          if (F32OUT) old32[h] = *reinterpret_cast<const float4*>(static_cast<const float*>(dx) + static_cast<long long>(r) * lddx + kth);
+          else old16[h] = *reinterpret_cast<const uint2*>(static_cast<const uint16_t*>(dx) + static_cast<long long>(r) * lddx + kth);
+        }
+      }
 #pragma unroll
       for (int j = 0; j < NL; ++j) {
         const uint16_t* at = At + (j * 256 + (kp0 - cb) + coln) * 8 + 2 * t;
@@ -556,12 +572,12 @@ __global__ void __launch_bounds__(256) lora_dx_drop_mma_kernel(const uint16_t* _
         const float* sv = h ? s1 : s0;
         if (F32OUT) {
           float4* pp = reinterpret_cast<float4*>(static_cast<float*>(dx) + static_cast<long long>(r) * lddx + kth);
-          float4 a = *pp;
+          float4 a = old32[h];
           a.x += sv[0] * d.scale; a.y += sv[1] * d.scale; a.z += sv[2] * d.scale; a.w += sv[3] * d.scale;
           *pp = a;
         } else {
           uint2* pp = reinterpret_cast<uint2*>(static_cast<uint16_t*>(dx) + static_cast<long long>(r) * lddx + kth);
-          const uint2 v = *pp;
+          const uint2 v = old16[h];
           *pp = make_uint2(pack2(unpack_lo(v.x, dtype) + sv[0] * d.scale, unpack_hi(v.x, dtype) + sv[1] * d.scale, dtype),
                            pack2(unpack_lo(v.y, dtype) + sv[2] * d.scale, unpack_hi(v.y, dtype) + sv[3] * d.scale, dtype));
         }
@@ -705,7 +721,7 @@ extern "C" int mrb_lora_dx_drop(const void* q, long long ldq, const void* A, lon
       bad16(q) || bad16(A) || bad16(dx) || p < 0.f || p >= 1.f)
     return MRB_ERR_ARG;
   const DropSpec d = make_drop(seed, site0, p);
-  const int rows_per_block = M <= 1024 ? 16 : 64;
+  const int rows_per_block = M <= 1024 ? 16 : 128;       // the A^T staging of a block is amortised over 8 row steps
   dim3 grid(blocks_for(K, 256), blocks_for(M, rows_per_block));
   const uint16_t* qp = static_cast<const uint16_t*>(q);
   const uint16_t* Ap = static_cast<const uint16_t*>(A);

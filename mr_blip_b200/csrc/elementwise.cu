@@ -74,6 +74,85 @@ __global__ void __launch_bounds__(256) norm_kernel(const float* __restrict__ x, 
   }
 }
 
+// Same arithmetic (two-pass mean / centred variance), one BLOCK per row for the encoder- / ViT-sized calls: 256 threads x <= 2 float4,
+// every load of a thread (x, add, w, bias) issued up front, 64 warps per SM instead of 8-16 (the warp-per-row kernel holds a whole
+// row in up to 64 registers per lane), row sums through shared memory in a fixed order.
+__global__ void __launch_bounds__(256) norm_row_kernel(const float* __restrict__ x, const float* __restrict__ add,
+                                                       const float* __restrict__ w, const float* __restrict__ bias, float eps,
+                                                       int rows, int C, int mode, float* __restrict__ out_f32,
+                                                       void* __restrict__ out_h, int h_dtype, long long ld_h,
+                                                       float* __restrict__ sum_out) {
+  mrb::pdl_trigger();
+  mrb::pdl_wait();      // before the first global access (common.cuh, MRB_PDL)
+  __shared__ float red[2][8];
+  const int row = blockIdx.x, nv = C >> 2, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const float4* xr = reinterpret_cast<const float4*>(x + static_cast<long long>(row) * C);
+  const float4* ar = add ? reinterpret_cast<const float4*>(add + static_cast<long long>(row) * C) : nullptr;
+  const float4* wr = reinterpret_cast<const float4*>(w);
+  const float4* br = bias ? reinterpret_cast<const float4*>(bias) : nullptr;
+  float4 v[2], ww[2], bb[2];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const int c = threadIdx.x + i * 256;
+    v[i] = ww[i] = bb[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (c < nv) {
+      v[i] = xr[c];
+      ww[i] = wr[c];
+      if (br) bb[i] = br[c];
+      if (ar) { const float4 a = ar[c]; v[i].x += a.x; v[i].y += a.y; v[i].z += a.z; v[i].w += a.w; }
+      s += v[i].x + v[i].y + v[i].z + v[i].w;
+    }
+  }
+  if (sum_out) {   // x + add is also the next residual stream
+    float4* so = reinterpret_cast<float4*>(sum_out + static_cast<long long>(row) * C);
+#pragma unroll
+    for (int i = 0; i < 2; ++i) { const int c = threadIdx.x + i * 256; if (c < nv) so[c] = v[i]; }
+  }
+  float mean = 0.f;
+  if (mode == 0) {
+    s = warp_sum(s);
+    if (lane == 0) red[0][warp] = s;
+    __syncthreads();
+    float t = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) t += red[0][k];
+    mean = t / C;
+  }
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const int c = threadIdx.x + i * 256;
+    if (c < nv) {
+      const float a = v[i].x - mean, b = v[i].y - mean, cc = v[i].z - mean, d = v[i].w - mean;
+      q += a * a + b * b + cc * cc + d * d;
+    }
+  }
+  q = warp_sum(q);
+  if (lane == 0) red[1][warp] = q;
+  __syncthreads();
+  float qt = 0.f;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) qt += red[1][k];
+  const float rstd = rsqrtf(qt / C + eps);
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const int c = threadIdx.x + i * 256;
+    if (c < nv) {
+      float4 y;
+      y.x = (v[i].x - mean) * rstd * ww[i].x + bb[i].x; y.y = (v[i].y - mean) * rstd * ww[i].y + bb[i].y;
+      y.z = (v[i].z - mean) * rstd * ww[i].z + bb[i].z; y.w = (v[i].w - mean) * rstd * ww[i].w + bb[i].w;
+      if (out_f32) reinterpret_cast<float4*>(out_f32 + static_cast<long long>(row) * C)[c] = y;
+      if (out_h) {
+        uint2 pk;
+        pk.x = pack2(y.x, y.y, h_dtype);
+        pk.y = pack2(y.z, y.w, h_dtype);
+        reinterpret_cast<uint2*>(static_cast<uint16_t*>(out_h) + static_cast<long long>(row) * ld_h)[c] = pk;
+      }
+    }
+  }
+}
+
 // RMSNorm backward: dres[row] += rstd * (w*dy) - x * rstd^3 * mean(w*dy*x)       (weights frozen: no dw)
 // dy: fp32 or 16-bit [rows, ld]; when A != null the LoRA input gradient is folded in first:
 //     dy_eff[k] = dy[k] + sum_r dy[C + r] * A[r, k]      (dy is then an "extended" dgrad buffer [rows, C+32])
@@ -130,6 +209,63 @@ __global__ void __launch_bounds__(256) rmsnorm_bwd_kernel(const float* __restric
     const int c = lane + i * 32;
     if (c < nv) {
       float4 o = out[c];
+      o.x += gv[i].x * rstd - xv[i].x * coef; o.y += gv[i].y * rstd - xv[i].y * coef;
+      o.z += gv[i].z * rstd - xv[i].z * coef; o.w += gv[i].w * rstd - xv[i].w * coef;
+      out[c] = o;
+    }
+  }
+}
+
+// Same arithmetic, one BLOCK per row (256 threads x <= 2 float4 each) for the encoder-sized calls (8192 rows x 2048): the warp-per-row
+// kernel above keeps x and w*dy of a whole row in 128 registers, runs 8 warps per SM and reads dres only after both reductions --
+// 103 us for 235 MB (2.3 TB/s, profiles/launch_summary_r02d.csv).  Here every load of a thread (x, dy, w, dres) is issued up front,
+// 64 warps fit an SM, and the two row sums meet in shared memory in a fixed order.
+__global__ void __launch_bounds__(256) rmsnorm_bwd_row_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                              const void* __restrict__ dy, int dy_dtype, long long ld, float eps,
+                                                              int rows, int C, float* __restrict__ dres) {
+  mrb::pdl_trigger();
+  mrb::pdl_wait();      // before the first global access (common.cuh, MRB_PDL)
+  __shared__ float red[2][8];
+  const int row = blockIdx.x, nv = C >> 2, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const float4* xr = reinterpret_cast<const float4*>(x + static_cast<long long>(row) * C);
+  const float4* wr = reinterpret_cast<const float4*>(w);
+  float4* out = reinterpret_cast<float4*>(dres + static_cast<long long>(row) * C);
+  float4 xv[2], gv[2], ov[2];
+  float ss = 0.f, dot = 0.f;
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const int c = threadIdx.x + i * 256;
+    xv[i] = gv[i] = ov[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (c < nv) {
+      xv[i] = xr[c];
+      ov[i] = out[c];
+      float4 d;
+      if (dy_dtype == MRB_DT_F32) {
+        d = reinterpret_cast<const float4*>(static_cast<const float*>(dy) + static_cast<long long>(row) * ld)[c];
+      } else {
+        const uint2 pk = reinterpret_cast<const uint2*>(static_cast<const uint16_t*>(dy) + static_cast<long long>(row) * ld)[c];
+        d = make_float4(unpack_lo(pk.x, dy_dtype), unpack_hi(pk.x, dy_dtype), unpack_lo(pk.y, dy_dtype), unpack_hi(pk.y, dy_dtype));
+      }
+      const float4 ww = wr[c];
+      gv[i] = make_float4(d.x * ww.x, d.y * ww.y, d.z * ww.z, d.w * ww.w);
+      ss += xv[i].x * xv[i].x + xv[i].y * xv[i].y + xv[i].z * xv[i].z + xv[i].w * xv[i].w;
+      dot += gv[i].x * xv[i].x + gv[i].y * xv[i].y + gv[i].z * xv[i].z + gv[i].w * xv[i].w;
+    }
+  }
+  ss = warp_sum(ss);
+  dot = warp_sum(dot);
+  if (lane == 0) { red[0][warp] = ss; red[1][warp] = dot; }
+  __syncthreads();
+  float sst = 0.f, dott = 0.f;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) { sst += red[0][k]; dott += red[1][k]; }
+  const float rstd = rsqrtf(sst / C + eps);
+  const float coef = dott / C * rstd * rstd * rstd;
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const int c = threadIdx.x + i * 256;
+    if (c < nv) {
+      float4 o = ov[i];
       o.x += gv[i].x * rstd - xv[i].x * coef; o.y += gv[i].y * rstd - xv[i].y * coef;
       o.z += gv[i].z * rstd - xv[i].z * coef; o.w += gv[i].w * rstd - xv[i].w * coef;
       out[c] = o;
@@ -289,8 +425,11 @@ __global__ void gated_gelu_bwd_kernel(const uint4* __restrict__ ab, const uint4*
     const float a0 = unpack_lo(aw[i], dtype), a1 = unpack_hi(aw[i], dtype);
     const float b0 = unpack_lo(bw[i], dtype), b1 = unpack_hi(bw[i], dtype);
     const float d0 = unpack_lo(dw[i], dtype), d1 = unpack_hi(dw[i], dtype);
-    oa[i] = pack2(d0 * b0 * gelu_erf_grad(a0), d1 * b1 * gelu_erf_grad(a1), dtype);
-    ob[i] = pack2(d0 * gelu_erf(a0), d1 * gelu_erf(a1), dtype);
+    float g0, g1, dg0, dg1;
+    gelu_erf_both(a0, g0, dg0);
+    gelu_erf_both(a1, g1, dg1);
+    oa[i] = pack2(d0 * b0 * dg0, d1 * b1 * dg1, dtype);
+    ob[i] = pack2(d0 * g0, d1 * g1, dtype);
   }
   dab[m * (lddab >> 3) + c] = make_uint4(oa[0], oa[1], oa[2], oa[3]);
   dab[m * (lddab >> 3) + fv + c] = make_uint4(ob[0], ob[1], ob[2], ob[3]);
@@ -707,6 +846,13 @@ extern "C" int mrb_norm(const float* x, const float* add, const float* w, const 
                         int mode, float* out_f32, void* out_h, int h_dtype, long long ld_h, float* sum_out, void* stream) {
   if (rows <= 0) return MRB_OK;
   if ((C & 3) || C > 2048 || (out_h && (ld_h & 3))) return MRB_ERR_ARG;
+  static int row_kernel = -1;             // MRB_NORM_ROW=0 keeps the warp-per-row kernel for large inputs (A/B measurements)
+  if (row_kernel < 0) { const char* e = getenv("MRB_NORM_ROW"); row_kernel = (e && e[0] == '0') ? 0 : 1; }
+  if (row_kernel && rows > 2 * 148) {
+    MRB_LAUNCH((norm_row_kernel), rows, 256, 0, STREAM, x, add, w, bias, eps, rows, C, mode, out_f32, out_h, h_dtype, ld_h, sum_out);
+    MRB_CHECK_LAUNCH();
+    return MRB_OK;
+  }
   const int nw = norm_warps(rows);
   const unsigned grid = blocks_for(rows, nw);
   if (C <= 1024) MRB_LAUNCH((norm_kernel<8>), grid, 32 * nw, 0, STREAM, x, add, w, bias, eps, rows, C, mode, out_f32, out_h, h_dtype, ld_h, sum_out);
@@ -720,6 +866,13 @@ extern "C" int mrb_rmsnorm_bwd(const float* x, const float* w, const void* dy, i
                                const float* lora_A, int R, float eps, int rows, int C, float* dres, void* stream) {
   if (rows <= 0) return MRB_OK;
   if ((C & 3) || C > 2048 || (ld_dy & 3) || R > 32 || (lora_A && dy_dtype == MRB_DT_F32)) return MRB_ERR_ARG;
+  static int row_kernel = -1;             // MRB_RMSNORM_BWD_ROW=0 keeps the warp-per-row kernel for large inputs (A/B measurements)
+  if (row_kernel < 0) { const char* e = getenv("MRB_RMSNORM_BWD_ROW"); row_kernel = (e && e[0] == '0') ? 0 : 1; }
+  if (row_kernel && !lora_A && rows > 2 * 148) {
+    MRB_LAUNCH((rmsnorm_bwd_row_kernel), rows, 256, 0, STREAM, x, w, dy, dy_dtype, ld_dy, eps, rows, C, dres);
+    MRB_CHECK_LAUNCH();
+    return MRB_OK;
+  }
   MRB_LAUNCH((rmsnorm_bwd_kernel<16>), blocks_for(rows, norm_warps(rows)), 32 * norm_warps(rows), 0, STREAM, x, w, dy, dy_dtype, ld_dy, lora_A, R, eps, rows, C, dres);
   MRB_CHECK_LAUNCH();
   return MRB_OK;

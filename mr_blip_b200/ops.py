@@ -11,7 +11,7 @@ F16, BF16, F32 = 0, 1, 2
 _DT = {torch.float16: F16, torch.bfloat16: BF16, torch.float32: F32}
 INT_MIN = -2 ** 31
 USE_TC_ATTENTION = True
-USE_FQ_ATTENTION = os.environ.get("MRB_ATTN_FQ", "1") != "0"       # 0: decoder cross-attention through the tcgen05 kernels (round-2 first path)
+USE_FQ_ATTENTION = os.environ.get("MRB_ATTN_FQ", "0") == "1"       # 1: decoder cross-attention through the few-query kernels (measured slower, off)
 USE_VIT_ATTENTION = os.environ.get("MRB_ATTN_VIT", "1") != "0"     # 0: the generic flash kernel + the single-row kernel (round 1 path)
 GEMM_PROFILE = None      # set to a list to record (M, N, K, cuda start event, cuda end event) per GEMM launch
 

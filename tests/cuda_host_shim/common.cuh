@@ -235,6 +235,7 @@ inline float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.7071067811
 inline float gelu_erf_grad(float x) {
   return 0.5f * (1.0f + erff(x * 0.70710678118654752f)) + x * 0.3989422804014327f * expf(-0.5f * x * x);
 }
+inline void gelu_erf_both(float x, float& g, float& dg) { g = gelu_erf(x); dg = gelu_erf_grad(x); }
 }  // namespace mrb
 
 inline float __half2float(__half h) { return mrb::f16_to_f(h.x); }

@@ -116,7 +116,12 @@ def test_full_depth_parity_vs_fp32_oracle_and_eager_autocast(full, name, frames,
                      "loss_eager_autocast": eag["loss"], "err_cuda_vs_fp32": e_cuda, "err_eager_autocast_vs_fp32": e_eager,
                      "gate": "err_cuda <= %.1f x err_eager" % GATE}
     print(json.dumps(RESULTS[name], indent=1))
-    bad = {k: (e_cuda[k], e_eager[k]) for k in e_cuda if e_cuda[k] > GATE * e_eager[k] + 1e-6}
+    # The eager regime returns its loss as an fp16 number (resolution 2^-7 at |loss| ~ 11: 10.796875, 11.1953125), so its own "error"
+    # of 1.4e-4 - 3.2e-4 is wherever the rounding happened to land inside half a unit (3.6e-4 relative); the product's fp32 loss moves
+    # by +-1.5e-4 with nothing but the summation order of a norm kernel (measured: 1.47e-4 <-> 2.48e-4, 2.97e-4 <-> 3.5e-5).  The
+    # scalar is therefore gated against that resolution; tensors (embeddings, logits, gradients) are gated against the measured error.
+    floor = {"loss": 0.5 * 2.0 ** -7 / abs(ref["loss"])}
+    bad = {k: (e_cuda[k], e_eager[k]) for k in e_cuda if e_cuda[k] > GATE * max(e_eager[k], floor.get(k, 0.0)) + 1e-6}
     assert not bad, "product further from the fp32 oracle than %.1f x the reference's own autocast regime: %s" % (GATE, bad)
     # absolute sanity at full depth (bf16 operands through 24 + 24 layers); the 2-layer tolerances of test_model_gpu.py do not apply
     assert e_cuda["qformer"] < 5e-3 and e_cuda["logits"] < 5e-2 and e_cuda["loss"] < 2e-3, e_cuda

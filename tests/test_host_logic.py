@@ -1262,6 +1262,28 @@ def test_elementwise_kernel_source_runs_on_host_shim(elementwise_kernels_on_host
     dres = torch.ones(rows, C)
     assert lib.mrb_rmsnorm_bwd(P(x), P(w), P(dy), BF, c_ll(C), None, 0, c_f(1e-6), rows, C, P(dres), None) == 0
     assert _relfro(dres - 1.0, xr.grad) < 1e-4
+    # encoder- / ViT-sized row counts take the one-block-per-row kernels (norm_row_kernel, rmsnorm_bwd_row_kernel): same arithmetic
+    rows3, C3 = 299, 1408
+    x3, a3, w3, b3 = (torch.randn(rows3, C3, generator=g) + 3.0, torch.randn(rows3, C3, generator=g), torch.randn(C3, generator=g),
+                      torch.randn(C3, generator=g))
+    o3, oh3, sum3 = torch.empty(rows3, C3), torch.zeros((rows3, C3 + 8), dtype=torch.float16), torch.empty(rows3, C3)
+    assert lib.mrb_norm(P(x3), P(a3), P(w3), P(b3), c_f(1e-6), rows3, C3, 0, P(o3), P(oh3), F16, c_ll(C3 + 8), P(sum3), None) == 0
+    want3 = torch.nn.functional.layer_norm(x3 + a3, (C3,), w3, b3, 1e-6)
+    assert _relfro(o3, want3) < 1e-5 and _relfro(oh3[:, :C3], want3) < 1e-3 and oh3[:, C3:].abs().max().item() == 0
+    assert torch.equal(sum3, x3 + a3)
+    x4, w4 = torch.randn(rows3, 2048, generator=g), torch.randn(2048, generator=g)
+    ob4 = torch.zeros((rows3, 2048 + 32), dtype=torch.bfloat16)
+    assert lib.mrb_norm(P(x4), None, P(w4), None, c_f(1e-6), rows3, 2048, 1, None, P(ob4), BF, c_ll(2048 + 32), None, None) == 0
+    assert _relfro(ob4[:, :2048], w4 * (x4 * torch.rsqrt(x4.pow(2).mean(-1, keepdim=True) + 1e-6))) < 4e-3
+    for rows2, C2 in ((300, 2048), (297, 1000)):
+        x2, w2 = torch.randn(rows2, C2, generator=g), torch.randn(C2, generator=g)
+        x2r = x2.clone().requires_grad_(True)
+        y2 = w2 * (x2r * torch.rsqrt(x2r.pow(2).mean(-1, keepdim=True) + 1e-6))
+        dy2 = torch.randn(rows2, C2, generator=g).to(torch.bfloat16)
+        y2.backward(dy2.float())
+        dres2 = torch.ones(rows2, C2)
+        assert lib.mrb_rmsnorm_bwd(P(x2), P(w2), P(dy2), BF, c_ll(C2), None, 0, c_f(1e-6), rows2, C2, P(dres2), None) == 0
+        assert _relfro(dres2 - 1.0, x2r.grad) < 1e-4
     # ---- gated GELU forward / backward
     M, Fd = 7, 5120
     ab = torch.randn(M, 2 * Fd, generator=g).to(torch.bfloat16)
