@@ -86,9 +86,11 @@ struct BwdSmem {
   static constexpr int OFF_X = 0;                          // [group][X, Y]
   static constexpr int OFF_U = 4 * X_BYTES;                // [stage][U, W]
   static constexpr int OFF_E = OFF_U + STAGES * 2 * U_BYTES;   // [group][P, dS] 128 x 64 16-bit operand tiles
-  static constexpr int OFF_WIN = OFF_E + 4 * X_BYTES;      // 8 warps x (96 bias + 64 lse + 64 delta) floats
+  static constexpr int EW = 16;                            // elementwise warps: 2 groups x 4 TMEM lane quadrants x 2 column halves
+  static constexpr int THREADS = (2 + EW) * 32;
+  static constexpr int OFF_WIN = OFF_E + 4 * X_BYTES;      // EW warps x (96 bias + 64 lse + 64 delta) floats
   static constexpr int WIN_FLOATS = 96 + 64 + 64;
-  static constexpr int OFF_BAR = OFF_WIN + 8 * WIN_FLOATS * 4;
+  static constexpr int OFF_BAR = OFF_WIN + EW * WIN_FLOATS * 4;
   static constexpr int NBAR = 1 + 2 * STAGES + 6;
   static constexpr int TOTAL = OFF_BAR + NBAR * 8 + 16 + 1024;
 };
@@ -105,17 +107,21 @@ template <int MODE, bool HAS_BIAS, bool MASKED, bool DROP = false>
 __device__ __forceinline__ void bwd_tile_rows(uint32_t lane_base, const float* wrow, const float* wlse, const float* wdl,
                                               float off, float dls, float sl2, float scale, uint32_t cm0, uint32_t cm1,
                                               bool row_key_ok, bool causal, int u0, int row_c, int q_pos0, uint8_t* prow,
-                                              int r, int dt, const BwdDrop& dd = BwdDrop()) {
+                                              int r, int dt, int cbeg, const BwdDrop& dd = BwdDrop()) {
+  // this warp's half of the streamed tile: columns [cbeg, cbeg + 32) in two 16-column steps (48 live registers per step instead of
+  // 96: the kernel runs 18 warps per CTA, i.e. at most 112 registers per thread)
 #pragma unroll
-  for (int c0 = 0; c0 < TT; c0 += 32) {
-    uint32_t sv[32], dv[32];
-    tmem_ld_32x32b_x32(lane_base + c0, sv);
-    tmem_ld_32x32b_x32(lane_base + 64 + c0, dv);
+  for (int cs = 0; cs < 32; cs += 16) {
+    const int c0 = cbeg + cs;
+    uint32_t sv[16], dv[16];
+    tmem_ld_32x32b_x16(lane_base + c0, sv);
+    tmem_ld_32x32b_x16(lane_base + 64 + c0, dv);
     tmem_ld_wait();
-    const uint32_t cm = c0 == 0 ? cm0 : cm1;
-    uint32_t pp[16], pd[16];
+    const uint32_t cm = c0 < 32 ? cm0 : cm1;
+    const int cb = c0 & 31;                   // bit of column c0 in cm
+    uint32_t pp[8], pd[8];
 #pragma unroll
-    for (int e8 = 0; e8 < 32; e8 += 8) {
+    for (int e8 = 0; e8 < 16; e8 += 8) {
       float off8[8], dl8[8];                  // DKV: (bias const - lse) and delta * scale of 8 streamed queries, broadcast loads
       if (MODE == MODE_DKV) {
         const float4 la = *reinterpret_cast<const float4*>(wlse + c0 + e8), lb = *reinterpret_cast<const float4*>(wlse + c0 + e8 + 4);
@@ -163,7 +169,7 @@ __device__ __forceinline__ void bwd_tile_rows(uint32_t lane_base, const float* w
           float pv = ex2b(fmaf(__uint_as_float(sv[e + q]), sl2, o));
           if (MASKED) {
             bool ok;
-            if (MODE == MODE_DQ) ok = ((cm >> (e + q)) & 1u) && !(causal && u0 + c > row_c + q_pos0);
+            if (MODE == MODE_DQ) ok = ((cm >> (cb + e + q)) & 1u) && !(causal && u0 + c > row_c + q_pos0);
             else ok = row_key_ok && !(causal && row_c > u0 + c + q_pos0);
             pv = ok ? pv : 0.f;
           }
@@ -175,7 +181,7 @@ __device__ __forceinline__ void bwd_tile_rows(uint32_t lane_base, const float* w
       }
     }
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
+    for (int q = 0; q < 2; ++q) {
       const int chunk = (c0 >> 3) + q;
       const int o16 = (chunk ^ (r & 7)) << 4;
       if (MODE == MODE_DKV)
@@ -188,7 +194,7 @@ __device__ __forceinline__ void bwd_tile_rows(uint32_t lane_base, const float* w
 // ENC = the encoder self-attention case that carries almost all of the time (bucketed bias, no causal mask, bf16): those
 // three facts become compile-time constants so the per-element loop has no uniform branches left.
 template <int MODE, bool ENC, bool DROP = false>
-__global__ void __launch_bounds__(320, 1)
+__global__ void __launch_bounds__(BwdSmem::THREADS, 1)
 attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmY,
                    const __grid_constant__ CUtensorMap tmU, const __grid_constant__ CUtensorMap tmW,
                    const typename BwdParamsOf<DROP>::type p) {
@@ -223,7 +229,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
     tma_prefetch_desc(&tmX); tma_prefetch_desc(&tmY); tma_prefetch_desc(&tmU); tma_prefetch_desc(&tmW);
     mbar_init(x_full, 1);
     for (int s = 0; s < STAGES; ++s) { mbar_init(&st_full[s], 1); mbar_init(&st_empty[s], 1); }
-    for (int g = 0; g < 2; ++g) { mbar_init(&t_full[g], 1); mbar_init(&e_full[g], 4); mbar_init(&acc_full[g], 1); }
+    for (int g = 0; g < 2; ++g) { mbar_init(&t_full[g], 1); mbar_init(&e_full[g], S::EW / 2); mbar_init(&acc_full[g], 1); }
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_holder, TMEM_COLS);
@@ -318,8 +324,13 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
       if (++st_next == STAGES) { st_next = 0; ph_next ^= 1; }
     }
   } else {
-    // ===================== elementwise groups: one thread per stationary row =====================
-    const int g = (warp - 2) >> 2;
+    // ===================== elementwise groups: TWO threads per stationary row =====================
+    // Warps 2-9 take columns [0, 32) of their group's 128 x 64 streamed tile, warps 10-17 columns [32, 64) (a warp reads the TMEM
+    // lanes of quadrant warp % 4, so warps w and w + 8 share their 32 rows).  The backward has no row reductions -- every element
+    // of P / dS is a function of its own S, dP and the row / column constants -- so the split needs no exchange; what it buys is
+    // four resident elementwise warps per scheduler instead of two for a loop that was bound by its own latency (tensor pipe 31-34 %,
+    // issue slots 40 %: profiles/ncu_attn_t5_r02d.md).
+    const int ew = warp - 2, g = (ew >> 2) & 1, cbeg = (ew >> 3) * 32;
     if (g < n_groups) {
       const int quad = warp & 3;
       const int r = quad * 32 + lane;
@@ -437,11 +448,11 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
         tc_fence_after();
         // warp-uniform dispatch (tcgen05.ld inside is warp-collective)
         if (vbias) {
-          if (masked) bwd_tile_rows<MODE, true, true, DROP>(lane_base, wrow, wlse, wdl, off, dls, sl2, tile_scale, cm0, cm1, row_key_ok, causal, u0, row_c, p.q_pos0, prow, r, dt, dd);
-          else bwd_tile_rows<MODE, true, false, DROP>(lane_base, wrow, wlse, wdl, off, dls, sl2, tile_scale, cm0, cm1, row_key_ok, causal, u0, row_c, p.q_pos0, prow, r, dt, dd);
+          if (masked) bwd_tile_rows<MODE, true, true, DROP>(lane_base, wrow, wlse, wdl, off, dls, sl2, tile_scale, cm0, cm1, row_key_ok, causal, u0, row_c, p.q_pos0, prow, r, dt, cbeg, dd);
+          else bwd_tile_rows<MODE, true, false, DROP>(lane_base, wrow, wlse, wdl, off, dls, sl2, tile_scale, cm0, cm1, row_key_ok, causal, u0, row_c, p.q_pos0, prow, r, dt, cbeg, dd);
         } else {
-          if (masked) bwd_tile_rows<MODE, false, true, DROP>(lane_base, wrow, wlse, wdl, off, dls, sl2, tile_scale, cm0, cm1, row_key_ok, causal, u0, row_c, p.q_pos0, prow, r, dt, dd);
-          else bwd_tile_rows<MODE, false, false, DROP>(lane_base, wrow, wlse, wdl, off, dls, sl2, tile_scale, cm0, cm1, row_key_ok, causal, u0, row_c, p.q_pos0, prow, r, dt, dd);
+          if (masked) bwd_tile_rows<MODE, false, true, DROP>(lane_base, wrow, wlse, wdl, off, dls, sl2, tile_scale, cm0, cm1, row_key_ok, causal, u0, row_c, p.q_pos0, prow, r, dt, cbeg, dd);
+          else bwd_tile_rows<MODE, false, false, DROP>(lane_base, wrow, wlse, wdl, off, dls, sl2, tile_scale, cm0, cm1, row_key_ok, causal, u0, row_c, p.q_pos0, prow, r, dt, cbeg, dd);
         }
         fence_proxy_async();
         tc_fence_before();
@@ -458,8 +469,8 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
         const long long bs = (MODE == MODE_DKV && a == 0) ? p.o2_bs : p.o1_bs;
         const long long rs = (MODE == MODE_DKV && a == 0) ? p.o2_rs : p.o1_rs;
         uint16_t* orow = static_cast<uint16_t*>(outp) + b * bs + static_cast<long long>(row_c) * rs + static_cast<long long>(h) * BHD;
-#pragma unroll
-        for (int c0 = 0; c0 < BHD; c0 += 32) {
+        {
+          const int c0 = cbeg;                                  // this warp's half of the 64 accumulator columns
           uint32_t v[32];
           tmem_ld_32x32b_x32(lane_base + 128 + a * 64 + c0, v);
           tmem_ld_wait();
@@ -556,7 +567,7 @@ static int launch_bwd_tc2(const CUtensorMap& x, const CUtensorMap& y, const CUte
     cfg = true;
   }
   dim3 grid((Lstat + 2 * TS - 1) / (2 * TS), p.H, p.B);
-  MRB_LAUNCH((attn_bwd_tc_kernel<MODE, ENC, DROP>), grid, 320, BwdSmem::TOTAL, s, x, y, u, w,
+  MRB_LAUNCH((attn_bwd_tc_kernel<MODE, ENC, DROP>), grid, BwdSmem::THREADS, BwdSmem::TOTAL, s, x, y, u, w,
              static_cast<const typename BwdParamsOf<DROP>::type&>(p));
   MRB_CHECK_LAUNCH();
   return MRB_OK;
