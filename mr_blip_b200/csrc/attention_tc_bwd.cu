@@ -79,6 +79,28 @@ __host__ __device__ constexpr uint32_t idesc_b(int fmt, int M, int N, int b_mn_m
          (static_cast<uint32_t>(b_mn_major) << 16) | (static_cast<uint32_t>(N >> 3) << 17) | (static_cast<uint32_t>(M >> 4) << 24);
 }
 
+// D[tmem] (+)= A[tmem] * B[smem]: the 16-bit A operand (K-major: TMEM lane = row, one 32-bit column = two consecutive k) is read from
+// tensor memory -- P^T / dS^T go from the elementwise warps' registers straight back over the S^T / dP^T columns they came from
+// (tcgen05.st) and never touch shared memory: an SS-form MMA of this shape (M 128, N 64, K 16) reads 4 KB of A + 2 KB of B from
+// shared memory for 32 clk of tensor work, i.e. 192 B/clk against the 128 B/clk a CTA's shared memory delivers.
+__device__ __forceinline__ void bw_umma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accum)
+      : "memory");
+}
+__device__ __forceinline__ void bw_tmem_st_x8(uint32_t taddr, const uint32_t* r) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+               ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+               : "memory");
+}
+// first TMEM column (relative to the S^T resp. dP^T block of a group) of the packed 16-bit operand of streamed columns [c0, c0 + 16):
+// each elementwise warp writes over columns it has already read -- warps 2-9 (streamed columns 0-31) into [0, 16), warps 10-17
+// (columns 32-63) into [32, 48)
+__host__ __device__ constexpr int bw_pcol(int c0) { return c0 < 32 ? (c0 >> 1) : 32 + ((c0 - 32) >> 1); }
+
 struct BwdSmem {
   static constexpr int X_BYTES = TS * 128;                 // one stationary tile (128 rows x 64 d)
   static constexpr int U_BYTES = TT * 128;                 // one streamed tile (64 rows x 64 d)
@@ -180,15 +202,11 @@ __device__ __forceinline__ void bwd_tile_rows(uint32_t lane_base, const float* w
         pd[e >> 1] = pack2(ds[0], ds[1], dt);
       }
     }
-#pragma unroll
-    for (int q = 0; q < 2; ++q) {
-      const int chunk = (c0 >> 3) + q;
-      const int o16 = (chunk ^ (r & 7)) << 4;
-      if (MODE == MODE_DKV)
-        *reinterpret_cast<uint4*>(prow + o16) = make_uint4(pp[4 * q], pp[4 * q + 1], pp[4 * q + 2], pp[4 * q + 3]);
-      *reinterpret_cast<uint4*>(prow + BwdSmem::X_BYTES + o16) = make_uint4(pd[4 * q], pd[4 * q + 1], pd[4 * q + 2], pd[4 * q + 3]);
-    }
+    // packed pairs (streamed column 2c | 2c + 1 << 16) = the K-major TMEM operand layout; S^T / dP^T columns [c0, c0 + 16) were read above
+    if (MODE == MODE_DKV) bw_tmem_st_x8(lane_base + bw_pcol(c0), pp);
+    bw_tmem_st_x8(lane_base + 64 + bw_pcol(c0), pd);
   }
+  tmem_st_wait();
 }
 
 // ENC = the encoder self-attention case that carries almost all of the time (bucketed bias, no causal mask, bf16): those
@@ -286,17 +304,17 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
       umma_commit(&t_full[g]);
     };
     auto issue_acc = [&](int g, int st, uint32_t acc) {
-      const uint64_t pd = dk0 + static_cast<uint32_t>((S::OFF_E + (2 * g) * S::X_BYTES) >> 4), sd = pd + (S::X_BYTES >> 4);   // P, dS
       const uint64_t um = dm0 + static_cast<uint32_t>((S::OFF_U + st * 2 * S::U_BYTES) >> 4), wm = um + (S::U_BYTES >> 4);
+      const uint32_t pt = tmem_base + g * 256, st_ = pt + 64;          // packed P^T over the S^T columns, dS^T over the dP^T columns
       const uint32_t a1 = tmem_base + g * 256 + 128, a2 = a1 + 64;
       if (MODE == MODE_DKV) {
 #pragma unroll
-        for (int k = 0; k < 4; ++k) umma_f16(a1, pd + 2 * k, wm + 128 * k, id_a, (k > 0) ? 1u : acc);      // dV += P^T dO_t
+        for (int k = 0; k < 4; ++k) bw_umma_ts(a1, pt + bw_pcol(16 * k), wm + 128 * k, id_a, (k > 0) ? 1u : acc);      // dV += P^T dO_t
 #pragma unroll
-        for (int k = 0; k < 4; ++k) umma_f16(a2, sd + 2 * k, um + 128 * k, id_a, (k > 0) ? 1u : acc);      // dK += dS^T Q_t
+        for (int k = 0; k < 4; ++k) bw_umma_ts(a2, st_ + bw_pcol(16 * k), um + 128 * k, id_a, (k > 0) ? 1u : acc);     // dK += dS^T Q_t
       } else {
 #pragma unroll
-        for (int k = 0; k < 4; ++k) umma_f16(a1, sd + 2 * k, um + 128 * k, id_a, (k > 0) ? 1u : acc);      // dQ += dS K_t
+        for (int k = 0; k < 4; ++k) bw_umma_ts(a1, st_ + bw_pcol(16 * k), um + 128 * k, id_a, (k > 0) ? 1u : acc);     // dQ += dS K_t
       }
     };
     mbar_wait(x_full, 0);
@@ -454,8 +472,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
           if (masked) bwd_tile_rows<MODE, false, true, DROP>(lane_base, wrow, wlse, wdl, off, dls, sl2, tile_scale, cm0, cm1, row_key_ok, causal, u0, row_c, p.q_pos0, prow, r, dt, cbeg, dd);
           else bwd_tile_rows<MODE, false, false, DROP>(lane_base, wrow, wlse, wdl, off, dls, sl2, tile_scale, cm0, cm1, row_key_ok, causal, u0, row_c, p.q_pos0, prow, r, dt, cbeg, dd);
         }
-        fence_proxy_async();
-        tc_fence_before();
+        tc_fence_before();                                  // the operand tiles were written with tcgen05.st (waited for in bwd_tile_rows)
         __syncwarp();
         if (lane == 0) mbar_arrive(&e_full[g]);
       }
