@@ -45,7 +45,7 @@ CONFIGS = {
                      beams=4, max_new_tokens=50, metric="video_clips_per_sec_generate_beam4_t60",
                      what="generate: batch 16 per GPU, 60 frames, T5 beam search (4 beams, 50 new tokens max)"),
 }
-NCU_FC1_TRAFFIC = 920.2e6          # dram__bytes_read.sum + dram__bytes_write.sum, one fc1 launch (profiles/ncu_gemm2_fc1_r01c.csv)
+NCU_FC1_TRAFFIC = 924.1e6          # dram__bytes_read.sum + dram__bytes_write.sum, one fc1 launch (profiles/ncu_gemm2_fc1_r02f.csv)
 
 _JSON_FD = None
 
@@ -467,9 +467,9 @@ def run_b200(args, cfg_name, cfg):
                             "all_gemm_launches": {"ms": all_ms, "tflops": all_flops / (all_ms / 1e3) / 1e12,
                                                   "note": "incl. the 1-CTA kernel's decoder-sized / N=32 launches"},
                             # dram__bytes_read+write of ONE launch of the dominant shape (ViT fc1, M61680 N6144 K1408, bias+GELU)
-                            # from profiles/ncu_gemm2_fc1_r01c.csv; its algorithmic bytes (A + B + C once) are 948.9e6
+                            # from profiles/ncu_gemm2_fc1_r02f.csv; its algorithmic bytes (A + B + C once) are 948.9e6
                             "traffic": NCU_FC1_TRAFFIC, "traffic_algorithmic": 948.9e6,
-                            "traffic_source": "profiles/ncu_gemm2_fc1_r01c.csv (ncu --set full, one fc1 launch; constant, not "
+                            "traffic_source": "profiles/ncu_gemm2_fc1_r02f.csv (ncu --set full, one fc1 launch; constant, not "
                                               "measured in this run)"}
         line["qformer_xattn"] = {"what": "Q-Former cross-attention path: batched K/V projection GEMM (6 layers, tcgen05) + 6 attention cores",
                                  "flops_per_step": x_flops, "ms_per_step": x_ms, "achieved": x_flops / (x_ms / 1e3) / 1e12,

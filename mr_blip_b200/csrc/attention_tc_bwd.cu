@@ -2,7 +2,7 @@
 // template.  Forward recap: S = scale*Q K^T + bias + mask, P = softmax(S), O = P V, lse = logsumexp(S).
 //   MODE_DKV  CTA owns 2 x 128 keys (two softmax groups); streams 64-query tiles (Q_t, dO_t):
 //               S^T  = K_g Q_t^T        dP^T = V_g dO_t^T           (128 x 64 fp32 tiles in TMEM)
-//               P^T  = exp(S^T - lse),  dS^T = P^T * (dP^T - delta) * scale   -> 16-bit, SWIZZLE_128B smem tiles
+//               P^T  = exp(S^T - lse),  dS^T = P^T * (dP^T - delta) * scale   -> 16-bit, packed back over the S^T / dP^T TMEM columns
 //               dV_g += P^T dO_t        dK_g += dS^T Q_t             (accumulated in TMEM over all query tiles)
 //   MODE_DQ   CTA owns 2 x 128 queries; streams 64-key tiles (K_t, V_t):
 //               S = Q_g K_t^T, dP = dO_g V_t^T, dS = P * (dP - delta) * scale,  dQ_g += dS K_t
@@ -101,24 +101,27 @@ __device__ __forceinline__ void bw_tmem_st_x8(uint32_t taddr, const uint32_t* r)
 // (columns 32-63) into [32, 48)
 __host__ __device__ constexpr int bw_pcol(int c0) { return c0 < 32 ? (c0 >> 1) : 32 + ((c0 - 32) >> 1); }
 
+#ifndef MRB_BWD_STAGES
+#define MRB_BWD_STAGES 6      // streamed-tile ring: 6 x 16 KB since the P^T / dS^T tiles left shared memory (3 stages: 0.709 / 0.928 ms per
+#endif                        // encoder layer without / with dropout, 6 stages: 0.659 / 0.876; unused padding instead: no change)
 struct BwdSmem {
   static constexpr int X_BYTES = TS * 128;                 // one stationary tile (128 rows x 64 d)
   static constexpr int U_BYTES = TT * 128;                 // one streamed tile (64 rows x 64 d)
-  static constexpr int STAGES = 3;
+  static constexpr int STAGES = MRB_BWD_STAGES;
   static constexpr int OFF_X = 0;                          // [group][X, Y]
   static constexpr int OFF_U = 4 * X_BYTES;                // [stage][U, W]
-  static constexpr int OFF_E = OFF_U + STAGES * 2 * U_BYTES;   // [group][P, dS] 128 x 64 16-bit operand tiles
   static constexpr int EW = 16;                            // elementwise warps: 2 groups x 4 TMEM lane quadrants x 2 column halves
   static constexpr int THREADS = (2 + EW) * 32;
-  static constexpr int OFF_WIN = OFF_E + 4 * X_BYTES;      // EW warps x (96 bias + 64 lse + 64 delta) floats
+  static constexpr int OFF_WIN = OFF_U + STAGES * 2 * U_BYTES;   // EW warps x (96 bias + 64 lse + 64 delta) floats (P^T / dS^T live in TMEM)
   static constexpr int WIN_FLOATS = 96 + 64 + 64;
   static constexpr int OFF_BAR = OFF_WIN + EW * WIN_FLOATS * 4;
   static constexpr int NBAR = 1 + 2 * STAGES + 6;
   static constexpr int TOTAL = OFF_BAR + NBAR * 8 + 16 + 1024;
 };
 
-// Elementwise core of one streamed tile for one stationary row (thread): P = exp2(S*sl2 + bias - lse) and
-// dS = P * (dP - delta) * scale for 64 streamed columns, written as 16-bit SWIZZLE_128B operand rows.
+// Elementwise core of one streamed tile for one stationary row (thread pair): P = exp2(S*sl2 + bias - lse) and
+// dS = P * (dP - delta) * scale for this warp's 32 of the 64 streamed columns, written as the 16-bit K-major TMEM operand of the
+// accumulating MMAs.
 //   off   : per-row constant added to every exp2 argument (DQ: [constant tile bias] - lse_row; DKV: 0, the per-column
 //           window wlse[] already holds [constant tile bias] - lse)
 //   dls   : DQ: delta_row * scale;  DKV: unused (wdl[] holds delta * scale)
@@ -128,7 +131,7 @@ struct BwdSmem {
 template <int MODE, bool HAS_BIAS, bool MASKED, bool DROP = false>
 __device__ __forceinline__ void bwd_tile_rows(uint32_t lane_base, const float* wrow, const float* wlse, const float* wdl,
                                               float off, float dls, float sl2, float scale, uint32_t cm0, uint32_t cm1,
-                                              bool row_key_ok, bool causal, int u0, int row_c, int q_pos0, uint8_t* prow,
+                                              bool row_key_ok, bool causal, int u0, int row_c, int q_pos0,
                                               int r, int dt, int cbeg, const BwdDrop& dd = BwdDrop()) {
   // this warp's half of the streamed tile: columns [cbeg, cbeg + 32) in two 16-column steps (48 live registers per step instead of
   // 96: the kernel runs 18 warps per CTA, i.e. at most 112 registers per thread)
@@ -367,7 +370,6 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
       float* win = reinterpret_cast<float*>(smem + S::OFF_WIN) + (warp - 2) * S::WIN_FLOATS;
       float* wlse = win + 96;
       float* wdl = win + 160;
-      uint8_t* prow = smem + S::OFF_E + (2 * g) * S::X_BYTES + r * 128;     // P row; dS row at + X_BYTES
       // per-row constants
       float lse_row = 0.f, dl_row = 0.f;
       bool row_key_ok = true;
@@ -466,11 +468,11 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
         tc_fence_after();
         // warp-uniform dispatch (tcgen05.ld inside is warp-collective)
         if (vbias) {
-          if (masked) bwd_tile_rows<MODE, true, true, DROP>(lane_base, wrow, wlse, wdl, off, dls, sl2, tile_scale, cm0, cm1, row_key_ok, causal, u0, row_c, p.q_pos0, prow, r, dt, cbeg, dd);
-          else bwd_tile_rows<MODE, true, false, DROP>(lane_base, wrow, wlse, wdl, off, dls, sl2, tile_scale, cm0, cm1, row_key_ok, causal, u0, row_c, p.q_pos0, prow, r, dt, cbeg, dd);
+          if (masked) bwd_tile_rows<MODE, true, true, DROP>(lane_base, wrow, wlse, wdl, off, dls, sl2, tile_scale, cm0, cm1, row_key_ok, causal, u0, row_c, p.q_pos0, r, dt, cbeg, dd);
+          else bwd_tile_rows<MODE, true, false, DROP>(lane_base, wrow, wlse, wdl, off, dls, sl2, tile_scale, cm0, cm1, row_key_ok, causal, u0, row_c, p.q_pos0, r, dt, cbeg, dd);
         } else {
-          if (masked) bwd_tile_rows<MODE, false, true, DROP>(lane_base, wrow, wlse, wdl, off, dls, sl2, tile_scale, cm0, cm1, row_key_ok, causal, u0, row_c, p.q_pos0, prow, r, dt, cbeg, dd);
-          else bwd_tile_rows<MODE, false, false, DROP>(lane_base, wrow, wlse, wdl, off, dls, sl2, tile_scale, cm0, cm1, row_key_ok, causal, u0, row_c, p.q_pos0, prow, r, dt, cbeg, dd);
+          if (masked) bwd_tile_rows<MODE, false, true, DROP>(lane_base, wrow, wlse, wdl, off, dls, sl2, tile_scale, cm0, cm1, row_key_ok, causal, u0, row_c, p.q_pos0, r, dt, cbeg, dd);
+          else bwd_tile_rows<MODE, false, false, DROP>(lane_base, wrow, wlse, wdl, off, dls, sl2, tile_scale, cm0, cm1, row_key_ok, causal, u0, row_c, p.q_pos0, r, dt, cbeg, dd);
         }
         tc_fence_before();                                  // the operand tiles were written with tcgen05.st (waited for in bwd_tile_rows)
         __syncwarp();
