@@ -77,14 +77,17 @@ __host__ __device__ constexpr uint32_t idesc_f16(int fmt, int M, int N, int a_mn
 // other runs its softmax, K/V tiles in a 2-stage ring.  G = 1 (short sequences, i.e. the ViT's 257 tokens): half the shared
 // memory and TMEM (one K and one V buffer with their own barriers), so TWO CTAs share an SM and one CTA's load / softmax
 // latency is covered by the other CTA's tensor work.
+#ifndef MRB_FWD_STAGES
+#define MRB_FWD_STAGES 2
+#endif
 template <int HD, int G>   // HD 64, or 96 (= 64-wide SW128 atom + 32-wide SW64 atom)
 struct TcSmem {
   static constexpr bool SPLIT = (HD == 96);
   static constexpr int Q_ONE = TQ * 64 * 2 + (SPLIT ? TQ * 32 * 2 : 0);       // one group's Q tile
   static constexpr int KV_ONE = TKV * 64 * 2 + (SPLIT ? TKV * 32 * 2 : 0);   // one of K or V
   static constexpr int STAGE_BYTES = 2 * KV_ONE;
-  static constexpr int STAGES = (G == 1) ? 1 : 2;                              // K+V stages held in shared memory
-  static constexpr int NBARST = 2;                                             // full / empty barrier pairs (G = 1: K and V)
+  static constexpr int STAGES = (G == 1) ? 1 : (HD == 64 ? MRB_FWD_STAGES : 2);  // K+V stages held in shared memory (hd 96: 3 would need 268 KB)
+  static constexpr int NBARST = (G == 1) ? 2 : STAGES;                         // full / empty barrier pairs (G = 1: K and V)
   static constexpr int P_BYTES = TQ * TKV * 2;                                 // two 64-key atoms, per group
   static constexpr int OFF_Q = 0;
   static constexpr int OFF_KV = G * Q_ONE;
