@@ -39,6 +39,7 @@ class VitEngine:
         # captured step) next to the tcgen05 kernel that handles the two full tiles.  MRB_OVERLAP=0 disables.
         import os
         self.overlap = os.environ.get("MRB_OVERLAP", "1") != "0"
+        self.split = self.overlap and os.environ.get("MRB_VIT_SPLIT", "0") == "1"
         self.side = torch.cuda.Stream()
         ops.splitk_register(self.side)
         self.blocks = []
@@ -56,6 +57,7 @@ class VitEngine:
     # CLIP normalisation of the video processors (lavis/processors/blip_processors.py:61-70), used when raw uint8 frames come in
     PIXEL_MEAN = (0.48145466, 0.4578275, 0.40821073)
     PIXEL_STD = (0.26862954, 0.26130258, 0.27577711)
+    SPLIT_MIN_FRAMES = 32          # two-stream block loop only when each half still fills the GPU (>= 32 frames = 8224 rows)
 
     def forward(self, image, return_all=False):
         """image fp32 [F,3,S,S] (cuda, already normalised as the dataset yields it) or raw uint8 [F,3,S,S] (normalisation
@@ -78,6 +80,27 @@ class VitEngine:
         hid = torch.empty((M, d.vit_mlp), dtype=H16, device="cuda")
         hd, Hh = d.vit_head_dim, d.vit_heads
         outs = [x.clone()] if return_all else None
+        if self.split and not return_all and F_ >= 2 * self.SPLIT_MIN_FRAMES and ops.attention_vit_ok(T, hd):
+            # Frames are independent in the ViT: the two halves of the batch run the 39 blocks on two streams (forked / joined
+            # inside the captured step).  The persistent GEMM / attention kernels of the two halves cannot share an SM (shared
+            # memory), so they alternate -- but the HBM-bound LayerNorms of one half run under the other half's tensor-core
+            # kernels, and a kernel's last partial wave is filled by the other stream's next kernel.  MRB_VIT_SPLIT=0 disables.
+            Fa = F_ // 2
+            main = torch.cuda.current_stream()
+            self.side.wait_stream(main)
+            for f0, f1, st in ((0, Fa, main), (Fa, F_, self.side)):
+                r0, r1 = f0 * T, f1 * T
+                with torch.cuda.stream(st):
+                    xs, xns, qkvs, aos, hids = x[r0:r1], xn[r0:r1], qkv[r0:r1], ao[r0:r1], hid[r0:r1]
+                    rs = 3 * W
+                    for blk in self.blocks:
+                        ops.norm(xs, blk["ln1_w"], blk["ln1_b"], d.vit_ln_eps, 0, out_h=xns)
+                        ops.gemm(xns, blk["qkv_w"], out=qkvs, bias=blk["qkv_b"])
+                        ops.attention_vit(qkvs, qkvs[:, W:], qkvs[:, 2 * W:], aos, f1 - f0, Hh, T, hd, hd ** -0.5,
+                                          (T * rs, rs), (T * rs, rs), (T * rs, rs), (T * W, W))
+                        self._tail(blk, xs, xns, aos, hids)
+            main.wait_stream(self.side)
+            return x
         for blk in self.blocks:
             ops.norm(x, blk["ln1_w"], blk["ln1_b"], d.vit_ln_eps, 0, out_h=xn)
             ops.gemm(xn, blk["qkv_w"], out=qkv, bias=blk["qkv_b"])
