@@ -285,9 +285,12 @@ __global__ void __launch_bounds__(NTHREADS) attn_fwd_kernel(const typename AttnP
 // in flight per CTA, two CTAs per SM -- the op is a pure HBM stream of the batched K/V projection), the four warps split the
 // keys in 16-key groups, each computes S / softmax partials / P.V for all 32 queries over its keys with mma.sync, and the
 // partial (max, sum, O) triples are merged through shared memory.  No loop-carried barriers, no running rescale.
-constexpr int XQ_MAXG = 5;                    // 16-key groups per warp: Lk <= 4 * 5 * 16 = 320
-template <typename T, bool DROP = false>
-__global__ void __launch_bounds__(128) attn_xq_kernel(const typename AttnParamsOf<DROP>::type p) {
+constexpr int XQ_MAX_LK = 320;
+// XW warps: 4 (five 16-key groups per warp) or 8 (three): the eight-warp form halves every warp's serial chain (S, softmax, P.V,
+// merge) and the cp.async issue per thread at the same shared memory per CTA.  MRB_XQ_WARPS=4 selects the four-warp form.
+template <typename T, bool DROP = false, int XW = 4>
+__global__ void __launch_bounds__(32 * XW) attn_xq_kernel(const typename AttnParamsOf<DROP>::type p) {
+  constexpr int XQ_MAXG = (XQ_MAX_LK / 16 + XW - 1) / XW, NT = 32 * XW;
   mrb::pdl_trigger();
   mrb::pdl_wait();      // before the first global access (common.cuh, MRB_PDL)
   // rows are 128 B (64 x 16 bit), 16-byte chunk c of row r lives at chunk (c ^ (r & 7)): conflict-free ldmatrix without
@@ -304,13 +307,13 @@ __global__ void __launch_bounds__(128) attn_xq_kernel(const typename AttnParamsO
   const T* gq = static_cast<const T*>(p.q) + b * p.q_bs + static_cast<long long>(h) * HD;
   const T* gk = static_cast<const T*>(p.k) + b * p.k_bs + static_cast<long long>(h) * HD;
   const T* gv = static_cast<const T*>(p.v) + b * p.v_bs + static_cast<long long>(h) * HD;
-  for (int i = threadIdx.x; i < LkP * 8; i += 128) {
+  for (int i = threadIdx.x; i < LkP * 8; i += NT) {
     const int r = i >> 3, c = i & 7;
     const bool ok = r < p.Lk;
     cp_async16(smem_u32(sK + sw(r, c)), ok ? gk + static_cast<long long>(r) * p.k_rs + c * 8 : gk, ok);
     cp_async16(smem_u32(sV + sw(r, c)), ok ? gv + static_cast<long long>(r) * p.v_rs + c * 8 : gv, ok);
   }
-  for (int i = threadIdx.x; i < LQ * 8; i += 128) {
+  for (int i = threadIdx.x; i < LQ * 8; i += NT) {
     const int r = i >> 3, c = i & 7;
     const bool ok = r < p.Lq;
     cp_async16(smem_u32(sQ + sw(r, c)), ok ? gq + static_cast<long long>(r) * p.q_rs + c * 8 : gq, ok);
@@ -320,7 +323,7 @@ __global__ void __launch_bounds__(128) attn_xq_kernel(const typename AttnParamsO
   __syncthreads();
 
   // this warp's contiguous range of 16-key groups
-  const int NG = LkP >> 4, base = NG >> 2, rem = NG & 3;
+  const int NG = LkP >> 4, base = NG / XW, rem = NG % XW;
   const int ng = base + (warp < rem ? 1 : 0);
   const int g0 = warp * base + min(warp, rem);
   const int krow0 = g0 * 16;
@@ -433,9 +436,9 @@ __global__ void __launch_bounds__(128) attn_xq_kernel(const typename AttnParamsO
   }
   __syncthreads();                               // every warp is done with K / V: reuse their space for the partials
   constexpr int LDO = HD + 2;
-  float* sO = reinterpret_cast<float*>(sK);      // [4 warps][32 rows][LDO]  (K and V regions together hold it)
-  float* sM = sO + 4 * LQ * LDO;                 // [4][32] running max (log2 domain), [4][32] sums
-  float* sL = sM + 4 * LQ;
+  float* sO = reinterpret_cast<float*>(sK);      // [XW warps][32 rows][LDO]  (the launcher sizes the K / V region for it)
+  float* sM = sO + XW * LQ * LDO;                // [XW][32] running max (log2 domain), [XW][32] sums
+  float* sL = sM + XW * LQ;
 #pragma unroll
   for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
@@ -448,34 +451,36 @@ __global__ void __launch_bounds__(128) attn_xq_kernel(const typename AttnParamsO
     }
   __syncthreads();
   {
-    const int row = threadIdx.x >> 2, c0 = (threadIdx.x & 3) * 16;
+    constexpr int TPR = NT / LQ, CW = HD / TPR;  // threads per row (4 / 8), columns per thread (16 / 8)
+    const int row = threadIdx.x / TPR, c0 = (threadIdx.x % TPR) * CW;
     if (row < p.Lq) {
       float m = -INFINITY;
 #pragma unroll
-      for (int w = 0; w < 4; ++w) m = fmaxf(m, sM[w * LQ + row]);
-      float f[4], L = 0.f;
+      for (int w = 0; w < XW; ++w) m = fmaxf(m, sM[w * LQ + row]);
+      float f[XW], L = 0.f;
 #pragma unroll
-      for (int w = 0; w < 4; ++w) {
+      for (int w = 0; w < XW; ++w) {
         const float mw = sM[w * LQ + row];
         f[w] = mw == -INFINITY ? 0.f : exp2f(mw - m);
         L += f[w] * sL[w * LQ + row];
       }
       const float inv = (L > 0.f ? 1.f / L : 0.f) * dscale;
       T* go = static_cast<T*>(p.o) + b * p.o_bs + static_cast<long long>(row) * p.o_rs + static_cast<long long>(h) * HD + c0;
-      uint32_t w8[8];
+      uint32_t w8[CW / 2];
 #pragma unroll
-      for (int c = 0; c < 16; c += 2) {
+      for (int c = 0; c < CW; c += 2) {
         float a0 = 0.f, a1 = 0.f;
 #pragma unroll
-        for (int w = 0; w < 4; ++w) {
+        for (int w = 0; w < XW; ++w) {
           const float2 v = *reinterpret_cast<const float2*>(sO + (w * LQ + row) * LDO + c0 + c);
           a0 = fmaf(f[w], v.x, a0);
           a1 = fmaf(f[w], v.y, a1);
         }
         w8[c >> 1] = MmaType<T>::pack(a0 * inv, a1 * inv);
       }
-      *reinterpret_cast<uint4*>(go) = make_uint4(w8[0], w8[1], w8[2], w8[3]);
-      *reinterpret_cast<uint4*>(go + 8) = make_uint4(w8[4], w8[5], w8[6], w8[7]);
+#pragma unroll
+      for (int c = 0; c < CW / 8; ++c)
+        *reinterpret_cast<uint4*>(go + 8 * c) = make_uint4(w8[4 * c], w8[4 * c + 1], w8[4 * c + 2], w8[4 * c + 3]);
     }
   }
 }
@@ -1270,15 +1275,23 @@ static int launch_fwd(const typename AttnParamsOf<DROP>::type& p, cudaStream_t s
   return MRB_OK;
 }
 
-template <typename T, bool DROP = false>
-static int launch_xq(const typename AttnParamsOf<DROP>::type& p, cudaStream_t s) {
+template <typename T, bool DROP, int XW>
+static int launch_xq_w(const typename AttnParamsOf<DROP>::type& p, cudaStream_t s) {
   const int LkP = (p.Lk + 15) & ~15;
-  const int smem = (32 + 2 * LkP) * 64 * 2;
+  const int kv = 2 * LkP * 64 * 2, part = XW * 32 * (64 + 2) * 4 + 2 * XW * 32 * 4;     // K + V, reused for the warps' partials
+  const int smem = 32 * 64 * 2 + (kv > part ? kv : part);
   static int cfg = 0;
-  if (cfg < smem) { if (int rc = set_smem(attn_xq_kernel<T, DROP>, smem)) return rc; cfg = smem; }
-  MRB_LAUNCH((attn_xq_kernel<T, DROP>), dim3(p.H, p.B), 128, smem, s, p);
+  if (cfg < smem) { if (int rc = set_smem(attn_xq_kernel<T, DROP, XW>, smem)) return rc; cfg = smem; }
+  MRB_LAUNCH((attn_xq_kernel<T, DROP, XW>), dim3(p.H, p.B), 32 * XW, smem, s, p);
   MRB_CHECK_LAUNCH();
   return MRB_OK;
+}
+
+template <typename T, bool DROP = false>
+static int launch_xq(const typename AttnParamsOf<DROP>::type& p, cudaStream_t s) {
+  static int warps = 0;                   // MRB_XQ_WARPS=4: the four-warp form (A/B measurements)
+  if (!warps) { const char* e = getenv("MRB_XQ_WARPS"); warps = (e && e[0] == '4') ? 4 : 8; }
+  return warps == 4 ? launch_xq_w<T, DROP, 4>(p, s) : launch_xq_w<T, DROP, 8>(p, s);
 }
 
 // few query rows x >= 512 keys (the T5 decoder's cross-attention), hd = 64
@@ -1375,7 +1388,7 @@ static int attention_fwd_impl(const void* q, long long q_bs, long long q_rs, con
   // few queries x a few hundred keys, no bias / mask (Q-Former cross-attention): one-shot K/V fetch, keys split over the warps
   static int use_xq = -1;                 // MRB_ATTN_XQ=0 keeps the generic kernel (A/B measurements)
   if (use_xq < 0) { const char* e = getenv("MRB_ATTN_XQ"); use_xq = (e && e[0] == '0') ? 0 : 1; }
-  const bool xq_shape = use_xq && hd == 64 && Lq <= 32 && Lk > 64 && Lk <= 16 * 4 * XQ_MAXG && !bias && !kmask && !causal && !lse &&
+  const bool xq_shape = use_xq && hd == 64 && Lq <= 32 && Lk > 64 && Lk <= XQ_MAX_LK && !bias && !kmask && !causal && !lse &&
                         p.kv_div == 1 && 4 * 32 * (64 + 2) * 4 + 8 * 32 * 4 <= 2 * ((Lk + 15) & ~15) * 64 * 2;
   const bool fq = fq_shape(Lq, Lk, hd);   // few query rows x thousands of keys (T5 decoder cross-attention): keys split over a cluster
   if (drop_seed && drop_p > 0.f) {

@@ -50,8 +50,9 @@ __device__ __forceinline__ void delta_mma(float* c, const uint32_t* a, uint32_t 
 // which order d runs): K and V of a head are read from L2 exactly once per query tile.  (A first version with one block per query
 // row re-read them Lq times: 1 GB of L2 traffic, 106 us per decoder layer.)  The warps' partial sums meet in shared memory in a
 // fixed order: no atomics, the result is bit-reproducible from run to run (graph replay vs eager launches compare exactly).
-constexpr int DELTA_WARPS = 8;
-
+// DELTA_WARPS = 16 for the decoder's cross-attention (~2000 keys: 16 key tiles per warp instead of 32, the launch is a chain of
+// dependent L2 round trips on 128 blocks -- 51.6 us per decoder layer with 8 warps, profiles/launch_summary_r02f.csv), 8 otherwise.
+template <int DELTA_WARPS>
 static __global__ void __launch_bounds__(DELTA_WARPS * 32) attn_delta_exact_kernel(const DeltaExactParams p) {
   pdl_trigger();
   pdl_wait();
@@ -81,6 +82,7 @@ static __global__ void __launch_bounds__(DELTA_WARPS * 32) attn_delta_exact_kern
     }
     const float lse_a = oka ? p.lse[row0 + ia] * LOG2E : 0.f, lse_b = okb ? p.lse[row0 + ib] * LOG2E : 0.f;
     float acc_a = 0.f, acc_b = 0.f;
+#pragma unroll 2
     for (int j0 = key_lo + 8 * warp; j0 < key_hi; j0 += 8 * DELTA_WARPS) {
       // B fragments: key j0 + g, bytes [32 t, 32 t + 32) of its K and V rows
       const int jk = j0 + g;
@@ -139,7 +141,10 @@ static __global__ void __launch_bounds__(DELTA_WARPS * 32) attn_delta_exact_kern
 }
 
 static inline int launch_delta_exact(const DeltaExactParams& d, cudaStream_t s) {
-  MRB_LAUNCH((attn_delta_exact_kernel), dim3(d.H, d.B), DELTA_WARPS * 32, 0, s, d);
+  static int wide = -1;                   // MRB_DELTA_WIDE=0: 8 warps for every key count (A/B measurements)
+  if (wide < 0) { const char* e = getenv("MRB_DELTA_WIDE"); wide = (e && e[0] == '0') ? 0 : 1; }
+  if (wide && d.Lk >= 512) MRB_LAUNCH((attn_delta_exact_kernel<16>), dim3(d.H, d.B), 16 * 32, 0, s, d);
+  else MRB_LAUNCH((attn_delta_exact_kernel<8>), dim3(d.H, d.B), 8 * 32, 0, s, d);
   MRB_CHECK_LAUNCH();
   return MRB_OK;
 }

@@ -731,19 +731,23 @@ __global__ void __launch_bounds__(256) lora_pack_kernel(const LoraPackDesc* __re
 
 // ---------------------------------------------------------------- LoRA down-projection for small M
 // out[m, r] = sum_k x[m, k] * W[r, k], r < 32 (16-bit x / W / out): one block per row.  Used when M is too small for the
-// tensor-core path to spread over the SMs (decoder steps).
-__global__ void __launch_bounds__(256) small_down_kernel(const uint16_t* __restrict__ x, long long ldx,
-                                                         const uint16_t* __restrict__ W, long long ldw, int K,
-                                                         uint16_t* __restrict__ out, long long ldo, int dtype) {
+// tensor-core path to spread over the SMs (decoder steps).  The block has ceil(K / 2048) x 256 threads (<= 1024), so a thread
+// makes one pass (two for K = 10240) with its 32 W loads in flight together; a warp's 32 sums are folded across its lanes by a
+// butterfly that halves the live values per step (31 shuffles, lane r ends with sum r) instead of 32 full warp reductions.
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS) small_down_kernel(const uint16_t* __restrict__ x, long long ldx,
+                                                             const uint16_t* __restrict__ W, long long ldw, int K,
+                                                             uint16_t* __restrict__ out, long long ldo, int dtype) {
   mrb::pdl_trigger();
   mrb::pdl_wait();      // before the first global access (common.cuh, MRB_PDL)
-  __shared__ float red[8][32];
+  __shared__ float red[THREADS / 32][33];
   const int m = blockIdx.x;
+  constexpr int nwarps = THREADS / 32;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   float acc[32];
 #pragma unroll
   for (int r = 0; r < 32; ++r) acc[r] = 0.f;
-  for (int k = threadIdx.x * 8; k < K; k += 256 * 8) {
+  for (int k = threadIdx.x * 8; k < K; k += THREADS * 8) {
     const uint4 xv = *reinterpret_cast<const uint4*>(x + static_cast<long long>(m) * ldx + k);
     const uint32_t xw[4] = {xv.x, xv.y, xv.z, xv.w};
     float xf[8];
@@ -757,16 +761,23 @@ __global__ void __launch_bounds__(256) small_down_kernel(const uint16_t* __restr
       for (int i = 0; i < 4; ++i) acc[r] += xf[2 * i] * unpack_lo(ww[i], dtype) + xf[2 * i + 1] * unpack_hi(ww[i], dtype);
     }
   }
+  // butterfly: after the step with offset `off`, acc[i] (i < off) of a lane is a partial sum of output i + (lane & off ? off : 0) + ...
 #pragma unroll
-  for (int r = 0; r < 32; ++r) {
-    const float v = warp_sum(acc[r]);
-    if (lane == 0) red[warp][r] = v;
+  for (int off = 16; off >= 1; off >>= 1) {
+    const bool up = (lane & off) != 0;
+#pragma unroll
+    for (int i = 0; i < off; ++i) {
+      const float send = up ? acc[i] : acc[i + off];
+      const float keep = up ? acc[i + off] : acc[i];
+      acc[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+    }
   }
+  red[warp][lane] = acc[0];                  // lane r: this warp's sum for output r
   __syncthreads();
   if (threadIdx.x < 32) {
     float v = 0.f;
 #pragma unroll
-    for (int w = 0; w < 8; ++w) v += red[w][threadIdx.x];
+    for (int w = 0; w < nwarps; ++w) v += red[w][threadIdx.x];
     out[static_cast<long long>(m) * ldo + threadIdx.x] = static_cast<uint16_t>(pack2(v, 0.f, dtype) & 0xffff);
   }
 }
@@ -841,6 +852,11 @@ static inline unsigned blocks_for(long long n, int per) { return static_cast<uns
 // Row kernels (one warp per row): 8 rows per block, but decoder-sized inputs (64 rows) would then sit on 8 of the 148 SMs and run
 // at the latency of 8 serial row passes per SM -- one row per block spreads them.
 static inline int norm_warps(int rows) { return rows <= 2 * 148 ? 1 : 8; }
+static inline bool small_rows_take_row_kernel() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("MRB_NORM_ROW_SMALL"); v = (e && e[0] == '0') ? 0 : 1; }
+  return v == 1;
+}
 
 extern "C" int mrb_norm(const float* x, const float* add, const float* w, const float* bias, float eps, int rows, int C,
                         int mode, float* out_f32, void* out_h, int h_dtype, long long ld_h, float* sum_out, void* stream) {
@@ -848,7 +864,10 @@ extern "C" int mrb_norm(const float* x, const float* add, const float* w, const 
   if ((C & 3) || C > 2048 || (out_h && (ld_h & 3))) return MRB_ERR_ARG;
   static int row_kernel = -1;             // MRB_NORM_ROW=0 keeps the warp-per-row kernel for large inputs (A/B measurements)
   if (row_kernel < 0) { const char* e = getenv("MRB_NORM_ROW"); row_kernel = (e && e[0] == '0') ? 0 : 1; }
-  if (row_kernel && rows > 2 * 148) {
+  // decoder-sized inputs (64 rows x 2048): the one-warp-per-row kernel walks its 16 float4 per lane as dependent round trips
+  // (10 / 18 us per launch forward / backward, profiles/launch_summary_r02f.csv); a block per row issues every load at once.
+  // MRB_NORM_ROW_SMALL=0 restores the warp-per-row kernels for them (A/B measurements).
+  if (row_kernel && (rows > 2 * 148 || (C >= 1024 && small_rows_take_row_kernel()))) {
     MRB_LAUNCH((norm_row_kernel), rows, 256, 0, STREAM, x, add, w, bias, eps, rows, C, mode, out_f32, out_h, h_dtype, ld_h, sum_out);
     MRB_CHECK_LAUNCH();
     return MRB_OK;
@@ -868,7 +887,7 @@ extern "C" int mrb_rmsnorm_bwd(const float* x, const float* w, const void* dy, i
   if ((C & 3) || C > 2048 || (ld_dy & 3) || R > 32 || (lora_A && dy_dtype == MRB_DT_F32)) return MRB_ERR_ARG;
   static int row_kernel = -1;             // MRB_RMSNORM_BWD_ROW=0 keeps the warp-per-row kernel for large inputs (A/B measurements)
   if (row_kernel < 0) { const char* e = getenv("MRB_RMSNORM_BWD_ROW"); row_kernel = (e && e[0] == '0') ? 0 : 1; }
-  if (row_kernel && !lora_A && rows > 2 * 148) {
+  if (row_kernel && !lora_A && (rows > 2 * 148 || (C >= 1024 && small_rows_take_row_kernel()))) {
     MRB_LAUNCH((rmsnorm_bwd_row_kernel), rows, 256, 0, STREAM, x, w, dy, dy_dtype, ld_dy, eps, rows, C, dres);
     MRB_CHECK_LAUNCH();
     return MRB_OK;
@@ -1018,8 +1037,16 @@ extern "C" int mrb_small_down(const void* x, long long ldx, const void* W, long 
                               long long ldo, int dtype, void* stream) {
   if (M <= 0) return MRB_OK;
   if ((K & 7) || (ldx & 7) || (ldw & 7)) return MRB_ERR_ARG;
-  MRB_LAUNCH((small_down_kernel), M, 256, 0, STREAM, static_cast<const uint16_t*>(x), ldx, static_cast<const uint16_t*>(W), ldw, K,
-                                           static_cast<uint16_t*>(out), ldo, dtype);
+  static int wide = -1;                   // MRB_SMALL_DOWN_WIDE=0: 256 threads for every K (A/B measurements)
+  if (wide < 0) { const char* e = getenv("MRB_SMALL_DOWN_WIDE"); wide = (e && e[0] == '0') ? 0 : 1; }
+  int threads = 256;
+  if (wide) { threads = ((K + 2047) / 2048) * 256; if (threads > 1024) threads = 1024; }
+  const uint16_t* xp = static_cast<const uint16_t*>(x);
+  const uint16_t* wp = static_cast<const uint16_t*>(W);
+  uint16_t* op = static_cast<uint16_t*>(out);
+  if (threads <= 256) MRB_LAUNCH((small_down_kernel<256>), M, 256, 0, STREAM, xp, ldx, wp, ldw, K, op, ldo, dtype);
+  else if (threads <= 512) MRB_LAUNCH((small_down_kernel<512>), M, 512, 0, STREAM, xp, ldx, wp, ldw, K, op, ldo, dtype);
+  else MRB_LAUNCH((small_down_kernel<1024>), M, 1024, 0, STREAM, xp, ldx, wp, ldw, K, op, ldo, dtype);
   MRB_CHECK_LAUNCH();
   return MRB_OK;
 }

@@ -12,6 +12,7 @@
 // (tmem_full/tmem_empty mbarriers) so the epilogue of tile i overlaps the MMAs of tile i+1.
 #include "common.cuh"
 #include <stdlib.h>
+#include <mutex>
 
 namespace mrb {
 
@@ -33,7 +34,17 @@ struct GemmParams {
   // [s * kb_per_split, min(k_blocks, (s + 1) * kb_per_split)) into fp32 partials at out + s * split_stride
   int splits, kb_per_split;
   long long split_stride;
+  // split-K with the reduce folded into the launch (tile_counters != null): the CTA that finishes an output tile LAST (per-tile
+  // arrival counter, zero on entry and left zero) sums the partials of all splits in split order and applies this epilogue --
+  // the arithmetic of splitk_reduce_kernel, without the second launch
+  int* tile_counters;
+  const float* fin_bias; int fin_gelu; const float* fin_resid; long long fin_ldr;
+  void* fin_out; int fin_dtype; long long fin_ldc;
 };
+
+// per-workspace arrival counters of the folded split-K reduce: zero at module load, every launch leaves them zero
+constexpr int SPLITK_SLOTS = 16, SPLITK_COUNTERS = 256;
+__device__ int g_splitk_counters[SPLITK_SLOTS][SPLITK_COUNTERS];
 
 constexpr int BM = 128;
 constexpr int BK = 64;
@@ -84,6 +95,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   uint64_t* tmem_full = empty_bar + STAGES;
   uint64_t* tmem_empty = tmem_full + 2;
   uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  volatile uint32_t* last_flag = tmem_holder + 1;      // [2]: "this CTA arrived last at its output tile" (folded split-K reduce)
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -275,6 +287,57 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty[as]);
+      if constexpr (SPLIT) {
+        if (p.tile_counters) {
+          // ---- folded reduce.  Release: every epilogue thread fences its partial stores, the eight warps meet, one thread
+          //      bumps the tile's counter.  Acquire: the CTA that sees splits - 1 earlier arrivals fences and reads all partials
+          //      (L2 loads: other CTAs wrote them).  Counter reset by the last arriver: the next launch finds zeros.
+          __threadfence();
+          asm volatile("bar.sync 1, 256;" ::: "memory");
+          if (warp == 2 && lane == 0) {
+            const int prev = atomicAdd(p.tile_counters + tile, 1);
+            const bool last = prev == p.splits - 1;
+            if (last) { p.tile_counters[tile] = 0; __threadfence(); }
+            last_flag[it & 1] = last ? 1u : 0u;
+          }
+          asm volatile("bar.sync 1, 256;" ::: "memory");
+          if (last_flag[it & 1]) {
+            const float* ws = static_cast<const float*>(p.out);
+#pragma unroll 1
+            for (int c = c_begin; c < c_end; c += 32) {
+              const int n0 = tn * BN + c;
+              if (n0 >= p.N) break;
+              const int col = n0 + chunk * 4;
+              if (col >= p.N) continue;             // N is a multiple of 8: a float4 is all in or all out
+              float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (p.fin_bias) b4 = __ldg(reinterpret_cast<const float4*>(p.fin_bias + col));
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                const int m = m_base + i * 4 + sub_row;
+                if (m >= p.M) continue;
+                const float* src = ws + static_cast<long long>(m) * p.N + col;
+                float4 x = __ldcg(reinterpret_cast<const float4*>(src));
+                for (int sp = 1; sp < p.splits; ++sp) {
+                  const float4 y = __ldcg(reinterpret_cast<const float4*>(src + sp * p.split_stride));
+                  x.x += y.x; x.y += y.y; x.z += y.z; x.w += y.w;
+                }
+                x.x += b4.x; x.y += b4.y; x.z += b4.z; x.w += b4.w;
+                if (p.fin_gelu) { x.x = gelu_erf(x.x); x.y = gelu_erf(x.y); x.z = gelu_erf(x.z); x.w = gelu_erf(x.w); }
+                if (p.fin_resid) {
+                  const float4 r4 = *reinterpret_cast<const float4*>(p.fin_resid + m * p.fin_ldr + col);
+                  x.x += r4.x; x.y += r4.y; x.z += r4.z; x.w += r4.w;
+                }
+                if (p.fin_dtype == MRB_DT_F32) {
+                  *reinterpret_cast<float4*>(static_cast<float*>(p.fin_out) + m * p.fin_ldc + col) = x;
+                } else {
+                  *reinterpret_cast<uint2*>(static_cast<uint16_t*>(p.fin_out) + m * p.fin_ldc + col) =
+                      make_uint2(pack2(x.x, x.y, p.fin_dtype), pack2(x.z, x.w, p.fin_dtype));
+                }
+              }
+            }
+          }
+        }
+      }
     }
   }
 
@@ -432,6 +495,29 @@ static int pick_bn(int M, int N, int sms) {
   return best;
 }
 
+// Arrival counters of the folded split-K reduce for the workspace `ws` (one workspace per issuing stream, so launches that
+// share a slot are stream-ordered): a slot of g_splitk_counters per distinct workspace address.  nullptr -> two-pass path
+// (MRB_SPLITK_FUSED=0, more output tiles than counters, or more than SPLITK_SLOTS workspaces).
+static int* splitk_counters_for(const void* ws, int tiles) {
+  static int fused = -1;
+  if (fused < 0) { const char* e = getenv("MRB_SPLITK_FUSED"); fused = (e && e[0] == '0') ? 0 : 1; }
+  if (!fused || tiles > SPLITK_COUNTERS) return nullptr;
+  static std::mutex mu;
+  static const void* owner[SPLITK_SLOTS] = {};
+  static int* base = nullptr;
+  std::lock_guard<std::mutex> lock(mu);
+  if (!base) {
+    void* sym = nullptr;
+    if (cudaGetSymbolAddress(&sym, g_splitk_counters) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    base = static_cast<int*>(sym);
+  }
+  for (int i = 0; i < SPLITK_SLOTS; ++i) {
+    if (owner[i] == ws) return base + i * SPLITK_COUNTERS;
+    if (owner[i] == nullptr) { owner[i] = ws; return base + i * SPLITK_COUNTERS; }
+  }
+  return nullptr;
+}
+
 extern "C" int mrb_gemm2_launch(const CUtensorMap* tmA, const CUtensorMap* tmB, int M, int N, int K, int dtype,
                                 const float* bias, int gelu, const float* resid, long long ldr, void* out, int out_dtype,
                                 long long ldc, int row_group, int num_sms, void* stream);
@@ -482,6 +568,8 @@ static int gemm_impl(const void* A, long long lda, const void* B, long long ldb,
   p.bias = bias; p.gelu = gelu; p.resid = resid; p.ldr = ldr;
   p.out = out; p.out_dtype = out_dtype; p.ldc = ldc; p.row_group = row_group;
   p.splits = 1; p.kb_per_split = 0; p.split_stride = 0;
+  p.tile_counters = nullptr; p.fin_bias = nullptr; p.fin_gelu = 0; p.fin_resid = nullptr; p.fin_ldr = 0;
+  p.fin_out = nullptr; p.fin_dtype = 0; p.fin_ldc = 0;
   {
     static int mode = -1;                 // MRB_GEMM_EPI=direct selects the row-per-thread 16-bit epilogue (A/B measurements)
     if (mode < 0) { const char* e = getenv("MRB_GEMM_EPI"); mode = e ? (e[0] == 'd' ? 1 : 2) : 0; }
@@ -493,6 +581,12 @@ static int gemm_impl(const void* A, long long lda, const void* B, long long ldb,
     p.bias = nullptr; p.gelu = 0; p.resid = nullptr; p.ldr = 0; p.epi_direct = 0;
     p.out = ws; p.out_dtype = MRB_DT_F32; p.ldc = N;
     p.splits = plan.splits; p.kb_per_split = plan.kb_per; p.split_stride = static_cast<long long>(M) * N;
+    int* counters = splitk_counters_for(ws, p.m_tiles * ((N + bn - 1) / bn));
+    if (counters) {                       // reduce folded into the launch: the last CTA of every output tile applies the epilogue
+      p.tile_counters = counters;
+      p.fin_bias = bias; p.fin_gelu = gelu; p.fin_resid = resid; p.fin_ldr = ldr;
+      p.fin_out = out; p.fin_dtype = out_dtype; p.fin_ldc = ldc;
+    }
     switch (bn) {
       case 256: rc = launch_gemm<256, 4, true>(tmA, tmB, p, s); break;
       case 128: rc = launch_gemm<128, 6, true>(tmA, tmB, p, s); break;
@@ -501,6 +595,7 @@ static int gemm_impl(const void* A, long long lda, const void* B, long long ldb,
       default: return MRB_ERR_ARG;
     }
     if (rc) return rc;
+    if (counters) return MRB_OK;
     const long long quads = static_cast<long long>(M) * (N >> 2);
     long long blocks = (quads + 255) / 256;
     if (blocks > 4LL * g_num_sms) blocks = 4LL * g_num_sms;

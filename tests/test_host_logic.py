@@ -1331,10 +1331,11 @@ def test_elementwise_kernel_source_runs_on_host_shim(elementwise_kernels_on_host
             assert lib.mrb_skinny_wgrad(P(Pm), c_ll(264), ctypes.c_void_p(Q.data_ptr() + 16), c_ll(16), M, 264, P(o), tr, BF, None) == 0
             want = Pm.float().t() @ Q[:, 8:16].float()
             assert _relfro((o - 1.0).t() if tr else o - 1.0, want) < 1e-4, (M, tr)
-    xs, Wd = torch.randn(5, 2048 + 32, generator=g).to(torch.bfloat16), torch.randn(32, 2048, generator=g).to(torch.bfloat16)
-    od = torch.zeros((5, 32), dtype=torch.bfloat16)
-    assert lib.mrb_small_down(P(xs), c_ll(2048 + 32), P(Wd), c_ll(2048), 5, 2048, P(od), c_ll(32), BF, None) == 0
-    assert _relfro(od, xs[:, :2048].float() @ Wd.float().t()) < 4e-3
+    for Kd in (2048, 1032, 4096, 5120, 10240):     # 256 / 256 / 512 / 1024 / 1024 threads per row (ceil(K / 2048) x 256, capped)
+        xs, Wd = torch.randn(5, Kd + 32, generator=g).to(torch.bfloat16), torch.randn(32, Kd, generator=g).to(torch.bfloat16)
+        od = torch.zeros((5, 32), dtype=torch.bfloat16)
+        assert lib.mrb_small_down(P(xs), c_ll(Kd + 32), P(Wd), c_ll(Kd), 5, Kd, P(od), c_ll(32), BF, None) == 0
+        assert _relfro(od, xs[:, :Kd].float() @ Wd.float().t()) < 4e-3, Kd
     K, N, scale = 264, 520, 0.5
     A, B = torch.randn(8, K, generator=g), torch.randn(N, 8, generator=g)
     ext = torch.zeros((N, K + 32), dtype=torch.bfloat16)

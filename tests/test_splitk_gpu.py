@@ -142,3 +142,54 @@ def test_splitk_whole_model_step(monkeypatch, tiny_sd):
     # (they did on the B200); the logits they are decoded from must agree
     assert ((p1[0] - p0[0]).norm() / p0[0].norm()).item() < 1e-2      # B200: 4e-3 through 2 + 2 bf16 layers
     assert len(p0[1]) == len(p1[1])
+
+
+_FOLD_SCRIPT = r"""
+import math, sys, torch
+sys.path.insert(0, sys.argv[2])
+from mr_blip_b200 import _lib
+from mr_blip_b200.ops import _DT, _ptr
+_lib.load()
+outs = []
+for i, (M, N, K, dt, gelu, use_bias, use_resid, od) in enumerate([
+        (56, 2048, 2080, torch.bfloat16, False, False, True, torch.float32), (64, 10240, 2080, torch.bfloat16, False, False, False, torch.bfloat16),
+        (64, 2048, 10272, torch.bfloat16, False, True, False, torch.float32), (5, 2048, 2080, torch.float16, True, True, False, torch.float16),
+        (8132, 32, 2048, torch.bfloat16, False, False, False, torch.bfloat16), (128, 2048, 5152, torch.bfloat16, False, True, True, torch.float32)]):
+    g = torch.Generator(device="cuda").manual_seed(100 + i)
+    a = torch.randn((M, K), generator=g, device="cuda").to(dt)
+    b = (torch.randn((N, K), generator=g, device="cuda") / math.sqrt(K)).to(dt)
+    bias = torch.randn((N,), generator=g, device="cuda") if use_bias else None
+    resid = torch.randn((M, N), generator=g, device="cuda") if use_resid else None
+    ws = torch.full((48 << 18,), float("nan"), device="cuda")
+    out = torch.empty((M, N), dtype=od, device="cuda")
+    for rep in range(3):          # the arrival counters must come back to zero: repeated launches on one workspace agree
+        _lib.call("mrb_gemm_splitk", a.data_ptr(), a.stride(0), b.data_ptr(), b.stride(0), M, N, K, _DT[dt], _ptr(bias), int(gelu),
+                  _ptr(resid), resid.stride(0) if resid is not None else 0, out.data_ptr(), _DT[od], out.stride(0), 0, 0,
+                  ws.data_ptr(), ws.numel() * 4, 8, torch.cuda.current_stream().cuda_stream)
+        torch.cuda.synchronize()
+        if rep == 0:
+            first = out.clone()
+        assert torch.equal(out, first), (i, rep)
+    outs.append(out.cpu())
+torch.save(outs, sys.argv[1])
+"""
+
+
+def test_folded_reduce_is_bit_identical_to_the_two_pass_reduce(lib, tmp_path):
+    """The reduce folded into the split-K launch (the CTA that arrives last at an output tile sums the partials in split order and
+    applies the epilogue; csrc/gemm.cu, default) against the separate splitk_reduce_kernel launch (MRB_SPLITK_FUSED=0): the same
+    arithmetic in the same order, so the outputs must be EQUAL -- for every epilogue, and launch after launch on one workspace."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    script = tmp_path / "fold.py"
+    script.write_text(_FOLD_SCRIPT)
+    res = {}
+    for fused in ("1", "0"):
+        env = dict(os.environ, MRB_SPLITK_FUSED=fused)
+        f = str(tmp_path / ("out%s.pt" % fused))
+        subprocess.check_call([sys.executable, str(script), f, root], env=env)
+        res[fused] = torch.load(f)
+    for x, y in zip(res["1"], res["0"]):
+        assert torch.isfinite(x.float()).all()
+        assert torch.equal(x, y)

@@ -2,7 +2,7 @@
 captured into its OWN CUDA graph and replayed: encoder forward, decoder chain (decoder forward + lm_head + cross-entropy +
 lm_head / decoder backward, incl. the side-stream cross K/V work), encoder backward.  The ncu launch list serialises kernels and
 flushes caches between them, which overstates the ~2 000 decoder-sized kernels; this is the number they cost inside a graph.
-python tools/t5_phase_bench.py [out.json]      (MRB_TRAIN_DROPOUT=0: eval arithmetic)"""
+python tools/t5_phase_bench.py [out.json]      (MRB_TRAIN_DROPOUT=0: eval arithmetic; MRB_T5_PHASES=dec_chain: that phase only)"""
 import json
 import os
 import sys
@@ -60,7 +60,12 @@ def main():
         t5.side_join()
 
     res = {}
+    only = os.environ.get("MRB_T5_PHASES", "")          # e.g. "dec_chain": time that phase alone (the encoder forward runs once, untimed)
+    if only:
+        enc_fwd()
     for name, fn in (("enc_fwd", enc_fwd), ("dec_chain", dec_chain), ("enc_fwd_bwd", enc_bwd)):
+        if only and name not in only.split(","):
+            continue
         for _ in range(2):
             fn()
         torch.cuda.synchronize()
@@ -79,7 +84,8 @@ def main():
         torch.cuda.synchronize()
         res[name] = round(e0.elapsed_time(e1) / reps, 3)
         print(name, res[name], "ms", flush=True)
-    res["enc_bwd"] = round(res["enc_fwd_bwd"] - res["enc_fwd"], 3)
+    if "enc_fwd_bwd" in res and "enc_fwd" in res:
+        res["enc_bwd"] = round(res["enc_fwd_bwd"] - res["enc_fwd"], 3)
     res["dropout"] = t5.drop is not None
     print(json.dumps(res))
     if len(sys.argv) > 1:
