@@ -287,7 +287,9 @@ __global__ void __launch_bounds__(NTHREADS) attn_fwd_kernel(const typename AttnP
 // partial (max, sum, O) triples are merged through shared memory.  No loop-carried barriers, no running rescale.
 constexpr int XQ_MAX_LK = 320;
 // XW warps: 4 (five 16-key groups per warp) or 8 (three): the eight-warp form halves every warp's serial chain (S, softmax, P.V,
-// merge) and the cp.async issue per thread at the same shared memory per CTA.  MRB_XQ_WARPS=4 selects the four-warp form.
+// merge) and the cp.async issue per thread at the same shared memory per CTA -- but its 116-127 registers x 256 threads leave two
+// CTAs per SM instead of three, and it measured SLOWER on a B200 (path 1.80-1.83 -> 2.0-2.2 ms per step, call 26): the four-warp
+// form stays the default, MRB_XQ_WARPS=8 selects the other.
 template <typename T, bool DROP = false, int XW = 4>
 __global__ void __launch_bounds__(32 * XW) attn_xq_kernel(const typename AttnParamsOf<DROP>::type p) {
   constexpr int XQ_MAXG = (XQ_MAX_LK / 16 + XW - 1) / XW, NT = 32 * XW;
@@ -307,19 +309,25 @@ __global__ void __launch_bounds__(32 * XW) attn_xq_kernel(const typename AttnPar
   const T* gq = static_cast<const T*>(p.q) + b * p.q_bs + static_cast<long long>(h) * HD;
   const T* gk = static_cast<const T*>(p.k) + b * p.k_bs + static_cast<long long>(h) * HD;
   const T* gv = static_cast<const T*>(p.v) + b * p.v_bs + static_cast<long long>(h) * HD;
-  for (int i = threadIdx.x; i < LkP * 8; i += NT) {
-    const int r = i >> 3, c = i & 7;
-    const bool ok = r < p.Lk;
-    cp_async16(smem_u32(sK + sw(r, c)), ok ? gk + static_cast<long long>(r) * p.k_rs + c * 8 : gk, ok);
-    cp_async16(smem_u32(sV + sw(r, c)), ok ? gv + static_cast<long long>(r) * p.v_rs + c * 8 : gv, ok);
-  }
+  // two commit groups: Q and K first (the scores and the softmax start as soon as they have landed), V behind them
   for (int i = threadIdx.x; i < LQ * 8; i += NT) {
     const int r = i >> 3, c = i & 7;
     const bool ok = r < p.Lq;
     cp_async16(smem_u32(sQ + sw(r, c)), ok ? gq + static_cast<long long>(r) * p.q_rs + c * 8 : gq, ok);
   }
+  for (int i = threadIdx.x; i < LkP * 8; i += NT) {
+    const int r = i >> 3, c = i & 7;
+    const bool ok = r < p.Lk;
+    cp_async16(smem_u32(sK + sw(r, c)), ok ? gk + static_cast<long long>(r) * p.k_rs + c * 8 : gk, ok);
+  }
   cp_async_commit();
-  cp_async_wait<0>();
+  for (int i = threadIdx.x; i < LkP * 8; i += NT) {
+    const int r = i >> 3, c = i & 7;
+    const bool ok = r < p.Lk;
+    cp_async16(smem_u32(sV + sw(r, c)), ok ? gv + static_cast<long long>(r) * p.v_rs + c * 8 : gv, ok);
+  }
+  cp_async_commit();
+  cp_async_wait<1>();
   __syncthreads();
 
   // this warp's contiguous range of 16-key groups
@@ -413,6 +421,8 @@ __global__ void __launch_bounds__(32 * XW) attn_xq_kernel(const typename AttnPar
       ls[mt][r] += __shfl_xor_sync(0xffffffffu, ls[mt][r], 1);
       ls[mt][r] += __shfl_xor_sync(0xffffffffu, ls[mt][r], 2);
     }
+  cp_async_wait<0>();
+  __syncthreads();                               // V has landed (every thread's copies)
   // O partial = P V over this warp's keys
   float oa[2][HD / 8][4];
 #pragma unroll
@@ -1289,8 +1299,8 @@ static int launch_xq_w(const typename AttnParamsOf<DROP>::type& p, cudaStream_t 
 
 template <typename T, bool DROP = false>
 static int launch_xq(const typename AttnParamsOf<DROP>::type& p, cudaStream_t s) {
-  static int warps = 0;                   // MRB_XQ_WARPS=4: the four-warp form (A/B measurements)
-  if (!warps) { const char* e = getenv("MRB_XQ_WARPS"); warps = (e && e[0] == '4') ? 4 : 8; }
+  static int warps = 0;                   // MRB_XQ_WARPS=8: the eight-warp form (A/B measurements)
+  if (!warps) { const char* e = getenv("MRB_XQ_WARPS"); warps = (e && e[0] == '8') ? 8 : 4; }
   return warps == 4 ? launch_xq_w<T, DROP, 4>(p, s) : launch_xq_w<T, DROP, 8>(p, s);
 }
 

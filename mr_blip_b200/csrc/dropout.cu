@@ -369,17 +369,19 @@ __device__ __forceinline__ uint32_t flag_mask(uint32_t t, int bit) { return 0u -
 // ---- forward: u[m, 8j + r] = scale * sum_k keep_j(m,k) x[m,k] A[8j + r, k].  Block = 16 rows, its 8 warps split K; lane (g, t)
 //      loads 16 bytes of rows g and g + 8 (columns k0 + 8t ..): fragment slots (2t, 2t+1 | 2t+8, 2t+9) of two mma's are those 8
 //      columns, and the B fragment is the matching 16 bytes of A row 8j + g.  Partial sums of the warps meet in shared memory.
-template <int NL>
-__global__ void __launch_bounds__(256) lora_down_drop_mma_kernel(const uint16_t* __restrict__ x, long long ldx, const uint16_t* __restrict__ A,
+// NW warps split K: 8 for the encoder-sized calls, 16 for decoder-sized inputs (M <= 128: four blocks, the launch is one serial chain
+// of K / (32 NW) load-hash-mma steps per warp -- 8.5 us at K 2048, 17.5 us at K 5120 with 8 warps, profiles/launch_summary_r02f.csv).
+template <int NL, int NW = 8>
+__global__ void __launch_bounds__(32 * NW) lora_down_drop_mma_kernel(const uint16_t* __restrict__ x, long long ldx, const uint16_t* __restrict__ A,
                                                                  long long lda, int M, int K, uint16_t* __restrict__ out, long long ldo,
                                                                  int dtype, const DropSpec d) {
   pdl_trigger();
   pdl_wait();
-  __shared__ float red[8 * NL * 16 * 8];
+  __shared__ float red[NW * NL * 16 * 8];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
   const int m0 = blockIdx.x * 16, r0 = m0 + g, r1 = r0 + 8;
   const bool ok0 = r0 < M, ok1 = r1 < M;
-  const int steps = (K + 31) >> 5, per = (steps + 7) >> 3;
+  const int steps = (K + 31) >> 5, per = (steps + NW - 1) / NW;
   const int ks = warp * per * 32, ke = min(K, ks + per * 32);
   const uint32_t ng = static_cast<uint32_t>(K >> 2), rb0 = static_cast<uint32_t>(r0) * ng, rb1 = static_cast<uint32_t>(r1) * ng;
   const uint32_t add = (256u - d.thr) * 0x00010001u;
@@ -418,14 +420,14 @@ __global__ void __launch_bounds__(256) lora_down_drop_mma_kernel(const uint16_t*
     rj[(g + 8) * 8 + 2 * t] = acc[j][2]; rj[(g + 8) * 8 + 2 * t + 1] = acc[j][3];
   }
   __syncthreads();
-  for (int idx = threadIdx.x; idx < 16 * 16; idx += 256) {        // (row, pair of output columns): 16 rows x 16 pairs = 32 columns
+  for (int idx = threadIdx.x; idx < 16 * 16; idx += 32 * NW) {        // (row, pair of output columns): 16 rows x 16 pairs = 32 columns
     const int row = idx >> 4, c2 = (idx & 15) * 2, m = m0 + row;
     if (m >= M) continue;
     float s0 = 0.f, s1 = 0.f;
     if (c2 < 8 * NL) {
       const int j = c2 >> 3, n = c2 & 7;
 #pragma unroll
-      for (int w = 0; w < 8; ++w) {
+      for (int w = 0; w < NW; ++w) {
         s0 += red[((w * NL + j) * 16 + row) * 8 + n];
         s1 += red[((w * NL + j) * 16 + row) * 8 + n + 1];
       }
@@ -679,6 +681,18 @@ extern "C" int mrb_lora_down_drop(const void* x, long long ldx, const void* A, l
   uint16_t* op = static_cast<uint16_t*>(out);
   if (lora_drop_mma()) {
     const unsigned grid = blocks_for(M, 16);
+    static int wide = -1;                 // MRB_LORA_DOWN_WIDE=0: 8 warps per block for every M (A/B measurements)
+    if (wide < 0) { const char* e = getenv("MRB_LORA_DOWN_WIDE"); wide = (e && e[0] == '0') ? 0 : 1; }
+    if (wide && M <= 128 && K >= 1024) {
+      switch (nlin) {
+        case 1: MRB_LAUNCH((lora_down_drop_mma_kernel<1, 16>), grid, 512, 0, STREAM, xp, ldx, Ap, lda, M, K, op, ldo, dtype, d); break;
+        case 2: MRB_LAUNCH((lora_down_drop_mma_kernel<2, 16>), grid, 512, 0, STREAM, xp, ldx, Ap, lda, M, K, op, ldo, dtype, d); break;
+        case 3: MRB_LAUNCH((lora_down_drop_mma_kernel<3, 16>), grid, 512, 0, STREAM, xp, ldx, Ap, lda, M, K, op, ldo, dtype, d); break;
+        default: return MRB_ERR_ARG;
+      }
+      MRB_CHECK_LAUNCH();
+      return MRB_OK;
+    }
     switch (nlin) {
       case 1: MRB_LAUNCH((lora_down_drop_mma_kernel<1>), grid, 256, 0, STREAM, xp, ldx, Ap, lda, M, K, op, ldo, dtype, d); break;
       case 2: MRB_LAUNCH((lora_down_drop_mma_kernel<2>), grid, 256, 0, STREAM, xp, ldx, Ap, lda, M, K, op, ldo, dtype, d); break;

@@ -497,10 +497,14 @@ static int pick_bn(int M, int N, int sms) {
 
 // Arrival counters of the folded split-K reduce for the workspace `ws` (one workspace per issuing stream, so launches that
 // share a slot are stream-ordered): a slot of g_splitk_counters per distinct workspace address.  nullptr -> two-pass path
-// (MRB_SPLITK_FUSED=0, more output tiles than counters, or more than SPLITK_SLOTS workspaces).
+// (the default; more output tiles than counters; more than SPLITK_SLOTS workspaces).
+// OFF by default, MRB_SPLITK_FUSED=1 enables: measured on a B200 (call 26) the decoder chain went from 18.8 to 27.3 ms in-graph
+// with it -- the last CTA of a tile reads splits x 64 x BN fp32 through ONE SM's L2 port as dependent round trips, where the
+// separate reduce launch spreads the same bytes over >= 128 blocks in 4.6 us.  Kept (bit-identical to the two-pass result,
+// tests/test_splitk_gpu.py) as the measured negative result.
 static int* splitk_counters_for(const void* ws, int tiles) {
   static int fused = -1;
-  if (fused < 0) { const char* e = getenv("MRB_SPLITK_FUSED"); fused = (e && e[0] == '0') ? 0 : 1; }
+  if (fused < 0) { const char* e = getenv("MRB_SPLITK_FUSED"); fused = (e && e[0] == '1') ? 1 : 0; }
   if (!fused || tiles > SPLITK_COUNTERS) return nullptr;
   static std::mutex mu;
   static const void* owner[SPLITK_SLOTS] = {};
@@ -516,6 +520,34 @@ static int* splitk_counters_for(const void* ws, int tiles) {
     if (owner[i] == nullptr) { owner[i] = ws; return base + i * SPLITK_COUNTERS; }
   }
   return nullptr;
+}
+
+// Per-stream SM cap of the persistent GEMM kernels (mrb_stream_sm_limit).  A CTA of the 2-CTA kernel owns the whole shared
+// memory of its SM for the length of the launch, so a GEMM on a SIDE stream that takes all SMs stalls the dependent chain of
+// small kernels on the main stream for that long (the T5 decoder: 48 encoder-sized cross-attention K/V GEMMs next to ~1 500
+// decoder-sized kernels); capped, it leaves SMs to the chain and the two really overlap.
+static std::mutex g_sm_limit_mu;
+static const void* g_sm_limit_stream[8] = {};
+static int g_sm_limit_value[8] = {};
+static int sms_for_stream(const void* stream) {
+  std::lock_guard<std::mutex> lock(g_sm_limit_mu);
+  for (int i = 0; i < 8; ++i)
+    if (g_sm_limit_value[i] > 0 && g_sm_limit_stream[i] == stream) return g_sm_limit_value[i] < g_num_sms ? g_sm_limit_value[i] : g_num_sms;
+  return g_num_sms;
+}
+
+extern "C" int mrb_stream_sm_limit(void* stream, int sms) {
+  if (sms < 0 || (sms & 1)) return MRB_ERR_ARG;
+  std::lock_guard<std::mutex> lock(g_sm_limit_mu);
+  int free_slot = -1;
+  for (int i = 0; i < 8; ++i) {
+    if (g_sm_limit_value[i] > 0 && g_sm_limit_stream[i] == stream) { g_sm_limit_value[i] = sms; return MRB_OK; }
+    if (g_sm_limit_value[i] == 0 && free_slot < 0) free_slot = i;
+  }
+  if (sms == 0) return MRB_OK;
+  if (free_slot < 0) return MRB_ERR_UNSUPPORTED;
+  g_sm_limit_stream[free_slot] = stream; g_sm_limit_value[free_slot] = sms;
+  return MRB_OK;
 }
 
 extern "C" int mrb_gemm2_launch(const CUtensorMap* tmA, const CUtensorMap* tmB, int M, int N, int K, int dtype,
@@ -545,7 +577,7 @@ static int gemm_impl(const void* A, long long lda, const void* B, long long ldb,
     rc2 = make_tmap(&tmB2, B, dtype, N, K, ldb, 128);
     if (rc2) return rc2;
     return mrb_gemm2_launch(&tmA2, &tmB2, M, N, K, dtype, bias, gelu, resid, ldr, out, out_dtype, ldc, row_group,
-                            g_num_sms, stream);
+                            sms_for_stream(stream), stream);
   }
   int bn = force_bn ? force_bn : pick_bn(M, N, g_num_sms);
   SplitPlan plan = {bn, 1, 0};

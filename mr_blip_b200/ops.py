@@ -59,6 +59,11 @@ class phase:
         return False
 
 
+def stream_sm_limit(stream, sms):
+    """GEMMs launched on `stream` occupy at most `sms` SMs (even; 0 = no cap): csrc/gemm.cu mrb_stream_sm_limit."""
+    _lib.call("mrb_stream_sm_limit", stream.cuda_stream, int(sms))
+
+
 def _stream():
     return torch.cuda.current_stream().cuda_stream
 

@@ -231,6 +231,11 @@ class T5Engine:
         self.overlap = os.environ.get("MRB_OVERLAP", "1") != "0"
         self.side = torch.cuda.Stream()
         ops.splitk_register(self.side)
+        # SM cap of the side stream's GEMMs (the decoder's 48 encoder-sized cross K/V GEMMs): uncapped, each holds every SM's
+        # shared memory for ~100 us and the main chain's small kernels wait behind it.  MRB_SIDE_SMS=0 lifts the cap.
+        self.side_sms = int(os.environ.get("MRB_SIDE_SMS", "0"))
+        if self.overlap and self.side_sms > 0:
+            ops.stream_sm_limit(self.side, self.side_sms)
         self._hold = []
         self._side_open = False
 

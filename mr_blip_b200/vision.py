@@ -265,6 +265,48 @@ class QFormerEngine:
             return h, h16, ie32, outs
         return h, h16
 
+    def time_xattn_path(self, frames, train=True, reps=10):
+        """The kernels of the cross-attention path ALONE -- the batched K/V projection GEMM of the 6 cross-attention layers and the
+        6 attention cores, same shapes, strides and dropout sites as forward() -- back to back in one CUDA graph, replayed `reps`
+        times between two events: ms per pass.  (CUDA events around the eager calls of forward() also count the launch gap in
+        front of every small kernel, the host being the slower side there.)  Inputs are random: the kernels' time does not
+        depend on the values."""
+        from .dropout import DropState
+        d = self.d
+        Hq, nq, T, heads = d.qf_hidden, d.num_query, d.vit_tokens, d.qf_heads
+        hd, M = Hq // heads, frames * nq
+        g = torch.Generator(device="cuda").manual_seed(0)
+        ie16 = torch.randn((frames * T, d.vit_width), device="cuda", generator=g).to(H16)
+        qc = (torch.randn((M, Hq), device="cuda", generator=g) * 0.5).to(H16)
+        ctx = torch.empty((M, Hq), dtype=H16, device="cuda")
+        kv = torch.empty((frames * T, self.n_cross * 2 * Hq), dtype=H16, device="cuda")
+        kv_rs = kv.shape[1]
+        drop = DropState() if train else None
+        cross = [(li, L["cross"]) for li, L in enumerate(self.layers) if L["cross"] is not None]
+
+        def path():
+            ops.gemm(ie16, self.kv_w, out=kv, bias=self.kv_b)
+            for li, c in cross:
+                kbase = kv[:, c["idx"] * 2 * Hq:]
+                ops.attention_fwd(qc, kbase, kbase[:, Hq:], ctx, frames, heads, nq, T, hd, hd ** -0.5,
+                                  (nq * Hq, Hq), (T * kv_rs, kv_rs), (T * kv_rs, kv_rs), (nq * Hq, Hq),
+                                  drop=drop.attn(dr.site(dr.QF, li, dr.CROSS_P), drop.qformer) if drop is not None else None)
+
+        path()
+        torch.cuda.synchronize()
+        gr = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(gr, capture_error_mode="thread_local"):
+            path()
+        for _ in range(2):
+            gr.replay()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            gr.replay()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / reps
+
     def project(self, h16):
         """t5_proj (blip2_mr.py:491): fp32 [F*32, 2048]."""
         return ops.gemm(h16, self.proj_w16, bias=self.proj_b, out_dtype=torch.float32)

@@ -807,7 +807,8 @@ def test_dropout_kernel_source_runs_on_host_shim_and_matches_oracle(dropout_kern
     assert _relfro(dab[:, :Fd], a.grad) < 6e-3 and _relfro(dab[:, Fd:2 * Fd], b.grad) < 6e-3
     # ---- LoRA input dropout: forward down-projection (both lane layouts), dA, dx (16-bit and fp32)
     p, site0 = 0.05, 0x2108
-    for M, K, nlin in ((21, 520, 3), (2051, 264, 2), (70, 256, 1)):          # K not a multiple of the 256-column tile; M over / under 2048
+    for M, K, nlin in ((21, 520, 3), (2051, 264, 2), (70, 256, 1), (37, 1096, 3)):   # K not a multiple of the 256-column tile; M over / under 2048;
+        #                                                                       M <= 128 and K >= 1024: 16 warps split K in the down-projection
         x_ext = torch.zeros((M, K + 32), dtype=torch.bfloat16)
         x_ext[:, :K] = _bf16(torch.randn(M, K, generator=g))
         A = torch.zeros((32, K), dtype=torch.bfloat16)
