@@ -440,6 +440,9 @@ def run_b200(args, cfg_name, cfg):
         ops.GEMM_PROFILE = []
         samples["video"] = video_dev
         model.cuda_graphs = False                  # per-launch CUDA events need the eager launch sequence
+        vit_engine = model.engines()[0]
+        vit_split, vit_engine.split = vit_engine.split, False      # ... and ONE stream in the ViT (the two-stream block loop
+        #                                                            overlaps kernels, an event pair would time both halves)
         t5_engine = model.engines()[2]
         dg, t5_engine.decode_graphs = t5_engine.decode_graphs, False
         if train:
@@ -448,6 +451,7 @@ def run_b200(args, cfg_name, cfg):
             model.generate(samples, num_beams=cfg["beams"], max_length=cfg["max_new_tokens"])
         torch.cuda.synchronize()
         model.cuda_graphs, t5_engine.decode_graphs = True, dg
+        vit_engine.split = vit_split
         prof, ops.GEMM_PROFILE = ops.GEMM_PROFILE, None
         xev, qf_engine.xattn_events = qf_engine.xattn_events, None
         x_ms = sum(a.elapsed_time(b) for a, b in xev)

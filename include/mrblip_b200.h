@@ -176,6 +176,17 @@ int mrb_dropout(const void* x, long long ldx, void* out, long long ldo, int rows
 /* out = resid + drop(branch), fp32 [rows, cols] contiguous: hidden + dropout(sublayer) (modeling_t5.py:346,652,690) */
 int mrb_dropout_add(const float* resid, const float* branch, float* out, int rows, int cols, const unsigned* seed,
                     unsigned site, float p, void* stream);
+/* sum_out = x + drop(add) and out_h = T5LayerNorm(sum_out) * w as a 16-bit operand [rows, ld_h]: the residual add under dropout
+ * (modeling_t5.py:346,652,690) fused with the next sublayer's norm (:263-277); = mrb_dropout_add then mrb_norm(mode 1), bit for
+ * bit.  C % 4 == 0, C <= 2048; x, add, sum_out fp32 [rows, C] contiguous (sum_out may alias neither). */
+int mrb_dropout_add_norm(const float* x, const float* add, const float* w, float eps, int rows, int C, void* out_h, int h_dtype,
+                         long long ld_h, float* sum_out, const unsigned* seed, unsigned site, float p, void* stream);
+/* mrb_rmsnorm_bwd (frozen weight, no LoRA fold) that also emits dy_next = drop_site(dres) as a 16-bit operand [rows, ld_next]:
+ * the masked gradient the next sublayer's backward starts from (autograd of hidden + dropout(branch), modeling_t5.py:346,652,690),
+ * = mrb_rmsnorm_bwd then mrb_dropout(fp32 -> 16 bit), bit for bit. */
+int mrb_rmsnorm_bwd_drop(const float* x, const float* w, const void* dy, int dy_dtype, long long ld_dy, float eps, int rows, int C,
+                         float* dres, void* dy_next, int next_dtype, long long ld_next, const unsigned* seed, unsigned site, float p,
+                         void* stream);
 /* mrb_gated_gelu_fwd / _bwd with the FF-inner dropout (modeling_t5.py:327): h = drop(gelu(a) * b) */
 int mrb_gated_gelu_fwd_drop(const void* ab, void* h, int M, int F, long long ldh, int dtype, const unsigned* seed,
                             unsigned site, float p, void* stream);

@@ -58,6 +58,8 @@ SIGNATURES = {
                                _i, _i, _i, _i, _i, _i, _f, _p, _i, _i, _p, _i, _i, _p, _p, _p, _u, _f, _p],
     "mrb_dropout": [_p, _ll, _p, _ll, _i, _i, _i, _i, _p, _u, _f, _p],
     "mrb_dropout_add": [_p, _p, _p, _i, _i, _p, _u, _f, _p],
+    "mrb_dropout_add_norm": [_p, _p, _p, _f, _i, _i, _p, _i, _ll, _p, _p, _u, _f, _p],
+    "mrb_rmsnorm_bwd_drop": [_p, _p, _p, _i, _ll, _f, _i, _i, _p, _p, _i, _ll, _p, _u, _f, _p],
     "mrb_gated_gelu_fwd_drop": [_p, _p, _i, _i, _ll, _i, _p, _u, _f, _p],
     "mrb_gated_gelu_bwd_drop": [_p, _p, _ll, _p, _ll, _i, _i, _i, _p, _u, _f, _p],
     "mrb_lora_down_drop": [_p, _ll, _p, _ll, _i, _i, _i, _p, _ll, _i, _p, _u, _f, _p],

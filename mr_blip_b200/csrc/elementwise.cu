@@ -3,6 +3,7 @@
 // (blip2_mr.py:691-783), embedding lookup, cross-entropy, LoRA down-projection and LoRA weight
 // gradients, casts/transposes.  All are one pass over their operands with 16-byte accesses.
 #include "common.cuh"
+#include "dropmask.cuh"
 
 namespace mrb {
 
@@ -81,11 +82,14 @@ __global__ void __launch_bounds__(256) norm_row_kernel(const float* __restrict__
                                                        const float* __restrict__ w, const float* __restrict__ bias, float eps,
                                                        int rows, int C, int mode, float* __restrict__ out_f32,
                                                        void* __restrict__ out_h, int h_dtype, long long ld_h,
-                                                       float* __restrict__ sum_out) {
+                                                       float* __restrict__ sum_out, const DropSpec dsp) {
   mrb::pdl_trigger();
   mrb::pdl_wait();      // before the first global access (common.cuh, MRB_PDL)
   __shared__ float red[2][8];
   const int row = blockIdx.x, nv = C >> 2, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // dsp.seed != null: `add` is a sublayer output under train-mode dropout -- x + drop(add) is the new residual stream (sum_out)
+  // and its norm the next sublayer's input: dropout_add_kernel + this kernel in one pass (same arithmetic, same order)
+  const uint32_t dkey = dsp.seed ? drop_key(*dsp.seed, dsp.site) : 0u, drow = static_cast<uint32_t>(row) * static_cast<uint32_t>(nv);
   const float4* xr = reinterpret_cast<const float4*>(x + static_cast<long long>(row) * C);
   const float4* ar = add ? reinterpret_cast<const float4*>(add + static_cast<long long>(row) * C) : nullptr;
   const float4* wr = reinterpret_cast<const float4*>(w);
@@ -100,7 +104,15 @@ __global__ void __launch_bounds__(256) norm_row_kernel(const float* __restrict__
       v[i] = xr[c];
       ww[i] = wr[c];
       if (br) bb[i] = br[c];
-      if (ar) { const float4 a = ar[c]; v[i].x += a.x; v[i].y += a.y; v[i].z += a.z; v[i].w += a.w; }
+      if (ar) {
+        float4 a = ar[c];
+        if (dsp.seed) {
+          const uint32_t w = drop_word(dkey, drow, static_cast<uint32_t>(c));
+          a.x = drop_keep(w, 0, dsp.thr) ? a.x * dsp.scale : 0.f; a.y = drop_keep(w, 1, dsp.thr) ? a.y * dsp.scale : 0.f;
+          a.z = drop_keep(w, 2, dsp.thr) ? a.z * dsp.scale : 0.f; a.w = drop_keep(w, 3, dsp.thr) ? a.w * dsp.scale : 0.f;
+        }
+        v[i].x += a.x; v[i].y += a.y; v[i].z += a.z; v[i].w += a.w;
+      }
       s += v[i].x + v[i].y + v[i].z + v[i].w;
     }
   }
@@ -222,7 +234,8 @@ __global__ void __launch_bounds__(256) rmsnorm_bwd_kernel(const float* __restric
 // 64 warps fit an SM, and the two row sums meet in shared memory in a fixed order.
 __global__ void __launch_bounds__(256) rmsnorm_bwd_row_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                                               const void* __restrict__ dy, int dy_dtype, long long ld, float eps,
-                                                              int rows, int C, float* __restrict__ dres) {
+                                                              int rows, int C, float* __restrict__ dres, const DropSpec dsp,
+                                                              uint16_t* __restrict__ dy_next, int next_dtype, long long ld_next) {
   mrb::pdl_trigger();
   mrb::pdl_wait();      // before the first global access (common.cuh, MRB_PDL)
   __shared__ float red[2][8];
@@ -269,6 +282,16 @@ __global__ void __launch_bounds__(256) rmsnorm_bwd_row_kernel(const float* __res
       o.x += gv[i].x * rstd - xv[i].x * coef; o.y += gv[i].y * rstd - xv[i].y * coef;
       o.z += gv[i].z * rstd - xv[i].z * coef; o.w += gv[i].w * rstd - xv[i].w * coef;
       out[c] = o;
+      if (dy_next) {
+        // the next sublayer's backward starts from this gradient under ITS residual-dropout mask, as a 16-bit dgrad operand
+        // (dropout_kernel<2> of csrc/dropout.cu, here without re-reading the fp32 gradient)
+        const uint32_t w = drop_word(drop_key(*dsp.seed, dsp.site), static_cast<uint32_t>(row) * static_cast<uint32_t>(nv),
+                                     static_cast<uint32_t>(c));
+        const float m0 = drop_keep(w, 0, dsp.thr) ? o.x * dsp.scale : 0.f, m1 = drop_keep(w, 1, dsp.thr) ? o.y * dsp.scale : 0.f;
+        const float m2 = drop_keep(w, 2, dsp.thr) ? o.z * dsp.scale : 0.f, m3 = drop_keep(w, 3, dsp.thr) ? o.w * dsp.scale : 0.f;
+        *reinterpret_cast<uint2*>(dy_next + static_cast<long long>(row) * ld_next + 4 * c) =
+            make_uint2(pack2(m0, m1, next_dtype), pack2(m2, m3, next_dtype));
+      }
     }
   }
 }
@@ -868,7 +891,9 @@ extern "C" int mrb_norm(const float* x, const float* add, const float* w, const 
   // (10 / 18 us per launch forward / backward, profiles/launch_summary_r02f.csv); a block per row issues every load at once.
   // MRB_NORM_ROW_SMALL=0 restores the warp-per-row kernels for them (A/B measurements).
   if (row_kernel && (rows > 2 * 148 || (C >= 1024 && small_rows_take_row_kernel()))) {
-    MRB_LAUNCH((norm_row_kernel), rows, 256, 0, STREAM, x, add, w, bias, eps, rows, C, mode, out_f32, out_h, h_dtype, ld_h, sum_out);
+    DropSpec none;
+    none.seed = nullptr; none.site = 0; none.thr = 0; none.scale = 1.f;
+    MRB_LAUNCH((norm_row_kernel), rows, 256, 0, STREAM, x, add, w, bias, eps, rows, C, mode, out_f32, out_h, h_dtype, ld_h, sum_out, none);
     MRB_CHECK_LAUNCH();
     return MRB_OK;
   }
@@ -888,11 +913,45 @@ extern "C" int mrb_rmsnorm_bwd(const float* x, const float* w, const void* dy, i
   static int row_kernel = -1;             // MRB_RMSNORM_BWD_ROW=0 keeps the warp-per-row kernel for large inputs (A/B measurements)
   if (row_kernel < 0) { const char* e = getenv("MRB_RMSNORM_BWD_ROW"); row_kernel = (e && e[0] == '0') ? 0 : 1; }
   if (row_kernel && !lora_A && (rows > 2 * 148 || (C >= 1024 && small_rows_take_row_kernel()))) {
-    MRB_LAUNCH((rmsnorm_bwd_row_kernel), rows, 256, 0, STREAM, x, w, dy, dy_dtype, ld_dy, eps, rows, C, dres);
+    DropSpec none;
+    none.seed = nullptr; none.site = 0; none.thr = 0; none.scale = 1.f;
+    MRB_LAUNCH((rmsnorm_bwd_row_kernel), rows, 256, 0, STREAM, x, w, dy, dy_dtype, ld_dy, eps, rows, C, dres, none,
+               static_cast<uint16_t*>(nullptr), 0, 0LL);
     MRB_CHECK_LAUNCH();
     return MRB_OK;
   }
   MRB_LAUNCH((rmsnorm_bwd_kernel<16>), blocks_for(rows, norm_warps(rows)), 32 * norm_warps(rows), 0, STREAM, x, w, dy, dy_dtype, ld_dy, lora_A, R, eps, rows, C, dres);
+  MRB_CHECK_LAUNCH();
+  return MRB_OK;
+}
+
+// sum_out = x + drop(add), out_h = RMSNorm(sum_out) * w: the residual add under train-mode dropout (modeling_t5.py:346,652,690)
+// and the next sublayer's T5LayerNorm (:263-277) in one pass over the row -- mrb_dropout_add followed by mrb_norm(mode 1), same
+// arithmetic in the same order (bit-identical), one launch and one read of the residual stream less.
+extern "C" int mrb_dropout_add_norm(const float* x, const float* add, const float* w, float eps, int rows, int C, void* out_h,
+                                    int h_dtype, long long ld_h, float* sum_out, const unsigned* seed, unsigned site, float p,
+                                    void* stream) {
+  if (rows <= 0) return MRB_OK;
+  if (!x || !add || !w || !out_h || !sum_out || !seed || (C & 3) || C > 2048 || (ld_h & 3) || p < 0.f || p >= 1.f) return MRB_ERR_ARG;
+  const DropSpec d = make_drop(seed, site, p);
+  MRB_LAUNCH((norm_row_kernel), rows, 256, 0, STREAM, x, add, w, static_cast<const float*>(nullptr), eps, rows, C, 1,
+             static_cast<float*>(nullptr), out_h, h_dtype, ld_h, sum_out, d);
+  MRB_CHECK_LAUNCH();
+  return MRB_OK;
+}
+
+// mrb_rmsnorm_bwd (weights frozen, no LoRA fold) that also writes dy_next = drop_site(dres) as a 16-bit operand [rows, ld_next]:
+// the gradient the NEXT sublayer's backward starts from (mrb_dropout fp32 -> 16 bit of the updated residual-stream gradient).
+extern "C" int mrb_rmsnorm_bwd_drop(const float* x, const float* w, const void* dy, int dy_dtype, long long ld_dy, float eps, int rows,
+                                    int C, float* dres, void* dy_next, int next_dtype, long long ld_next, const unsigned* seed,
+                                    unsigned site, float p, void* stream) {
+  if (rows <= 0) return MRB_OK;
+  if ((C & 3) || C > 2048 || (ld_dy & 3) || (ld_next & 3) || !dy_next || !seed || p < 0.f || p >= 1.f ||
+      (next_dtype != MRB_DT_F16 && next_dtype != MRB_DT_BF16))
+    return MRB_ERR_ARG;
+  const DropSpec d = make_drop(seed, site, p);
+  MRB_LAUNCH((rmsnorm_bwd_row_kernel), rows, 256, 0, STREAM, x, w, dy, dy_dtype, ld_dy, eps, rows, C, dres, d,
+             static_cast<uint16_t*>(dy_next), next_dtype, ld_next);
   MRB_CHECK_LAUNCH();
   return MRB_OK;
 }

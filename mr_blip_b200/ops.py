@@ -329,6 +329,23 @@ def dropout(x, out, rows, cols, seed, site, p):
     return out
 
 
+def dropout_add_norm(resid, branch, out, w, eps, xn, seed, site, p):
+    """out = resid + drop(branch) (fp32, contiguous) and xn[:, :C] = T5 RMSNorm(out) * w (16-bit, row stride xn.stride(0)): one pass."""
+    assert resid.is_contiguous() and branch.is_contiguous() and out.is_contiguous() and xn.stride(1) == 1
+    rows, C = branch.shape
+    _lib.call("mrb_dropout_add_norm", resid.data_ptr(), branch.data_ptr(), w.data_ptr(), float(eps), rows, C, xn.data_ptr(),
+              _DT[xn.dtype], xn.stride(0), out.data_ptr(), seed.data_ptr(), site, float(p), _stream())
+    return out
+
+
+def rmsnorm_bwd_drop(x, w, dy, eps, dres, dy_next, seed, site, p):
+    """rmsnorm_bwd that also writes dy_next[:, :C] = drop_site(dres) (16-bit): the next sublayer's masked dgrad operand."""
+    rows, C = x.shape
+    assert dres.is_contiguous() and x.is_contiguous() and dy_next.stride(1) == 1
+    _lib.call("mrb_rmsnorm_bwd_drop", x.data_ptr(), w.data_ptr(), dy.data_ptr(), _DT[dy.dtype], dy.stride(0), float(eps), rows, C,
+              dres.data_ptr(), dy_next.data_ptr(), _DT[dy_next.dtype], dy_next.stride(0), seed.data_ptr(), site, float(p), _stream())
+
+
 def dropout_add(resid, branch, out, seed, site, p):
     """out = resid + drop(branch): fp32 [rows, cols], all contiguous."""
     assert resid.is_contiguous() and branch.is_contiguous() and out.is_contiguous()

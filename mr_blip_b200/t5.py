@@ -232,12 +232,18 @@ class T5Engine:
         self.side = torch.cuda.Stream()
         ops.splitk_register(self.side)
         # SM cap of the side stream's GEMMs (the decoder's 48 encoder-sized cross K/V GEMMs): uncapped, each holds every SM's
-        # shared memory for ~100 us and the main chain's small kernels wait behind it.  MRB_SIDE_SMS=0 lifts the cap.
-        self.side_sms = int(os.environ.get("MRB_SIDE_SMS", "0"))
+        # shared memory for ~100 us and the main chain's small kernels wait behind it.  Decoder chain in-graph on a B200 (call 27):
+        # 18.36 ms uncapped, 17.73 at 132 SMs, 17.88 / 17.74 / 18.12 at 116 / 100 / 84.  MRB_SIDE_SMS=0 lifts the cap.
+        self.side_sms = int(os.environ.get("MRB_SIDE_SMS", "132"))
         if self.overlap and self.side_sms > 0:
             ops.stream_sm_limit(self.side, self.side_sms)
         self._hold = []
         self._side_open = False
+        # Train-mode fusions of the residual stream's elementwise passes (MRB_T5_FUSE_NORM=0 disables): dropout-add + the next
+        # T5LayerNorm in one kernel, RMSNorm backward + the next sublayer's masked 16-bit gradient in one kernel.
+        self.fuse_norm = os.environ.get("MRB_T5_FUSE_NORM", "1") != "0"
+        self._pre_norm = None                             # (residual stream, ln weight, normalised operand) of the fused add
+        self._pre_grad = None                             # (gradient stream, site, masked 16-bit operand) of the fused backward
 
         def grp(names):
             g = LoraGroup(get, names, scale, self)
@@ -367,6 +373,9 @@ class T5Engine:
     def _grad_ext(self, dh, M, site=None):
         """fp32 residual-stream gradient -> 16-bit extended dgrad operand [M, d_model + 32]; with `site` it is the gradient
         of hidden + dropout(branch) w.r.t. the branch, i.e. dh under that site's mask."""
+        pre, self._pre_grad = self._pre_grad, None
+        if pre is not None and pre[0] is dh and pre[1] == site:
+            return pre[2]                                    # written by the previous sublayer's fused RMSNorm backward
         dy = self._ext(M, self.d.d_model)
         if site is not None and self._p() > 0.0:
             ops.dropout(dh, dy, M, self.d.d_model, self.drop.word, site, self._p())
@@ -374,37 +383,61 @@ class T5Engine:
             ops.cast2d(dh, dy, M, self.d.d_model)
         return dy
 
-    def _branch(self, grp, x_ext, M, h, site):
+    def _branch(self, grp, x_ext, M, h, site, next_ln=None):
         """h + dropout(Linear(x)) (modeling_t5.py:346,652,690) -> new fp32 residual stream.  Eval mode: the residual add is
-        the GEMM's epilogue; train mode: the branch leaves the GEMM in fp32 and one pass applies mask and add."""
+        the GEMM's epilogue; train mode: the branch leaves the GEMM in fp32 and one pass applies mask and add -- and, when the
+        caller names the T5LayerNorm weight that reads the new stream next (`next_ln`), that norm too (picked up by _norm_ext)."""
         out = torch.empty_like(h)
         if self._p() > 0.0:
             br = grp.forward(x_ext, M, out_dtype=torch.float32)
+            if next_ln is not None and self.fuse_norm:
+                xn = self._ext(M, self.d.d_model)
+                ops.dropout_add_norm(h, br, out, next_ln, self.d.t5_ln_eps, xn, self.drop.word, site, self._p())
+                self._pre_norm = (out, next_ln, xn)
+                return out
             return ops.dropout_add(h, br, out, self.drop.word, site, self._p())
         grp.forward(x_ext, M, out=out, resid=h)
         return out
+
+    def _norm_ext(self, h, ln, M):
+        """T5LayerNorm(h) * ln as an extended 16-bit operand [M, d_model + 32] (modeling_t5.py:263-277)."""
+        pre, self._pre_norm = self._pre_norm, None
+        if pre is not None and pre[0] is h and pre[1] is ln:
+            return pre[2]                                    # written by the fused residual add of the previous sublayer
+        xn = self._ext(M, self.d.d_model)
+        ops.norm(h, ln, None, self.d.t5_ln_eps, 1, out_h=xn)
+        return xn
+
+    def _rmsnorm_bwd(self, x, ln, dy, dh, M, next_site=None):
+        """dh += T5LayerNorm'(x; ln) . dy; with `next_site` (the residual-dropout site of the sublayer whose backward runs next)
+        the same pass writes that sublayer's masked 16-bit dgrad operand (picked up by _grad_ext)."""
+        if next_site is not None and self._p() > 0.0 and self.fuse_norm:
+            dyn = self._ext(M, self.d.d_model)
+            ops.rmsnorm_bwd_drop(x, ln, dy, self.d.t5_ln_eps, dh, dyn, self.drop.word, next_site, self._p())
+            self._pre_grad = (dh, next_site, dyn)
+            return
+        ops.rmsnorm_bwd(x, ln, dy, self.d.t5_ln_eps, dh)
 
     def _drop_inplace(self, t, rows, cols, site):
         if self._p() > 0.0:
             ops.dropout(t, t, rows, cols, self.drop.word, site, self._p())
         return t
 
-    def _ff(self, L, h, M, save):
+    def _ff(self, L, h, M, save, next_ln=None):
         d = self.d
-        xn = self._ext(M, d.d_model)
-        ops.norm(h, L["ln_ff"], None, d.t5_ln_eps, 1, out_h=xn)
+        xn = self._norm_ext(h, L["ln_ff"], M)
         ab = L["wi"].forward(xn, M)
         hm = self._ext(M, d.d_ff)
         if self._p() > 0.0:
             ops.gated_gelu_fwd_drop(ab, hm, M, d.d_ff, self.drop.word, self._site(L, dr.FF_INNER), self._p())
         else:
             ops.gated_gelu_fwd(ab, hm, M, d.d_ff)
-        h2 = self._branch(L["wo"], hm, M, h, self._site(L, dr.FF_RES))
+        h2 = self._branch(L["wo"], hm, M, h, self._site(L, dr.FF_RES), next_ln)
         if save is not None:
             save.update(ff_x=h, ff_xn=xn, ff_ab=ab, ff_hm=hm)
         return h2
 
-    def _ff_bwd(self, L, s, dh, M):
+    def _ff_bwd(self, L, s, dh, M, next_site=None):
         """dh (fp32 residual-stream gradient) is updated in place."""
         d = self.d
         dhm = L["wo"].backward(self._grad_ext(dh, M, self._site(L, dr.FF_RES)), s["ff_hm"], M)          # [M, d_ff]
@@ -414,7 +447,7 @@ class T5Engine:
         else:
             ops.gated_gelu_bwd(s["ff_ab"], dhm, dab, M, d.d_ff)
         dxn = L["wi"].backward(dab, s["ff_xn"], M)
-        ops.rmsnorm_bwd(s["ff_x"], L["ln_ff"], dxn, d.t5_ln_eps, dh)
+        self._rmsnorm_bwd(s["ff_x"], L["ln_ff"], dxn, dh, M, next_site)
 
     # ------------------------------------------------------------------ encoder
     def encoder_forward(self, x, kmask, B, L, save=None):
@@ -429,21 +462,19 @@ class T5Engine:
         for li, layer in enumerate(self.enc):
             layer["ln_ff"] = layer["ln1"]
             s = {} if save is not None else None
-            xn = self._ext(M, d.d_model)
-            ops.norm(h, layer["ln0"], None, d.t5_ln_eps, 1, out_h=xn)
+            xn = self._norm_ext(h, layer["ln0"], M)
             qkv = self._ext(M, 3 * inner)                    # ext width so that dqkv can share the layout
             layer["qkv"].forward(xn, M, out=qkv[:, :3 * inner])
             ao = self._ext(M, d.d_model)
             lse = torch.empty((B, d.t5_heads, L), dtype=torch.float32, device="cuda") if save is not None else None
             self._self_attn(qkv, ao, B, L, bias, kmask, False, lse, self._site(layer, dr.SELF_P))
-            h1 = self._branch(layer["o"], ao, M, h, self._site(layer, dr.SELF_RES))
+            h1 = self._branch(layer["o"], ao, M, h, self._site(layer, dr.SELF_RES), layer["ln_ff"])
             if s is not None:
                 s.update(x=h, xn=xn, qkv=qkv, ao=ao, lse=lse)
-            h = self._ff(layer, h1, M, s)
+            h = self._ff(layer, h1, M, s, self.enc[li + 1]["ln0"] if li + 1 < len(self.enc) else self.enc_final_ln)
             if save is not None:
                 save.append(s)
-        out = self._ext(M, d.d_model)
-        ops.norm(h, self.enc_final_ln, None, d.t5_ln_eps, 1, out_h=out)
+        out = self._norm_ext(h, self.enc_final_ln, M)
         self._drop_inplace(out[:, :d.d_model], M, d.d_model, dr.site(dr.ENC, 0, dr.FINAL))      # modeling_t5.py:1258
         return out, h, bias
 
@@ -453,11 +484,11 @@ class T5Engine:
         M = B * L
         dh = torch.zeros((M, d.d_model), dtype=torch.float32, device="cuda")
         self._drop_inplace(d_enc_out, M, d.d_model, dr.site(dr.ENC, 0, dr.FINAL))
-        ops.rmsnorm_bwd(h_last, self.enc_final_ln, d_enc_out, d.t5_ln_eps, dh)
+        self._rmsnorm_bwd(h_last, self.enc_final_ln, d_enc_out, dh, M, self._site(self.enc[-1], dr.FF_RES))
         inner = d.t5_heads * d.d_kv
         ws = torch.empty((B * d.t5_heads * L,), dtype=torch.float32, device="cuda")
         for layer, s in zip(reversed(self.enc), reversed(saves)):
-            self._ff_bwd(layer, s, dh, M)
+            self._ff_bwd(layer, s, dh, M, self._site(layer, dr.SELF_RES))
             dao = layer["o"].backward(self._grad_ext(dh, M, self._site(layer, dr.SELF_RES)), s["ao"], M)   # [M, D] = dO of the attention
             qkv = s["qkv"]
             rs = qkv.stride(0)
@@ -468,7 +499,8 @@ class T5Engine:
                               (L * s["ao"].stride(0), s["ao"].stride(0)), (L * dao.stride(0), dao.stride(0)), s["lse"], ws,
                               bias=bias, bias_zero=L - 1, kmask=kmask, causal=False, drop=self._pdrop(self._site(layer, dr.SELF_P)))
             dxn = layer["qkv"].backward(dqkv, s["xn"], M)
-            ops.rmsnorm_bwd(s["x"], layer["ln0"], dxn, d.t5_ln_eps, dh)
+            self._rmsnorm_bwd(s["x"], layer["ln0"], dxn, dh, M,
+                              self._site(self.enc[layer["li"] - 1], dr.FF_RES) if layer["li"] > 0 else None)
             self.side_join()                                 # this layer's weight-gradient reductions are done
             s.clear()
         return self._drop_inplace(dh, M, d.d_model, dr.site(dr.ENC, 0, dr.EMB))      # d inputs_embeds through the input dropout
@@ -496,17 +528,15 @@ class T5Engine:
         for li, layer in enumerate(self.dec):
             layer["ln_ff"] = layer["ln2"]
             s = {} if save is not None else None
-            xn = self._ext(M, d.d_model)
-            ops.norm(h, layer["ln0"], None, d.t5_ln_eps, 1, out_h=xn)
+            xn = self._norm_ext(h, layer["ln0"], M)
             qkv = self._ext(M, 3 * inner)
             layer["qkv"].forward(xn, M, out=qkv[:, :3 * inner])
             ao = self._ext(M, d.d_model)
             lse = torch.empty((B, d.t5_heads, Ld), dtype=torch.float32, device="cuda") if save is not None else None
             self._self_attn(qkv, ao, B, Ld, bias, dmask, True, lse, self._site(layer, dr.SELF_P))
-            h1 = self._branch(layer["o"], ao, M, h, self._site(layer, dr.SELF_RES))
+            h1 = self._branch(layer["o"], ao, M, h, self._site(layer, dr.SELF_RES), layer["ln1"])
             # cross attention
-            xn2 = self._ext(M, d.d_model)
-            ops.norm(h1, layer["ln1"], None, d.t5_ln_eps, 1, out_h=xn2)
+            xn2 = self._norm_ext(h1, layer["ln1"], M)
             cq = self._ext(M, inner)
             layer["cq"].forward(xn2, M, out=cq[:, :inner])
             if self.overlap:
@@ -521,14 +551,13 @@ class T5Engine:
             ops.attention_fwd(cq, ckv, ckv[:, inner:], co, B, d.t5_heads, Ld, Le, d.d_kv, 1.0, (Ld * qs, qs),
                               (Le * ks, ks), (Le * ks, ks), (Ld * co.stride(0), co.stride(0)), kmask=enc_kmask, lse=lse2,
                               drop=self._pdrop(self._site(layer, dr.CROSS_P)))
-            h2 = self._branch(layer["co"], co, M, h1, self._site(layer, dr.CROSS_RES))
+            h2 = self._branch(layer["co"], co, M, h1, self._site(layer, dr.CROSS_RES), layer["ln_ff"])
             if s is not None:
                 s.update(x=h, xn=xn, qkv=qkv, ao=ao, lse=lse, x1=h1, xn2=xn2, cq=cq, ckv=ckv, co=co, lse2=lse2)
-            h = self._ff(layer, h2, M, s)
+            h = self._ff(layer, h2, M, s, self.dec[li + 1]["ln0"] if li + 1 < len(self.dec) else self.dec_final_ln)
             if save is not None:
                 save.append(s)
-        out = self._ext(M, d.d_model)
-        ops.norm(h, self.dec_final_ln, None, d.t5_ln_eps, 1, out_h=out)
+        out = self._norm_ext(h, self.dec_final_ln, M)
         self._drop_inplace(out[:, :d.d_model], M, d.d_model, dr.site(dr.DEC, 0, dr.FINAL))
         self.side_join()
         return out, h, bias
@@ -541,11 +570,11 @@ class T5Engine:
         inner = d.t5_heads * d.d_kv
         dh = torch.zeros((M, d.d_model), dtype=torch.float32, device="cuda")
         self._drop_inplace(d_out[:, :d.d_model], M, d.d_model, dr.site(dr.DEC, 0, dr.FINAL))
-        ops.rmsnorm_bwd(h_last, self.dec_final_ln, d_out, d.t5_ln_eps, dh)
+        self._rmsnorm_bwd(h_last, self.dec_final_ln, d_out, dh, M, self._site(self.dec[-1], dr.FF_RES))
         d_enc = torch.zeros((Me, d.d_model), dtype=torch.float32, device="cuda")
         ws = torch.empty((B * d.t5_heads * Ld,), dtype=torch.float32, device="cuda")
         for layer, s in zip(reversed(self.dec), reversed(saves)):
-            self._ff_bwd(layer, s, dh, M)
+            self._ff_bwd(layer, s, dh, M, self._site(layer, dr.CROSS_RES))
             # cross attention
             dco = layer["co"].backward(self._grad_ext(dh, M, self._site(layer, dr.CROSS_RES)), s["co"], M)
             cq, ckv = s["cq"], s["ckv"]
@@ -567,7 +596,7 @@ class T5Engine:
                 layer["ckv"].down(enc_ext, Me)               # recompute this layer's x.A^T columns of the shared input
                 layer["ckv"].backward(dckv, enc_ext, Me, out=d_enc, resid=d_enc)     # accumulates over the 24 layers
             dxn2 = layer["cq"].backward(dcq, s["xn2"], M)
-            ops.rmsnorm_bwd(s["x1"], layer["ln1"], dxn2, d.t5_ln_eps, dh)
+            self._rmsnorm_bwd(s["x1"], layer["ln1"], dxn2, dh, M, self._site(layer, dr.SELF_RES))
             # self attention
             dao = layer["o"].backward(self._grad_ext(dh, M, self._site(layer, dr.SELF_RES)), s["ao"], M)
             qkv = s["qkv"]
@@ -579,7 +608,8 @@ class T5Engine:
                               (Ld * s["ao"].stride(0), s["ao"].stride(0)), (Ld * dao.stride(0), dao.stride(0)), s["lse"], ws,
                               bias=bias, bias_zero=Ld - 1, kmask=dmask, causal=True, drop=self._pdrop(self._site(layer, dr.SELF_P)))
             dxn = layer["qkv"].backward(dqkv, s["xn"], M)
-            ops.rmsnorm_bwd(s["x"], layer["ln0"], dxn, d.t5_ln_eps, dh)
+            self._rmsnorm_bwd(s["x"], layer["ln0"], dxn, dh, M,
+                              self._site(self.dec[layer["li"] - 1], dr.FF_RES) if layer["li"] > 0 else None)
             if not self.overlap:
                 s.clear()
         self.side_join()                                     # d_enc is complete; saved activations may go

@@ -39,7 +39,7 @@ class VitEngine:
         # captured step) next to the tcgen05 kernel that handles the two full tiles.  MRB_OVERLAP=0 disables.
         import os
         self.overlap = os.environ.get("MRB_OVERLAP", "1") != "0"
-        self.split = self.overlap and os.environ.get("MRB_VIT_SPLIT", "0") == "1"
+        self.split = self.overlap and os.environ.get("MRB_VIT_SPLIT", "1") == "1"
         self.side = torch.cuda.Stream()
         ops.splitk_register(self.side)
         self.blocks = []
@@ -84,7 +84,10 @@ class VitEngine:
             # Frames are independent in the ViT: the two halves of the batch run the 39 blocks on two streams (forked / joined
             # inside the captured step).  The persistent GEMM / attention kernels of the two halves cannot share an SM (shared
             # memory), so they alternate -- but the HBM-bound LayerNorms of one half run under the other half's tensor-core
-            # kernels, and a kernel's last partial wave is filled by the other stream's next kernel.  MRB_VIT_SPLIT=0 disables.
+            # kernels, and a kernel's last partial wave is filled by the other stream's next kernel.  B200, alternating runs on
+            # one box: 255.0 / 251.7 -> 253.6 / 249.9 ms per step (call 25), 251.2 / 253.3 -> 249.9 (call 27).  MRB_VIT_SPLIT=0
+            # disables; per-launch CUDA-event timing (bench.py's roofline pass) sets self.split = False, overlapping kernels of
+            # two streams would be timed into each other.
             Fa = F_ // 2
             main = torch.cuda.current_stream()
             self.side.wait_stream(main)

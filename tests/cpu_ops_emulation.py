@@ -30,6 +30,10 @@ def splitk_register(side_stream=None):
     pass
 
 
+def stream_sm_limit(stream, sms):
+    pass
+
+
 @contextlib.contextmanager
 def phase(name):
     yield
@@ -313,6 +317,18 @@ def dropout_add(resid, branch, out, seed, site, p):
     return out
 
 
+def dropout_add_norm(resid, branch, out, w, eps, xn, seed, site, p):
+    dropout_add(resid, branch, out, seed, site, p)
+    norm(out, w, None, eps, 1, out_h=xn)
+    return out
+
+
+def rmsnorm_bwd_drop(x, w, dy, eps, dres, dy_next, seed, site, p):
+    rmsnorm_bwd(x, w, dy, eps, dres)
+    rows, C = x.shape
+    dropout(dres, dy_next, rows, C, seed, site, p)
+
+
 def lora_down_drop(x, A_down, out, M, K, nlin, seed, site0, p):
     out[:M, :32] = 0
     for j in range(nlin):
@@ -407,6 +423,8 @@ class HostCAbi:
             (q, q_bs, q_rs, k, k_bs, k_rs, v, v_bs, v_rs, o, o_bs, o_rs, frames, H, L, hd, dt, scale, st) = args
             return self.call("mrb_attention_fwd", q, q_bs, q_rs, k, k_bs, k_rs, v, v_bs, v_rs, o, o_bs, o_rs, frames, H, L, L, hd, dt,
                              scale, None, 0, 0, None, 1, 0, 0, None, st)
+        if name == "mrb_stream_sm_limit":                    # scheduling only
+            return None
         if name == "mrb_gemm_splitk":                        # same contract + (workspace, bytes, max splits) before the stream
             return self._gemm(*args[:17], args[-1])
         if name == "mrb_skinny_wgrad_tc2":

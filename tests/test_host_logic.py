@@ -1020,6 +1020,9 @@ def test_ops_wrappers_pass_what_the_c_abi_declares(monkeypatch):
     ops.lora_down_drop(xe[:, :64], A, xe[:, 64:], 8, 64, 3, word, 5, 0.05)
     ops.lora_wgrad_drop(xe.data_ptr(), xe.stride(0), xe.data_ptr() + 128, xe.stride(0), 8, 64, torch.zeros((8, 64)), ops.BF16, word, 5, 0.05)
     ops.lora_dx_drop(xe[:, 64:], A, 3, x, 8, 64, word, 5, 0.05)
+    ops.dropout_add_norm(x, x, torch.empty_like(x), torch.zeros(64), 1e-6, xe, word, 5, 0.1)
+    ops.rmsnorm_bwd_drop(x, torch.zeros(64), xe, 1e-6, torch.zeros_like(x), torch.zeros_like(xe), word, 5, 0.1)
+    ops.stream_sm_limit(type("S", (), {"cuda_stream": 0})(), 132)
     monkeypatch.setattr(ops, "SPLITK", False)
     ops.gemm(xe, A, out=torch.zeros((8, 32)), M=8, K=64)
     monkeypatch.setattr(ops, "SPLITK", True)                 # the default: small-M / 32-column GEMMs take the split-K entry point
@@ -1029,7 +1032,7 @@ def test_ops_wrappers_pass_what_the_c_abi_declares(monkeypatch):
     assert {"mrb_attention_fwd", "mrb_attention_fwd_tc", "mrb_attention_fwd_drop", "mrb_attention_fwd_tc_drop", "mrb_attention_bwd",
             "mrb_attention_bwd_tc", "mrb_attention_bwd_drop", "mrb_attention_bwd_tc_drop", "mrb_dropout", "mrb_dropout_add",
             "mrb_gated_gelu_fwd_drop", "mrb_gated_gelu_bwd_drop", "mrb_lora_down_drop", "mrb_lora_wgrad_drop", "mrb_lora_dx_drop",
-            "mrb_gemm"} <= set(seen)
+            "mrb_gemm", "mrb_dropout_add_norm", "mrb_rmsnorm_bwd_drop", "mrb_stream_sm_limit"} <= set(seen)
 
 
 def test_ctypes_signatures_match_header_and_source_prototypes():
@@ -1374,6 +1377,38 @@ def test_elementwise_kernel_source_runs_on_host_shim(elementwise_kernels_on_host
     assert _relfro(a2[:, :588], want) < 1e-3 and a2[:, 588:].abs().max().item() == 0
 
 
+def test_fused_residual_kernels_equal_their_two_pass_forms(elementwise_kernels_on_host, dropout_kernels_on_host):
+    """mrb_dropout_add_norm == mrb_dropout_add then mrb_norm(mode 1), and mrb_rmsnorm_bwd_drop == mrb_rmsnorm_bwd then
+    mrb_dropout(fp32 -> 16 bit): the fused train-mode passes of the T5 residual stream (one launch instead of two on a chain of
+    ~1 500 dependent decoder kernels) do the same arithmetic in the same order -- compared bit for bit on the host shim, for
+    decoder-sized (one warp per row would be the old path) and a ragged encoder-like row count."""
+    elt, drp = elementwise_kernels_on_host, dropout_kernels_on_host
+    c_ll, c_f, c_u = ctypes.c_longlong, ctypes.c_float, ctypes.c_uint
+    P = lambda t: ctypes.c_void_p(t.data_ptr()) if t is not None else None
+    BF = 1
+    g = torch.Generator().manual_seed(5)
+    word = torch.tensor([0x1234567], dtype=torch.int32)
+    for rows, C, p in ((64, 2048, 0.1), (301, 2048, 0.1), (7, 1024, 0.05)):
+        x, br, w = torch.randn(rows, C, generator=g), torch.randn(rows, C, generator=g), torch.randn(C, generator=g)
+        site = 0x1046
+        out1, xn1 = torch.empty(rows, C), torch.zeros((rows, C + 32), dtype=torch.bfloat16)
+        assert drp.mrb_dropout_add(P(x), P(br), P(out1), rows, C, P(word), c_u(site), c_f(p), None) == 0
+        assert elt.mrb_norm(P(out1), None, P(w), None, c_f(1e-6), rows, C, 1, None, P(xn1), BF, c_ll(C + 32), None, None) == 0
+        out2, xn2 = torch.empty(rows, C), torch.zeros((rows, C + 32), dtype=torch.bfloat16)
+        assert elt.mrb_dropout_add_norm(P(x), P(br), P(w), c_f(1e-6), rows, C, P(xn2), BF, c_ll(C + 32), P(out2), P(word), c_u(site),
+                                        c_f(p), None) == 0
+        assert torch.equal(out1, out2) and torch.equal(xn1, xn2)
+        assert (out1 != x).any() and (out1 == x).float().mean().item() > p / 2            # some elements dropped, most kept
+        dy = torch.randn(rows, C + 32, generator=g).to(torch.bfloat16)
+        d1, n1 = torch.ones(rows, C), torch.zeros((rows, C + 32), dtype=torch.bfloat16)
+        assert elt.mrb_rmsnorm_bwd(P(x), P(w), P(dy), BF, c_ll(C + 32), None, 0, c_f(1e-6), rows, C, P(d1), None) == 0
+        assert drp.mrb_dropout(P(d1), c_ll(C), P(n1), c_ll(C + 32), rows, C, 2, BF, P(word), c_u(site + 3), c_f(p), None) == 0
+        d2, n2 = torch.ones(rows, C), torch.zeros((rows, C + 32), dtype=torch.bfloat16)
+        assert elt.mrb_rmsnorm_bwd_drop(P(x), P(w), P(dy), BF, c_ll(C + 32), c_f(1e-6), rows, C, P(d2), P(n2), BF, c_ll(C + 32), P(word),
+                                        c_u(site + 3), c_f(p), None) == 0
+        assert torch.equal(d1, d2) and torch.equal(n1, n2) and n2[:, C:].abs().max().item() == 0
+
+
 @pytest.mark.parametrize("train_dropout", [False] + ([True] if os.environ.get("MRB_TEST_SLOW", "0") == "1" else []))   # train mode: the whole-model test below
 def test_t5_engine_through_the_real_c_abi_on_host_kernels(monkeypatch, train_dropout, elementwise_kernels_on_host,
                                                           dropout_kernels_on_host, attention_kernels_on_host):
@@ -1426,8 +1461,9 @@ def test_t5_engine_through_the_real_c_abi_on_host_kernels(monkeypatch, train_dro
     want_calls = {"mrb_gemm_splitk", "mrb_norm", "mrb_rmsnorm_bwd", "mrb_attention_fwd", "mrb_attention_bwd", "mrb_cross_entropy", "mrb_gather_rows"}
     if train_dropout:
         want_calls = (want_calls - {"mrb_attention_fwd", "mrb_attention_bwd"}) | {
-            "mrb_attention_fwd_drop", "mrb_attention_bwd_drop", "mrb_dropout", "mrb_dropout_add", "mrb_gated_gelu_fwd_drop",
-            "mrb_gated_gelu_bwd_drop", "mrb_lora_down_drop", "mrb_lora_wgrad_drop", "mrb_lora_dx_drop"}
+            "mrb_attention_fwd_drop", "mrb_attention_bwd_drop", "mrb_dropout", "mrb_dropout_add_norm", "mrb_rmsnorm_bwd_drop",
+            "mrb_gated_gelu_fwd_drop", "mrb_gated_gelu_bwd_drop", "mrb_lora_down_drop", "mrb_lora_wgrad_drop", "mrb_lora_dx_drop"}
+        assert "mrb_dropout_add" not in abi.calls            # every residual add of a train-mode step is fused with the next norm
     assert want_calls <= set(abi.calls), sorted(set(abi.calls))
 
 
