@@ -241,7 +241,11 @@ class T5Engine:
         self._side_open = False
         # Train-mode fusions of the residual stream's elementwise passes (MRB_T5_FUSE_NORM=0 disables): dropout-add + the next
         # T5LayerNorm in one kernel, RMSNorm backward + the next sublayer's masked 16-bit gradient in one kernel.
+        # B200, each phase as its own graph (call 28, fused off -> on): encoder forward 28.66-28.74 -> 27.92-28.29 ms, encoder
+        # backward 52.49-52.95 -> 51.82-51.98 ms, but the decoder chain (64 rows) 17.83 -> 18.15-18.19 ms: encoder-sized inputs only
+        # (MRB_T5_FUSE_MIN_ROWS, default 512; 0 = every size).
         self.fuse_norm = os.environ.get("MRB_T5_FUSE_NORM", "1") != "0"
+        self.fuse_min_rows = int(os.environ.get("MRB_T5_FUSE_MIN_ROWS", "512"))
         self._pre_norm = None                             # (residual stream, ln weight, normalised operand) of the fused add
         self._pre_grad = None                             # (gradient stream, site, masked 16-bit operand) of the fused backward
 
@@ -390,7 +394,7 @@ class T5Engine:
         out = torch.empty_like(h)
         if self._p() > 0.0:
             br = grp.forward(x_ext, M, out_dtype=torch.float32)
-            if next_ln is not None and self.fuse_norm:
+            if next_ln is not None and self.fuse_norm and M >= self.fuse_min_rows:
                 xn = self._ext(M, self.d.d_model)
                 ops.dropout_add_norm(h, br, out, next_ln, self.d.t5_ln_eps, xn, self.drop.word, site, self._p())
                 self._pre_norm = (out, next_ln, xn)
@@ -411,7 +415,7 @@ class T5Engine:
     def _rmsnorm_bwd(self, x, ln, dy, dh, M, next_site=None):
         """dh += T5LayerNorm'(x; ln) . dy; with `next_site` (the residual-dropout site of the sublayer whose backward runs next)
         the same pass writes that sublayer's masked 16-bit dgrad operand (picked up by _grad_ext)."""
-        if next_site is not None and self._p() > 0.0 and self.fuse_norm:
+        if next_site is not None and self._p() > 0.0 and self.fuse_norm and M >= self.fuse_min_rows:
             dyn = self._ext(M, self.d.d_model)
             ops.rmsnorm_bwd_drop(x, ln, dy, self.d.t5_ln_eps, dh, dyn, self.drop.word, next_site, self._p())
             self._pre_grad = (dh, next_site, dyn)
