@@ -43,12 +43,12 @@ int mrb_gemm_splitk(const void* A, long long lda, const void* B, long long ldb, 
  * the unsplit path.  Host arithmetic only (no device work): workspace sizing and tests. */
 int mrb_gemm_splitk_plan(int M, int N, int K, int sms, int force_bn, int max_splits, int* bn, int* splits, int* kb_per_split);
 
-/* Cap the SMs the persistent GEMM kernels of mrb_gemm / mrb_gemm_splitk occupy when launched on `stream` (sms even; 0 lifts the
- * cap).  For GEMMs a caller issues on a side stream NEXT TO a chain of small dependent kernels: a CTA of the 2-CTA kernel holds
- * its SM's whole shared memory, so an uncapped side GEMM stalls the chain for its length.  Used for the 48 encoder-sized
+/* Cap the SMs the persistent 2-CTA kernel of mrb_gemm occupies for the launches the calling thread issues from now on (sms even;
+ * 0 lifts the cap).  For GEMMs a caller issues on a side stream NEXT TO a chain of small dependent kernels: a CTA of that kernel
+ * holds its SM's whole shared memory, so an uncapped side GEMM stalls the chain for its length.  Used around the 48 encoder-sized
  * cross-attention K/V GEMMs (projection and dgrad) of the T5 decoder, which torch's autograd runs serially with the decoder's
  * M = B x L_dec kernels (modeling_t5.py:542-558 key_value_states branch).  No reference counterpart: scheduling only. */
-int mrb_stream_sm_limit(void* stream, int sms);
+int mrb_gemm_sm_limit(int sms);
 
 /* softmax(scale * Q K^T + bias[h, j - i] + mask) V, scores never written to HBM; optional log-sum-exp for backward.
  * kv_div > 1: query batch b reads K/V/mask batch b / kv_div (beams sharing one encoder output).

@@ -12,7 +12,7 @@ _p, _ll, _i, _f, _u = ctypes.c_void_p, ctypes.c_longlong, ctypes.c_int, ctypes.c
 SIGNATURES = {
     "mrb_gemm": [_p, _ll, _p, _ll, _i, _i, _i, _i, _p, _i, _p, _ll, _p, _i, _ll, _i, _i, _p],
     "mrb_gemm_splitk_plan": [_i, _i, _i, _i, _i, _i, _p, _p, _p],
-    "mrb_stream_sm_limit": [_p, _i],
+    "mrb_gemm_sm_limit": [_i],
     "mrb_gemm_splitk": [_p, _ll, _p, _ll, _i, _i, _i, _i, _p, _i, _p, _ll, _p, _i, _ll, _i, _i, _p, _ll, _i, _p],
     "mrb_attention_fwd": [_p, _ll, _ll, _p, _ll, _ll, _p, _ll, _ll, _p, _ll, _ll, _i, _i, _i, _i, _i, _i, _f, _p, _i, _i,
                           _p, _i, _i, _i, _p, _p],

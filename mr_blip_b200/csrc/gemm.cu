@@ -522,31 +522,17 @@ static int* splitk_counters_for(const void* ws, int tiles) {
   return nullptr;
 }
 
-// Per-stream SM cap of the persistent GEMM kernels (mrb_stream_sm_limit).  A CTA of the 2-CTA kernel owns the whole shared
-// memory of its SM for the length of the launch, so a GEMM on a SIDE stream that takes all SMs stalls the dependent chain of
-// small kernels on the main stream for that long (the T5 decoder: 48 encoder-sized cross-attention K/V GEMMs next to ~1 500
-// decoder-sized kernels); capped, it leaves SMs to the chain and the two really overlap.
-static std::mutex g_sm_limit_mu;
-static const void* g_sm_limit_stream[8] = {};
-static int g_sm_limit_value[8] = {};
-static int sms_for_stream(const void* stream) {
-  std::lock_guard<std::mutex> lock(g_sm_limit_mu);
-  for (int i = 0; i < 8; ++i)
-    if (g_sm_limit_value[i] > 0 && g_sm_limit_stream[i] == stream) return g_sm_limit_value[i] < g_num_sms ? g_sm_limit_value[i] : g_num_sms;
-  return g_num_sms;
-}
+// SM cap of the persistent 2-CTA GEMM kernel for the launches the CALLING THREAD issues next (mrb_gemm_sm_limit).  A CTA of that
+// kernel owns the whole shared memory of its SM for the length of the launch, so a GEMM on a SIDE stream that takes all SMs stalls
+// the dependent chain of small kernels on the main stream for that long (the T5 decoder: 48 encoder-sized cross-attention K/V
+// GEMMs next to ~1 500 decoder-sized kernels); capped, it leaves SMs to the chain and the two really overlap.  Per thread and per
+// call site, not per stream: stream handles are pooled and reused, a table keyed by them would outlive its owner.
+static thread_local int t_sm_limit = 0;
+static int sms_for_launch() { return (t_sm_limit > 0 && t_sm_limit < g_num_sms) ? t_sm_limit : g_num_sms; }
 
-extern "C" int mrb_stream_sm_limit(void* stream, int sms) {
+extern "C" int mrb_gemm_sm_limit(int sms) {
   if (sms < 0 || (sms & 1)) return MRB_ERR_ARG;
-  std::lock_guard<std::mutex> lock(g_sm_limit_mu);
-  int free_slot = -1;
-  for (int i = 0; i < 8; ++i) {
-    if (g_sm_limit_value[i] > 0 && g_sm_limit_stream[i] == stream) { g_sm_limit_value[i] = sms; return MRB_OK; }
-    if (g_sm_limit_value[i] == 0 && free_slot < 0) free_slot = i;
-  }
-  if (sms == 0) return MRB_OK;
-  if (free_slot < 0) return MRB_ERR_UNSUPPORTED;
-  g_sm_limit_stream[free_slot] = stream; g_sm_limit_value[free_slot] = sms;
+  t_sm_limit = sms;
   return MRB_OK;
 }
 
@@ -577,7 +563,7 @@ static int gemm_impl(const void* A, long long lda, const void* B, long long ldb,
     rc2 = make_tmap(&tmB2, B, dtype, N, K, ldb, 128);
     if (rc2) return rc2;
     return mrb_gemm2_launch(&tmA2, &tmB2, M, N, K, dtype, bias, gelu, resid, ldr, out, out_dtype, ldc, row_group,
-                            sms_for_stream(stream), stream);
+                            sms_for_launch(), stream);
   }
   int bn = force_bn ? force_bn : pick_bn(M, N, g_num_sms);
   SplitPlan plan = {bn, 1, 0};

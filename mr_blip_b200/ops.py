@@ -59,9 +59,9 @@ class phase:
         return False
 
 
-def stream_sm_limit(stream, sms):
-    """GEMMs launched on `stream` occupy at most `sms` SMs (even; 0 = no cap): csrc/gemm.cu mrb_stream_sm_limit."""
-    _lib.call("mrb_stream_sm_limit", stream.cuda_stream, int(sms))
+def gemm_sm_limit(sms):
+    """The large GEMMs this thread launches from now on occupy at most `sms` SMs (even; 0 = no cap): csrc/gemm.cu mrb_gemm_sm_limit."""
+    _lib.call("mrb_gemm_sm_limit", int(sms))
 
 
 def _stream():

@@ -234,9 +234,7 @@ class T5Engine:
         # SM cap of the side stream's GEMMs (the decoder's 48 encoder-sized cross K/V GEMMs): uncapped, each holds every SM's
         # shared memory for ~100 us and the main chain's small kernels wait behind it.  Decoder chain in-graph on a B200 (call 27):
         # 18.36 ms uncapped, 17.73 at 132 SMs, 17.88 / 17.74 / 18.12 at 116 / 100 / 84.  MRB_SIDE_SMS=0 lifts the cap.
-        self.side_sms = int(os.environ.get("MRB_SIDE_SMS", "132"))
-        if self.overlap and self.side_sms > 0:
-            ops.stream_sm_limit(self.side, self.side_sms)
+        self.side_sms = int(os.environ.get("MRB_SIDE_SMS", "132"))      # applied by side_block() around its launches
         self._hold = []
         self._side_open = False
         # Train-mode fusions of the residual stream's elementwise passes (MRB_T5_FUSE_NORM=0 disables): dropout-add + the next
@@ -300,8 +298,12 @@ class T5Engine:
                 eng._side_open = True
                 self.cm = torch.cuda.stream(eng.side)
                 self.cm.__enter__()
+                if eng.side_sms > 0:
+                    ops.gemm_sm_limit(eng.side_sms)          # this thread's large GEMMs leave SMs to the main chain
 
             def __exit__(self, *a):
+                if eng.side_sms > 0:
+                    ops.gemm_sm_limit(0)
                 return self.cm.__exit__(*a)
 
         return _Ctx()

@@ -30,7 +30,7 @@ def splitk_register(side_stream=None):
     pass
 
 
-def stream_sm_limit(stream, sms):
+def gemm_sm_limit(sms):
     pass
 
 
@@ -423,7 +423,7 @@ class HostCAbi:
             (q, q_bs, q_rs, k, k_bs, k_rs, v, v_bs, v_rs, o, o_bs, o_rs, frames, H, L, hd, dt, scale, st) = args
             return self.call("mrb_attention_fwd", q, q_bs, q_rs, k, k_bs, k_rs, v, v_bs, v_rs, o, o_bs, o_rs, frames, H, L, L, hd, dt,
                              scale, None, 0, 0, None, 1, 0, 0, None, st)
-        if name == "mrb_stream_sm_limit":                    # scheduling only
+        if name == "mrb_gemm_sm_limit":                      # scheduling only
             return None
         if name == "mrb_gemm_splitk":                        # same contract + (workspace, bytes, max splits) before the stream
             return self._gemm(*args[:17], args[-1])

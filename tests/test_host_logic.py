@@ -1023,7 +1023,7 @@ def test_ops_wrappers_pass_what_the_c_abi_declares(monkeypatch):
     ops.lora_dx_drop(xe[:, 64:], A, 3, x, 8, 64, word, 5, 0.05)
     ops.dropout_add_norm(x, x, torch.empty_like(x), torch.zeros(64), 1e-6, xe, word, 5, 0.1)
     ops.rmsnorm_bwd_drop(x, torch.zeros(64), xe, 1e-6, torch.zeros_like(x), torch.zeros_like(xe), word, 5, 0.1)
-    ops.stream_sm_limit(type("S", (), {"cuda_stream": 0})(), 132)
+    ops.gemm_sm_limit(132)
     monkeypatch.setattr(ops, "SPLITK", False)
     ops.gemm(xe, A, out=torch.zeros((8, 32)), M=8, K=64)
     monkeypatch.setattr(ops, "SPLITK", True)                 # the default: small-M / 32-column GEMMs take the split-K entry point
@@ -1033,7 +1033,7 @@ def test_ops_wrappers_pass_what_the_c_abi_declares(monkeypatch):
     assert {"mrb_attention_fwd", "mrb_attention_fwd_tc", "mrb_attention_fwd_drop", "mrb_attention_fwd_tc_drop", "mrb_attention_bwd",
             "mrb_attention_bwd_tc", "mrb_attention_bwd_drop", "mrb_attention_bwd_tc_drop", "mrb_dropout", "mrb_dropout_add",
             "mrb_gated_gelu_fwd_drop", "mrb_gated_gelu_bwd_drop", "mrb_lora_down_drop", "mrb_lora_wgrad_drop", "mrb_lora_dx_drop",
-            "mrb_gemm", "mrb_dropout_add_norm", "mrb_rmsnorm_bwd_drop", "mrb_stream_sm_limit"} <= set(seen)
+            "mrb_gemm", "mrb_dropout_add_norm", "mrb_rmsnorm_bwd_drop", "mrb_gemm_sm_limit"} <= set(seen)
 
 
 def test_ctypes_signatures_match_header_and_source_prototypes():
