@@ -403,6 +403,24 @@ def run_b200(args, cfg_name, cfg):
         t = torch.tensor([sorted(ts)[1]], device=dev)
         tdist.all_reduce(t, op=tdist.ReduceOp.MAX)
         ar_ms = t.item()
+        # every rank's OWN step time: the same steps with the exchange left out, so no rank waits for another; the spread over
+        # the ranks (not the all-reduce) is what separates the N-GPU step from the 1-GPU step -- the job runs at the slowest replica
+        samples["video"] = video_dev
+        n_local = min(args.steps, 5)
+        torch.cuda.synchronize()
+        tdist.barrier()
+        r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        r0.record()
+        for _ in range(n_local):
+            model(samples)["loss"].backward()
+            opt.step()
+            opt.zero_grad(set_to_none=True)
+        r1.record()
+        torch.cuda.synchronize()
+        mine = torch.tensor([r0.elapsed_time(r1) / n_local], device=dev)
+        every = [torch.zeros_like(mine) for _ in range(world)]
+        tdist.all_gather(every, mine)
+        replica_ms = [round(x.item(), 2) for x in every]
     clips = B * world * args.steps
     value = clips / (ms / 1e3)
     e2e = clips / (ms_e2e / 1e3)
@@ -428,6 +446,9 @@ def run_b200(args, cfg_name, cfg):
         line["loss"] = float(last)
         line["config"].update(L_enc=host["Le"], L_dec=host["Ld"])
     if ar_ms is not None:
+        line["replicas_without_exchange"] = {"ms_per_step": replica_ms, "steps": n_local,
+                                             "what": "each rank's own step time (same step, all-reduce left out, nobody waits): "
+                                                     "the N-GPU step runs at the slowest of these"}
         line["grad_allreduce"] = {"ms": ar_ms, "bytes": int(sum(p.numel() for p in trainable) * 4), "share_of_step": ar_ms / (ms / args.steps),
                                   "what": "one in-place NCCL all-reduce (AVG) of the flat fp32 gradient buffer after backward, timed alone "
                                           "(barrier first), median of 3, max over ranks"}
