@@ -34,6 +34,9 @@ def test_cabi_library_exports_every_declared_symbol():
     assert lib.mrb_abi_version() == 1
     # the python binding covers every compute entry point of the header
     assert declared - {"mrb_abi_version", "mrb_last_error"} == set(_lib.SIGNATURES)
+    # host-only entry points answer without a device: the per-thread SM cap of the large GEMMs takes even counts, 0 lifts it
+    assert lib.mrb_gemm_sm_limit(132) == 0 and lib.mrb_gemm_sm_limit(0) == 0
+    assert lib.mrb_gemm_sm_limit(131) != 0 and lib.mrb_gemm_sm_limit(-2) != 0
 
 
 def test_model_surface_and_state_dict_names(tiny_sd):

@@ -283,6 +283,31 @@ def test_rmsnorm_bwd(ops):
     _close(acc, dy_eff + 1.0, 1e-5, 1e-5, "lora_up_add acc")
 
 
+@pytest.mark.parametrize("rows", [64, 8192, 517])
+def test_fused_residual_kernels_equal_their_two_pass_forms(ops, rows):
+    """mrb_dropout_add_norm == mrb_dropout_add then mrb_norm(mode 1), mrb_rmsnorm_bwd_drop == mrb_rmsnorm_bwd then mrb_dropout
+    (fp32 -> bf16): bit for bit on the device, decoder- and encoder-sized (the train step fuses them from 512 rows)."""
+    C, p, site = 2048, 0.1, 0x1046
+    word = torch.tensor([0x1234567], dtype=torch.int32, device="cuda")
+    x, br = _rand((rows, C), torch.float32, 1.5, 51), _rand((rows, C), torch.float32, 1.0, 52)
+    w = _rand((C,), torch.float32, 0.2, 53) + 1.0
+    out1, xn1 = torch.empty_like(x), torch.zeros((rows, C + 32), dtype=torch.bfloat16, device="cuda")
+    ops.dropout_add(x, br, out1, word, site, p)
+    ops.norm(out1, w, None, 1e-6, 1, out_h=xn1)
+    out2, xn2 = torch.empty_like(x), torch.zeros((rows, C + 32), dtype=torch.bfloat16, device="cuda")
+    ops.dropout_add_norm(x, br, out2, w, 1e-6, xn2, word, site, p)
+    assert torch.equal(out1, out2) and torch.equal(xn1, xn2)
+    kept = (out1 != x).float().mean().item()
+    assert abs(kept - (1.0 - 26.0 / 256.0)) < 0.01                       # 0.1 quantised to 26 / 256 of the branch elements dropped
+    dy = _rand((rows, C + 32), torch.bfloat16, 1.0, 54)
+    d1, n1 = _rand((rows, C), torch.float32, 1.0, 55), torch.zeros((rows, C + 32), dtype=torch.bfloat16, device="cuda")
+    d2, n2 = d1.clone(), torch.zeros_like(n1)
+    ops.rmsnorm_bwd(x, w, dy, 1e-6, d1)
+    ops.dropout(d1, n1, rows, C, word, site + 3, p)
+    ops.rmsnorm_bwd_drop(x, w, dy, 1e-6, d2, n2, word, site + 3, p)
+    assert torch.equal(d1, d2) and torch.equal(n1, n2) and n2[:, C:].abs().max().item() == 0
+
+
 # ------------------------------------------------------------------------------------------- small kernels
 def test_patchify_matches_conv_unfold(ops):
     F, S, P = 3, 224, 14
