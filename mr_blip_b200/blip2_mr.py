@@ -48,11 +48,13 @@ class _GraphedStep:
     """Static input buffers + the captured CUDA graph of the device half of one training step, for one shape signature
     (clips, frames, encoder length, decoder length).  All small integer inputs travel in ONE pinned int32 buffer."""
 
-    def __init__(self, b, t, Le, Ld, img_size, video_dtype=torch.float32):
+    def __init__(self, b, t, Le, Ld, img_size, video_dtype=torch.float32, front=None):
         n = 2 * b * Le + 3 * b * Ld
         self.host = torch.empty(n, dtype=torch.int32).pin_memory()
         self.dev = torch.empty(n, dtype=torch.int32, device="cuda")
-        self.video = torch.empty((b, t, 3, img_size, img_size), dtype=video_dtype, device="cuda")
+        self.front = front                                   # _GraphedFront: the text-independent front runs as its own graph
+        self.video = front.video if front is not None else \
+            torch.empty((b, t, 3, img_size, img_size), dtype=video_dtype, device="cuda")
         self.loss = torch.zeros((1,), dtype=torch.float32, device="cuda")
         self.h, self.d = {}, {}
         off = 0
@@ -74,7 +76,22 @@ class _GraphedStep:
         self.dev.copy_(self.host, non_blocking=True)
         self.staged = torch.cuda.Event()
         self.staged.record()
-        self.video.copy_(video.reshape(self.video.shape), non_blocking=True)
+        if video is not None:                                # None: the front graph's own buffer already holds the frames
+            self.video.copy_(video.reshape(self.video.shape), non_blocking=True)
+
+
+class _GraphedFront:
+    """The part of a training step that does not depend on the text -- t5_proj re-cast, ViT, ln_vision, Q-Former, t5_proj
+    (-> mean) -- as its OWN captured graph with its own static frame buffer, for one (clips, frames) signature.  It is launched
+    as soon as the frames are on their way to the device, BEFORE the host builds the prompt table (tokeniser, interleave rows:
+    ~3 ms of Python), so that work runs under the ViT instead of in front of the step -- which is where it sits whenever the
+    caller reads the loss every iteration, as the reference's loop does (base_task.py:_train_inner_loop, loss.item())."""
+
+    def __init__(self, b, t, img_size, video_dtype=torch.float32):
+        self.video = torch.empty((b, t, 3, img_size, img_size), dtype=video_dtype, device="cuda")
+        self.out = None                                      # (frames_for_t5, Q-Former hidden fp32, fp16): static once captured
+        self.graph = None
+        self.n_launch = 0
 
 
 class Blip2Base(BaseModel):
@@ -185,6 +202,10 @@ class BLIP2_MR(Blip2Base):
         self._seen = {}                                      # shape signature -> times seen (survives LRU eviction)
         self._graph_pool = None
         self._in_device_step = False
+        self._defer_refresh = False                          # the captured step re-packs LoRA / t5_proj itself
+        # MRB_SPLIT_GRAPH=1: front (ViT .. t5_proj) and back (T5) of the step as two graphs, the host's prompt assembly in between
+        self.split_graph = os.environ.get("MRB_SPLIT_GRAPH", "0") == "1"
+        self._fronts = {}
         # Train-mode dropout (the reference's train() step: Q-Former / T5 0.1, LoRA inputs 0.05; mr_blip_b200/dropout.py): ON by
         # default, as in the reference, where module.train() switches every nn.Dropout on.  train_dropout=False (or
         # MRB_TRAIN_DROPOUT=0) makes train() steps run the eval() arithmetic -- rate 0 -- which is what the parity tests of the
@@ -247,7 +268,7 @@ class BLIP2_MR(Blip2Base):
     def reset_graphs(self):
         """Drop every captured step graph (and the private memory pool they share: a pool handle is only valid while
         one of its graphs is alive)."""
-        self._steps, self._seen, self._graph_pool = {}, {}, None
+        self._steps, self._seen, self._graph_pool, self._fronts = {}, {}, None, {}
 
     def _weights_changed(self):
         self._engines = None
@@ -293,7 +314,7 @@ class BLIP2_MR(Blip2Base):
             import torch.distributed as tdist
             rank = tdist.get_rank() if (tdist.is_available() and tdist.is_initialized()) else 0
             self.drop_state = DropState(base_seed=self.dropout_seed + rank)      # per-rank masks (reference: train.py:57-58, seed + get_rank())
-        if self._in_device_step:                             # (captured) device step: LoRA re-pack is part of the step itself
+        if self._in_device_step or self._defer_refresh:      # (captured) device step: LoRA re-pack is part of the step itself
             return vit, qf, t5
         tr = self._answerer if self._answerer is not None else t5
         vers = tuple(p._version for g in tr.groups for p in g.A_params + g.B_params)
@@ -587,13 +608,16 @@ class BLIP2_MR(Blip2Base):
                     b=b, t=t, Le=table.shape[1], Ld=labels.shape[1])
 
     # ---- device half of a step (no host synchronisation: capturable) ------------------------------
-    def _device_phase(self, video, idx, kmask, labels, dec_ids, dmask, need_grad, want_logits=False, loss_out=None):
+    def _device_phase(self, video, idx, kmask, labels, dec_ids, dmask, need_grad, want_logits=False, loss_out=None, front=None):
         """ViT -> ln_vision -> Q-Former -> t5_proj -> interleave gather -> T5 loss (-> backward into the flat gradient
         buffer).  idx int32 [B*Le], kmask/dmask int32, labels/dec_ids int64 -- all on the GPU."""
         vit, qf, t5 = self.engines()
         d = self.dims
         b, t = video.shape[:2]
-        frames, _, (qh, qh16) = self.get_frame_embeddings_and_attentions(video, want_aux=True)
+        if front is not None:
+            frames, qh, qh16 = front
+        else:
+            frames, _, (qh, qh16) = self.get_frame_embeddings_and_attentions(video, want_aux=True)
         B, TN, C = frames.shape
         Le = idx.numel() // B
         inputs = torch.empty((B * Le, C), dtype=torch.float32, device="cuda")
@@ -625,29 +649,75 @@ class BLIP2_MR(Blip2Base):
         try:
             _, qf, t5 = self._engines
             t5.refresh()
-            qf.set_t5_proj(self.t5_proj.weight, self.t5_proj.bias)
+            if st.front is None:
+                qf.set_t5_proj(self.t5_proj.weight, self.t5_proj.bias)
             x = st.d
             self._device_phase(st.video, x["idx"], x["kmask"], x["labels"].to(torch.int64), x["dec_ids"].to(torch.int64),
-                               x["dmask"], need_grad=True, loss_out=st.loss)
+                               x["dmask"], need_grad=True, loss_out=st.loss, front=st.front.out if st.front is not None else None)
         finally:
             self._in_device_step = False
 
+    def _front_step(self, fr):
+        """What the front graph holds: t5_proj re-cast (the optimiser changed it) + ViT -> ln_vision -> Q-Former -> t5_proj."""
+        self.engines()
+        self._in_device_step = True
+        try:
+            _, qf, _ = self._engines
+            qf.set_t5_proj(self.t5_proj.weight, self.t5_proj.bias)
+            frames, _, (qh, qh16) = self.get_frame_embeddings_and_attentions(fr.video, want_aux=True)
+            fr.out = (frames, qh, qh16)
+        finally:
+            self._in_device_step = False
+
+    def _run_front(self, video, vdt):
+        """Copy the frames into the front graph's buffer and launch it (eager on first sight, captured on the second)."""
+        b, t = video.shape[:2]
+        fkey = (b, t, bool(self.frame_token_aggregation), vdt, self._engines[1].drop is not None)
+        fr = self._fronts.get(fkey)
+        if fr is None:
+            fr = self._fronts[fkey] = _GraphedFront(b, t, self.dims.img_size, vdt)
+        fr.video.copy_(video.reshape(fr.video.shape), non_blocking=True)
+        seen = self._seen[("front",) + fkey] = self._seen.get(("front",) + fkey, 0) + 1
+        if fr.graph is not None:
+            fr.graph.replay()
+            _lib.launch_count += fr.n_launch
+        elif seen < 2:
+            self._front_step(fr)
+        else:
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            l0 = _lib.launch_count
+            with torch.cuda.graph(g, pool=self._graph_pool, capture_error_mode="thread_local"):
+                self._front_step(fr)
+            fr.n_launch = _lib.launch_count - l0
+            if self._graph_pool is None:
+                self._graph_pool = g.pool()
+            fr.graph = g
+            g.replay()
+        return fr
+
     def _graphed_step(self, samples):
-        host = self._host_phase(samples, bucket=self.graph_bucket)
         video = self._video_of(samples)
         vdt = torch.uint8 if video.dtype == torch.uint8 else torch.float32
+        front = None
+        if self.split_graph:
+            self.engines()
+            front = self._run_front(video, vdt)              # the GPU starts on the ViT; the prompt table is built under it
+        host = self._host_phase(samples, bucket=self.graph_bucket)
         key = (host["b"], host["t"], host["Le"], host["Ld"], bool(self.frame_token_aggregation), vdt,
-               self._engines[2].drop is not None)
+               self._engines[2].drop is not None if self._engines is not None else None, front is not None)
         st = self._steps.pop(key, None)
+        if st is not None and st.front is not front:         # captured against another front's output buffers
+            st = None
         if st is None:
             while len(self._steps) >= self.max_graphs:       # least recently used shape goes first
                 self._steps.pop(next(iter(self._steps)))
-            if not any(x.graph is not None for x in self._steps.values()):
+            if not any(x.graph is not None for x in self._steps.values()) and not any(f.graph is not None for f in self._fronts.values()):
                 self._graph_pool = None                      # no live graph holds the old pool any more
-            st = _GraphedStep(host["b"], host["t"], host["Le"], host["Ld"], self.dims.img_size, vdt)
+            st = _GraphedStep(host["b"], host["t"], host["Le"], host["Ld"], self.dims.img_size, vdt, front=front)
         self._steps[key] = st
         self.engines()
-        st.stage(host, video)
+        st.stage(host, None if front is not None else video)
         seen = self._seen[key] = self._seen.get(key, 0) + 1
         if st.graph is not None:
             st.graph.replay()
@@ -683,12 +753,17 @@ class BLIP2_MR(Blip2Base):
 
     def forward_mr(self, samples, want_logits=False):
         """blip2_mr.py:433-570."""
-        self.engines()
-        self._set_dropout(self.training)                     # nn.Dropout follows module.training, with or without grad
         need_grad = self.training and torch.is_grad_enabled()
-        if need_grad and self.cuda_graphs and not want_logits:
-            loss = self._graphed_step(samples).reshape(())
-            return {"loss": _HandOverGrads.apply(loss, self, *self._grad_params)}
+        graphed = need_grad and self.cuda_graphs and not want_logits
+        self._defer_refresh = graphed and self._engines is not None      # the (captured) step re-packs LoRA / t5_proj itself:
+        try:                                                              # no second, eager re-pack in front of it
+            self.engines()
+            self._set_dropout(self.training)                 # nn.Dropout follows module.training, with or without grad
+            if graphed:
+                loss = self._graphed_step(samples).reshape(())
+                return {"loss": _HandOverGrads.apply(loss, self, *self._grad_params)}
+        finally:
+            self._defer_refresh = False
         host = self._host_phase(samples)
         dev = {k: torch.from_numpy(host[k]).to("cuda", non_blocking=True) for k in ("idx", "kmask", "labels", "dec_ids", "dmask")}
         video = self._video_of(samples)
